@@ -1,0 +1,11 @@
+"""iak3d_b200 -- B200 (sm_100a) implementation of iak3d's data-parallel hot path behind the reference's interface.
+
+The compute lives in lib/libiak3d.so (CUDA, C ABI: include/iak3d.h); this package is the host-side mirror of the
+reference's R functions for that path.  Importing the package does not load the library; the first call does, and
+fails loudly when the library or an sm_100-class GPU is missing (there is no CPU path).
+"""
+from ._lib import EXPORTS, LIB_PATH, Context, Iak3dError, default_context, load  # noqa: F401
+from .api import (BADNLL, KeptFit, SetupMats, SetupMats2, gradnllIAK3D, iaCovMatern2, lndetANDinvCb, logitab,  # noqa: F401
+                  nll_terms_batch, nllIAK3D, nllIAK3D_CL, predictIAK3D, readParsIAK3D, reml_tail, setCIAK3D, setCIAK3D2,
+                  setupIAK3D, setupIAK3D2, setupIAK3D_CL, spatialCovIAK3D, tauTfm)
+from . import parallel, synth  # noqa: F401

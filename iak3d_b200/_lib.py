@@ -1,0 +1,200 @@
+"""ctypes binding of libiak3d.so (include/iak3d.h).  No fallback: a missing library or a failing call raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libiak3d.so")
+
+OK, NOT_SPD, BAD_PARS = 0, 1, 2
+ERR_CUDA, ERR_ARG, ERR_TIMEOUT = -1, -2, -3
+MODELX = {"nugget": 0, "spherical": 1, "matern": 2, "wendland": 3}
+
+
+class Iak3dError(RuntimeError):
+    pass
+
+
+class Pars(C.Structure):
+    """struct iak3d_pars (include/iak3d.h)."""
+    _fields_ = [
+        ("modelx", C.c_int32), ("cmeOpt", C.c_int32), ("sdfdType", C.c_int32 * 3), ("quirk_cd1_unscaled", C.c_int32),
+        ("ax", C.c_double), ("nux", C.c_double), ("ad", C.c_double), ("nud", C.c_double),
+        ("cx0", C.c_double), ("cx1", C.c_double), ("cd1", C.c_double), ("cxd0", C.c_double), ("cxd1", C.c_double),
+        ("cme", C.c_double), ("sdfdPars", (C.c_double * 2) * 3),
+    ]
+
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_vp = C.c_void_p
+_i64 = C.c_int64
+_i32 = C.c_int32
+
+_PROTOS = {
+    "iak3d_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "iak3d_ctx_destroy": (C.c_int, [_vp]),
+    "iak3d_last_error": (C.c_char_p, [_vp]),
+    "iak3d_device_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(_i64)]),
+    "iak3d_launch_count": (_i64, [_vp]),
+    "iak3d_dataset_create": (C.c_int, [_vp, _i64, _dp, _dp, _dp, _i32, C.POINTER(_vp)]),
+    "iak3d_dataset_destroy": (C.c_int, [_vp]),
+    "iak3d_dataset_set_W": (C.c_int, [_vp, _dp, _i32]),
+    "iak3d_dataset_info": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i32)]),
+    "iak3d_dataset_ids": (C.c_int, [_vp, _ip, _ip]),
+    "iak3d_iacov": (C.c_int, [_vp, _i64, _dp, _i64, _dp, C.c_double, C.c_double, _i32, _dp, _dp, _dp]),
+    "iak3d_spatial_cov": (C.c_int, [_vp, _i64, _dp, _i32, C.c_double, C.c_double, C.c_double, _dp]),
+    "iak3d_cov_build": (C.c_int, [_vp, C.POINTER(Pars), _dp, _dp]),
+    "iak3d_cov_cross": (C.c_int, [_vp, C.POINTER(Pars), _i64, _dp, _dp, _dp]),
+    "iak3d_lndet_invCb": (C.c_int, [_vp, _i64, _dp, _i32, _dp, _dp, _dp]),
+    "iak3d_nll_terms": (C.c_int, [_vp, C.POINTER(Pars), _dp, _dp, _dp]),
+    "iak3d_nll_terms_batch": (C.c_int, [_vp, _i32, C.POINTER(_vp), C.POINTER(Pars), _dp, _dp, _ip]),
+    "iak3d_nll_terms_batch_enqueue": (C.c_int, [_vp, _i32, C.POINTER(_vp), C.POINTER(Pars)]),
+    "iak3d_nll_terms_batch_fetch": (C.c_int, [_vp, _dp, _dp, _ip]),
+    "iak3d_fit_create": (C.c_int, [_vp, C.POINTER(Pars), _dp, _dp, C.POINTER(_vp)]),
+    "iak3d_fit_destroy": (C.c_int, [_vp]),
+    "iak3d_fit_get": (C.c_int, [_vp, _dp, _dp, _dp, _dp]),
+    "iak3d_predict": (C.c_int, [_vp, _i64, _dp, _dp, _dp, _dp, _dp]),
+    "iak3d_predict_stage": (C.c_int, [_vp, _i64, _dp, _dp, _dp]),
+    "iak3d_predict_enqueue": (C.c_int, [_vp]),
+    "iak3d_predict_fetch": (C.c_int, [_vp, _dp, _dp]),
+    "iak3d_gradhess": (C.c_int, [_vp, C.POINTER(Pars), _i32, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "iak3d_sync": (C.c_int, [_vp]),
+    "iak3d_timer_start": (C.c_int, [_vp]),
+    "iak3d_timer_stop": (C.c_int, [_vp, _dp]),
+    "iak3d_flush_l2": (C.c_int, [_vp]),
+    "iak3d_fp64_peak": (C.c_int, [_vp, _i32, _dp]),
+    "iak3d_last_stage_ms": (C.c_int, [_vp, _dp, _dp, _dp]),
+}
+EXPORTS = tuple(sorted(_PROTOS))
+
+_lib = None
+
+
+def load():
+    """Load libiak3d.so and set the prototypes.  Raises if the library is missing (no CPU path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Iak3dError(f"{LIB_PATH} is missing: run `make` (or __graft_entry__.build()); there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _PROTOS.items():
+        fn = getattr(lib, name)           # AttributeError if the ABI lost a symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def dptr(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def iptr(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+def f64(a, order="F"):
+    """Column-major (R native) float64 copy/view."""
+    return np.require(np.asarray(a, dtype=np.float64), dtype=np.float64, requirements=["F" if order == "F" else "C", "A"])
+
+
+def make_pars(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, quirk_cd1_unscaled=True):
+    """parsBTfmd (the list readParsIAK3D returns, fitIAK3D.R:1405-1408) -> struct iak3d_pars."""
+    P = Pars()
+    P.modelx = MODELX[modelx]
+    P.cmeOpt = int(cmeOpt)
+    types = (int(sdfdType_cd1), int(sdfdType_cxd0), int(sdfdType_cxd1))
+    for i, t in enumerate(types):
+        P.sdfdType[i] = t
+    P.quirk_cd1_unscaled = 1 if quirk_cd1_unscaled else 0
+    g = lambda k: float(np.asarray(parsBTfmd[k]).reshape(-1)[0]) if np.size(parsBTfmd[k]) else float("nan")
+    P.ax, P.nux, P.ad, P.nud = g("ax"), g("nux"), g("ad"), g("nud")
+    P.cx0, P.cx1, P.cd1, P.cxd0, P.cxd1, P.cme = g("cx0"), g("cx1"), g("cd1"), g("cxd0"), g("cxd1"), g("cme")
+    for i, k in enumerate(("sdfdPars_cd1", "sdfdPars_cxd0", "sdfdPars_cxd1")):
+        v = np.asarray(parsBTfmd.get(k, []), float).reshape(-1)
+        if types[i] == -1:
+            if v.size != 2:
+                raise ValueError(f"{k} must hold (tau1, tau2) when its sdfdType is -1")
+            P.sdfdPars[i][0], P.sdfdPars[i][1] = float(v[0]), float(v[1])
+    return P
+
+
+class Context:
+    """One per GPU (iak3d_ctx)."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = _vp()
+        st = self.lib.iak3d_ctx_create(int(device), C.byref(h))
+        if st != OK or not h.value:
+            raise Iak3dError(f"iak3d_ctx_create(device={device}) failed with status {st}: an sm_100-class GPU is required "
+                             "(there is no CPU fallback)")
+        self.h = h
+        self.device = int(device)
+
+    def check(self, st, allow=()):
+        if st == OK or st in allow:
+            return st
+        msg = self.lib.iak3d_last_error(self.h)
+        raise Iak3dError(f"libiak3d status {st}: {msg.decode() if msg else ''}")
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.iak3d_ctx_destroy(self.h)
+            self.h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- measurement helpers -------------------------------------------------------------------
+    def launch_count(self):
+        return int(self.lib.iak3d_launch_count(self.h))
+
+    def sync(self):
+        self.check(self.lib.iak3d_sync(self.h))
+
+    def timer_start(self):
+        self.check(self.lib.iak3d_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self.check(self.lib.iak3d_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def flush_l2(self):
+        self.check(self.lib.iak3d_flush_l2(self.h))
+
+    def fp64_peak(self, kind):
+        t = C.c_double()
+        self.check(self.lib.iak3d_fp64_peak(self.h, int(kind), C.byref(t)))
+        return t.value
+
+    def last_stage_ms(self):
+        ms = (C.c_double * 4)()
+        fl, by = C.c_double(), C.c_double()
+        self.check(self.lib.iak3d_last_stage_ms(self.h, ms, C.byref(fl), C.byref(by)))
+        return list(ms), fl.value, by.value
+
+    def device_info(self):
+        a, b, c, d = C.c_int(), C.c_int(), C.c_int(), _i64()
+        self.check(self.lib.iak3d_device_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return dict(sm_count=a.value, cc=(b.value, c.value), total_mem=d.value)
+
+
+_default_ctx = {}
+
+
+def default_context(device=None):
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]

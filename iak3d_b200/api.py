@@ -1,0 +1,580 @@
+"""Host-side mirror of the reference's interface for the hot path (same names, argument meaning and error
+behaviour as the R functions), driving libiak3d.so through the C ABI.  Everything O(n^2) or larger runs on the
+GPU; what stays here is what stays in R in the reference-side integration: the parameter
+transforms and the O(p^3) REML / ML tail.
+
+    setupIAK3D / setupIAK3D2      iaCovMatern.R:413-548, 581-678
+    readParsIAK3D, logitab, tauTfm fitIAK3D.R:1332-1417, 1587-1635
+    setCIAK3D / setCIAK3D2        fitIAK3D.R:955-1112, 1117-1252
+    lndetANDinvCb                 optim_functions.R:268-312
+    nllIAK3D, gradnllIAK3D        fitIAK3D.R:670-949, 1865-1886
+    nllIAK3D_CL                   compositeLikIAK3D.R:6-307
+    predictIAK3D                  predictIAK3D.R:5-287
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from ._lib import BAD_PARS, NOT_SPD, OK, Context, Iak3dError, Pars, default_context, dptr, f64, iptr, make_pars
+
+BADNLL = 9e99   # fitIAK3D.R:685
+
+
+# ---------------------------------------------------------------------------------------------
+# parameter transforms (host; fitIAK3D.R:1332-1417, 1474-1504, 1587-1635)
+# ---------------------------------------------------------------------------------------------
+def logitab(z, a=0.0, b=1.0, invt=False):
+    z = np.asarray(z, dtype=float)
+    if invt:
+        return (1.0 / (1.0 + np.exp(-z))) * (b - a) + a
+    u = (z - a) / (b - a)
+    return np.log(u / (1.0 - u))
+
+
+def tauTfm(parsIn, parBnds, invt=False):
+    v = np.asarray(parsIn, dtype=float).reshape(-1)
+    if v.size == 0:
+        return np.zeros(0)
+    if v.size != 2:
+        raise ValueError("tauTfm: not ready for this number of parameters")
+    lo, hi = parBnds["tau2Bnds"]
+    maxd = parBnds["maxd"]
+    if invt:
+        t2 = float(logitab(v[1], lo, hi, invt=True))
+        return np.array([(1.0 - math.exp(v[0])) / (1.0 - math.exp(-t2 * maxd)), t2])
+    return np.array([math.log(1.0 - v[0] * (1.0 - math.exp(-v[1] * maxd))), float(logitab(v[1], lo, hi))])
+
+
+def readParsIAK3D(pars, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds, lnTfmdData=False):
+    """Unconstrained optimiser vector -> parsBTfmd (natural scale), in the reference's consumption order."""
+    v = list(np.asarray(pars, dtype=float).reshape(-1))
+    take = lambda: v.pop(0)
+    ev = lambda: 1e-8 + math.exp(take())
+    if modelx not in ("matern", "wendland", "spherical", "nugget"):
+        raise ValueError("unknown modelx")
+    nugget = modelx == "nugget"
+    ax = nux = float("nan")
+    if not nugget:
+        ax = float(logitab(take(), *parBnds["axBnds"], invt=True))
+        if modelx != "spherical":
+            nux = float(logitab(take(), *parBnds["nuxBnds"], invt=True))
+    ad = float(logitab(take(), *parBnds["adBnds"], invt=True))
+    cx0 = cx1 = 0.0
+    if prodSum:
+        cx0 = ev()
+        if not nugget:
+            cx1 = ev()
+    cd1 = ev() if sdfdType_cd1 != -9 else 0.0
+    if not lnTfmdData:
+        if nugget:
+            cxd0, cxd1 = 1.0, 0.0
+        else:
+            cxd1 = float(logitab(take(), *parBnds["sxd1Bnds"], invt=True))
+            cxd0 = 1.0 - cxd1
+    else:
+        cxd0 = ev()
+        cxd1 = 0.0 if nugget else ev()
+    sd = []
+    for t in (sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1):
+        if t == -1:
+            sd.append(tauTfm([take(), take()], parBnds, invt=True))
+        elif t > 0:
+            sd.append(np.array([take() for _ in range(t)]))
+        elif t in (0, -9):
+            sd.append(np.zeros(0))
+        else:
+            raise ValueError("sdfd option not yet programmed")
+    cme = math.exp(take()) if cmeOpt == 1 else 0.0
+    out = dict(ax=ax, nux=nux, ad=ad, nud=nud, cx0=cx0, cx1=cx1, cd1=cd1, cxd0=cxd0, cxd1=cxd1,
+               sdfdPars_cd1=sd[0], sdfdPars_cxd0=sd[1], sdfdPars_cxd1=sd[2], cme=cme)
+    if v:
+        out["cssre"] = np.exp(np.array(v))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# setupMats
+# ---------------------------------------------------------------------------------------------
+class SetupMats:
+    """`setupMats` of the reference as a device-resident dataset handle (iak3d_ds)."""
+
+    def __init__(self, xData, dIData, W=None, ctx=None):
+        self.ctx = ctx or default_context()
+        self.xData = f64(np.asarray(xData, float).reshape(len(xData), -1))
+        if self.xData.shape[1] != 2:
+            raise ValueError("xData must have two coordinate columns")
+        self.dIData = f64(np.asarray(dIData, float).reshape(-1, 2))
+        self.n = self.xData.shape[0]
+        if self.dIData.shape[0] != self.n:
+            raise ValueError("xData and dIData must have the same number of rows")
+        self._W = None
+        h = C.c_void_p()
+        Wp, q = None, 0
+        if W is not None:
+            self._W = f64(W)
+            Wp, q = dptr(self._W), self._W.shape[1]
+        self.ctx.check(self.ctx.lib.iak3d_dataset_create(self.ctx.h, self.n, dptr(self.xData), dptr(self.dIData), Wp, q, C.byref(h)))
+        self.h = h
+        n_, nx, nd, q_ = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
+        self.ctx.check(self.ctx.lib.iak3d_dataset_info(self.h, C.byref(n_), C.byref(nx), C.byref(nd), C.byref(q_)))
+        self.nxU, self.ndIU, self.q = nx.value, nd.value, q_.value
+        self.maxd = max(float(self.dIData.max()), 2.0)     # iaCovMatern.R:435
+
+    def set_W(self, W):
+        W = f64(W)
+        if W.shape[0] != self.n:
+            raise ValueError("W must have n rows")
+        if self._W is not None and W.shape == self._W.shape and np.array_equal(W, self._W):
+            return
+        self.ctx.check(self.ctx.lib.iak3d_dataset_set_W(self.h, dptr(W), W.shape[1]))
+        self._W, self.q = W, W.shape[1]
+
+    def upload_W(self, W):
+        """Unconditional host->device copy of W (bench.py's end-to-end leg)."""
+        W = f64(W)
+        self.ctx.check(self.ctx.lib.iak3d_dataset_set_W(self.h, dptr(W), W.shape[1]))
+        self._W, self.q = W, W.shape[1]
+
+    def ids(self):
+        xid = np.empty(self.n, np.int32); did = np.empty(self.n, np.int32)
+        self.ctx.check(self.ctx.lib.iak3d_dataset_ids(self.h, iptr(xid), iptr(did)))
+        return xid, did
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.ctx.lib.iak3d_dataset_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def setupIAK3D(xData, dIData, ctx=None, **_ignored):
+    return SetupMats(xData, dIData, ctx=ctx)
+
+
+class SetupMats2:
+    """setupIAK3D2: set 1 (rows of the result) stays on the host, set 2 is a resident dataset."""
+
+    def __init__(self, xData, dIData, xData2, dIData2, ctx=None, setup2=None):
+        self.x1 = f64(np.asarray(xData, float).reshape(len(xData), -1))
+        self.d1 = f64(np.asarray(dIData, float).reshape(-1, 2))
+        self.set2 = setup2 if setup2 is not None else SetupMats(xData2, dIData2, ctx=ctx)
+
+
+def setupIAK3D2(xData, dIData, xData2, dIData2, ctx=None, **_ignored):
+    return SetupMats2(xData, dIData, xData2, dIData2, ctx=ctx)
+
+
+# ---------------------------------------------------------------------------------------------
+# covariance assembly
+# ---------------------------------------------------------------------------------------------
+def setCIAK3D(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, setupMats, rtnC=True):
+    """-> dict(C, sigma2Vec); C is None (R: NA) for invalid parameters."""
+    sm = setupMats
+    P = make_pars(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt)
+    Cm = np.empty((sm.n, sm.n), order="F") if rtnC else None
+    s2 = np.empty(sm.n)
+    st = sm.ctx.check(sm.ctx.lib.iak3d_cov_build(sm.h, C.byref(P), dptr(Cm), dptr(s2)), allow=(BAD_PARS,))
+    if st == BAD_PARS:
+        return dict(C=None, sigma2Vec=None)
+    return dict(C=Cm, sigma2Vec=s2)
+
+
+def setCIAK3D2(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, setupMats):
+    sm = setupMats
+    P = make_pars(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt)
+    n1, n2 = sm.x1.shape[0], sm.set2.n
+    out = np.empty((n1, n2), order="F")
+    ctx = sm.set2.ctx
+    st = ctx.check(ctx.lib.iak3d_cov_cross(sm.set2.h, C.byref(P), n1, dptr(sm.x1), dptr(sm.d1), dptr(out)), allow=(BAD_PARS,))
+    return None if st == BAD_PARS else out
+
+
+def iaCovMatern2(dIData, dIData2, ad, nud, sdfdPars, sdfdType, ctx=None):
+    ctx = ctx or default_context()
+    d1 = f64(np.asarray(dIData, float).reshape(-1, 2)); d2 = f64(np.asarray(dIData2, float).reshape(-1, 2))
+    out = np.empty((d1.shape[0], d2.shape[0]), order="F"); av = np.empty(d1.shape[0])
+    sp = f64(np.asarray(sdfdPars, float).reshape(-1)[:2]) if sdfdType == -1 else None
+    st = ctx.check(ctx.lib.iak3d_iacov(ctx.h, d1.shape[0], dptr(d1), d2.shape[0], dptr(d2), float(ad), float(nud), int(sdfdType),
+                                        dptr(sp), dptr(out), dptr(av)), allow=(BAD_PARS,))
+    if st == BAD_PARS:
+        raise ValueError("This function can only be applied with nud = 0.5, 1.5 or 2.5 and sdfdType = 0 or -1!")
+    return out, av
+
+
+def spatialCovIAK3D(D, pars, covModel="matern", ctx=None):
+    ctx = ctx or default_context()
+    Dm = f64(D)
+    out = np.empty(Dm.shape, order="F")
+    nu = float(pars[2]) if len(pars) > 2 and pars[2] is not None else float("nan")
+    st = ctx.check(ctx.lib.iak3d_spatial_cov(ctx.h, Dm.size, dptr(Dm), _lib.MODELX[covModel], float(pars[0]), float(pars[1]), nu,
+                                              dptr(out)), allow=(BAD_PARS,))
+    return None if st == BAD_PARS else out
+
+
+# ---------------------------------------------------------------------------------------------
+# factorisation
+# ---------------------------------------------------------------------------------------------
+def lndetANDinvCb(Cm, b=None, ctx=None):
+    """-> dict(lndetC, invCb); (nan, None) where the reference returns (NA, NA)."""
+    ctx = ctx or default_context()
+    Cm = f64(Cm)
+    n = Cm.shape[0]
+    lnd = C.c_double()
+    if b is None:
+        out = np.empty((n, n), order="F")
+        st = ctx.check(ctx.lib.iak3d_lndet_invCb(ctx.h, n, dptr(Cm), 0, None, C.byref(lnd), dptr(out)), allow=(NOT_SPD,))
+    else:
+        bm = f64(np.asarray(b, float).reshape(n, -1))
+        out = np.empty(bm.shape, order="F")
+        st = ctx.check(ctx.lib.iak3d_lndet_invCb(ctx.h, n, dptr(Cm), bm.shape[1], dptr(bm), C.byref(lnd), dptr(out)), allow=(NOT_SPD,))
+    if st == NOT_SPD:
+        return dict(lndetC=float("nan"), invCb=None)
+    return dict(lndetC=lnd.value, invCb=out)
+
+
+# ---------------------------------------------------------------------------------------------
+# likelihood
+# ---------------------------------------------------------------------------------------------
+def _small_chol_solve(A, b):
+    """lndetANDinvCb on the p x p system (host: O(p^3), as in the reference-side R glue)."""
+    try:
+        L = np.linalg.cholesky(A)
+    except np.linalg.LinAlgError:
+        return float("nan"), None
+    d = np.diag(L)
+    if not np.all(np.isfinite(d)) or np.any(d <= 0):
+        return float("nan"), None
+    y = np.linalg.solve(L, b)
+    return 2.0 * float(np.sum(np.log(d))), np.linalg.solve(L.T, y)
+
+
+def reml_tail(WiAW, lndetA, n, p, useReml=True, n_for_cxd=None, n_for_lndet=None):
+    """fitIAK3D.R:821-880 / compositeLikIAK3D.R:191-265.  -> dict(nll, betahat, cxdhat, lndetXiAX, resiAres)."""
+    XiAX = WiAW[:p, :p]; XiAz = WiAW[:p, p:p + 1]; ziAz = float(WiAW[p, p])
+    lndetXiAX, betahat = _small_chol_solve(XiAX, XiAz)
+    if not np.isfinite(lndetXiAX):
+        return dict(nll=BADNLL, betahat=None, cxdhat=float("nan"))
+    resiAres = float(ziAz - 2.0 * (betahat.T @ XiAz)[0, 0] + (betahat.T @ XiAX @ betahat)[0, 0])
+    if n_for_cxd is not None:
+        cxdhat = resiAres / n_for_cxd
+    else:
+        cxdhat = resiAres / (n - p) if useReml else resiAres / n
+    nn = n if n_for_lndet is None else n_for_lndet
+    with np.errstate(invalid="ignore", divide="ignore"):
+        lndetC = lndetA + nn * np.log(cxdhat)
+        lndetXiCX = lndetXiAX - p * np.log(cxdhat)
+        resiCres = resiAres / cxdhat if cxdhat != 0 else float("nan")
+        if useReml:
+            nll = 0.5 * ((n - p) * math.log(2.0 * math.pi) + lndetC + lndetXiCX + resiCres)
+        else:
+            nll = 0.5 * (n * math.log(2.0 * math.pi) + lndetC + resiCres)
+    nll = float(nll)
+    if not np.isfinite(nll):
+        nll = BADNLL
+    return dict(nll=nll, betahat=betahat, cxdhat=cxdhat, lndetXiAX=lndetXiAX, resiAres=resiAres)
+
+
+def nll_terms_batch(ctx, setups, parsList):
+    """One launch for many (setupMats, struct pars) pairs -> lndetA[count], WiAW[count,q,q], status[count]."""
+    count = len(setups)
+    q = setups[0].q
+    dsarr = (C.c_void_p * count)(*[s.h for s in setups])
+    parr = (Pars * count)(*parsList)
+    lnd = np.empty(count); W = np.empty((count, q * q)); st = np.empty(count, np.int32)
+    ctx.check(ctx.lib.iak3d_nll_terms_batch(ctx.h, count, dsarr, parr, dptr(lnd), dptr(W), iptr(st)))
+    # G is stored column-major q x q and is symmetric
+    return lnd, W.reshape(count, q, q), st
+
+
+def _symm_upper(M):
+    return np.triu(M) + np.triu(M, 1).T     # forceSymmetric keeps the upper triangle (fitIAK3D.R:811)
+
+
+def nllIAK3D(pars, zData, XData, vXU=None, iU=None, modelx="matern", nud=0.5, sdfdType_cd1=0, sdfdType_cxd0=0, sdfdType_cxd1=0,
+             cmeOpt=0, prodSum=True, setupMats=None, parBnds=None, useReml=True, lnTfmdData=False, rtnAll=False,
+             forCompLik=False, attachBigMats=False, nCores=8, parsBTfmd=None):
+    """fitIAK3D.R:670-949 (lnTfmdData = FALSE).  `parsBTfmd` may be passed to skip the transform."""
+    if lnTfmdData:
+        raise NotImplementedError("lnTfmdData = TRUE (nrUpdatesIAK3DlnN) is not on the accelerated path")
+    if setupMats is None:
+        raise ValueError("setupMats (from setupIAK3D) is required")
+    sm = setupMats
+    zData = np.asarray(zData, float).reshape(-1)
+    XData = np.asarray(XData, float).reshape(zData.size, -1)
+    n, p = XData.shape
+    if parsBTfmd is None:
+        parsBTfmd = readParsIAK3D(pars, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds)
+    parsBTfmd = dict(parsBTfmd)
+    sm.set_W(np.column_stack([XData, zData]))                      # W <- cbind(XData, zData), :757
+    P = make_pars(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt)
+    ctx = sm.ctx
+    lnd = C.c_double(); G = np.empty((p + 1, p + 1), order="F")
+    want_iAW = forCompLik or (rtnAll and not attachBigMats)
+    iAW = np.empty((n, p + 1), order="F") if want_iAW else None
+    st = ctx.check(ctx.lib.iak3d_nll_terms(sm.h, C.byref(P), C.byref(lnd), dptr(G), dptr(iAW)), allow=(NOT_SPD, BAD_PARS))
+    bad = dict(nll=BADNLL, pars=pars, parsBTfmd=parsBTfmd, betahat=None, vbetahat=None, cxdhat=float("nan")) if rtnAll else BADNLL
+    if st != OK:
+        if forCompLik:
+            return dict(pars=pars, parsBTfmd=parsBTfmd, WiAW=np.full((p + 1, p + 1), np.nan), lndetA=float("nan"))
+        return bad
+    WiAW = _symm_upper(np.array(G))
+    lndetA = lnd.value
+    if forCompLik:
+        out = dict(pars=pars, parsBTfmd=parsBTfmd, WiAW=WiAW, lndetA=lndetA, iAW=iAW)
+        out["sigma2Vec"] = setCIAK3D(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, sm, rtnC=attachBigMats)
+        if attachBigMats:
+            out["A"] = out["sigma2Vec"]["C"]
+        out["sigma2Vec"] = out["sigma2Vec"]["sigma2Vec"]
+        return out
+    t = reml_tail(WiAW, lndetA, n, p, useReml)
+    if t["nll"] == BADNLL and t["betahat"] is None:
+        return bad
+    if not rtnAll:
+        return t["nll"]
+    cxdhat, betahat = t["cxdhat"], t["betahat"]
+    unscaled = dict(parsBTfmd)
+    for k in ("cx0", "cx1", "cd1", "cxd0", "cxd1"):                # :857-861
+        parsBTfmd[k] = cxdhat * parsBTfmd[k]
+    if cmeOpt == 1:
+        parsBTfmd["cme"] = cxdhat * parsBTfmd["cme"]
+    vbetahat = cxdhat * np.linalg.inv(WiAW[:p, :p])                # :870
+    s2 = setCIAK3D(unscaled, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, sm, rtnC=False)["sigma2Vec"]
+    out = dict(nll=t["nll"], pars=pars, parsBTfmd=parsBTfmd, betahat=betahat, vbetahat=vbetahat, cxdhat=cxdhat,
+               sigma2Vec=cxdhat * s2, XData=XData, zData=zData, vXU=vXU, iU=iU, lndetA=lndetA, WiAW=WiAW,
+               modelx=modelx, nud=nud, sdfdType_cd1=sdfdType_cd1, sdfdType_cxd0=sdfdType_cxd0, sdfdType_cxd1=sdfdType_cxd1,
+               cmeOpt=cmeOpt, setupMats=sm, xData=sm.xData, dIData=sm.dIData)
+    if attachBigMats:
+        # the big matrices stay on the device as a kept factorisation (iak3d_fit); iCX / iCz_muhat are copied out
+        fit = KeptFit(sm, parsBTfmd, modelx, (sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1), cmeOpt, betahat, vbetahat)
+        iCX, iCz = fit.get_small()
+        out.update(fit=fit, iCX=iCX, iCz_muhat=iCz)
+    else:
+        out.update(iAX=iAW[:, :p], iAz=iAW[:, p:p + 1])
+    return out
+
+
+def gradnllIAK3D(pars, zData, XData, vXU=None, iU=None, modelx="matern", nud=0.5, sdfdType_cd1=0, sdfdType_cxd0=0,
+                 sdfdType_cxd1=0, cmeOpt=0, prodSum=True, setupMats=None, parBnds=None, useReml=True, lnTfmdData=False,
+                 delta=1e-6, rtn_nll=False):
+    """Forward-difference gradient (fitIAK3D.R:1865-1886): the npar + 1 evaluations go to the GPU as ONE batch
+    (the reference forks them with mclapply, :1804).  NA differences become 0 (:1813)."""
+    if lnTfmdData:
+        raise NotImplementedError("lnTfmdData = TRUE is not on the accelerated path")
+    sm = setupMats
+    pars = np.asarray(pars, float).reshape(-1)
+    zData = np.asarray(zData, float).reshape(-1)
+    XData = np.asarray(XData, float).reshape(zData.size, -1)
+    n, p = XData.shape
+    sm.set_W(np.column_stack([XData, zData]))
+    npar = pars.size
+    cand = [pars.copy()]
+    for i in range(npar):
+        v = pars.copy(); v[i] += delta
+        cand.append(v)
+    structs = []
+    for v in cand:
+        pb = readParsIAK3D(v, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds)
+        structs.append(make_pars(pb, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt))
+    lnd, G, st = nll_terms_batch(sm.ctx, [sm] * len(cand), structs)
+    vals = np.empty(len(cand))
+    for i in range(len(cand)):
+        vals[i] = reml_tail(_symm_upper(G[i].T), lnd[i], n, p, useReml)["nll"] if st[i] == OK else BADNLL
+    g = (vals[1:] - vals[0]) / delta
+    g[~np.isfinite(g)] = 0.0
+    return (g, vals[0]) if rtn_nll else g
+
+
+def nllIAK3D_CL(pars, zData, XData, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds, useReml,
+                compLikMats, parsBTfmd=None, rtnTerms=False, comm=None):
+    """compositeLikIAK3D.R:6-307.  `compLikMats` carries compLikOptn, listBlocks, subsetPairsAdj, subsetPairsNonadj and
+    the per-unit device datasets made by :func:`setupIAK3D_CL` (first the adjacent pairs, then the single blocks --
+    the order of iaCovMatern.R:551-575).  With `comm` (a parallel.BlockComm) the units are sharded across ranks and
+    the sums are combined by one all-reduce of (p+1)^2 + 2 doubles."""
+    zData = np.asarray(zData, float).reshape(-1)
+    XData = np.asarray(XData, float).reshape(zData.size, -1)
+    n, p = XData.shape
+    optn = compLikMats["compLikOptn"]
+    nB = len(compLikMats["listBlocks"])
+    if parsBTfmd is None:
+        parsBTfmd = readParsIAK3D(pars, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds)
+    P = make_pars(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt)
+    units = compLikMats["units"]               # list of dict(kind, weight, n, setup) owned by this rank
+    S = np.zeros((p + 1, p + 1)); lnd_sum = 0.0; n_SUM = 0.0; failed = 0.0
+    if units:
+        ctx = units[0]["setup"].ctx
+        lnd, G, st = nll_terms_batch(ctx, [u["setup"] for u in units], [P] * len(units))
+        for i, u in enumerate(units):
+            if st[i] != OK:
+                failed = 1.0
+                continue
+            w = u["weight"]
+            S += w * _symm_upper(G[i].T); lnd_sum += w * lnd[i]
+            if u["kind"] == "pair":
+                n_SUM += u["n"]
+    buf = np.concatenate([S.reshape(-1), [lnd_sum, n_SUM, failed]])
+    if comm is not None:
+        buf = comm.allreduce_sum(buf)
+    S = buf[:(p + 1) ** 2].reshape(p + 1, p + 1); lnd_sum, n_SUM, failed = buf[-3], buf[-2], buf[-1]
+    if failed > 0:
+        return BADNLL
+    if optn == 3:
+        n_SUM = n * (nB - 1)
+    if optn == 1:
+        XziAXz = S / (nB - 1); lndetA = lnd_sum / (nB - 1)
+    else:
+        XziAXz = S; lndetA = lnd_sum
+    if optn in (2, 3):
+        if useReml:
+            raise ValueError("Eidsvik was only defined for ML, not REML estimation!")
+        t = reml_tail(XziAXz, lndetA, n, p, useReml, n_for_cxd=n_SUM, n_for_lndet=n_SUM)
+    else:
+        t = reml_tail(XziAXz, lndetA, n, p, useReml)
+    if rtnTerms:
+        return dict(nll=t["nll"], XziAXz_SUM=S, lndetA_SUM=lnd_sum, n_SUM=n_SUM, cxdhat=t["cxdhat"], betahat=t["betahat"])
+    return t["nll"]
+
+
+def setupIAK3D_CL(xData, dIData, zData, XData, compLikMats, ctx=None, rank=0, world=1):
+    """iaCovMatern.R:551-575 + the unit weights of compositeLikIAK3D.R:42-179, as a list of device datasets.
+
+    Units: every adjacent pair (optn < 4) and every single block that some non-adjacent pair needs (optn 1, 3: a
+    block's terms are added once per non-adjacent pair it belongs to, :126-155) or all single blocks (optn 4).
+    With world > 1 the units are dealt to ranks by longest-processing-time on n^3."""
+    ctx = ctx or default_context()
+    xData = np.asarray(xData, float); dIData = np.asarray(dIData, float).reshape(-1, 2)
+    zData = np.asarray(zData, float).reshape(-1); XData = np.asarray(XData, float).reshape(zData.size, -1)
+    optn = compLikMats["compLikOptn"]
+    blocks = compLikMats["listBlocks"]
+    units = []
+    if optn < 4:
+        for (k, l) in np.asarray(compLikMats["subsetPairsAdj"]).reshape(-1, 2):
+            rows = np.concatenate([blocks[k], blocks[l]])
+            units.append(dict(kind="pair", weight=1.0, rows=rows))
+    if optn in (1, 3):
+        cnt = np.zeros(len(blocks))
+        for (k, l) in np.asarray(compLikMats.get("subsetPairsNonadj", np.zeros((0, 2), int))).reshape(-1, 2):
+            cnt[k] += 1; cnt[l] += 1
+        for b, c in enumerate(cnt):
+            if c > 0:
+                units.append(dict(kind="block", weight=float(c), rows=blocks[b]))
+    elif optn == 4:
+        for b in range(len(blocks)):
+            units.append(dict(kind="block", weight=1.0, rows=blocks[b]))
+    # longest-processing-time assignment
+    order = np.argsort([-len(u["rows"]) for u in units], kind="stable")
+    load = np.zeros(world); mine = []
+    for i in order:
+        r = int(np.argmin(load)); load[r] += float(len(units[i]["rows"])) ** 3
+        if r == rank:
+            mine.append(i)
+    out = []
+    for i in sorted(mine):
+        u = units[i]; rows = u["rows"]
+        W = np.column_stack([XData[rows], zData[rows]])
+        u["setup"] = SetupMats(xData[rows], dIData[rows], W=W, ctx=ctx)
+        u["n"] = len(rows)
+        out.append(u)
+    cl = dict(compLikMats)
+    cl["units"] = out
+    cl["n_units_total"] = len(units)
+    return cl
+
+
+# ---------------------------------------------------------------------------------------------
+# kept fit + kriging
+# ---------------------------------------------------------------------------------------------
+class KeptFit:
+    """The big matrices of lmmFit (C, iC, iCX, iCz_muhat) as a factorisation kept on the device (iak3d_fit)."""
+
+    def __init__(self, setupMats, parsBTfmd, modelx, sdfdTypes, cmeOpt, betahat, vbetahat):
+        sm = setupMats
+        self.sm, self.ctx = sm, sm.ctx
+        self.p = sm.q - 1
+        P = make_pars(parsBTfmd, modelx, *sdfdTypes, cmeOpt)
+        b = f64(np.asarray(betahat, float).reshape(-1)); V = f64(np.asarray(vbetahat, float).reshape(self.p, self.p))
+        h = C.c_void_p()
+        st = self.ctx.check(self.ctx.lib.iak3d_fit_create(sm.h, C.byref(P), dptr(b), dptr(V), C.byref(h)), allow=(NOT_SPD, BAD_PARS))
+        if st != OK:
+            raise Iak3dError("fit_create: the fitted covariance matrix is not positive definite" if st == NOT_SPD
+                             else "fit_create: invalid parameters")
+        self.h = h
+
+    def get_small(self):
+        n, p = self.sm.n, self.p
+        iCX = np.empty((n, p), order="F"); iCz = np.empty((n, 1), order="F")
+        self.ctx.check(self.ctx.lib.iak3d_fit_get(self.h, dptr(iCX), dptr(iCz), None, None))
+        return iCX, iCz
+
+    def get_big(self, want_C=True, want_iC=True):
+        n = self.sm.n
+        Cm = np.empty((n, n), order="F") if want_C else None
+        iC = np.empty((n, n), order="F") if want_iC else None
+        self.ctx.check(self.ctx.lib.iak3d_fit_get(self.h, None, None, dptr(Cm), dptr(iC)))
+        return Cm, iC
+
+    def predict(self, xMap, dIMap, XMap):
+        xMap = f64(np.asarray(xMap, float).reshape(-1, 2)); dIMap = f64(np.asarray(dIMap, float).reshape(-1, 2))
+        XMap = f64(np.asarray(XMap, float).reshape(xMap.shape[0], -1))
+        m = xMap.shape[0]
+        z = np.empty(m); v = np.empty(m)
+        self.ctx.check(self.ctx.lib.iak3d_predict(self.h, m, dptr(xMap), dptr(dIMap), dptr(XMap), dptr(z), dptr(v)))
+        return z, v
+
+    def stage(self, xMap, dIMap, XMap):
+        xMap = f64(np.asarray(xMap, float).reshape(-1, 2)); dIMap = f64(np.asarray(dIMap, float).reshape(-1, 2))
+        XMap = f64(np.asarray(XMap, float).reshape(xMap.shape[0], -1))
+        self.ctx.check(self.ctx.lib.iak3d_predict_stage(self.h, xMap.shape[0], dptr(xMap), dptr(dIMap), dptr(XMap)))
+        self._m = xMap.shape[0]
+
+    def enqueue(self):
+        self.ctx.check(self.ctx.lib.iak3d_predict_enqueue(self.h))
+
+    def fetch(self):
+        z = np.empty(self._m); v = np.empty(self._m)
+        self.ctx.check(self.ctx.lib.iak3d_predict_fetch(self.h, dptr(z), dptr(v)))
+        return z, v
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.ctx.lib.iak3d_fit_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def predictIAK3D(xMap, dIMap, XMap_fn, lmmFit, nxPerBatch=2000, cells=None):
+    """predictIAK3D.R:5-287 for compLikOptn = 0, lnTfmdData = FALSE.  `lmmFit` is the rtnAll/attachBigMats dict of
+    :func:`nllIAK3D`; `XMap_fn(iDepth, cellIdx)` supplies the design rows (makeXvX is an input of the hot path).
+    Rows of XMap containing NaN are skipped and stay NaN (predictIAK3D.R:160-163).  `cells` restricts the work to a
+    slice of the map (prediction-grid tiles per GPU).  -> dict(zMap, vMap, pi90LMap, pi90UMap) [ndIMap x nxMap]."""
+    xMap = np.asarray(xMap, float).reshape(len(xMap), -1)
+    dIMap = np.round(np.asarray(dIMap, float).reshape(-1, 2), 2)       # :29
+    nd, nx = dIMap.shape[0], xMap.shape[0]
+    fit = lmmFit["fit"]
+    idx_all = np.arange(nx) if cells is None else np.asarray(cells)
+    zMap = np.full((nd, nx), np.nan); vMap = np.full((nd, nx), np.nan)
+    for i in range(nd):
+        XM = np.asarray(XMap_fn(i, idx_all), float)
+        ok = ~np.isnan(XM.mean(axis=1))
+        if not ok.any():
+            continue
+        sel = idx_all[ok]
+        dI = np.repeat(dIMap[i:i + 1], sel.size, axis=0)                # :150
+        z, v = fit.predict(xMap[sel], dI, XM[ok])
+        zMap[i, sel] = z; vMap[i, sel] = v
+    with np.errstate(invalid="ignore"):
+        s = np.sqrt(vMap)
+    return dict(zMap=zMap, vMap=vMap, pi90LMap=zMap - 1.645 * s, pi90UMap=zMap + 1.645 * s)   # :272-273

@@ -1,0 +1,865 @@
+// api.cu -- the extern "C" boundary of libiak3d.so (include/iak3d.h): contexts, datasets (setupIAK3D as id
+// vectors), evaluation planning from parsBTfmd, and the likelihood-term pipeline
+//     tables -> covariance build into the factor layout -> ticketed tile Cholesky -> finish.
+// Host logic only; all arithmetic on matrices happens in the kernels of tables.cu / covbuild.cu / chol.cu.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <unordered_map>
+
+#include "common.cuh"
+
+// ================================================================================================
+// helpers
+// ================================================================================================
+namespace {
+
+struct Key2 {
+  uint64_t a, b;
+  bool operator==(const Key2& o) const { return a == o.a && b == o.b; }
+};
+struct Key2Hash {
+  size_t operator()(const Key2& k) const {
+    uint64_t h = k.a * 0x9E3779B97F4A7C15ull;
+    h ^= (h >> 29);
+    h += k.b * 0xC2B2AE3D27D4EB4Full;
+    h ^= (h >> 32);
+    return (size_t)h;
+  }
+};
+inline uint64_t dbits(double v) {
+  if (v == 0.0) v = 0.0;   // -0.0 == 0.0 in R's `==`
+  uint64_t u;
+  memcpy(&u, &v, 8);
+  return u;
+}
+
+}  // namespace
+
+// rows (c0[i], c1[i]) -> ids in first-occurrence order (`!duplicated`, iaCovMatern.R:418-419) + unique table
+void iak_unique_first(int64_t n, const double* c0, const double* c1, std::vector<int32_t>& id, std::vector<double>& U) {
+  std::unordered_map<Key2, int32_t, Key2Hash> map;
+  map.reserve((size_t)std::min<int64_t>(n, 1 << 22));
+  std::vector<double> u0, u1;
+  id.resize((size_t)n);
+  for (int64_t i = 0; i < n; i++) {
+    const Key2 k{dbits(c0[i]), dbits(c1[i])};
+    auto it = map.find(k);
+    if (it == map.end()) {
+      const int32_t v = (int32_t)u0.size();
+      map.emplace(k, v);
+      u0.push_back(c0[i]); u1.push_back(c1[i]);
+      id[(size_t)i] = v;
+    } else {
+      id[(size_t)i] = it->second;
+    }
+  }
+  const size_t nu = u0.size();
+  U.resize(2 * nu);
+  for (size_t i = 0; i < nu; i++) { U[i] = u0[i]; U[nu + i] = u1[i]; }
+}
+
+// parsBTfmd -> plan.  `square`: setCIAK3D (the cd1 quirk of fitIAK3D.R:1052 applies); otherwise setCIAK3D2 (:1211).
+// Returns <0 for unsupported requests (spline sdfd), otherwise 0 with plan.status in {0, IAK3D_BAD_PARS}.
+int iak_make_plan(iak3d_ctx* ctx, const iak3d_pars* p, bool square, EvalPlan* pl) {
+  *pl = EvalPlan();
+  for (int c = 0; c < 3; c++) {
+    const int t = p->sdfdType[c];
+    if (t > 0) { ctx->err = "spline sd functions (sdfdType > 0, setCApproxIAK3D) are not implemented"; return IAK3D_ERR_ARG; }
+    if (!(t == 0 || t == -1 || (t == -9 && c == 0))) { ctx->err = "sdfdType must be 0, -1 (or -9 for cd1)"; return IAK3D_ERR_ARG; }
+  }
+  if (p->modelx < IAK3D_MODELX_NUGGET || p->modelx > IAK3D_MODELX_WENDLAND) { ctx->err = "unknown modelx"; return IAK3D_ERR_ARG; }
+  const bool nugget = (p->modelx == IAK3D_MODELX_NUGGET);
+  pl->cx0 = p->cx0; pl->cx1 = nugget ? 0.0 : p->cx1; pl->cd1 = p->cd1; pl->cxd0 = p->cxd0; pl->cxd1 = nugget ? 0.0 : p->cxd1;
+  pl->cme = p->cme;
+  // NA / Inf guards of nllIAK3D (fitIAK3D.R:718-741)
+  const double vs[6] = {pl->cx0, pl->cx1, pl->cd1, pl->cxd0, pl->cxd1, pl->cme};
+  for (double v : vs) if (!isfinite(v)) { pl->status = IAK3D_BAD_PARS; return 0; }
+  if (!isfinite(p->ad) || !(p->ad > 0.0)) { pl->status = IAK3D_BAD_PARS; return 0; }
+  for (int c = 0; c < 3; c++)
+    if (p->sdfdType[c] == -1 && !(isfinite(p->sdfdPars[c][0]) && isfinite(p->sdfdPars[c][1]))) { pl->status = IAK3D_BAD_PARS; return 0; }
+  // depth tables: one shared stationary table (fitIAK3D.R:986-993) + one per non-stationary component
+  int stat = -1;
+  for (int c = 0; c < 3; c++) {
+    const int t = p->sdfdType[c];
+    if (c == 2 && nugget) { pl->tidx[c] = -1; continue; }           // :1018-1020
+    if (t == -9) { pl->tidx[c] = -1; continue; }                     // :998-1000
+    if (t == 0) {
+      if (stat < 0) {
+        stat = pl->ntab++;
+        if (iak_prm_init(&pl->prm[stat], p->ad, p->nud, 0, 0.0, 0.0) != 0) { pl->status = IAK3D_BAD_PARS; return 0; }
+      }
+      pl->tidx[c] = stat;
+    } else {
+      const int k = pl->ntab++;
+      if (iak_prm_init(&pl->prm[k], p->ad, p->nud, -1, p->sdfdPars[c][0], p->sdfdPars[c][1]) != 0) { pl->status = IAK3D_BAD_PARS; return 0; }
+      pl->tidx[c] = k;
+    }
+  }
+  pl->kd1 = pl->cd1;
+  if (square && p->sdfdType[0] == -1 && p->quirk_cd1_unscaled) pl->kd1 = 1.0;   // fitIAK3D.R:1052 (sic)
+  pl->has_phix = !nugget;
+  if (!nugget) {
+    const int st = hx_init(&pl->H, p->modelx, p->ax, p->nux);
+    if (st != 0) { pl->status = IAK3D_BAD_PARS; return 0; }
+  }
+  return 0;
+}
+
+// ================================================================================================
+// context
+// ================================================================================================
+struct Batch {
+  int32_t count = 0, q = 0;
+  std::vector<iak3d_ds*> ds;
+  std::vector<Slot*> slots;
+  std::vector<int> plan_status;
+  std::vector<int64_t> key;          // geometry key of the cached task list
+  ProblemDesc* d_probs = nullptr; int32_t probs_cap = 0;
+  int4* d_tasks = nullptr; int64_t tasks_cap = 0; int32_t ntasks = 0;
+  int32_t* d_ticket = nullptr;
+  int32_t* d_status = nullptr; int32_t status_cap = 0;
+  double* d_results = nullptr; double* h_results = nullptr; int64_t results_cap = 0;
+  int32_t stride = 0;
+  bool pending = false;
+};
+
+extern "C" int iak3d_ctx_create(int device, iak3d_ctx** out) {
+  if (out == nullptr) return IAK3D_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return IAK3D_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return IAK3D_ERR_CUDA;
+  if (prop.major != 10) return IAK3D_ERR_CUDA;   // sm_100-class only: no fallback of any kind
+  if (cudaSetDevice(device) != cudaSuccess) return IAK3D_ERR_CUDA;
+  iak3d_ctx* ctx = new iak3d_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->cc_major = prop.major; ctx->cc_minor = prop.minor;
+  ctx->total_mem = prop.totalGlobalMem;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return IAK3D_ERR_CUDA; }
+  cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+  for (int i = 0; i < 5; i++) cudaEventCreate(&ctx->evs[i]);
+  ctx->batch = new Batch();
+  if (cudaMalloc(&ctx->batch->d_ticket, 2 * sizeof(int32_t)) != cudaSuccess) { delete ctx->batch; delete ctx; return IAK3D_ERR_CUDA; }
+  if (chol_configure(ctx) != 0) { delete ctx->batch; delete ctx; return IAK3D_ERR_CUDA; }
+  *out = ctx;
+  return IAK3D_OK;
+}
+
+extern "C" int iak3d_ctx_destroy(iak3d_ctx* ctx) {
+  if (ctx == nullptr) return IAK3D_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  Batch* b = ctx->batch;
+  if (b != nullptr) {
+    cudaFree(b->d_probs); cudaFree(b->d_tasks); cudaFree(b->d_ticket); cudaFree(b->d_status); cudaFree(b->d_results);
+    if (b->h_results) cudaFreeHost(b->h_results);
+    delete b;
+  }
+  if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+  cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+  for (int i = 0; i < 5; i++) cudaEventDestroy(ctx->evs[i]);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return IAK3D_OK;
+}
+
+extern "C" const char* iak3d_last_error(iak3d_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int iak3d_device_info(iak3d_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, int64_t* total_mem) {
+  if (!ctx) return IAK3D_ERR_ARG;
+  if (sm_count) *sm_count = ctx->sm_count;
+  if (cc_major) *cc_major = ctx->cc_major;
+  if (cc_minor) *cc_minor = ctx->cc_minor;
+  if (total_mem) *total_mem = (int64_t)ctx->total_mem;
+  return IAK3D_OK;
+}
+
+extern "C" int64_t iak3d_launch_count(iak3d_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+// ================================================================================================
+// dataset
+// ================================================================================================
+static void free_slot(Slot* s) {
+  if (!s) return;
+  cudaFree(s->d_L); cudaFree(s->d_phix); cudaFree(s->d_phid); cudaFree(s->d_invd); cudaFree(s->d_flags);
+  cudaFree(s->d_logsum); cudaFree(s->d_G);
+  delete s;
+}
+
+// factor-buffer workspace for an n x n problem with q bordered rows (tables optional: nxU = ndIU = 0)
+int iak_alloc_slot(iak3d_ctx* ctx, int64_t n, int32_t q, int64_t nxU, int64_t ndIU, Slot** out) {
+  Slot* s = new Slot();
+  s->n = n; s->q = q; s->nxU = nxU; s->ndIU = ndIU;
+  s->Npad = round_up(std::max<int64_t>(n, 1), TN);
+  s->ld = round_up(s->Npad + q, TM);
+  s->nCB = (int32_t)(s->Npad / TN); s->nRB = (int32_t)(s->ld / TM);
+  cudaError_t e = cudaSuccess;
+  auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, std::max<size_t>(bytes, 16)); };
+  A((void**)&s->d_L, (size_t)s->ld * s->Npad * sizeof(double));
+  A((void**)&s->d_phix, (size_t)nxU * nxU * sizeof(double));
+  A((void**)&s->d_phid, (size_t)(3 * ndIU * ndIU + 3 * ndIU) * sizeof(double));
+  A((void**)&s->d_invd, (size_t)s->nCB * TN * TN * sizeof(double));
+  const size_t nflags = (size_t)s->nRB * s->nCB + s->nCB;
+  A((void**)&s->d_flags, nflags * sizeof(int32_t));
+  A((void**)&s->d_logsum, (size_t)s->nCB * sizeof(double));
+  A((void**)&s->d_G, 64 * 64 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemsetAsync(s->d_flags, 0, nflags * sizeof(int32_t), ctx->stream);
+  if (e != cudaSuccess) {
+    ctx->err = std::string("slot allocation failed: ") + cudaGetErrorString(e);
+    free_slot(s);
+    cudaGetLastError();
+    return IAK3D_ERR_CUDA;
+  }
+  *out = s;
+  return 0;
+}
+void iak_free_slot(Slot* s) { free_slot(s); }
+
+static void ds_geometry(iak3d_ds* ds) {
+  ds->Npad = round_up(std::max<int64_t>(ds->n, 1), TN);
+  ds->ld = round_up(ds->Npad + ds->q, TM);
+  ds->nCB = (int32_t)(ds->Npad / TN); ds->nRB = (int32_t)(ds->ld / TM);
+}
+
+extern "C" int iak3d_dataset_set_W(iak3d_ds* ds, const double* W, int32_t q) {
+  if (!ds) return IAK3D_ERR_ARG;
+  iak3d_ctx* ctx = ds->ctx;
+  if (q < 0 || q > 64 || (q > 0 && W == nullptr)) { ctx->err = "set_W: q must be in [0,64] (p <= 63 fixed effects)"; return IAK3D_ERR_ARG; }
+  cudaSetDevice(ctx->device);
+  if (q != ds->q) {
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (Slot* s : ds->slots) free_slot(s);
+    ds->slots.clear();
+    cudaFree(ds->d_W); ds->d_W = nullptr;
+    ds->q = q;
+    ds_geometry(ds);
+    if (q > 0) CUDA_TRY(ctx, cudaMalloc(&ds->d_W, (size_t)ds->n * q * sizeof(double)));
+  }
+  if (q > 0) {
+    ds->h_W.assign(W, W + (size_t)ds->n * q);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ds->d_W, W, (size_t)ds->n * q * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // the caller's buffer may be reused on return
+  } else {
+    ds->h_W.clear();
+  }
+  return IAK3D_OK;
+}
+
+extern "C" int iak3d_dataset_create(iak3d_ctx* ctx, int64_t n, const double* xy, const double* dI, const double* W, int32_t q,
+                                    iak3d_ds** out) {
+  if (!ctx || !out) return IAK3D_ERR_ARG;
+  *out = nullptr;
+  if (n <= 0 || xy == nullptr || dI == nullptr) { ctx->err = "dataset_create: n > 0, xy and dI are required"; return IAK3D_ERR_ARG; }
+  if (n > (int64_t)1 << 30) { ctx->err = "dataset_create: n too large"; return IAK3D_ERR_ARG; }
+  cudaSetDevice(ctx->device);
+  iak3d_ds* ds = new iak3d_ds();
+  ds->ctx = ctx; ds->n = n; ds->q = -1;
+  iak_unique_first(n, xy, xy + n, ds->h_xid, ds->h_xU);
+  iak_unique_first(n, dI, dI + n, ds->h_did, ds->h_dIU);
+  ds->nxU = (int64_t)ds->h_xU.size() / 2; ds->ndIU = (int64_t)ds->h_dIU.size() / 2;
+  cudaError_t e = cudaSuccess;
+  auto up = [&](void** p, const void* src, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(*p, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  };
+  up((void**)&ds->d_xid, ds->h_xid.data(), (size_t)n * 4);
+  up((void**)&ds->d_did, ds->h_did.data(), (size_t)n * 4);
+  up((void**)&ds->d_xU, ds->h_xU.data(), ds->h_xU.size() * 8);
+  up((void**)&ds->d_dIU, ds->h_dIU.data(), ds->h_dIU.size() * 8);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    ctx->err = std::string("dataset_create: ") + cudaGetErrorString(e);
+    iak3d_dataset_destroy(ds);
+    return IAK3D_ERR_CUDA;
+  }
+  const int st = iak3d_dataset_set_W(ds, W, W ? q : 0);
+  if (st != 0) { iak3d_dataset_destroy(ds); return st; }
+  *out = ds;
+  return IAK3D_OK;
+}
+
+extern "C" int iak3d_dataset_destroy(iak3d_ds* ds) {
+  if (!ds) return IAK3D_OK;
+  cudaSetDevice(ds->ctx->device);
+  cudaStreamSynchronize(ds->ctx->stream);
+  for (Slot* s : ds->slots) free_slot(s);
+  cudaFree(ds->d_xid); cudaFree(ds->d_did); cudaFree(ds->d_xU); cudaFree(ds->d_dIU); cudaFree(ds->d_W);
+  delete ds;
+  return IAK3D_OK;
+}
+
+extern "C" int iak3d_dataset_info(iak3d_ds* ds, int64_t* n, int64_t* nxU, int64_t* ndIU, int32_t* q) {
+  if (!ds) return IAK3D_ERR_ARG;
+  if (n) *n = ds->n;
+  if (nxU) *nxU = ds->nxU;
+  if (ndIU) *ndIU = ds->ndIU;
+  if (q) *q = ds->q;
+  return IAK3D_OK;
+}
+
+extern "C" int iak3d_dataset_ids(iak3d_ds* ds, int32_t* xid, int32_t* did) {
+  if (!ds) return IAK3D_ERR_ARG;
+  if (xid) memcpy(xid, ds->h_xid.data(), (size_t)ds->n * 4);
+  if (did) memcpy(did, ds->h_did.data(), (size_t)ds->n * 4);
+  return IAK3D_OK;
+}
+
+int iak_get_slot(iak3d_ds* ds, size_t k, Slot** out) {
+  while (ds->slots.size() <= k) {
+    Slot* s = nullptr;
+    const int st = iak_alloc_slot(ds->ctx, ds->n, ds->q, ds->nxU, ds->ndIU, &s);
+    if (st != 0) return st;
+    ds->slots.push_back(s);
+  }
+  *out = ds->slots[k];
+  return 0;
+}
+
+// ================================================================================================
+// tables for one evaluation of a dataset (square) into a slot; fills CovArgs
+// ================================================================================================
+int iak_square_tables(iak3d_ctx* ctx, const iak3d_ds* ds, const EvalPlan& pl, Slot* s, CovArgs* a) {
+  const int64_t nd = ds->ndIU, nx = ds->nxU;
+  for (int k = 0; k < 3; k++) a->T[k] = nullptr;
+  for (int k = 0; k < pl.ntab; k++) {
+    double* T = s->d_phid + (size_t)k * nd * nd;
+    double* av = s->d_phid + (size_t)3 * nd * nd + (size_t)k * nd;
+    const int st = launch_iacov_table(ctx, pl.prm[k], ds->d_dIU, nd, ds->d_dIU, nd, T, av);
+    if (st != 0) return st;
+    a->T[k] = T;
+  }
+  for (int c = 0; c < 3; c++) a->tidx[c] = pl.tidx[c];
+  a->ntab = pl.ntab;
+  a->phix = nullptr; a->same = nullptr;
+  if (pl.has_phix) {
+    const int st = launch_phix_table(ctx, pl.H, ds->d_xU, nx, ds->d_xU, nx, s->d_phix, nullptr);
+    if (st != 0) return st;
+    a->phix = s->d_phix;
+  }
+  a->cx0 = pl.cx0; a->cx1 = pl.cx1; a->kd1 = pl.kd1; a->cxd0 = pl.cxd0; a->cxd1 = pl.cxd1; a->cme = pl.cme;
+  a->xid_r = ds->d_xid; a->did_r = ds->d_did; a->xid_c = ds->d_xid; a->did_c = ds->d_did;
+  a->nr = ds->n; a->nc = ds->n; a->nxU_r = nx; a->ndIU_r = nd;
+  return 0;
+}
+
+// ================================================================================================
+// depth / horizontal kernels on caller-supplied unique sets
+// ================================================================================================
+extern "C" int iak3d_iacov(iak3d_ctx* ctx, int64_t n1, const double* dI1, int64_t n2, const double* dI2, double ad, double nud,
+                           int32_t sdfdType, const double* sdfdPars, double* out, double* avVar) {
+  if (!ctx || n1 < 0 || n2 < 0 || (n1 > 0 && !dI1) || (n2 > 0 && !dI2) || !out) return IAK3D_ERR_ARG;
+  IaPrm P;
+  const double s1 = (sdfdType == -1 && sdfdPars) ? sdfdPars[0] : 0.0, s2 = (sdfdType == -1 && sdfdPars) ? sdfdPars[1] : 0.0;
+  if (sdfdType == -1 && !sdfdPars) return IAK3D_ERR_ARG;
+  if (iak_prm_init(&P, ad, nud, sdfdType, s1, s2) != 0) return IAK3D_BAD_PARS;
+  if (n1 == 0 || n2 == 0) return IAK3D_OK;
+  cudaSetDevice(ctx->device);
+  double *d1 = nullptr, *d2 = nullptr, *dout = nullptr, *dav = nullptr;
+  int rc = IAK3D_OK;
+  do {
+    if (cudaMalloc(&d1, (size_t)n1 * 16) != cudaSuccess || cudaMalloc(&d2, (size_t)n2 * 16) != cudaSuccess ||
+        cudaMalloc(&dout, (size_t)n1 * n2 * 8) != cudaSuccess || cudaMalloc(&dav, (size_t)n1 * 8) != cudaSuccess) {
+      ctx->err = "iacov: allocation failed"; rc = IAK3D_ERR_CUDA; break;
+    }
+    cudaMemcpyAsync(d1, dI1, (size_t)n1 * 16, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d2, dI2, (size_t)n2 * 16, cudaMemcpyHostToDevice, ctx->stream);
+    rc = launch_iacov_table(ctx, P, d1, n1, d2, n2, dout, dav);
+    if (rc != 0) break;
+    cudaMemcpyAsync(out, dout, (size_t)n1 * n2 * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (avVar) cudaMemcpyAsync(avVar, dav, (size_t)n1 * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ctx->err = std::string("iacov: ") + cudaGetErrorString(e); rc = IAK3D_ERR_CUDA; }
+  } while (0);
+  cudaFree(d1); cudaFree(d2); cudaFree(dout); cudaFree(dav);
+  return rc;
+}
+
+extern "C" int iak3d_spatial_cov(iak3d_ctx* ctx, int64_t m, const double* D, int32_t modelx, double c1, double a, double nu,
+                                 double* out) {
+  if (!ctx || m < 0 || (m > 0 && (!D || !out))) return IAK3D_ERR_ARG;
+  if (modelx < IAK3D_MODELX_SPHERICAL || modelx > IAK3D_MODELX_WENDLAND) return IAK3D_ERR_ARG;
+  if (!(c1 > 0.0)) return IAK3D_BAD_PARS;                              // iaCovMatern.R:335,354,379
+  HxPrm H;
+  if (hx_init(&H, modelx, a, nu) != 0) return IAK3D_BAD_PARS;
+  if (m == 0) return IAK3D_OK;
+  cudaSetDevice(ctx->device);
+  double *dD = nullptr, *dout = nullptr;
+  int rc = IAK3D_OK;
+  do {
+    if (cudaMalloc(&dD, (size_t)m * 8) != cudaSuccess || cudaMalloc(&dout, (size_t)m * 8) != cudaSuccess) {
+      ctx->err = "spatial_cov: allocation failed"; rc = IAK3D_ERR_CUDA; break;
+    }
+    cudaMemcpyAsync(dD, D, (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream);
+    rc = launch_phix_vec(ctx, H, dD, m, dout);
+    if (rc != 0) break;
+    cudaMemcpyAsync(out, dout, (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ctx->err = std::string("spatial_cov: ") + cudaGetErrorString(e); rc = IAK3D_ERR_CUDA; break; }
+    if (c1 != 1.0) for (int64_t i = 0; i < m; i++) out[i] = c1 * out[i];
+  } while (0);
+  cudaFree(dD); cudaFree(dout);
+  return rc;
+}
+
+// ================================================================================================
+// covariance assembly returned to the caller
+// ================================================================================================
+extern "C" int iak3d_cov_build(iak3d_ds* ds, const iak3d_pars* pars, double* C, double* sigma2Vec) {
+  if (!ds || !pars) return IAK3D_ERR_ARG;
+  iak3d_ctx* ctx = ds->ctx;
+  cudaSetDevice(ctx->device);
+  EvalPlan pl;
+  int st = iak_make_plan(ctx, pars, true, &pl);
+  if (st != 0) return st;
+  if (pl.status != 0) return pl.status;
+  Slot* s = nullptr;
+  st = iak_get_slot(ds, 0, &s);
+  if (st != 0) return st;
+  CovArgs a;
+  st = iak_square_tables(ctx, ds, pl, s, &a);
+  if (st != 0) return st;
+  const int64_t n = ds->n;
+  double *dC = nullptr, *ds2 = nullptr;
+  int rc = IAK3D_OK;
+  do {
+    if (C) {
+      if (cudaMalloc(&dC, (size_t)n * n * 8) != cudaSuccess) { ctx->err = "cov_build: allocation failed"; rc = IAK3D_ERR_CUDA; cudaGetLastError(); break; }
+      rc = launch_cov_rect(ctx, a, dC, n, n, n, 1);
+      if (rc != 0) break;
+      cudaMemcpyAsync(C, dC, (size_t)n * n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (sigma2Vec) {
+      if (cudaMalloc(&ds2, (size_t)n * 8) != cudaSuccess) { ctx->err = "cov_build: allocation failed"; rc = IAK3D_ERR_CUDA; cudaGetLastError(); break; }
+      rc = launch_sigma2(ctx, pl, s->d_phid + (size_t)3 * ds->ndIU * ds->ndIU, ds->ndIU, ds->d_did, n, ds2);
+      if (rc != 0) break;
+      cudaMemcpyAsync(sigma2Vec, ds2, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ctx->err = std::string("cov_build: ") + cudaGetErrorString(e); rc = IAK3D_ERR_CUDA; }
+  } while (0);
+  cudaFree(dC); cudaFree(ds2);
+  return rc;
+}
+
+// Cross-covariance tables between set 1 (given as unique tables + ids on the device) and a dataset (set 2).
+// Allocates into *bufs (freed by the caller with cross_free).
+struct CrossBufs {
+  double* d_x1 = nullptr; double* d_d1 = nullptr; int32_t* d_xid1 = nullptr; int32_t* d_did1 = nullptr;
+  double* d_phix = nullptr; uint8_t* d_same = nullptr; double* d_T = nullptr;
+  int64_t nx1 = 0, nd1 = 0;
+};
+void iak_cross_free(CrossBufs* b) {
+  cudaFree(b->d_x1); cudaFree(b->d_d1); cudaFree(b->d_xid1); cudaFree(b->d_did1); cudaFree(b->d_phix); cudaFree(b->d_same);
+  cudaFree(b->d_T);
+  *b = CrossBufs();
+}
+int iak_cross_tables(iak3d_ctx* ctx, const iak3d_ds* ds2, const EvalPlan& pl, int64_t n1, const std::vector<int32_t>& xid1,
+                     const std::vector<double>& xU1, const std::vector<int32_t>& did1, const std::vector<double>& dIU1,
+                     CrossBufs* b, CovArgs* a) {
+  const int64_t nx1 = (int64_t)xU1.size() / 2, nd1 = (int64_t)dIU1.size() / 2;
+  b->nx1 = nx1; b->nd1 = nd1;
+  cudaError_t e = cudaSuccess;
+  auto up = [&](void** p, const void* src, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMalloc(p, std::max<size_t>(bytes, 16));
+    if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(*p, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  };
+  up((void**)&b->d_x1, xU1.data(), xU1.size() * 8);
+  up((void**)&b->d_d1, dIU1.data(), dIU1.size() * 8);
+  up((void**)&b->d_xid1, xid1.data(), (size_t)n1 * 4);
+  up((void**)&b->d_did1, did1.data(), (size_t)n1 * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&b->d_phix, std::max<size_t>((size_t)nx1 * ds2->nxU * 8, 16));
+  if (e == cudaSuccess) e = cudaMalloc(&b->d_same, std::max<size_t>((size_t)nx1 * ds2->nxU, 16));
+  if (e == cudaSuccess) e = cudaMalloc(&b->d_T, std::max<size_t>((size_t)3 * nd1 * ds2->ndIU * 8, 16));
+  if (e != cudaSuccess) { ctx->err = std::string("cross tables: ") + cudaGetErrorString(e); cudaGetLastError(); return IAK3D_ERR_CUDA; }
+  for (int k = 0; k < 3; k++) a->T[k] = nullptr;
+  for (int k = 0; k < pl.ntab; k++) {
+    double* T = b->d_T + (size_t)k * nd1 * ds2->ndIU;
+    const int st = launch_iacov_table(ctx, pl.prm[k], b->d_d1, nd1, ds2->d_dIU, ds2->ndIU, T, nullptr);
+    if (st != 0) return st;
+    a->T[k] = T;
+  }
+  for (int c = 0; c < 3; c++) a->tidx[c] = pl.tidx[c];
+  a->ntab = pl.ntab;
+  // phix0 = 1[Dx == 0] (fitIAK3D.R:1138-1141) always; phix1 unless nugget
+  const int st = launch_phix_table(ctx, pl.H, b->d_x1, nx1, ds2->d_xU, ds2->nxU, pl.has_phix ? b->d_phix : nullptr, b->d_same);
+  if (st != 0) return st;
+  a->phix = pl.has_phix ? b->d_phix : nullptr;
+  a->same = b->d_same;
+  a->cx0 = pl.cx0; a->cx1 = pl.cx1; a->kd1 = pl.kd1; a->cxd0 = pl.cxd0; a->cxd1 = pl.cxd1; a->cme = 0.0;   // no cme (:1243)
+  a->xid_r = b->d_xid1; a->did_r = b->d_did1; a->xid_c = ds2->d_xid; a->did_c = ds2->d_did;
+  a->nr = n1; a->nc = ds2->n; a->nxU_r = nx1; a->ndIU_r = nd1;
+  return 0;
+}
+
+extern "C" int iak3d_cov_cross(iak3d_ds* ds2, const iak3d_pars* pars, int64_t n1, const double* xy1, const double* dI1, double* out) {
+  if (!ds2 || !pars || n1 < 0 || (n1 > 0 && (!xy1 || !dI1 || !out))) return IAK3D_ERR_ARG;
+  iak3d_ctx* ctx = ds2->ctx;
+  cudaSetDevice(ctx->device);
+  EvalPlan pl;
+  int st = iak_make_plan(ctx, pars, false, &pl);
+  if (st != 0) return st;
+  if (pl.status != 0) return pl.status;
+  if (n1 == 0) return IAK3D_OK;
+  std::vector<int32_t> xid1, did1; std::vector<double> xU1, dIU1;
+  iak_unique_first(n1, xy1, xy1 + n1, xid1, xU1);
+  iak_unique_first(n1, dI1, dI1 + n1, did1, dIU1);
+  CrossBufs b; CovArgs a;
+  double* dout = nullptr;
+  int rc = iak_cross_tables(ctx, ds2, pl, n1, xid1, xU1, did1, dIU1, &b, &a);
+  do {
+    if (rc != 0) break;
+    if (cudaMalloc(&dout, (size_t)n1 * ds2->n * 8) != cudaSuccess) { ctx->err = "cov_cross: allocation failed"; rc = IAK3D_ERR_CUDA; cudaGetLastError(); break; }
+    rc = launch_cov_rect(ctx, a, dout, n1, n1, ds2->n, 0);
+    if (rc != 0) break;
+    cudaMemcpyAsync(out, dout, (size_t)n1 * ds2->n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ctx->err = std::string("cov_cross: ") + cudaGetErrorString(e); rc = IAK3D_ERR_CUDA; }
+  } while (0);
+  cudaFree(dout);
+  iak_cross_free(&b);
+  return rc;
+}
+
+// ================================================================================================
+// likelihood terms: the batch pipeline
+// ================================================================================================
+static int batch_reserve(iak3d_ctx* ctx, Batch* b, int32_t count, int32_t q) {
+  if (count > b->probs_cap) {
+    cudaFree(b->d_probs); b->d_probs = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&b->d_probs, (size_t)count * sizeof(ProblemDesc)));
+    b->probs_cap = count;
+  }
+  if (count > b->status_cap) {
+    cudaFree(b->d_status); b->d_status = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&b->d_status, (size_t)count * 2 * sizeof(int32_t)));
+    b->status_cap = count;
+  }
+  const int32_t stride = 2 + q * q;
+  if ((int64_t)count * stride > b->results_cap) {
+    cudaFree(b->d_results); b->d_results = nullptr;
+    if (b->h_results) { cudaFreeHost(b->h_results); b->h_results = nullptr; }
+    CUDA_TRY(ctx, cudaMalloc(&b->d_results, (size_t)count * stride * sizeof(double)));
+    CUDA_TRY(ctx, cudaMallocHost(&b->h_results, (size_t)count * stride * sizeof(double)));
+    b->results_cap = (int64_t)count * stride;
+  }
+  b->stride = stride;
+  return 0;
+}
+
+// Task order: by column block, then problem, then row block.  Every dependency of a task (same problem: earlier
+// columns; the column's own diagonal task) precedes it, which is all the ticket scheduler needs (chol.cu).
+static int batch_tasks(iak3d_ctx* ctx, Batch* b, const std::vector<ProblemDesc>& probs, const std::vector<int>& live) {
+  std::vector<int64_t> key;
+  key.reserve(live.size() * 3);
+  for (size_t i = 0; i < live.size(); i++) { key.push_back(live[i]); key.push_back(probs[i].nCB); key.push_back(probs[i].nRB); }
+  if (key == b->key && b->d_tasks != nullptr) return 0;
+  std::vector<int4> tasks;
+  int maxCB = 0;
+  for (size_t i = 0; i < live.size(); i++) if (live[i]) maxCB = std::max(maxCB, (int)probs[i].nCB);
+  for (int j = 0; j < maxCB; j++)
+    for (size_t i = 0; i < live.size(); i++) {
+      if (!live[i] || j >= probs[i].nCB) continue;
+      for (int r = j / 2; r < probs[i].nRB; r++) tasks.push_back(make_int4((int)i, r, j, 0));
+    }
+  if ((int64_t)tasks.size() > b->tasks_cap) {
+    cudaFree(b->d_tasks); b->d_tasks = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&b->d_tasks, std::max<size_t>(tasks.size(), 1) * sizeof(int4)));
+    b->tasks_cap = (int64_t)tasks.size();
+  }
+  if (!tasks.empty())
+    CUDA_TRY(ctx, cudaMemcpyAsync(b->d_tasks, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  b->ntasks = (int32_t)tasks.size();
+  b->key = key;
+  return 0;
+}
+
+static void fill_problem(ProblemDesc* pd, Slot* s, int32_t* d_status) {
+  pd->L = s->d_L; pd->ldL = s->ld; pd->P = s->d_L; pd->ldP = s->ld;
+  pd->invd = s->d_invd;
+  pd->doneL = s->d_flags; pd->doneP = s->d_flags; pd->invdone = s->d_flags + (size_t)s->nRB * s->nCB;
+  pd->nCB = s->nCB; pd->nRB = s->nRB; pd->mode = 0; pd->epoch = s->epoch;
+  pd->w0 = (int32_t)s->Npad; pd->q = s->q;
+  pd->G = s->d_G; pd->ldG = s->q;
+  pd->logsum = s->d_logsum; pd->status = d_status; pd->YW = nullptr;
+}
+
+extern "C" int iak3d_nll_terms_batch_enqueue(iak3d_ctx* ctx, int32_t count, iak3d_ds* const* dss, const iak3d_pars* pars) {
+  if (!ctx || count <= 0 || !dss || !pars) return IAK3D_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  Batch* b = ctx->batch;
+  if (b->pending) { ctx->err = "nll_terms_batch_enqueue: previous batch not fetched"; return IAK3D_ERR_ARG; }
+  const int32_t q = dss[0]->q;
+  for (int i = 0; i < count; i++) {
+    if (!dss[i] || dss[i]->ctx != ctx) { ctx->err = "batch: dataset belongs to another context"; return IAK3D_ERR_ARG; }
+    if (dss[i]->q != q) { ctx->err = "batch: all datasets must share q"; return IAK3D_ERR_ARG; }
+  }
+  int st = batch_reserve(ctx, b, count, q);
+  if (st != 0) return st;
+  // plans (host) and slots
+  std::vector<EvalPlan> plans((size_t)count);
+  b->ds.assign(dss, dss + count);
+  b->slots.assign((size_t)count, nullptr);
+  b->plan_status.assign((size_t)count, 0);
+  std::unordered_map<iak3d_ds*, size_t> uses;
+  std::vector<int> live((size_t)count, 0);
+  for (int i = 0; i < count; i++) {
+    st = iak_make_plan(ctx, &pars[i], true, &plans[i]);
+    if (st != 0) return st;
+    b->plan_status[i] = plans[i].status;
+    const size_t k = uses[dss[i]]++;
+    st = iak_get_slot(dss[i], k, &b->slots[i]);
+    if (st != 0) return st;
+    live[i] = (plans[i].status == 0);
+  }
+  std::vector<ProblemDesc> probs((size_t)count);
+  double flops = 0.0, bytes = 0.0;
+  for (int i = 0; i < count; i++) {
+    Slot* s = b->slots[i];
+    s->epoch++;
+    fill_problem(&probs[i], s, b->d_status + 2 * i);
+    if (live[i]) { const double n = (double)s->n; flops += n * n * n / 3.0; bytes += 8.0 * n * (n + 1.0) / 2.0; }
+  }
+  st = batch_tasks(ctx, b, probs, live);
+  if (st != 0) return st;
+  ctx->last_chol_flops = flops; ctx->last_cov_bytes = bytes;
+
+  CUDA_TRY(ctx, cudaEventRecord(ctx->evs[0], ctx->stream));
+  std::vector<CovArgs> cargs((size_t)count);
+  for (int i = 0; i < count; i++) {
+    if (!live[i]) continue;
+    st = iak_square_tables(ctx, dss[i], plans[i], b->slots[i], &cargs[i]);
+    if (st != 0) return st;
+  }
+  CUDA_TRY(ctx, cudaEventRecord(ctx->evs[1], ctx->stream));
+  for (int i = 0; i < count; i++) {
+    if (!live[i]) continue;
+    Slot* s = b->slots[i];
+    st = launch_cov_factor_layout(ctx, cargs[i], dss[i]->d_W, q, s->n, s->Npad, s->ld, s->nCB, s->d_L);
+    if (st != 0) return st;
+  }
+  CUDA_TRY(ctx, cudaEventRecord(ctx->evs[2], ctx->stream));
+  CUDA_TRY(ctx, cudaMemsetAsync(b->d_status, 0, (size_t)count * 2 * sizeof(int32_t), ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(b->d_probs, probs.data(), (size_t)count * sizeof(ProblemDesc), cudaMemcpyHostToDevice, ctx->stream));
+  st = launch_tile_tasks(ctx, b->d_probs, b->d_tasks, b->ntasks, b->d_ticket);
+  if (st != 0) return st;
+  CUDA_TRY(ctx, cudaEventRecord(ctx->evs[3], ctx->stream));
+  st = launch_finish(ctx, b->d_probs, count, b->d_results, b->stride);
+  if (st != 0) return st;
+  CUDA_TRY(ctx, cudaMemcpyAsync(b->h_results, b->d_results, (size_t)count * b->stride * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaEventRecord(ctx->evs[4], ctx->stream));
+  ctx->stage_events_valid = true;
+  b->count = count; b->q = q; b->pending = true;
+  return IAK3D_OK;
+}
+
+extern "C" int iak3d_nll_terms_batch_fetch(iak3d_ctx* ctx, double* lndetA, double* WiAW, int32_t* status) {
+  if (!ctx) return IAK3D_ERR_ARG;
+  Batch* b = ctx->batch;
+  if (!b->pending) { ctx->err = "nll_terms_batch_fetch: nothing enqueued"; return IAK3D_ERR_ARG; }
+  b->pending = false;
+  cudaSetDevice(ctx->device);
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  const int q = b->q, qq = q * q;
+  int rc = IAK3D_OK;
+  for (int i = 0; i < b->count; i++) {
+    const double* r = b->h_results + (size_t)i * b->stride;
+    int st = b->plan_status[i];
+    if (st == 0) {
+      const int flags = (int)r[1];
+      if (flags & 2) { ctx->err = "factorisation: dependency wait timed out (internal error)"; rc = IAK3D_ERR_TIMEOUT; st = IAK3D_ERR_TIMEOUT; }
+      else if ((flags & 1) || !isfinite(r[0])) st = IAK3D_NOT_SPD;
+    }
+    if (status) status[i] = st;
+    const double nanv = nan("");
+    if (lndetA) lndetA[i] = (st == 0) ? r[0] : nanv;
+    if (WiAW) for (int e = 0; e < qq; e++) WiAW[(size_t)i * qq + e] = (st == 0) ? r[2 + e] : nanv;
+  }
+  return rc;
+}
+
+extern "C" int iak3d_nll_terms_batch(iak3d_ctx* ctx, int32_t count, iak3d_ds* const* ds, const iak3d_pars* pars, double* lndetA,
+                                     double* WiAW, int32_t* status) {
+  const int st = iak3d_nll_terms_batch_enqueue(ctx, count, ds, pars);
+  if (st != 0) return st;
+  return iak3d_nll_terms_batch_fetch(ctx, lndetA, WiAW, status);
+}
+
+// iAW = A^-1 W from the slot's factor (rows Npad.. hold Y' = (L^-1 W)').  out: n x q column-major (host).
+int iak_backsolve_to_host(iak3d_ctx* ctx, Slot* s, double* out_host, double* d_out_opt) {
+  const int q = s->q;
+  if (q <= 0) return 0;
+  double *dY = nullptr, *dX = nullptr;
+  int rc = 0;
+  do {
+    if (cudaMalloc(&dY, (size_t)q * s->Npad * 8) != cudaSuccess || cudaMalloc(&dX, (size_t)s->Npad * q * 8) != cudaSuccess) {
+      ctx->err = "backsolve: allocation failed"; rc = IAK3D_ERR_CUDA; cudaGetLastError(); break;
+    }
+    // copy the Y' rows (q x Npad, ld = s->ld) into a compact q x Npad buffer
+    if (cudaMemcpy2DAsync(dY, (size_t)q * 8, s->d_L + s->Npad, (size_t)s->ld * 8, (size_t)q * 8, (size_t)s->Npad,
+                          cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) { ctx->err = "backsolve: copy failed"; rc = IAK3D_ERR_CUDA; break; }
+    rc = launch_backsolve(ctx, s->d_L, s->ld, s->Npad, s->d_invd, dY, q, q, dX);
+    if (rc != 0) break;
+    if (out_host)
+      cudaMemcpy2DAsync(out_host, (size_t)s->n * 8, dX, (size_t)s->Npad * 8, (size_t)s->n * 8, (size_t)q, cudaMemcpyDeviceToHost, ctx->stream);
+    if (d_out_opt)
+      cudaMemcpy2DAsync(d_out_opt, (size_t)s->n * 8, dX, (size_t)s->Npad * 8, (size_t)s->n * 8, (size_t)q, cudaMemcpyDeviceToDevice, ctx->stream);
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ctx->err = std::string("backsolve: ") + cudaGetErrorString(e); rc = IAK3D_ERR_CUDA; }
+  } while (0);
+  cudaFree(dY); cudaFree(dX);
+  return rc;
+}
+
+extern "C" int iak3d_nll_terms(iak3d_ds* ds, const iak3d_pars* pars, double* lndetA, double* WiAW, double* iAW) {
+  if (!ds || !pars) return IAK3D_ERR_ARG;
+  iak3d_ctx* ctx = ds->ctx;
+  iak3d_ds* one[1] = {ds};
+  int32_t status = 0;
+  int st = iak3d_nll_terms_batch(ctx, 1, one, pars, lndetA, WiAW, &status);
+  if (st != 0) return st;
+  if (status != 0) return status;
+  if (iAW) st = iak_backsolve_to_host(ctx, ds->slots[0], iAW, nullptr);
+  return st;
+}
+
+// ================================================================================================
+// lndetANDinvCb on a caller-supplied matrix (optim_functions.R:268-312)
+// ================================================================================================
+int iak_factor_slot(iak3d_ctx* ctx, Slot* s, int32_t* status_out, double* lndet_out, double* G_out /* q*q or null */) {
+  Batch* b = ctx->batch;
+  if (b->pending) { ctx->err = "factor: a batch is pending"; return IAK3D_ERR_ARG; }
+  int st = batch_reserve(ctx, b, 1, s->q);
+  if (st != 0) return st;
+  s->epoch++;
+  std::vector<ProblemDesc> probs(1);
+  fill_problem(&probs[0], s, b->d_status);
+  std::vector<int> live(1, 1);
+  st = batch_tasks(ctx, b, probs, live);
+  if (st != 0) return st;
+  CUDA_TRY(ctx, cudaMemsetAsync(b->d_status, 0, 2 * sizeof(int32_t), ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(b->d_probs, probs.data(), sizeof(ProblemDesc), cudaMemcpyHostToDevice, ctx->stream));
+  st = launch_tile_tasks(ctx, b->d_probs, b->d_tasks, b->ntasks, b->d_ticket);
+  if (st != 0) return st;
+  st = launch_finish(ctx, b->d_probs, 1, b->d_results, b->stride);
+  if (st != 0) return st;
+  CUDA_TRY(ctx, cudaMemcpyAsync(b->h_results, b->d_results, (size_t)b->stride * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->stage_events_valid = false;
+  const int flags = (int)b->h_results[1];
+  if (flags & 2) { ctx->err = "factorisation: dependency wait timed out (internal error)"; return IAK3D_ERR_TIMEOUT; }
+  *status_out = ((flags & 1) || !isfinite(b->h_results[0])) ? IAK3D_NOT_SPD : 0;
+  if (lndet_out) *lndet_out = b->h_results[0];
+  if (G_out) for (int e = 0; e < s->q * s->q; e++) G_out[e] = b->h_results[2 + e];
+  return 0;
+}
+
+int iak_inverse_from_factor(iak3d_ctx* ctx, Slot* s, double* d_iC /* n x n */);   // gemm.cu
+
+extern "C" int iak3d_lndet_invCb(iak3d_ctx* ctx, int64_t n, const double* C, int32_t nrhs, const double* b, double* lndetC,
+                                 double* invCb) {
+  if (!ctx || n <= 0 || !C || nrhs < 0 || (nrhs > 0 && !b)) return IAK3D_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  double* dC = nullptr; double* db = nullptr; double* d_iC = nullptr;
+  std::vector<Slot*> made;
+  int rc = IAK3D_OK;
+  const double nanv = nan("");
+  do {
+    if (cudaMalloc(&dC, (size_t)n * n * 8) != cudaSuccess) { ctx->err = "lndet_invCb: allocation failed"; rc = IAK3D_ERR_CUDA; cudaGetLastError(); break; }
+    cudaMemcpyAsync(dC, C, (size_t)n * n * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (nrhs > 0) {
+      if (cudaMalloc(&db, (size_t)n * nrhs * 8) != cudaSuccess) { ctx->err = "lndet_invCb: allocation failed"; rc = IAK3D_ERR_CUDA; cudaGetLastError(); break; }
+      cudaMemcpyAsync(db, b, (size_t)n * nrhs * 8, cudaMemcpyHostToDevice, ctx->stream);
+    }
+    // right-hand sides go through the bordered rows 64 at a time; the first pass also factorises
+    const int npass = nrhs > 0 ? (nrhs + 63) / 64 : 1;
+    for (int ps = 0; ps < npass && rc == 0; ps++) {
+      const int q = nrhs > 0 ? std::min(64, nrhs - ps * 64) : 0;
+      Slot* s = nullptr;
+      rc = iak_alloc_slot(ctx, n, q, 0, 0, &s);
+      if (rc != 0) break;
+      made.push_back(s);
+      rc = launch_pack_factor_layout(ctx, dC, n, db ? db + (size_t)ps * 64 * n : nullptr, q, s->Npad, s->ld, s->d_L);
+      if (rc != 0) break;
+      int32_t status = 0; double lndet = 0.0;
+      rc = iak_factor_slot(ctx, s, &status, &lndet, nullptr);
+      if (rc != 0) break;
+      if (status != 0) {                                            // NA, NA (optim_functions.R:292-294)
+        if (lndetC) *lndetC = nanv;
+        rc = IAK3D_NOT_SPD;
+        break;
+      }
+      if (lndetC) *lndetC = lndet;
+      if (q > 0 && invCb) rc = iak_backsolve_to_host(ctx, s, invCb + (size_t)ps * 64 * n, nullptr);
+      if (nrhs == 0 && invCb) {                                     // chol2inv (optim_functions.R:297)
+        if (cudaMalloc(&d_iC, (size_t)n * n * 8) != cudaSuccess) { ctx->err = "lndet_invCb: allocation failed"; rc = IAK3D_ERR_CUDA; cudaGetLastError(); break; }
+        rc = iak_inverse_from_factor(ctx, s, d_iC);
+        if (rc != 0) break;
+        cudaMemcpyAsync(invCb, d_iC, (size_t)n * n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "lndet_invCb: copy failed"; rc = IAK3D_ERR_CUDA; }
+      }
+      if (ps + 1 < npass) { free_slot(s); made.pop_back(); }
+    }
+  } while (0);
+  cudaStreamSynchronize(ctx->stream);
+  for (Slot* s : made) free_slot(s);
+  cudaFree(dC); cudaFree(db); cudaFree(d_iC);
+  return rc;
+}
+
+// ================================================================================================
+// measurement helpers
+// ================================================================================================
+extern "C" int iak3d_sync(iak3d_ctx* ctx) {
+  if (!ctx) return IAK3D_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return IAK3D_OK;
+}
+extern "C" int iak3d_timer_start(iak3d_ctx* ctx) {
+  if (!ctx) return IAK3D_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  return IAK3D_OK;
+}
+extern "C" int iak3d_timer_stop(iak3d_ctx* ctx, double* ms) {
+  if (!ctx || !ms) return IAK3D_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev1));
+  float f = 0;
+  CUDA_TRY(ctx, cudaEventElapsedTime(&f, ctx->ev0, ctx->ev1));
+  *ms = (double)f;
+  return IAK3D_OK;
+}
+extern "C" int iak3d_flush_l2(iak3d_ctx* ctx) {
+  if (!ctx) return IAK3D_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  const size_t bytes = (size_t)256 << 20;
+  if (!ctx->flush_buf) { CUDA_TRY(ctx, cudaMalloc(&ctx->flush_buf, bytes)); ctx->flush_bytes = bytes; }
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->flush_buf, 0x5a, ctx->flush_bytes, ctx->stream));
+  return IAK3D_OK;
+}
+extern "C" int iak3d_fp64_peak(iak3d_ctx* ctx, int32_t kind, double* tflops) {
+  if (!ctx || !tflops || kind < 0 || kind > 1) return IAK3D_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  return launch_peak(ctx, kind, tflops);
+}
+extern "C" int iak3d_last_stage_ms(iak3d_ctx* ctx, double* ms4, double* chol_flops, double* cov_bytes) {
+  if (!ctx || !ms4) return IAK3D_ERR_ARG;
+  if (!ctx->stage_events_valid) { ctx->err = "last_stage_ms: no batch has been run"; return IAK3D_ERR_ARG; }
+  cudaSetDevice(ctx->device);
+  CUDA_TRY(ctx, cudaEventSynchronize(ctx->evs[4]));
+  for (int i = 0; i < 4; i++) {
+    float f = 0;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&f, ctx->evs[i], ctx->evs[i + 1]));
+    ms4[i] = (double)f;
+  }
+  if (chol_flops) *chol_flops = ctx->last_chol_flops;
+  if (cov_bytes) *cov_bytes = ctx->last_cov_bytes;
+  return IAK3D_OK;
+}

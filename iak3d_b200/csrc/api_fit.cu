@@ -1,0 +1,355 @@
+// api_fit.cu -- the kept fit (big matrices of lmmFit, fitIAK3D.R:919-936) and block kriging
+// (per-batch body of predictIAK3D, predictIAK3D.R:179-255) behind the C ABI.
+//
+// Kriging never forms iC.  With C = L L' kept on the device and Yw = L^-1 [X, z - X betahat] kept in the bordered
+// rows of the factor buffer, a panel of cross-covariance rows Ckh is pushed through the same tile engine as the
+// factorisation (mode 1: X = Ckh L^-T, DMMA), and
+//     Ckh iC X = X Yw(:,1:p),   Ckh iC (z - mu) = X Yw(:,p+1),   rowSums((Ckh iC) * Ckh) = rowSums(X * X)
+// come out of the tile epilogues -- n^2 flops per prediction instead of the reference's 2 n^2.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+// from api.cu
+void iak_unique_first(int64_t n, const double* c0, const double* c1, std::vector<int32_t>& id, std::vector<double>& U);
+int iak_make_plan(iak3d_ctx* ctx, const iak3d_pars* p, bool square, EvalPlan* pl);
+int iak_alloc_slot(iak3d_ctx* ctx, int64_t n, int32_t q, int64_t nxU, int64_t ndIU, Slot** out);
+void iak_free_slot(Slot* s);
+int iak_square_tables(iak3d_ctx* ctx, const iak3d_ds* ds, const EvalPlan& pl, Slot* s, CovArgs* a);
+int iak_factor_slot(iak3d_ctx* ctx, Slot* s, int32_t* status_out, double* lndet_out, double* G_out);
+int iak_backsolve_to_host(iak3d_ctx* ctx, Slot* s, double* out_host, double* d_out_opt);
+int iak_inverse_from_factor(iak3d_ctx* ctx, Slot* s, double* d_iC);
+
+constexpr int64_t PRED_CHUNK = 16384;   // prediction rows per panel (128 row blocks)
+
+struct iak3d_fit {
+  iak3d_ds* ds = nullptr;
+  iak3d_ctx* ctx = nullptr;
+  iak3d_pars pars;
+  EvalPlan plan_sq, plan_x;      // square (Ckk, C) and cross (Ckh) plans of the same parameters
+  Slot* slot = nullptr;          // L, inv diag blocks, Yw rows
+  int32_t p = 0, q = 0;
+  double* d_W2 = nullptr;        // n x q: [X, z - X betahat]
+  double* d_beta = nullptr;      // p
+  double* d_vbeta = nullptr;     // p x p
+  // ---- staged prediction job ----
+  int64_t m = 0;
+  int64_t nd1 = 0;
+  double* d_xy = nullptr;        // per chunk: rows x 2 column-major blocks
+  double* d_X = nullptr;         // m x p column-major
+  int32_t* d_did1 = nullptr;     // m
+  double* d_dIU1 = nullptr;      // nd1 x 2
+  double* d_z = nullptr; double* d_v = nullptr; double* d_ckk = nullptr;
+  int64_t cap_m = 0;
+  // ---- panel workspace (one chunk) ----
+  int64_t ldP = 0;
+  double* d_P = nullptr;         // ldP x Npad
+  double* d_G = nullptr;         // ldP x (q+1)
+  int32_t* d_pflags = nullptr;   // (ldP/TM) x nCB
+  int32_t pepoch = 0;
+  double* d_phix = nullptr; uint8_t* d_same = nullptr;   // ldP x nxU2
+  double* d_T = nullptr;         // 3 x nd1cap x ndIU2
+  double* d_Tself = nullptr;     // 3 x nd1cap x nd1cap
+  int64_t nd1cap = 0;
+  int32_t* d_iota = nullptr;     // 0..ldP-1
+  ProblemDesc* d_prob = nullptr;
+  int4* d_tasks = nullptr; int32_t ntasks = 0; int64_t tasks_rows = 0;
+  int32_t* d_ticket = nullptr; int32_t* d_status = nullptr; int32_t* h_status = nullptr;
+  bool staged = false, enqueued = false;
+};
+
+static void fit_free_job(iak3d_fit* f) {
+  cudaFree(f->d_xy); cudaFree(f->d_X); cudaFree(f->d_did1); cudaFree(f->d_dIU1); cudaFree(f->d_z); cudaFree(f->d_v); cudaFree(f->d_ckk);
+  f->d_xy = f->d_X = f->d_dIU1 = f->d_z = f->d_v = f->d_ckk = nullptr; f->d_did1 = nullptr; f->cap_m = 0;
+}
+static void fit_free_panel(iak3d_fit* f) {
+  cudaFree(f->d_P); cudaFree(f->d_G); cudaFree(f->d_pflags); cudaFree(f->d_phix); cudaFree(f->d_same); cudaFree(f->d_T);
+  cudaFree(f->d_Tself); cudaFree(f->d_iota); cudaFree(f->d_tasks);
+  f->d_P = f->d_G = f->d_phix = f->d_T = f->d_Tself = nullptr; f->d_pflags = nullptr; f->d_same = nullptr; f->d_iota = nullptr;
+  f->d_tasks = nullptr; f->ldP = 0; f->nd1cap = 0; f->tasks_rows = 0;
+}
+
+extern "C" int iak3d_fit_destroy(iak3d_fit* f) {
+  if (!f) return IAK3D_OK;
+  cudaSetDevice(f->ctx->device);
+  cudaStreamSynchronize(f->ctx->stream);
+  fit_free_job(f); fit_free_panel(f);
+  iak_free_slot(f->slot);
+  cudaFree(f->d_W2); cudaFree(f->d_beta); cudaFree(f->d_vbeta); cudaFree(f->d_prob); cudaFree(f->d_ticket); cudaFree(f->d_status);
+  if (f->h_status) cudaFreeHost(f->h_status);
+  delete f;
+  return IAK3D_OK;
+}
+
+extern "C" int iak3d_fit_create(iak3d_ds* ds, const iak3d_pars* pars, const double* betahat, const double* vbetahat, iak3d_fit** out) {
+  if (!ds || !pars || !out) return IAK3D_ERR_ARG;
+  *out = nullptr;
+  iak3d_ctx* ctx = ds->ctx;
+  if (ds->q < 2 || !betahat || !vbetahat) { ctx->err = "fit_create: the dataset needs W = [X z] and betahat / vbetahat"; return IAK3D_ERR_ARG; }
+  cudaSetDevice(ctx->device);
+  iak3d_fit* f = new iak3d_fit();
+  f->ds = ds; f->ctx = ctx; f->pars = *pars; f->q = ds->q; f->p = ds->q - 1;
+  int rc = iak_make_plan(ctx, pars, true, &f->plan_sq);
+  if (rc == 0) rc = iak_make_plan(ctx, pars, false, &f->plan_x);
+  if (rc == 0 && f->plan_sq.status != 0) rc = f->plan_sq.status;
+  if (rc != 0) { delete f; return rc; }
+  const int64_t n = ds->n; const int p = f->p, q = f->q;
+  // W2 = [X, z - X betahat]  (predictIAK3D.R:111,134)
+  std::vector<double> W2(ds->h_W);
+  for (int64_t i = 0; i < n; i++) {
+    double mu = 0.0;
+    for (int a = 0; a < p; a++) mu = mu + ds->h_W[(size_t)a * n + i] * betahat[a];
+    W2[(size_t)p * n + i] = ds->h_W[(size_t)p * n + i] - mu;
+  }
+  do {
+    cudaError_t e = cudaMalloc(&f->d_W2, (size_t)n * q * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_beta, (size_t)p * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_vbeta, (size_t)p * p * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_prob, sizeof(ProblemDesc));
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_ticket, 2 * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_status, 2 * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMallocHost(&f->h_status, 2 * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(f->d_W2, W2.data(), (size_t)n * q * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(f->d_beta, betahat, (size_t)p * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(f->d_vbeta, vbetahat, (size_t)p * p * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ctx->err = std::string("fit_create: ") + cudaGetErrorString(e); rc = IAK3D_ERR_CUDA; cudaGetLastError(); break; }
+    rc = iak_alloc_slot(ctx, n, q, ds->nxU, ds->ndIU, &f->slot);
+    if (rc != 0) break;
+    CovArgs a;
+    rc = iak_square_tables(ctx, ds, f->plan_sq, f->slot, &a);
+    if (rc != 0) break;
+    Slot* s = f->slot;
+    rc = launch_cov_factor_layout(ctx, a, f->d_W2, q, s->n, s->Npad, s->ld, s->nCB, s->d_L);
+    if (rc != 0) break;
+    int32_t status = 0;
+    rc = iak_factor_slot(ctx, s, &status, nullptr, nullptr);
+    if (rc != 0) break;
+    if (status != 0) { rc = status; break; }
+  } while (0);
+  if (rc != 0) { iak3d_fit_destroy(f); return rc; }
+  *out = f;
+  return IAK3D_OK;
+}
+
+extern "C" int iak3d_fit_get(iak3d_fit* f, double* iCX, double* iCz_muhat, double* C, double* iC) {
+  if (!f) return IAK3D_ERR_ARG;
+  iak3d_ctx* ctx = f->ctx;
+  cudaSetDevice(ctx->device);
+  const int64_t n = f->ds->n; const int p = f->p, q = f->q;
+  int rc = IAK3D_OK;
+  if (iCX || iCz_muhat) {
+    std::vector<double> tmp((size_t)n * q);
+    rc = iak_backsolve_to_host(ctx, f->slot, tmp.data(), nullptr);
+    if (rc != 0) return rc;
+    if (iCX) memcpy(iCX, tmp.data(), (size_t)n * p * 8);
+    if (iCz_muhat) memcpy(iCz_muhat, tmp.data() + (size_t)n * p, (size_t)n * 8);
+  }
+  if (C || iC) {
+    double* d = nullptr;
+    if (cudaMalloc(&d, (size_t)n * n * 8) != cudaSuccess) { ctx->err = "fit_get: allocation failed"; cudaGetLastError(); return IAK3D_ERR_CUDA; }
+    do {
+      if (C) {
+        // the tables of the slot are still those of the fit parameters
+        CovArgs a;
+        rc = iak_square_tables(ctx, f->ds, f->plan_sq, f->slot, &a);
+        if (rc != 0) break;
+        rc = launch_cov_rect(ctx, a, d, n, n, n, 1);
+        if (rc != 0) break;
+        cudaMemcpyAsync(C, d, (size_t)n * n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "fit_get: copy failed"; rc = IAK3D_ERR_CUDA; break; }
+      }
+      if (iC) {
+        rc = iak_inverse_from_factor(ctx, f->slot, d);
+        if (rc != 0) break;
+        cudaMemcpyAsync(iC, d, (size_t)n * n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "fit_get: copy failed"; rc = IAK3D_ERR_CUDA; break; }
+      }
+    } while (0);
+    cudaFree(d);
+  }
+  return rc;
+}
+
+// ---- panel workspace ----------------------------------------------------------------------------
+static int fit_reserve_panel(iak3d_fit* f, int64_t rows, int64_t nd1) {
+  iak3d_ctx* ctx = f->ctx;
+  Slot* s = f->slot;
+  const int64_t ldP = round_up(rows, TM);
+  if (ldP > f->ldP) {
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(f->d_P); cudaFree(f->d_G); cudaFree(f->d_pflags); cudaFree(f->d_phix); cudaFree(f->d_same); cudaFree(f->d_iota);
+    f->d_P = f->d_G = f->d_phix = nullptr; f->d_pflags = nullptr; f->d_same = nullptr; f->d_iota = nullptr; f->ldP = 0;
+    CUDA_TRY(ctx, cudaMalloc(&f->d_P, (size_t)ldP * s->Npad * 8));
+    CUDA_TRY(ctx, cudaMalloc(&f->d_G, (size_t)ldP * (f->q + 1) * 8));
+    const size_t nfl = (size_t)(ldP / TM) * s->nCB;
+    CUDA_TRY(ctx, cudaMalloc(&f->d_pflags, nfl * 4));
+    CUDA_TRY(ctx, cudaMemsetAsync(f->d_pflags, 0, nfl * 4, ctx->stream));
+    f->pepoch = 0;
+    CUDA_TRY(ctx, cudaMalloc(&f->d_phix, (size_t)ldP * f->ds->nxU * 8));
+    CUDA_TRY(ctx, cudaMalloc(&f->d_same, (size_t)ldP * f->ds->nxU));
+    std::vector<int32_t> iota((size_t)ldP);
+    for (int64_t i = 0; i < ldP; i++) iota[(size_t)i] = (int32_t)i;
+    CUDA_TRY(ctx, cudaMalloc(&f->d_iota, (size_t)ldP * 4));
+    CUDA_TRY(ctx, cudaMemcpyAsync(f->d_iota, iota.data(), (size_t)ldP * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    f->ldP = ldP;
+  }
+  if (nd1 > f->nd1cap) {
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(f->d_T); cudaFree(f->d_Tself); f->d_T = f->d_Tself = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&f->d_T, (size_t)3 * nd1 * f->ds->ndIU * 8));
+    CUDA_TRY(ctx, cudaMalloc(&f->d_Tself, (size_t)3 * nd1 * nd1 * 8));
+    f->nd1cap = nd1;
+  }
+  return 0;
+}
+
+static int fit_panel_tasks(iak3d_fit* f, int64_t rowsP) {
+  iak3d_ctx* ctx = f->ctx;
+  if (f->tasks_rows == rowsP && f->d_tasks) return 0;
+  const int nRBp = (int)(rowsP / TM), nCB = f->slot->nCB;
+  std::vector<int4> tasks;
+  tasks.reserve((size_t)nRBp * nCB);
+  for (int j = 0; j < nCB; j++)
+    for (int r = 0; r < nRBp; r++) tasks.push_back(make_int4(0, r, j, 0));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(f->d_tasks); f->d_tasks = nullptr;
+  CUDA_TRY(ctx, cudaMalloc(&f->d_tasks, tasks.size() * sizeof(int4)));
+  CUDA_TRY(ctx, cudaMemcpyAsync(f->d_tasks, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  f->ntasks = (int32_t)tasks.size();
+  f->tasks_rows = rowsP;
+  return 0;
+}
+
+extern "C" int iak3d_predict_stage(iak3d_fit* f, int64_t m, const double* xyMap, const double* dIMap, const double* XMap) {
+  if (!f || m < 0 || (m > 0 && (!xyMap || !dIMap || !XMap))) return IAK3D_ERR_ARG;
+  iak3d_ctx* ctx = f->ctx;
+  cudaSetDevice(ctx->device);
+  f->staged = false; f->enqueued = false;
+  f->m = m;
+  if (m == 0) { f->staged = true; return IAK3D_OK; }
+  const int p = f->p;
+  if (m > f->cap_m) {
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    fit_free_job(f);
+    CUDA_TRY(ctx, cudaMalloc(&f->d_xy, (size_t)m * 16));
+    CUDA_TRY(ctx, cudaMalloc(&f->d_X, (size_t)m * p * 8));
+    CUDA_TRY(ctx, cudaMalloc(&f->d_did1, (size_t)m * 4));
+    CUDA_TRY(ctx, cudaMalloc(&f->d_z, (size_t)m * 8));
+    CUDA_TRY(ctx, cudaMalloc(&f->d_v, (size_t)m * 8));
+    CUDA_TRY(ctx, cudaMalloc(&f->d_ckk, (size_t)m * 8));
+    f->cap_m = m;
+  }
+  // unique depth intervals of the map supports (usually one per call: predictIAK3D.R:150)
+  std::vector<int32_t> did1; std::vector<double> dIU1;
+  iak_unique_first(m, dIMap, dIMap + m, did1, dIU1);
+  f->nd1 = (int64_t)dIU1.size() / 2;
+  cudaFree(f->d_dIU1); f->d_dIU1 = nullptr;
+  CUDA_TRY(ctx, cudaMalloc(&f->d_dIU1, dIU1.size() * 8));
+  CUDA_TRY(ctx, cudaMemcpyAsync(f->d_dIU1, dIU1.data(), dIU1.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(f->d_did1, did1.data(), (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
+  // coordinates: one (rows x 2) column-major block per chunk
+  for (int64_t r0 = 0; r0 < m; r0 += PRED_CHUNK) {
+    const int64_t rows = std::min(PRED_CHUNK, m - r0);
+    CUDA_TRY(ctx, cudaMemcpyAsync(f->d_xy + 2 * r0, xyMap + r0, (size_t)rows * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(f->d_xy + 2 * r0 + rows, xyMap + m + r0, (size_t)rows * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CUDA_TRY(ctx, cudaMemcpyAsync(f->d_X, XMap, (size_t)m * p * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  int rc = fit_reserve_panel(f, std::min(PRED_CHUNK, m), f->nd1);
+  if (rc != 0) return rc;
+  f->staged = true;
+  return IAK3D_OK;
+}
+
+extern "C" int iak3d_predict_enqueue(iak3d_fit* f) {
+  if (!f) return IAK3D_ERR_ARG;
+  iak3d_ctx* ctx = f->ctx;
+  if (!f->staged) { ctx->err = "predict_enqueue: nothing staged"; return IAK3D_ERR_ARG; }
+  cudaSetDevice(ctx->device);
+  f->enqueued = true;
+  const int64_t m = f->m;
+  if (m == 0) return IAK3D_OK;
+  Slot* s = f->slot;
+  iak3d_ds* ds = f->ds;
+  const int64_t nd1 = f->nd1, nd2 = ds->ndIU;
+  const EvalPlan& px = f->plan_x; const EvalPlan& ps = f->plan_sq;
+  int rc;
+  // depth tables: cross (nd1 x nd2) and self (nd1 x nd1, for Ckk)
+  CovArgs a;
+  const double* Tself[3] = {nullptr, nullptr, nullptr};
+  for (int k = 0; k < 3; k++) a.T[k] = nullptr;
+  for (int k = 0; k < px.ntab; k++) {
+    double* T = f->d_T + (size_t)k * nd1 * nd2;
+    rc = launch_iacov_table(ctx, px.prm[k], f->d_dIU1, nd1, ds->d_dIU, nd2, T, nullptr);
+    if (rc != 0) return rc;
+    a.T[k] = T;
+    double* Ts = f->d_Tself + (size_t)k * nd1 * nd1;
+    rc = launch_iacov_table(ctx, ps.prm[k], f->d_dIU1, nd1, f->d_dIU1, nd1, Ts, nullptr);
+    if (rc != 0) return rc;
+    Tself[k] = Ts;
+  }
+  rc = launch_ckk(ctx, ps, Tself, nd1, f->d_did1, m, f->d_ckk);
+  if (rc != 0) return rc;
+  for (int c = 0; c < 3; c++) a.tidx[c] = px.tidx[c];
+  a.ntab = px.ntab;
+  a.cx0 = px.cx0; a.cx1 = px.cx1; a.kd1 = px.kd1; a.cxd0 = px.cxd0; a.cxd1 = px.cxd1; a.cme = 0.0;
+  a.xid_c = ds->d_xid; a.did_c = ds->d_did; a.nc = ds->n; a.ndIU_r = nd1;
+  CUDA_TRY(ctx, cudaMemsetAsync(f->d_status, 0, 2 * sizeof(int32_t), ctx->stream));
+  for (int64_t r0 = 0; r0 < m; r0 += PRED_CHUNK) {
+    const int64_t rows = std::min(PRED_CHUNK, m - r0);
+    const int64_t rowsP = round_up(rows, TM);
+    // horizontal tables of this chunk: every map row is its own location
+    rc = launch_phix_table(ctx, px.H, f->d_xy + 2 * r0, rows, ds->d_xU, ds->nxU, px.has_phix ? f->d_phix : nullptr, f->d_same);
+    if (rc != 0) return rc;
+    a.phix = px.has_phix ? f->d_phix : nullptr;
+    a.same = f->d_same;
+    a.xid_r = f->d_iota; a.did_r = f->d_did1 + r0; a.nr = rows; a.nxU_r = rows;
+    rc = launch_cov_rect(ctx, a, f->d_P, rowsP, rowsP, s->Npad, 0);
+    if (rc != 0) return rc;
+    rc = fit_panel_tasks(f, rowsP);
+    if (rc != 0) return rc;
+    ProblemDesc pd;
+    pd.L = s->d_L; pd.ldL = s->ld; pd.P = f->d_P; pd.ldP = rowsP; pd.invd = s->d_invd;
+    pd.doneL = nullptr; pd.doneP = f->d_pflags; pd.invdone = nullptr;
+    pd.nCB = s->nCB; pd.nRB = (int32_t)(rowsP / TM); pd.mode = 1; pd.epoch = ++f->pepoch;
+    pd.w0 = 0; pd.q = f->q; pd.G = f->d_G; pd.ldG = rowsP; pd.logsum = nullptr; pd.status = f->d_status;
+    pd.YW = s->d_L + s->Npad;
+    CUDA_TRY(ctx, cudaMemcpyAsync(f->d_prob, &pd, sizeof(pd), cudaMemcpyHostToDevice, ctx->stream));
+    rc = launch_tile_tasks(ctx, f->d_prob, f->d_tasks, f->ntasks, f->d_ticket);
+    if (rc != 0) return rc;
+    rc = launch_krige_finish(ctx, f->d_G, rowsP, f->q, f->d_X + r0, m, rows, f->d_ckk + r0, f->d_beta, f->d_vbeta, f->d_z + r0,
+                             f->d_v + r0);
+    if (rc != 0) return rc;
+  }
+  CUDA_TRY(ctx, cudaMemcpyAsync(f->h_status, f->d_status, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  return IAK3D_OK;
+}
+
+extern "C" int iak3d_predict_fetch(iak3d_fit* f, double* z, double* v) {
+  if (!f) return IAK3D_ERR_ARG;
+  iak3d_ctx* ctx = f->ctx;
+  if (!f->enqueued) { ctx->err = "predict_fetch: nothing enqueued"; return IAK3D_ERR_ARG; }
+  cudaSetDevice(ctx->device);
+  f->enqueued = false;
+  if (f->m == 0) return IAK3D_OK;
+  if (z) CUDA_TRY(ctx, cudaMemcpyAsync(z, f->d_z, (size_t)f->m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (v) CUDA_TRY(ctx, cudaMemcpyAsync(v, f->d_v, (size_t)f->m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (f->h_status[1] != 0) { ctx->err = "kriging: dependency wait timed out (internal error)"; return IAK3D_ERR_TIMEOUT; }
+  return IAK3D_OK;
+}
+
+extern "C" int iak3d_predict(iak3d_fit* f, int64_t m, const double* xyMap, const double* dIMap, const double* XMap, double* z,
+                             double* v) {
+  int rc = iak3d_predict_stage(f, m, xyMap, dIMap, XMap);
+  if (rc != 0) return rc;
+  rc = iak3d_predict_enqueue(f);
+  if (rc != 0) return rc;
+  return iak3d_predict_fetch(f, z, v);
+}

@@ -1,0 +1,513 @@
+// chol.cu -- the factorisation engine: a persistent, ticket-scheduled, left-looking tile Cholesky
+// whose update GEMMs run on the FP64 tensor pipe (DMMA, mma.sync.m8n8k4.f64) and whose operands are
+// staged by the TMA engine (cp.async.bulk + mbarrier), one CTA per SM.
+//
+// It replaces  chol() + forwardsolve()  of lndetANDinvCb (optim_functions.R:292-302) and the
+// t(W) %*% iAW product of nllIAK3D (fitIAK3D.R:810), and -- run on extra "bordered" row panels --
+// the  Ckh %*% iC  products of predictIAK3D (predictIAK3D.R:202-208).
+//
+// Data layout.  The factor buffer is column-major with leading dimension ld (multiple of TM):
+//   rows [0,n) x cols [0,n)            lower triangle of A, overwritten by L
+//   rows/cols [n,Npad)                 identity padding (Npad = n rounded up to TN)
+//   rows [Npad,Npad+q) x cols [0,Npad) W' (q = p+1 rows), overwritten by Y' = W' L^-T
+// so that sum_j Y_j' Y_j = W' A^-1 W comes out of the same sweep ("bordered" Cholesky).
+//
+// Tiles are TM x TN = 128 x 64.  Task (r, j) owns tile rows [128r,128r+128) x cols [64j,64j+64):
+//   acc = A_tile - sum_{k<j} L(r,k) L(jrows,k)'          K-loop, DMMA, operands via TMA bulk copies
+//   diagonal tile:  potf2 of the 64x64 block fused with its inverse (shared memory)
+//   all other rows: X = acc * inv(L_jj)'                  DMMA
+// Dependencies are per-tile epoch flags in global memory (release/acquire); tasks are claimed from
+// an atomic ticket in column-major (topological) order, so a waiting CTA only ever waits for a CTA
+// that already holds an earlier ticket: no deadlock, no co-residency requirement.
+#include "common.cuh"
+
+namespace {
+
+constexpr int KC = 32;                 // k-depth of one pipeline stage
+constexpr int STAGES = 3;
+constexpr int LDA_S = TM + 4;          // 132: conflict-free DMMA A-fragment loads (stride = 4 mod 16)
+constexpr int LDB_S = TN + 4;          // 68
+constexpr int A_STAGE = KC * LDA_S;
+constexpr int B_STAGE = KC * LDB_S;
+constexpr int STAGE_D = A_STAGE + B_STAGE;          // doubles per stage (51,200 B)
+constexpr int AT_D = TN * LDA_S;                    // the task's own tile (67,584 B)
+constexpr int SMEM_BYTES = (STAGES * STAGE_D + AT_D) * 8;   // 221,184 B
+constexpr int NCW = 8;                 // consumer (MMA) warps: 4 (rows) x 2 (cols), 32x32 each
+constexpr int NTHREADS = (NCW + 1) * 32;
+constexpr unsigned long long WAIT_TIMEOUT_NS = 4000000000ull;
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t;
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+               : "=r"(ok) : "r"(s_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol error turns into status[1] = 1 instead of a hung GPU
+__device__ __forceinline__ int ld_volatile(const int32_t* p) {
+  int v; asm volatile("ld.volatile.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int32_t* status, int32_t* abort_flag) {
+  if (mbar_try(bar, parity)) return;
+  const unsigned long long t0 = gtime();
+  uint32_t spins = 0;
+  while (!mbar_try(bar, parity)) {
+    if ((++spins & 1023u) == 0) {
+      if (ld_volatile(abort_flag) != 0) return;
+      if (gtime() - t0 > WAIT_TIMEOUT_NS) { atomicExch(status + 1, 1); atomicExch(abort_flag, 1); return; }
+    }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_u32(dst)),
+               "l"(src), "r"(bytes), "r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ int ld_acquire(const int32_t* p) {
+  int v; asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release(int32_t* p, int v) {
+  asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void wait_flag(const int32_t* f, int epoch, int32_t* status, int32_t* abort_flag) {
+  if (ld_acquire(f) == epoch) return;
+  const unsigned long long t0 = gtime();
+  uint32_t spins = 0;
+  while (ld_acquire(f) != epoch) {
+    __nanosleep(40);
+    if ((++spins & 63u) == 0) {
+      if (ld_volatile(abort_flag) != 0) return;
+      if (gtime() - t0 > WAIT_TIMEOUT_NS) { atomicExch(status + 1, 1); atomicExch(abort_flag, 1); return; }
+    }
+  }
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory"); }
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// one k4 step of a warp's 32x32 sub-tile: A k-major (stride lda), B k-major (stride ldb)
+__device__ __forceinline__ void warp_mma_k4(double (&acc)[4][4][2], const double* __restrict__ As, int lda,
+                                            const double* __restrict__ Bs, int ldb, int k0, int wm, int wn, int lane) {
+  const int kq = lane & 3, rq = lane >> 2;
+  double a[4], b[4];
+#pragma unroll
+  for (int mi = 0; mi < 4; mi++) a[mi] = As[(k0 + kq) * lda + wm * 32 + mi * 8 + rq];
+#pragma unroll
+  for (int ni = 0; ni < 4; ni++) b[ni] = Bs[(k0 + kq) * ldb + wn * 32 + ni * 8 + rq];
+#pragma unroll
+  for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+}
+
+// Cholesky of the 64x64 block D (rows off.. of the tile in At) fused with its inverse (into Ys).
+// Right-looking, one CTA barrier per column.  D(r,c) = At[c*LDA_S + off + r]; Y(r,c) = Ys[c*LDB_S + r].
+__device__ void potf2_inv(double* __restrict__ At, int off, double* __restrict__ Ys, int tid, double* logsum_out,
+                          int32_t* status) {
+  const int rr = tid & 63, g = tid >> 6;
+  for (int idx = tid; idx < TN * TN; idx += NCW * 32) Ys[(idx >> 6) * LDB_S + (idx & 63)] = ((idx >> 6) == (idx & 63)) ? 1.0 : 0.0;
+  consumer_bar();
+  double lsum = 0.0;
+  bool bad = false;
+  double* Dr = At + off + rr;
+  for (int c = 0; c < TN; c++) {
+    const double d = At[c * LDA_S + off + c];
+    if (!(d > 0.0) || isinf(d)) bad = true;
+    const double rs = rsqrt(d);
+    if (tid == 0) lsum += log(d);
+    const double lrc = Dr[c * LDA_S] * rs;
+    if (rr > c) {
+      for (int c2 = c + 1 + g; c2 <= rr; c2 += 4) Dr[c2 * LDA_S] -= lrc * (At[c * LDA_S + off + c2] * rs);
+      for (int k = g; k <= c; k += 4) Ys[k * LDB_S + rr] -= lrc * (Ys[k * LDB_S + c] * rs);
+    }
+    consumer_bar();
+    if (g == 0) Dr[c * LDA_S] = (rr > c) ? lrc : ((rr == c) ? d * rs : 0.0);
+    if (g == 1 && rr <= c) Ys[rr * LDB_S + c] *= rs;
+  }
+  consumer_bar();
+  if (tid == 0) { *logsum_out = lsum; if (bad) atomicExch(status, 1); }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__ tasks, int ntasks, int32_t* ticket) {
+  extern __shared__ __align__(128) double smem[];
+  double* At = smem + STAGES * STAGE_D;
+  double* Ys = smem;                           // stage 0 is free once the K-loop has drained
+  double* Ws = smem + STAGE_D;                 // stage 1: W rows of the factor for the kriging epilogue
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t at_bar;
+  __shared__ int s_task;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NCW); }
+    mbar_init(&at_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  int32_t* const abort_flag = ticket + 1;   // set by the first CTA whose bounded wait expired
+  uint32_t it = 0;          // pipeline chunk counter, identical in every thread
+  uint32_t at_phase = 0;
+
+  while (true) {
+    if (tid == 0) s_task = (ld_volatile(abort_flag) != 0) ? ntasks : atomicAdd(ticket, 1);
+    __syncthreads();
+    const int t = s_task;
+    if (t >= ntasks) break;
+    const int4 tk = tasks[t];
+    const ProblemDesc* pb = probs + tk.x;
+    const int r = tk.y, j = tk.z;
+    double* __restrict__ L = pb->L; const int64_t ldL = pb->ldL;
+    double* __restrict__ P = pb->P; const int64_t ldP = pb->ldP;
+    const int nCB = pb->nCB, mode = pb->mode, epoch = pb->epoch;
+    int32_t* status = pb->status;
+    const int64_t R0 = (int64_t)r * TM, C0 = (int64_t)j * TN;
+    const int nchunks = j * (TN / KC);
+    const uint32_t it0 = it;
+
+    if (warp == NCW) {
+      // ===================== producer: TMA bulk copies =====================
+      if (lane == 0) {
+        // generic-proxy accesses of the previous task (epilogue reads/writes of At, Ys) were ordered by the
+        // end-of-task __syncthreads; make them visible to the async proxy before it overwrites smem.
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&at_bar, TN * TM * 8);
+        for (int c = 0; c < TN; c++) bulk_g2s(At + c * LDA_S, P + (C0 + c) * ldP + R0, TM * 8, &at_bar);
+        uint32_t itp = it0;
+        for (int c = 0; c < nchunks; c++, itp++) {
+          const int k = c >> 1;
+          if ((c & 1) == 0) {
+            wait_flag(pb->doneP + (int64_t)r * nCB + k, epoch, status, abort_flag);
+            if (mode == 0) wait_flag(pb->doneL + (int64_t)(j >> 1) * nCB + k, epoch, status, abort_flag);
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+          }
+          const uint32_t s = itp % STAGES, use = itp / STAGES;
+          if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1, status, abort_flag);
+          mbar_expect_tx(&full_bar[s], KC * (TM + TN) * 8);
+          double* As = smem + s * STAGE_D;
+          double* Bs = As + A_STAGE;
+          const int64_t col0 = (int64_t)k * TN + (c & 1) * KC;
+          const double* srcA = P + col0 * ldP + R0;
+          const double* srcB = L + col0 * ldL + C0;
+#pragma unroll 4
+          for (int kk = 0; kk < KC; kk++) {
+            bulk_g2s(As + kk * LDA_S, srcA + kk * ldP, TM * 8, &full_bar[s]);
+            bulk_g2s(Bs + kk * LDB_S, srcB + kk * ldL, TN * 8, &full_bar[s]);
+          }
+        }
+      }
+      __syncwarp();
+    } else {
+      // ===================== consumers: DMMA K-loop + epilogue =====================
+      const int wm = warp & 3, wn = warp >> 2;
+      double acc[4][4][2];
+#pragma unroll
+      for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+      uint32_t itc = it0;
+      for (int c = 0; c < nchunks; c++, itc++) {
+        const uint32_t s = itc % STAGES;
+        mbar_wait(&full_bar[s], (itc / STAGES) & 1, status, abort_flag);
+        const double* As = smem + s * STAGE_D;
+        const double* Bs = As + A_STAGE;
+#pragma unroll
+        for (int k4 = 0; k4 < KC / 4; k4++) warp_mma_k4(acc, As, LDA_S, Bs, LDB_S, k4 * 4, wm, wn, lane);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+      }
+      // ---- E1: tile = A - acc (in shared memory) ----
+      mbar_wait(&at_bar, at_phase, status, abort_flag);
+      {
+        const int kq = lane & 3, rq = lane >> 2;
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+          for (int ni = 0; ni < 4; ni++) {
+            const int row = wm * 32 + mi * 8 + rq, col = wn * 32 + ni * 8 + kq * 2;
+            At[col * LDA_S + row] -= acc[mi][ni][0];
+            At[(col + 1) * LDA_S + row] -= acc[mi][ni][1];
+          }
+      }
+      consumer_bar();
+      // ---- E2: diagonal block or fetch of the inverted diagonal block ----
+      int row_lo = 0;
+      const bool is_diag = (mode == 0) && (r == (j >> 1));
+      if (is_diag) {
+        const int off = (j & 1) * TN;
+        potf2_inv(At, off, Ys, tid, pb->logsum + j, status);
+        double* invd = pb->invd + (int64_t)j * TN * TN;
+        for (int idx = tid; idx < TN * TN; idx += NCW * 32) invd[idx] = Ys[(idx >> 6) * LDB_S + (idx & 63)];
+        for (int idx = tid; idx < TN * (TN / 2); idx += NCW * 32) {
+          const int c = idx >> 5, rp = (idx & 31) * 2;
+          const double2 v = *reinterpret_cast<const double2*>(At + c * LDA_S + off + rp);
+          *reinterpret_cast<double2*>(P + (C0 + c) * ldP + R0 + off + rp) = v;
+        }
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");   // later readers fetch this block with the TMA engine
+        consumer_bar();
+        if (tid == 0) st_release(pb->invdone + j, epoch);
+        row_lo = off + TN;
+      } else {
+        // a finished factor (mode 1) needs no wait: its inverse diagonal blocks were published long ago
+        if (mode == 0) {
+          if (tid == 0) wait_flag(pb->invdone + j, epoch, status, abort_flag);
+          consumer_bar();
+        }
+        const double* invd = pb->invd + (int64_t)j * TN * TN;
+        for (int idx = tid; idx < TN * TN; idx += NCW * 32) Ys[(idx >> 6) * LDB_S + (idx & 63)] = __ldcg(invd + idx);
+        consumer_bar();
+      }
+      if (row_lo < TM) {
+        // ---- E3: X = tile * inv(L_jj)' on the tensor pipe ----
+        double x[4][4][2];
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+          for (int ni = 0; ni < 4; ni++) { x[mi][ni][0] = 0.0; x[mi][ni][1] = 0.0; }
+#pragma unroll 4
+        for (int k4 = 0; k4 < TN / 4; k4++) warp_mma_k4(x, At, LDA_S, Ys, LDB_S, k4 * 4, wm, wn, lane);
+        consumer_bar();
+        {
+          const int kq = lane & 3, rq = lane >> 2;
+#pragma unroll
+          for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) {
+              const int row = wm * 32 + mi * 8 + rq, col = wn * 32 + ni * 8 + kq * 2;
+              if (row >= row_lo) { At[col * LDA_S + row] = x[mi][ni][0]; At[(col + 1) * LDA_S + row] = x[mi][ni][1]; }
+            }
+        }
+        consumer_bar();
+        // ---- E4: coalesced copy-out of rows [row_lo, TM) ----
+        const int npairs = (TM - row_lo) / 2;
+        for (int idx = tid; idx < TN * npairs; idx += NCW * 32) {
+          const int c = idx / npairs, rp = row_lo + (idx % npairs) * 2;
+          const double2 v = *reinterpret_cast<const double2*>(At + c * LDA_S + rp);
+          *reinterpret_cast<double2*>(P + (C0 + c) * ldP + R0 + rp) = v;
+        }
+        // ---- E5: border reductions (ordered by the flag chain => deterministic, no atomics) ----
+        const int q = pb->q;
+        if (mode == 0) {
+          const int wl0 = pb->w0 - (int)R0;
+          if (q > 0 && wl0 >= row_lo && wl0 < TM) {
+            for (int e = tid; e < q * q; e += NCW * 32) {
+              const int a = e % q, b = e / q;
+              double s = 0.0;
+              for (int c = 0; c < TN; c++) s += At[c * LDA_S + wl0 + a] * At[c * LDA_S + wl0 + b];
+              double* G = pb->G + e;            // __ldcg: the previous column's CTA wrote it through L2
+              *G = (j == 0 ? 0.0 : __ldcg(G)) + s;
+            }
+          }
+        } else {
+          // kriging rows: G(:,0..q-1) += X Yw', G(:,q) += rowsum(X^2)
+          for (int idx = tid; idx < q * TN; idx += NCW * 32) {
+            const int w = idx % q, c = idx / q;
+            Ws[c * 64 + w] = __ldcg(pb->YW + (C0 + c) * ldL + w);
+          }
+          consumer_bar();
+          if (tid < TM) {
+            double* G = pb->G + R0 + tid;
+            double ssq = 0.0;
+            for (int c = 0; c < TN; c++) { const double xv = At[c * LDA_S + tid]; ssq += xv * xv; }
+            G[(int64_t)q * pb->ldG] = (j == 0 ? 0.0 : __ldcg(G + (int64_t)q * pb->ldG)) + ssq;
+            for (int wb = 0; wb < q; wb += 16) {
+              double g[16];
+#pragma unroll
+              for (int w = 0; w < 16; w++) g[w] = 0.0;
+              for (int c = 0; c < TN; c++) {
+                const double xv = At[c * LDA_S + tid];
+#pragma unroll
+                for (int w = 0; w < 16; w++) g[w] += xv * Ws[c * 64 + ((wb + w) & 63)];
+              }
+#pragma unroll
+              for (int w = 0; w < 16; w++)
+                if (wb + w < q) G[(int64_t)(wb + w) * pb->ldG] = (j == 0 ? 0.0 : __ldcg(G + (int64_t)(wb + w) * pb->ldG)) + g[w];
+            }
+          }
+        }
+      }
+      // ---- E6: publish ----
+      __threadfence();
+      asm volatile("fence.proxy.async;" ::: "memory");     // the tile is re-read by other CTAs' TMA bulk copies
+      consumer_bar();
+      if (tid == 0) st_release(pb->doneP + (int64_t)r * nCB + j, epoch);
+    }
+    it = it0 + nchunks;
+    at_phase ^= 1;
+    __syncthreads();
+  }
+}
+
+// lndet = sum_j logsum_j in fixed order; results[b] = {lndet, G(q*q)}; status copied alongside
+__global__ void finish_kernel(const ProblemDesc* __restrict__ probs, int count, double* __restrict__ results, int stride) {
+  const int b = blockIdx.x;
+  if (b >= count) return;
+  const ProblemDesc* pb = probs + b;
+  double* out = results + (int64_t)b * stride;
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int j = 0; j < pb->nCB; j++) s += pb->logsum[j];
+    out[0] = s;
+    out[1] = (double)(pb->status[0] | (pb->status[1] << 1));
+  }
+  const int qq = pb->q * pb->q;
+  for (int i = threadIdx.x; i < qq; i += blockDim.x) out[2 + i] = pb->G[i];
+}
+
+// ---- back-substitution  L' X = Y  for a few right-hand sides (iAW of fitIAK3D.R:782-808) ------------
+// Y is stored as rows (Y' in the W rows of the factor buffer).  Block-column sweep from the right:
+//   x_J = inv(L_JJ)' y_J ;  y_K -= L(J,K)' x_J for all K < J.   Not on the optimiser's hot loop.
+__global__ void backsolve_diag_kernel(const double* __restrict__ invd, int J, const double* __restrict__ Yw, int64_t ldY, int q,
+                                      double* __restrict__ X, int64_t ldX) {
+  // x_J (64 x q) = invL_JJ' * y_J ; thread (row i of x, rhs w)
+  __shared__ double ys[TN * 64];
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < TN * q; idx += blockDim.x) { const int c = idx / q, w = idx % q; ys[c * 64 + w] = Yw[(int64_t)(J * TN + c) * ldY + w]; }
+  __syncthreads();
+  const double* Li = invd + (int64_t)J * TN * TN;     // column-major 64x64, lower
+  for (int idx = tid; idx < TN * q; idx += blockDim.x) {
+    const int i = idx % TN, w = idx / TN;
+    double s = 0.0;
+    for (int k = i; k < TN; k++) s += Li[(int64_t)i * TN + k] * ys[k * 64 + w];   // (invL')(i,k) = invL(k,i)
+    X[(int64_t)w * ldX + J * TN + i] = s;
+  }
+}
+__global__ void backsolve_update_kernel(const double* __restrict__ L, int64_t ldL, int J, const double* __restrict__ X,
+                                        int64_t ldX, int q, double* __restrict__ Yw, int64_t ldY) {
+  // for column c < J*TN : y_c(w) -= sum_{i in block J} L(J*TN+i, c) * x_J(i, w)
+  __shared__ double xs[TN * 64];
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < TN * q; idx += blockDim.x) { const int i = idx % TN, w = idx / TN; xs[i * 64 + w] = X[(int64_t)w * ldX + J * TN + i]; }
+  __syncthreads();
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + tid;
+  if (c >= (int64_t)J * TN) return;
+  const double* col = L + c * ldL + (int64_t)J * TN;
+  for (int wb = 0; wb < q; wb += 16) {
+    double s[16];
+#pragma unroll
+    for (int w = 0; w < 16; w++) s[w] = 0.0;
+    for (int i = 0; i < TN; i++) {
+      const double l = col[i];
+#pragma unroll
+      for (int w = 0; w < 16; w++) s[w] += l * xs[i * 64 + ((wb + w) & 63)];
+    }
+#pragma unroll
+    for (int w = 0; w < 16; w++) if (wb + w < q) Yw[c * ldY + wb + w] -= s[w];
+  }
+}
+
+// ---- FP64 peak microbenchmarks -------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) peak_dfma_kernel(double* out, int iters) {
+  double a[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) a[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+  const double b = 1.0000001, c = 1e-12;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = fma(a[i], b, c);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) s += a[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) peak_dmma_kernel(double* out, int iters) {
+  double acc[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+  const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) dmma(acc[i][0], acc[i][1], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += acc[i][0] + acc[i][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace
+
+int chol_configure(iak3d_ctx* ctx) {
+  CUDA_TRY(ctx, cudaFuncSetAttribute(tile_task_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  return 0;
+}
+
+int launch_tile_tasks(iak3d_ctx* ctx, const ProblemDesc* d_problems, const int4* d_tasks, int32_t ntasks, int32_t* d_ticket) {
+  if (ntasks <= 0) return 0;
+  CUDA_TRY(ctx, cudaMemsetAsync(d_ticket, 0, 2 * sizeof(int32_t), ctx->stream));   // [0] ticket, [1] abort flag
+  int grid = ctx->sm_count;
+  if (grid > ntasks) grid = ntasks;
+  tile_task_kernel<<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(d_problems, d_tasks, ntasks, d_ticket);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return 0;
+}
+
+int launch_finish(iak3d_ctx* ctx, const ProblemDesc* d_problems, int32_t count, double* d_results, int32_t stride) {
+  if (count <= 0) return 0;
+  finish_kernel<<<count, 128, 0, ctx->stream>>>(d_problems, count, d_results, stride);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return 0;
+}
+
+int launch_backsolve(iak3d_ctx* ctx, const double* d_L, int64_t ld, int64_t Npad, const double* d_invd, double* d_Yw, int64_t ldY,
+                     int32_t q, double* d_X) {
+  // d_Yw: q x Npad (column-major, ldY) copy of the Y' rows -- destroyed.  d_X: Npad x q column-major out.
+  const int nCB = (int)(Npad / TN);
+  for (int J = nCB - 1; J >= 0; J--) {
+    backsolve_diag_kernel<<<1, 256, 0, ctx->stream>>>(d_invd, J, d_Yw, ldY, q, d_X, Npad);
+    ctx->launches++;
+    if (J > 0) {
+      const int blocks = (J * TN + 127) / 128;
+      backsolve_update_kernel<<<blocks, 128, 0, ctx->stream>>>(d_L, ld, J, d_X, Npad, q, d_Yw, ldY);
+      ctx->launches++;
+    }
+  }
+  CUDA_TRY(ctx, cudaGetLastError());
+  return 0;
+}
+
+int launch_peak(iak3d_ctx* ctx, int kind, double* tflops) {
+  const int blocks = ctx->sm_count * 4, threads = 256, iters = 20000;
+  double* d_out = nullptr;
+  CUDA_TRY(ctx, cudaMalloc(&d_out, (size_t)blocks * threads * sizeof(double)));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(ctx, cudaEventCreate(&e0)); CUDA_TRY(ctx, cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
+    if (kind == 0) peak_dfma_kernel<<<blocks, threads, 0, ctx->stream>>>(d_out, iters);
+    else peak_dmma_kernel<<<blocks, threads, 0, ctx->stream>>>(d_out, iters);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaEventRecord(e1, ctx->stream));
+    CUDA_TRY(ctx, cudaEventSynchronize(e1));
+    float ms = 0; CUDA_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+  double flops;
+  if (kind == 0) flops = (double)blocks * threads * iters * 16.0 * 2.0;
+  else flops = (double)blocks * (threads / 32) * iters * 8.0 * (8.0 * 8.0 * 4.0 * 2.0);
+  *tflops = flops / (best * 1e-3) / 1e12;
+  return 0;
+}

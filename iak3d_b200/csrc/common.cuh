@@ -1,0 +1,149 @@
+// common.cuh -- internal structures of libiak3d.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/iak3d.h"
+#include "iak3d_math.h"
+
+// ---- tiling constants shared by the covariance-build and factorisation kernels ---------------
+constexpr int TM = 128;      // tile rows  (row-block height)
+constexpr int TN = 64;       // tile cols  (column-block width == panel width of the factorisation)
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+struct iak3d_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  size_t total_mem = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t evs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // stage boundaries of the last batch
+  std::string err;
+  int64_t launches = 0;
+  // scratch
+  void* flush_buf = nullptr; size_t flush_bytes = 0;
+  // batch state (nll_terms_batch_enqueue -> fetch)
+  struct Batch* batch = nullptr;
+  double last_chol_flops = 0, last_cov_bytes = 0;
+  bool stage_events_valid = false;
+};
+
+// Workspace of ONE likelihood evaluation of a dataset: the factor buffer, the unique-pair tables and the
+// dependency flags.  A dataset owns as many slots as the largest number of simultaneous evaluations asked of
+// it (1 for a composite-likelihood block, npar+1 for a forward-difference gradient).
+struct Slot {
+  int64_t n = 0, Npad = 0, ld = 0, nxU = 0, ndIU = 0;
+  int32_t q = 0, nCB = 0, nRB = 0;
+  double* d_L = nullptr;          // ld x Npad factor buffer (A in, L out; W' rows at Npad..Npad+q-1)
+  double* d_phix = nullptr;       // nxU x nxU horizontal correlation table
+  double* d_phid = nullptr;       // 3 tables ndIU x ndIU + 3 avVar vectors
+  double* d_invd = nullptr;       // nCB x (TN*TN) inverted diagonal blocks
+  int32_t* d_flags = nullptr;     // done[nRB*nCB] + invdone[nCB]
+  double* d_logsum = nullptr;     // nCB
+  double* d_G = nullptr;          // 64*64 Gram accumulator (WiAW)
+  int32_t epoch = 0;              // flags are valid when == epoch
+};
+
+// Device-resident dataset == setupMats (+ W) of the reference, expressed as id vectors.
+struct iak3d_ds {
+  iak3d_ctx* ctx = nullptr;
+  int64_t n = 0, nxU = 0, ndIU = 0;
+  int32_t q = 0;
+  std::vector<int32_t> h_xid, h_did;
+  std::vector<double> h_xU, h_dIU;       // nxU x 2, ndIU x 2 (column-major)
+  std::vector<double> h_W;               // n x q column-major copy (fit_create forms z - X betahat from it)
+  int32_t *d_xid = nullptr, *d_did = nullptr;
+  double *d_xU = nullptr, *d_dIU = nullptr;   // column-major nxU x 2 / ndIU x 2
+  double* d_W = nullptr;                  // n x q column-major
+  // factorisation geometry (depends on n and q only)
+  int64_t Npad = 0;     // round_up(n, TN): columns factorised (identity padded)
+  int64_t ld = 0;       // rows of the factor buffer = round_up(Npad + q, TM)
+  int32_t nCB = 0, nRB = 0;
+  std::vector<Slot*> slots;
+};
+
+// One covariance evaluation planned on the host from parsBTfmd (no device work).
+struct EvalPlan {
+  int status = 0;           // 0, IAK3D_BAD_PARS
+  int ntab = 0;             // distinct depth tables
+  IaPrm prm[3];
+  int tidx[3] = {-1, -1, -1};   // table of cd1, cxd0, cxd1 (-1 absent)
+  bool has_phix = false;
+  HxPrm H;
+  double cx0 = 0, cx1 = 0, cd1 = 0, kd1 = 0, cxd0 = 0, cxd1 = 0, cme = 0;
+};
+
+#define CUDA_TRY(ctx, expr)                                                                   \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      char _b[512];                                                                           \
+      snprintf(_b, sizeof(_b), "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      (ctx)->err = _b;                                                                        \
+      return IAK3D_ERR_CUDA;                                                                  \
+    }                                                                                         \
+  } while (0)
+
+// ---- table kernels (tables.cu) ----------------------------------------------------------------
+int launch_iacov_table(iak3d_ctx* ctx, const IaPrm& P, const double* d_dI1, int64_t n1, const double* d_dI2,
+                       int64_t n2, double* d_out /* n1 x n2 col-major: out[j*n1+i] */, double* d_avvar1);
+int launch_phix_table(iak3d_ctx* ctx, const HxPrm& H, const double* d_x1, int64_t n1, const double* d_x2, int64_t n2,
+                      double* d_out /* out[j*n1+i] */, uint8_t* d_zero /* optional: D==0 indicator */);
+int launch_phix_vec(iak3d_ctx* ctx, const HxPrm& H, const double* d_D, int64_t m, double* d_out);
+int hx_init(HxPrm* H, int modelx, double a, double nu);   // returns 2 when the reference returns NA
+
+// ---- covariance assembly (covbuild.cu) --------------------------------------------------------
+struct CovArgs {
+  // value(i,j) = [same loc](cx0 + cxd0*T0) + kd1*Td + phix*(cx1 + cxd1*T1) + (i==j)*cme
+  const double* T[3];      // distinct depth tables (may alias); T[tidx[c]] for c = cd1, cxd0, cxd1; tidx<0 = absent
+  int tidx[3];
+  int ntab;
+  const double* phix;      // horizontal table or nullptr (nugget)
+  const uint8_t* same;     // cross only: D==0 indicator table; square: nullptr (xid equality)
+  double cx0, cx1, kd1, cxd0, cxd1, cme;
+  const int32_t *xid_r, *did_r, *xid_c, *did_c;   // row ids / col ids
+  int64_t nr, nc;          // live rows / cols
+  int64_t nxU_r, ndIU_r;   // leading dims of tables (row-id extent)
+};
+int launch_cov_factor_layout(iak3d_ctx* ctx, const CovArgs& a, const double* d_W, int32_t q, int64_t n, int64_t Npad, int64_t ld,
+                             int32_t nCB, double* d_L);
+// generic symmetric matrix (host-supplied C, optim_functions.R:268) + b' rows into the factor layout
+int launch_pack_factor_layout(iak3d_ctx* ctx, const double* d_C, int64_t n, const double* d_b, int32_t q, int64_t Npad,
+                              int64_t ld, double* d_L);
+int launch_sigma2(iak3d_ctx* ctx, const EvalPlan& pl, const double* d_avvar /* 3 x ndIU */, int64_t ndIU, const int32_t* d_did,
+                  int64_t n, double* d_out);
+int launch_ckk(iak3d_ctx* ctx, const EvalPlan& pl, const double* const* d_Tself /* per table: ndIU1 x ndIU1 */, int64_t ndIU1,
+               const int32_t* d_did1, int64_t m, double* d_out);
+int launch_cov_rect(iak3d_ctx* ctx, const CovArgs& a, double* d_out, int64_t ld, int64_t rows_total, int64_t cols_total,
+                    int symmetric_square);
+
+// ---- factorisation (chol.cu) -------------------------------------------------------------------
+struct ProblemDesc {
+  double* L; int64_t ldL;        // factor storage; B operand + diagonal blocks
+  double* P; int64_t ldP;        // row-panel storage the task owns (== L when factorising)
+  double* invd;                  // nCB x TN*TN inverse diagonal blocks
+  int32_t* doneL; int32_t* doneP; int32_t* invdone;
+  int32_t nCB, nRB;              // col-blocks of L / row-blocks of P
+  int32_t mode;                  // 0 = factorise (P == L), 1 = bordered rows against a finished factor
+  int32_t epoch;
+  int32_t w0, q;                 // factorise: local W rows start (global row index) and count; mode 1: q of YW
+  double* G;                     // mode 0: q*q Gram; mode 1: rowsP x (q+1) accumulators
+  int64_t ldG;
+  double* logsum;                // nCB
+  int32_t* status;               // [0] not-SPD, [1] timeout
+  const double* YW;              // mode 1: W rows of the factor buffer (L + w0), ld = ldL
+};
+int chol_configure(iak3d_ctx* ctx);
+int launch_tile_tasks(iak3d_ctx* ctx, const ProblemDesc* d_problems, const int4* d_tasks, int32_t ntasks, int32_t* d_ticket /* 2 ints */);
+int launch_finish(iak3d_ctx* ctx, const ProblemDesc* d_problems, int32_t count, double* d_results, int32_t stride);
+int launch_backsolve(iak3d_ctx* ctx, const double* d_L, int64_t ld, int64_t Npad, const double* d_invd, double* d_Yw, int64_t ldY,
+                     int32_t q, double* d_X /* Npad x q col-major out */);
+int launch_peak(iak3d_ctx* ctx, int kind, double* tflops);
+// kriging epilogue (predictIAK3D.R:229-255): z, v from the bordered-row accumulators G (ldG x (q+1))
+int launch_krige_finish(iak3d_ctx* ctx, const double* d_G, int64_t ldG, int32_t q, const double* d_XMap, int64_t ldX, int64_t m,
+                        const double* d_Ckk, const double* d_beta, const double* d_vbeta, double* d_z, double* d_v);

@@ -1,0 +1,317 @@
+// covbuild.cu -- covariance assembly (setCIAK3D fitIAK3D.R:955-1112, setCIAK3D2 :1117-1252).
+//
+//   A(i,j) = cme*[i==j] + [x_i==x_j]*(cx0 + cxd0*Phi_cxd0(I_i,I_j)) + kd1*Phi_cd1(I_i,I_j)
+//            + phi_x(x_i,x_j)*(cx1 + cxd1*Phi_cxd1(I_i,I_j))
+//
+// The reference reaches this through two n(n+1)/2-long gather index vectors (iaCovMatern.R:473-481);
+// here each entry is formed directly from the row's (location id, interval id) pair and the small
+// unique-pair tables of tables.cu, which stay L2-resident.  The pass is HBM-write-bound: 8 bytes per
+// entry, coalesced 16-byte stores down the (column-major) columns.  Row/column id tiles are staged
+// into shared memory with cp.async.bulk (TMA 1-D bulk copies, mbarrier completion).
+#include "common.cuh"
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(
+          smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct CovDev {
+  const double* T[3];
+  int tidx[3];
+  int ntab;
+  const double* phix;
+  const uint8_t* same;
+  double cx0, cx1, kd1, cxd0, cxd1, cme;
+  const int32_t *xid_r, *did_r, *xid_c, *did_c;
+  int64_t nr, nc, nxU_r, ndIU_r;
+};
+
+// Terms are accumulated in the reference's order (fitIAK3D.R:973,976,1038,1048/1052,1067,1071) and this file is
+// compiled with -fmad=false, so an entry rounds like the chain of R matrix additions.
+__device__ __forceinline__ double cov_value(const CovDev& a, int xi, int di, int xj, int dj, bool diag) {
+  double t[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) t[k] = (k < a.ntab) ? __ldg(a.T[k] + (int64_t)dj * a.ndIU_r + di) : 0.0;
+  auto pick = [&](int k) -> double { return k == 0 ? t[0] : (k == 1 ? t[1] : (k == 2 ? t[2] : 0.0)); };
+  const double td = pick(a.tidx[0]), t0 = pick(a.tidx[1]), t1 = pick(a.tidx[2]);
+  bool same;
+  if (a.same != nullptr) same = __ldg(a.same + (int64_t)xj * a.nxU_r + xi) != 0;
+  else same = (xi == xj);
+  double v = diag ? a.cme : 0.0;
+  if (same) { v = v + a.cx0; v = v + a.cxd0 * t0; }
+  if (a.tidx[0] >= 0) v = v + a.kd1 * td;
+  if (a.phix != nullptr) {
+    const double px = __ldg(a.phix + (int64_t)xj * a.nxU_r + xi);
+    v = v + a.cx1 * px;
+    v = v + (a.cxd1 * px) * t1;
+  }
+  return v;
+}
+
+// ---- factor-layout build: lower-triangular TM x TN tiles of the padded factor buffer ---------------
+// rows [0,n) data, [n,Npad) identity padding, [Npad,Npad+q) the W' rows (bordered system), rest zero.
+__global__ void __launch_bounds__(256) cov_factor_kernel(CovDev a, const double* __restrict__ W, int q, int64_t n,
+                                                         int64_t Npad, double* __restrict__ L, int64_t ld, int nCB) {
+  __shared__ __align__(16) int32_t s_xr[TM], s_dr[TM], s_xc[TN], s_dc[TN];
+  __shared__ __align__(8) uint64_t bar;
+  // decode (r, j) from the linear lower-triangular tile index: column-block j has row-blocks j/2 .. nRB-1
+  const int nRB = (int)(ld / TM);
+  int j = 0, r = 0;
+  {
+    int64_t t = blockIdx.x;   // tiles enumerated column-block by column-block
+    // tiles before column j: sum_{c<j} (nRB - c/2)
+    // solve by a short loop (nCB <= a few thousand; one thread per CTA would do, all do it redundantly)
+    int lo = 0, hi = nCB - 1;
+    auto before = [&](int64_t c) -> int64_t {   // number of tiles in columns [0,c)
+      const int64_t h = c / 2;                   // pairs of columns share the same first row-block
+      return c * (int64_t)nRB - (h * (h - 1) + (c & 1) * h);   // sum_{c'<c} floor(c'/2) = h(h-1) + (c odd ? h : 0)
+    };
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (before(mid) <= t) lo = mid; else hi = mid - 1; }
+    j = lo; r = (int)(t - before(j)) + j / 2;
+  }
+  const int64_t R0 = (int64_t)r * TM, C0 = (int64_t)j * TN;
+  const int tid = threadIdx.x;
+  // stage the id tiles (TMA bulk copies when the whole tile is inside the data range)
+  const bool rows_in = (R0 + TM <= n), cols_in = (C0 + TN <= n);
+  if (tid == 0) { mbar_init(&bar, 1); }
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    uint32_t bytes = 0;
+    if (rows_in) bytes += 2 * TM * 4;
+    if (cols_in) bytes += 2 * TN * 4;
+    mbar_expect_tx(&bar, bytes);
+    if (rows_in) { bulk_g2s(s_xr, a.xid_r + R0, TM * 4, &bar); bulk_g2s(s_dr, a.did_r + R0, TM * 4, &bar); }
+    if (cols_in) { bulk_g2s(s_xc, a.xid_c + C0, TN * 4, &bar); bulk_g2s(s_dc, a.did_c + C0, TN * 4, &bar); }
+  }
+  if (!rows_in && tid < TM) { const int64_t i = R0 + tid; s_xr[tid] = i < n ? a.xid_r[i] : -1; s_dr[tid] = i < n ? a.did_r[i] : 0; }
+  if (!cols_in && tid < TN) { const int64_t c = C0 + tid; s_xc[tid] = c < n ? a.xid_c[c] : -1; s_dc[tid] = c < n ? a.did_c[c] : 0; }
+  __syncthreads();
+  mbar_wait(&bar, 0);
+
+  const int rp = tid & 63, cg = tid >> 6;           // row pair (2 rows), column group (16 columns)
+  const int lr = rp * 2;
+  const int64_t i0 = R0 + lr;
+  const int xi0 = s_xr[lr], di0 = s_dr[lr], xi1 = s_xr[lr + 1], di1 = s_dr[lr + 1];
+#pragma unroll 4
+  for (int cc = 0; cc < 16; cc++) {
+    const int lc = cg * 16 + cc;
+    const int64_t c = C0 + lc;
+    const int xj = s_xc[lc], dj = s_dc[lc];
+    double v[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int64_t i = i0 + e;
+      const int xi = e ? xi1 : xi0, di = e ? di1 : di0;
+      double val;
+      if (i < c) val = 0.0;                                             // strictly upper: never read
+      else if (c >= n) val = (i == c && c < Npad) ? 1.0 : 0.0;          // identity padding columns
+      else if (i < n) val = cov_value(a, xi, di, xj, dj, i == c);
+      else if (i >= Npad && i < Npad + q) val = W[(int64_t)(i - Npad) * n + c];   // W' rows
+      else val = 0.0;
+      v[e] = val;
+    }
+    *reinterpret_cast<double2*>(L + c * ld + i0) = make_double2(v[0], v[1]);
+  }
+}
+
+int launch_cov_factor_layout(iak3d_ctx* ctx, const CovArgs& h, const double* d_W, int32_t q, int64_t n, int64_t Npad, int64_t ld,
+                             int32_t nCB_, double* d_L) {
+  CovDev a;
+  for (int k = 0; k < 3; k++) { a.T[k] = h.T[k]; a.tidx[k] = h.tidx[k]; }
+  a.ntab = h.ntab; a.phix = h.phix; a.same = h.same;
+  a.cx0 = h.cx0; a.cx1 = h.cx1; a.kd1 = h.kd1; a.cxd0 = h.cxd0; a.cxd1 = h.cxd1; a.cme = h.cme;
+  a.xid_r = h.xid_r; a.did_r = h.did_r; a.xid_c = h.xid_c; a.did_c = h.did_c;
+  a.nr = h.nr; a.nc = h.nc; a.nxU_r = h.nxU_r; a.ndIU_r = h.ndIU_r;
+  const int64_t nRB = ld / TM, nCB = nCB_;
+  int64_t tiles = 0;
+  for (int64_t c = 0; c < nCB; c++) tiles += nRB - c / 2;
+  cov_factor_kernel<<<(unsigned)tiles, 256, 0, ctx->stream>>>(a, d_W, q, n, Npad, d_L, ld, (int)nCB);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return 0;
+}
+
+// ---- rectangular / full build (setCIAK3D returning C, setCIAK3D2, prediction row panels) -------------
+// out is column-major with leading dimension ld; rows >= nr and cols >= nc are zero-filled up to
+// rows_total x cols_total.  symmetric_square adds cme on the diagonal (row index == col index).
+__global__ void __launch_bounds__(256) cov_rect_kernel(CovDev a, double* __restrict__ out, int64_t ld, int64_t rows_total,
+                                                       int64_t cols_total, int sym) {
+  __shared__ int32_t s_xc[TN], s_dc[TN];
+  const int64_t R0 = (int64_t)blockIdx.x * TM, C0 = (int64_t)blockIdx.y * TN;
+  const int tid = threadIdx.x;
+  if (tid < TN) { const int64_t c = C0 + tid; s_xc[tid] = c < a.nc ? a.xid_c[c] : -1; s_dc[tid] = c < a.nc ? a.did_c[c] : 0; }
+  __syncthreads();
+  const int rp = tid & 63, cg = tid >> 6;
+  const int64_t i0 = R0 + rp * 2;
+  int xi[2], di[2];
+#pragma unroll
+  for (int e = 0; e < 2; e++) { const int64_t i = i0 + e; xi[e] = i < a.nr ? a.xid_r[i] : -1; di[e] = i < a.nr ? a.did_r[i] : 0; }
+  for (int cc = 0; cc < 16; cc++) {
+    const int lc = cg * 16 + cc;
+    const int64_t c = C0 + lc;
+    if (c >= cols_total) break;
+    const int xj = s_xc[lc], dj = s_dc[lc];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int64_t i = i0 + e;
+      if (i >= rows_total) continue;
+      double val = 0.0;
+      if (i < a.nr && c < a.nc) val = cov_value(a, xi[e], di[e], xj, dj, sym && i == c);
+      out[c * ld + i] = val;
+    }
+  }
+}
+
+int launch_cov_rect(iak3d_ctx* ctx, const CovArgs& h, double* d_out, int64_t ld, int64_t rows_total, int64_t cols_total,
+                    int symmetric_square) {
+  CovDev a;
+  for (int k = 0; k < 3; k++) { a.T[k] = h.T[k]; a.tidx[k] = h.tidx[k]; }
+  a.ntab = h.ntab; a.phix = h.phix; a.same = h.same;
+  a.cx0 = h.cx0; a.cx1 = h.cx1; a.kd1 = h.kd1; a.cxd0 = h.cxd0; a.cxd1 = h.cxd1; a.cme = h.cme;
+  a.xid_r = h.xid_r; a.did_r = h.did_r; a.xid_c = h.xid_c; a.did_c = h.did_c;
+  a.nr = h.nr; a.nc = h.nc; a.nxU_r = h.nxU_r; a.ndIU_r = h.ndIU_r;
+  if (rows_total == 0 || cols_total == 0) return 0;
+  dim3 grid((unsigned)((rows_total + TM - 1) / TM), (unsigned)((cols_total + TN - 1) / TN));
+  if (grid.y > 65535) { ctx->err = "cov_rect: too many column tiles"; return IAK3D_ERR_ARG; }
+  cov_rect_kernel<<<grid, 256, 0, ctx->stream>>>(a, d_out, ld, rows_total, cols_total, symmetric_square);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return 0;
+}
+
+// ---- generic symmetric input (lndetANDinvCb called with a caller-built C, optim_functions.R:268) ------
+__global__ void __launch_bounds__(256) pack_factor_kernel(const double* __restrict__ C, int64_t n, const double* __restrict__ b, int q,
+                                                          int64_t Npad, int64_t ld, double* __restrict__ L) {
+  const int64_t c = blockIdx.y;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ld; i += (int64_t)gridDim.x * blockDim.x) {
+    double v = 0.0;
+    if (c < n) {
+      if (i < n) v = (i >= c) ? C[c * n + i] : 0.0;                 // lower triangle of the caller's matrix
+      else if (i >= Npad && i < Npad + q) v = b[(int64_t)(i - Npad) * n + c];
+    } else {
+      v = (i == c) ? 1.0 : 0.0;
+    }
+    L[c * ld + i] = v;
+  }
+}
+int launch_pack_factor_layout(iak3d_ctx* ctx, const double* d_C, int64_t n, const double* d_b, int32_t q, int64_t Npad,
+                              int64_t ld, double* d_L) {
+  if (Npad > 65535 * 64) { ctx->err = "pack_factor: matrix too large"; return IAK3D_ERR_ARG; }
+  dim3 grid((unsigned)((ld + 255) / 256), (unsigned)Npad);
+  if (Npad > 65535) { ctx->err = "pack_factor: more than 65535 columns"; return IAK3D_ERR_ARG; }
+  pack_factor_kernel<<<grid, 256, 0, ctx->stream>>>(d_C, n, d_b, q, Npad, ld, d_L);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return 0;
+}
+
+// ---- sigma2Vec (fitIAK3D.R:1083-1086) ------------------------------------------------------------------
+struct S2Dev { double cxd0, cxd1, cme, cx0, cx1, cd1; int t0, t1, td; };
+__global__ void sigma2_kernel(S2Dev a, const double* __restrict__ av, int64_t ndIU, const int32_t* __restrict__ did, int64_t n,
+                              double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int d = did[i];
+  const double a0 = a.t0 >= 0 ? av[(int64_t)a.t0 * ndIU + d] : 0.0;
+  const double a1 = a.t1 >= 0 ? av[(int64_t)a.t1 * ndIU + d] : 0.0;
+  const double ad = a.td >= 0 ? av[(int64_t)a.td * ndIU + d] : 0.0;
+  double v = a.cxd0 * a0;
+  v = v + a.cxd1 * a1;
+  v = v + a.cme; v = v + a.cx0; v = v + a.cx1;
+  v = v + a.cd1 * ad;
+  out[i] = v;
+}
+int launch_sigma2(iak3d_ctx* ctx, const EvalPlan& pl, const double* d_avvar, int64_t ndIU, const int32_t* d_did, int64_t n,
+                  double* d_out) {
+  if (n == 0) return 0;
+  S2Dev a{pl.cxd0, pl.cxd1, pl.cme, pl.cx0, pl.cx1, pl.cd1, pl.tidx[1], pl.tidx[2], pl.tidx[0]};
+  sigma2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(a, d_avvar, ndIU, d_did, n, d_out);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return 0;
+}
+
+// ---- Ckk = diag(setCIAK3D(map supports)) (predictIAK3D.R:179-189): every term at zero separation --------
+struct CkkDev { const double* T[3]; int tidx[3]; double cx0, cx1, kd1, cxd0, cxd1, cme; int has_phix; HxPrm H; };
+__global__ void ckk_kernel(CkkDev a, int64_t ndIU1, const int32_t* __restrict__ did1, int64_t m, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const int64_t d = did1[i];
+  const double td = a.tidx[0] >= 0 ? a.T[a.tidx[0]][d * ndIU1 + d] : 0.0;
+  const double t0 = a.tidx[1] >= 0 ? a.T[a.tidx[1]][d * ndIU1 + d] : 0.0;
+  const double t1 = a.tidx[2] >= 0 ? a.T[a.tidx[2]][d * ndIU1 + d] : 0.0;
+  double v = a.cme;
+  v = v + a.cx0; v = v + a.cxd0 * t0;
+  if (a.tidx[0] >= 0) v = v + a.kd1 * td;
+  if (a.has_phix) {
+    const double px = iak_phix(0.0, &a.H);
+    v = v + a.cx1 * px;
+    v = v + (a.cxd1 * px) * t1;
+  }
+  out[i] = v;
+}
+int launch_ckk(iak3d_ctx* ctx, const EvalPlan& pl, const double* const* d_Tself, int64_t ndIU1, const int32_t* d_did1, int64_t m,
+               double* d_out) {
+  if (m == 0) return 0;
+  CkkDev a;
+  for (int k = 0; k < 3; k++) { a.T[k] = d_Tself[k]; a.tidx[k] = pl.tidx[k]; }
+  a.cx0 = pl.cx0; a.cx1 = pl.cx1; a.kd1 = pl.kd1; a.cxd0 = pl.cxd0; a.cxd1 = pl.cxd1; a.cme = pl.cme;
+  a.has_phix = pl.has_phix ? 1 : 0; a.H = pl.H;
+  ckk_kernel<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(a, ndIU1, d_did1, m, d_out);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return 0;
+}
+
+// ---- kriging epilogue (predictIAK3D.R:229-255) ---------------------------------------------------------
+//   G(:,0..p-1) = Ckh iC X, G(:,p) = Ckh iC (z - X betahat), G(:,p+1) = rowSums((Ckh iC) * Ckh)
+//   z = XMap betahat + G(:,p);  v = Ckk - G(:,p+1) + (XMap - CkhiCX) vbetahat (XMap - CkhiCX)'
+__global__ void krige_finish_kernel(const double* __restrict__ G, int64_t ldG, int q, const double* __restrict__ XMap, int64_t ldX,
+                                    int64_t m, const double* __restrict__ Ckk, const double* __restrict__ beta,
+                                    const double* __restrict__ vbeta, double* __restrict__ z, double* __restrict__ v) {
+  extern __shared__ double sh[];
+  const int p = q - 1;
+  double* sb = sh; double* sv = sh + p;
+  for (int i = threadIdx.x; i < p; i += blockDim.x) sb[i] = beta[i];
+  for (int i = threadIdx.x; i < p * p; i += blockDim.x) sv[i] = vbeta[i];
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  double mu = 0.0;
+  for (int a = 0; a < p; a++) mu = mu + XMap[(int64_t)a * ldX + i] * sb[a];
+  z[i] = mu + G[(int64_t)p * ldG + i];
+  double quad = 0.0;
+  for (int a = 0; a < p; a++) {
+    double s = 0.0;
+    for (int b = 0; b < p; b++) s = s + sv[(int64_t)b * p + a] * (XMap[(int64_t)b * ldX + i] - G[(int64_t)b * ldG + i]);
+    quad = quad + (XMap[(int64_t)a * ldX + i] - G[(int64_t)a * ldG + i]) * s;
+  }
+  v[i] = Ckk[i] - G[(int64_t)q * ldG + i] + quad;
+}
+int launch_krige_finish(iak3d_ctx* ctx, const double* d_G, int64_t ldG, int32_t q, const double* d_XMap, int64_t ldX, int64_t m,
+                        const double* d_Ckk, const double* d_beta, const double* d_vbeta, double* d_z, double* d_v) {
+  if (m == 0) return 0;
+  const int p = q - 1;
+  krige_finish_kernel<<<(unsigned)((m + 127) / 128), 128, (size_t)(p + p * p) * sizeof(double), ctx->stream>>>(
+      d_G, ldG, q, d_XMap, ldX, m, d_Ckk, d_beta, d_vbeta, d_z, d_v);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,127 @@
+// tables.cu -- unique-pair tables: the transcendental part of the covariance build.
+//
+// The reference evaluates the depth kernel on unique interval pairs (iaCovMatern.R:76-89) and the
+// horizontal model on unique location pairs (fitIAK3D.R:979) and then gathers them to n x n through
+// index vectors (fitIAK3D.R:1038-1074).  We keep that split: these kernels do the exp / Bessel work
+// on the (small) unique sets; covbuild.cu expands by id.  This translation unit is compiled with
+// -fmad=false so that the closed forms round like the reference's operation order.
+#include "common.cuh"
+
+__global__ void iacov_table_kernel(IaPrm P, const double* __restrict__ dI1, int64_t n1,
+                                   const double* __restrict__ dI2, int64_t n2, double* __restrict__ out,
+                                   double* __restrict__ avvar1) {
+  const int64_t total = n1 * n2;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = idx % n1, j = idx / n1;
+    out[idx] = iak_avcov(dI1[i], dI1[n1 + i], dI2[j], dI2[n2 + j], &P);
+    if (avvar1 != nullptr && j == 0) avvar1[i] = iak_avvar(dI1[i], dI1[n1 + i], &P);
+  }
+}
+
+int launch_iacov_table(iak3d_ctx* ctx, const IaPrm& P, const double* d_dI1, int64_t n1, const double* d_dI2, int64_t n2,
+                       double* d_out, double* d_avvar1) {
+  const int64_t total = n1 * n2;
+  if (total == 0) return 0;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+  iacov_table_kernel<<<blocks, 256, 0, ctx->stream>>>(P, d_dI1, n1, d_dI2, n2, d_out, d_avvar1);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return 0;
+}
+
+// phi_x on unique location pairs; D as in xyDist (iaCovMatern.R:888-920): squares added in dimension
+// order, then sqrt.  Optionally records the exact-equality indicator 1[D == 0] (fitIAK3D.R:1138).
+__global__ void phix_table_kernel(HxPrm H, const double* __restrict__ x1, int64_t n1, const double* __restrict__ x2,
+                                  int64_t n2, double* __restrict__ out, uint8_t* __restrict__ zero) {
+  const int64_t total = n1 * n2;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = idx % n1, j = idx / n1;
+    const double dx = x1[i] - x2[j], dy = x1[n1 + i] - x2[n2 + j];
+    double D = 0.0;
+    D = D + dx * dx;
+    D = D + dy * dy;
+    D = sqrt(D);
+    if (out != nullptr) out[idx] = iak_phix(D, &H);
+    if (zero != nullptr) zero[idx] = (D == 0.0) ? 1 : 0;
+  }
+}
+
+int launch_phix_table(iak3d_ctx* ctx, const HxPrm& H, const double* d_x1, int64_t n1, const double* d_x2, int64_t n2,
+                      double* d_out, uint8_t* d_zero) {
+  const int64_t total = n1 * n2;
+  if (total == 0) return 0;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+  phix_table_kernel<<<blocks, 256, 0, ctx->stream>>>(H, d_x1, n1, d_x2, n2, d_out, d_zero);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return 0;
+}
+
+__global__ void phix_vec_kernel(HxPrm H, const double* __restrict__ D, int64_t m, double* __restrict__ out) {
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < m; idx += (int64_t)gridDim.x * blockDim.x)
+    out[idx] = iak_phix(D[idx], &H);
+}
+
+int launch_phix_vec(iak3d_ctx* ctx, const HxPrm& H, const double* d_D, int64_t m, double* d_out) {
+  if (m == 0) return 0;
+  int blocks = (int)((m + 255) / 256);
+  if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+  phix_vec_kernel<<<blocks, 256, 0, ctx->stream>>>(H, d_D, m, d_out);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return 0;
+}
+
+// ---- host-side parameter preparation ------------------------------------------------------------
+static double pochdown(double q, int k) {     // fields.pochdown incl. the 1:(k-1) quirk (iaCovMatern.R:1435-1452)
+  if (k == 0) return 1.0;
+  double n = q;
+  if (k - 1 >= 1) for (int j = 1; j <= k - 1; j++) n = n * (q - j);
+  return n;
+}
+static double pochup(double q, int k) {       // iaCovMatern.R:1454-1471
+  if (k == 0) return 1.0;
+  double n = q;
+  if (k - 1 >= 1) for (int j = 1; j <= k - 1; j++) n = n * (q + j);
+  return n;
+}
+// Wendland.beta(n = 2, k): column k of the (k+1)x(k+1) table (iaCovMatern.R:1405-1433)
+static void wendland_beta_col(int k, double* out /* k+1 */) {
+  const int l = 1 + k + 1;
+  std::vector<double> M((size_t)(k + 1) * (k + 1), 0.0);
+  auto at = [&](int r, int c) -> double& { return M[(size_t)c * (k + 1) + r]; };
+  at(0, 0) = 1.0;
+  for (int col = 0; col <= k - 1; col++) {
+    int row = 0; double beta = 0.0;
+    for (int m = 0; m <= col; m++) beta += at(m, col) * pochdown(m + 1, m - row + 1) / pochup(l + 2 * col - m + 1, m - row + 2);
+    at(row, col + 1) = beta;
+    for (row = 1; row <= col + 1; row++) {
+      beta = 0.0;
+      for (int m = row - 1; m <= col; m++) beta += at(m, col) * pochdown(m + 1, m - row + 1) / pochup(l + 2 * col - m + 1, m - row + 2);
+      at(row, col + 1) = beta;
+    }
+  }
+  for (int r = 0; r <= k; r++) out[r] = at(r, k);
+}
+
+int hx_init(HxPrm* H, int modelx, double a, double nu) {
+  *H = HxPrm();
+  H->modelx = modelx; H->a = a; H->nu = nu;
+  if (modelx == IAK3D_MODELX_SPHERICAL) {
+    if (!(a > 0.0)) return IAK3D_BAD_PARS;                               // iaCovMatern.R:335
+  } else if (modelx == IAK3D_MODELX_MATERN) {
+    if (!(a > 0.0 && nu >= 0.05 && nu <= 20.0)) return IAK3D_BAD_PARS;   // :354
+    H->s = sqrt(2.0 * nu) / a;
+    H->lconst = -(nu - 1.0) * log(2.0) - lgamma(nu);
+    H->half = (nu == 0.5) ? 1 : (nu == 1.5) ? 3 : (nu == 2.5) ? 5 : 0;
+  } else if (modelx == IAK3D_MODELX_WENDLAND) {
+    if (!(a > 0.0 && nu >= 1.0 && nu <= 20.0)) return IAK3D_BAD_PARS;    // :379
+    H->kf = (int)floor(nu); H->kc = (int)ceil(nu);
+    H->wf = (double)H->kc - nu; H->wc = nu - (double)H->kf;             // :385-386
+    wendland_beta_col(H->kf, H->betaf); wendland_beta_col(H->kc, H->betac);
+    H->scf = iak_wend_eval(0.0, H->kf, H->betaf); H->scc = iak_wend_eval(0.0, H->kc, H->betac);
+  }
+  return 0;
+}

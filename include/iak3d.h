@@ -1,0 +1,162 @@
+/* iak3d.h -- C ABI of libiak3d.so: the B200 (sm_100a) implementation of iak3d's data-parallel
+ * hot path (covariance build -> REML / composite-likelihood evaluation -> block kriging).
+ *
+ * The reference (ortont/iak3d, 100 % R) has no FFI boundary of its own; this ABI is what an R
+ * `.Call` / `.C` binding (or Python ctypes) binds for the functions listed below.  Each entry point
+ * cites the reference interface (file:line in the reference) that it replaces.
+ *
+ * Conventions
+ *  - every pointer is a HOST pointer owned by the caller (R vectors); the library copies in/out.
+ *  - matrices are column-major (R native); doubles are IEEE FP64; ids are int32.
+ *  - return value: 0 = OK; 1 = matrix not positive definite / non-finite (R glue maps this to
+ *    badnll = 9E99, fitIAK3D.R:685,785-806); 2 = invalid parameters (reference returns C = NA,
+ *    fitIAK3D.R:739,885); <0 = CUDA failure (R glue calls stop()).  Never abort()/exit().
+ *  - the wire format of the covariance parameters is the NATURAL scale list `parsBTfmd`
+ *    (output of readParsIAK3D, fitIAK3D.R:1405-1408); transforms stay on the host.
+ *  - no CPU fallback exists: every compute entry point fails with a negative status when no
+ *    sm_100-class device is usable.
+ */
+#ifndef IAK3D_H
+#define IAK3D_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define IAK3D_API __attribute__((visibility("default")))
+#else
+#define IAK3D_API
+#endif
+
+#define IAK3D_OK 0
+#define IAK3D_NOT_SPD 1
+#define IAK3D_BAD_PARS 2
+#define IAK3D_ERR_CUDA (-1)
+#define IAK3D_ERR_ARG (-2)
+#define IAK3D_ERR_TIMEOUT (-3)
+
+/* modelx, fitIAK3D.R:978-984 */
+#define IAK3D_MODELX_NUGGET 0
+#define IAK3D_MODELX_SPHERICAL 1
+#define IAK3D_MODELX_MATERN 2
+#define IAK3D_MODELX_WENDLAND 3
+
+/* parsBTfmd + the model switches that select terms (fitIAK3D.R:1405-1408, 955-956). */
+typedef struct iak3d_pars {
+  int32_t modelx;          /* IAK3D_MODELX_* */
+  int32_t cmeOpt;          /* informational; cme is used as given (0 when cmeOpt == 0) */
+  int32_t sdfdType[3];     /* cd1, cxd0, cxd1: 0 stationary, -1 exponential sd(d), -9 component absent */
+  int32_t quirk_cd1_unscaled; /* 1 = reproduce fitIAK3D.R:1052 (non-stationary cd1 term added without cd1) */
+  double ax, nux, ad, nud; /* nud must be 0.5, 1.5 or 2.5 (iaCovMatern.R:12-29) */
+  double cx0, cx1, cd1, cxd0, cxd1, cme;
+  double sdfdPars[3][2];   /* (tau1, tau2) of each non-stationary component (iaCovMatern.R:40-43) */
+} iak3d_pars;
+
+typedef struct iak3d_ctx iak3d_ctx;   /* one per GPU: stream, workspaces, error text */
+typedef struct iak3d_ds iak3d_ds;     /* a dataset resident in HBM == `setupMats` + W of the reference */
+typedef struct iak3d_fit iak3d_fit;   /* a kept factorisation == the big matrices of `lmmFit` */
+
+/* ---- context ------------------------------------------------------------------------------ */
+IAK3D_API int iak3d_ctx_create(int device, iak3d_ctx** out);
+IAK3D_API int iak3d_ctx_destroy(iak3d_ctx* ctx);
+IAK3D_API const char* iak3d_last_error(iak3d_ctx* ctx);
+IAK3D_API int iak3d_device_info(iak3d_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, int64_t* total_mem);
+/* number of kernels this library launched on ctx since creation (bench.py's gpu_launches claim) */
+IAK3D_API int64_t iak3d_launch_count(iak3d_ctx* ctx);
+
+/* ---- dataset == setupIAK3D (iaCovMatern.R:413-548) ----------------------------------------
+ * xy: n x 2, dI: n x 2 (already rounded to the cm by the caller, fitIAK3D.R:127), W = cbind(X, z)
+ * (fitIAK3D.R:757): n x q with q = p + 1 (W may be NULL with q = 0 when only C is wanted).
+ * Unique locations / intervals keep first-occurrence order (`!duplicated`, iaCovMatern.R:418-419). */
+IAK3D_API int iak3d_dataset_create(iak3d_ctx* ctx, int64_t n, const double* xy, const double* dI,
+                         const double* W, int32_t q, iak3d_ds** out);
+IAK3D_API int iak3d_dataset_destroy(iak3d_ds* ds);
+IAK3D_API int iak3d_dataset_set_W(iak3d_ds* ds, const double* W, int32_t q);
+IAK3D_API int iak3d_dataset_info(iak3d_ds* ds, int64_t* n, int64_t* nxU, int64_t* ndIU, int32_t* q);
+/* 0-based ids of each row's unique location / unique depth interval (Kx, Kd as id vectors) */
+IAK3D_API int iak3d_dataset_ids(iak3d_ds* ds, int32_t* xid, int32_t* did);
+
+/* ---- depth / horizontal kernels on unique pairs ---------------------------------------------
+ * iaCovMatern2 (iaCovMatern.R:107-191): out is n1 x n2 column-major; avVar (n1) may be NULL
+ * (avVarVec of set 1, iaCovMatern.R:53-54).  sdfdType in {0,-1}. */
+IAK3D_API int iak3d_iacov(iak3d_ctx* ctx, int64_t n1, const double* dI1, int64_t n2, const double* dI2,
+                double ad, double nud, int32_t sdfdType, const double* sdfdPars,
+                double* out, double* avVar);
+/* spatialCovIAK3D (iaCovMatern.R:327-408) applied element-wise to m distances, pars = (c1,a,nu) */
+IAK3D_API int iak3d_spatial_cov(iak3d_ctx* ctx, int64_t m, const double* D, int32_t modelx,
+                      double c1, double a, double nu, double* out);
+
+/* ---- covariance assembly --------------------------------------------------------------------
+ * setCIAK3D (fitIAK3D.R:955-1112): C (n x n, full symmetric, may be NULL) and sigma2Vec (n, may
+ * be NULL). */
+IAK3D_API int iak3d_cov_build(iak3d_ds* ds, const iak3d_pars* pars, double* C, double* sigma2Vec);
+/* setCIAK3D2 (fitIAK3D.R:1117-1252): cross-covariance between set 1 (n1 rows given here) and the
+ * dataset (set 2); out is n1 x n, no cme (fitIAK3D.R:1243). */
+IAK3D_API int iak3d_cov_cross(iak3d_ds* ds2, const iak3d_pars* pars, int64_t n1, const double* xy1,
+                    const double* dI1, double* out);
+
+/* ---- factorisation --------------------------------------------------------------------------
+ * lndetANDinvCb (optim_functions.R:268-312, methodSolveTEST == 1): chol(C), lndetC = 2 sum log diag,
+ * invCb = C^-1 b (n x nrhs) or C^-1 itself when b == NULL (then invCb is n x n).  Returns
+ * IAK3D_NOT_SPD where the reference returns NA. */
+IAK3D_API int iak3d_lndet_invCb(iak3d_ctx* ctx, int64_t n, const double* C, int32_t nrhs, const double* b,
+                      double* lndetC, double* invCb);
+
+/* ---- likelihood terms == nllIAK3D(..., forCompLik = TRUE) (fitIAK3D.R:730-819) ---------------
+ * Builds A = setCIAK3D(pars), factorises it and returns lndetA and WiAW = t(W) A^-1 W (q x q).
+ * iAW (n x q, A^-1 W; fitIAK3D.R:782-808) is optional (NULL to skip the back-substitution). */
+IAK3D_API int iak3d_nll_terms(iak3d_ds* ds, const iak3d_pars* pars, double* lndetA, double* WiAW, double* iAW);
+/* The same for `count` independent (dataset, parameter) pairs in one launch: the composite-
+ * likelihood block loop (compositeLikIAK3D.R:49-93,105-155; mcmapply over blocks) and the forward-
+ * difference gradient (fitIAK3D.R:1865-1886; npar+1 evaluations).  status[i] is per evaluation;
+ * lndetA[i], WiAW + i*q*q are outputs.  All datasets must share q. */
+IAK3D_API int iak3d_nll_terms_batch(iak3d_ctx* ctx, int32_t count, iak3d_ds* const* ds, const iak3d_pars* pars,
+                          double* lndetA, double* WiAW, int32_t* status);
+/* split form for device-resident timing: enqueue on the context stream, then fetch (sync + D2H). */
+IAK3D_API int iak3d_nll_terms_batch_enqueue(iak3d_ctx* ctx, int32_t count, iak3d_ds* const* ds, const iak3d_pars* pars);
+IAK3D_API int iak3d_nll_terms_batch_fetch(iak3d_ctx* ctx, double* lndetA, double* WiAW, int32_t* status);
+
+/* ---- kept fit == the big matrices of lmmFit (fitIAK3D.R:919-936; predictIAK3D.R:110-139) -----
+ * pars are the RESCALED parameters (cxdhat folded in, fitIAK3D.R:857-863), so C = setCIAK3D(pars).
+ * betahat (p), vbetahat (p x p).  Computes and keeps L = chol(C), iCX, iCz_muhat on the device. */
+IAK3D_API int iak3d_fit_create(iak3d_ds* ds, const iak3d_pars* pars, const double* betahat, const double* vbetahat,
+                     iak3d_fit** out);
+IAK3D_API int iak3d_fit_destroy(iak3d_fit* fit);
+/* copies out what lmmFit carries: iCX (n x p), iCz_muhat (n), and optionally C and iC (n x n, NULL to skip) */
+IAK3D_API int iak3d_fit_get(iak3d_fit* fit, double* iCX, double* iCz_muhat, double* C, double* iC);
+
+/* ---- block kriging == per-batch body of predictIAK3D (predictIAK3D.R:179-208,229-255) --------
+ * m prediction supports (location, depth interval) with design rows XMap (m x p, column-major).
+ * z (m), v (m) = universal-kriging prediction and variance incl. beta uncertainty. */
+IAK3D_API int iak3d_predict(iak3d_fit* fit, int64_t m, const double* xyMap, const double* dIMap, const double* XMap,
+                  double* z, double* v);
+/* device-resident variant for timing: inputs staged by iak3d_predict_stage, results by _fetch */
+IAK3D_API int iak3d_predict_stage(iak3d_fit* fit, int64_t m, const double* xyMap, const double* dIMap, const double* XMap);
+IAK3D_API int iak3d_predict_enqueue(iak3d_fit* fit);
+IAK3D_API int iak3d_predict_fetch(iak3d_fit* fit, double* z, double* v);
+
+/* ---- Newton-Raphson terms == gradHessIAK3D (nrUpdatesIAK3D.R:118-216) -----------------------
+ * Components dA_i are the unit-variance terms of setCIAK3D in the order cx0, cx1, cd1, cxd0, cxd1,
+ * cme (ncomp = 5 or 6); lnvPars (ncomp) their log-variances.  Outputs: nll, grad (ncomp), hess and
+ * fim (ncomp x ncomp), betahat (p), vbetahat (p x p). */
+IAK3D_API int iak3d_gradhess(iak3d_ds* ds, const iak3d_pars* pars, int32_t ncomp, const double* lnvPars,
+                   double* nll, double* grad, double* hess, double* fim, double* betahat, double* vbetahat);
+
+/* ---- measurement helpers (bench.py) ---------------------------------------------------------- */
+IAK3D_API int iak3d_sync(iak3d_ctx* ctx);
+IAK3D_API int iak3d_timer_start(iak3d_ctx* ctx);                 /* cudaEventRecord on the context stream */
+IAK3D_API int iak3d_timer_stop(iak3d_ctx* ctx, double* ms);      /* record + synchronize + elapsed */
+IAK3D_API int iak3d_flush_l2(iak3d_ctx* ctx);                    /* writes a 256 MiB scratch buffer */
+/* FP64 peak microbenchmarks: kind 0 = DFMA (vector), 1 = DMMA (mma.sync m8n8k4 f64). */
+IAK3D_API int iak3d_fp64_peak(iak3d_ctx* ctx, int32_t kind, double* tflops);
+/* per-stage device times (ms) of the last nll_terms_batch_enqueue: [0] table kernels, [1] covariance
+ * build, [2] factorisation, [3] finish; and the algorithmic flop / byte counts of that launch. */
+IAK3D_API int iak3d_last_stage_ms(iak3d_ctx* ctx, double* ms4, double* chol_flops, double* cov_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IAK3D_H */

@@ -1,0 +1,187 @@
+"""Pins the CPU oracle (oracle/iak3d_oracle.py): known-answer vectors, an independent quadrature of the defining
+integral, the reference's own (dead) consistency checks, and LAPACK identities.  The reference ships no tests for
+this path, so these are the anchors the oracle's header lists."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import scipy.integrate as sint
+import scipy.special as ssp
+
+from iak3d_b200 import synth
+from oracle import iak3d_oracle as orc
+from helpers import MODEL_CASES, PARBNDS, case_pars, relerr
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _kat():
+    with open(os.path.join(HERE, "golden", "iacov_kat.json")) as f:
+        return json.load(f)
+
+
+def test_iacov_known_answers():
+    kat = _kat()
+    for case in kat["cases"]:
+        for (nud, st), want in zip(kat["columns"], case["values"]):
+            got = orc.iaCovMatern2([case["I1"]], [case["I2"]], kat["ad"], nud, kat["sdfdPars"], st)[0, 0]
+            assert abs(got - want) <= 2e-15 * abs(want) + 1e-16, (case["case"], nud, st, got, want)
+
+
+def _point_cov(h, ad, nud):
+    x = np.abs(h) / ad
+    if nud == 0.5:
+        return np.exp(-x)
+    if nud == 1.5:
+        return (1 + math.sqrt(3) * x) * np.exp(-math.sqrt(3) * x)
+    return (1 + math.sqrt(5) * x + 5 * x * x / 3) * np.exp(-math.sqrt(5) * x)
+
+
+@pytest.mark.parametrize("nud", [0.5, 1.5, 2.5])
+@pytest.mark.parametrize("st", [0, -1])
+def test_iacov_against_quadrature(nud, st):
+    ad, sp = 0.35, (0.6, 1.7)
+    s = (lambda d: 1.0) if st == 0 else (lambda d: (1 - sp[0]) + sp[0] * math.exp(-sp[1] * d))
+    for (a, b, c, d) in [(0.0, 0.1, 0.3, 0.6), (0.0, 0.3, 0.15, 0.6), (0.0, 1.0, 0.2, 0.5), (0.05, 0.15, 0.05, 0.15)]:
+        # split at the kink |x - y| = 0 by integrating x over [a,b] and y over the two sides
+        f = lambda y, x: s(x) * s(y) * _point_cov(x - y, ad, nud)
+        val = 0.0
+        for (ylo, yhi) in [(c, d)]:
+            val, _ = sint.dblquad(f, a, b, lambda x: ylo, lambda x: yhi, epsabs=1e-13, epsrel=1e-12)
+        want = val / ((b - a) * (d - c))
+        got = orc.iaCovMatern2([[a, b]], [[c, d]], ad, nud, sp, st)[0, 0]
+        assert abs(got - want) <= 5e-8 * abs(want)   # dblquad across the kink is the limiting accuracy here
+
+
+def test_iacov_square_equals_rectangular_and_symmetric():
+    ds = synth.make_dataset(300, 11)
+    sm = orc.setupIAK3D(ds["xData"], ds["dIData"])
+    for nud in (0.5, 1.5, 2.5):
+        for st, sp in ((0, (1, 0, 1)), (-1, (0.6, 1.7))):
+            M, av = orc.iaCovMatern(sm["dIU"], 0.35, nud, sp, st)
+            R = orc.iaCovMatern2(sm["dIU"], sm["dIU"], 0.35, nud, sp, st)
+            assert relerr(M, R) <= 1e-13
+            assert np.allclose(M, M.T, rtol=0, atol=0)
+            # diag of the averaged covariance <= averaged variance (Cauchy-Schwarz) and both positive
+            assert np.all(np.diag(M) > 0) and np.all(av > 0)
+
+
+def test_iacov_discretisation_converges():
+    """iaCovDsc (iaCovMatern.R:709-739), the reference's own cross-check, converges to the closed form."""
+    dI = np.array([[0.0, 0.1], [0.1, 0.3], [0.3, 0.6], [0.05, 0.5]])
+    M, _ = orc.iaCovMatern(dI, 0.35, 1.5, (0.6, 1.7), -1)
+    e50 = np.max(np.abs(orc.iaCovDsc(dI, 0.35, 1.5, (0.6, 1.7), -1, 50) - M))
+    e200 = np.max(np.abs(orc.iaCovDsc(dI, 0.35, 1.5, (0.6, 1.7), -1, 200) - M))
+    assert e200 < e50 < 2e-3 and e200 < 2e-4
+
+
+def test_matern_halfinteger_closed_forms():
+    D = np.array([0.0, 1e-6, 0.3, 2.0, 17.0, 200.0])
+    for nu, f in ((0.5, lambda x: np.exp(-x)), (1.5, lambda x: (1 + x) * np.exp(-x)),
+                  (2.5, lambda x: (1 + x + x * x / 3) * np.exp(-x))):
+        got = orc.spatialCovIAK3D(D, [1.0, 10.0, nu], "matern")
+        want = f(math.sqrt(2 * nu) * D / 10.0)
+        assert relerr(got[1:], want[1:]) < 5e-13 and got[0] == 1.0
+
+
+def test_spatial_cov_edge_cases():
+    # the "distant" prediction point (9E99, 9E99): exactly 0, never NaN
+    D = np.array([math.sqrt(2.0) * 9e99])
+    assert orc.spatialCovIAK3D(D, [1.0, 25.0, None], "spherical")[0] == 0.0
+    assert orc.spatialCovIAK3D(D, [1.0, 25.0, 0.8], "matern")[0] == 0.0
+    assert orc.spatialCovIAK3D(np.array([1.0]), [1.0, -1.0, 0.5], "matern") is None
+    assert orc.spatialCovIAK3D(np.array([1.0]), [1.0, 1.0, 25.0], "matern") is None
+    w = orc.spatialCovIAK3D(np.array([0.0, 15.0, 30.0, 31.0]), [1.0, 30.0, 2.4], "wendland")
+    assert w[0] == pytest.approx(1.0, abs=1e-14) and w[2] == 0.0 and w[3] == 0.0 and 0 < w[1] < 1
+
+
+@pytest.mark.parametrize("label,kind,nonstat,nud", MODEL_CASES)
+def test_cross_equals_square_minus_nugget(label, kind, nonstat, nud):
+    """setCIAK3D2(S,S) + cme I == setCIAK3D(S): the reference's own (dead) 1e-8 check, compositeLikIAK3D.R:382."""
+    ds = synth.make_dataset(160, 5)
+    P, modelx, types, cmeOpt = case_pars(kind, nonstat, nud)
+    sm = orc.setupIAK3D(ds["xData"], ds["dIData"])
+    Cs, s2 = orc.setCIAK3D(P, modelx, *types, cmeOpt, sm, quirk_cd1_unscaled=False)
+    sm2 = orc.setupIAK3D2(ds["xData"], ds["dIData"], ds["xData"], ds["dIData"])
+    Cx = orc.setCIAK3D2(P, modelx, *types, cmeOpt, sm2)
+    assert np.max(np.abs(Cx + P["cme"] * np.eye(160) - Cs)) <= 1e-13
+    assert np.all(s2 >= np.diag(Cs) - 1e-12)           # point variance >= increment-averaged variance
+
+
+def test_cd1_quirk_is_reproduced():
+    ds = synth.make_dataset(100, 5)
+    P, modelx, types, cmeOpt = case_pars("matern0.5", True, 0.5)
+    sm = orc.setupIAK3D(ds["xData"], ds["dIData"])
+    Cq, _ = orc.setCIAK3D(P, modelx, *types, cmeOpt, sm, quirk_cd1_unscaled=True)
+    Cn, _ = orc.setCIAK3D(P, modelx, *types, cmeOpt, sm, quirk_cd1_unscaled=False)
+    Phi, _ = orc.iaCovMatern(sm["dIU"], P["ad"], P["nud"], P["sdfdPars_cd1"], -1)
+    want = (1.0 - P["cd1"]) * Phi[sm["did"][:, None], sm["did"][None, :]]
+    assert np.max(np.abs((Cq - Cn) - want)) < 1e-14
+
+
+def test_likelihood_against_dense_formula():
+    ds = synth.make_dataset(250, 3)
+    P, modelx, types, cmeOpt = case_pars("matern0.5", False, 0.5)
+    sm = orc.setupIAK3D(ds["xData"], ds["dIData"])
+    A, _ = orc.setCIAK3D(P, modelx, *types, cmeOpt, sm)
+    X, z = ds["XData"], ds["zData"]
+    n, p = X.shape
+    nll = orc.nllIAK3D(None, z, X, modelx, 0.5, *types, cmeOpt, True, sm, PARBNDS, useReml=True, parsBTfmd=P)
+    iA = np.linalg.inv(A)
+    XiAX = X.T @ iA @ X
+    beta = np.linalg.solve(XiAX, X.T @ iA @ z)
+    r = z - X @ beta
+    s2 = float(r @ iA @ r) / (n - p)
+    want = 0.5 * ((n - p) * math.log(2 * math.pi) + np.linalg.slogdet(s2 * A)[1] + np.linalg.slogdet(XiAX / s2)[1] + (n - p))
+    assert abs(nll - want) <= 1e-9 * abs(want)
+
+
+def test_cl_single_block_equals_exact():
+    ds = synth.make_dataset(200, 9)
+    P, modelx, types, cmeOpt = case_pars("edgeroi", False, 0.5)
+    sm = orc.setupIAK3D(ds["xData"], ds["dIData"])
+    exact = orc.nllIAK3D(None, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True, sm, PARBNDS, useReml=True, parsBTfmd=P)
+    cl = dict(compLikOptn=4, listBlocks=[np.arange(200)], subsetPairsAdj=np.zeros((0, 2), int), subsetPairsNonadj=np.zeros((0, 2), int))
+    got = orc.nllIAK3D_CL(None, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True, PARBNDS, True, cl, ds["xData"],
+                          ds["dIData"], parsBTfmd=P)
+    assert abs(got - exact) <= 1e-12 * abs(exact)
+
+
+def test_kriging_reproduces_data_without_measurement_error():
+    ds = synth.make_dataset(150, 21)
+    P, modelx, types, _ = case_pars("matern0.5", False, 0.5)
+    P = dict(P); P["cme"] = 0.0
+    sm = orc.setupIAK3D(ds["xData"], ds["dIData"])
+    fit = orc.nllIAK3D(None, ds["zData"], ds["XData"], modelx, 0.5, *types, 0, True, sm, PARBNDS, useReml=True, rtnAll=True, parsBTfmd=P)
+    fit["xData"], fit["dIData"] = ds["xData"], ds["dIData"]
+    sel = np.array([3, 40, 77])
+    zs, vs = [], []
+    for i in sel:
+        z, v, _, _ = orc.predictIAK3D(ds["xData"][i:i + 1], ds["dIData"][i:i + 1], lambda k, idx: ds["XData"][i:i + 1], fit,
+                                      modelx, types, 0)
+        zs.append(z[0, 0]); vs.append(v[0, 0])
+    assert np.allclose(zs, ds["zData"][sel], rtol=1e-8)
+    assert np.max(np.abs(vs)) < 1e-7
+
+
+def test_gradhess_matches_finite_differences():
+    ds = synth.make_dataset(120, 4)
+    P, modelx, types, cmeOpt = case_pars("matern0.5", False, 0.5)
+    sm = orc.setupIAK3D(ds["xData"], ds["dIData"])
+    dA = orc.component_matrices(P, modelx, types, sm)
+    th = np.log([P[k] for k in ("cx0", "cx1", "cd1", "cxd0", "cxd1", "cme")])
+    W = np.column_stack([ds["XData"], ds["zData"]])
+    g = orc.gradHessIAK3D(dA, th, W)
+    for i in range(6):
+        e = np.zeros(6); e[i] = 1e-5
+        fd = (orc.gradHessIAK3D(dA, th + e, W)["nll"] - orc.gradHessIAK3D(dA, th - e, W)["nll"]) / 2e-5
+        assert abs(fd - g["grad"][i]) <= 1e-5 * max(1.0, abs(g["grad"][i]))
+
+
+def test_bessel_reference_values():
+    # scipy.special.kv (the oracle's Bessel) against mpmath-free closed forms for half-integer orders
+    x = np.array([0.01, 0.5, 2.0, 9.0, 40.0])
+    assert relerr(ssp.kv(0.5, x), np.sqrt(np.pi / (2 * x)) * np.exp(-x)) < 1e-14
+    assert relerr(ssp.kv(1.5, x), np.sqrt(np.pi / (2 * x)) * np.exp(-x) * (1 + 1 / x)) < 1e-14
