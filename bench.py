@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- REML log-likelihood evaluations per second on the 5k-interval single-block workload
+(BASELINE.json configs[1]) and the other hot-path workloads, on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W [--workload s5|cl|krige] [--impl ours|reference]
+
+A step (default workload `s5`) is one forward-difference gradient of the REML objective as the optimiser asks for
+it (gradnllIAK3D, fitIAK3D.R:1865-1886): npar + 1 likelihood evaluations -- covariance build + Cholesky + solves
+each -- sent to the GPU as one batch.  `value` times the library calls with the dataset resident in HBM; `e2e`
+goes through the reference-facing call with host buffers (W re-uploaded from host memory each step, results read
+back, REML tail on the host).  Single-block REML does not shard ("replicas only"), so --gpus N runs N
+independent replicas and reports weak scaling; `--workload cl` and `--workload krige` are the workloads that shard.
+One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PARBNDS = dict(axBnds=(0.05, 60.0), nuxBnds=(0.05, 20.0), adBnds=(0.02, 1.2), tau2Bnds=(0.01, 20.0),
+               sxd1Bnds=(1e-8, 1.0 - 1e-8), maxd=2.0)
+METRIC = "REML loglik evals/sec at n obs"
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    _REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                try:
+                    r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self._REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=2.0)
+        if not self.samples:
+            try:    # one-shot fallback through the CLI
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+                a, b = [float(x) for x in out.strip().split(",")[:2]]
+                self.samples, self.max_mhz = [a], b
+            except Exception:
+                pass
+        med = float(np.median(self.samples)) if self.samples else None
+        return dict(sm_mhz=med, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons), samples=len(self.samples))
+
+
+# ---------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------
+def s5_inputs(n):
+    from iak3d_b200 import synth
+    ds = synth.make_dataset(n, synth.SEEDS["S5"])
+    P, modelx, types, cmeOpt = synth.default_pars("matern0.5")
+    # unconstrained vector of the matern / prodSum / cd1 / cme model: ax, nux, ad, cx0, cx1, cd1, cxd1, cme (npar = 8)
+    from iak3d_b200 import api
+    pars = np.array([float(api.logitab(P["ax"], *PARBNDS["axBnds"])), float(api.logitab(P["nux"], *PARBNDS["nuxBnds"])),
+                     float(api.logitab(P["ad"], *PARBNDS["adBnds"])), np.log(P["cx0"]), np.log(P["cx1"]), np.log(P["cd1"]),
+                     float(api.logitab(P["cxd1"], *PARBNDS["sxd1Bnds"])), np.log(P["cme"])])
+    return ds, pars, modelx, types, cmeOpt
+
+
+def fd_candidates(pars, step_no, delta=1e-6):
+    """pars and its npar forward-difference neighbours; the base point moves a little every step, as it does along
+    an optimiser's path (no two steps evaluate the same matrices)."""
+    base = pars + 1e-3 * np.sin(0.7 * step_no + np.arange(pars.size))
+    out = [base.copy()]
+    for i in range(pars.size):
+        v = base.copy(); v[i] += delta
+        out.append(v)
+    return out
+
+
+def run_s5(args, rank, local_rank, world, comm):
+    import ctypes as C
+    import iak3d_b200 as iak
+    from iak3d_b200 import api
+    from iak3d_b200._lib import Pars, make_pars, dptr, iptr
+
+    n = args.n
+    ds, pars, modelx, types, cmeOpt = s5_inputs(n)
+    ctx = iak.Context(local_rank)
+    W = np.asfortranarray(np.column_stack([ds["XData"], ds["zData"]]))
+    p = ds["XData"].shape[1]; q = p + 1
+    sm = iak.SetupMats(ds["xData"], ds["dIData"], W=W, ctx=ctx)
+    nb = pars.size + 1
+    lib = ctx.lib
+    dsarr = (C.c_void_p * nb)(*[sm.h] * nb)
+    lnd = np.empty(nb); G = np.empty((nb, q * q)); st = np.empty(nb, np.int32)
+
+    def structs(step_no):
+        arr = (Pars * nb)()
+        for i, v in enumerate(fd_candidates(pars, step_no)):
+            pb = api.readParsIAK3D(v, modelx, 0.5, *types, cmeOpt, True, PARBNDS)
+            arr[i] = make_pars(pb, modelx, *types, cmeOpt)
+        return arr
+
+    def step_resident(step_no):
+        ctx.check(lib.iak3d_nll_terms_batch_enqueue(ctx.h, nb, dsarr, structs(step_no)))
+        ctx.check(lib.iak3d_nll_terms_batch_fetch(ctx.h, dptr(lnd), dptr(G), iptr(st)))
+
+    def step_e2e(step_no):
+        """the reference-facing call: host W in, nll values out"""
+        sm.upload_W(W)
+        lnd_, G_, st_ = api.nll_terms_batch(ctx, [sm] * nb, list(structs(step_no)))
+        return [api.reml_tail(api._symm_upper(G_[i].T), lnd_[i], n, p, True)["nll"] for i in range(nb)]
+
+    peaks = dict(dfma=ctx.fp64_peak(0), dmma=ctx.fp64_peak(1))
+    for w in range(args.warmup):
+        step_resident(-1 - w)
+    assert np.all(st == 0), f"warm-up evaluations failed: {st}"
+    ctx.sync()
+
+    # ---- device-resident timing (value) ----
+    clk = ClockSampler(local_rank)
+    comm.barrier(); ctx.sync()
+    l0 = ctx.launch_count()
+    clk.start()
+    stage = np.zeros(4)
+    ctx.timer_start()
+    for k in range(args.steps):
+        step_resident(k)
+        ms4, flops, cov_bytes = ctx.last_stage_ms()
+        stage += np.array(ms4)
+    ms_total = ctx.timer_stop()
+    comm.barrier(); ctx.sync()
+    clocks = clk.stop()
+    launches = ctx.launch_count() - l0
+    ms_total = float(comm.allreduce_max(np.array([ms_total]))[0])
+    stage /= args.steps
+
+    # ---- single-evaluation latency (the optimiser's fn call) ----
+    one = (C.c_void_p * 1)(sm.h)
+    ctx.sync(); ctx.timer_start()
+    reps = max(3, min(20, args.steps))
+    for k in range(reps):
+        ctx.check(lib.iak3d_nll_terms_batch_enqueue(ctx.h, 1, one, structs(k)))
+        ctx.check(lib.iak3d_nll_terms_batch_fetch(ctx.h, dptr(lnd), dptr(G), iptr(st)))
+    single_ms = ctx.timer_stop() / reps
+
+    # ---- end to end through the plugin call (e2e) ----
+    for w in range(min(args.warmup, 3)):
+        step_e2e(-1 - w)
+    comm.barrier(); ctx.sync()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        vals = step_e2e(k)
+    ctx.sync()
+    e2e_s = time.perf_counter() - t0
+    e2e_s = float(comm.allreduce_max(np.array([e2e_s]))[0])
+    assert all(np.isfinite(v) and v < 1e90 for v in vals)
+
+    evals = nb * args.steps * world
+    value = evals / (ms_total * 1e-3)
+    tf = (nb * n ** 3 / 3.0) / (stage[2] * 1e-3) / 1e12
+    cov_gbs = (nb * 8.0 * n * (n + 1) / 2.0) / (stage[1] * 1e-3) / 1e9
+    hbm_peak, hbm_src = measured_peak("hbm_gbs", 6650.0)
+    out = dict(
+        metric=METRIC, value=value, unit="evals/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+        ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+        config=dict(workload=f"synthetic {n}-interval single-block REML: iaCovMatern build + Cholesky loglik (BASELINE configs[1])",
+                    n=n, p=p, nxU=sm.nxU, ndIU=sm.ndIU, modelx=modelx, nux=0.5, nud=0.5, sdfdTypes=list(types), cmeOpt=cmeOpt,
+                    evals_per_step=nb, step="one forward-difference gradient (npar+1 evaluations in one batch)",
+                    parallelism="replicas only" if world > 1 else "1 GPU",
+                    l2="working set (factor buffers %.0f MB) exceeds the 126 MB L2; no flush needed" % (nb * 8.0 * n * n / 1e6)),
+        single_eval_ms=single_ms, single_eval_per_s=1e3 / single_ms,
+        stage_ms=dict(tables=stage[0], cov_build=stage[1], factorise=stage[2], finish=stage[3]),
+        roofline=dict(kernel="tile_task_kernel (tile Cholesky + bordered solves, FP64 DMMA)", bound="tensor", achieved=tf,
+                      peak=peaks["dmma"], unit="TFLOP/s", frac=tf / peaks["dmma"], traffic=None,
+                      flops_per_launch=nb * n ** 3 / 3.0,
+                      peak_source="FP64 mma.sync m8n8k4 microbenchmark run inside this bench (MEASURED_PEAKS.json holds no FP64 "
+                                  "figure); DFMA microbenchmark = %.1f TFLOP/s" % peaks["dfma"]),
+        roofline_cov_build=dict(kernel="cov_factor_kernel", bound="hbm", achieved=cov_gbs, peak=hbm_peak, unit="GB/s",
+                                frac=cov_gbs / hbm_peak, bytes_per_launch=8.0 * n * (n + 1) / 2.0, peak_source=hbm_src),
+        e2e=dict(value=evals / e2e_s, unit="evals/s", h2d_bytes_per_step=int(W.nbytes + nb * C.sizeof(Pars)),
+                 d2h_bytes_per_step=int(nb * (2 + q * q) * 8)),
+        gpu_launches=int(launches), clocks=clocks)
+    return out, ctx
+
+
+def measured_peak(key, fallback):
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)[key]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return fallback, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline_s5(n, budget_s=20.0):
+    """The oracle (NumPy/SciPy port of the reference algorithm; R is not installed) on the host cores."""
+    from oracle import iak3d_oracle as orc
+    from iak3d_b200 import synth
+    ds = synth.make_dataset(n, synth.SEEDS["S5"])
+    P, modelx, types, cmeOpt = synth.default_pars("matern0.5")
+    sm = orc.setupIAK3D(ds["xData"], ds["dIData"])
+    f = lambda: orc.nllIAK3D(None, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True, sm, PARBNDS, useReml=True, parsBTfmd=P)
+    f()
+    t0 = time.perf_counter(); k = 0
+    while True:
+        f(); k += 1
+        if time.perf_counter() - t0 > budget_s or k >= 20:
+            break
+    dt = time.perf_counter() - t0
+    return dict(value=k / dt, unit="evals/s", cores=os.cpu_count(), kind="port",
+                sample=f"{k} single evaluations of the same n={n} workload by oracle/iak3d_oracle.nllIAK3D (NumPy/SciPy, OpenBLAS "
+                       f"threads = host cores); R is not installed, so this is a port, not the R reference")
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference algorithm's CPU implementation (oracle port) on the host cores."""
+    if rank != 0:
+        return None
+    from oracle import iak3d_oracle as orc
+    from iak3d_b200 import synth
+    n = args.n
+    ds = synth.make_dataset(n, synth.SEEDS["S5"])
+    P, modelx, types, cmeOpt = synth.default_pars("matern0.5")
+    sm = orc.setupIAK3D(ds["xData"], ds["dIData"])
+    f = lambda: orc.nllIAK3D(None, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True, sm, PARBNDS, useReml=True, parsBTfmd=P)
+    t0 = time.perf_counter(); f(); t1 = time.perf_counter() - t0
+    warm = max(0, min(args.warmup, 1))
+    budget = 150.0
+    steps = int(max(1, min(args.steps, budget // max(t1, 1e-3))))
+    for _ in range(warm):
+        f()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        f()
+    dt = time.perf_counter() - t0
+    v = steps / dt
+    cb = dict(value=v, unit="evals/s", cores=os.cpu_count(), kind="port",
+              sample=f"{steps} single evaluations (one of the npar+1 evaluations of a step each) of the n={n} workload, oracle port "
+                     "(NumPy/SciPy + OpenBLAS, all host cores); the reference is R and R is not installed")
+    return dict(impl="reference", metric=METRIC, value=v, unit="evals/s", n_gpus=world, steps=steps, steps_requested=args.steps,
+                warmup=warm, ms_per_step=1e3 * dt / steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                data="synthetic",
+                config=dict(workload=f"synthetic {n}-interval single-block REML: iaCovMatern build + Cholesky loglik (BASELINE configs[1])",
+                            n=n, p=ds["XData"].shape[1]),
+                cpu_baseline=cb, e2e=dict(value=v, unit="evals/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="s5", choices=["s5", "cl", "krige"])
+    ap.add_argument("--n", type=int, default=5000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    from iak3d_b200 import parallel
+    rank, local_rank, world = parallel.dist_env()
+    if args.impl == "reference":
+        out = run_reference(args, rank, world)
+        if out is not None:
+            print(json.dumps(out), flush=True)
+        return 0
+    parallel.init()
+    comm = parallel.BlockComm()
+    if args.workload == "s5":
+        out, ctx = run_s5(args, rank, local_rank, world, comm)
+    else:
+        import bench_extra
+        out, ctx = bench_extra.run(args, rank, local_rank, world, comm)
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline and args.workload == "s5":
+            out["cpu_baseline"] = cpu_baseline_s5(args.n)
+        print(json.dumps(out), flush=True)
+    ctx.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -3,6 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -24,7 +25,7 @@ class Pars(C.Structure):
         ("modelx", C.c_int32), ("cmeOpt", C.c_int32), ("sdfdType", C.c_int32 * 3), ("quirk_cd1_unscaled", C.c_int32),
         ("ax", C.c_double), ("nux", C.c_double), ("ad", C.c_double), ("nud", C.c_double),
         ("cx0", C.c_double), ("cx1", C.c_double), ("cd1", C.c_double), ("cxd0", C.c_double), ("cxd1", C.c_double),
-        ("cme", C.c_double), ("sdfdPars", (C.c_double * 2) * 3),
+        ("cme", C.c_double), ("sdfdPars", (C.c_double * 2) * 3), ("quirk_scale", C.c_double),
     ]
 
 
@@ -103,7 +104,7 @@ def f64(a, order="F"):
     return np.require(np.asarray(a, dtype=np.float64), dtype=np.float64, requirements=["F" if order == "F" else "C", "A"])
 
 
-def make_pars(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, quirk_cd1_unscaled=True):
+def make_pars(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, quirk_cd1_unscaled=True, quirk_scale=1.0):
     """parsBTfmd (the list readParsIAK3D returns, fitIAK3D.R:1405-1408) -> struct iak3d_pars."""
     P = Pars()
     P.modelx = MODELX[modelx]
@@ -112,6 +113,7 @@ def make_pars(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cme
     for i, t in enumerate(types):
         P.sdfdType[i] = t
     P.quirk_cd1_unscaled = 1 if quirk_cd1_unscaled else 0
+    P.quirk_scale = float(quirk_scale)
     g = lambda k: float(np.asarray(parsBTfmd[k]).reshape(-1)[0]) if np.size(parsBTfmd[k]) else float("nan")
     P.ax, P.nux, P.ad, P.nud = g("ax"), g("nux"), g("ad"), g("nud")
     P.cx0, P.cx1, P.cd1, P.cxd0, P.cxd1, P.cme = g("cx0"), g("cx1"), g("cd1"), g("cxd0"), g("cxd1"), g("cme")
@@ -136,6 +138,10 @@ class Context:
                              "(there is no CPU fallback)")
         self.h = h
         self.device = int(device)
+        self._children = weakref.WeakSet()     # datasets / kept fits: destroyed before the context
+
+    def adopt(self, child):
+        self._children.add(child)
 
     def check(self, st, allow=()):
         if st == OK or st in allow:
@@ -145,6 +151,9 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h.value:
+            kids = sorted(list(self._children), key=lambda c: getattr(c, "_close_order", 1))
+            for c in kids:
+                c.close()
             self.lib.iak3d_ctx_destroy(self.h)
             self.h = _vp()
 

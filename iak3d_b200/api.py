@@ -119,6 +119,7 @@ class SetupMats:
             Wp, q = dptr(self._W), self._W.shape[1]
         self.ctx.check(self.ctx.lib.iak3d_dataset_create(self.ctx.h, self.n, dptr(self.xData), dptr(self.dIData), Wp, q, C.byref(h)))
         self.h = h
+        self.ctx.adopt(self)
         n_, nx, nd, q_ = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
         self.ctx.check(self.ctx.lib.iak3d_dataset_info(self.h, C.byref(n_), C.byref(nx), C.byref(nd), C.byref(q_)))
         self.nxU, self.ndIU, self.q = nx.value, nd.value, q_.value
@@ -354,7 +355,7 @@ def nllIAK3D(pars, zData, XData, vXU=None, iU=None, modelx="matern", nud=0.5, sd
                cmeOpt=cmeOpt, setupMats=sm, xData=sm.xData, dIData=sm.dIData)
     if attachBigMats:
         # the big matrices stay on the device as a kept factorisation (iak3d_fit); iCX / iCz_muhat are copied out
-        fit = KeptFit(sm, parsBTfmd, modelx, (sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1), cmeOpt, betahat, vbetahat)
+        fit = KeptFit(sm, parsBTfmd, modelx, (sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1), cmeOpt, betahat, vbetahat, cxdhat)
         iCX, iCz = fit.get_small()
         out.update(fit=fit, iCX=iCX, iCz_muhat=iCz)
     else:
@@ -495,11 +496,12 @@ def setupIAK3D_CL(xData, dIData, zData, XData, compLikMats, ctx=None, rank=0, wo
 class KeptFit:
     """The big matrices of lmmFit (C, iC, iCX, iCz_muhat) as a factorisation kept on the device (iak3d_fit)."""
 
-    def __init__(self, setupMats, parsBTfmd, modelx, sdfdTypes, cmeOpt, betahat, vbetahat):
+    def __init__(self, setupMats, parsBTfmd, modelx, sdfdTypes, cmeOpt, betahat, vbetahat, cxdhat=1.0):
         sm = setupMats
         self.sm, self.ctx = sm, sm.ctx
         self.p = sm.q - 1
-        P = make_pars(parsBTfmd, modelx, *sdfdTypes, cmeOpt)
+        # C = cxdhat * A (fitIAK3D.R:871): the term the reference adds without its cd1 multiplier (:1052) is scaled too
+        P = make_pars(parsBTfmd, modelx, *sdfdTypes, cmeOpt, quirk_scale=cxdhat)
         b = f64(np.asarray(betahat, float).reshape(-1)); V = f64(np.asarray(vbetahat, float).reshape(self.p, self.p))
         h = C.c_void_p()
         st = self.ctx.check(self.ctx.lib.iak3d_fit_create(sm.h, C.byref(P), dptr(b), dptr(V), C.byref(h)), allow=(NOT_SPD, BAD_PARS))
@@ -507,6 +509,8 @@ class KeptFit:
             raise Iak3dError("fit_create: the fitted covariance matrix is not positive definite" if st == NOT_SPD
                              else "fit_create: invalid parameters")
         self.h = h
+        self._close_order = 0          # kept fits go before their datasets
+        self.ctx.adopt(self)
 
     def get_small(self):
         n, p = self.sm.n, self.p

@@ -98,7 +98,8 @@ int iak_make_plan(iak3d_ctx* ctx, const iak3d_pars* p, bool square, EvalPlan* pl
     }
   }
   pl->kd1 = pl->cd1;
-  if (square && p->sdfdType[0] == -1 && p->quirk_cd1_unscaled) pl->kd1 = 1.0;   // fitIAK3D.R:1052 (sic)
+  if (square && p->sdfdType[0] == -1 && p->quirk_cd1_unscaled)                   // fitIAK3D.R:1052 (sic)
+    pl->kd1 = (p->quirk_scale != 0.0) ? p->quirk_scale : 1.0;
   pl->has_phix = !nugget;
   if (!nugget) {
     const int st = hx_init(&pl->H, p->modelx, p->ax, p->nux);
@@ -235,16 +236,20 @@ extern "C" int iak3d_dataset_set_W(iak3d_ds* ds, const double* W, int32_t q) {
     for (Slot* s : ds->slots) free_slot(s);
     ds->slots.clear();
     cudaFree(ds->d_W); ds->d_W = nullptr;
+    if (ds->h_W) { cudaFreeHost(ds->h_W); ds->h_W = nullptr; }
     ds->q = q;
     ds_geometry(ds);
-    if (q > 0) CUDA_TRY(ctx, cudaMalloc(&ds->d_W, (size_t)ds->n * q * sizeof(double)));
+    if (q > 0) {
+      CUDA_TRY(ctx, cudaMalloc(&ds->d_W, (size_t)ds->n * q * sizeof(double)));
+      CUDA_TRY(ctx, cudaMallocHost(&ds->h_W, (size_t)ds->n * q * sizeof(double)));
+    }
   }
   if (q > 0) {
-    ds->h_W.assign(W, W + (size_t)ds->n * q);
-    CUDA_TRY(ctx, cudaMemcpyAsync(ds->d_W, W, (size_t)ds->n * q * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // the caller's buffer may be reused on return
-  } else {
-    ds->h_W.clear();
+    // caller's (pageable, R-owned) buffer -> pinned staging -> device; the staging copy doubles as the host copy.
+    // A previous asynchronous copy out of the staging buffer must have finished before it is overwritten.
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(ds->h_W, W, (size_t)ds->n * q * sizeof(double));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ds->d_W, ds->h_W, (size_t)ds->n * q * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   }
   return IAK3D_OK;
 }
@@ -288,6 +293,7 @@ extern "C" int iak3d_dataset_destroy(iak3d_ds* ds) {
   cudaStreamSynchronize(ds->ctx->stream);
   for (Slot* s : ds->slots) free_slot(s);
   cudaFree(ds->d_xid); cudaFree(ds->d_did); cudaFree(ds->d_xU); cudaFree(ds->d_dIU); cudaFree(ds->d_W);
+  if (ds->h_W) cudaFreeHost(ds->h_W);
   delete ds;
   return IAK3D_OK;
 }

@@ -29,7 +29,7 @@ struct iak3d_fit {
   iak3d_ds* ds = nullptr;
   iak3d_ctx* ctx = nullptr;
   iak3d_pars pars;
-  EvalPlan plan_sq, plan_x;      // square (Ckk, C) and cross (Ckh) plans of the same parameters
+  EvalPlan plan_sq, plan_x, plan_kk;   // C of the fit, cross-covariance Ckh, and Ckk = diag(setCIAK3D(map)) plans
   Slot* slot = nullptr;          // L, inv diag blocks, Yw rows
   int32_t p = 0, q = 0;
   double* d_W2 = nullptr;        // n x q: [X, z - X betahat]
@@ -94,11 +94,12 @@ extern "C" int iak3d_fit_create(iak3d_ds* ds, const iak3d_pars* pars, const doub
   f->ds = ds; f->ctx = ctx; f->pars = *pars; f->q = ds->q; f->p = ds->q - 1;
   int rc = iak_make_plan(ctx, pars, true, &f->plan_sq);
   if (rc == 0) rc = iak_make_plan(ctx, pars, false, &f->plan_x);
+  if (rc == 0) { iak3d_pars pk = *pars; pk.quirk_scale = 1.0; rc = iak_make_plan(ctx, &pk, true, &f->plan_kk); }
   if (rc == 0 && f->plan_sq.status != 0) rc = f->plan_sq.status;
   if (rc != 0) { delete f; return rc; }
   const int64_t n = ds->n; const int p = f->p, q = f->q;
   // W2 = [X, z - X betahat]  (predictIAK3D.R:111,134)
-  std::vector<double> W2(ds->h_W);
+  std::vector<double> W2(ds->h_W, ds->h_W + (size_t)n * q);
   for (int64_t i = 0; i < n; i++) {
     double mu = 0.0;
     for (int a = 0; a < p; a++) mu = mu + ds->h_W[(size_t)a * n + i] * betahat[a];
@@ -278,7 +279,7 @@ extern "C" int iak3d_predict_enqueue(iak3d_fit* f) {
   Slot* s = f->slot;
   iak3d_ds* ds = f->ds;
   const int64_t nd1 = f->nd1, nd2 = ds->ndIU;
-  const EvalPlan& px = f->plan_x; const EvalPlan& ps = f->plan_sq;
+  const EvalPlan& px = f->plan_x; const EvalPlan& ps = f->plan_kk;
   int rc;
   // depth tables: cross (nd1 x nd2) and self (nd1 x nd1, for Ckk)
   CovArgs a;

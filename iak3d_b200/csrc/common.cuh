@@ -56,7 +56,7 @@ struct iak3d_ds {
   int32_t q = 0;
   std::vector<int32_t> h_xid, h_did;
   std::vector<double> h_xU, h_dIU;       // nxU x 2, ndIU x 2 (column-major)
-  std::vector<double> h_W;               // n x q column-major copy (fit_create forms z - X betahat from it)
+  double* h_W = nullptr;                 // n x q column-major copy in PINNED host memory: staging of the H2D copy
   int32_t *d_xid = nullptr, *d_did = nullptr;
   double *d_xU = nullptr, *d_dIU = nullptr;   // column-major nxU x 2 / ndIU x 2
   double* d_W = nullptr;                  // n x q column-major

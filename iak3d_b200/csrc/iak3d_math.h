@@ -225,7 +225,11 @@ IAK_HD double iak_phix(double D, const HxPrm* H) {
   if (H->modelx == 1) {                                              // spherical :336-348
     const double r = D / H->a;
     if (r > 1.0) return 0.0;
-    return 1.0 - (1.5 * r - 0.5 * (r * r * r));
+    // R evaluates DOVERa^3 with libm pow() (correctly rounded); r*r*r would carry two roundings, and the
+    // expression cancels near the range.  p + e == r*r exactly, so r3 is r^3 rounded (almost always) once.
+    const double p = r * r, e = fma(r, r, -p);
+    const double r3 = fma(p, r, e * r);
+    return 1.0 - (1.5 * r - 0.5 * r3);
   }
   if (H->modelx == 2) {                                              // matern :353-377
     if (D == 0.0) return 1.0;

@@ -53,6 +53,9 @@ typedef struct iak3d_pars {
   double ax, nux, ad, nud; /* nud must be 0.5, 1.5 or 2.5 (iaCovMatern.R:12-29) */
   double cx0, cx1, cd1, cxd0, cxd1, cme;
   double sdfdPars[3][2];   /* (tau1, tau2) of each non-stationary component (iaCovMatern.R:40-43) */
+  double quirk_scale;      /* multiplier of the unscaled cd1 term when quirk_cd1_unscaled applies; 0 is read as 1.
+                              1 while optimising and for Ckk (predictIAK3D.R:183 rebuilds from parsBTfmd); cxdhat for
+                              the kept C = cxdhat * A of a fit (fitIAK3D.R:871) */
 } iak3d_pars;
 
 typedef struct iak3d_ctx iak3d_ctx;   /* one per GPU: stream, workspaces, error text */

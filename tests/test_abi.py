@@ -36,8 +36,8 @@ def test_exports_every_declared_symbol():
 
 
 def test_pars_struct_layout():
-    # struct iak3d_pars: 6 int32 + 10 doubles + 6 doubles, natural alignment
-    assert C.sizeof(_lib.Pars) == 24 + 8 * 16
+    # struct iak3d_pars: 6 int32 + 10 doubles + 6 doubles + 1 double, natural alignment
+    assert C.sizeof(_lib.Pars) == 24 + 8 * 17
     assert _lib.Pars.ax.offset == 24 and _lib.Pars.sdfdPars.offset == 24 + 80
 
 

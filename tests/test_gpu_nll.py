@@ -1,0 +1,144 @@
+"""GPU parity: factorisation and likelihood through the C ABI against the oracle.
+Tolerance (north_star): <= 1e-8 relative on log-likelihood (and on the terms it is made of)."""
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+import iak3d_b200 as iak
+from iak3d_b200 import synth
+from oracle import iak3d_oracle as orc
+from helpers import MODEL_CASES, PARBNDS, case_pars, relerr, scaled_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-8
+
+
+def _spd(n, seed, cond=1e4):
+    rng = np.random.default_rng(seed)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    return (Q * np.geomspace(1.0, cond, n)) @ Q.T
+
+
+@pytest.mark.parametrize("n,nrhs", [(1, 1), (5, 2), (64, 3), (65, 9), (128, 1), (129, 64), (200, 70), (777, 9), (1500, 4)])
+def test_lndetANDinvCb_vs_lapack(ctx, n, nrhs):
+    A = _spd(n, n); A = 0.5 * (A + A.T)
+    b = np.random.default_rng(n + 1).standard_normal((n, nrhs))
+    got = iak.lndetANDinvCb(A, b, ctx=ctx)
+    want_lnd, want_x = orc.lndetANDinvCb(A, b)
+    assert abs(got["lndetC"] - want_lnd) <= TOL * max(1.0, abs(want_lnd))
+    assert scaled_err(got["invCb"], want_x) <= TOL
+
+
+def test_lndetANDinvCb_not_spd_returns_na(ctx):
+    A = _spd(90, 4); A[40, 40] = -1.0
+    got = iak.lndetANDinvCb(A, np.ones((90, 1)), ctx=ctx)
+    assert np.isnan(got["lndetC"]) and got["invCb"] is None
+    A = _spd(90, 4); A[3, 7] = A[7, 3] = np.nan
+    assert np.isnan(iak.lndetANDinvCb(A, np.ones((90, 1)), ctx=ctx)["lndetC"])
+
+
+@pytest.mark.parametrize("label,kind,nonstat,nud", MODEL_CASES)
+def test_nll_terms_vs_oracle(ctx, label, kind, nonstat, nud):
+    ds = synth.make_dataset(900, 41)
+    P, modelx, types, cmeOpt = case_pars(kind, nonstat, nud)
+    sm = iak.setupIAK3D(ds["xData"], ds["dIData"], ctx=ctx)
+    got = iak.nllIAK3D(None, ds["zData"], ds["XData"], modelx=modelx, nud=nud, sdfdType_cd1=types[0], sdfdType_cxd0=types[1],
+                       sdfdType_cxd1=types[2], cmeOpt=cmeOpt, setupMats=sm, parBnds=PARBNDS, forCompLik=True, parsBTfmd=P)
+    want = orc.nllIAK3D(None, ds["zData"], ds["XData"], modelx, nud, *types, cmeOpt, True,
+                        orc.setupIAK3D(ds["xData"], ds["dIData"]), PARBNDS, forCompLik=True, parsBTfmd=P)
+    assert abs(got["lndetA"] - want["lndetA"]) <= TOL * abs(want["lndetA"])
+    assert scaled_err(got["WiAW"], want["WiAW"]) <= TOL
+    assert scaled_err(got["iAW"], want["iAW"]) <= TOL
+    assert relerr(got["sigma2Vec"], want["sigma2Vec"]) <= 1e-13
+
+
+@pytest.mark.parametrize("useReml", [True, False])
+@pytest.mark.parametrize("n", [1200, 2049])
+def test_nll_value_vs_oracle(ctx, useReml, n):
+    ds = synth.make_dataset(n, synth.SEEDS["E"])
+    P, modelx, types, cmeOpt = case_pars("edgeroi", False, 0.5)      # the Edgeroi settings, egEdgeroi.R:83-97
+    sm = iak.setupIAK3D(ds["xData"], ds["dIData"], ctx=ctx)
+    kw = dict(modelx=modelx, nud=0.5, sdfdType_cd1=types[0], sdfdType_cxd0=types[1], sdfdType_cxd1=types[2], cmeOpt=cmeOpt,
+              setupMats=sm, parBnds=PARBNDS, useReml=useReml, parsBTfmd=P)
+    got = iak.nllIAK3D(None, ds["zData"], ds["XData"], **kw)
+    want = orc.nllIAK3D(None, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True,
+                        orc.setupIAK3D(ds["xData"], ds["dIData"]), PARBNDS, useReml=useReml, parsBTfmd=P)
+    assert abs(got - want) <= TOL * abs(want)
+    # evaluating twice gives the same bits (deterministic reductions: the optimiser differentiates by 1e-6 steps)
+    assert iak.nllIAK3D(None, ds["zData"], ds["XData"], **kw) == got
+
+
+def test_nll_from_unconstrained_pars_and_gradient(ctx):
+    ds = synth.make_dataset(800, 77)
+    modelx, types, cmeOpt, nud = "spherical", (-9, 0, 0), 1, 0.5
+    pars = np.array([0.3, -0.2, -1.5, -0.7, 0.4, -2.0])      # ax.lt, ad.lt, cx0.l, cx1.l, cxd1.lt, cme.l
+    sm = iak.setupIAK3D(ds["xData"], ds["dIData"], ctx=ctx)
+    kw = dict(modelx=modelx, nud=nud, sdfdType_cd1=types[0], sdfdType_cxd0=types[1], sdfdType_cxd1=types[2], cmeOpt=cmeOpt,
+              prodSum=True, setupMats=sm, parBnds=PARBNDS, useReml=True)
+    osm = orc.setupIAK3D(ds["xData"], ds["dIData"])
+    f = lambda v: orc.nllIAK3D(v, ds["zData"], ds["XData"], modelx, nud, *types, cmeOpt, True, osm, PARBNDS, useReml=True)
+    got = iak.nllIAK3D(pars, ds["zData"], ds["XData"], **kw)
+    want = f(pars)
+    assert abs(got - want) <= TOL * abs(want)
+    g, f0 = iak.gradnllIAK3D(pars, ds["zData"], ds["XData"], rtn_nll=True, **kw)
+    assert f0 == got                                       # batch slot 0 == single evaluation, bit for bit
+    gw = np.array([(f(pars + 1e-6 * np.eye(6)[i]) - want) / 1e-6 for i in range(6)])
+    # forward differences of a ~1e3-sized nll with 1e-6 steps carry ~1e-3 absolute noise at 1e-9 relative agreement
+    assert np.max(np.abs(g - gw)) <= 2e-2 * max(1.0, np.max(np.abs(gw)))
+
+
+def test_failures_map_to_badnll(ctx):
+    ds = synth.make_dataset(300, 5)
+    P, modelx, types, cmeOpt = case_pars("matern0.5", False, 0.5)
+    sm = iak.setupIAK3D(ds["xData"], ds["dIData"], ctx=ctx)
+    kw = dict(modelx=modelx, nud=0.5, sdfdType_cd1=0, sdfdType_cxd0=0, sdfdType_cxd1=0, cmeOpt=cmeOpt, setupMats=sm, parBnds=PARBNDS)
+    bad = dict(P); bad["cxd0"] = -5.0; bad["cxd1"] = -5.0; bad["cme"] = 0.0; bad["cx0"] = 0.0     # not positive definite
+    assert iak.nllIAK3D(None, ds["zData"], ds["XData"], parsBTfmd=bad, **kw) == iak.BADNLL
+    bad = dict(P); bad["ax"] = -1.0                                                                # spatialCov returns NA
+    assert iak.nllIAK3D(None, ds["zData"], ds["XData"], parsBTfmd=bad, **kw) == iak.BADNLL
+    out = iak.nllIAK3D(None, ds["zData"], ds["XData"], parsBTfmd=bad, forCompLik=True, **kw)
+    assert np.isnan(out["lndetA"]) and np.all(np.isnan(out["WiAW"]))
+    # and a good evaluation afterwards is unaffected
+    good = iak.nllIAK3D(None, ds["zData"], ds["XData"], parsBTfmd=P, **kw)
+    want = orc.nllIAK3D(None, ds["zData"], ds["XData"], modelx, 0.5, 0, 0, 0, cmeOpt, True, orc.setupIAK3D(ds["xData"], ds["dIData"]),
+                        PARBNDS, parsBTfmd=P)
+    assert abs(good - want) <= TOL * abs(want)
+
+
+def test_batch_mixed_sizes_and_bad_members(ctx):
+    """nll_terms_batch: independent (dataset, parameter) pairs in one launch (CL blocks / FD gradient)."""
+    P, modelx, types, cmeOpt = case_pars("matern1.5", False, 1.5)
+    sets, wants = [], []
+    for n, seed in ((130, 1), (64, 2), (1000, 3), (391, 4)):
+        ds = synth.make_dataset(n, seed)
+        W = np.column_stack([ds["XData"], ds["zData"]])
+        sets.append(iak.SetupMats(ds["xData"], ds["dIData"], W=W, ctx=ctx))
+        wants.append(orc.nllIAK3D(None, ds["zData"], ds["XData"], modelx, 1.5, *types, cmeOpt, True,
+                                  orc.setupIAK3D(ds["xData"], ds["dIData"]), PARBNDS, forCompLik=True, parsBTfmd=P))
+    good = iak._lib.make_pars(P, modelx, *types, cmeOpt)
+    badP = dict(P); badP["nux"] = 99.0
+    bad = iak._lib.make_pars(badP, modelx, *types, cmeOpt)
+    lnd, G, st = iak.nll_terms_batch(ctx, sets + [sets[0]], [good] * 4 + [bad])
+    assert list(st) == [0, 0, 0, 0, 2]
+    for i in range(4):
+        assert abs(lnd[i] - wants[i]["lndetA"]) <= TOL * abs(wants[i]["lndetA"])
+        assert scaled_err(G[i], wants[i]["WiAW"]) <= TOL
+    assert np.isnan(lnd[4])
+
+
+def test_full_size_5k_against_lapack(ctx):
+    """BASELINE.json configs[1] size: the factorisation of the 5k-interval matrix against LAPACK on the host."""
+    ds = synth.make_dataset(5000, synth.SEEDS["S5"])
+    P, modelx, types, cmeOpt = case_pars("matern0.5", False, 0.5)
+    sm = iak.setupIAK3D(ds["xData"], ds["dIData"], ctx=ctx)
+    got = iak.nllIAK3D(None, ds["zData"], ds["XData"], modelx=modelx, nud=0.5, sdfdType_cd1=0, sdfdType_cxd0=0, sdfdType_cxd1=0,
+                       cmeOpt=cmeOpt, setupMats=sm, parBnds=PARBNDS, forCompLik=True, parsBTfmd=P, attachBigMats=True)
+    A = got["A"]
+    W = np.column_stack([ds["XData"], ds["zData"]])
+    c = sla.cho_factor(A, lower=True)
+    lnd = 2.0 * np.sum(np.log(np.diag(c[0])))
+    want = W.T @ sla.cho_solve(c, W)
+    assert abs(got["lndetA"] - lnd) <= TOL * abs(lnd)
+    assert scaled_err(got["WiAW"], want) <= TOL
+    # size-independent property: A (A^-1 W) == W
+    assert scaled_err(A @ got["iAW"], W) <= 1e-8

@@ -1,0 +1,118 @@
+"""GPU parity: kept fit + block kriging and composite likelihood through the C ABI against the oracle.
+Tolerance (north_star): <= 1e-8 relative on predictions, kriging variances and log-likelihood."""
+import numpy as np
+import pytest
+
+import iak3d_b200 as iak
+from iak3d_b200 import synth
+from oracle import iak3d_oracle as orc
+from helpers import PARBNDS, case_pars, relerr, scaled_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-8
+
+
+def _fit_both(ctx, ds, kind, nonstat, nud, cme=None):
+    P, modelx, types, cmeOpt = case_pars(kind, nonstat, nud)
+    if cme is not None:
+        P = dict(P); P["cme"] = cme; cmeOpt = 1 if cme > 0 else 0
+    sm = iak.setupIAK3D(ds["xData"], ds["dIData"], ctx=ctx)
+    got = iak.nllIAK3D(None, ds["zData"], ds["XData"], modelx=modelx, nud=nud, sdfdType_cd1=types[0], sdfdType_cxd0=types[1],
+                       sdfdType_cxd1=types[2], cmeOpt=cmeOpt, setupMats=sm, parBnds=PARBNDS, rtnAll=True, attachBigMats=True,
+                       parsBTfmd=P)
+    want = orc.nllIAK3D(None, ds["zData"], ds["XData"], modelx, nud, *types, cmeOpt, True,
+                        orc.setupIAK3D(ds["xData"], ds["dIData"]), PARBNDS, rtnAll=True, parsBTfmd=P)
+    want["xData"], want["dIData"] = ds["xData"], ds["dIData"]
+    return got, want, modelx, types, cmeOpt
+
+
+@pytest.mark.parametrize("kind,nonstat,nud", [("edgeroi", False, 0.5), ("matern0.5", False, 0.5), ("matern0.8", True, 1.5),
+                                              ("nugget", False, 0.5), ("wendland", False, 2.5)])
+def test_rtnAll_lists_match(ctx, kind, nonstat, nud):
+    ds = synth.make_dataset(600, 8)
+    got, want, *_ = _fit_both(ctx, ds, kind, nonstat, nud)
+    assert abs(got["nll"] - want["nll"]) <= TOL * abs(want["nll"])
+    assert abs(got["cxdhat"] - want["cxdhat"]) <= TOL * abs(want["cxdhat"])
+    assert scaled_err(got["betahat"], want["betahat"]) <= TOL
+    assert scaled_err(got["vbetahat"], want["vbetahat"]) <= TOL
+    assert scaled_err(got["iCX"], want["iCX"]) <= 1e-7          # explicit-inverse products of an ill-conditioned C
+    assert scaled_err(got["iCz_muhat"], want["iCz_muhat"]) <= 1e-7
+    assert relerr(got["sigma2Vec"], want["sigma2Vec"]) <= TOL
+    for k in ("cx0", "cx1", "cd1", "cxd0", "cxd1", "cme"):
+        assert abs(got["parsBTfmd"][k] - want["parsBTfmd"][k]) <= TOL * abs(want["parsBTfmd"][k]) + 1e-300
+    Cg, _ = got["fit"].get_big(want_C=True, want_iC=False)
+    assert scaled_err(Cg, want["C"]) <= 1e-9
+
+
+@pytest.mark.parametrize("kind,nonstat,nud", [("edgeroi", False, 0.5), ("matern0.5", True, 0.5), ("matern0.8", False, 2.5),
+                                              ("nugget", False, 1.5)])
+def test_predict_vs_oracle(ctx, kind, nonstat, nud):
+    ds = synth.make_dataset(700, 15)
+    got, want, modelx, types, cmeOpt = _fit_both(ctx, ds, kind, nonstat, nud)
+    rng = np.random.default_rng(2)
+    # map: random cells + cells exactly at data locations + the "distant" point (fitIAK3D.R:606)
+    xMap = np.vstack([rng.uniform(0, 100, (300, 2)), ds["xData"][::50], [[9e99, 9e99]]])
+    dIMap = synth.GSM_INTERVALS
+    Xfn = lambda i, idx: synth.grid_design(np.clip(xMap[idx], 0, 100), dIMap[i], 3)
+    pg = iak.predictIAK3D(xMap, dIMap, Xfn, got)
+    zw, vw, lw, uw = orc.predictIAK3D(xMap, dIMap, Xfn, want, modelx, types, cmeOpt)
+    assert scaled_err(pg["zMap"], zw) <= TOL
+    assert scaled_err(pg["vMap"], vw) <= TOL
+    assert scaled_err(pg["pi90LMap"], lw) <= TOL and scaled_err(pg["pi90UMap"], uw) <= TOL
+
+
+def test_kriging_is_exact_at_data_supports_without_measurement_error(ctx):
+    ds = synth.make_dataset(500, 21)
+    got, want, modelx, types, cmeOpt = _fit_both(ctx, ds, "matern0.5", False, 0.5, cme=0.0)
+    sel = np.arange(0, 500, 7)
+    z, v = got["fit"].predict(ds["xData"][sel], ds["dIData"][sel], ds["XData"][sel])
+    assert np.max(np.abs(z - ds["zData"][sel])) <= 1e-7 * np.max(np.abs(ds["zData"]))
+    assert np.max(np.abs(v)) <= 1e-6 * got["cxdhat"]
+
+
+def test_predict_chunking_and_nan_rows(ctx):
+    """More supports than one panel (16384) and NaN design rows (predictIAK3D.R:160-163)."""
+    ds = synth.make_dataset(300, 5)
+    got, want, modelx, types, cmeOpt = _fit_both(ctx, ds, "edgeroi", False, 0.5)
+    xMap = synth.make_grid(135)[:18000]
+    dIMap = synth.GSM_INTERVALS[2:3]
+
+    def Xfn(i, idx):
+        X = synth.grid_design(xMap[idx], dIMap[i], 3)
+        X[idx % 1000 == 7, 2] = np.nan
+        return X
+    pg = iak.predictIAK3D(xMap, dIMap, Xfn, got)
+    sub = np.r_[0:50, 16350:16450, 17950:18000]
+    zw, vw, _, _ = orc.predictIAK3D(xMap[sub], dIMap, lambda i, idx: Xfn(i, sub[idx]), want, modelx, types, cmeOpt)
+    okw = ~np.isnan(zw[0])
+    assert np.array_equal(np.isnan(pg["zMap"][0, sub]), ~okw)
+    assert scaled_err(pg["zMap"][0, sub][okw], zw[0][okw]) <= TOL
+    assert scaled_err(pg["vMap"][0, sub][okw], vw[0][okw]) <= TOL
+    assert np.isnan(pg["zMap"][0, 7]) and np.isnan(pg["vMap"][0, 1007])
+
+
+@pytest.mark.parametrize("optn,useReml", [(1, True), (2, False), (3, False), (4, True), (4, False)])
+def test_composite_likelihood_vs_oracle(ctx, optn, useReml):
+    ds = synth.make_dataset(1500, 61)
+    P, modelx, types, cmeOpt = case_pars("edgeroi", False, 0.5)
+    blk = synth.make_blocks(ds["xData"], ds["prof"], 7, 61)
+    blk["compLikOptn"] = optn
+    cl = iak.setupIAK3D_CL(ds["xData"], ds["dIData"], ds["zData"], ds["XData"], blk, ctx=ctx)
+    got = iak.nllIAK3D_CL(None, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True, PARBNDS, useReml, cl, parsBTfmd=P,
+                          rtnTerms=True)
+    want = orc.nllIAK3D_CL(None, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True, PARBNDS, useReml, blk, ds["xData"],
+                           ds["dIData"], parsBTfmd=P, rtnTerms=True)
+    assert abs(got["nll"] - want["nll"]) <= TOL * abs(want["nll"])
+    assert scaled_err(got["XziAXz_SUM"], want["XziAXz_SUM"]) <= TOL
+    assert abs(got["lndetA_SUM"] - want["lndetA_SUM"]) <= TOL * abs(want["lndetA_SUM"])
+
+
+def test_cl_single_block_equals_exact(ctx):
+    ds = synth.make_dataset(640, 9)
+    P, modelx, types, cmeOpt = case_pars("matern0.5", False, 0.5)
+    sm = iak.setupIAK3D(ds["xData"], ds["dIData"], ctx=ctx)
+    exact = iak.nllIAK3D(None, ds["zData"], ds["XData"], modelx=modelx, nud=0.5, cmeOpt=cmeOpt, setupMats=sm, parBnds=PARBNDS, parsBTfmd=P)
+    blk = dict(compLikOptn=4, listBlocks=[np.arange(640)], subsetPairsAdj=np.zeros((0, 2), int), subsetPairsNonadj=np.zeros((0, 2), int))
+    cl = iak.setupIAK3D_CL(ds["xData"], ds["dIData"], ds["zData"], ds["XData"], blk, ctx=ctx)
+    got = iak.nllIAK3D_CL(None, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True, PARBNDS, True, cl, parsBTfmd=P)
+    assert got == exact
