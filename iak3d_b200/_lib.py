@@ -69,6 +69,7 @@ _PROTOS = {
     "iak3d_flush_l2": (C.c_int, [_vp]),
     "iak3d_fp64_peak": (C.c_int, [_vp, _i32, _dp]),
     "iak3d_last_stage_ms": (C.c_int, [_vp, _dp, _dp, _dp]),
+    "iak3d_last_task_profile": (C.c_int, [_vp, C.POINTER(_i64), _i64, C.POINTER(_i64)]),
 }
 EXPORTS = tuple(sorted(_PROTOS))
 

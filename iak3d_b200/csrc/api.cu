@@ -3,6 +3,7 @@
 //     tables -> covariance build into the factor layout -> ticketed tile Cholesky -> finish.
 // Host logic only; all arithmetic on matrices happens in the kernels of tables.cu / covbuild.cu / chol.cu.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -161,6 +162,7 @@ extern "C" int iak3d_ctx_destroy(iak3d_ctx* ctx) {
     delete b;
   }
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+  cudaFree(ctx->d_prof);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   for (int i = 0; i < 5; i++) cudaEventDestroy(ctx->evs[i]);
   cudaStreamDestroy(ctx->stream);
@@ -203,7 +205,7 @@ int iak_alloc_slot(iak3d_ctx* ctx, int64_t n, int32_t q, int64_t nxU, int64_t nd
   A((void**)&s->d_L, (size_t)s->ld * s->Npad * sizeof(double));
   A((void**)&s->d_phix, (size_t)nxU * nxU * sizeof(double));
   A((void**)&s->d_phid, (size_t)(3 * ndIU * ndIU + 3 * ndIU) * sizeof(double));
-  A((void**)&s->d_invd, (size_t)s->nCB * TN * TN * sizeof(double));
+  A((void**)&s->d_invd, (size_t)s->nCB * INVD_BLOCK * sizeof(double));
   const size_t nflags = (size_t)s->nRB * s->nCB + s->nCB;
   A((void**)&s->d_flags, nflags * sizeof(int32_t));
   A((void**)&s->d_logsum, (size_t)s->nCB * sizeof(double));
@@ -591,7 +593,7 @@ static void fill_problem(ProblemDesc* pd, Slot* s, int32_t* d_status) {
   pd->nCB = s->nCB; pd->nRB = s->nRB; pd->mode = 0; pd->epoch = s->epoch;
   pd->w0 = (int32_t)s->Npad; pd->q = s->q;
   pd->G = s->d_G; pd->ldG = s->q;
-  pd->logsum = s->d_logsum; pd->status = d_status; pd->YW = nullptr;
+  pd->logsum = s->d_logsum; pd->status = d_status; pd->YW = nullptr; pd->prof = nullptr;
 }
 
 extern "C" int iak3d_nll_terms_batch_enqueue(iak3d_ctx* ctx, int32_t count, iak3d_ds* const* dss, const iak3d_pars* pars) {
@@ -633,6 +635,15 @@ extern "C" int iak3d_nll_terms_batch_enqueue(iak3d_ctx* ctx, int32_t count, iak3
   st = batch_tasks(ctx, b, probs, live);
   if (st != 0) return st;
   ctx->last_chol_flops = flops; ctx->last_cov_bytes = bytes;
+  if (getenv("IAK3D_PROF") != nullptr) {        // diagnostics: per-task timestamps (iak3d_last_task_profile)
+    if (b->ntasks > ctx->prof_cap) {
+      cudaFree(ctx->d_prof); ctx->d_prof = nullptr;
+      CUDA_TRY(ctx, cudaMalloc(&ctx->d_prof, (size_t)b->ntasks * 8 * sizeof(long long)));
+      ctx->prof_cap = b->ntasks;
+    }
+    ctx->prof_ntasks = b->ntasks;
+    for (int i = 0; i < count; i++) probs[i].prof = ctx->d_prof;
+  }
 
   CUDA_TRY(ctx, cudaEventRecord(ctx->evs[0], ctx->stream));
   std::vector<CovArgs> cargs((size_t)count);
@@ -855,6 +866,24 @@ extern "C" int iak3d_fp64_peak(iak3d_ctx* ctx, int32_t kind, double* tflops) {
   cudaSetDevice(ctx->device);
   return launch_peak(ctx, kind, tflops);
 }
+extern "C" int iak3d_last_task_profile(iak3d_ctx* ctx, int64_t* out, int64_t cap_tasks, int64_t* ntasks) {
+  if (!ctx || !ntasks) return IAK3D_ERR_ARG;
+  *ntasks = ctx->prof_ntasks;
+  if (!out || ctx->prof_ntasks == 0) return IAK3D_OK;
+  cudaSetDevice(ctx->device);
+  const int64_t nt = std::min<int64_t>(cap_tasks, ctx->prof_ntasks);
+  std::vector<int4> tasks((size_t)nt);
+  std::vector<long long> tm((size_t)nt * 8);
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpy(tasks.data(), ctx->batch->d_tasks, (size_t)nt * sizeof(int4), cudaMemcpyDeviceToHost));
+  CUDA_TRY(ctx, cudaMemcpy(tm.data(), ctx->d_prof, (size_t)nt * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+  for (int64_t t = 0; t < nt; t++) {
+    out[t * 11 + 0] = tasks[(size_t)t].x; out[t * 11 + 1] = tasks[(size_t)t].y; out[t * 11 + 2] = tasks[(size_t)t].z;
+    for (int k = 0; k < 8; k++) out[t * 11 + 3 + k] = tm[(size_t)t * 8 + k];
+  }
+  return IAK3D_OK;
+}
+
 extern "C" int iak3d_last_stage_ms(iak3d_ctx* ctx, double* ms4, double* chol_flops, double* cov_bytes) {
   if (!ctx || !ms4) return IAK3D_ERR_ARG;
   if (!ctx->stage_events_valid) { ctx->err = "last_stage_ms: no batch has been run"; return IAK3D_ERR_ARG; }

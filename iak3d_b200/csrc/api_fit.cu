@@ -320,7 +320,7 @@ extern "C" int iak3d_predict_enqueue(iak3d_fit* f) {
     pd.doneL = nullptr; pd.doneP = f->d_pflags; pd.invdone = nullptr;
     pd.nCB = s->nCB; pd.nRB = (int32_t)(rowsP / TM); pd.mode = 1; pd.epoch = ++f->pepoch;
     pd.w0 = 0; pd.q = f->q; pd.G = f->d_G; pd.ldG = rowsP; pd.logsum = nullptr; pd.status = f->d_status;
-    pd.YW = s->d_L + s->Npad;
+    pd.YW = s->d_L + s->Npad; pd.prof = nullptr;
     CUDA_TRY(ctx, cudaMemcpyAsync(f->d_prob, &pd, sizeof(pd), cudaMemcpyHostToDevice, ctx->stream));
     rc = launch_tile_tasks(ctx, f->d_prob, f->d_tasks, f->ntasks, f->d_ticket);
     if (rc != 0) return rc;

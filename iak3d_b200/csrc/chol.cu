@@ -26,7 +26,7 @@ namespace {
 constexpr int KC = 32;                 // k-depth of one pipeline stage
 constexpr int STAGES = 3;
 constexpr int LDA_S = TM + 4;          // 132: conflict-free DMMA A-fragment loads (stride = 4 mod 16)
-constexpr int LDB_S = TN + 4;          // 68
+constexpr int LDB_S = INVD_LD;         // 68
 constexpr int A_STAGE = KC * LDA_S;
 constexpr int B_STAGE = KC * LDB_S;
 constexpr int STAGE_D = A_STAGE + B_STAGE;          // doubles per stage (51,200 B)
@@ -115,31 +115,122 @@ __device__ __forceinline__ void warp_mma_k4(double (&acc)[4][4][2], const double
 }
 
 // Cholesky of the 64x64 block D (rows off.. of the tile in At) fused with its inverse (into Ys).
-// Right-looking, one CTA barrier per column.  D(r,c) = At[c*LDA_S + off + r]; Y(r,c) = Ys[c*LDB_S + r].
-__device__ void potf2_inv(double* __restrict__ At, int off, double* __restrict__ Ys, int tid, double* logsum_out,
-                          int32_t* status) {
-  const int rr = tid & 63, g = tid >> 6;
-  for (int idx = tid; idx < TN * TN; idx += NCW * 32) Ys[(idx >> 6) * LDB_S + (idx & 63)] = ((idx >> 6) == (idx & 63)) ? 1.0 : 0.0;
-  consumer_bar();
-  double lsum = 0.0;
-  bool bad = false;
-  double* Dr = At + off + rr;
-  for (int c = 0; c < TN; c++) {
-    const double d = At[c * LDA_S + off + c];
-    if (!(d > 0.0) || isinf(d)) bad = true;
-    const double rs = rsqrt(d);
-    if (tid == 0) lsum += log(d);
-    const double lrc = Dr[c * LDA_S] * rs;
-    if (rr > c) {
-      for (int c2 = c + 1 + g; c2 <= rr; c2 += 4) Dr[c2 * LDA_S] -= lrc * (At[c * LDA_S + off + c2] * rs);
-      for (int k = g; k <= c; k += 4) Ys[k * LDB_S + rr] -= lrc * (Ys[k * LDB_S + c] * rs);
-    }
-    consumer_bar();
-    if (g == 0) Dr[c * LDA_S] = (rr > c) ? lrc : ((rr == c) ? d * rs : 0.0);
-    if (g == 1 && rr <= c) Ys[rr * LDB_S + c] *= rs;
+// D(r,c) = At[c*LDA_S + off + r]; Y(r,c) = Ys[c*LDB_S + r].
+//
+// Right-looking, register-blocked: consumer thread t owns the 4x4 blocks D(4br.., 4bc..) and Y(4br.., 4bc..)
+// with br = t/16, bc = t%16 (only bc <= br is live: both matrices are lower triangular).  Column c of the
+// trailing matrix and row c of the running inverse are published through double-buffered shared vectors, so
+// a step costs ONE barrier: publish -> barrier -> {pivot, rsqrt, rank-1 update of D, forward substitution of Y}.
+// The step is a template on c % 4 so that every register-array index is a compile-time constant.
+// 1/sqrt(x) for a positive finite pivot: MUFU seed + two Newton steps (relative error ~1e-16); rsqrt() from the
+// math library carries special-case handling that sits on the column-to-column dependency chain.
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  double e = fma(-hx * y, y, 0.5);      // 0.5 - 0.5 x y^2
+  y = fma(y, e, y);
+  e = fma(-hx * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-hx * y, y, 0.5);
+  y = fma(y, e, y);
+  return y;
+}
+
+template <int CI>
+__device__ __forceinline__ void potf2_step(int cb, int br, int bc, bool live, double (&d)[4][4], double (&y)[4][4],
+                                           double* __restrict__ colbuf, double* __restrict__ yrow, double* __restrict__ pivs,
+                                           bool& bad) {
+  const int c = 4 * cb + CI, buf = (CI & 1) * 64;
+  if (bc == cb && br >= cb) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) colbuf[buf + 4 * br + i] = d[i][CI];
+  }
+  if (br == cb && bc <= cb) {
+#pragma unroll
+    for (int jj = 0; jj < 4; jj++) yrow[buf + 4 * bc + jj] = y[CI][jj];
   }
   consumer_bar();
-  if (tid == 0) { *logsum_out = lsum; if (bad) atomicExch(status, 1); }
+  if (live && br >= cb) {
+    const double piv = colbuf[buf + c];
+    if (!(piv > 0.0) || isinf(piv)) bad = true;
+    const double rs = fast_rsqrt(piv);
+    if (br == cb && bc == cb) pivs[c] = piv;
+    double li[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) li[i] = (4 * br + i > c) ? colbuf[buf + 4 * br + i] * rs : 0.0;
+    if (bc >= cb) {          // columns beyond c exist in this block: rank-1 update of the trailing matrix
+      double lj[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; jj++) lj[jj] = (4 * bc + jj > c) ? colbuf[buf + 4 * bc + jj] * rs : 0.0;
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) d[i][jj] -= li[i] * lj[jj];
+    }
+    if (bc <= cb) {          // columns up to c exist in this block: forward substitution of the inverse
+      double yk[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; jj++) yk[jj] = (4 * bc + jj <= c) ? yrow[buf + 4 * bc + jj] * rs : 0.0;
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) y[i][jj] -= li[i] * yk[jj];
+      if (br == cb) {        // row c of the inverse is final
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) y[CI][jj] = yk[jj];
+      }
+    }
+    if (bc == cb) {          // column c of L is final
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int r = 4 * br + i;
+        d[i][CI] = (r > c) ? li[i] : ((r == c) ? piv * rs : 0.0);
+      }
+    }
+  }
+}
+
+__device__ void potf2_inv(double* __restrict__ At, int off, double* __restrict__ Ys, double* __restrict__ comm /* 4*64+64 doubles */,
+                          int tid, double* logsum_out, int32_t* status) {
+  double* colbuf = comm;            // [2][64]
+  double* yrow = comm + 128;        // [2][64]
+  double* pivs = comm + 256;        // [64]
+  const int br = tid >> 4, bc = tid & 15;
+  const bool live = (bc <= br);
+  double d[4][4], y[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int jj = 0; jj < 4; jj++) {
+      d[i][jj] = live ? At[(4 * bc + jj) * LDA_S + off + 4 * br + i] : 0.0;
+      y[i][jj] = (br == bc && i == jj) ? 1.0 : 0.0;
+    }
+  bool bad = false;
+#pragma unroll 1
+  for (int cb = 0; cb < TN / 4; cb++) {
+    potf2_step<0>(cb, br, bc, live, d, y, colbuf, yrow, pivs, bad);
+    potf2_step<1>(cb, br, bc, live, d, y, colbuf, yrow, pivs, bad);
+    potf2_step<2>(cb, br, bc, live, d, y, colbuf, yrow, pivs, bad);
+    potf2_step<3>(cb, br, bc, live, d, y, colbuf, yrow, pivs, bad);
+  }
+  // ---- write L (zeros above the diagonal) and the inverse back to shared memory ----
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int jj = 0; jj < 4; jj++) {
+      const int r = 4 * br + i, cc = 4 * bc + jj;
+      At[cc * LDA_S + off + r] = (live && r >= cc) ? d[i][jj] : 0.0;
+      Ys[cc * LDB_S + r] = (live && r >= cc) ? y[i][jj] : 0.0;
+    }
+  if (bad) atomicExch(status, 1);
+  consumer_bar();
+  if (tid < 32) {   // log-determinant of the block: fixed-order tree, deterministic
+    double v = log(pivs[tid]) + log(pivs[tid + 32]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (tid == 0) *logsum_out = v;
+  }
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -151,12 +242,16 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ __align__(8) uint64_t at_bar;
+  __shared__ __align__(8) uint64_t inv_bar;
+  __shared__ __align__(16) double s_comm[4 * 64 + 64];
   __shared__ int s_task;
+  __shared__ long long s_tdep;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NCW); }
     mbar_init(&at_bar, 1);
+    mbar_init(&inv_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -164,7 +259,7 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
 
   int32_t* const abort_flag = ticket + 1;   // set by the first CTA whose bounded wait expired
   uint32_t it = 0;          // pipeline chunk counter, identical in every thread
-  uint32_t at_phase = 0;
+  uint32_t at_phase = 0, inv_phase = 0;
 
   while (true) {
     if (tid == 0) s_task = (ld_volatile(abort_flag) != 0) ? ntasks : atomicAdd(ticket, 1);
@@ -181,37 +276,44 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
     const int64_t R0 = (int64_t)r * TM, C0 = (int64_t)j * TN;
     const int nchunks = j * (TN / KC);
     const uint32_t it0 = it;
+    long long* prof = pb->prof ? pb->prof + (int64_t)t * 8 : nullptr;
+    long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0, tp4 = 0, kwait = 0;
+    if (prof && tid == 0) tp0 = (long long)gtime();
 
     if (warp == NCW) {
-      // ===================== producer: TMA bulk copies =====================
-      if (lane == 0) {
-        // generic-proxy accesses of the previous task (epilogue reads/writes of At, Ys) were ordered by the
-        // end-of-task __syncthreads; make them visible to the async proxy before it overwrites smem.
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&at_bar, TN * TM * 8);
-        for (int c = 0; c < TN; c++) bulk_g2s(At + c * LDA_S, P + (C0 + c) * ldP + R0, TM * 8, &at_bar);
-        uint32_t itp = it0;
-        for (int c = 0; c < nchunks; c++, itp++) {
-          const int k = c >> 1;
-          if ((c & 1) == 0) {
+      // ===================== producer warp: TMA bulk copies, one column per lane =====================
+      // generic-proxy accesses of the previous task (epilogue reads/writes of At, Ys) were ordered by the
+      // end-of-task __syncthreads; make them visible to the async proxy before it overwrites smem.
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (lane == 0) mbar_expect_tx(&at_bar, TN * TM * 8);
+      __syncwarp();
+      for (int c = lane; c < TN; c += 32) bulk_g2s(At + c * LDA_S, P + (C0 + c) * ldP + R0, TM * 8, &at_bar);
+      uint32_t itp = it0;
+      for (int c = 0; c < nchunks; c++, itp++) {
+        const int k = c >> 1;
+        if ((c & 1) == 0) {
+          // lane 0 polls (32 pollers per CTA would hammer one L2 sector); then every lane performs its own acquire
+          // load of the now-set flags, because each lane issues copies of the data they guard
+          if (lane == 0) {
             wait_flag(pb->doneP + (int64_t)r * nCB + k, epoch, status, abort_flag);
             if (mode == 0) wait_flag(pb->doneL + (int64_t)(j >> 1) * nCB + k, epoch, status, abort_flag);
-            asm volatile("fence.proxy.async.global;" ::: "memory");
           }
-          const uint32_t s = itp % STAGES, use = itp / STAGES;
-          if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1, status, abort_flag);
-          mbar_expect_tx(&full_bar[s], KC * (TM + TN) * 8);
-          double* As = smem + s * STAGE_D;
-          double* Bs = As + A_STAGE;
-          const int64_t col0 = (int64_t)k * TN + (c & 1) * KC;
-          const double* srcA = P + col0 * ldP + R0;
-          const double* srcB = L + col0 * ldL + C0;
-#pragma unroll 4
-          for (int kk = 0; kk < KC; kk++) {
-            bulk_g2s(As + kk * LDA_S, srcA + kk * ldP, TM * 8, &full_bar[s]);
-            bulk_g2s(Bs + kk * LDB_S, srcB + kk * ldL, TN * 8, &full_bar[s]);
-          }
+          __syncwarp();
+          (void)ld_acquire(pb->doneP + (int64_t)r * nCB + k);
+          if (mode == 0) (void)ld_acquire(pb->doneL + (int64_t)(j >> 1) * nCB + k);
+          asm volatile("fence.proxy.async;" ::: "memory");
+          if (prof && lane == 0 && k == j - 1) s_tdep = (long long)gtime();
         }
+        const uint32_t s = itp % STAGES, use = itp / STAGES;
+        if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1, status, abort_flag);
+        if (lane == 0) mbar_expect_tx(&full_bar[s], KC * (TM + TN) * 8);
+        __syncwarp();
+        double* As = smem + s * STAGE_D;
+        double* Bs = As + A_STAGE;
+        const int64_t col0 = (int64_t)k * TN + (c & 1) * KC;
+        static_assert(KC == 32, "one k-column per producer lane");
+        bulk_g2s(As + lane * LDA_S, P + (col0 + lane) * ldP + R0, TM * 8, &full_bar[s]);
+        bulk_g2s(Bs + lane * LDB_S, L + (col0 + lane) * ldL + C0, TN * 8, &full_bar[s]);
       }
       __syncwarp();
     } else {
@@ -225,7 +327,13 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
       uint32_t itc = it0;
       for (int c = 0; c < nchunks; c++, itc++) {
         const uint32_t s = itc % STAGES;
-        mbar_wait(&full_bar[s], (itc / STAGES) & 1, status, abort_flag);
+        if (prof && tid == 0) {
+          const long long c0 = clock64();
+          mbar_wait(&full_bar[s], (itc / STAGES) & 1, status, abort_flag);
+          kwait += clock64() - c0;
+        } else {
+          mbar_wait(&full_bar[s], (itc / STAGES) & 1, status, abort_flag);
+        }
         const double* As = smem + s * STAGE_D;
         const double* Bs = As + A_STAGE;
 #pragma unroll
@@ -234,6 +342,7 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
         if (lane == 0) mbar_arrive(&empty_bar[s]);
       }
       // ---- E1: tile = A - acc (in shared memory) ----
+      if (prof && tid == 0) tp1 = (long long)gtime();
       mbar_wait(&at_bar, at_phase, status, abort_flag);
       {
         const int kq = lane & 3, rq = lane >> 2;
@@ -247,14 +356,16 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
           }
       }
       consumer_bar();
+      if (prof && tid == 0) tp2 = (long long)gtime();
       // ---- E2: diagonal block or fetch of the inverted diagonal block ----
       int row_lo = 0;
       const bool is_diag = (mode == 0) && (r == (j >> 1));
       if (is_diag) {
         const int off = (j & 1) * TN;
-        potf2_inv(At, off, Ys, tid, pb->logsum + j, status);
-        double* invd = pb->invd + (int64_t)j * TN * TN;
-        for (int idx = tid; idx < TN * TN; idx += NCW * 32) invd[idx] = Ys[(idx >> 6) * LDB_S + (idx & 63)];
+        potf2_inv(At, off, Ys, s_comm, tid, pb->logsum + j, status);
+        double* invd = pb->invd + (int64_t)j * INVD_BLOCK;       // stored with the padded stride: one bulk copy reloads it
+        for (int idx = tid; idx < INVD_BLOCK / 2; idx += NCW * 32)
+          reinterpret_cast<double2*>(invd)[idx] = reinterpret_cast<const double2*>(Ys)[idx];
         for (int idx = tid; idx < TN * (TN / 2); idx += NCW * 32) {
           const int c = idx >> 5, rp = (idx & 31) * 2;
           const double2 v = *reinterpret_cast<const double2*>(At + c * LDA_S + off + rp);
@@ -267,14 +378,16 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
         row_lo = off + TN;
       } else {
         // a finished factor (mode 1) needs no wait: its inverse diagonal blocks were published long ago
-        if (mode == 0) {
-          if (tid == 0) wait_flag(pb->invdone + j, epoch, status, abort_flag);
-          consumer_bar();
+        if (tid == 0) {
+          if (mode == 0) wait_flag(pb->invdone + j, epoch, status, abort_flag);
+          asm volatile("fence.proxy.async;" ::: "memory");
+          mbar_expect_tx(&inv_bar, INVD_BLOCK * 8);
+          bulk_g2s(Ys, pb->invd + (int64_t)j * INVD_BLOCK, INVD_BLOCK * 8, &inv_bar);
         }
-        const double* invd = pb->invd + (int64_t)j * TN * TN;
-        for (int idx = tid; idx < TN * TN; idx += NCW * 32) Ys[(idx >> 6) * LDB_S + (idx & 63)] = __ldcg(invd + idx);
-        consumer_bar();
+        mbar_wait(&inv_bar, inv_phase, status, abort_flag);
+        inv_phase ^= 1;
       }
+      if (prof && tid == 0) tp3 = (long long)gtime();
       if (row_lo < TM) {
         // ---- E3: X = tile * inv(L_jj)' on the tensor pipe ----
         double x[4][4][2];
@@ -345,10 +458,16 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
         }
       }
       // ---- E6: publish ----
+      if (prof && tid == 0) tp4 = (long long)gtime();
       __threadfence();
       asm volatile("fence.proxy.async;" ::: "memory");     // the tile is re-read by other CTAs' TMA bulk copies
       consumer_bar();
       if (tid == 0) st_release(pb->doneP + (int64_t)r * nCB + j, epoch);
+      if (prof && tid == 0) {
+        prof[0] = tp0; prof[1] = tp1; prof[2] = tp2; prof[3] = tp3; prof[4] = tp4; prof[5] = (long long)gtime();
+        prof[6] = (nchunks > 0) ? s_tdep : tp0;
+        prof[7] = (kwait << 1) | (is_diag ? 1 : 0);     // cycles warp 0 spent waiting for operands in the K-loop
+      }
     }
     it = it0 + nchunks;
     at_phase ^= 1;
@@ -382,11 +501,11 @@ __global__ void backsolve_diag_kernel(const double* __restrict__ invd, int J, co
   const int tid = threadIdx.x;
   for (int idx = tid; idx < TN * q; idx += blockDim.x) { const int c = idx / q, w = idx % q; ys[c * 64 + w] = Yw[(int64_t)(J * TN + c) * ldY + w]; }
   __syncthreads();
-  const double* Li = invd + (int64_t)J * TN * TN;     // column-major 64x64, lower
+  const double* Li = invd + (int64_t)J * INVD_BLOCK;  // column-major 64x64 (stride LDB_S), lower
   for (int idx = tid; idx < TN * q; idx += blockDim.x) {
     const int i = idx % TN, w = idx / TN;
     double s = 0.0;
-    for (int k = i; k < TN; k++) s += Li[(int64_t)i * TN + k] * ys[k * 64 + w];   // (invL')(i,k) = invL(k,i)
+    for (int k = i; k < TN; k++) s += Li[(int64_t)i * LDB_S + k] * ys[k * 64 + w];   // (invL')(i,k) = invL(k,i)
     X[(int64_t)w * ldX + J * TN + i] = s;
   }
 }

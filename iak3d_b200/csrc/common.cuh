@@ -12,6 +12,8 @@
 // ---- tiling constants shared by the covariance-build and factorisation kernels ---------------
 constexpr int TM = 128;      // tile rows  (row-block height)
 constexpr int TN = 64;       // tile cols  (column-block width == panel width of the factorisation)
+constexpr int INVD_LD = TN + 4;              // inverse diagonal blocks are kept with the padded shared-memory stride
+constexpr int INVD_BLOCK = TN * INVD_LD;     // doubles per stored inverse block
 
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
@@ -31,6 +33,7 @@ struct iak3d_ctx {
   struct Batch* batch = nullptr;
   double last_chol_flops = 0, last_cov_bytes = 0;
   bool stage_events_valid = false;
+  long long* d_prof = nullptr; int64_t prof_cap = 0; int32_t prof_ntasks = 0;   // IAK3D_PROF=1 diagnostics
 };
 
 // Workspace of ONE likelihood evaluation of a dataset: the factor buffer, the unique-pair tables and the
@@ -42,7 +45,7 @@ struct Slot {
   double* d_L = nullptr;          // ld x Npad factor buffer (A in, L out; W' rows at Npad..Npad+q-1)
   double* d_phix = nullptr;       // nxU x nxU horizontal correlation table
   double* d_phid = nullptr;       // 3 tables ndIU x ndIU + 3 avVar vectors
-  double* d_invd = nullptr;       // nCB x (TN*TN) inverted diagonal blocks
+  double* d_invd = nullptr;       // nCB x INVD_BLOCK inverted diagonal blocks
   int32_t* d_flags = nullptr;     // done[nRB*nCB] + invdone[nCB]
   double* d_logsum = nullptr;     // nCB
   double* d_G = nullptr;          // 64*64 Gram accumulator (WiAW)
@@ -137,6 +140,7 @@ struct ProblemDesc {
   double* logsum;                // nCB
   int32_t* status;               // [0] not-SPD, [1] timeout
   const double* YW;              // mode 1: W rows of the factor buffer (L + w0), ld = ldL
+  long long* prof;               // optional per-task timestamps (8 per task, globaltimer ns), nullptr = off
 };
 int chol_configure(iak3d_ctx* ctx);
 int launch_tile_tasks(iak3d_ctx* ctx, const ProblemDesc* d_problems, const int4* d_tasks, int32_t ntasks, int32_t* d_ticket /* 2 ints */);

@@ -159,6 +159,11 @@ IAK3D_API int iak3d_fp64_peak(iak3d_ctx* ctx, int32_t kind, double* tflops);
  * build, [2] factorisation, [3] finish; and the algorithmic flop / byte counts of that launch. */
 IAK3D_API int iak3d_last_stage_ms(iak3d_ctx* ctx, double* ms4, double* chol_flops, double* cov_bytes);
 
+/* diagnostics: when the environment variable IAK3D_PROF is set, every tile task of the last nll_terms_batch records
+ * device timestamps; out holds 11 int64 per task: problem, row block, column block, then 8 values -- start, K-loop
+ * end, tile ready, diagonal/inverse ready, copy-out done, published, last dependency seen (ns), (smid << 32) | is_diag. */
+IAK3D_API int iak3d_last_task_profile(iak3d_ctx* ctx, int64_t* out, int64_t cap_tasks, int64_t* ntasks);
+
 #ifdef __cplusplus
 }
 #endif
