@@ -202,7 +202,7 @@ int iak_alloc_slot(iak3d_ctx* ctx, int64_t n, int32_t q, int64_t nxU, int64_t nd
   s->nCB = (int32_t)(s->Npad / TN); s->nRB = (int32_t)(s->ld / TM);
   cudaError_t e = cudaSuccess;
   auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, std::max<size_t>(bytes, 16)); };
-  A((void**)&s->d_L, (size_t)s->ld * s->Npad * sizeof(double));
+  A((void**)&s->d_L, (size_t)ubuf_doubles(s->ld, s->Npad) * sizeof(double));
   A((void**)&s->d_phix, (size_t)nxU * nxU * sizeof(double));
   A((void**)&s->d_phid, (size_t)(3 * ndIU * ndIU + 3 * ndIU) * sizeof(double));
   A((void**)&s->d_invd, (size_t)s->nCB * INVD_BLOCK * sizeof(double));
@@ -587,13 +587,13 @@ static int batch_tasks(iak3d_ctx* ctx, Batch* b, const std::vector<ProblemDesc>&
 }
 
 static void fill_problem(ProblemDesc* pd, Slot* s, int32_t* d_status) {
-  pd->L = s->d_L; pd->ldL = s->ld; pd->P = s->d_L; pd->ldP = s->ld;
+  pd->L = s->d_L; pd->nRUL = s->ld / UR; pd->P = s->d_L; pd->nRUP = s->ld / UR;
   pd->invd = s->d_invd;
   pd->doneL = s->d_flags; pd->doneP = s->d_flags; pd->invdone = s->d_flags + (size_t)s->nRB * s->nCB;
   pd->nCB = s->nCB; pd->nRB = s->nRB; pd->mode = 0; pd->epoch = s->epoch;
   pd->w0 = (int32_t)s->Npad; pd->q = s->q;
   pd->G = s->d_G; pd->ldG = s->q;
-  pd->logsum = s->d_logsum; pd->status = d_status; pd->YW = nullptr; pd->prof = nullptr;
+  pd->logsum = s->d_logsum; pd->status = d_status; pd->prof = nullptr;
 }
 
 extern "C" int iak3d_nll_terms_batch_enqueue(iak3d_ctx* ctx, int32_t count, iak3d_ds* const* dss, const iak3d_pars* pars) {
@@ -710,16 +710,13 @@ extern "C" int iak3d_nll_terms_batch(iak3d_ctx* ctx, int32_t count, iak3d_ds* co
 int iak_backsolve_to_host(iak3d_ctx* ctx, Slot* s, double* out_host, double* d_out_opt) {
   const int q = s->q;
   if (q <= 0) return 0;
-  double *dY = nullptr, *dX = nullptr;
+  double* dX = nullptr;
   int rc = 0;
   do {
-    if (cudaMalloc(&dY, (size_t)q * s->Npad * 8) != cudaSuccess || cudaMalloc(&dX, (size_t)s->Npad * q * 8) != cudaSuccess) {
+    if (cudaMalloc(&dX, (size_t)s->Npad * q * 8) != cudaSuccess) {
       ctx->err = "backsolve: allocation failed"; rc = IAK3D_ERR_CUDA; cudaGetLastError(); break;
     }
-    // copy the Y' rows (q x Npad, ld = s->ld) into a compact q x Npad buffer
-    if (cudaMemcpy2DAsync(dY, (size_t)q * 8, s->d_L + s->Npad, (size_t)s->ld * 8, (size_t)q * 8, (size_t)s->Npad,
-                          cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) { ctx->err = "backsolve: copy failed"; rc = IAK3D_ERR_CUDA; break; }
-    rc = launch_backsolve(ctx, s->d_L, s->ld, s->Npad, s->d_invd, dY, q, q, dX);
+    rc = launch_backsolve(ctx, s->d_L, s->ld / UR, s->Npad, s->d_invd, q, dX);
     if (rc != 0) break;
     if (out_host)
       cudaMemcpy2DAsync(out_host, (size_t)s->n * 8, dX, (size_t)s->Npad * 8, (size_t)s->n * 8, (size_t)q, cudaMemcpyDeviceToHost, ctx->stream);
@@ -728,7 +725,7 @@ int iak_backsolve_to_host(iak3d_ctx* ctx, Slot* s, double* out_host, double* d_o
     const cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { ctx->err = std::string("backsolve: ") + cudaGetErrorString(e); rc = IAK3D_ERR_CUDA; }
   } while (0);
-  cudaFree(dY); cudaFree(dX);
+  cudaFree(dX);
   return rc;
 }
 

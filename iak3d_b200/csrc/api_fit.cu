@@ -184,7 +184,7 @@ static int fit_reserve_panel(iak3d_fit* f, int64_t rows, int64_t nd1) {
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(f->d_P); cudaFree(f->d_G); cudaFree(f->d_pflags); cudaFree(f->d_phix); cudaFree(f->d_same); cudaFree(f->d_iota);
     f->d_P = f->d_G = f->d_phix = nullptr; f->d_pflags = nullptr; f->d_same = nullptr; f->d_iota = nullptr; f->ldP = 0;
-    CUDA_TRY(ctx, cudaMalloc(&f->d_P, (size_t)ldP * s->Npad * 8));
+    CUDA_TRY(ctx, cudaMalloc(&f->d_P, (size_t)ubuf_doubles(ldP, s->Npad) * 8));
     CUDA_TRY(ctx, cudaMalloc(&f->d_G, (size_t)ldP * (f->q + 1) * 8));
     const size_t nfl = (size_t)(ldP / TM) * s->nCB;
     CUDA_TRY(ctx, cudaMalloc(&f->d_pflags, nfl * 4));
@@ -311,16 +311,16 @@ extern "C" int iak3d_predict_enqueue(iak3d_fit* f) {
     a.phix = px.has_phix ? f->d_phix : nullptr;
     a.same = f->d_same;
     a.xid_r = f->d_iota; a.did_r = f->d_did1 + r0; a.nr = rows; a.nxU_r = rows;
-    rc = launch_cov_rect(ctx, a, f->d_P, rowsP, rowsP, s->Npad, 0);
+    rc = launch_cov_rect(ctx, a, f->d_P, rowsP, rowsP, s->Npad, 0, /*blocked=*/1);
     if (rc != 0) return rc;
     rc = fit_panel_tasks(f, rowsP);
     if (rc != 0) return rc;
     ProblemDesc pd;
-    pd.L = s->d_L; pd.ldL = s->ld; pd.P = f->d_P; pd.ldP = rowsP; pd.invd = s->d_invd;
+    pd.L = s->d_L; pd.nRUL = s->ld / UR; pd.P = f->d_P; pd.nRUP = rowsP / UR; pd.invd = s->d_invd;
     pd.doneL = nullptr; pd.doneP = f->d_pflags; pd.invdone = nullptr;
     pd.nCB = s->nCB; pd.nRB = (int32_t)(rowsP / TM); pd.mode = 1; pd.epoch = ++f->pepoch;
-    pd.w0 = 0; pd.q = f->q; pd.G = f->d_G; pd.ldG = rowsP; pd.logsum = nullptr; pd.status = f->d_status;
-    pd.YW = s->d_L + s->Npad; pd.prof = nullptr;
+    pd.w0 = (int32_t)s->Npad; pd.q = f->q; pd.G = f->d_G; pd.ldG = rowsP; pd.logsum = nullptr; pd.status = f->d_status;
+    pd.prof = nullptr;
     CUDA_TRY(ctx, cudaMemcpyAsync(f->d_prob, &pd, sizeof(pd), cudaMemcpyHostToDevice, ctx->stream));
     rc = launch_tile_tasks(ctx, f->d_prob, f->d_tasks, f->ntasks, f->d_ticket);
     if (rc != 0) return rc;

@@ -6,32 +6,35 @@
 // t(W) %*% iAW product of nllIAK3D (fitIAK3D.R:810), and -- run on extra "bordered" row panels --
 // the  Ckh %*% iC  products of predictIAK3D (predictIAK3D.R:202-208).
 //
-// Data layout.  The factor buffer is column-major with leading dimension ld (multiple of TM):
+// Data layout.  The factor buffer is BLOCKED (common.cuh: 64 x 32 units with the padded stride 68, ordered column
+// panel by column panel) and has ld rows (multiple of TM):
 //   rows [0,n) x cols [0,n)            lower triangle of A, overwritten by L
 //   rows/cols [n,Npad)                 identity padding (Npad = n rounded up to TN)
 //   rows [Npad,Npad+q) x cols [0,Npad) W' (q = p+1 rows), overwritten by Y' = W' L^-T
 // so that sum_j Y_j' Y_j = W' A^-1 W comes out of the same sweep ("bordered" Cholesky).
 //
 // Tiles are TM x TN = 128 x 64.  Task (r, j) owns tile rows [128r,128r+128) x cols [64j,64j+64):
-//   acc = A_tile - sum_{k<j} L(r,k) L(jrows,k)'          K-loop, DMMA, operands via TMA bulk copies
-//   diagonal tile:  potf2 of the 64x64 block fused with its inverse (shared memory)
+//   acc = A_tile - sum_{k<j} L(r,k) L(jrows,k)'          K-loop, DMMA; a 32-deep stage is TWO bulk copies
+//                                                         (two stacked A units, one B unit)
+//   diagonal tile:  potf2 of the 64x64 block fused with its inverse (registers + shared memory)
 //   all other rows: X = acc * inv(L_jj)'                  DMMA
 // Dependencies are per-tile epoch flags in global memory (release/acquire); tasks are claimed from
-// an atomic ticket in column-major (topological) order, so a waiting CTA only ever waits for a CTA
+// an atomic ticket in a topological order, so a waiting CTA only ever waits for a CTA
 // that already holds an earlier ticket: no deadlock, no co-residency requirement.
 #include "common.cuh"
 
 namespace {
 
-constexpr int KC = 32;                 // k-depth of one pipeline stage
+constexpr int KC = UC;                 // k-depth of one pipeline stage == unit width (32)
 constexpr int STAGES = 3;
-constexpr int LDA_S = TM + 4;          // 132: conflict-free DMMA A-fragment loads (stride = 4 mod 16)
-constexpr int LDB_S = INVD_LD;         // 68
-constexpr int A_STAGE = KC * LDA_S;
-constexpr int B_STAGE = KC * LDB_S;
-constexpr int STAGE_D = A_STAGE + B_STAGE;          // doubles per stage (51,200 B)
-constexpr int AT_D = TN * LDA_S;                    // the task's own tile (67,584 B)
-constexpr int SMEM_BYTES = (STAGES * STAGE_D + AT_D) * 8;   // 221,184 B
+constexpr int LDB_S = UL;              // 68: conflict-free DMMA fragment loads (stride = 4 mod 16)
+constexpr int A_STAGE = 2 * UNIT;      // two vertically stacked units: 128 rows x 32 k
+constexpr int B_STAGE = UNIT;          // one unit: 64 rows x 32 k
+constexpr int STAGE_D = A_STAGE + B_STAGE;          // doubles per stage (52,224 B)
+constexpr int AT_D = 4 * UNIT;                      // the task's own tile: [col half][row half] units (69,632 B)
+constexpr int SMEM_BYTES = (STAGES * STAGE_D + AT_D) * 8;   // 226,304 B
+// tile element (row 0..127, col 0..63) inside At
+#define AT_IDX(row, col) ((((col) >> 5) * 2 + ((row) >> 6)) * UNIT + ((col) & 31) * UL + ((row) & 63))
 constexpr int NCW = 8;                 // consumer (MMA) warps: 4 (rows) x 2 (cols), 32x32 each
 constexpr int NTHREADS = (NCW + 1) * 32;
 constexpr unsigned long long WAIT_TIMEOUT_NS = 4000000000ull;
@@ -99,29 +102,22 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// one k4 step of a warp's 32x32 sub-tile: A k-major (stride lda), B k-major (stride ldb)
-__device__ __forceinline__ void warp_mma_k4(double (&acc)[4][4][2], const double* __restrict__ As, int lda,
-                                            const double* __restrict__ Bs, int ldb, int k0, int wm, int wn, int lane) {
-  const int kq = lane & 3, rq = lane >> 2;
+// one k4 step of a warp's 32x32 sub-tile.  A element (row, k) at Ab[k*UL + row-part] with the row-part folded into
+// aoff (unit of the row half + row within the unit); B element (col, k) at Bb[k*UL + col].
+__device__ __forceinline__ void warp_mma_k4(double (&acc)[4][4][2], const double* __restrict__ Ab, int aoff,
+                                            const double* __restrict__ Bb, int boff, int k0, int lane) {
+  const int kq = lane & 3;
   double a[4], b[4];
 #pragma unroll
-  for (int mi = 0; mi < 4; mi++) a[mi] = As[(k0 + kq) * lda + wm * 32 + mi * 8 + rq];
+  for (int mi = 0; mi < 4; mi++) a[mi] = Ab[(k0 + kq) * UL + aoff + mi * 8];
 #pragma unroll
-  for (int ni = 0; ni < 4; ni++) b[ni] = Bs[(k0 + kq) * ldb + wn * 32 + ni * 8 + rq];
+  for (int ni = 0; ni < 4; ni++) b[ni] = Bb[(k0 + kq) * UL + boff + ni * 8];
 #pragma unroll
   for (int mi = 0; mi < 4; mi++)
 #pragma unroll
     for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
 }
 
-// Cholesky of the 64x64 block D (rows off.. of the tile in At) fused with its inverse (into Ys).
-// D(r,c) = At[c*LDA_S + off + r]; Y(r,c) = Ys[c*LDB_S + r].
-//
-// Right-looking, register-blocked: consumer thread t owns the 4x4 blocks D(4br.., 4bc..) and Y(4br.., 4bc..)
-// with br = t/16, bc = t%16 (only bc <= br is live: both matrices are lower triangular).  Column c of the
-// trailing matrix and row c of the running inverse are published through double-buffered shared vectors, so
-// a step costs ONE barrier: publish -> barrier -> {pivot, rsqrt, rank-1 update of D, forward substitution of Y}.
-// The step is a template on c % 4 so that every register-array index is a compile-time constant.
 // 1/sqrt(x) for a positive finite pivot: MUFU seed + two Newton steps (relative error ~1e-16); rsqrt() from the
 // math library carries special-case handling that sits on the column-to-column dependency chain.
 __device__ __forceinline__ double fast_rsqrt(double x) {
@@ -203,7 +199,7 @@ __device__ void potf2_inv(double* __restrict__ At, int off, double* __restrict__
   for (int i = 0; i < 4; i++)
 #pragma unroll
     for (int jj = 0; jj < 4; jj++) {
-      d[i][jj] = live ? At[(4 * bc + jj) * LDA_S + off + 4 * br + i] : 0.0;
+      d[i][jj] = live ? At[AT_IDX(off + 4 * br + i, 4 * bc + jj)] : 0.0;
       y[i][jj] = (br == bc && i == jj) ? 1.0 : 0.0;
     }
   bool bad = false;
@@ -220,7 +216,7 @@ __device__ void potf2_inv(double* __restrict__ At, int off, double* __restrict__
 #pragma unroll
     for (int jj = 0; jj < 4; jj++) {
       const int r = 4 * br + i, cc = 4 * bc + jj;
-      At[cc * LDA_S + off + r] = (live && r >= cc) ? d[i][jj] : 0.0;
+      At[AT_IDX(off + r, cc)] = (live && r >= cc) ? d[i][jj] : 0.0;
       Ys[cc * LDB_S + r] = (live && r >= cc) ? y[i][jj] : 0.0;
     }
   if (bad) atomicExch(status, 1);
@@ -237,7 +233,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__ tasks, int ntasks, int32_t* ticket) {
   extern __shared__ __align__(128) double smem[];
   double* At = smem + STAGES * STAGE_D;
-  double* Ys = smem;                           // stage 0 is free once the K-loop has drained
+  double* Ys = smem;                           // stage 0 (A part, 2 units) is free once the K-loop has drained
   double* Ws = smem + STAGE_D;                 // stage 1: W rows of the factor for the kriging epilogue
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
@@ -269,56 +265,54 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
     const int4 tk = tasks[t];
     const ProblemDesc* pb = probs + tk.x;
     const int r = tk.y, j = tk.z;
-    double* __restrict__ L = pb->L; const int64_t ldL = pb->ldL;
-    double* __restrict__ P = pb->P; const int64_t ldP = pb->ldP;
+    double* __restrict__ L = pb->L; const int64_t nRUL = pb->nRUL;
+    double* __restrict__ P = pb->P; const int64_t nRUP = pb->nRUP;
     const int nCB = pb->nCB, mode = pb->mode, epoch = pb->epoch;
     int32_t* status = pb->status;
-    const int64_t R0 = (int64_t)r * TM, C0 = (int64_t)j * TN;
+    const int64_t R0 = (int64_t)r * TM;
     const int nchunks = j * (TN / KC);
     const uint32_t it0 = it;
     long long* prof = pb->prof ? pb->prof + (int64_t)t * 8 : nullptr;
     long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0, tp4 = 0, kwait = 0;
     if (prof && tid == 0) tp0 = (long long)gtime();
+    // the tile's four units in the owner's buffer: column halves 2j, 2j+1; row units 2r, 2r+1 (adjacent in memory)
+    double* const Pt0 = P + ((int64_t)(2 * j) * nRUP + 2 * r) * UNIT;
+    double* const Pt1 = P + ((int64_t)(2 * j + 1) * nRUP + 2 * r) * UNIT;
 
     if (warp == NCW) {
-      // ===================== producer warp: TMA bulk copies, one column per lane =====================
-      // generic-proxy accesses of the previous task (epilogue reads/writes of At, Ys) were ordered by the
-      // end-of-task __syncthreads; make them visible to the async proxy before it overwrites smem.
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      if (lane == 0) mbar_expect_tx(&at_bar, TN * TM * 8);
-      __syncwarp();
-      for (int c = lane; c < TN; c += 32) bulk_g2s(At + c * LDA_S, P + (C0 + c) * ldP + R0, TM * 8, &at_bar);
-      uint32_t itp = it0;
-      for (int c = 0; c < nchunks; c++, itp++) {
-        const int k = c >> 1;
-        if ((c & 1) == 0) {
-          // lane 0 polls (32 pollers per CTA would hammer one L2 sector); then every lane performs its own acquire
-          // load of the now-set flags, because each lane issues copies of the data they guard
-          if (lane == 0) {
+      // ===================== producer: TMA bulk copies, issued by one lane =====================
+      if (lane == 0) {
+        // generic-proxy accesses of the previous task (epilogue reads/writes of At, Ys) were ordered by the
+        // end-of-task __syncthreads; make them visible to the async proxy before it overwrites smem.
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&at_bar, AT_D * 8);
+        bulk_g2s(At, Pt0, 2 * UNIT * 8, &at_bar);
+        bulk_g2s(At + 2 * UNIT, Pt1, 2 * UNIT * 8, &at_bar);
+        uint32_t itp = it0;
+        for (int c = 0; c < nchunks; c++, itp++) {
+          const int k = c >> 1;
+          if ((c & 1) == 0) {
             wait_flag(pb->doneP + (int64_t)r * nCB + k, epoch, status, abort_flag);
             if (mode == 0) wait_flag(pb->doneL + (int64_t)(j >> 1) * nCB + k, epoch, status, abort_flag);
+            asm volatile("fence.proxy.async;" ::: "memory");
+            if (prof && k == j - 1) s_tdep = (long long)gtime();
           }
-          __syncwarp();
-          (void)ld_acquire(pb->doneP + (int64_t)r * nCB + k);
-          if (mode == 0) (void)ld_acquire(pb->doneL + (int64_t)(j >> 1) * nCB + k);
-          asm volatile("fence.proxy.async;" ::: "memory");
-          if (prof && lane == 0 && k == j - 1) s_tdep = (long long)gtime();
+          const uint32_t s = itp % STAGES, use = itp / STAGES;
+          if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1, status, abort_flag);
+          mbar_expect_tx(&full_bar[s], STAGE_D * 8);
+          double* As = smem + s * STAGE_D;
+          // unit column c (32 columns of L): A = row units 2r, 2r+1 of the owner's panel; B = row unit j of the factor
+          bulk_g2s(As, P + ((int64_t)c * nRUP + 2 * r) * UNIT, A_STAGE * 8, &full_bar[s]);
+          bulk_g2s(As + A_STAGE, L + ((int64_t)c * nRUL + j) * UNIT, B_STAGE * 8, &full_bar[s]);
         }
-        const uint32_t s = itp % STAGES, use = itp / STAGES;
-        if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1, status, abort_flag);
-        if (lane == 0) mbar_expect_tx(&full_bar[s], KC * (TM + TN) * 8);
-        __syncwarp();
-        double* As = smem + s * STAGE_D;
-        double* Bs = As + A_STAGE;
-        const int64_t col0 = (int64_t)k * TN + (c & 1) * KC;
-        static_assert(KC == 32, "one k-column per producer lane");
-        bulk_g2s(As + lane * LDA_S, P + (col0 + lane) * ldP + R0, TM * 8, &full_bar[s]);
-        bulk_g2s(Bs + lane * LDB_S, L + (col0 + lane) * ldL + C0, TN * 8, &full_bar[s]);
       }
       __syncwarp();
     } else {
       // ===================== consumers: DMMA K-loop + epilogue =====================
       const int wm = warp & 3, wn = warp >> 2;
+      const int kq = lane & 3, rq = lane >> 2;
+      const int aoff = (wm >> 1) * UNIT + (wm & 1) * 32 + rq;       // A fragment: unit of the row half + row in unit
+      const int boff = wn * 32 + rq;                                 // B fragment: row of the 64-row unit
       double acc[4][4][2];
 #pragma unroll
       for (int mi = 0; mi < 4; mi++)
@@ -337,24 +331,21 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
         const double* As = smem + s * STAGE_D;
         const double* Bs = As + A_STAGE;
 #pragma unroll
-        for (int k4 = 0; k4 < KC / 4; k4++) warp_mma_k4(acc, As, LDA_S, Bs, LDB_S, k4 * 4, wm, wn, lane);
+        for (int k4 = 0; k4 < KC / 4; k4++) warp_mma_k4(acc, As, aoff, Bs, boff, k4 * 4, lane);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[s]);
       }
       // ---- E1: tile = A - acc (in shared memory) ----
       if (prof && tid == 0) tp1 = (long long)gtime();
       mbar_wait(&at_bar, at_phase, status, abort_flag);
-      {
-        const int kq = lane & 3, rq = lane >> 2;
 #pragma unroll
-        for (int mi = 0; mi < 4; mi++)
+      for (int mi = 0; mi < 4; mi++)
 #pragma unroll
-          for (int ni = 0; ni < 4; ni++) {
-            const int row = wm * 32 + mi * 8 + rq, col = wn * 32 + ni * 8 + kq * 2;
-            At[col * LDA_S + row] -= acc[mi][ni][0];
-            At[(col + 1) * LDA_S + row] -= acc[mi][ni][1];
-          }
-      }
+        for (int ni = 0; ni < 4; ni++) {
+          const int row = wm * 32 + mi * 8 + rq, col = wn * 32 + ni * 8 + kq * 2;
+          At[AT_IDX(row, col)] -= acc[mi][ni][0];
+          At[AT_IDX(row, col + 1)] -= acc[mi][ni][1];
+        }
       consumer_bar();
       if (prof && tid == 0) tp2 = (long long)gtime();
       // ---- E2: diagonal block or fetch of the inverted diagonal block ----
@@ -366,10 +357,11 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
         double* invd = pb->invd + (int64_t)j * INVD_BLOCK;       // stored with the padded stride: one bulk copy reloads it
         for (int idx = tid; idx < INVD_BLOCK / 2; idx += NCW * 32)
           reinterpret_cast<double2*>(invd)[idx] = reinterpret_cast<const double2*>(Ys)[idx];
-        for (int idx = tid; idx < TN * (TN / 2); idx += NCW * 32) {
-          const int c = idx >> 5, rp = (idx & 31) * 2;
-          const double2 v = *reinterpret_cast<const double2*>(At + c * LDA_S + off + rp);
-          *reinterpret_cast<double2*>(P + (C0 + c) * ldP + R0 + off + rp) = v;
+        // L_jj: the two units (column halves) of row half off/64
+        for (int idx = tid; idx < UNIT; idx += NCW * 32) {        // UNIT double2 = 2 units
+          const int ch = idx / (UNIT / 2), w2 = idx % (UNIT / 2);
+          const double2 v = reinterpret_cast<const double2*>(At + (ch * 2 + (off >> 6)) * UNIT)[w2];
+          reinterpret_cast<double2*>((ch ? Pt1 : Pt0) + (off >> 6) * UNIT)[w2] = v;
         }
         __threadfence();
         asm volatile("fence.proxy.async;" ::: "memory");   // later readers fetch this block with the TMA engine
@@ -389,32 +381,36 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
       }
       if (prof && tid == 0) tp3 = (long long)gtime();
       if (row_lo < TM) {
-        // ---- E3: X = tile * inv(L_jj)' on the tensor pipe ----
+        // ---- E3: X = tile * inv(L_jj)' on the tensor pipe (k runs over the tile's 64 columns: two column halves) ----
         double x[4][4][2];
 #pragma unroll
         for (int mi = 0; mi < 4; mi++)
 #pragma unroll
           for (int ni = 0; ni < 4; ni++) { x[mi][ni][0] = 0.0; x[mi][ni][1] = 0.0; }
+#pragma unroll
+        for (int ch = 0; ch < 2; ch++) {
 #pragma unroll 4
-        for (int k4 = 0; k4 < TN / 4; k4++) warp_mma_k4(x, At, LDA_S, Ys, LDB_S, k4 * 4, wm, wn, lane);
-        consumer_bar();
-        {
-          const int kq = lane & 3, rq = lane >> 2;
-#pragma unroll
-          for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-            for (int ni = 0; ni < 4; ni++) {
-              const int row = wm * 32 + mi * 8 + rq, col = wn * 32 + ni * 8 + kq * 2;
-              if (row >= row_lo) { At[col * LDA_S + row] = x[mi][ni][0]; At[(col + 1) * LDA_S + row] = x[mi][ni][1]; }
-            }
+          for (int k4 = 0; k4 < KC / 4; k4++)
+            warp_mma_k4(x, At + ch * 2 * UNIT, aoff, Ys + ch * KC * LDB_S, boff, k4 * 4, lane);
         }
         consumer_bar();
-        // ---- E4: coalesced copy-out of rows [row_lo, TM) ----
-        const int npairs = (TM - row_lo) / 2;
-        for (int idx = tid; idx < TN * npairs; idx += NCW * 32) {
-          const int c = idx / npairs, rp = row_lo + (idx % npairs) * 2;
-          const double2 v = *reinterpret_cast<const double2*>(At + c * LDA_S + rp);
-          *reinterpret_cast<double2*>(P + (C0 + c) * ldP + R0 + rp) = v;
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+          for (int ni = 0; ni < 4; ni++) {
+            const int row = wm * 32 + mi * 8 + rq, col = wn * 32 + ni * 8 + kq * 2;
+            if (row >= row_lo) { At[AT_IDX(row, col)] = x[mi][ni][0]; At[AT_IDX(row, col + 1)] = x[mi][ni][1]; }
+          }
+        consumer_bar();
+        // ---- E4: copy-out of row halves [row_lo/64, 2): whole units, coalesced 16-byte stores ----
+        {
+          const int rh0 = row_lo >> 6, nun = (2 - rh0) * 2;       // units to store
+          for (int idx = tid; idx < nun * (UNIT / 2); idx += NCW * 32) {
+            const int u = idx / (UNIT / 2), w2 = idx % (UNIT / 2);
+            const int ch = u / (2 - rh0), rh = rh0 + u % (2 - rh0);
+            const double2 v = reinterpret_cast<const double2*>(At + (ch * 2 + rh) * UNIT)[w2];
+            reinterpret_cast<double2*>((ch ? Pt1 : Pt0) + rh * UNIT)[w2] = v;
+          }
         }
         // ---- E5: border reductions (ordered by the flag chain => deterministic, no atomics) ----
         const int q = pb->q;
@@ -424,29 +420,29 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
             for (int e = tid; e < q * q; e += NCW * 32) {
               const int a = e % q, b = e / q;
               double s = 0.0;
-              for (int c = 0; c < TN; c++) s += At[c * LDA_S + wl0 + a] * At[c * LDA_S + wl0 + b];
+              for (int c = 0; c < TN; c++) s += At[AT_IDX(wl0 + a, c)] * At[AT_IDX(wl0 + b, c)];
               double* G = pb->G + e;            // __ldcg: the previous column's CTA wrote it through L2
               *G = (j == 0 ? 0.0 : __ldcg(G)) + s;
             }
           }
         } else {
-          // kriging rows: G(:,0..q-1) += X Yw', G(:,q) += rowsum(X^2)
+          // kriging rows: G(:,0..q-1) += X Yw', G(:,q) += rowsum(X^2); Yw = rows w0.. of the factor buffer
           for (int idx = tid; idx < q * TN; idx += NCW * 32) {
             const int w = idx % q, c = idx / q;
-            Ws[c * 64 + w] = __ldcg(pb->YW + (C0 + c) * ldL + w);
+            Ws[c * 64 + w] = __ldcg(L + uidx((int64_t)pb->w0 + w, (int64_t)j * TN + c, nRUL));
           }
           consumer_bar();
           if (tid < TM) {
             double* G = pb->G + R0 + tid;
             double ssq = 0.0;
-            for (int c = 0; c < TN; c++) { const double xv = At[c * LDA_S + tid]; ssq += xv * xv; }
+            for (int c = 0; c < TN; c++) { const double xv = At[AT_IDX(tid, c)]; ssq += xv * xv; }
             G[(int64_t)q * pb->ldG] = (j == 0 ? 0.0 : __ldcg(G + (int64_t)q * pb->ldG)) + ssq;
             for (int wb = 0; wb < q; wb += 16) {
               double g[16];
 #pragma unroll
               for (int w = 0; w < 16; w++) g[w] = 0.0;
               for (int c = 0; c < TN; c++) {
-                const double xv = At[c * LDA_S + tid];
+                const double xv = At[AT_IDX(tid, c)];
 #pragma unroll
                 for (int w = 0; w < 16; w++) g[w] += xv * Ws[c * 64 + ((wb + w) & 63)];
               }
@@ -492,8 +488,14 @@ __global__ void finish_kernel(const ProblemDesc* __restrict__ probs, int count, 
 }
 
 // ---- back-substitution  L' X = Y  for a few right-hand sides (iAW of fitIAK3D.R:782-808) ------------
-// Y is stored as rows (Y' in the W rows of the factor buffer).  Block-column sweep from the right:
-//   x_J = inv(L_JJ)' y_J ;  y_K -= L(J,K)' x_J for all K < J.   Not on the optimiser's hot loop.
+// Y' lives in the bordered rows of the blocked factor buffer; it is first gathered to a compact q x Npad array.
+// Block-column sweep from the right:  x_J = inv(L_JJ)' y_J ;  y_K -= L(J,K)' x_J for all K < J.
+// Not on the optimiser's hot loop.
+__global__ void gather_border_kernel(const double* __restrict__ L, int64_t nRU, int64_t Npad, int q, double* __restrict__ Yw) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Npad) return;
+  for (int w = 0; w < q; w++) Yw[c * q + w] = L[uidx(Npad + w, c, nRU)];
+}
 __global__ void backsolve_diag_kernel(const double* __restrict__ invd, int J, const double* __restrict__ Yw, int64_t ldY, int q,
                                       double* __restrict__ X, int64_t ldX) {
   // x_J (64 x q) = invL_JJ' * y_J ; thread (row i of x, rhs w)
@@ -509,7 +511,7 @@ __global__ void backsolve_diag_kernel(const double* __restrict__ invd, int J, co
     X[(int64_t)w * ldX + J * TN + i] = s;
   }
 }
-__global__ void backsolve_update_kernel(const double* __restrict__ L, int64_t ldL, int J, const double* __restrict__ X,
+__global__ void backsolve_update_kernel(const double* __restrict__ L, int64_t nRU, int J, const double* __restrict__ X,
                                         int64_t ldX, int q, double* __restrict__ Yw, int64_t ldY) {
   // for column c < J*TN : y_c(w) -= sum_{i in block J} L(J*TN+i, c) * x_J(i, w)
   __shared__ double xs[TN * 64];
@@ -518,7 +520,7 @@ __global__ void backsolve_update_kernel(const double* __restrict__ L, int64_t ld
   __syncthreads();
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + tid;
   if (c >= (int64_t)J * TN) return;
-  const double* col = L + c * ldL + (int64_t)J * TN;
+  const double* col = L + uidx((int64_t)J * TN, c, nRU);     // 64 consecutive rows of one unit
   for (int wb = 0; wb < q; wb += 16) {
     double s[16];
 #pragma unroll
@@ -589,20 +591,26 @@ int launch_finish(iak3d_ctx* ctx, const ProblemDesc* d_problems, int32_t count, 
   return 0;
 }
 
-int launch_backsolve(iak3d_ctx* ctx, const double* d_L, int64_t ld, int64_t Npad, const double* d_invd, double* d_Yw, int64_t ldY,
-                     int32_t q, double* d_X) {
-  // d_Yw: q x Npad (column-major, ldY) copy of the Y' rows -- destroyed.  d_X: Npad x q column-major out.
+int launch_backsolve(iak3d_ctx* ctx, const double* d_L, int64_t nRU, int64_t Npad, const double* d_invd, int32_t q, double* d_X) {
+  // d_X: Npad x q column-major out
+  double* d_Yw = nullptr;
+  CUDA_TRY(ctx, cudaMalloc(&d_Yw, (size_t)q * Npad * sizeof(double)));
+  gather_border_kernel<<<(unsigned)((Npad + 127) / 128), 128, 0, ctx->stream>>>(d_L, nRU, Npad, q, d_Yw);
+  ctx->launches++;
   const int nCB = (int)(Npad / TN);
   for (int J = nCB - 1; J >= 0; J--) {
-    backsolve_diag_kernel<<<1, 256, 0, ctx->stream>>>(d_invd, J, d_Yw, ldY, q, d_X, Npad);
+    backsolve_diag_kernel<<<1, 256, 0, ctx->stream>>>(d_invd, J, d_Yw, q, q, d_X, Npad);
     ctx->launches++;
     if (J > 0) {
       const int blocks = (J * TN + 127) / 128;
-      backsolve_update_kernel<<<blocks, 128, 0, ctx->stream>>>(d_L, ld, J, d_X, Npad, q, d_Yw, ldY);
+      backsolve_update_kernel<<<blocks, 128, 0, ctx->stream>>>(d_L, nRU, J, d_X, Npad, q, d_Yw, q);
       ctx->launches++;
     }
   }
-  CUDA_TRY(ctx, cudaGetLastError());
+  const cudaError_t e = cudaGetLastError();
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_Yw);
+  CUDA_TRY(ctx, e);
   return 0;
 }
 

@@ -15,6 +15,22 @@ constexpr int TN = 64;       // tile cols  (column-block width == panel width of
 constexpr int INVD_LD = TN + 4;              // inverse diagonal blocks are kept with the padded shared-memory stride
 constexpr int INVD_BLOCK = TN * INVD_LD;     // doubles per stored inverse block
 
+// ---- blocked storage of factor buffers and kriging panels ---------------------------------------
+// A matrix with R rows (multiple of 128) is stored as UNITS of 64 rows x 32 columns.  Inside a unit the 32
+// columns are column-major with leading dimension UL = 68 -- exactly the bank-conflict-free layout the DMMA
+// fragment loads want in shared memory -- so that one cp.async.bulk (TMA) of a whole unit (17,408 B), or of the two
+// vertically adjacent units of a 128-row block (34,816 B), lands a pipeline stage without any reshaping.
+// Units are ordered column-panel by column-panel: unit (ru, cu) sits at (cu * nRU + ru) * UNIT, nRU = R / 64.
+constexpr int UR = 64, UC = 32, UL = 68;
+constexpr int UNIT = UC * UL;                // 2176 doubles
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline int64_t uidx(int64_t i, int64_t c, int64_t nRU) {
+  return ((c >> 5) * nRU + (i >> 6)) * UNIT + (c & 31) * UL + (i & 63);
+}
+static inline int64_t ubuf_doubles(int64_t rows, int64_t cols) { return (cols / UC) * (rows / UR) * (int64_t)UNIT; }
+
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 struct iak3d_ctx {
@@ -42,7 +58,7 @@ struct iak3d_ctx {
 struct Slot {
   int64_t n = 0, Npad = 0, ld = 0, nxU = 0, ndIU = 0;
   int32_t q = 0, nCB = 0, nRB = 0;
-  double* d_L = nullptr;          // ld x Npad factor buffer (A in, L out; W' rows at Npad..Npad+q-1)
+  double* d_L = nullptr;          // ld x Npad factor buffer, BLOCKED (uidx): A in, L out; W' rows at Npad..Npad+q-1
   double* d_phix = nullptr;       // nxU x nxU horizontal correlation table
   double* d_phid = nullptr;       // 3 tables ndIU x ndIU + 3 avVar vectors
   double* d_invd = nullptr;       // nCB x INVD_BLOCK inverted diagonal blocks
@@ -122,31 +138,31 @@ int launch_sigma2(iak3d_ctx* ctx, const EvalPlan& pl, const double* d_avvar /* 3
                   int64_t n, double* d_out);
 int launch_ckk(iak3d_ctx* ctx, const EvalPlan& pl, const double* const* d_Tself /* per table: ndIU1 x ndIU1 */, int64_t ndIU1,
                const int32_t* d_did1, int64_t m, double* d_out);
+// blocked != 0: d_out is a blocked buffer (uidx) with rows_total rows; otherwise plain column-major with leading dim ld
 int launch_cov_rect(iak3d_ctx* ctx, const CovArgs& a, double* d_out, int64_t ld, int64_t rows_total, int64_t cols_total,
-                    int symmetric_square);
+                    int symmetric_square, int blocked = 0);
 
 // ---- factorisation (chol.cu) -------------------------------------------------------------------
 struct ProblemDesc {
-  double* L; int64_t ldL;        // factor storage; B operand + diagonal blocks
-  double* P; int64_t ldP;        // row-panel storage the task owns (== L when factorising)
-  double* invd;                  // nCB x TN*TN inverse diagonal blocks
+  double* L; int64_t nRUL;       // factor storage (blocked, nRUL row units); B operand + diagonal blocks
+  double* P; int64_t nRUP;       // row-panel storage the task owns (== L when factorising), blocked
+  double* invd;                  // nCB x INVD_BLOCK inverse diagonal blocks
   int32_t* doneL; int32_t* doneP; int32_t* invdone;
   int32_t nCB, nRB;              // col-blocks of L / row-blocks of P
   int32_t mode;                  // 0 = factorise (P == L), 1 = bordered rows against a finished factor
   int32_t epoch;
-  int32_t w0, q;                 // factorise: local W rows start (global row index) and count; mode 1: q of YW
+  int32_t w0, q;                 // W rows start (global row index in L) and count
   double* G;                     // mode 0: q*q Gram; mode 1: rowsP x (q+1) accumulators
   int64_t ldG;
   double* logsum;                // nCB
   int32_t* status;               // [0] not-SPD, [1] timeout
-  const double* YW;              // mode 1: W rows of the factor buffer (L + w0), ld = ldL
   long long* prof;               // optional per-task timestamps (8 per task, globaltimer ns), nullptr = off
 };
 int chol_configure(iak3d_ctx* ctx);
 int launch_tile_tasks(iak3d_ctx* ctx, const ProblemDesc* d_problems, const int4* d_tasks, int32_t ntasks, int32_t* d_ticket /* 2 ints */);
 int launch_finish(iak3d_ctx* ctx, const ProblemDesc* d_problems, int32_t count, double* d_results, int32_t stride);
-int launch_backsolve(iak3d_ctx* ctx, const double* d_L, int64_t ld, int64_t Npad, const double* d_invd, double* d_Yw, int64_t ldY,
-                     int32_t q, double* d_X /* Npad x q col-major out */);
+// X = L^-T Y for the q bordered rows of a finished blocked factor; d_X: Npad x q column-major out
+int launch_backsolve(iak3d_ctx* ctx, const double* d_L, int64_t nRU, int64_t Npad, const double* d_invd, int32_t q, double* d_X);
 int launch_peak(iak3d_ctx* ctx, int kind, double* tflops);
 // kriging epilogue (predictIAK3D.R:229-255): z, v from the bordered-row accumulators G (ldG x (q+1))
 int launch_krige_finish(iak3d_ctx* ctx, const double* d_G, int64_t ldG, int32_t q, const double* d_XMap, int64_t ldX, int64_t m,

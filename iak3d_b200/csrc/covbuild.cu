@@ -64,7 +64,7 @@ __device__ __forceinline__ double cov_value(const CovDev& a, int xi, int di, int
   return v;
 }
 
-// ---- factor-layout build: lower-triangular TM x TN tiles of the padded factor buffer ---------------
+// ---- factor-layout build: lower-triangular TM x TN tiles of the padded, BLOCKED factor buffer (common.cuh) ----
 // rows [0,n) data, [n,Npad) identity padding, [Npad,Npad+q) the W' rows (bordered system), rest zero.
 __global__ void __launch_bounds__(256) cov_factor_kernel(CovDev a, const double* __restrict__ W, int q, int64_t n,
                                                          int64_t Npad, double* __restrict__ L, int64_t ld, int nCB) {
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256) cov_factor_kernel(CovDev a, const double*
       else val = 0.0;
       v[e] = val;
     }
-    *reinterpret_cast<double2*>(L + c * ld + i0) = make_double2(v[0], v[1]);
+    *reinterpret_cast<double2*>(L + uidx(i0, c, nRB * 2)) = make_double2(v[0], v[1]);   // blocked layout, 16-byte store
   }
 }
 
@@ -152,7 +152,7 @@ int launch_cov_factor_layout(iak3d_ctx* ctx, const CovArgs& h, const double* d_W
 // out is column-major with leading dimension ld; rows >= nr and cols >= nc are zero-filled up to
 // rows_total x cols_total.  symmetric_square adds cme on the diagonal (row index == col index).
 __global__ void __launch_bounds__(256) cov_rect_kernel(CovDev a, double* __restrict__ out, int64_t ld, int64_t rows_total,
-                                                       int64_t cols_total, int sym) {
+                                                       int64_t cols_total, int sym, int blocked) {
   __shared__ int32_t s_xc[TN], s_dc[TN];
   const int64_t R0 = (int64_t)blockIdx.x * TM, C0 = (int64_t)blockIdx.y * TN;
   const int tid = threadIdx.x;
@@ -174,13 +174,13 @@ __global__ void __launch_bounds__(256) cov_rect_kernel(CovDev a, double* __restr
       if (i >= rows_total) continue;
       double val = 0.0;
       if (i < a.nr && c < a.nc) val = cov_value(a, xi[e], di[e], xj, dj, sym && i == c);
-      out[c * ld + i] = val;
+      if (blocked) out[uidx(i, c, rows_total >> 6)] = val; else out[c * ld + i] = val;
     }
   }
 }
 
 int launch_cov_rect(iak3d_ctx* ctx, const CovArgs& h, double* d_out, int64_t ld, int64_t rows_total, int64_t cols_total,
-                    int symmetric_square) {
+                    int symmetric_square, int blocked) {
   CovDev a;
   for (int k = 0; k < 3; k++) { a.T[k] = h.T[k]; a.tidx[k] = h.tidx[k]; }
   a.ntab = h.ntab; a.phix = h.phix; a.same = h.same;
@@ -190,7 +190,7 @@ int launch_cov_rect(iak3d_ctx* ctx, const CovArgs& h, double* d_out, int64_t ld,
   if (rows_total == 0 || cols_total == 0) return 0;
   dim3 grid((unsigned)((rows_total + TM - 1) / TM), (unsigned)((cols_total + TN - 1) / TN));
   if (grid.y > 65535) { ctx->err = "cov_rect: too many column tiles"; return IAK3D_ERR_ARG; }
-  cov_rect_kernel<<<grid, 256, 0, ctx->stream>>>(a, d_out, ld, rows_total, cols_total, symmetric_square);
+  cov_rect_kernel<<<grid, 256, 0, ctx->stream>>>(a, d_out, ld, rows_total, cols_total, symmetric_square, blocked);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return 0;
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(256) pack_factor_kernel(const double* __restri
     } else {
       v = (i == c) ? 1.0 : 0.0;
     }
-    L[c * ld + i] = v;
+    L[uidx(i, c, ld >> 6)] = v;
   }
 }
 int launch_pack_factor_layout(iak3d_ctx* ctx, const double* d_C, int64_t n, const double* d_b, int32_t q, int64_t Npad,
