@@ -558,8 +558,11 @@ static int batch_reserve(iak3d_ctx* ctx, Batch* b, int32_t count, int32_t q) {
   return 0;
 }
 
-// Task order: by column block, then problem, then row block.  Every dependency of a task (same problem: earlier
-// columns; the column's own diagonal task) precedes it, which is all the ticket scheduler needs (chol.cu).
+// Task order: by column block, then problem; inside a (column j, problem) group the tile that the NEXT diagonal
+// block needs comes first, then the next column's diagonal task itself (look-ahead: its long K-loop and its
+// potf2 overlap with the rest of column j, so column j+1's tiles find the inverse diagonal block ready), then the
+// remaining row blocks.  Every dependency of a task (same problem: earlier columns of its row block and of the
+// column block's rows; the column's own diagonal task) precedes it, which is all the ticket scheduler needs.
 static int batch_tasks(iak3d_ctx* ctx, Batch* b, const std::vector<ProblemDesc>& probs, const std::vector<int>& live) {
   std::vector<int64_t> key;
   key.reserve(live.size() * 3);
@@ -571,7 +574,15 @@ static int batch_tasks(iak3d_ctx* ctx, Batch* b, const std::vector<ProblemDesc>&
   for (int j = 0; j < maxCB; j++)
     for (size_t i = 0; i < live.size(); i++) {
       if (!live[i] || j >= probs[i].nCB) continue;
-      for (int r = j / 2; r < probs[i].nRB; r++) tasks.push_back(make_int4((int)i, r, j, 0));
+      const int nCB = probs[i].nCB, nRB = probs[i].nRB;
+      const int rd = j >> 1;                       // row block of this column's diagonal task
+      if (j == 0) tasks.push_back(make_int4((int)i, 0, 0, 0));
+      const int rn = (j + 1) >> 1;                 // row block holding the next diagonal block
+      const bool have_next = (j + 1 < nCB);
+      if (have_next && rn != rd) tasks.push_back(make_int4((int)i, rn, j, 0));
+      if (have_next) tasks.push_back(make_int4((int)i, rn, j + 1, 0));          // look-ahead diagonal task
+      for (int r = rd + 1; r < nRB; r++)
+        if (!(have_next && r == rn)) tasks.push_back(make_int4((int)i, r, j, 0));
     }
   if ((int64_t)tasks.size() > b->tasks_cap) {
     cudaFree(b->d_tasks); b->d_tasks = nullptr;
