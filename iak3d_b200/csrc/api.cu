@@ -330,23 +330,50 @@ int iak_get_slot(iak3d_ds* ds, size_t k, Slot** out) {
 // ================================================================================================
 // tables for one evaluation of a dataset (square) into a slot; fills CovArgs
 // ================================================================================================
-int iak_square_tables(iak3d_ctx* ctx, const iak3d_ds* ds, const EvalPlan& pl, Slot* s, CovArgs* a) {
+// `cache` (optional) de-duplicates tables inside one batch: the npar+1 evaluations of a forward-difference gradient
+// differ in one parameter each, so all but one share the horizontal table and all but one the depth tables.
+struct TableCache {
+  struct Entry { const iak3d_ds* ds; int kind; double k[6]; const double* ptr; };
+  std::vector<Entry> e;
+  const double* find(const iak3d_ds* ds, int kind, const double* k) const {
+    for (const Entry& x : e)
+      if (x.ds == ds && x.kind == kind && memcmp(x.k, k, sizeof(x.k)) == 0) return x.ptr;
+    return nullptr;
+  }
+  void add(const iak3d_ds* ds, int kind, const double* k, const double* ptr) {
+    Entry x; x.ds = ds; x.kind = kind; memcpy(x.k, k, sizeof(x.k)); x.ptr = ptr; e.push_back(x);
+  }
+};
+
+int iak_square_tables(iak3d_ctx* ctx, const iak3d_ds* ds, const EvalPlan& pl, Slot* s, CovArgs* a, TableCache* cache = nullptr) {
   const int64_t nd = ds->ndIU, nx = ds->nxU;
   for (int k = 0; k < 3; k++) a->T[k] = nullptr;
   for (int k = 0; k < pl.ntab; k++) {
+    const IaPrm& P = pl.prm[k];
+    const double key[6] = {P.psi, P.tau0, P.tau1, P.tau2, P.g11[1], P.g11[2]};     // (ad, nud, sd function) determine the table
+    const double* hit = cache ? cache->find(ds, 1, key) : nullptr;
+    if (hit != nullptr) { a->T[k] = hit; continue; }
     double* T = s->d_phid + (size_t)k * nd * nd;
     double* av = s->d_phid + (size_t)3 * nd * nd + (size_t)k * nd;
-    const int st = launch_iacov_table(ctx, pl.prm[k], ds->d_dIU, nd, ds->d_dIU, nd, T, av);
+    const int st = launch_iacov_table(ctx, P, ds->d_dIU, nd, ds->d_dIU, nd, T, av);
     if (st != 0) return st;
     a->T[k] = T;
+    if (cache) cache->add(ds, 1, key, T);
   }
   for (int c = 0; c < 3; c++) a->tidx[c] = pl.tidx[c];
   a->ntab = pl.ntab;
   a->phix = nullptr; a->same = nullptr;
   if (pl.has_phix) {
-    const int st = launch_phix_table(ctx, pl.H, ds->d_xU, nx, ds->d_xU, nx, s->d_phix, nullptr);
-    if (st != 0) return st;
-    a->phix = s->d_phix;
+    const double key[6] = {(double)pl.H.modelx, pl.H.a, pl.H.nu, 0, 0, 0};
+    const double* hit = cache ? cache->find(ds, 2, key) : nullptr;
+    if (hit != nullptr) {
+      a->phix = hit;
+    } else {
+      const int st = launch_phix_table(ctx, pl.H, ds->d_xU, nx, ds->d_xU, nx, s->d_phix, nullptr);
+      if (st != 0) return st;
+      a->phix = s->d_phix;
+      if (cache) cache->add(ds, 2, key, s->d_phix);
+    }
   }
   a->cx0 = pl.cx0; a->cx1 = pl.cx1; a->kd1 = pl.kd1; a->cxd0 = pl.cxd0; a->cxd1 = pl.cxd1; a->cme = pl.cme;
   a->xid_r = ds->d_xid; a->did_r = ds->d_did; a->xid_c = ds->d_xid; a->did_c = ds->d_did;
@@ -658,9 +685,10 @@ extern "C" int iak3d_nll_terms_batch_enqueue(iak3d_ctx* ctx, int32_t count, iak3
 
   CUDA_TRY(ctx, cudaEventRecord(ctx->evs[0], ctx->stream));
   std::vector<CovArgs> cargs((size_t)count);
+  TableCache cache;
   for (int i = 0; i < count; i++) {
     if (!live[i]) continue;
-    st = iak_square_tables(ctx, dss[i], plans[i], b->slots[i], &cargs[i]);
+    st = iak_square_tables(ctx, dss[i], plans[i], b->slots[i], &cargs[i], &cache);
     if (st != 0) return st;
   }
   CUDA_TRY(ctx, cudaEventRecord(ctx->evs[1], ctx->stream));

@@ -132,7 +132,22 @@ IAK_HD double iak_chebev(const double* c, int m, double x) {        // Clenshaw 
   return x * d - dd + 0.5 * c[0];
 }
 
-IAK_HD double iak_besselk(double nu, double x) {
+// Optional per-order reciprocal table `rt` (device: built once per thread block in shared memory by
+// iak_besselk_table): the divisors of both iterations depend only on the order, not on x, so the table
+// removes every division from the Temme loop and two of the three from the Steed loop.
+//   rt[4*i + 0] = 1/(i*i - mu^2)   rt[4*i + 1] = 1/(i - mu)   rt[4*i + 2] = 1/(i + mu)        (Temme, i >= 1)
+//   rt[4*i + 3] = 1/a_i with a_i = -(1/4 - mu^2) - i(i-1)                                      (Steed, i >= 2)
+#define IAK_BK_NRT 48
+IAK_HD void iak_besselk_table(double nu, double* rt, int i) {       // entry i of the table (1 <= i < IAK_BK_NRT)
+  const int nl = (int)(nu + 0.5);
+  const double xmu = nu - nl, xmu2 = xmu * xmu;
+  rt[4 * i + 0] = 1.0 / (i * (double)i - xmu2);
+  rt[4 * i + 1] = 1.0 / (i - xmu);
+  rt[4 * i + 2] = 1.0 / (i + xmu);
+  rt[4 * i + 3] = 1.0 / (-(0.25 - xmu2) - (double)i * (i - 1));
+}
+
+IAK_HD double iak_besselk(double nu, double x, const double* rt) {
   const double EPS = 1e-16, PI = 3.141592653589793238462643;
   if (!(x > 0.0)) return INFINITY;
   if (x > 705.342) return 0.0;                                       // R nmath xmax_BESS_K
@@ -158,10 +173,17 @@ IAK_HD double iak_besselk(double nu, double x) {
     d = 0.25 * x * x;
     double sum1 = p;
     for (int i = 1; i <= 10000; i++) {
-      ff = (i * ff + p + q) / (i * (double)i - xmu2);
-      c *= (d / i);
-      p /= (i - xmu);
-      q /= (i + xmu);
+      if (rt != nullptr && i < IAK_BK_NRT) {
+        ff = (i * ff + p + q) * rt[4 * i + 0];
+        c *= d * (1.0 / i);
+        p *= rt[4 * i + 1];
+        q *= rt[4 * i + 2];
+      } else {
+        ff = (i * ff + p + q) / (i * (double)i - xmu2);
+        c *= (d / i);
+        p /= (i - xmu);
+        q /= (i + xmu);
+      }
       const double del = c * ff;
       sum += del;
       sum1 += c * (p - i * ff);
@@ -174,8 +196,14 @@ IAK_HD double iak_besselk(double nu, double x) {
     double q = a1, c = a1, a = -a1, s = 1.0 + q * delh;
     for (int i = 2; i <= 10000; i++) {
       a -= 2 * (i - 1);
-      c = -a * c / i;
-      const double qnew = (q1 - b * q2) / a;
+      double qnew;
+      if (rt != nullptr && i < IAK_BK_NRT) {
+        c = -a * c * (1.0 / i);
+        qnew = (q1 - b * q2) * rt[4 * i + 3];
+      } else {
+        c = -a * c / i;
+        qnew = (q1 - b * q2) / a;
+      }
       q1 = q2; q2 = qnew;
       q += c * qnew;
       b += 2.0;
@@ -221,7 +249,7 @@ IAK_HD double iak_wendland(double D, double theta, int k, const double* beta, do
   return (d < 1.0) ? iak_wend_eval(d, k, beta) / sc : 0.0;
 }
 
-IAK_HD double iak_phix(double D, const HxPrm* H) {
+IAK_HD double iak_phix(double D, const HxPrm* H, const double* rt = nullptr) {
   if (H->modelx == 1) {                                              // spherical :336-348
     const double r = D / H->a;
     if (r > 1.0) return 0.0;
@@ -237,7 +265,7 @@ IAK_HD double iak_phix(double D, const HxPrm* H) {
     if (H->half == 1) return exp(-x);
     if (H->half == 3) return (1.0 + x) * exp(-x);
     if (H->half == 5) return (1.0 + x + (x * x) / 3.0) * exp(-x);
-    const double K = iak_besselk(H->nu, x);
+    const double K = iak_besselk(H->nu, x, rt);
     const double v = exp(H->nu * log(x) + H->lconst + log(K));
     if (isinf(v)) return 1.0;                                        // :364 is.infinite -> c1
     return v;

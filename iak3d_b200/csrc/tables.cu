@@ -33,16 +33,28 @@ int launch_iacov_table(iak3d_ctx* ctx, const IaPrm& P, const double* d_dI1, int6
 // phi_x on unique location pairs; D as in xyDist (iaCovMatern.R:888-920): squares added in dimension
 // order, then sqrt.  Optionally records the exact-equality indicator 1[D == 0] (fitIAK3D.R:1138).
 __global__ void phix_table_kernel(HxPrm H, const double* __restrict__ x1, int64_t n1, const double* __restrict__ x2,
-                                  int64_t n2, double* __restrict__ out, uint8_t* __restrict__ zero) {
+                                  int64_t n2, double* __restrict__ out, uint8_t* __restrict__ zero, int symmetric) {
+  __shared__ double s_rt[4 * IAK_BK_NRT];
+  const bool bessel = (H.modelx == 2 && H.half == 0);
+  if (bessel) {
+    for (int i = 1 + threadIdx.x; i < IAK_BK_NRT; i += blockDim.x) iak_besselk_table(H.nu, s_rt, i);
+    __syncthreads();
+  }
+  const double* rt = bessel ? s_rt : nullptr;
   const int64_t total = n1 * n2;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = idx % n1, j = idx / n1;
+    if (symmetric && i < j) continue;            // x1 == x2: the lower triangle is mirrored (same arithmetic, same bits)
     const double dx = x1[i] - x2[j], dy = x1[n1 + i] - x2[n2 + j];
     double D = 0.0;
     D = D + dx * dx;
     D = D + dy * dy;
     D = sqrt(D);
-    if (out != nullptr) out[idx] = iak_phix(D, &H);
+    if (out != nullptr) {
+      const double v = iak_phix(D, &H, rt);
+      out[idx] = v;
+      if (symmetric) out[i * n1 + j] = v;
+    }
     if (zero != nullptr) zero[idx] = (D == 0.0) ? 1 : 0;
   }
 }
@@ -53,15 +65,23 @@ int launch_phix_table(iak3d_ctx* ctx, const HxPrm& H, const double* d_x1, int64_
   if (total == 0) return 0;
   int blocks = (int)((total + 255) / 256);
   if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
-  phix_table_kernel<<<blocks, 256, 0, ctx->stream>>>(H, d_x1, n1, d_x2, n2, d_out, d_zero);
+  const int symmetric = (d_x1 == d_x2 && n1 == n2 && d_zero == nullptr) ? 1 : 0;
+  phix_table_kernel<<<blocks, 256, 0, ctx->stream>>>(H, d_x1, n1, d_x2, n2, d_out, d_zero, symmetric);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return 0;
 }
 
 __global__ void phix_vec_kernel(HxPrm H, const double* __restrict__ D, int64_t m, double* __restrict__ out) {
+  __shared__ double s_rt[4 * IAK_BK_NRT];
+  const bool bessel = (H.modelx == 2 && H.half == 0);
+  if (bessel) {
+    for (int i = 1 + threadIdx.x; i < IAK_BK_NRT; i += blockDim.x) iak_besselk_table(H.nu, s_rt, i);
+    __syncthreads();
+  }
+  const double* rt = bessel ? s_rt : nullptr;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < m; idx += (int64_t)gridDim.x * blockDim.x)
-    out[idx] = iak_phix(D[idx], &H);
+    out[idx] = iak_phix(D[idx], &H, rt);
 }
 
 int launch_phix_vec(iak3d_ctx* ctx, const HxPrm& H, const double* d_D, int64_t m, double* d_out) {

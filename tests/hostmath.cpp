@@ -18,7 +18,13 @@ int hm_avvar(double a, double b, double ad, double nud, int sdfdType, double s1,
   *out = iak_avvar(a, b, &P);
   return 0;
 }
-double hm_besselk(double nu, double x) { return iak_besselk(nu, x); }
+double hm_besselk(double nu, double x) { return iak_besselk(nu, x, nullptr); }
+/* the table-driven variant the device kernels use */
+double hm_besselk_rt(double nu, double x) {
+  double rt[4 * IAK_BK_NRT];
+  for (int i = 1; i < IAK_BK_NRT; i++) iak_besselk_table(nu, rt, i);
+  return iak_besselk(nu, x, rt);
+}
 /* Matern / spherical only (the Wendland coefficients are prepared in tables.cu) */
 double hm_phix(double D, int modelx, double a, double nu) {
   HxPrm H;
