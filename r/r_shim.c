@@ -1,0 +1,203 @@
+/* r_shim.c -- .Call entry points that bind libiak3d.so (include/iak3d.h) into R.
+ *
+ * Build where R is installed (it is not in the image this repository is developed in):
+ *     R CMD SHLIB -o iak3dR.so r/r_shim.c -I include -L iak3d_b200/lib -liak3d -Wl,-rpath,$PWD/iak3d_b200/lib
+ * then  dyn.load("iak3dR.so"); source("r/iak3d_cuda.R")  AFTER the reference's own source() calls
+ * (egEdgeroi.R:53-71).  Handles are R external pointers with finalizers; every numeric argument is an R double
+ * vector / matrix (column-major, exactly what the ABI takes); status codes are returned to R, which maps
+ * 1 / 2 to badnll = 9E99 (fitIAK3D.R:685,785-806) and negative values to stop().
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+#include <string.h>
+
+#include "iak3d.h"
+
+static iak3d_ctx* g_ctx = NULL;
+
+static iak3d_ctx* ctx_get(void) {
+  if (g_ctx == NULL) {
+    int st = iak3d_ctx_create(0, &g_ctx);
+    if (st != IAK3D_OK) error("iak3d: no sm_100-class GPU / library initialisation failed (status %d); there is no CPU fallback", st);
+  }
+  return g_ctx;
+}
+
+static void ds_finalizer(SEXP p) {
+  iak3d_ds* ds = (iak3d_ds*)R_ExternalPtrAddr(p);
+  if (ds) { iak3d_dataset_destroy(ds); R_ClearExternalPtr(p); }
+}
+static void fit_finalizer(SEXP p) {
+  iak3d_fit* f = (iak3d_fit*)R_ExternalPtrAddr(p);
+  if (f) { iak3d_fit_destroy(f); R_ClearExternalPtr(p); }
+}
+
+/* parsBTfmd (list from readParsIAK3D) + model switches -> struct iak3d_pars.  pv = c(modelx, cmeOpt, sdfdType_cd1,
+ * sdfdType_cxd0, sdfdType_cxd1, quirk, ax, nux, ad, nud, cx0, cx1, cd1, cxd0, cxd1, cme, tau(3x2 row-major), quirk_scale) */
+static void pars_from(SEXP pv, iak3d_pars* P) {
+  const double* v = REAL(pv);
+  if (LENGTH(pv) != 23) error("iak3d: parameter vector must have 23 entries");
+  memset(P, 0, sizeof(*P));
+  P->modelx = (int32_t)v[0]; P->cmeOpt = (int32_t)v[1];
+  P->sdfdType[0] = (int32_t)v[2]; P->sdfdType[1] = (int32_t)v[3]; P->sdfdType[2] = (int32_t)v[4];
+  P->quirk_cd1_unscaled = (int32_t)v[5];
+  P->ax = v[6]; P->nux = v[7]; P->ad = v[8]; P->nud = v[9];
+  P->cx0 = v[10]; P->cx1 = v[11]; P->cd1 = v[12]; P->cxd0 = v[13]; P->cxd1 = v[14]; P->cme = v[15];
+  for (int c = 0; c < 3; c++) { P->sdfdPars[c][0] = v[16 + 2 * c]; P->sdfdPars[c][1] = v[17 + 2 * c]; }
+  P->quirk_scale = v[22];
+}
+
+/* setupIAK3D: xData (n x 2), dIData (n x 2, already rounded, fitIAK3D.R:127), W = cbind(X, z) or NULL */
+SEXP iak3dR_dataset(SEXP xy, SEXP dI, SEXP W) {
+  const int64_t n = nrows(xy);
+  iak3d_ds* ds = NULL;
+  const int q = isNull(W) ? 0 : ncols(W);
+  int st = iak3d_dataset_create(ctx_get(), n, REAL(xy), REAL(dI), isNull(W) ? NULL : REAL(W), q, &ds);
+  if (st != IAK3D_OK) error("iak3d_dataset_create: %s", iak3d_last_error(g_ctx));
+  SEXP p = PROTECT(R_MakeExternalPtr(ds, R_NilValue, R_NilValue));
+  R_RegisterCFinalizerEx(p, ds_finalizer, TRUE);
+  UNPROTECT(1);
+  return p;
+}
+
+SEXP iak3dR_set_W(SEXP dsp, SEXP W) {
+  int st = iak3d_dataset_set_W((iak3d_ds*)R_ExternalPtrAddr(dsp), REAL(W), ncols(W));
+  if (st != IAK3D_OK) error("iak3d_dataset_set_W: %s", iak3d_last_error(g_ctx));
+  return R_NilValue;
+}
+
+/* nllIAK3D(..., forCompLik = TRUE) terms for `count` parameter vectors on one dataset (count = 1: a function value;
+ * count = npar + 1: a forward-difference gradient).  pmat: 23 x count.  Returns list(status, lndetA, WiAW (q*q x count)). */
+SEXP iak3dR_nll_terms(SEXP dsp, SEXP pmat) {
+  iak3d_ds* ds = (iak3d_ds*)R_ExternalPtrAddr(dsp);
+  const int count = ncols(pmat);
+  int32_t q = 0; int64_t n = 0;
+  iak3d_dataset_info(ds, &n, NULL, NULL, &q);
+  iak3d_pars* P = (iak3d_pars*)R_alloc(count, sizeof(iak3d_pars));
+  iak3d_ds** dss = (iak3d_ds**)R_alloc(count, sizeof(iak3d_ds*));
+  for (int i = 0; i < count; i++) {
+    SEXP col = PROTECT(allocVector(REALSXP, 23));
+    memcpy(REAL(col), REAL(pmat) + 23 * (size_t)i, 23 * sizeof(double));
+    pars_from(col, &P[i]);
+    UNPROTECT(1);
+    dss[i] = ds;
+  }
+  SEXP status = PROTECT(allocVector(INTSXP, count));
+  SEXP lndet = PROTECT(allocVector(REALSXP, count));
+  SEXP G = PROTECT(allocMatrix(REALSXP, q * q, count));
+  int st = iak3d_nll_terms_batch(g_ctx, count, dss, P, REAL(lndet), REAL(G), (int32_t*)INTEGER(status));
+  if (st < 0) error("iak3d_nll_terms_batch: %s", iak3d_last_error(g_ctx));
+  SEXP out = PROTECT(allocVector(VECSXP, 3));
+  SET_VECTOR_ELT(out, 0, status); SET_VECTOR_ELT(out, 1, lndet); SET_VECTOR_ELT(out, 2, G);
+  UNPROTECT(4);
+  return out;
+}
+
+/* one evaluation that also returns iAW = A^-1 W (n x q) for rtnAll / forCompLik callers */
+SEXP iak3dR_nll_terms_iAW(SEXP dsp, SEXP pv) {
+  iak3d_ds* ds = (iak3d_ds*)R_ExternalPtrAddr(dsp);
+  iak3d_pars P; pars_from(pv, &P);
+  int32_t q = 0; int64_t n = 0;
+  iak3d_dataset_info(ds, &n, NULL, NULL, &q);
+  SEXP lndet = PROTECT(allocVector(REALSXP, 1));
+  SEXP G = PROTECT(allocMatrix(REALSXP, q, q));
+  SEXP iAW = PROTECT(allocMatrix(REALSXP, (int)n, q));
+  int st = iak3d_nll_terms(ds, &P, REAL(lndet), REAL(G), REAL(iAW));
+  if (st < 0) error("iak3d_nll_terms: %s", iak3d_last_error(g_ctx));
+  SEXP out = PROTECT(allocVector(VECSXP, 4));
+  SET_VECTOR_ELT(out, 0, ScalarInteger(st)); SET_VECTOR_ELT(out, 1, lndet); SET_VECTOR_ELT(out, 2, G); SET_VECTOR_ELT(out, 3, iAW);
+  UNPROTECT(4);
+  return out;
+}
+
+/* setCIAK3D: list(status, C (n x n), sigma2Vec) */
+SEXP iak3dR_cov_build(SEXP dsp, SEXP pv, SEXP wantC) {
+  iak3d_ds* ds = (iak3d_ds*)R_ExternalPtrAddr(dsp);
+  iak3d_pars P; pars_from(pv, &P);
+  int64_t n = 0; iak3d_dataset_info(ds, &n, NULL, NULL, NULL);
+  const int want = asLogical(wantC);
+  SEXP C = PROTECT(want ? allocMatrix(REALSXP, (int)n, (int)n) : allocVector(REALSXP, 0));
+  SEXP s2 = PROTECT(allocVector(REALSXP, (R_xlen_t)n));
+  int st = iak3d_cov_build(ds, &P, want ? REAL(C) : NULL, REAL(s2));
+  if (st < 0) error("iak3d_cov_build: %s", iak3d_last_error(g_ctx));
+  SEXP out = PROTECT(allocVector(VECSXP, 3));
+  SET_VECTOR_ELT(out, 0, ScalarInteger(st)); SET_VECTOR_ELT(out, 1, C); SET_VECTOR_ELT(out, 2, s2);
+  UNPROTECT(3);
+  return out;
+}
+
+/* setCIAK3D2: cross-covariance between rows (xy1, dI1) and the dataset */
+SEXP iak3dR_cov_cross(SEXP dsp, SEXP pv, SEXP xy1, SEXP dI1) {
+  iak3d_ds* ds = (iak3d_ds*)R_ExternalPtrAddr(dsp);
+  iak3d_pars P; pars_from(pv, &P);
+  int64_t n = 0; iak3d_dataset_info(ds, &n, NULL, NULL, NULL);
+  const int n1 = nrows(xy1);
+  SEXP out = PROTECT(allocMatrix(REALSXP, n1, (int)n));
+  int st = iak3d_cov_cross(ds, &P, n1, REAL(xy1), REAL(dI1), REAL(out));
+  if (st < 0) error("iak3d_cov_cross: %s", iak3d_last_error(g_ctx));
+  UNPROTECT(1);
+  return st == IAK3D_OK ? out : ScalarReal(NA_REAL);
+}
+
+/* lndetANDinvCb(C, b): list(lndetC, invCb) with NA, NA on failure (optim_functions.R:292-294) */
+SEXP iak3dR_lndet_invCb(SEXP C, SEXP b) {
+  const int n = nrows(C);
+  const int nrhs = isNull(b) ? 0 : ncols(b);
+  SEXP lnd = PROTECT(allocVector(REALSXP, 1));
+  SEXP inv = PROTECT(nrhs ? allocMatrix(REALSXP, n, nrhs) : allocMatrix(REALSXP, n, n));
+  int st = iak3d_lndet_invCb(ctx_get(), n, REAL(C), nrhs, nrhs ? REAL(b) : NULL, REAL(lnd), REAL(inv));
+  if (st < 0) error("iak3d_lndet_invCb: %s", iak3d_last_error(g_ctx));
+  SEXP out = PROTECT(allocVector(VECSXP, 2));
+  if (st == IAK3D_OK) { SET_VECTOR_ELT(out, 0, lnd); SET_VECTOR_ELT(out, 1, inv); }
+  else { SET_VECTOR_ELT(out, 0, ScalarReal(NA_REAL)); SET_VECTOR_ELT(out, 1, ScalarReal(NA_REAL)); }
+  UNPROTECT(3);
+  return out;
+}
+
+/* kept fit (the big matrices of lmmFit) and kriging */
+SEXP iak3dR_fit(SEXP dsp, SEXP pv, SEXP betahat, SEXP vbetahat) {
+  iak3d_pars P; pars_from(pv, &P);
+  iak3d_fit* f = NULL;
+  int st = iak3d_fit_create((iak3d_ds*)R_ExternalPtrAddr(dsp), &P, REAL(betahat), REAL(vbetahat), &f);
+  if (st != IAK3D_OK) error("iak3d_fit_create: status %d %s", st, iak3d_last_error(g_ctx));
+  SEXP p = PROTECT(R_MakeExternalPtr(f, R_NilValue, dsp));      /* keeps the dataset alive */
+  R_RegisterCFinalizerEx(p, fit_finalizer, TRUE);
+  UNPROTECT(1);
+  return p;
+}
+SEXP iak3dR_fit_small(SEXP fp, SEXP n_, SEXP p_) {              /* iCX, iCz_muhat */
+  const int n = asInteger(n_), p = asInteger(p_);
+  SEXP iCX = PROTECT(allocMatrix(REALSXP, n, p));
+  SEXP iCz = PROTECT(allocMatrix(REALSXP, n, 1));
+  int st = iak3d_fit_get((iak3d_fit*)R_ExternalPtrAddr(fp), REAL(iCX), REAL(iCz), NULL, NULL);
+  if (st != IAK3D_OK) error("iak3d_fit_get: %s", iak3d_last_error(g_ctx));
+  SEXP out = PROTECT(allocVector(VECSXP, 2));
+  SET_VECTOR_ELT(out, 0, iCX); SET_VECTOR_ELT(out, 1, iCz);
+  UNPROTECT(3);
+  return out;
+}
+SEXP iak3dR_predict(SEXP fp, SEXP xyMap, SEXP dIMap, SEXP XMap) {
+  const int m = nrows(xyMap);
+  SEXP z = PROTECT(allocVector(REALSXP, m));
+  SEXP v = PROTECT(allocVector(REALSXP, m));
+  int st = iak3d_predict((iak3d_fit*)R_ExternalPtrAddr(fp), m, REAL(xyMap), REAL(dIMap), REAL(XMap), REAL(z), REAL(v));
+  if (st != IAK3D_OK) error("iak3d_predict: %s", iak3d_last_error(g_ctx));
+  SEXP out = PROTECT(allocVector(VECSXP, 2));
+  SET_VECTOR_ELT(out, 0, z); SET_VECTOR_ELT(out, 1, v);
+  UNPROTECT(3);
+  return out;
+}
+
+static const R_CallMethodDef call_methods[] = {
+  {"iak3dR_dataset", (DL_FUNC)&iak3dR_dataset, 3},       {"iak3dR_set_W", (DL_FUNC)&iak3dR_set_W, 2},
+  {"iak3dR_nll_terms", (DL_FUNC)&iak3dR_nll_terms, 2},   {"iak3dR_nll_terms_iAW", (DL_FUNC)&iak3dR_nll_terms_iAW, 2},
+  {"iak3dR_cov_build", (DL_FUNC)&iak3dR_cov_build, 3},   {"iak3dR_cov_cross", (DL_FUNC)&iak3dR_cov_cross, 4},
+  {"iak3dR_lndet_invCb", (DL_FUNC)&iak3dR_lndet_invCb, 2}, {"iak3dR_fit", (DL_FUNC)&iak3dR_fit, 4},
+  {"iak3dR_fit_small", (DL_FUNC)&iak3dR_fit_small, 3},   {"iak3dR_predict", (DL_FUNC)&iak3dR_predict, 4},
+  {NULL, NULL, 0}};
+
+void R_init_iak3dR(DllInfo* dll) {
+  R_registerRoutines(dll, NULL, call_methods, NULL, NULL);
+  R_useDynamicSymbols(dll, FALSE);
+}
