@@ -1,0 +1,146 @@
+"""The two workloads of the path that shard across GPUs (BASELINE.json configs[3], configs[4]); driven by
+`bench.py --workload cl|krige`.
+
+  cl     synthetic composite likelihood (compositeLikIAK3D.R:6-307, compLikOptn = 2: adjacent block pairs, ML): the
+         block pairs are dealt to the ranks (LPT on n^3), each rank evaluates its pairs in ONE batch launch, and the
+         sums are combined by one all-reduce of (p+1)^2 + 3 doubles (NCCL through torch.distributed).  Strong scaling.
+  krige  block kriging of a cells x 6 GlobalSoilMap-interval grid (predictIAK3D.R:5-287, egEdgeroi.R:396) against a
+         kept fit of the 5k-interval dataset; every rank holds the factor and predicts a contiguous tile of the grid;
+         no collective in the data path.  Strong scaling.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from bench import PARBNDS, ClockSampler, measured_peak
+
+
+def _cl(args, rank, local_rank, world, comm):
+    import iak3d_b200 as iak
+    from iak3d_b200 import api, synth
+    n = args.n if args.n != 5000 else 200000
+    nblocks = max(4, int(round(n / 2000.0)))
+    ctx = iak.Context(local_rank)
+    ds = synth.make_dataset(n, synth.SEEDS["CL200"])
+    blk = synth.make_blocks(ds["xData"], ds["prof"], nblocks, synth.SEEDS["CL200"])
+    blk["compLikOptn"] = 2
+    P0, modelx, types, cmeOpt = synth.default_pars("edgeroi")
+    cl = iak.setupIAK3D_CL(ds["xData"], ds["dIData"], ds["zData"], ds["XData"], blk, ctx=ctx, rank=rank, world=world)
+    sizes = [u["n"] for u in cl["units"]]
+    p = ds["XData"].shape[1]
+
+    def step(k):
+        P = dict(P0); P["ax"] = P0["ax"] * (1.0 + 1e-3 * np.sin(0.7 * k)); P["cme"] = P0["cme"] * (1.0 + 1e-3 * np.cos(0.3 * k))
+        return iak.nllIAK3D_CL(None, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True, PARBNDS, False, cl, parsBTfmd=P, comm=comm)
+
+    peak = ctx.fp64_peak(1)
+    for w in range(args.warmup):
+        v = step(-1 - w)
+    assert np.isfinite(v) and v < 1e90
+    clk = ClockSampler(local_rank)
+    comm.barrier(); ctx.sync()
+    l0 = ctx.launch_count(); clk.start()
+    stage = np.zeros(4)
+    ctx.timer_start()
+    for k in range(args.steps):
+        step(k)
+        if cl["units"]:
+            stage += np.array(ctx.last_stage_ms()[0])
+    ms = ctx.timer_stop()
+    comm.barrier(); ctx.sync()
+    clocks = clk.stop()
+    launches = ctx.launch_count() - l0
+    ms = float(comm.allreduce_max(np.array([ms]))[0])
+    flops_rank = sum(float(s) ** 3 / 3.0 for s in sizes)
+    flops = float(comm.allreduce_sum(np.array([flops_rank]))[0])
+    stage /= args.steps
+    tf_rank = flops_rank / max(stage[2], 1e-9) / 1e9
+    out = dict(metric="composite-likelihood evals/sec at n obs", value=args.steps / (ms * 1e-3), unit="evals/s", n_gpus=world,
+               steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong",
+               vs_baseline=None, dtype="f64", data="synthetic",
+               config=dict(workload=f"synthetic {n}-interval composite likelihood, {nblocks} Voronoi blocks, compLikOptn=2 "
+                                    "(adjacent pairs, ML) (BASELINE configs[3])", n=n, p=p, blocks=nblocks,
+                           block_pairs=int(cl["n_units_total"]), pairs_this_rank=len(sizes), mean_pair_size=float(np.mean(sizes)) if sizes else 0,
+                           parallelism=f"block pairs over {world} GPU(s), one all-reduce of {(p + 1) ** 2 + 3} doubles per evaluation",
+                           l2="per-rank factor buffers exceed the 126 MB L2; no flush needed"),
+               units_per_s=int(cl["n_units_total"]) * args.steps / (ms * 1e-3),
+               stage_ms=dict(tables=stage[0], cov_build=stage[1], factorise=stage[2], finish=stage[3]),
+               roofline=dict(kernel="tile_task_kernel (rank 0's share)", bound="tensor", achieved=tf_rank, peak=peak, unit="TFLOP/s",
+                             frac=tf_rank / peak, traffic=None, flops_per_launch=flops_rank,
+                             peak_source="FP64 DMMA microbenchmark in this run"),
+               whole_job_tflops=flops * args.steps / (ms * 1e-3) / 1e12,
+               e2e=dict(value=args.steps / (ms * 1e-3), unit="evals/s", h2d_bytes_per_step=int(len(sizes) * 192),
+                        d2h_bytes_per_step=int(len(sizes) * (2 + (p + 1) ** 2) * 8),
+                        note="the timed call IS the reference-facing call (nllIAK3D_CL with host parameters, host result); "
+                             "block data are resident like setupMats"),
+               gpu_launches=int(launches), clocks=clocks)
+    return out, ctx
+
+
+def _krige(args, rank, local_rank, world, comm):
+    import iak3d_b200 as iak
+    from iak3d_b200 import parallel, synth
+    n = args.n
+    cells = getattr(args, "cells", 1000000)
+    ctx = iak.Context(local_rank)
+    ds = synth.make_dataset(n, synth.SEEDS["S5"])
+    P, modelx, types, cmeOpt = synth.default_pars("edgeroi")
+    sm = iak.setupIAK3D(ds["xData"], ds["dIData"], ctx=ctx)
+    fit = iak.nllIAK3D(None, ds["zData"], ds["XData"], modelx=modelx, nud=0.5, sdfdType_cd1=types[0], sdfdType_cxd0=types[1],
+                       sdfdType_cxd1=types[2], cmeOpt=cmeOpt, setupMats=sm, parBnds=PARBNDS, rtnAll=True, attachBigMats=True, parsBTfmd=P)
+    side = int(np.ceil(np.sqrt(cells)))
+    lo, hi = parallel.grid_tile(cells, rank, world)
+    xMap = synth.make_grid(side)[lo:hi]
+    m = hi - lo
+    nd = len(synth.GSM_INTERVALS)
+    # one staged job per rank: its tile of cells x all six depth intervals (rows ordered interval by interval)
+    xy = np.tile(xMap, (nd, 1))
+    dI = np.repeat(synth.GSM_INTERVALS, m, axis=0)
+    X = np.vstack([synth.grid_design(xMap, synth.GSM_INTERVALS[i], synth.SEEDS["P1M"]) for i in range(nd)])
+    k = fit["fit"]
+    peak = ctx.fp64_peak(1)
+    k.stage(xy, dI, X)
+    for w in range(max(1, min(args.warmup, 2))):
+        k.enqueue(); z, v = k.fetch()
+    assert np.all(np.isfinite(z)) and np.all(np.isfinite(v))
+    clk = ClockSampler(local_rank)
+    comm.barrier(); ctx.sync()
+    l0 = ctx.launch_count(); clk.start()
+    ctx.timer_start()
+    for s in range(args.steps):
+        k.enqueue()
+    ms = ctx.timer_stop()
+    z, v = k.fetch()
+    comm.barrier(); ctx.sync()
+    clocks = clk.stop()
+    launches = ctx.launch_count() - l0
+    ms = float(comm.allreduce_max(np.array([ms]))[0])
+    # end to end through the plugin call: host arrays in, z and v out
+    comm.barrier(); t0 = time.perf_counter()
+    for s in range(args.steps):
+        z2, v2 = k.predict(xy, dI, X)
+    e2e_s = float(comm.allreduce_max(np.array([time.perf_counter() - t0]))[0])
+    preds = cells * nd * args.steps
+    tf = (m * nd * float(n) ** 2) * args.steps / (ms * 1e-3) / 1e12
+    out = dict(metric="kriging preds/sec", value=preds / (ms * 1e-3), unit="preds/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+               ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
+               config=dict(workload=f"block kriging of a {cells}-cell grid x {nd} GlobalSoilMap intervals with variances against the "
+                                    f"{n}-interval fit (BASELINE configs[4])", n=n, p=ds["XData"].shape[1], cells=cells, intervals=nd,
+                           cells_this_rank=m, parallelism=f"grid tiles over {world} GPU(s), no data-path collective",
+                           l2="each 16384-support panel (0.7 GB) exceeds the 126 MB L2; no flush needed"),
+               roofline=dict(kernel="tile_task_kernel, mode 1 (rank 0's tile)", bound="tensor", achieved=tf, peak=peak, unit="TFLOP/s",
+                             frac=tf / peak, traffic=None, flops_per_launch=16384.0 * n * n,
+                             note="n^2 flops per prediction (X = Ckh L^-T); the reference's Ckh %*% iC costs 2 n^2",
+                             peak_source="FP64 DMMA microbenchmark in this run"),
+               e2e=dict(value=preds / e2e_s, unit="preds/s", h2d_bytes_per_step=int(xy.nbytes + dI.nbytes + X.nbytes),
+                        d2h_bytes_per_step=int(2 * m * nd * 8)),
+               gpu_launches=int(launches), clocks=clocks)
+    return out, ctx
+
+
+def run(args, rank, local_rank, world, comm):
+    if args.workload == "cl":
+        return _cl(args, rank, local_rank, world, comm)
+    return _krige(args, rank, local_rank, world, comm)

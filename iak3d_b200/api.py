@@ -421,7 +421,13 @@ def nllIAK3D_CL(pars, zData, XData, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sd
             S += w * _symm_upper(G[i].T); lnd_sum += w * lnd[i]
             if u["kind"] == "pair":
                 n_SUM += u["n"]
-    buf = np.concatenate([S.reshape(-1), [lnd_sum, n_SUM, failed]])
+    return cl_reduce_and_tail(S, lnd_sum, n_SUM, failed, n, p, optn, nB, useReml, comm, rtnTerms)
+
+
+def cl_reduce_and_tail(S, lnd_sum, n_SUM, failed, n, p, optn, nB, useReml, comm=None, rtnTerms=False):
+    """The exchange step of the composite likelihood -- Reduce('+') over the workers, compositeLikIAK3D.R:63-64 -- as
+    one all-reduce of (p+1)^2 + 3 doubles, then the closed-form tail (:181-265) on every rank."""
+    buf = np.concatenate([np.asarray(S, float).reshape(-1), [lnd_sum, n_SUM, failed]])
     if comm is not None:
         buf = comm.allreduce_sum(buf)
     S = buf[:(p + 1) ** 2].reshape(p + 1, p + 1); lnd_sum, n_SUM, failed = buf[-3], buf[-2], buf[-1]
@@ -444,22 +450,18 @@ def nllIAK3D_CL(pars, zData, XData, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sd
     return t["nll"]
 
 
-def setupIAK3D_CL(xData, dIData, zData, XData, compLikMats, ctx=None, rank=0, world=1):
-    """iaCovMatern.R:551-575 + the unit weights of compositeLikIAK3D.R:42-179, as a list of device datasets.
+def cl_plan_units(compLikMats, world=1):
+    """Units of one composite-likelihood evaluation and their owner ranks.
 
     Units: every adjacent pair (optn < 4) and every single block that some non-adjacent pair needs (optn 1, 3: a
-    block's terms are added once per non-adjacent pair it belongs to, :126-155) or all single blocks (optn 4).
-    With world > 1 the units are dealt to ranks by longest-processing-time on n^3."""
-    ctx = ctx or default_context()
-    xData = np.asarray(xData, float); dIData = np.asarray(dIData, float).reshape(-1, 2)
-    zData = np.asarray(zData, float).reshape(-1); XData = np.asarray(XData, float).reshape(zData.size, -1)
+    block's terms are added once per non-adjacent pair it belongs to, compositeLikIAK3D.R:157-164) or all single
+    blocks (optn 4).  Owners: longest-processing-time on n^3 (the factorisation cost)."""
     optn = compLikMats["compLikOptn"]
     blocks = compLikMats["listBlocks"]
     units = []
     if optn < 4:
         for (k, l) in np.asarray(compLikMats["subsetPairsAdj"]).reshape(-1, 2):
-            rows = np.concatenate([blocks[k], blocks[l]])
-            units.append(dict(kind="pair", weight=1.0, rows=rows))
+            units.append(dict(kind="pair", weight=1.0, rows=np.concatenate([blocks[k], blocks[l]])))
     if optn in (1, 3):
         cnt = np.zeros(len(blocks))
         for (k, l) in np.asarray(compLikMats.get("subsetPairsNonadj", np.zeros((0, 2), int))).reshape(-1, 2):
@@ -470,16 +472,26 @@ def setupIAK3D_CL(xData, dIData, zData, XData, compLikMats, ctx=None, rank=0, wo
     elif optn == 4:
         for b in range(len(blocks)):
             units.append(dict(kind="block", weight=1.0, rows=blocks[b]))
-    # longest-processing-time assignment
     order = np.argsort([-len(u["rows"]) for u in units], kind="stable")
-    load = np.zeros(world); mine = []
+    load = np.zeros(world)
     for i in order:
         r = int(np.argmin(load)); load[r] += float(len(units[i]["rows"])) ** 3
-        if r == rank:
-            mine.append(i)
+        units[i]["owner"] = r
+    return units
+
+
+def setupIAK3D_CL(xData, dIData, zData, XData, compLikMats, ctx=None, rank=0, world=1):
+    """iaCovMatern.R:551-575 + the unit weights of compositeLikIAK3D.R:42-179, as a list of device datasets owned by
+    this rank (see :func:`cl_plan_units`)."""
+    ctx = ctx or default_context()
+    xData = np.asarray(xData, float); dIData = np.asarray(dIData, float).reshape(-1, 2)
+    zData = np.asarray(zData, float).reshape(-1); XData = np.asarray(XData, float).reshape(zData.size, -1)
+    units = cl_plan_units(compLikMats, world)
     out = []
-    for i in sorted(mine):
-        u = units[i]; rows = u["rows"]
+    for u in units:
+        if u["owner"] != rank:
+            continue
+        rows = u["rows"]
         W = np.column_stack([XData[rows], zData[rows]])
         u["setup"] = SetupMats(xData[rows], dIData[rows], W=W, ctx=ctx)
         u["n"] = len(rows)
