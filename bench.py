@@ -290,7 +290,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="s5", choices=["s5", "cl", "krige"])
-    ap.add_argument("--n", type=int, default=5000)
+    ap.add_argument("--nobs", dest="n", type=int, default=5000, help="observations (torchrun's parser trips over a bare --n)")
     ap.add_argument("--cells", type=int, default=1000000, help="grid cells of --workload krige")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

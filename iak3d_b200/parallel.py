@@ -24,10 +24,12 @@ def init(backend=None):
         if not dist.is_initialized():
             if backend is None:
                 backend = "nccl" if torch.cuda.is_available() else "gloo"
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             if backend == "nccl":
                 torch.cuda.set_device(local_rank)
-            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-            dist.init_process_group(backend=backend, rank=rank, world_size=world)
+                dist.init_process_group(backend=backend, rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+            else:
+                dist.init_process_group(backend=backend, rank=rank, world_size=world)
     return rank, local_rank, world
 
 
