@@ -502,6 +502,25 @@ def setupIAK3D_CL(xData, dIData, zData, XData, compLikMats, ctx=None, rank=0, wo
     return cl
 
 
+def gradHessIAK3D(setupMats, parsBTfmd, modelx, sdfdTypes, lnvPars):
+    """nrUpdatesIAK3D.R:118-216 for C = sum_i exp(lnvPars[i]) dA_i with dA_i the unit-variance terms of setCIAK3D in the
+    order cx0, cx1, cd1, cxd0, cxd1[, cme] (the `dA` list the reference is handed, :130-138).  The dataset must carry
+    W = [X z].  -> dict(nll, grad, hess, fim, betahat, vbetahat); nll is nan where chol fails."""
+    sm = setupMats
+    th = f64(np.asarray(lnvPars, float).reshape(-1))
+    m = th.size
+    p = sm.q - 1
+    P = make_pars(parsBTfmd, modelx, *sdfdTypes, 1 if m == 6 else 0, quirk_cd1_unscaled=False)
+    nll = C.c_double()
+    grad = np.empty(m); hess = np.empty((m, m), order="F"); fim = np.empty((m, m), order="F")
+    beta = np.empty(p); vb = np.empty((p, p), order="F")
+    st = sm.ctx.check(sm.ctx.lib.iak3d_gradhess(sm.h, C.byref(P), m, dptr(th), C.byref(nll), dptr(grad), dptr(hess), dptr(fim),
+                                                dptr(beta), dptr(vb)), allow=(NOT_SPD, BAD_PARS))
+    if st != OK:
+        return dict(nll=float("nan"))
+    return dict(nll=nll.value, grad=grad, hess=hess, fim=fim, betahat=beta.reshape(-1, 1), vbetahat=vb)
+
+
 # ---------------------------------------------------------------------------------------------
 # kept fit + kriging
 # ---------------------------------------------------------------------------------------------

@@ -270,7 +270,9 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
     const int nCB = pb->nCB, mode = pb->mode, epoch = pb->epoch;
     int32_t* status = pb->status;
     const int64_t R0 = (int64_t)r * TM;
-    const int nchunks = j * (TN / KC);
+    const int nchunks = (mode == 2) ? pb->kchunks : j * (TN / KC);
+    const double* __restrict__ Asrc = (mode == 2) ? pb->A : P;
+    const int64_t nRUA = (mode == 2) ? pb->nRUA : nRUP;
     const uint32_t it0 = it;
     long long* prof = pb->prof ? pb->prof + (int64_t)t * 8 : nullptr;
     long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0, tp4 = 0, kwait = 0;
@@ -291,7 +293,7 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
         uint32_t itp = it0;
         for (int c = 0; c < nchunks; c++, itp++) {
           const int k = c >> 1;
-          if ((c & 1) == 0) {
+          if ((c & 1) == 0 && mode != 2) {
             wait_flag(pb->doneP + (int64_t)r * nCB + k, epoch, status, abort_flag);
             if (mode == 0) wait_flag(pb->doneL + (int64_t)(j >> 1) * nCB + k, epoch, status, abort_flag);
             asm volatile("fence.proxy.async;" ::: "memory");
@@ -302,7 +304,7 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
           mbar_expect_tx(&full_bar[s], STAGE_D * 8);
           double* As = smem + s * STAGE_D;
           // unit column c (32 columns of L): A = row units 2r, 2r+1 of the owner's panel; B = row unit j of the factor
-          bulk_g2s(As, P + ((int64_t)c * nRUP + 2 * r) * UNIT, A_STAGE * 8, &full_bar[s]);
+          bulk_g2s(As, Asrc + ((int64_t)c * nRUA + 2 * r) * UNIT, A_STAGE * 8, &full_bar[s]);
           bulk_g2s(As + A_STAGE, L + ((int64_t)c * nRUL + j) * UNIT, B_STAGE * 8, &full_bar[s]);
         }
       }
@@ -338,6 +340,28 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
       // ---- E1: tile = A - acc (in shared memory) ----
       if (prof && tid == 0) tp1 = (long long)gtime();
       mbar_wait(&at_bar, at_phase, status, abort_flag);
+      if (mode == 2) {
+        // ---- plain product: tile = use_cin * tile + alpha * acc, stored straight back; no dependencies to publish ----
+        const double alpha = pb->alpha; const bool cin = pb->use_cin != 0;
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+          for (int ni = 0; ni < 4; ni++) {
+            const int row = wm * 32 + mi * 8 + rq, col = wn * 32 + ni * 8 + kq * 2;
+            const int i0 = AT_IDX(row, col), i1 = AT_IDX(row, col + 1);
+            At[i0] = (cin ? At[i0] : 0.0) + alpha * acc[mi][ni][0];
+            At[i1] = (cin ? At[i1] : 0.0) + alpha * acc[mi][ni][1];
+          }
+        consumer_bar();
+        for (int idx = tid; idx < 4 * (UNIT / 2); idx += NCW * 32) {
+          const int u = idx / (UNIT / 2), w2 = idx % (UNIT / 2);
+          reinterpret_cast<double2*>(((u >> 1) ? Pt1 : Pt0) + (u & 1) * UNIT)[w2] = reinterpret_cast<const double2*>(At + u * UNIT)[w2];
+        }
+        it = it0 + nchunks;
+        at_phase ^= 1;
+        __syncthreads();
+        continue;
+      }
 #pragma unroll
       for (int mi = 0; mi < 4; mi++)
 #pragma unroll

@@ -149,7 +149,12 @@ struct ProblemDesc {
   double* invd;                  // nCB x INVD_BLOCK inverse diagonal blocks
   int32_t* doneL; int32_t* doneP; int32_t* invdone;
   int32_t nCB, nRB;              // col-blocks of L / row-blocks of P
-  int32_t mode;                  // 0 = factorise (P == L), 1 = bordered rows against a finished factor
+  int32_t mode;                  // 0 = factorise (P == L), 1 = bordered rows against a finished factor,
+                                 // 2 = plain product  P(r,j) = use_cin * P(r,j) + alpha * sum_k A(r,k) L(j,k)'  (no flags)
+  const double* A; int64_t nRUA; // mode 2: left operand (blocked); modes 0/1 read their own panel P
+  int32_t kchunks;               // mode 2: K / 32
+  int32_t use_cin;               // mode 2: accumulate onto the existing tile
+  double alpha;                  // mode 2: scale of the product
   int32_t epoch;
   int32_t w0, q;                 // W rows start (global row index in L) and count
   double* G;                     // mode 0: q*q Gram; mode 1: rowsP x (q+1) accumulators

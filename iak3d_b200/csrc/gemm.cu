@@ -1,17 +1,369 @@
 // gemm.cu -- dense FP64 products behind the explicit inverse (chol2inv / solve(C): optim_functions.R:297,
-// fitIAK3D.R:931) and the Newton-Raphson terms (gradHessIAK3D, nrUpdatesIAK3D.R:118-216).
+// fitIAK3D.R:931) and the Newton-Raphson terms on log-variances (gradHessIAK3D, nrUpdatesIAK3D.R:118-216).
+//
+// Every O(n^3) product runs through the tile engine of chol.cu (DMMA K-loop, TMA-staged blocked operands):
+//   U  = L^-T                 mode 1 with an identity panel
+//   iC = U U'                 mode 2 (plain product  Out = use_cin * Out + alpha * A B')
+//   T  = iC - (iCX V) iCX'    mode 2, K = 32 (p padded)
+//   M_i = T dC_i              mode 2 (dC_i symmetric, so T dC_i = T dC_i')
+// The O(n^2) pieces (traces, tr(M_i M_j), matrix-vector products) are plain kernels with fixed-order reductions.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 
-int iak_inverse_from_factor(iak3d_ctx* ctx, Slot* s, double* d_iC) {
-  (void)s; (void)d_iC;
-  ctx->err = "explicit inverse: not implemented yet";
-  return IAK3D_ERR_ARG;
+// from api.cu
+struct TableCache;
+int iak_make_plan(iak3d_ctx* ctx, const iak3d_pars* p, bool square, EvalPlan* pl);
+int iak_alloc_slot(iak3d_ctx* ctx, int64_t n, int32_t q, int64_t nxU, int64_t ndIU, Slot** out);
+void iak_free_slot(Slot* s);
+int iak_square_tables(iak3d_ctx* ctx, const iak3d_ds* ds, const EvalPlan& pl, Slot* s, CovArgs* a, TableCache* cache = nullptr);
+int iak_factor_slot(iak3d_ctx* ctx, Slot* s, int32_t* status_out, double* lndet_out, double* G_out);
+int iak_backsolve_to_host(iak3d_ctx* ctx, Slot* s, double* out_host, double* d_out_opt);
+
+namespace {
+
+__global__ void identity_blocked_kernel(double* __restrict__ P, int64_t nRU, int64_t rows, int64_t cols) {
+  // one thread per (unit column c, row i): zero, except the diagonal
+  const int64_t c = blockIdx.y;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (int64_t)gridDim.x * blockDim.x)
+    P[uidx(i, c, nRU)] = (i == c && c < cols) ? 1.0 : 0.0;
+}
+__global__ void unblock_kernel(const double* __restrict__ B, int64_t nRU, int64_t n, double* __restrict__ out) {
+  const int64_t c = blockIdx.y;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[c * n + i] = B[uidx(i, c, nRU)];
+}
+// column-major n x k (k <= 32) -> blocked rows x 32 panel, zero padded
+__global__ void block_panel_kernel(const double* __restrict__ src, int64_t n, int k, double* __restrict__ dst, int64_t nRU, int64_t rows) {
+  const int c = blockIdx.y;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (int64_t)gridDim.x * blockDim.x)
+    dst[uidx(i, c, nRU)] = (i < n && c < k) ? src[(int64_t)c * n + i] : 0.0;
+}
+// y = M x over the leading n x n part (thread per row, columns in order: deterministic)
+__global__ void matvec_rows_kernel(const double* __restrict__ M, int64_t nRU, int64_t n, const double* __restrict__ x, double* __restrict__ y) {
+  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  double s = 0.0;
+  for (int64_t b = 0; b < n; b++) s = fma(M[uidx(a, b, nRU)], __ldg(x + b), s);
+  y[a] = s;
+}
+// y = M' x (warp per column, lanes stride the rows, fixed shuffle tree)
+__global__ void matvec_cols_kernel(const double* __restrict__ M, int64_t nRU, int64_t n, const double* __restrict__ x, double* __restrict__ y) {
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= n) return;
+  double s = 0.0;
+  for (int64_t a = lane; a < n; a += 32) s = fma(M[uidx(a, b, nRU)], __ldg(x + a), s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) y[b] = s;
+}
+// partial[blockIdx.x] = sum over a in this block's 32 rows, all b < n, of Mi(a,b) * Mj(b,a)   (Mj == nullptr: trace of Mi)
+__global__ void __launch_bounds__(256) trace_pair_kernel(const double* __restrict__ Mi, const double* __restrict__ Mj, int64_t nRU,
+                                                         int64_t n, double* __restrict__ partial) {
+  __shared__ double sj[32][33];
+  __shared__ double red[256];
+  const int64_t a0 = (int64_t)blockIdx.x * 32;
+  const int tf = threadIdx.x & 31, ts = threadIdx.x >> 5;      // fast index 0..31, slow index 0..7
+  double acc = 0.0;
+  if (Mj == nullptr) {
+    if (threadIdx.x < 32) { const int64_t a = a0 + threadIdx.x; if (a < n) acc = Mi[uidx(a, a, nRU)]; }
+  } else {
+    for (int64_t b0 = 0; b0 < n; b0 += 32) {
+      // Mj block rows b0.. (fast), cols a0.. (slow) -> shared, then read transposed
+      for (int s = ts; s < 32; s += 8) {
+        const int64_t b = b0 + tf, a = a0 + s;
+        sj[s][tf] = (b < n && a < n) ? Mj[uidx(b, a, nRU)] : 0.0;
+      }
+      __syncthreads();
+      for (int s = ts; s < 32; s += 8) {
+        const int64_t a = a0 + tf, b = b0 + s;
+        if (a < n && b < n) acc = fma(Mi[uidx(a, b, nRU)], sj[tf][s], acc);
+      }
+      __syncthreads();
+    }
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 16)); }
+  template <class T> T* as() { return (T*)p; }
+};
+
+// all (r, j) tiles of a rows x cols output, column-major task order (mode 1 needs it; mode 2 does not care)
+int run_tiles(iak3d_ctx* ctx, const ProblemDesc& pd, int nRB, int nCB) {
+  std::vector<int4> tasks;
+  tasks.reserve((size_t)nRB * nCB);
+  for (int j = 0; j < nCB; j++)
+    for (int r = 0; r < nRB; r++) tasks.push_back(make_int4(0, r, j, 0));
+  DevBuf d_tasks, d_prob, d_ticket;
+  CUDA_TRY(ctx, d_tasks.alloc(tasks.size() * sizeof(int4)));
+  CUDA_TRY(ctx, d_prob.alloc(sizeof(ProblemDesc)));
+  CUDA_TRY(ctx, d_ticket.alloc(2 * sizeof(int32_t)));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_tasks.p, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_prob.p, &pd, sizeof(pd), cudaMemcpyHostToDevice, ctx->stream));
+  const int st = launch_tile_tasks(ctx, d_prob.as<ProblemDesc>(), d_tasks.as<int4>(), (int32_t)tasks.size(), d_ticket.as<int32_t>());
+  if (st != 0) return st;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// Out(rowsOut x colsOut, blocked) = use_cin * Out + alpha * A(rowsOut x K) B(colsOut x K)'   (all blocked, K multiple of 32)
+int gemm_nt(iak3d_ctx* ctx, const double* A, int64_t rowsA, const double* B, int64_t rowsB, double* Out, int64_t rowsOut,
+            int64_t colsOut, int64_t K, double alpha, int use_cin, int32_t* d_status) {
+  ProblemDesc pd;
+  memset(&pd, 0, sizeof(pd));
+  pd.L = const_cast<double*>(B); pd.nRUL = rowsB / UR;
+  pd.P = Out; pd.nRUP = rowsOut / UR;
+  pd.A = A; pd.nRUA = rowsA / UR;
+  pd.nCB = (int32_t)(colsOut / TN); pd.nRB = (int32_t)(rowsOut / TM);
+  pd.mode = 2; pd.kchunks = (int32_t)(K / UC); pd.use_cin = use_cin; pd.alpha = alpha;
+  pd.status = d_status;
+  return run_tiles(ctx, pd, pd.nRB, pd.nCB);
+}
+
+}  // namespace
+
+// iC (blocked, rowsU x Npad with rowsU = round_up(Npad, 128)) from a finished factor.  Caller frees *out with cudaFree.
+int iak_inverse_blocked(iak3d_ctx* ctx, Slot* s, double** out, int64_t* rowsU_out) {
+  const int64_t Npad = s->Npad, rowsU = round_up(Npad, TM), nRU = rowsU / UR;
+  const size_t bytes = (size_t)ubuf_doubles(rowsU, Npad) * sizeof(double);
+  DevBuf U, G, flags, status;
+  double* iC = nullptr;
+  CUDA_TRY(ctx, U.alloc(bytes));
+  CUDA_TRY(ctx, G.alloc((size_t)rowsU * sizeof(double)));
+  const size_t nfl = (size_t)(rowsU / TM) * s->nCB;
+  CUDA_TRY(ctx, flags.alloc(nfl * sizeof(int32_t)));
+  CUDA_TRY(ctx, status.alloc(2 * sizeof(int32_t)));
+  CUDA_TRY(ctx, cudaMemsetAsync(flags.p, 0, nfl * sizeof(int32_t), ctx->stream));
+  CUDA_TRY(ctx, cudaMemsetAsync(status.p, 0, 2 * sizeof(int32_t), ctx->stream));
+  {
+    dim3 grid((unsigned)((rowsU + 255) / 256), (unsigned)Npad);
+    if (Npad > 65535) { ctx->err = "inverse: more than 65535 columns"; return IAK3D_ERR_ARG; }
+    identity_blocked_kernel<<<grid, 256, 0, ctx->stream>>>(U.as<double>(), nRU, rowsU, Npad);
+    ctx->launches++;
+  }
+  // U = I L^-T  (mode 1 against the finished factor)
+  ProblemDesc pd;
+  memset(&pd, 0, sizeof(pd));
+  pd.L = s->d_L; pd.nRUL = s->ld / UR; pd.P = U.as<double>(); pd.nRUP = nRU; pd.invd = s->d_invd;
+  pd.doneP = flags.as<int32_t>(); pd.nCB = s->nCB; pd.nRB = (int32_t)(rowsU / TM); pd.mode = 1; pd.epoch = 1;
+  pd.w0 = (int32_t)s->Npad; pd.q = 0; pd.G = G.as<double>(); pd.ldG = rowsU; pd.status = status.as<int32_t>();
+  int rc = run_tiles(ctx, pd, pd.nRB, pd.nCB);
+  if (rc != 0) return rc;
+  // iC = U U'
+  if (cudaMalloc(&iC, bytes) != cudaSuccess) { ctx->err = "inverse: allocation failed"; cudaGetLastError(); return IAK3D_ERR_CUDA; }
+  rc = gemm_nt(ctx, U.as<double>(), rowsU, U.as<double>(), rowsU, iC, rowsU, Npad, Npad, 1.0, 0, status.as<int32_t>());
+  if (rc != 0) { cudaFree(iC); return rc; }
+  int32_t hs[2] = {0, 0};
+  CUDA_TRY(ctx, cudaMemcpy(hs, status.p, sizeof(hs), cudaMemcpyDeviceToHost));
+  if (hs[1] != 0) { cudaFree(iC); ctx->err = "inverse: dependency wait timed out (internal error)"; return IAK3D_ERR_TIMEOUT; }
+  *out = iC; *rowsU_out = rowsU;
+  return 0;
+}
+
+int iak_inverse_from_factor(iak3d_ctx* ctx, Slot* s, double* d_iC /* n x n column-major */) {
+  double* iCb = nullptr; int64_t rowsU = 0;
+  int rc = iak_inverse_blocked(ctx, s, &iCb, &rowsU);
+  if (rc != 0) return rc;
+  dim3 grid((unsigned)((s->n + 255) / 256), (unsigned)s->n);
+  unblock_kernel<<<grid, 256, 0, ctx->stream>>>(iCb, rowsU / UR, s->n, d_iC);
+  ctx->launches++;
+  const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(iCb);
+  CUDA_TRY(ctx, e);
+  return 0;
+}
+
+// ---- small dense helpers on the host (p x p, p <= 63) -------------------------------------------------
+static bool host_chol(int p, const double* A /* col-major */, double* L) {
+  for (int j = 0; j < p; j++) {
+    for (int i = j; i < p; i++) {
+      double s = A[(size_t)j * p + i];
+      for (int k = 0; k < j; k++) s -= L[(size_t)k * p + i] * L[(size_t)k * p + j];
+      if (i == j) { if (!(s > 0.0) || !isfinite(s)) return false; L[(size_t)j * p + j] = sqrt(s); }
+      else L[(size_t)j * p + i] = s / L[(size_t)j * p + j];
+    }
+    for (int i = 0; i < j; i++) L[(size_t)j * p + i] = 0.0;
+  }
+  return true;
+}
+static void host_chol_solve(int p, const double* L, const double* b, double* x) {   // (L L') x = b
+  std::vector<double> y((size_t)p);
+  for (int i = 0; i < p; i++) { double s = b[i]; for (int k = 0; k < i; k++) s -= L[(size_t)k * p + i] * y[k]; y[i] = s / L[(size_t)i * p + i]; }
+  for (int i = p - 1; i >= 0; i--) { double s = y[i]; for (int k = i + 1; k < p; k++) s -= L[(size_t)i * p + k] * x[k]; x[i] = s / L[(size_t)i * p + i]; }
 }
 
 extern "C" int iak3d_gradhess(iak3d_ds* ds, const iak3d_pars* pars, int32_t ncomp, const double* lnvPars, double* nll, double* grad,
                               double* hess, double* fim, double* betahat, double* vbetahat) {
-  (void)pars; (void)ncomp; (void)lnvPars; (void)nll; (void)grad; (void)hess; (void)fim; (void)betahat; (void)vbetahat;
-  if (!ds) return IAK3D_ERR_ARG;
-  ds->ctx->err = "gradhess: not implemented yet";
-  return IAK3D_ERR_ARG;
+  if (!ds || !pars || !lnvPars || !nll || !grad || !hess || !fim) return IAK3D_ERR_ARG;
+  iak3d_ctx* ctx = ds->ctx;
+  if (ncomp != 5 && ncomp != 6) { ctx->err = "gradhess: ncomp must be 5 or 6 (cx0, cx1, cd1, cxd0, cxd1[, cme])"; return IAK3D_ERR_ARG; }
+  if (ds->q < 2) { ctx->err = "gradhess: the dataset needs W = [X z]"; return IAK3D_ERR_ARG; }
+  cudaSetDevice(ctx->device);
+  const int64_t n = ds->n;
+  const int q = ds->q, p = q - 1, m = ncomp;
+  // C = sum_i exp(theta_i) dA_i  (nrUpdatesIAK3D.R:130-138): setCIAK3D with these variances, no quirk
+  iak3d_pars P = *pars;
+  double var[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < m; i++) var[i] = exp(lnvPars[i]);
+  P.cx0 = var[0]; P.cx1 = var[1]; P.cd1 = var[2]; P.cxd0 = var[3]; P.cxd1 = var[4]; P.cme = var[5];
+  P.quirk_cd1_unscaled = 0;
+  EvalPlan pl;
+  int rc = iak_make_plan(ctx, &P, true, &pl);
+  if (rc != 0) return rc;
+  if (pl.status != 0) return pl.status;
+  const double nanv = nan("");
+  Slot* s = nullptr;
+  rc = iak_alloc_slot(ctx, n, q, ds->nxU, ds->ndIU, &s);
+  if (rc != 0) return rc;
+  double* iCb = nullptr;
+  std::vector<double*> Mi((size_t)m, nullptr);
+  do {
+    CovArgs a;
+    rc = iak_square_tables(ctx, ds, pl, s, &a);
+    if (rc != 0) break;
+    rc = launch_cov_factor_layout(ctx, a, ds->d_W, q, s->n, s->Npad, s->ld, s->nCB, s->d_L);
+    if (rc != 0) break;
+    int32_t status = 0; double lndetC = 0.0;
+    std::vector<double> G((size_t)q * q);
+    rc = iak_factor_slot(ctx, s, &status, &lndetC, G.data());
+    if (rc != 0) break;
+    if (status != 0) { *nll = nanv; rc = status; break; }
+    std::vector<double> iCW((size_t)n * q);
+    rc = iak_backsolve_to_host(ctx, s, iCW.data(), nullptr);
+    if (rc != 0) break;
+    // ---- p x p algebra on the host (nrUpdatesIAK3D.R:160-190) ----
+    std::vector<double> XiCX((size_t)p * p), XiCz((size_t)p), Lp((size_t)p * p), beta((size_t)p), iXiCX((size_t)p * p);
+    for (int c = 0; c < p; c++) for (int r = 0; r < p; r++) XiCX[(size_t)c * p + r] = 0.5 * (G[(size_t)c * q + r] + G[(size_t)r * q + c]);
+    for (int r = 0; r < p; r++) XiCz[r] = 0.5 * (G[(size_t)p * q + r] + G[(size_t)r * q + p]);
+    const double ziCz = G[(size_t)p * q + p];
+    if (!host_chol(p, XiCX.data(), Lp.data())) { *nll = nanv; rc = IAK3D_NOT_SPD; break; }
+    host_chol_solve(p, Lp.data(), XiCz.data(), beta.data());
+    for (int c = 0; c < p; c++) { std::vector<double> e((size_t)p, 0.0); e[c] = 1.0; host_chol_solve(p, Lp.data(), e.data(), &iXiCX[(size_t)c * p]); }
+    double lndetXiCX = 0.0;
+    for (int i = 0; i < p; i++) lndetXiCX += 2.0 * log(Lp[(size_t)i * p + i]);
+    double bXz = 0.0, bXXb = 0.0;
+    for (int r = 0; r < p; r++) { bXz += beta[r] * XiCz[r]; double t = 0.0; for (int c = 0; c < p; c++) t += XiCX[(size_t)c * p + r] * beta[c]; bXXb += beta[r] * t; }
+    const double zTz = ziCz - 2.0 * bXz + bXXb;
+    std::vector<double> Tz((size_t)n), A1((size_t)n * p);
+    for (int64_t i = 0; i < n; i++) {
+      double t = iCW[(size_t)p * n + i];
+      for (int c = 0; c < p; c++) t -= iCW[(size_t)c * n + i] * beta[c];
+      Tz[(size_t)i] = t;
+      for (int c = 0; c < p; c++) { double v = 0.0; for (int k = 0; k < p; k++) v += iCW[(size_t)k * n + i] * iXiCX[(size_t)c * p + k]; A1[(size_t)c * n + i] = v; }
+    }
+    // ---- T = iC - iCX (X'iCX)^-1 iCX'  (:183) ----
+    int64_t rowsU = 0;
+    rc = iak_inverse_blocked(ctx, s, &iCb, &rowsU);
+    if (rc != 0) break;
+    const int64_t nRU = rowsU / UR, Npad = s->Npad;
+    const size_t mbytes = (size_t)ubuf_doubles(rowsU, Npad) * sizeof(double);
+    DevBuf dA1, dB1, pA, pB, dTz, dz, du, dv, dr, dpart, dstatus, dC;
+    const size_t pbytes = (size_t)ubuf_doubles(rowsU, TN) * sizeof(double);     // rowsU x 64 panel (K = 32 uses the first unit column)
+    cudaError_t e = dA1.alloc((size_t)n * p * 8);
+    if (e == cudaSuccess) e = dB1.alloc((size_t)n * p * 8);
+    if (e == cudaSuccess) e = pA.alloc(pbytes);
+    if (e == cudaSuccess) e = pB.alloc(pbytes);
+    if (e == cudaSuccess) e = dTz.alloc((size_t)n * 8);
+    if (e == cudaSuccess) e = dz.alloc((size_t)n * 8);
+    if (e == cudaSuccess) e = du.alloc((size_t)n * 8);
+    if (e == cudaSuccess) e = dv.alloc((size_t)n * 8);
+    if (e == cudaSuccess) e = dr.alloc((size_t)n * 8);
+    const int nblk = (int)((n + 31) / 32);
+    if (e == cudaSuccess) e = dpart.alloc((size_t)nblk * 8);
+    if (e == cudaSuccess) e = dstatus.alloc(2 * sizeof(int32_t));
+    if (e == cudaSuccess) e = dC.alloc(mbytes);
+    if (e != cudaSuccess) { ctx->err = std::string("gradhess: allocation failed: ") + cudaGetErrorString(e); cudaGetLastError(); rc = IAK3D_ERR_CUDA; break; }
+    cudaMemsetAsync(dstatus.p, 0, 2 * sizeof(int32_t), ctx->stream);
+    cudaMemcpyAsync(dA1.p, A1.data(), (size_t)n * p * 8, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(dB1.p, iCW.data(), (size_t)n * p * 8, cudaMemcpyHostToDevice, ctx->stream);      // iCX = first p columns
+    cudaMemcpyAsync(dTz.p, Tz.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(dz.p, ds->h_W + (size_t)p * n, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
+    {
+      dim3 grid((unsigned)((rowsU + 255) / 256), TN);
+      block_panel_kernel<<<grid, 256, 0, ctx->stream>>>(dA1.as<double>(), n, p, pA.as<double>(), nRU, rowsU);
+      block_panel_kernel<<<grid, 256, 0, ctx->stream>>>(dB1.as<double>(), n, p, pB.as<double>(), nRU, rowsU);
+      ctx->launches += 2;
+    }
+    if (p > 32) {   // K = 64: both unit columns of the panels
+      rc = gemm_nt(ctx, pA.as<double>(), rowsU, pB.as<double>(), rowsU, iCb, rowsU, Npad, 64, -1.0, 1, dstatus.as<int32_t>());
+    } else {
+      rc = gemm_nt(ctx, pA.as<double>(), rowsU, pB.as<double>(), rowsU, iCb, rowsU, Npad, 32, -1.0, 1, dstatus.as<int32_t>());
+    }
+    if (rc != 0) break;
+    double* T = iCb;
+    // ---- per component: dC_i, u_i = dC_i Tz, M_i = T dC_i, tr M_i, v_i = M_i Tz, r_i = M_i' z ----
+    std::vector<double> trM((size_t)m, 0.0), zTdCTz((size_t)m, 0.0);
+    std::vector<std::vector<double>> vv((size_t)m, std::vector<double>((size_t)n)), rr((size_t)m, std::vector<double>((size_t)n));
+    std::vector<double> part((size_t)nblk), hu((size_t)n);
+    const double cv[6][6] = {{1, 0, 0, 0, 0, 0}, {0, 1, 0, 0, 0, 0}, {0, 0, 1, 0, 0, 0}, {0, 0, 0, 1, 0, 0}, {0, 0, 0, 0, 1, 0}, {0, 0, 0, 0, 0, 1}};
+    const unsigned rb = (unsigned)((n + 127) / 128), wb = (unsigned)((n * 32 + 255) / 256);
+    for (int i = 0; i < m && rc == 0; i++) {
+      CovArgs ai = a;
+      ai.cx0 = cv[i][0] * pl.cx0; ai.cx1 = cv[i][1] * pl.cx1; ai.kd1 = cv[i][2] * pl.cd1; ai.cxd0 = cv[i][3] * pl.cxd0;
+      ai.cxd1 = cv[i][4] * pl.cxd1; ai.cme = cv[i][5] * pl.cme;
+      rc = launch_cov_rect(ctx, ai, dC.as<double>(), rowsU, rowsU, Npad, 1, /*blocked=*/1);
+      if (rc != 0) break;
+      matvec_rows_kernel<<<rb, 128, 0, ctx->stream>>>(dC.as<double>(), nRU, n, dTz.as<double>(), du.as<double>());
+      ctx->launches++;
+      cudaMemcpyAsync(hu.data(), du.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+      if (cudaMalloc(&Mi[i], mbytes) != cudaSuccess) { ctx->err = "gradhess: allocation failed (M_i)"; cudaGetLastError(); rc = IAK3D_ERR_CUDA; break; }
+      rc = gemm_nt(ctx, T, rowsU, dC.as<double>(), rowsU, Mi[i], rowsU, Npad, Npad, 1.0, 0, dstatus.as<int32_t>());
+      if (rc != 0) break;
+      double t = 0.0;
+      for (int64_t k = 0; k < n; k++) t += Tz[(size_t)k] * hu[(size_t)k];
+      zTdCTz[i] = t;
+      trace_pair_kernel<<<nblk, 256, 0, ctx->stream>>>(Mi[i], nullptr, nRU, n, dpart.as<double>());
+      matvec_rows_kernel<<<rb, 128, 0, ctx->stream>>>(Mi[i], nRU, n, dTz.as<double>(), dv.as<double>());
+      matvec_cols_kernel<<<wb, 256, 0, ctx->stream>>>(Mi[i], nRU, n, dz.as<double>(), dr.as<double>());
+      ctx->launches += 3;
+      cudaMemcpyAsync(part.data(), dpart.p, (size_t)nblk * 8, cudaMemcpyDeviceToHost, ctx->stream);
+      cudaMemcpyAsync(vv[i].data(), dv.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+      cudaMemcpyAsync(rr[i].data(), dr.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+      if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "gradhess: kernel failure"; rc = IAK3D_ERR_CUDA; break; }
+      t = 0.0;
+      for (int k = 0; k < nblk; k++) t += part[(size_t)k];
+      trM[i] = t;
+    }
+    if (rc != 0) break;
+    // ---- gradient, Hessian, Fisher information (:197-210), REML nll (:213) ----
+    for (int i = 0; i < m; i++) grad[i] = 0.5 * (trM[i] - zTdCTz[i]);
+    for (int i = 0; i < m && rc == 0; i++)
+      for (int j = i; j < m; j++) {
+        trace_pair_kernel<<<nblk, 256, 0, ctx->stream>>>(Mi[i], Mi[j], nRU, n, dpart.as<double>());
+        ctx->launches++;
+        // the context stream is non-blocking: a plain cudaMemcpy would not wait for the kernel
+        cudaMemcpyAsync(part.data(), dpart.p, (size_t)nblk * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "gradhess: kernel failure"; rc = IAK3D_ERR_CUDA; break; }
+        double tr = 0.0;
+        for (int k = 0; k < nblk; k++) tr += part[(size_t)k];
+        double qij = 0.0;                                            // z' T dC_i T dC_j T z = (M_i' z) . (M_j Tz)
+        for (int64_t k = 0; k < n; k++) qij += rr[i][(size_t)k] * vv[j][(size_t)k];
+        if (i == j) hess[(size_t)i * m + j] = 0.5 * (trM[i] - tr - zTdCTz[i] + 2.0 * qij);
+        else hess[(size_t)i * m + j] = hess[(size_t)j * m + i] = 0.5 * (-tr + 2.0 * qij);
+        fim[(size_t)i * m + j] = fim[(size_t)j * m + i] = 0.5 * tr;
+      }
+    if (rc != 0) break;
+    int32_t hs[2] = {0, 0};
+    cudaMemcpy(hs, dstatus.p, sizeof(hs), cudaMemcpyDeviceToHost);
+    if (hs[1] != 0) { ctx->err = "gradhess: dependency wait timed out (internal error)"; rc = IAK3D_ERR_TIMEOUT; break; }
+    *nll = 0.5 * ((double)(n - p) * log(2.0 * 3.14159265358979323846) + lndetC + lndetXiCX + zTz);
+    if (betahat) memcpy(betahat, beta.data(), (size_t)p * 8);
+    if (vbetahat) memcpy(vbetahat, iXiCX.data(), (size_t)p * p * 8);
+  } while (0);
+  cudaStreamSynchronize(ctx->stream);
+  for (double* mptr : Mi) if (mptr) cudaFree(mptr);
+  if (iCb) cudaFree(iCb);
+  iak_free_slot(s);
+  return rc;
 }
