@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libiak3d.so")
 
 OK, NOT_SPD, BAD_PARS = 0, 1, 2
 ERR_CUDA, ERR_ARG, ERR_TIMEOUT = -1, -2, -3
+MAX_SPL = 12          # IAK3D_MAX_SPL
 MODELX = {"nugget": 0, "spherical": 1, "matern": 2, "wendland": 3}
 
 
@@ -26,6 +27,7 @@ class Pars(C.Structure):
         ("ax", C.c_double), ("nux", C.c_double), ("ad", C.c_double), ("nud", C.c_double),
         ("cx0", C.c_double), ("cx1", C.c_double), ("cd1", C.c_double), ("cxd0", C.c_double), ("cxd1", C.c_double),
         ("cme", C.c_double), ("sdfdPars", (C.c_double * 2) * 3), ("quirk_scale", C.c_double),
+        ("sdfdSpl", (C.c_double * MAX_SPL) * 3),
     ]
 
 
@@ -46,6 +48,9 @@ _PROTOS = {
     "iak3d_dataset_set_W": (C.c_int, [_vp, _dp, _i32]),
     "iak3d_dataset_info": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i32)]),
     "iak3d_dataset_ids": (C.c_int, [_vp, _ip, _ip]),
+    "iak3d_dataset_set_sdfd_spline": (C.c_int, [_vp, _i32, _i32, _dp]),
+    "iak3d_cov_cross_spl": (C.c_int, [_vp, C.POINTER(Pars), _i64, _dp, _dp, C.POINTER(_dp), _dp]),
+    "iak3d_predict_stage_spl": (C.c_int, [_vp, _i64, _dp, _dp, _dp, C.POINTER(_dp)]),
     "iak3d_iacov": (C.c_int, [_vp, _i64, _dp, _i64, _dp, C.c_double, C.c_double, _i32, _dp, _dp, _dp]),
     "iak3d_spatial_cov": (C.c_int, [_vp, _i64, _dp, _i32, C.c_double, C.c_double, C.c_double, _dp]),
     "iak3d_cov_build": (C.c_int, [_vp, C.POINTER(Pars), _dp, _dp]),
@@ -124,7 +129,20 @@ def make_pars(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cme
             if v.size != 2:
                 raise ValueError(f"{k} must hold (tau1, tau2) when its sdfdType is -1")
             P.sdfdPars[i][0], P.sdfdPars[i][1] = float(v[0]), float(v[1])
+        elif types[i] > 0:
+            if types[i] > MAX_SPL or v.size != types[i]:
+                raise ValueError(f"{k} must hold sdfdType = {types[i]} (<= {MAX_SPL}) spline coefficients")
+            for e in range(types[i]):
+                P.sdfdSpl[i][e] = float(v[e])
     return P
+
+
+def spl_ptrs(mats):
+    """[3] array of double* (or NULL) for the *_spl entry points; `mats` are n x ncol F-ordered arrays or None."""
+    arr = (_dp * 3)()
+    for i, m in enumerate(mats):
+        arr[i] = dptr(m) if m is not None else None
+    return arr
 
 
 class Context:

@@ -19,7 +19,7 @@ import math
 import numpy as np
 
 from . import _lib
-from ._lib import BAD_PARS, NOT_SPD, OK, Context, Iak3dError, Pars, default_context, dptr, f64, iptr, make_pars
+from ._lib import BAD_PARS, NOT_SPD, OK, Context, Iak3dError, Pars, default_context, dptr, f64, iptr, make_pars, spl_ptrs
 
 BADNLL = 9e99   # fitIAK3D.R:685
 
@@ -97,12 +97,74 @@ def readParsIAK3D(pars, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1,
 
 
 # ---------------------------------------------------------------------------------------------
+# spline basis of the sd functions (host, once per dataset: splineBasisFns.R:158-325)
+# ---------------------------------------------------------------------------------------------
+def makeXnsClampedUG0(x, bdryKnots, intKnots, paramVs=0):
+    """Natural cubic spline basis with the gradient clamped to 0 beyond the upper boundary knot.  `x` is a vector of
+    points or an n x 2 matrix of intervals (then the columns are interval averages).  paramVs = 1 is the
+    parameterisation (a, g1..gK-1, w) used for the sd functions (iaCovMatern.R:520-539)."""
+    x = np.asarray(x, float)
+    ia = x.ndim == 2 and x.shape[1] == 2
+    if not ia:
+        x = x.reshape(-1)
+    n = x.shape[0]
+    xL, xU = float(bdryKnots[0]), float(bdryKnots[1])
+    knots = np.asarray(intKnots if intKnots is not None else [], float).reshape(-1)
+    K = knots.size
+    X = np.ones((n, 1 + K))
+    if K == 0:
+        return X
+    if paramVs not in (0, 1):
+        raise ValueError("Unknonwn parameterisation option for spline function!")
+    pos = lambda v: np.where(v < 0, 0.0, v)
+    if ia:
+        w = x[:, 1] - x[:, 0]
+        E3 = lambda k: 0.25 * (pos(x[:, 1] - k) ** 4 - pos(x[:, 0] - k) ** 4) / w        # E[(x - k)_+^3] over the interval
+        lin = 0.5 * (x[:, 0] + x[:, 1])
+    else:
+        E3 = lambda k: pos(x - k) ** 3
+        lin = x
+    EL, EU = E3(xL), E3(xU)
+    h = lambda k: E3(k) - ((xU - k) / (xU - xL)) * EL + ((xL - k) / (xU - xL)) * EU + 3 * (xU - k) * (k - xL) * lin
+    if paramVs == 0:
+        for ik in range(K):
+            X[:, 1 + ik] = h(knots[ik])
+        return X
+    kK = knots[K - 1]
+    hK = h(kK)
+    den = (xU - kK) * (kK - xL) * (kK + xL + xU)
+    X[:, 0] = 1 - hK / den
+    for ik in range(K - 1):
+        k = knots[ik]
+        q = ((xU - k) * (k - xL) * (k + xL + xU)) / den
+        X[:, 1 + ik] = h(k) - q * hK
+    X[:, K] = hK / den
+    return X
+
+
+_SDFD_COMPS = ("cd1", "cxd0", "cxd1")
+
+
+def _sdfd_spline_bases(dI, sdfdTypes, sdfdKnots):
+    """XsdfdSplineU_{cd1,cxd0,cxd1} of iaCovMatern.R:520-539 on the intervals `dI` (None where the type is not > 0)."""
+    out = []
+    for c, t in zip(_SDFD_COMPS, sdfdTypes):
+        if t > 0:
+            if sdfdKnots is None:
+                raise ValueError("sdfdKnots are required when an sdfdType is > 0")
+            out.append(f64(makeXnsClampedUG0(dI, sdfdKnots["bdryKnots"], sdfdKnots["intKnots_" + c], paramVs=1)))
+        else:
+            out.append(None)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 # setupMats
 # ---------------------------------------------------------------------------------------------
 class SetupMats:
     """`setupMats` of the reference as a device-resident dataset handle (iak3d_ds)."""
 
-    def __init__(self, xData, dIData, W=None, ctx=None):
+    def __init__(self, xData, dIData, W=None, ctx=None, sdfdType_cd1=0, sdfdType_cxd0=0, sdfdType_cxd1=0, sdfdKnots=None):
         self.ctx = ctx or default_context()
         self.xData = f64(np.asarray(xData, float).reshape(len(xData), -1))
         if self.xData.shape[1] != 2:
@@ -124,6 +186,17 @@ class SetupMats:
         self.ctx.check(self.ctx.lib.iak3d_dataset_info(self.h, C.byref(n_), C.byref(nx), C.byref(nd), C.byref(q_)))
         self.nxU, self.ndIU, self.q = nx.value, nd.value, q_.value
         self.maxd = max(float(self.dIData.max()), 2.0)     # iaCovMatern.R:435
+        self.sdfdKnots = sdfdKnots
+        self.sdfdTypes = (sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1)
+        if max(self.sdfdTypes) > 0:                        # iaCovMatern.R:520-539
+            _, did = self.ids()
+            first = np.full(self.ndIU, -1, np.int64)
+            first[did[::-1]] = np.arange(self.n)[::-1]     # first occurrence of each unique interval
+            self.dIU = self.dIData[first]
+            self.XsdfdSplineU = _sdfd_spline_bases(self.dIU, self.sdfdTypes, sdfdKnots)
+            for c, B in enumerate(self.XsdfdSplineU):
+                if B is not None:
+                    self.ctx.check(self.ctx.lib.iak3d_dataset_set_sdfd_spline(self.h, c, B.shape[1], dptr(B)))
 
     def set_W(self, W):
         W = f64(W)
@@ -157,21 +230,33 @@ class SetupMats:
             pass
 
 
-def setupIAK3D(xData, dIData, ctx=None, **_ignored):
-    return SetupMats(xData, dIData, ctx=ctx)
+def setupIAK3D(xData, dIData, ctx=None, sdfdType_cd1=0, sdfdType_cxd0=0, sdfdType_cxd1=0, sdfdKnots=None, **_ignored):
+    return SetupMats(xData, dIData, ctx=ctx, sdfdType_cd1=sdfdType_cd1, sdfdType_cxd0=sdfdType_cxd0, sdfdType_cxd1=sdfdType_cxd1,
+                     sdfdKnots=sdfdKnots)
 
 
 class SetupMats2:
     """setupIAK3D2: set 1 (rows of the result) stays on the host, set 2 is a resident dataset."""
 
-    def __init__(self, xData, dIData, xData2, dIData2, ctx=None, setup2=None):
+    def __init__(self, xData, dIData, xData2, dIData2, ctx=None, setup2=None, sdfdType_cd1=0, sdfdType_cxd0=0, sdfdType_cxd1=0,
+                 sdfdKnots=None):
         self.x1 = f64(np.asarray(xData, float).reshape(len(xData), -1))
         self.d1 = f64(np.asarray(dIData, float).reshape(-1, 2))
-        self.set2 = setup2 if setup2 is not None else SetupMats(xData2, dIData2, ctx=ctx)
+        types = (sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1)
+        self.set2 = setup2 if setup2 is not None else SetupMats(xData2, dIData2, ctx=ctx, sdfdType_cd1=sdfdType_cd1,
+                                                                sdfdType_cxd0=sdfdType_cxd0, sdfdType_cxd1=sdfdType_cxd1,
+                                                                sdfdKnots=sdfdKnots)
+        if setup2 is not None and sdfdKnots is None:
+            sdfdKnots, types = setup2.sdfdKnots, setup2.sdfdTypes
+        # spline basis on the rows of set 1 (XsdfdSplineU_* expanded by Kd, iaCovMatern.R:627-645)
+        self.Xspl1 = _sdfd_spline_bases(self.d1, types, sdfdKnots) if max(types) > 0 else [None, None, None]
 
 
-def setupIAK3D2(xData, dIData, xData2, dIData2, ctx=None, **_ignored):
-    return SetupMats2(xData, dIData, xData2, dIData2, ctx=ctx)
+def setupIAK3D2(xData, dIData, xData2, dIData2, ctx=None, sdfdType_cd1=0, sdfdType_cxd0=0, sdfdType_cxd1=0, sdfdKnots=None,
+                setup2=None, **_ignored):
+    """`setup2`: an existing SetupMats of set 2 (then xData2 / dIData2 are not re-uploaded)."""
+    return SetupMats2(xData, dIData, xData2, dIData2, ctx=ctx, setup2=setup2, sdfdType_cd1=sdfdType_cd1, sdfdType_cxd0=sdfdType_cxd0,
+                      sdfdType_cxd1=sdfdType_cxd1, sdfdKnots=sdfdKnots)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -195,7 +280,11 @@ def setCIAK3D2(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cm
     n1, n2 = sm.x1.shape[0], sm.set2.n
     out = np.empty((n1, n2), order="F")
     ctx = sm.set2.ctx
-    st = ctx.check(ctx.lib.iak3d_cov_cross(sm.set2.h, C.byref(P), n1, dptr(sm.x1), dptr(sm.d1), dptr(out)), allow=(BAD_PARS,))
+    if max(sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1) > 0:     # setCApproxIAK3D2, fitIAK3D.R:1121-1124
+        st = ctx.check(ctx.lib.iak3d_cov_cross_spl(sm.set2.h, C.byref(P), n1, dptr(sm.x1), dptr(sm.d1), spl_ptrs(sm.Xspl1),
+                                                   dptr(out)), allow=(BAD_PARS,))
+    else:
+        st = ctx.check(ctx.lib.iak3d_cov_cross(sm.set2.h, C.byref(P), n1, dptr(sm.x1), dptr(sm.d1), dptr(out)), allow=(BAD_PARS,))
     return None if st == BAD_PARS else out
 
 
@@ -557,17 +646,18 @@ class KeptFit:
         return Cm, iC
 
     def predict(self, xMap, dIMap, XMap):
-        xMap = f64(np.asarray(xMap, float).reshape(-1, 2)); dIMap = f64(np.asarray(dIMap, float).reshape(-1, 2))
-        XMap = f64(np.asarray(XMap, float).reshape(xMap.shape[0], -1))
-        m = xMap.shape[0]
-        z = np.empty(m); v = np.empty(m)
-        self.ctx.check(self.ctx.lib.iak3d_predict(self.h, m, dptr(xMap), dptr(dIMap), dptr(XMap), dptr(z), dptr(v)))
-        return z, v
+        self.stage(xMap, dIMap, XMap)
+        self.enqueue()
+        return self.fetch()
 
     def stage(self, xMap, dIMap, XMap):
         xMap = f64(np.asarray(xMap, float).reshape(-1, 2)); dIMap = f64(np.asarray(dIMap, float).reshape(-1, 2))
         XMap = f64(np.asarray(XMap, float).reshape(xMap.shape[0], -1))
-        self.ctx.check(self.ctx.lib.iak3d_predict_stage(self.h, xMap.shape[0], dptr(xMap), dptr(dIMap), dptr(XMap)))
+        if max(self.sm.sdfdTypes) > 0:       # spline sd functions: basis on the map supports (setCApproxIAK3D2)
+            spl = _sdfd_spline_bases(dIMap, self.sm.sdfdTypes, self.sm.sdfdKnots)
+            self.ctx.check(self.ctx.lib.iak3d_predict_stage_spl(self.h, xMap.shape[0], dptr(xMap), dptr(dIMap), dptr(XMap), spl_ptrs(spl)))
+        else:
+            self.ctx.check(self.ctx.lib.iak3d_predict_stage(self.h, xMap.shape[0], dptr(xMap), dptr(dIMap), dptr(XMap)))
         self._m = xMap.shape[0]
 
     def enqueue(self):

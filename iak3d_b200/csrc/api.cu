@@ -67,8 +67,9 @@ int iak_make_plan(iak3d_ctx* ctx, const iak3d_pars* p, bool square, EvalPlan* pl
   *pl = EvalPlan();
   for (int c = 0; c < 3; c++) {
     const int t = p->sdfdType[c];
-    if (t > 0) { ctx->err = "spline sd functions (sdfdType > 0, setCApproxIAK3D) are not implemented"; return IAK3D_ERR_ARG; }
-    if (!(t == 0 || t == -1 || (t == -9 && c == 0))) { ctx->err = "sdfdType must be 0, -1 (or -9 for cd1)"; return IAK3D_ERR_ARG; }
+    if (t > IAK3D_MAX_SPL) { ctx->err = "sdfdType: more internal knots than IAK3D_MAX_SPL"; return IAK3D_ERR_ARG; }
+    if (t > 0) pl->approx = true;                                     // fitIAK3D.R:959-962 / 1121-1124
+    if (!(t >= -1 || (t == -9 && c == 0))) { ctx->err = "sdfdType must be 0, -1, k > 0 (or -9 for cd1)"; return IAK3D_ERR_ARG; }
   }
   if (p->modelx < IAK3D_MODELX_NUGGET || p->modelx > IAK3D_MODELX_WENDLAND) { ctx->err = "unknown modelx"; return IAK3D_ERR_ARG; }
   const bool nugget = (p->modelx == IAK3D_MODELX_NUGGET);
@@ -78,9 +79,12 @@ int iak_make_plan(iak3d_ctx* ctx, const iak3d_pars* p, bool square, EvalPlan* pl
   const double vs[6] = {pl->cx0, pl->cx1, pl->cd1, pl->cxd0, pl->cxd1, pl->cme};
   for (double v : vs) if (!isfinite(v)) { pl->status = IAK3D_BAD_PARS; return 0; }
   if (!isfinite(p->ad) || !(p->ad > 0.0)) { pl->status = IAK3D_BAD_PARS; return 0; }
-  for (int c = 0; c < 3; c++)
+  for (int c = 0; c < 3; c++) {
     if (p->sdfdType[c] == -1 && !(isfinite(p->sdfdPars[c][0]) && isfinite(p->sdfdPars[c][1]))) { pl->status = IAK3D_BAD_PARS; return 0; }
-  // depth tables: one shared stationary table (fitIAK3D.R:986-993) + one per non-stationary component
+    for (int k = 0; k < p->sdfdType[c]; k++) if (!isfinite(p->sdfdSpl[c][k])) { pl->status = IAK3D_BAD_PARS; return 0; }
+  }
+  // depth tables: one shared stationary table (fitIAK3D.R:986-993) + one per non-stationary component.  With the
+  // approximation every table starts from the stationary one and is scaled by its component's averaged sd (:1960).
   int stat = -1;
   for (int c = 0; c < 3; c++) {
     const int t = p->sdfdType[c];
@@ -92,19 +96,69 @@ int iak_make_plan(iak3d_ctx* ctx, const iak3d_pars* p, bool square, EvalPlan* pl
         if (iak_prm_init(&pl->prm[stat], p->ad, p->nud, 0, 0.0, 0.0) != 0) { pl->status = IAK3D_BAD_PARS; return 0; }
       }
       pl->tidx[c] = stat;
-    } else {
+    } else if (!pl->approx) {
       const int k = pl->ntab++;
       if (iak_prm_init(&pl->prm[k], p->ad, p->nud, -1, p->sdfdPars[c][0], p->sdfdPars[c][1]) != 0) { pl->status = IAK3D_BAD_PARS; return 0; }
+      pl->tidx[c] = k;
+    } else {
+      const int k = pl->ntab++;
+      if (iak_prm_init(&pl->prm[k], p->ad, p->nud, 0, 0.0, 0.0) != 0) { pl->status = IAK3D_BAD_PARS; return 0; }
+      pl->sd_type[k] = t; pl->sd_comp[k] = c;
+      if (t == -1) { pl->sd_coef[k][0] = p->sdfdPars[c][0]; pl->sd_coef[k][1] = p->sdfdPars[c][1]; }
+      else for (int e = 0; e < t; e++) pl->sd_coef[k][e] = p->sdfdSpl[c][e];
       pl->tidx[c] = k;
     }
   }
   pl->kd1 = pl->cd1;
-  if (square && p->sdfdType[0] == -1 && p->quirk_cd1_unscaled)                   // fitIAK3D.R:1052 (sic)
+  if (square && (p->sdfdType[0] == -1 || p->sdfdType[0] > 0) && p->quirk_cd1_unscaled)   // fitIAK3D.R:1052, 2026 (sic)
     pl->kd1 = (p->quirk_scale != 0.0) ? p->quirk_scale : 1.0;
   pl->has_phix = !nugget;
   if (!nugget) {
     const int st = hx_init(&pl->H, p->modelx, p->ax, p->nux);
     if (st != 0) { pl->status = IAK3D_BAD_PARS; return 0; }
+  }
+  return 0;
+}
+
+// iasdfd (fitIAK3D.R:1448-1468) of table k on a set of unique intervals (host: ndIU values).  XsplU: nd x ncol spline
+// basis of the table's component on that set (type > 0).  Returns IAK3D_BAD_PARS when min(avsd) < 0 (:1994, 2172).
+int iak_avsd_host(iak3d_ctx* ctx, const EvalPlan& pl, int k, const double* dIU, int64_t nd, const double* XsplU, int ncol,
+                  std::vector<double>& s) {
+  const int t = pl.sd_type[k];
+  s.assign((size_t)nd, 1.0);
+  if (t == -1) {
+    const double t1 = pl.sd_coef[k][0], t2 = pl.sd_coef[k][1];
+    for (int64_t i = 0; i < nd; i++) {
+      const double dU = dIU[i], dL = dIU[nd + i];
+      s[(size_t)i] = (1.0 - t1) - (t1 / t2) * (exp(-t2 * dL) - exp(-t2 * dU)) / (dL - dU);
+    }
+  } else if (t > 0) {
+    if (XsplU == nullptr || ncol != t + 1) {
+      ctx->err = "spline sd function: the basis of this component is missing or has the wrong number of columns "
+                 "(iak3d_dataset_set_sdfd_spline / Xspl1; ncol must be sdfdType + 1)";
+      return IAK3D_ERR_ARG;
+    }
+    for (int64_t i = 0; i < nd; i++) {
+      double v = XsplU[i];                                            // c(1, sdfdPars): first column times 1
+      for (int e = 0; e < t; e++) v += XsplU[(size_t)(e + 1) * nd + i] * pl.sd_coef[k][e];
+      s[(size_t)i] = v;
+    }
+  }
+  for (int64_t i = 0; i < nd; i++) if (!(s[(size_t)i] >= 0.0) || !isfinite(s[(size_t)i])) return IAK3D_BAD_PARS;
+  return 0;
+}
+
+// parsOK of setCApproxIAK3D (fitIAK3D.R:1993-1994) decided at planning time: a negative averaged sd -> C = NA
+int iak_plan_check_avsd(iak3d_ctx* ctx, const iak3d_ds* ds, EvalPlan* pl) {
+  if (!pl->approx || pl->status != 0) return 0;
+  std::vector<double> sv;
+  for (int k = 0; k < pl->ntab; k++) {
+    if (pl->sd_type[k] == 0) continue;
+    const int c = pl->sd_comp[k];
+    const int st = iak_avsd_host(ctx, *pl, k, ds->h_dIU.data(), ds->ndIU, ds->h_spl[c].empty() ? nullptr : ds->h_spl[c].data(),
+                                 ds->spl_ncol[c], sv);
+    if (st == IAK3D_BAD_PARS) { pl->status = IAK3D_BAD_PARS; return 0; }
+    if (st != 0) return st;
   }
   return 0;
 }
@@ -204,7 +258,7 @@ int iak_alloc_slot(iak3d_ctx* ctx, int64_t n, int32_t q, int64_t nxU, int64_t nd
   auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, std::max<size_t>(bytes, 16)); };
   A((void**)&s->d_L, (size_t)ubuf_doubles(s->ld, s->Npad) * sizeof(double));
   A((void**)&s->d_phix, (size_t)nxU * nxU * sizeof(double));
-  A((void**)&s->d_phid, (size_t)(3 * ndIU * ndIU + 3 * ndIU) * sizeof(double));
+  A((void**)&s->d_phid, (size_t)(NTAB_BUF * ndIU * ndIU + NTAB_BUF * ndIU + 3 * ndIU) * sizeof(double));
   A((void**)&s->d_invd, (size_t)s->nCB * INVD_BLOCK * sizeof(double));
   const size_t nflags = (size_t)s->nRB * s->nCB + s->nCB;
   A((void**)&s->d_flags, nflags * sizeof(int32_t));
@@ -316,6 +370,17 @@ extern "C" int iak3d_dataset_ids(iak3d_ds* ds, int32_t* xid, int32_t* did) {
   return IAK3D_OK;
 }
 
+extern "C" int iak3d_dataset_set_sdfd_spline(iak3d_ds* ds, int32_t comp, int32_t ncol, const double* XsplU) {
+  if (!ds) return IAK3D_ERR_ARG;
+  if (comp < 0 || comp > 2 || ncol < 0 || ncol > IAK3D_MAX_SPL + 1 || (ncol > 0 && !XsplU)) {
+    ds->ctx->err = "dataset_set_sdfd_spline: comp in 0..2, ncol in 0..IAK3D_MAX_SPL+1";
+    return IAK3D_ERR_ARG;
+  }
+  ds->spl_ncol[comp] = ncol;
+  ds->h_spl[comp].assign(XsplU, XsplU + (size_t)ncol * ds->ndIU);
+  return IAK3D_OK;
+}
+
 int iak_get_slot(iak3d_ds* ds, size_t k, Slot** out) {
   while (ds->slots.size() <= k) {
     Slot* s = nullptr;
@@ -347,18 +412,47 @@ struct TableCache {
 
 int iak_square_tables(iak3d_ctx* ctx, const iak3d_ds* ds, const EvalPlan& pl, Slot* s, CovArgs* a, TableCache* cache = nullptr) {
   const int64_t nd = ds->ndIU, nx = ds->nxU;
+  double* const avbase = s->d_phid + (size_t)NTAB_BUF * nd * nd;
   for (int k = 0; k < 3; k++) a->T[k] = nullptr;
-  for (int k = 0; k < pl.ntab; k++) {
+  auto plain_table = [&](int k, int buf, const double** out) -> int {   // iaCovMatern on the unique intervals
     const IaPrm& P = pl.prm[k];
     const double key[6] = {P.psi, P.tau0, P.tau1, P.tau2, P.g11[1], P.g11[2]};     // (ad, nud, sd function) determine the table
     const double* hit = cache ? cache->find(ds, 1, key) : nullptr;
-    if (hit != nullptr) { a->T[k] = hit; continue; }
-    double* T = s->d_phid + (size_t)k * nd * nd;
-    double* av = s->d_phid + (size_t)3 * nd * nd + (size_t)k * nd;
-    const int st = launch_iacov_table(ctx, P, ds->d_dIU, nd, ds->d_dIU, nd, T, av);
+    if (hit != nullptr) { *out = hit; return 0; }
+    double* T = s->d_phid + (size_t)buf * nd * nd;
+    const int st = launch_iacov_table(ctx, P, ds->d_dIU, nd, ds->d_dIU, nd, T, avbase + (size_t)buf * nd);
     if (st != 0) return st;
-    a->T[k] = T;
+    *out = T;
     if (cache) cache->add(ds, 1, key, T);
+    return 0;
+  };
+  if (!pl.approx) {
+    for (int k = 0; k < pl.ntab; k++) {
+      const int st = plain_table(k, k, &a->T[k]);
+      if (st != 0) return st;
+    }
+  } else {
+    // setCApproxIAK3D (fitIAK3D.R:1919-2085): the stationary table, then avCor * avsd(I) * avsd(J) per component
+    int ksrc = -1;
+    for (int k = 0; k < pl.ntab; k++) if (pl.sd_type[k] == 0) ksrc = k;
+    const double* src = nullptr;
+    const int st0 = plain_table(ksrc >= 0 ? ksrc : 0, ksrc >= 0 ? ksrc : NTAB_BUF - 1, &src);
+    if (st0 != 0) return st0;
+    if (ksrc >= 0) a->T[ksrc] = src;
+    std::vector<double> sv;
+    for (int k = 0; k < pl.ntab; k++) {
+      if (pl.sd_type[k] == 0) continue;
+      const int c = pl.sd_comp[k];
+      const int st = iak_avsd_host(ctx, pl, k, ds->h_dIU.data(), nd, ds->h_spl[c].empty() ? nullptr : ds->h_spl[c].data(),
+                                   ds->spl_ncol[c], sv);
+      if (st != 0) return st;                                         // IAK3D_BAD_PARS: C = NA (:2079)
+      double* d_s = avbase + (size_t)NTAB_BUF * nd + (size_t)k * nd;
+      CUDA_TRY(ctx, cudaMemcpyAsync(d_s, sv.data(), (size_t)nd * 8, cudaMemcpyHostToDevice, ctx->stream));
+      double* T = s->d_phid + (size_t)k * nd * nd;
+      const int st2 = launch_scale_table(ctx, src, d_s, nd, d_s, nd, 1, T, avbase + (size_t)k * nd);
+      if (st2 != 0) return st2;
+      a->T[k] = T;
+    }
   }
   for (int c = 0; c < 3; c++) a->tidx[c] = pl.tidx[c];
   a->ntab = pl.ntab;
@@ -449,6 +543,7 @@ extern "C" int iak3d_cov_build(iak3d_ds* ds, const iak3d_pars* pars, double* C, 
   cudaSetDevice(ctx->device);
   EvalPlan pl;
   int st = iak_make_plan(ctx, pars, true, &pl);
+  if (st == 0) st = iak_plan_check_avsd(ctx, ds, &pl);
   if (st != 0) return st;
   if (pl.status != 0) return pl.status;
   Slot* s = nullptr;
@@ -469,7 +564,7 @@ extern "C" int iak3d_cov_build(iak3d_ds* ds, const iak3d_pars* pars, double* C, 
     }
     if (sigma2Vec) {
       if (cudaMalloc(&ds2, (size_t)n * 8) != cudaSuccess) { ctx->err = "cov_build: allocation failed"; rc = IAK3D_ERR_CUDA; cudaGetLastError(); break; }
-      rc = launch_sigma2(ctx, pl, s->d_phid + (size_t)3 * ds->ndIU * ds->ndIU, ds->ndIU, ds->d_did, n, ds2);
+      rc = launch_sigma2(ctx, pl, s->d_phid + (size_t)NTAB_BUF * ds->ndIU * ds->ndIU, ds->ndIU, ds->d_did, n, ds2);
       if (rc != 0) break;
       cudaMemcpyAsync(sigma2Vec, ds2, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
     }
@@ -484,17 +579,73 @@ extern "C" int iak3d_cov_build(iak3d_ds* ds, const iak3d_pars* pars, double* C, 
 // Allocates into *bufs (freed by the caller with cross_free).
 struct CrossBufs {
   double* d_x1 = nullptr; double* d_d1 = nullptr; int32_t* d_xid1 = nullptr; int32_t* d_did1 = nullptr;
-  double* d_phix = nullptr; uint8_t* d_same = nullptr; double* d_T = nullptr;
+  double* d_phix = nullptr; uint8_t* d_same = nullptr; double* d_T = nullptr; double* d_s = nullptr;
   int64_t nx1 = 0, nd1 = 0;
 };
 void iak_cross_free(CrossBufs* b) {
   cudaFree(b->d_x1); cudaFree(b->d_d1); cudaFree(b->d_xid1); cudaFree(b->d_did1); cudaFree(b->d_phix); cudaFree(b->d_same);
-  cudaFree(b->d_T);
+  cudaFree(b->d_T); cudaFree(b->d_s);
   *b = CrossBufs();
 }
+// Depth tables between the unique intervals of set 1 (device d_d1, host dIU1) and of a dataset: iaCovMatern2 per table
+// (fitIAK3D.R:1156-1184) or, with spline sd functions, the stationary table scaled by avsd1(I) * avsd2(J) (:2128-2168).
+// d_T: NTAB_BUF x nd1 x nd2; d_s: 3 x (nd1 + nd2) scratch.  spl1U[c]: nd1 x ncol basis of set 1 (may be null).
+// Returns IAK3D_BAD_PARS when an averaged sd is negative (C = NA, :2172).
+int iak_cross_depth_tables(iak3d_ctx* ctx, const iak3d_ds* ds2, const EvalPlan& pl, const double* d_d1, const double* dIU1,
+                           int64_t nd1, const std::vector<double>* spl1U, double* d_T, double* d_s, const double** Tout) {
+  const int64_t nd2 = ds2->ndIU;
+  for (int k = 0; k < 3; k++) Tout[k] = nullptr;
+  if (!pl.approx) {
+    for (int k = 0; k < pl.ntab; k++) {
+      double* T = d_T + (size_t)k * nd1 * nd2;
+      const int st = launch_iacov_table(ctx, pl.prm[k], d_d1, nd1, ds2->d_dIU, nd2, T, nullptr);
+      if (st != 0) return st;
+      Tout[k] = T;
+    }
+    return 0;
+  }
+  int ksrc = -1;
+  for (int k = 0; k < pl.ntab; k++) if (pl.sd_type[k] == 0) ksrc = k;
+  double* src = d_T + (size_t)(ksrc >= 0 ? ksrc : NTAB_BUF - 1) * nd1 * nd2;
+  int st = launch_iacov_table(ctx, pl.prm[0], d_d1, nd1, ds2->d_dIU, nd2, src, nullptr);
+  if (st != 0) return st;
+  if (ksrc >= 0) Tout[ksrc] = src;
+  std::vector<double> s1, s2;
+  for (int k = 0; k < pl.ntab; k++) {
+    if (pl.sd_type[k] == 0) continue;
+    const int c = pl.sd_comp[k];
+    const std::vector<double>* b1 = spl1U ? &spl1U[c] : nullptr;
+    const int ncol1 = (b1 && nd1 > 0) ? (int)(b1->size() / (size_t)nd1) : 0;
+    st = iak_avsd_host(ctx, pl, k, dIU1, nd1, (b1 && !b1->empty()) ? b1->data() : nullptr, ncol1, s1);
+    if (st != 0) return st;
+    st = iak_avsd_host(ctx, pl, k, ds2->h_dIU.data(), nd2, ds2->h_spl[c].empty() ? nullptr : ds2->h_spl[c].data(), ds2->spl_ncol[c], s2);
+    if (st != 0) return st;
+    double* ds1 = d_s + (size_t)k * (nd1 + nd2); double* ds2v = ds1 + nd1;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ds1, s1.data(), (size_t)nd1 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ds2v, s2.data(), (size_t)nd2 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    double* T = d_T + (size_t)k * nd1 * nd2;
+    st = launch_scale_table(ctx, src, ds1, nd1, ds2v, nd2, 0, T, nullptr);
+    if (st != 0) return st;
+    Tout[k] = T;
+  }
+  return 0;
+}
+
+// rows of a per-row basis (n1 x ncol) at the first occurrence of each unique interval -> nd1 x ncol
+void iak_spl_unique_rows(const double* Xrow, int64_t n1, int ncol, const std::vector<int32_t>& did1, int64_t nd1, std::vector<double>& out) {
+  out.assign((size_t)nd1 * ncol, 0.0);
+  std::vector<char> seen((size_t)nd1, 0);
+  for (int64_t i = 0; i < n1; i++) {
+    const int32_t u = did1[(size_t)i];
+    if (seen[(size_t)u]) continue;
+    seen[(size_t)u] = 1;
+    for (int e = 0; e < ncol; e++) out[(size_t)e * nd1 + u] = Xrow[(size_t)e * n1 + i];
+  }
+}
+
 int iak_cross_tables(iak3d_ctx* ctx, const iak3d_ds* ds2, const EvalPlan& pl, int64_t n1, const std::vector<int32_t>& xid1,
                      const std::vector<double>& xU1, const std::vector<int32_t>& did1, const std::vector<double>& dIU1,
-                     CrossBufs* b, CovArgs* a) {
+                     const std::vector<double>* spl1U, CrossBufs* b, CovArgs* a) {
   const int64_t nx1 = (int64_t)xU1.size() / 2, nd1 = (int64_t)dIU1.size() / 2;
   b->nx1 = nx1; b->nd1 = nd1;
   cudaError_t e = cudaSuccess;
@@ -508,19 +659,15 @@ int iak_cross_tables(iak3d_ctx* ctx, const iak3d_ds* ds2, const EvalPlan& pl, in
   up((void**)&b->d_did1, did1.data(), (size_t)n1 * 4);
   if (e == cudaSuccess) e = cudaMalloc(&b->d_phix, std::max<size_t>((size_t)nx1 * ds2->nxU * 8, 16));
   if (e == cudaSuccess) e = cudaMalloc(&b->d_same, std::max<size_t>((size_t)nx1 * ds2->nxU, 16));
-  if (e == cudaSuccess) e = cudaMalloc(&b->d_T, std::max<size_t>((size_t)3 * nd1 * ds2->ndIU * 8, 16));
+  if (e == cudaSuccess) e = cudaMalloc(&b->d_T, std::max<size_t>((size_t)NTAB_BUF * nd1 * ds2->ndIU * 8, 16));
+  if (e == cudaSuccess) e = cudaMalloc(&b->d_s, std::max<size_t>((size_t)3 * (nd1 + ds2->ndIU) * 8, 16));
   if (e != cudaSuccess) { ctx->err = std::string("cross tables: ") + cudaGetErrorString(e); cudaGetLastError(); return IAK3D_ERR_CUDA; }
-  for (int k = 0; k < 3; k++) a->T[k] = nullptr;
-  for (int k = 0; k < pl.ntab; k++) {
-    double* T = b->d_T + (size_t)k * nd1 * ds2->ndIU;
-    const int st = launch_iacov_table(ctx, pl.prm[k], b->d_d1, nd1, ds2->d_dIU, ds2->ndIU, T, nullptr);
-    if (st != 0) return st;
-    a->T[k] = T;
-  }
+  int st = iak_cross_depth_tables(ctx, ds2, pl, b->d_d1, dIU1.data(), nd1, spl1U, b->d_T, b->d_s, a->T);
+  if (st != 0) return st;
   for (int c = 0; c < 3; c++) a->tidx[c] = pl.tidx[c];
   a->ntab = pl.ntab;
   // phix0 = 1[Dx == 0] (fitIAK3D.R:1138-1141) always; phix1 unless nugget
-  const int st = launch_phix_table(ctx, pl.H, b->d_x1, nx1, ds2->d_xU, ds2->nxU, pl.has_phix ? b->d_phix : nullptr, b->d_same);
+  st = launch_phix_table(ctx, pl.H, b->d_x1, nx1, ds2->d_xU, ds2->nxU, pl.has_phix ? b->d_phix : nullptr, b->d_same);
   if (st != 0) return st;
   a->phix = pl.has_phix ? b->d_phix : nullptr;
   a->same = b->d_same;
@@ -530,7 +677,8 @@ int iak_cross_tables(iak3d_ctx* ctx, const iak3d_ds* ds2, const EvalPlan& pl, in
   return 0;
 }
 
-extern "C" int iak3d_cov_cross(iak3d_ds* ds2, const iak3d_pars* pars, int64_t n1, const double* xy1, const double* dI1, double* out) {
+extern "C" int iak3d_cov_cross_spl(iak3d_ds* ds2, const iak3d_pars* pars, int64_t n1, const double* xy1, const double* dI1,
+                                   const double* const* Xspl1, double* out) {
   if (!ds2 || !pars || n1 < 0 || (n1 > 0 && (!xy1 || !dI1 || !out))) return IAK3D_ERR_ARG;
   iak3d_ctx* ctx = ds2->ctx;
   cudaSetDevice(ctx->device);
@@ -542,9 +690,12 @@ extern "C" int iak3d_cov_cross(iak3d_ds* ds2, const iak3d_pars* pars, int64_t n1
   std::vector<int32_t> xid1, did1; std::vector<double> xU1, dIU1;
   iak_unique_first(n1, xy1, xy1 + n1, xid1, xU1);
   iak_unique_first(n1, dI1, dI1 + n1, did1, dIU1);
+  std::vector<double> spl1U[3];
+  for (int c = 0; c < 3; c++)
+    if (pars->sdfdType[c] > 0 && Xspl1 && Xspl1[c]) iak_spl_unique_rows(Xspl1[c], n1, pars->sdfdType[c] + 1, did1, (int64_t)dIU1.size() / 2, spl1U[c]);
   CrossBufs b; CovArgs a;
   double* dout = nullptr;
-  int rc = iak_cross_tables(ctx, ds2, pl, n1, xid1, xU1, did1, dIU1, &b, &a);
+  int rc = iak_cross_tables(ctx, ds2, pl, n1, xid1, xU1, did1, dIU1, spl1U, &b, &a);
   do {
     if (rc != 0) break;
     if (cudaMalloc(&dout, (size_t)n1 * ds2->n * 8) != cudaSuccess) { ctx->err = "cov_cross: allocation failed"; rc = IAK3D_ERR_CUDA; cudaGetLastError(); break; }
@@ -554,9 +705,14 @@ extern "C" int iak3d_cov_cross(iak3d_ds* ds2, const iak3d_pars* pars, int64_t n1
     const cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { ctx->err = std::string("cov_cross: ") + cudaGetErrorString(e); rc = IAK3D_ERR_CUDA; }
   } while (0);
+  cudaStreamSynchronize(ctx->stream);
   cudaFree(dout);
   iak_cross_free(&b);
   return rc;
+}
+
+extern "C" int iak3d_cov_cross(iak3d_ds* ds2, const iak3d_pars* pars, int64_t n1, const double* xy1, const double* dI1, double* out) {
+  return iak3d_cov_cross_spl(ds2, pars, n1, xy1, dI1, nullptr, out);
 }
 
 // ================================================================================================
@@ -655,6 +811,7 @@ extern "C" int iak3d_nll_terms_batch_enqueue(iak3d_ctx* ctx, int32_t count, iak3
   std::vector<int> live((size_t)count, 0);
   for (int i = 0; i < count; i++) {
     st = iak_make_plan(ctx, &pars[i], true, &plans[i]);
+    if (st == 0) st = iak_plan_check_avsd(ctx, dss[i], &plans[i]);
     if (st != 0) return st;
     b->plan_status[i] = plans[i].status;
     const size_t k = uses[dss[i]]++;

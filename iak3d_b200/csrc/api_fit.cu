@@ -23,6 +23,12 @@ int iak_square_tables(iak3d_ctx* ctx, const iak3d_ds* ds, const EvalPlan& pl, Sl
 int iak_factor_slot(iak3d_ctx* ctx, Slot* s, int32_t* status_out, double* lndet_out, double* G_out);
 int iak_backsolve_to_host(iak3d_ctx* ctx, Slot* s, double* out_host, double* d_out_opt);
 int iak_inverse_from_factor(iak3d_ctx* ctx, Slot* s, double* d_iC);
+int iak_plan_check_avsd(iak3d_ctx* ctx, const iak3d_ds* ds, EvalPlan* pl);
+int iak_avsd_host(iak3d_ctx* ctx, const EvalPlan& pl, int k, const double* dIU, int64_t nd, const double* XsplU, int ncol,
+                  std::vector<double>& s);
+int iak_cross_depth_tables(iak3d_ctx* ctx, const iak3d_ds* ds2, const EvalPlan& pl, const double* d_d1, const double* dIU1,
+                           int64_t nd1, const std::vector<double>* spl1U, double* d_T, double* d_s, const double** Tout);
+void iak_spl_unique_rows(const double* Xrow, int64_t n1, int ncol, const std::vector<int32_t>& did1, int64_t nd1, std::vector<double>& out);
 
 constexpr int64_t PRED_CHUNK = 16384;   // prediction rows per panel (128 row blocks)
 
@@ -43,6 +49,9 @@ struct iak3d_fit {
   double* d_X = nullptr;         // m x p column-major
   int32_t* d_did1 = nullptr;     // m
   double* d_dIU1 = nullptr;      // nd1 x 2
+  std::vector<double> h_dIU1;    // host copy
+  std::vector<double> spl1U[3];  // spline sd basis of the map supports' unique intervals (nd1 x ncol), setCApproxIAK3D2
+  double* d_s = nullptr;         // averaged-sd vectors: 3 x (nd1cap + ndIU2) cross + 3 x nd1cap self
   double* d_z = nullptr; double* d_v = nullptr; double* d_ckk = nullptr;
   int64_t cap_m = 0;
   // ---- panel workspace (one chunk) ----
@@ -68,8 +77,8 @@ static void fit_free_job(iak3d_fit* f) {
 }
 static void fit_free_panel(iak3d_fit* f) {
   cudaFree(f->d_P); cudaFree(f->d_G); cudaFree(f->d_pflags); cudaFree(f->d_phix); cudaFree(f->d_same); cudaFree(f->d_T);
-  cudaFree(f->d_Tself); cudaFree(f->d_iota); cudaFree(f->d_tasks);
-  f->d_P = f->d_G = f->d_phix = f->d_T = f->d_Tself = nullptr; f->d_pflags = nullptr; f->d_same = nullptr; f->d_iota = nullptr;
+  cudaFree(f->d_Tself); cudaFree(f->d_iota); cudaFree(f->d_tasks); cudaFree(f->d_s);
+  f->d_P = f->d_G = f->d_phix = f->d_T = f->d_Tself = f->d_s = nullptr; f->d_pflags = nullptr; f->d_same = nullptr; f->d_iota = nullptr;
   f->d_tasks = nullptr; f->ldP = 0; f->nd1cap = 0; f->tasks_rows = 0;
 }
 
@@ -96,6 +105,7 @@ extern "C" int iak3d_fit_create(iak3d_ds* ds, const iak3d_pars* pars, const doub
   int rc = iak_make_plan(ctx, pars, true, &f->plan_sq);
   if (rc == 0) rc = iak_make_plan(ctx, pars, false, &f->plan_x);
   if (rc == 0) { iak3d_pars pk = *pars; pk.quirk_scale = 1.0; rc = iak_make_plan(ctx, &pk, true, &f->plan_kk); }
+  if (rc == 0) rc = iak_plan_check_avsd(ctx, ds, &f->plan_sq);
   if (rc == 0 && f->plan_sq.status != 0) rc = f->plan_sq.status;
   if (rc != 0) { delete f; return rc; }
   const int64_t n = ds->n; const int p = f->p, q = f->q;
@@ -202,9 +212,10 @@ static int fit_reserve_panel(iak3d_fit* f, int64_t rows, int64_t nd1) {
   }
   if (nd1 > f->nd1cap) {
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(f->d_T); cudaFree(f->d_Tself); f->d_T = f->d_Tself = nullptr;
-    CUDA_TRY(ctx, cudaMalloc(&f->d_T, (size_t)3 * nd1 * f->ds->ndIU * 8));
-    CUDA_TRY(ctx, cudaMalloc(&f->d_Tself, (size_t)3 * nd1 * nd1 * 8));
+    cudaFree(f->d_T); cudaFree(f->d_Tself); cudaFree(f->d_s); f->d_T = f->d_Tself = f->d_s = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&f->d_T, (size_t)NTAB_BUF * nd1 * f->ds->ndIU * 8));
+    CUDA_TRY(ctx, cudaMalloc(&f->d_Tself, (size_t)NTAB_BUF * nd1 * nd1 * 8));
+    CUDA_TRY(ctx, cudaMalloc(&f->d_s, (size_t)(3 * (nd1 + f->ds->ndIU) + 3 * nd1) * 8));
     f->nd1cap = nd1;
   }
   return 0;
@@ -229,6 +240,11 @@ static int fit_panel_tasks(iak3d_fit* f, int64_t rowsP) {
 }
 
 extern "C" int iak3d_predict_stage(iak3d_fit* f, int64_t m, const double* xyMap, const double* dIMap, const double* XMap) {
+  return iak3d_predict_stage_spl(f, m, xyMap, dIMap, XMap, nullptr);
+}
+
+extern "C" int iak3d_predict_stage_spl(iak3d_fit* f, int64_t m, const double* xyMap, const double* dIMap, const double* XMap,
+                                       const double* const* Xspl1) {
   if (!f || m < 0 || (m > 0 && (!xyMap || !dIMap || !XMap))) return IAK3D_ERR_ARG;
   iak3d_ctx* ctx = f->ctx;
   cudaSetDevice(ctx->device);
@@ -251,6 +267,11 @@ extern "C" int iak3d_predict_stage(iak3d_fit* f, int64_t m, const double* xyMap,
   std::vector<int32_t> did1; std::vector<double> dIU1;
   iak_unique_first(m, dIMap, dIMap + m, did1, dIU1);
   f->nd1 = (int64_t)dIU1.size() / 2;
+  f->h_dIU1 = dIU1;
+  for (int c = 0; c < 3; c++) {
+    f->spl1U[c].clear();
+    if (f->pars.sdfdType[c] > 0 && Xspl1 && Xspl1[c]) iak_spl_unique_rows(Xspl1[c], m, f->pars.sdfdType[c] + 1, did1, f->nd1, f->spl1U[c]);
+  }
   cudaFree(f->d_dIU1); f->d_dIU1 = nullptr;
   CUDA_TRY(ctx, cudaMalloc(&f->d_dIU1, dIU1.size() * 8));
   CUDA_TRY(ctx, cudaMemcpyAsync(f->d_dIU1, dIU1.data(), dIU1.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -285,16 +306,37 @@ extern "C" int iak3d_predict_enqueue(iak3d_fit* f) {
   // depth tables: cross (nd1 x nd2) and self (nd1 x nd1, for Ckk)
   CovArgs a;
   const double* Tself[3] = {nullptr, nullptr, nullptr};
-  for (int k = 0; k < 3; k++) a.T[k] = nullptr;
-  for (int k = 0; k < px.ntab; k++) {
-    double* T = f->d_T + (size_t)k * nd1 * nd2;
-    rc = launch_iacov_table(ctx, px.prm[k], f->d_dIU1, nd1, ds->d_dIU, nd2, T, nullptr);
+  rc = iak_cross_depth_tables(ctx, ds, px, f->d_dIU1, f->h_dIU1.data(), nd1, f->spl1U, f->d_T, f->d_s, a.T);
+  if (rc != 0) return rc;
+  if (!ps.approx) {
+    for (int k = 0; k < ps.ntab; k++) {
+      double* Ts = f->d_Tself + (size_t)k * nd1 * nd1;
+      rc = launch_iacov_table(ctx, ps.prm[k], f->d_dIU1, nd1, f->d_dIU1, nd1, Ts, nullptr);
+      if (rc != 0) return rc;
+      Tself[k] = Ts;
+    }
+  } else {
+    // Ckk = diag(setCApproxIAK3D(map supports)) (predictIAK3D.R:183; fitIAK3D.R:959-962)
+    int ksrc = -1;
+    for (int k = 0; k < ps.ntab; k++) if (ps.sd_type[k] == 0) ksrc = k;
+    double* src = f->d_Tself + (size_t)(ksrc >= 0 ? ksrc : NTAB_BUF - 1) * nd1 * nd1;
+    rc = launch_iacov_table(ctx, ps.prm[0], f->d_dIU1, nd1, f->d_dIU1, nd1, src, nullptr);
     if (rc != 0) return rc;
-    a.T[k] = T;
-    double* Ts = f->d_Tself + (size_t)k * nd1 * nd1;
-    rc = launch_iacov_table(ctx, ps.prm[k], f->d_dIU1, nd1, f->d_dIU1, nd1, Ts, nullptr);
-    if (rc != 0) return rc;
-    Tself[k] = Ts;
+    if (ksrc >= 0) Tself[ksrc] = src;
+    std::vector<double> s1;
+    for (int k = 0; k < ps.ntab; k++) {
+      if (ps.sd_type[k] == 0) continue;
+      const int c = ps.sd_comp[k];
+      const int ncol1 = (!f->spl1U[c].empty() && nd1 > 0) ? (int)(f->spl1U[c].size() / (size_t)nd1) : 0;
+      rc = iak_avsd_host(ctx, ps, k, f->h_dIU1.data(), nd1, f->spl1U[c].empty() ? nullptr : f->spl1U[c].data(), ncol1, s1);
+      if (rc != 0) return rc;
+      double* dsv = f->d_s + (size_t)3 * (nd1 + nd2) + (size_t)k * nd1;
+      CUDA_TRY(ctx, cudaMemcpyAsync(dsv, s1.data(), (size_t)nd1 * 8, cudaMemcpyHostToDevice, ctx->stream));
+      double* Ts = f->d_Tself + (size_t)k * nd1 * nd1;
+      rc = launch_scale_table(ctx, src, dsv, nd1, dsv, nd1, 1, Ts, nullptr);
+      if (rc != 0) return rc;
+      Tself[k] = Ts;
+    }
   }
   rc = launch_ckk(ctx, ps, Tself, nd1, f->d_did1, m, f->d_ckk);
   if (rc != 0) return rc;

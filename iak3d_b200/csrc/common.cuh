@@ -52,6 +52,8 @@ struct iak3d_ctx {
   long long* d_prof = nullptr; int64_t prof_cap = 0; int32_t prof_ntasks = 0;   // IAK3D_PROF=1 diagnostics
 };
 
+constexpr int NTAB_BUF = 4;   // depth-table buffers of a slot: <= 3 tables in use + the stationary source of the approximation
+
 // Workspace of ONE likelihood evaluation of a dataset: the factor buffer, the unique-pair tables and the
 // dependency flags.  A dataset owns as many slots as the largest number of simultaneous evaluations asked of
 // it (1 for a composite-likelihood block, npar+1 for a forward-difference gradient).
@@ -60,7 +62,7 @@ struct Slot {
   int32_t q = 0, nCB = 0, nRB = 0;
   double* d_L = nullptr;          // ld x Npad factor buffer, BLOCKED (uidx): A in, L out; W' rows at Npad..Npad+q-1
   double* d_phix = nullptr;       // nxU x nxU horizontal correlation table
-  double* d_phid = nullptr;       // 3 tables ndIU x ndIU + 3 avVar vectors
+  double* d_phid = nullptr;       // NTAB_BUF tables ndIU x ndIU + NTAB_BUF avVar vectors + 3 avsd vectors (spline sd)
   double* d_invd = nullptr;       // nCB x INVD_BLOCK inverted diagonal blocks
   int32_t* d_flags = nullptr;     // done[nRB*nCB] + invdone[nCB]
   double* d_logsum = nullptr;     // nCB
@@ -75,6 +77,8 @@ struct iak3d_ds {
   int32_t q = 0;
   std::vector<int32_t> h_xid, h_did;
   std::vector<double> h_xU, h_dIU;       // nxU x 2, ndIU x 2 (column-major)
+  std::vector<double> h_spl[3];          // XsdfdSplineU_{cd1,cxd0,cxd1}: ndIU x spl_ncol[c] column-major (iaCovMatern.R:520-539)
+  int32_t spl_ncol[3] = {0, 0, 0};
   double* h_W = nullptr;                 // n x q column-major copy in PINNED host memory: staging of the H2D copy
   int32_t *d_xid = nullptr, *d_did = nullptr;
   double *d_xU = nullptr, *d_dIU = nullptr;   // column-major nxU x 2 / ndIU x 2
@@ -94,6 +98,12 @@ struct EvalPlan {
   int tidx[3] = {-1, -1, -1};   // table of cd1, cxd0, cxd1 (-1 absent)
   bool has_phix = false;
   HxPrm H;
+  // setCApproxIAK3D[2] (any sdfdType > 0, fitIAK3D.R:959-962): every table is the stationary table scaled by the
+  // interval-averaged sd of its component, avCor * avsd(I) * avsd(J) (:1960-1963).  Per TABLE k:
+  bool approx = false;
+  int sd_type[3] = {0, 0, 0};            // 0: the stationary table itself; -1 / k > 0: scaled by iasdfd (fitIAK3D.R:1448-1468)
+  int sd_comp[3] = {0, 0, 0};            // component (0 cd1, 1 cxd0, 2 cxd1) whose spline basis applies
+  double sd_coef[3][IAK3D_MAX_SPL] = {}; // (tau1, tau2) or the spline coefficients
   double cx0 = 0, cx1 = 0, cd1 = 0, kd1 = 0, cxd0 = 0, cxd1 = 0, cme = 0;
 };
 
@@ -134,8 +144,12 @@ int launch_cov_factor_layout(iak3d_ctx* ctx, const CovArgs& a, const double* d_W
 // generic symmetric matrix (host-supplied C, optim_functions.R:268) + b' rows into the factor layout
 int launch_pack_factor_layout(iak3d_ctx* ctx, const double* d_C, int64_t n, const double* d_b, int32_t q, int64_t Npad,
                               int64_t ld, double* d_L);
-int launch_sigma2(iak3d_ctx* ctx, const EvalPlan& pl, const double* d_avvar /* 3 x ndIU */, int64_t ndIU, const int32_t* d_did,
+int launch_sigma2(iak3d_ctx* ctx, const EvalPlan& pl, const double* d_avvar /* NTAB_BUF x ndIU */, int64_t ndIU, const int32_t* d_did,
                   int64_t n, double* d_out);
+// setCApproxIAK3D[2]: out(i,j) = (src(i,j) * s1(i)) * s2(j) (rectangular, fitIAK3D.R:2146) or, symmetric, the packed-upper
+// order of :1963  (src * s[max(i,j)]) * s[min(i,j)];  avvar1 = s1^2 when not null
+int launch_scale_table(iak3d_ctx* ctx, const double* d_src, const double* d_s1, int64_t n1, const double* d_s2, int64_t n2,
+                       int symmetric, double* d_out, double* d_avvar1);
 int launch_ckk(iak3d_ctx* ctx, const EvalPlan& pl, const double* const* d_Tself /* per table: ndIU1 x ndIU1 */, int64_t ndIU1,
                const int32_t* d_did1, int64_t m, double* d_out);
 // blocked != 0: d_out is a blocked buffer (uidx) with rows_total rows; otherwise plain column-major with leading dim ld

@@ -265,7 +265,7 @@ int launch_pack_factor_layout(iak3d_ctx* ctx, const double* d_C, int64_t n, cons
 }
 
 // ---- sigma2Vec (fitIAK3D.R:1083-1086) ------------------------------------------------------------------
-struct S2Dev { double cxd0, cxd1, cme, cx0, cx1, cd1; int t0, t1, td; };
+struct S2Dev { double cxd0, cxd1, cme, cx0, cx1, cd1; int t0, t1, td; int approx; };
 __global__ void sigma2_kernel(S2Dev a, const double* __restrict__ av, int64_t ndIU, const int32_t* __restrict__ did, int64_t n,
                               double* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -274,16 +274,23 @@ __global__ void sigma2_kernel(S2Dev a, const double* __restrict__ av, int64_t nd
   const double a0 = a.t0 >= 0 ? av[(int64_t)a.t0 * ndIU + d] : 0.0;
   const double a1 = a.t1 >= 0 ? av[(int64_t)a.t1 * ndIU + d] : 0.0;
   const double ad = a.td >= 0 ? av[(int64_t)a.td * ndIU + d] : 0.0;
-  double v = a.cxd0 * a0;
-  v = v + a.cxd1 * a1;
-  v = v + a.cme; v = v + a.cx0; v = v + a.cx1;
-  v = v + a.cd1 * ad;
+  double v;
+  if (a.approx) {                    // setCApproxIAK3D's order (fitIAK3D.R:2056)
+    v = a.cx0 + a.cx1;
+    v = v + a.cd1 * ad; v = v + a.cxd0 * a0; v = v + a.cxd1 * a1;
+    v = v + a.cme;
+  } else {                           // setCIAK3D's order (fitIAK3D.R:1083)
+    v = a.cxd0 * a0;
+    v = v + a.cxd1 * a1;
+    v = v + a.cme; v = v + a.cx0; v = v + a.cx1;
+    v = v + a.cd1 * ad;
+  }
   out[i] = v;
 }
 int launch_sigma2(iak3d_ctx* ctx, const EvalPlan& pl, const double* d_avvar, int64_t ndIU, const int32_t* d_did, int64_t n,
                   double* d_out) {
   if (n == 0) return 0;
-  S2Dev a{pl.cxd0, pl.cxd1, pl.cme, pl.cx0, pl.cx1, pl.cd1, pl.tidx[1], pl.tidx[2], pl.tidx[0]};
+  S2Dev a{pl.cxd0, pl.cxd1, pl.cme, pl.cx0, pl.cx1, pl.cd1, pl.tidx[1], pl.tidx[2], pl.tidx[0], pl.approx ? 1 : 0};
   sigma2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(a, d_avvar, ndIU, d_did, n, d_out);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());

@@ -17,6 +17,7 @@
 // from api.cu
 struct TableCache;
 int iak_make_plan(iak3d_ctx* ctx, const iak3d_pars* p, bool square, EvalPlan* pl);
+int iak_plan_check_avsd(iak3d_ctx* ctx, const iak3d_ds* ds, EvalPlan* pl);
 int iak_alloc_slot(iak3d_ctx* ctx, int64_t n, int32_t q, int64_t nxU, int64_t ndIU, Slot** out);
 void iak_free_slot(Slot* s);
 int iak_square_tables(iak3d_ctx* ctx, const iak3d_ds* ds, const EvalPlan& pl, Slot* s, CovArgs* a, TableCache* cache = nullptr);
@@ -220,6 +221,7 @@ extern "C" int iak3d_gradhess(iak3d_ds* ds, const iak3d_pars* pars, int32_t ncom
   P.quirk_cd1_unscaled = 0;
   EvalPlan pl;
   int rc = iak_make_plan(ctx, &P, true, &pl);
+  if (rc == 0) rc = iak_plan_check_avsd(ctx, ds, &pl);
   if (rc != 0) return rc;
   if (pl.status != 0) return pl.status;
   const double nanv = nan("");

@@ -30,6 +30,35 @@ int launch_iacov_table(iak3d_ctx* ctx, const IaPrm& P, const double* d_dI1, int6
   return 0;
 }
 
+// setCApproxIAK3D[2]: avCor * avsd(I) * avsd(J) on unique interval pairs (fitIAK3D.R:1960-1963, 2146).  The multiplication
+// order is the reference's: rectangular (src * s1[i]) * s2[j]; symmetric (packed upper storage, element (i <= j) times
+// s[j] then s[i])  (src * s[max]) * s[min].
+__global__ void scale_table_kernel(const double* __restrict__ src, const double* __restrict__ s1, int64_t n1,
+                                   const double* __restrict__ s2, int64_t n2, int symmetric, double* __restrict__ out,
+                                   double* __restrict__ avvar1) {
+  const int64_t total = n1 * n2;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = idx % n1, j = idx / n1;
+    double v = src[idx];
+    if (symmetric) { const int64_t hi = i > j ? i : j, lo = i > j ? j : i; v = v * s1[hi]; v = v * s1[lo]; }
+    else { v = v * s1[i]; v = v * s2[j]; }
+    out[idx] = v;
+    if (avvar1 != nullptr && j == 0) avvar1[i] = s1[i] * s1[i];
+  }
+}
+
+int launch_scale_table(iak3d_ctx* ctx, const double* d_src, const double* d_s1, int64_t n1, const double* d_s2, int64_t n2,
+                       int symmetric, double* d_out, double* d_avvar1) {
+  const int64_t total = n1 * n2;
+  if (total == 0) return 0;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+  scale_table_kernel<<<blocks, 256, 0, ctx->stream>>>(d_src, d_s1, n1, d_s2, n2, symmetric, d_out, d_avvar1);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return 0;
+}
+
 // phi_x on unique location pairs; D as in xyDist (iaCovMatern.R:888-920): squares added in dimension
 // order, then sqrt.  Optionally records the exact-equality indicator 1[D == 0] (fitIAK3D.R:1138).
 __global__ void phix_table_kernel(HxPrm H, const double* __restrict__ x1, int64_t n1, const double* __restrict__ x2,

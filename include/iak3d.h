@@ -44,11 +44,16 @@ extern "C" {
 #define IAK3D_MODELX_MATERN 2
 #define IAK3D_MODELX_WENDLAND 3
 
+/* largest number of internal knots of a spline sd function (sdfdType > 0, fitIAK3D.R:1490-1495) */
+#define IAK3D_MAX_SPL 12
+
 /* parsBTfmd + the model switches that select terms (fitIAK3D.R:1405-1408, 955-956). */
 typedef struct iak3d_pars {
   int32_t modelx;          /* IAK3D_MODELX_* */
   int32_t cmeOpt;          /* informational; cme is used as given (0 when cmeOpt == 0) */
-  int32_t sdfdType[3];     /* cd1, cxd0, cxd1: 0 stationary, -1 exponential sd(d), -9 component absent */
+  int32_t sdfdType[3];     /* cd1, cxd0, cxd1: 0 stationary, -1 exponential sd(d), -9 component absent, k > 0 natural
+                              spline with k internal knots: then EVERY component goes through the interval-averaged
+                              sd approximation of setCApproxIAK3D[2] (fitIAK3D.R:959-962,1919-2233) */
   int32_t quirk_cd1_unscaled; /* 1 = reproduce fitIAK3D.R:1052 (non-stationary cd1 term added without cd1) */
   double ax, nux, ad, nud; /* nud must be 0.5, 1.5 or 2.5 (iaCovMatern.R:12-29) */
   double cx0, cx1, cd1, cxd0, cxd1, cme;
@@ -56,6 +61,8 @@ typedef struct iak3d_pars {
   double quirk_scale;      /* multiplier of the unscaled cd1 term when quirk_cd1_unscaled applies; 0 is read as 1.
                               1 while optimising and for Ckk (predictIAK3D.R:183 rebuilds from parsBTfmd); cxdhat for
                               the kept C = cxdhat * A of a fit (fitIAK3D.R:871) */
+  double sdfdSpl[3][IAK3D_MAX_SPL]; /* spline coefficients of a component with sdfdType k > 0 (the k free parameters;
+                              iasdfd multiplies the basis by c(1, sdfdPars), fitIAK3D.R:1458) */
 } iak3d_pars;
 
 typedef struct iak3d_ctx iak3d_ctx;   /* one per GPU: stream, workspaces, error text */
@@ -81,6 +88,10 @@ IAK3D_API int iak3d_dataset_set_W(iak3d_ds* ds, const double* W, int32_t q);
 IAK3D_API int iak3d_dataset_info(iak3d_ds* ds, int64_t* n, int64_t* nxU, int64_t* ndIU, int32_t* q);
 /* 0-based ids of each row's unique location / unique depth interval (Kx, Kd as id vectors) */
 IAK3D_API int iak3d_dataset_ids(iak3d_ds* ds, int32_t* xid, int32_t* did);
+/* setupMats$XsdfdSplineU_{cd1,cxd0,cxd1} (iaCovMatern.R:520-539): interval-averaged spline basis of component comp
+ * (0 cd1, 1 cxd0, 2 cxd1) on the dataset's UNIQUE depth intervals (first-occurrence order), ndIU x ncol column-major,
+ * ncol = sdfdType + 1.  Needed before any evaluation whose sdfdType[comp] > 0. */
+IAK3D_API int iak3d_dataset_set_sdfd_spline(iak3d_ds* ds, int32_t comp, int32_t ncol, const double* XsplU);
 
 /* ---- depth / horizontal kernels on unique pairs ---------------------------------------------
  * iaCovMatern2 (iaCovMatern.R:107-191): out is n1 x n2 column-major; avVar (n1) may be NULL
@@ -100,6 +111,11 @@ IAK3D_API int iak3d_cov_build(iak3d_ds* ds, const iak3d_pars* pars, double* C, d
  * dataset (set 2); out is n1 x n, no cme (fitIAK3D.R:1243). */
 IAK3D_API int iak3d_cov_cross(iak3d_ds* ds2, const iak3d_pars* pars, int64_t n1, const double* xy1,
                     const double* dI1, double* out);
+/* setCApproxIAK3D2 (fitIAK3D.R:2095-2233): the same with spline sd functions.  Xspl1[c] is the spline basis of
+ * component c on the ROWS of set 1 (n1 x (sdfdType[c]+1), column-major; setupMats$XsdfdSplineU_* expanded by Kd), or
+ * NULL for a component whose sdfdType is not > 0. */
+IAK3D_API int iak3d_cov_cross_spl(iak3d_ds* ds2, const iak3d_pars* pars, int64_t n1, const double* xy1,
+                        const double* dI1, const double* const* Xspl1, double* out);
 
 /* ---- factorisation --------------------------------------------------------------------------
  * lndetANDinvCb (optim_functions.R:268-312, methodSolveTEST == 1): chol(C), lndetC = 2 sum log diag,
@@ -138,6 +154,9 @@ IAK3D_API int iak3d_predict(iak3d_fit* fit, int64_t m, const double* xyMap, cons
                   double* z, double* v);
 /* device-resident variant for timing: inputs staged by iak3d_predict_stage, results by _fetch */
 IAK3D_API int iak3d_predict_stage(iak3d_fit* fit, int64_t m, const double* xyMap, const double* dIMap, const double* XMap);
+/* with spline sd functions: Xspl1[c] = basis of component c on the m map supports (m x (sdfdType[c]+1)) or NULL */
+IAK3D_API int iak3d_predict_stage_spl(iak3d_fit* fit, int64_t m, const double* xyMap, const double* dIMap, const double* XMap,
+                            const double* const* Xspl1);
 IAK3D_API int iak3d_predict_enqueue(iak3d_fit* fit);
 IAK3D_API int iak3d_predict_fetch(iak3d_fit* fit, double* z, double* v);
 

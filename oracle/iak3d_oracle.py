@@ -436,17 +436,79 @@ def _unique_first(rows):
     return rows[first[order]], rank[inv.reshape(-1)]
 
 
-def setupIAK3D(xData, dIData):
+def makeXnsClampedUG0(x, bdryKnots, intKnots, paramVs=0):
+    """splineBasisFns.R:158-325, restated branch by branch (point support and increment-averaged; paramVs 0 and 1)."""
+    x = np.asarray(x, float)
+    iaX = (x.ndim == 2 and x.shape[1] == 2)                              # :160-168
+    n = x.shape[0]
+    if not iaX:
+        x = x.reshape(-1)
+    b1, b2 = float(bdryKnots[0]), float(bdryKnots[1])
+    ik_ = np.asarray([] if intKnots is None else intKnots, float).reshape(-1)
+    nK = ik_.size
+    X = np.ones((n, 1 + nK))
+    if nK == 0:
+        return X
+
+    def clip0(v):
+        v = np.array(v, float)
+        v[v < 0] = 0.0
+        return v
+
+    if iaX:
+        def cube(k):                                                     # 0.25 (tmpU^4 - tmpL^4) / (x2 - x1), :176-186
+            return 0.25 * (clip0(x[:, 1] - k) ** 4 - clip0(x[:, 0] - k) ** 4) / (x[:, 1] - x[:, 0])
+        Ex = 0.5 * (x[:, 0] + x[:, 1])
+    else:
+        def cube(k):                                                     # :204-211
+            return clip0(x - k) ** 3
+        Ex = x
+    cL, cU = cube(b1), cube(b2)
+
+    def hfun(k):                                                         # :196-198 / :215-217
+        return (cube(k) - ((b2 - k) / (b2 - b1)) * cL + ((b1 - k) / (b2 - b1)) * cU
+                + 3 * (b2 - k) * (k - b1) * Ex)
+
+    if paramVs == 0:
+        for j in range(nK):
+            X[:, 1 + j] = hfun(ik_[j])
+    elif paramVs == 1:                                                   # :222-318
+        kK = ik_[nK - 1]
+        Ehxk = hfun(kK)
+        denomTmp = (b2 - kK) * (kK - b1) * (kK + b1 + b2)                # :253
+        X[:, 0] = 1 - Ehxk / denomTmp
+        for j in range(nK - 1):
+            qtmp = ((b2 - ik_[j]) * (ik_[j] - b1) * (ik_[j] + b1 + b2)) / denomTmp
+            X[:, 1 + j] = hfun(ik_[j]) - qtmp * Ehxk
+        X[:, nK] = Ehxk / denomTmp
+    else:
+        raise ValueError("Unknonwn parameterisation option for spline function!")
+    return X
+
+
+def _spline_bases(dIU, sdfdTypes, sdfdKnots):
+    """iaCovMatern.R:520-539: XsdfdSplineU_{cd1,cxd0,cxd1} (paramVs = 1)."""
+    out = {}
+    for nm, t in zip(("cd1", "cxd0", "cxd1"), sdfdTypes):
+        out[nm] = (makeXnsClampedUG0(dIU, sdfdKnots["bdryKnots"], sdfdKnots["intKnots_" + nm], paramVs=1)
+                   if t > 0 else None)
+    return out
+
+
+def setupIAK3D(xData, dIData, sdfdTypes=(0, 0, 0), sdfdKnots=None):
     """iaCovMatern.R:413-548.  Kx/Kd incidence matrices are represented by id vectors."""
     xData = np.asarray(xData, float).reshape(len(xData), -1)
     dIData = np.asarray(dIData, float).reshape(-1, 2)
     xU, xid = _unique_first(xData)
     dIU, did = _unique_first(dIData)
-    return dict(xU=xU, dIU=dIU, xid=xid, did=did, Dx=xyDist(xU, xU),
-                maxd=max(float(dIU.max()), 2.0), n=xData.shape[0])
+    sm = dict(xU=xU, dIU=dIU, xid=xid, did=did, Dx=xyDist(xU, xU),
+              maxd=max(float(dIU.max()), 2.0), n=xData.shape[0], sdfdKnots=sdfdKnots)
+    if max(sdfdTypes) > 0:
+        sm["XsdfdSplineU"] = _spline_bases(dIU, sdfdTypes, sdfdKnots)
+    return sm
 
 
-def setupIAK3D2(xData, dIData, xData2, dIData2):
+def setupIAK3D2(xData, dIData, xData2, dIData2, sdfdTypes=(0, 0, 0), sdfdKnots=None):
     """iaCovMatern.R:581-678."""
     xData = np.asarray(xData, float).reshape(len(xData), -1)
     xData2 = np.asarray(xData2, float).reshape(len(xData2), -1)
@@ -454,8 +516,12 @@ def setupIAK3D2(xData, dIData, xData2, dIData2):
     dIU, did = _unique_first(np.asarray(dIData, float).reshape(-1, 2))
     xU2, xid2 = _unique_first(xData2)
     dIU2, did2 = _unique_first(np.asarray(dIData2, float).reshape(-1, 2))
-    return dict(xU=xU, dIU=dIU, xid=xid, did=did, xU2=xU2, dIU2=dIU2, xid2=xid2, did2=did2,
-                Dx=xyDist(xU, xU2))
+    sm = dict(xU=xU, dIU=dIU, xid=xid, did=did, xU2=xU2, dIU2=dIU2, xid2=xid2, did2=did2,
+              Dx=xyDist(xU, xU2), sdfdKnots=sdfdKnots)
+    if max(sdfdTypes) > 0:
+        sm["XsdfdSplineU"] = _spline_bases(dIU, sdfdTypes, sdfdKnots)
+        sm["XsdfdSplineU2"] = _spline_bases(dIU2, sdfdTypes, sdfdKnots)
+    return sm
 
 
 # ---------------------------------------------------------------------------
@@ -488,8 +554,9 @@ def setCIAK3D(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cme
     cd1 multiplier (fitIAK3D.R:1052) while sigma2Vec (:1083) and setCIAK3D2 (:1211) include it.
     """
     types = (sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1)
-    if max(types) > 0:
-        raise NotImplementedError("spline sdfd (setCApproxIAK3D) is outside this oracle")
+    if max(types) > 0:                                                 # :959-962
+        return setCApproxIAK3D(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, setupMats,
+                               quirk_cd1_unscaled=quirk_cd1_unscaled)
     p = parsBTfmd
     xid, did = setupMats["xid"], setupMats["did"]
     n = xid.size
@@ -531,8 +598,8 @@ def setCIAK3D(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cme
 def setCIAK3D2(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, setupMats):
     """fitIAK3D.R:1117-1252.  Cross-covariance [set1 rows x set2 cols]; no cme (:1243)."""
     types = (sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1)
-    if max(types) > 0:
-        raise NotImplementedError("spline sdfd (setCApproxIAK3D2) is outside this oracle")
+    if max(types) > 0:                                                 # :1121-1124
+        return setCApproxIAK3D2(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, setupMats)
     p = parsBTfmd
     xid, did, xid2, did2 = setupMats["xid"], setupMats["did"], setupMats["xid2"], setupMats["did2"]
     Dx = setupMats["Dx"]
@@ -562,6 +629,123 @@ def setCIAK3D2(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cm
         K = phix1[xid[:, None], xid2[None, :]]
         C = C + p["cx1"] * K                                           # :1219
         C = C + p["cxd1"] * K * cxd1[0][dd]                            # :1222/1224
+    return C
+
+
+# ---------------------------------------------------------------------------
+# spline-sd approximation  C = avCor * avsd(I) * avsd(J)  (fitIAK3D.R:1448-1468, 1919-2233)
+# ---------------------------------------------------------------------------
+def iasdfd(dI, sdfdPars, sdfdType, XsdfdSpline=None):
+    """fitIAK3D.R:1448-1468: increment-averaged sd function on the intervals dI."""
+    dI = np.asarray(dI, float).reshape(-1, 2)
+    if sdfdType == 0 or sdfdType == -9:
+        return np.ones(dI.shape[0])
+    if sdfdType == -1:
+        sp = np.asarray(sdfdPars, float).reshape(-1)
+        return (1 - sp[0]) - (sp[0] / sp[1]) * (np.exp(-sp[1] * dI[:, 1]) - np.exp(-sp[1] * dI[:, 0])) / (dI[:, 1] - dI[:, 0])
+    if sdfdType > 0:
+        return np.asarray(XsdfdSpline, float) @ np.concatenate([[1.0], np.asarray(sdfdPars, float).reshape(-1)])
+    raise ValueError("sdfd option not yet programmed")
+
+
+def _approx_components(p, modelx, types, dIU, spl):
+    """avsd vectors of the three components on one set of unique intervals (None: the stationary table is used as is)."""
+    out = []
+    for nm, t in zip(("cd1", "cxd0", "cxd1"), types):
+        if t == 0 or (nm == "cd1" and t == -9) or (nm == "cxd1" and modelx == "nugget"):
+            out.append(None)
+        else:
+            out.append(iasdfd(dIU, p["sdfdPars_" + nm], t, None if spl is None else spl.get(nm)))
+    return out
+
+
+def setCApproxIAK3D(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, setupMats,
+                    quirk_cd1_unscaled=True):
+    """fitIAK3D.R:1919-2085.  -> (C, sigma2Vec) or (None, None)."""
+    types = (sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1)
+    p = parsBTfmd
+    xid, did = setupMats["xid"], setupMats["did"]
+    n = xid.size
+    C = np.zeros((n, n))
+    C[np.diag_indices(n)] = p["cme"]                                   # :1932
+    same = (xid[:, None] == xid[None, :])
+    C += p["cx0"] * same                                               # :1935
+    if modelx in ("matern", "spherical", "wendland"):
+        phix1 = spatialCovIAK3D(setupMats["Dx"], [1.0, p["ax"], p["nux"]], modelx)
+        if phix1 is None:
+            return None, None
+    else:
+        phix1 = None
+    phidStat, avVardStat = iaCovMatern(setupMats["dIU"], p["ad"], p["nud"], np.array([1.0, 0.0, 1.0]), 0)   # :1946
+    sd = _approx_components(p, modelx, types, setupMats["dIU"], setupMats.get("XsdfdSplineU"))
+    phid, avVar = [], []
+    nd = setupMats["dIU"].shape[0]
+    iu = np.triu_indices(nd)
+    for c, s_ in enumerate(sd):
+        absent = (c == 0 and types[0] == -9) or (c == 2 and modelx == "nugget")
+        if absent:
+            phid.append(None); avVar.append(0.0)
+        elif s_ is None:
+            phid.append(phidStat); avVar.append(avVardStat)
+        else:
+            if np.min(s_) < 0:                                         # :1994
+                return None, None
+            T = np.zeros((nd, nd))
+            # packed upper storage: element (i <= j) times avsd[j] then avsd[i]  (:1963)
+            T[iu] = (phidStat[iu] * s_[iu[1]]) * s_[iu[0]]
+            T = np.triu(T) + np.triu(T, 1).T
+            phid.append(T); avVar.append(s_ ** 2)
+    dd = (did[:, None], did[None, :])
+    C += p["cxd0"] * same * phid[1][dd]                                # :1998
+    if types[0] == 0:
+        C += p["cd1"] * phidStat[dd]                                   # :2007
+    elif types[0] != -9:
+        C += (1.0 if quirk_cd1_unscaled else p["cd1"]) * phid[0][dd]   # :2011 (sic: no cd1 multiplier)
+    if modelx != "nugget":
+        K = phix1[xid[:, None], xid[None, :]]
+        C += p["cx1"] * K                                              # :2026
+        C += p["cxd1"] * K * phid[2][dd]                               # :2029-2033
+    s2 = p["cx0"] + p["cx1"] + p["cd1"] * avVar[0] + p["cxd0"] * avVar[1] + p["cxd1"] * avVar[2] + p["cme"]   # :2041
+    s2 = np.broadcast_to(s2, (nd,))[did]
+    return C, np.array(s2)
+
+
+def setCApproxIAK3D2(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, setupMats):
+    """fitIAK3D.R:2095-2233."""
+    types = (sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1)
+    p = parsBTfmd
+    xid, did, xid2, did2 = setupMats["xid"], setupMats["did"], setupMats["xid2"], setupMats["did2"]
+    Dx = setupMats["Dx"]
+    K0 = (Dx == 0).astype(float)[xid[:, None], xid2[None, :]]          # :2110-2117
+    C = p["cx0"] * K0
+    if modelx in ("matern", "spherical", "wendland"):
+        phix1 = spatialCovIAK3D(Dx, [1.0, p["ax"], p["nux"]], modelx)
+        if phix1 is None:
+            return None
+    else:
+        phix1 = None
+    phidStat = iaCovMatern2(setupMats["dIU"], setupMats["dIU2"], p["ad"], p["nud"], np.array([1.0, 0.0, 1.0]), 0)   # :2128
+    sd1 = _approx_components(p, modelx, types, setupMats["dIU"], setupMats.get("XsdfdSplineU"))
+    sd2 = _approx_components(p, modelx, types, setupMats["dIU2"], setupMats.get("XsdfdSplineU2"))
+    phid = []
+    for c in range(3):
+        absent = (c == 0 and types[0] == -9) or (c == 2 and modelx == "nugget")
+        if absent:
+            phid.append(None)
+        elif sd1[c] is None:
+            phid.append(phidStat)
+        else:
+            if min(np.min(sd1[c]), np.min(sd2[c])) < 0:                # :2172
+                return None
+            phid.append((phidStat * sd1[c][:, None]) * sd2[c][None, :])   # :2140
+    dd = (did[:, None], did2[None, :])
+    C = C + p["cxd0"] * K0 * phid[1][dd]                               # :2181
+    if types[0] != -9:
+        C = C + p["cd1"] * phid[0][dd]                                 # :2186-2191
+    if modelx != "nugget":
+        K = phix1[xid[:, None], xid2[None, :]]
+        C = C + p["cx1"] * K                                           # :2199
+        C = C + p["cxd1"] * K * phid[2][dd]                            # :2202-2205
     return C
 
 
@@ -754,10 +938,11 @@ def predictIAK3D(xMap, dIMap, XMap_fn, lmmFit, modelx, sdfdTypes, cmeOpt, nxPerB
             idx = np.arange(b0, min(b0 + nxPerBatch, nx))
             dIThis = np.repeat(dIMap[i:i + 1], idx.size, axis=0)        # :150
             XMapThis = XMap_fn(i, idx)
-            sm = setupIAK3D(xMap[idx], dIThis)                          # :179
+            knots = lmmFit.get("sdfdKnots")
+            sm = setupIAK3D(xMap[idx], dIThis, sdfdTypes, knots)        # :179
             Ck, _ = setCIAK3D(P, modelx, *sdfdTypes, cmeOpt, sm)        # :183
             Ckk = np.diag(Ck)                                           # :189
-            sm2 = setupIAK3D2(xMap[idx], dIThis, lmmFit["xData"], lmmFit["dIData"])   # :192
+            sm2 = setupIAK3D2(xMap[idx], dIThis, lmmFit["xData"], lmmFit["dIData"], sdfdTypes, knots)   # :192
             Ckh = setCIAK3D2(P, modelx, *sdfdTypes, cmeOpt, sm2)        # :197
             CkhiCX = Ckh @ iCX; CkhiCz = Ckh @ iCz; CkhiC = Ckh @ iC    # :202
             q = np.sum(CkhiC * Ckh, axis=1)                             # :208

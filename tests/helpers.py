@@ -41,3 +41,27 @@ def scaled_err(a, b):
 
 def oracle_setup(ds):
     return orc.setupIAK3D(ds["xData"], ds["dIData"])
+
+
+# spline sd functions (sdfdType > 0 -> setCApproxIAK3D): knots and parameter sets used by the CPU and GPU tests
+SPLINE_KNOTS = dict(bdryKnots=(0.0, 1.6), intKnots_cd1=np.array([0.2, 0.7]), intKnots_cxd0=np.array([0.15, 0.45, 1.0]),
+                    intKnots_cxd1=np.array([0.5]))
+# (label, kind, types, spline coefficient lists per component)
+SPLINE_CASES = [
+    ("all-spline", "matern0.5", (2, 3, 1), dict(sdfdPars_cd1=[0.8, 0.55], sdfdPars_cxd0=[1.1, 0.7, 0.4], sdfdPars_cxd1=[0.6])),
+    ("mixed-stat-exp-spline", "matern1.5", (0, -1, 1), dict(sdfdPars_cd1=[], sdfdPars_cxd0=[0.6, 1.7], sdfdPars_cxd1=[0.35])),
+    ("edgeroi-no-cd1", "edgeroi", (-9, 3, 0), dict(sdfdPars_cd1=[], sdfdPars_cxd0=[0.9, 0.8, 0.5], sdfdPars_cxd1=[])),
+    ("nugget-spline", "nugget", (2, 3, 0), dict(sdfdPars_cd1=[1.2, 0.9], sdfdPars_cxd0=[0.9, 0.8, 0.5], sdfdPars_cxd1=[])),
+]
+
+
+def spline_case_pars(kind, types, coefs, nud=0.5):
+    P, modelx, _, cmeOpt = synth.default_pars(kind, False)
+    P = dict(P); P["nud"] = nud
+    for k, v in coefs.items():
+        P[k] = np.asarray(v, float)
+    if types[0] == -9:
+        P["cd1"] = 0.0
+    elif P.get("cd1", 0.0) == 0.0:
+        P["cd1"] = 0.15
+    return P, modelx, types, cmeOpt

@@ -35,10 +35,24 @@ def test_exports_every_declared_symbol():
     assert sorted(_lib.EXPORTS) == declared, "the ctypes prototypes and the header disagree"
 
 
-def test_pars_struct_layout():
-    # struct iak3d_pars: 6 int32 + 10 doubles + 6 doubles + 1 double, natural alignment
-    assert C.sizeof(_lib.Pars) == 24 + 8 * 17
-    assert _lib.Pars.ax.offset == 24 and _lib.Pars.sdfdPars.offset == 24 + 80
+def test_pars_struct_layout(tmp_path):
+    """struct iak3d_pars as gcc lays it out from include/iak3d.h == the ctypes mirror, field by field."""
+    import shutil
+    import subprocess
+    fields = [f[0] for f in _lib.Pars._fields_]
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not on PATH")
+    src = tmp_path / "layout.c"
+    body = "".join(f'  printf("{f} %zu\\n", offsetof(iak3d_pars, {f}));\n' for f in fields)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "iak3d.h"\nint main(void) {\n'
+                   '  printf("sizeof %zu\\n", sizeof(iak3d_pars));\n' + body + '  return 0;\n}\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    assert int(out["sizeof"]) == C.sizeof(_lib.Pars)
+    for f in fields:
+        assert int(out[f]) == getattr(_lib.Pars, f).offset, f
+    assert _lib.MAX_SPL == 12
 
 
 def test_sass_is_sm100a_with_tma_and_dmma():
