@@ -49,6 +49,10 @@ _PROTOS = {
     "iak3d_dataset_info": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i32)]),
     "iak3d_dataset_ids": (C.c_int, [_vp, _ip, _ip]),
     "iak3d_dataset_set_sdfd_spline": (C.c_int, [_vp, _i32, _i32, _dp]),
+    "iak3d_dataset_set_lnN_column": (C.c_int, [_vp, _i32]),
+    "iak3d_cov_diag": (C.c_int, [_vp, C.POINTER(Pars), _dp]),
+    "iak3d_fit_create_res": (C.c_int, [_vp, C.POINTER(Pars), _dp, _dp, _dp, C.POINTER(_vp)]),
+    "iak3d_predict_fetch_terms": (C.c_int, [_vp, _dp, _dp, _dp, _dp]),
     "iak3d_cov_cross_spl": (C.c_int, [_vp, C.POINTER(Pars), _i64, _dp, _dp, C.POINTER(_dp), _dp]),
     "iak3d_predict_stage_spl": (C.c_int, [_vp, _i64, _dp, _dp, _dp, C.POINTER(_dp)]),
     "iak3d_iacov": (C.c_int, [_vp, _i64, _dp, _i64, _dp, C.c_double, C.c_double, _i32, _dp, _dp, _dp]),

@@ -332,6 +332,175 @@ def lndetANDinvCb(Cm, b=None, ctx=None):
 
 
 # ---------------------------------------------------------------------------------------------
+# lognormal data (lnTfmdData = TRUE): setmuIAK3D, calcbetavXbeta, nrUpdatesIAK3DlnN in the Gram domain
+# ---------------------------------------------------------------------------------------------
+def calcbetavXbeta(vX, beta):
+    """fitIAK3D.R:1314-1328: beta' vX_i beta for every observation; vX is (n pU) x pU (blocks stacked)."""
+    beta = np.asarray(beta, float).reshape(-1)
+    pU = beta.size
+    if pU == 0:
+        return np.zeros((0, 1))
+    vX = np.asarray(vX, float).reshape(-1, pU)
+    n = vX.shape[0] // pU
+    return ((vX @ beta).reshape(n, pU) @ beta).reshape(n, 1)
+
+
+def setmuIAK3D(XData, vXU, iU, beta, diagC, sigma2Vec):
+    """fitIAK3D.R:1261-1267."""
+    beta = np.asarray(beta, float).reshape(-1, 1)
+    n = XData.shape[0]
+    bvb = calcbetavXbeta(vXU, beta[list(iU), 0]) if len(iU) else np.zeros((n, 1))
+    return XData @ beta + 0.5 * (np.asarray(sigma2Vec, float).reshape(n, 1) - np.asarray(diagC, float).reshape(n, 1) + bvb)
+
+
+def lnN_design(XData, zData, vXU, iU):
+    """F = [X, z, s, V_ab (a <= b over iU)]: every vector nrUpdatesIAK3DlnN ever multiplies by iC or TK is a linear
+    combination of these columns -- resU = z - XU betaU - (s + sum w_ab V_ab) / 2 with s = sigma2Vec - diag(C), and
+    XU + dbetavXbeta (nrUpdatesIAK3DlnN.R:188-207) -- so ONE bordered factorisation with W = F returns everything the
+    Newton iteration needs as the q x q Gram matrix F' iC F (no explicit iC or TK, which the reference forms, :22,63).
+    The s column depends on the covariance parameters: it is filled on the device (iak3d_dataset_set_lnN_column)."""
+    n, p = XData.shape
+    pU = len(iU)
+    cols = [XData, np.asarray(zData, float).reshape(n, 1), np.zeros((n, 1))]
+    pairs = [(a, b) for a in range(pU) for b in range(a, pU)]
+    if pU:
+        v = np.asarray(vXU, float).reshape(n, pU, pU)
+        if not np.allclose(v, np.transpose(v, (0, 2, 1)), rtol=1e-12, atol=0):
+            raise ValueError("vXU: the within-support covariance blocks must be symmetric")
+        cols += [v[:, a, b].reshape(n, 1) for (a, b) in pairs]
+    F = np.column_stack(cols)
+    if F.shape[1] > 64:
+        raise ValueError("lognormal data: p + 2 + pU (pU + 1) / 2 must not exceed 64")
+    return F, pairs
+
+
+def nrUpdatesIAK3DlnN_gram(G, lndetC, n, p, iU, pairs):
+    """nrUpdatesIAK3DlnN + gradHessIAK3DlnN (nrUpdatesIAK3DlnN.R:1-226) on G = F' iC F (see :func:`lnN_design`).
+    u' iC v = cu' G cv and u' TK v = cu' GT cv with GT = G - G[:,K] G[K,K]^-1 G[K,:] for vectors u = F cu, v = F cv.
+    The Hessian branch of the reference (`checkHess$cholC` on the result of solve(), :109) cannot run as written; the
+    evident intent is implemented: Newton step from the third update on, Fisher scoring if the Hessian solve fails."""
+    G = 0.5 * (G + G.T)                                                # :31
+    q = G.shape[0]
+    iU = list(iU); pU = len(iU)
+    iK = [j for j in range(p) if j not in iU]
+    zc, sc = p, p + 1
+    vcol = {pr: p + 2 + k for k, pr in enumerate(pairs)}
+    vcol.update({(b, a): c for (a, b), c in list(vcol.items())})
+    e = lambda j: np.eye(q)[:, j]
+    XiCX = G[:p, :p]
+    if pU == 0:                                                        # :37-50
+        c = e(zc) - 0.5 * e(sc)
+        XiCz = G[:p, :] @ c
+        beta = np.linalg.solve(XiCX, XiCz).reshape(-1, 1)
+        res = float(c @ G @ c - 2.0 * (beta[:, 0] @ XiCz) + beta[:, 0] @ XiCX @ beta[:, 0])
+        return dict(betahat=beta, nll=0.5 * (n * math.log(2.0 * math.pi) + lndetC + res), grad=None, hess=None, fim=-XiCX,
+                    noits=0, errFlag=0)
+    betaU = np.linalg.solve(XiCX, G[:p, zc])[iU]                       # :60
+    if iK:
+        GKK = G[np.ix_(iK, iK)]
+        GT = G - G[:, iK] @ np.linalg.solve(GKK, G[iK, :])             # TK, :62-64
+    else:
+        GKK, GT = None, G
+
+    def gh(bU, GTm=GT, K=iK, U=iU, lnd=lndetC):
+        cres = e(zc) - 0.5 * e(sc)                                     # resU, :194
+        ca = []
+        for a, ja in enumerate(U):
+            cres = cres - bU[a] * e(ja)
+            c = e(ja)
+            for b in range(len(U)):
+                c = c + bU[b] * e(vcol[(a, b)])                        # XU + dbetavXbeta, :204-207
+                cres = cres - 0.5 * bU[a] * bU[b] * e(vcol[(a, b)])    # betavXbeta / 2
+            ca.append(c)
+        Ca = np.column_stack(ca)
+        Tres = GTm @ cres
+        nll = 0.5 * (n * math.log(2.0 * math.pi) + lnd + float(cres @ Tres))      # :213
+        grad = -(Ca.T @ Tres)                                          # :215
+        fim = Ca.T @ GTm @ Ca                                          # :222
+        vT = np.array([[Tres[vcol[(a, b)]] for b in range(len(U))] for a in range(len(U))])
+        hess = -vT + fim                                               # :217-220
+        betahat = np.full((p, 1), np.nan)
+        betahat[U, 0] = bU
+        if K:
+            betahat[K, 0] = np.linalg.solve(GKK, G[K, :] @ cres)      # :199
+        return nll, grad, 0.5 * (hess + hess.T), 0.5 * (fim + fim.T), betahat
+
+    nllNew, grad, hess, fim, betahat = gh(betaU)
+    tol, noits, nllPrev = 1e-6, 0, math.inf
+    while noits < 20 and (nllNew < nllPrev - tol or noits < 4):        # :94
+        nllPrev = nllNew
+        step = None
+        if noits >= 2:
+            try:
+                step = np.linalg.solve(hess, grad)
+            except np.linalg.LinAlgError:
+                step = None
+        if step is None:
+            try:
+                step = np.linalg.solve(fim, grad)
+            except np.linalg.LinAlgError:
+                return dict(betahat=betahat, nll=nllNew, grad=grad, hess=hess, fim=fim, noits=noits, errFlag=1)
+        betaU = betaU - step
+        nllNew, grad, hess, fim, betahat = gh(betaU)
+        noits += 1
+    rnd = tol * 10                                                     # :160-161
+    return dict(betahat=betahat, nll=float(np.round(nllNew / rnd) * rnd), nll_unrounded=nllNew, grad=grad, hess=hess, fim=fim, noits=noits,
+                errFlag=2 if noits == 20 else 0, gh=gh)
+
+
+def _nll_lnN(pars, zData, XData, vXU, iU, sm, P, parsBTfmd, modelx, types, cmeOpt, rtnAll, attachBigMats):
+    """lnTfmdData branch of nllIAK3D (fitIAK3D.R:762-781, 919-945).  iU is 0-based."""
+    n, p = XData.shape
+    iU = [] if iU is None else [int(j) for j in iU]
+    F, pairs = lnN_design(XData, zData, vXU, iU)
+    ctx = sm.ctx
+    sm.set_W(F)
+    ctx.check(ctx.lib.iak3d_dataset_set_lnN_column(sm.h, p + 1))
+    q = F.shape[1]
+    lnd = C.c_double(); G = np.empty((q, q), order="F")
+    try:
+        st = ctx.check(ctx.lib.iak3d_nll_terms(sm.h, C.byref(P), C.byref(lnd), dptr(G), None), allow=(NOT_SPD, BAD_PARS))
+    finally:
+        ctx.check(ctx.lib.iak3d_dataset_set_lnN_column(sm.h, -1))
+    bad = dict(nll=BADNLL, pars=pars, parsBTfmd=parsBTfmd, betahat=None, vbetahat=None, cxdhat=float("nan")) if rtnAll else BADNLL
+    if st != OK:
+        return bad
+    nr = nrUpdatesIAK3DlnN_gram(np.array(G), lnd.value, n, p, iU, pairs)
+    nll = nr["nll"] if np.isfinite(nr["nll"]) else BADNLL
+    if not rtnAll:
+        return nll
+    betahat = nr["betahat"]
+    # vbetahat = solve(fim) with every column treated as varying and TK = iC (fitIAK3D.R:768-773)
+    Gs = 0.5 * (np.array(G) + np.array(G).T)
+    ca = []
+    vcol = {pr: p + 2 + k for k, pr in enumerate(pairs)}
+    vcol.update({(b, a): c for (a, b), c in list(vcol.items())})
+    for j in range(p):
+        c = np.eye(q)[:, j]
+        if j in iU:
+            a = iU.index(j)
+            for b, jb in enumerate(iU):
+                c = c + betahat[jb, 0] * np.eye(q)[:, vcol[(a, b)]]
+        ca.append(c)
+    Ca = np.column_stack(ca)
+    vbetahat = np.linalg.inv(Ca.T @ Gs @ Ca)
+    s2 = np.empty(n); dC = np.empty(n)
+    ctx.check(ctx.lib.iak3d_cov_build(sm.h, C.byref(P), None, dptr(s2)))
+    ctx.check(ctx.lib.iak3d_cov_diag(sm.h, C.byref(P), dptr(dC)))
+    muhat = setmuIAK3D(XData, vXU, iU, betahat, dC, s2)                # :921
+    out = dict(nll=nll, pars=pars, parsBTfmd=parsBTfmd, betahat=betahat, vbetahat=vbetahat, cxdhat=1.0, sigma2Vec=s2, XData=XData,
+               zData=zData, vXU=vXU, iU=iU, lndetA=lnd.value, modelx=modelx, nud=parsBTfmd["nud"], sdfdType_cd1=types[0],
+               sdfdType_cxd0=types[1], sdfdType_cxd1=types[2], cmeOpt=cmeOpt, setupMats=sm, xData=sm.xData, dIData=sm.dIData,
+               lnTfmdData=True, diagC=dC, noits=nr["noits"], errFlag=nr["errFlag"], nll_unrounded=nr.get("nll_unrounded", nll))
+    sm.set_W(np.column_stack([XData, zData]))
+    if attachBigMats:
+        fit = KeptFit(sm, parsBTfmd, modelx, types, cmeOpt, betahat, vbetahat, 1.0, z_muhat=zData.reshape(-1, 1) - muhat)
+        iCX, iCz = fit.get_small()
+        out.update(fit=fit, iCX=iCX, iCz_muhat=iCz)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 # likelihood
 # ---------------------------------------------------------------------------------------------
 def _small_chol_solve(A, b):
@@ -392,9 +561,9 @@ def _symm_upper(M):
 def nllIAK3D(pars, zData, XData, vXU=None, iU=None, modelx="matern", nud=0.5, sdfdType_cd1=0, sdfdType_cxd0=0, sdfdType_cxd1=0,
              cmeOpt=0, prodSum=True, setupMats=None, parBnds=None, useReml=True, lnTfmdData=False, rtnAll=False,
              forCompLik=False, attachBigMats=False, nCores=8, parsBTfmd=None):
-    """fitIAK3D.R:670-949 (lnTfmdData = FALSE).  `parsBTfmd` may be passed to skip the transform."""
-    if lnTfmdData:
-        raise NotImplementedError("lnTfmdData = TRUE (nrUpdatesIAK3DlnN) is not on the accelerated path")
+    """fitIAK3D.R:670-949.  `parsBTfmd` may be passed to skip the transform.  With lnTfmdData = TRUE (no profiling of
+    the variance, no REML: :147-155) `iU` holds the 0-based columns of XData that vary inside the sample supports and
+    `vXU` their (n pU) x pU within-support covariances."""
     if setupMats is None:
         raise ValueError("setupMats (from setupIAK3D) is required")
     sm = setupMats
@@ -402,8 +571,15 @@ def nllIAK3D(pars, zData, XData, vXU=None, iU=None, modelx="matern", nud=0.5, sd
     XData = np.asarray(XData, float).reshape(zData.size, -1)
     n, p = XData.shape
     if parsBTfmd is None:
-        parsBTfmd = readParsIAK3D(pars, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds)
+        parsBTfmd = readParsIAK3D(pars, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds,
+                                  lnTfmdData=lnTfmdData)
     parsBTfmd = dict(parsBTfmd)
+    if lnTfmdData:
+        if forCompLik:
+            raise ValueError("composite likelihood is not defined for lognormal data (fitIAK3D.R:135-140)")
+        P = make_pars(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt)
+        return _nll_lnN(pars, zData, XData, vXU, iU, sm, P, parsBTfmd, modelx, (sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1), cmeOpt,
+                        rtnAll, attachBigMats)
     sm.set_W(np.column_stack([XData, zData]))                      # W <- cbind(XData, zData), :757
     P = make_pars(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt)
     ctx = sm.ctx
@@ -616,7 +792,7 @@ def gradHessIAK3D(setupMats, parsBTfmd, modelx, sdfdTypes, lnvPars):
 class KeptFit:
     """The big matrices of lmmFit (C, iC, iCX, iCz_muhat) as a factorisation kept on the device (iak3d_fit)."""
 
-    def __init__(self, setupMats, parsBTfmd, modelx, sdfdTypes, cmeOpt, betahat, vbetahat, cxdhat=1.0):
+    def __init__(self, setupMats, parsBTfmd, modelx, sdfdTypes, cmeOpt, betahat, vbetahat, cxdhat=1.0, z_muhat=None):
         sm = setupMats
         self.sm, self.ctx = sm, sm.ctx
         self.p = sm.q - 1
@@ -624,7 +800,12 @@ class KeptFit:
         P = make_pars(parsBTfmd, modelx, *sdfdTypes, cmeOpt, quirk_scale=cxdhat)
         b = f64(np.asarray(betahat, float).reshape(-1)); V = f64(np.asarray(vbetahat, float).reshape(self.p, self.p))
         h = C.c_void_p()
-        st = self.ctx.check(self.ctx.lib.iak3d_fit_create(sm.h, C.byref(P), dptr(b), dptr(V), C.byref(h)), allow=(NOT_SPD, BAD_PARS))
+        if z_muhat is not None:        # lognormal data: the residual is z - setmuIAK3D(...), not z - X betahat
+            r = f64(np.asarray(z_muhat, float).reshape(-1))
+            st = self.ctx.check(self.ctx.lib.iak3d_fit_create_res(sm.h, C.byref(P), dptr(b), dptr(V), dptr(r), C.byref(h)),
+                                allow=(NOT_SPD, BAD_PARS))
+        else:
+            st = self.ctx.check(self.ctx.lib.iak3d_fit_create(sm.h, C.byref(P), dptr(b), dptr(V), C.byref(h)), allow=(NOT_SPD, BAD_PARS))
         if st != OK:
             raise Iak3dError("fit_create: the fitted covariance matrix is not positive definite" if st == NOT_SPD
                              else "fit_create: invalid parameters")
@@ -668,6 +849,12 @@ class KeptFit:
         self.ctx.check(self.ctx.lib.iak3d_predict_fetch(self.h, dptr(z), dptr(v)))
         return z, v
 
+    def fetch_terms(self):
+        """Ckk, sigma2Veck, CkhiCz_muhat, CkhiCChk of the last enqueued batch (predictIAK3D.R:183-208)."""
+        out = [np.empty(self._m) for _ in range(4)]
+        self.ctx.check(self.ctx.lib.iak3d_predict_fetch_terms(self.h, *[dptr(a) for a in out]))
+        return dict(Ckk=out[0], sigma2Veck=out[1], CkhiCz_muhat=out[2], CkhiCChk=out[3])
+
     def close(self):
         if getattr(self, "h", None) is not None and self.h.value:
             self.ctx.lib.iak3d_fit_destroy(self.h)
@@ -680,15 +867,17 @@ class KeptFit:
             pass
 
 
-def predictIAK3D(xMap, dIMap, XMap_fn, lmmFit, nxPerBatch=2000, cells=None):
-    """predictIAK3D.R:5-287 for compLikOptn = 0, lnTfmdData = FALSE.  `lmmFit` is the rtnAll/attachBigMats dict of
-    :func:`nllIAK3D`; `XMap_fn(iDepth, cellIdx)` supplies the design rows (makeXvX is an input of the hot path).
-    Rows of XMap containing NaN are skipped and stay NaN (predictIAK3D.R:160-163).  `cells` restricts the work to a
-    slice of the map (prediction-grid tiles per GPU).  -> dict(zMap, vMap, pi90LMap, pi90UMap) [ndIMap x nxMap]."""
+def predictIAK3D(xMap, dIMap, XMap_fn, lmmFit, nxPerBatch=2000, cells=None, vXUMap_fn=None, rqrBTfmdPreds=True):
+    """predictIAK3D.R:5-287 for compLikOptn = 0.  `lmmFit` is the rtnAll/attachBigMats dict of :func:`nllIAK3D`;
+    `XMap_fn(iDepth, cellIdx)` supplies the design rows (makeXvX is an input of the hot path) and, for lognormal data,
+    `vXUMap_fn(iDepth, cellIdx)` their within-support covariances ((m pU) x pU).  Rows of XMap containing NaN are skipped
+    and stay NaN (predictIAK3D.R:160-163).  `cells` restricts the work to a slice of the map (prediction-grid tiles per
+    GPU).  -> dict(zMap, vMap, pi90LMap, pi90UMap) [ndIMap x nxMap]."""
     xMap = np.asarray(xMap, float).reshape(len(xMap), -1)
     dIMap = np.round(np.asarray(dIMap, float).reshape(-1, 2), 2)       # :29
     nd, nx = dIMap.shape[0], xMap.shape[0]
     fit = lmmFit["fit"]
+    lnN = bool(lmmFit.get("lnTfmdData", False))
     idx_all = np.arange(nx) if cells is None else np.asarray(cells)
     zMap = np.full((nd, nx), np.nan); vMap = np.full((nd, nx), np.nan)
     for i in range(nd):
@@ -699,7 +888,22 @@ def predictIAK3D(xMap, dIMap, XMap_fn, lmmFit, nxPerBatch=2000, cells=None):
         sel = idx_all[ok]
         dI = np.repeat(dIMap[i:i + 1], sel.size, axis=0)                # :150
         z, v = fit.predict(xMap[sel], dI, XM[ok])
+        if lnN:                                                         # :229-255
+            t = fit.fetch_terms()
+            iU = lmmFit["iU"]
+            vX = None
+            if len(iU):
+                pU = len(iU)
+                vX = np.asarray(vXUMap_fn(i, idx_all), float).reshape(idx_all.size, pU, pU)[ok].reshape(-1, pU)
+            mu = setmuIAK3D(XM[ok], vX, iU, lmmFit["betahat"], t["Ckk"], t["sigma2Veck"]).reshape(-1)
+            z = mu + t["CkhiCz_muhat"]
+            v = t["Ckk"] - t["CkhiCChk"]                                # no beta uncertainty in the lognormal case (:251)
         zMap[i, sel] = z; vMap[i, sel] = v
     with np.errstate(invalid="ignore"):
-        s = np.sqrt(vMap)
-    return dict(zMap=zMap, vMap=vMap, pi90LMap=zMap - 1.645 * s, pi90UMap=zMap + 1.645 * s)   # :272-273
+        s_ = np.sqrt(vMap)
+    lo, hi = zMap - 1.645 * s_, zMap + 1.645 * s_                       # :272-273
+    if lnN and rqrBTfmdPreds:                                           # :276-284
+        zMap = np.exp(zMap + 0.5 * vMap)
+        lo, hi = np.exp(lo), np.exp(hi)
+        vMap = (np.exp(vMap) - 1.0) * zMap ** 2
+    return dict(zMap=zMap, vMap=vMap, pi90LMap=lo, pi90UMap=hi)

@@ -243,7 +243,7 @@ extern "C" int64_t iak3d_launch_count(iak3d_ctx* ctx) { return ctx ? ctx->launch
 static void free_slot(Slot* s) {
   if (!s) return;
   cudaFree(s->d_L); cudaFree(s->d_phix); cudaFree(s->d_phid); cudaFree(s->d_invd); cudaFree(s->d_flags);
-  cudaFree(s->d_logsum); cudaFree(s->d_G);
+  cudaFree(s->d_logsum); cudaFree(s->d_G); cudaFree(s->d_lncol);
   delete s;
 }
 
@@ -398,47 +398,47 @@ int iak_get_slot(iak3d_ds* ds, size_t k, Slot** out) {
 // `cache` (optional) de-duplicates tables inside one batch: the npar+1 evaluations of a forward-difference gradient
 // differ in one parameter each, so all but one share the horizontal table and all but one the depth tables.
 struct TableCache {
-  struct Entry { const iak3d_ds* ds; int kind; double k[6]; const double* ptr; };
+  struct Entry { const iak3d_ds* ds; int kind; double k[6]; const double* ptr; const double* av; };
   std::vector<Entry> e;
-  const double* find(const iak3d_ds* ds, int kind, const double* k) const {
+  const double* find(const iak3d_ds* ds, int kind, const double* k, const double** av = nullptr) const {
     for (const Entry& x : e)
-      if (x.ds == ds && x.kind == kind && memcmp(x.k, k, sizeof(x.k)) == 0) return x.ptr;
+      if (x.ds == ds && x.kind == kind && memcmp(x.k, k, sizeof(x.k)) == 0) { if (av) *av = x.av; return x.ptr; }
     return nullptr;
   }
-  void add(const iak3d_ds* ds, int kind, const double* k, const double* ptr) {
-    Entry x; x.ds = ds; x.kind = kind; memcpy(x.k, k, sizeof(x.k)); x.ptr = ptr; e.push_back(x);
+  void add(const iak3d_ds* ds, int kind, const double* k, const double* ptr, const double* av = nullptr) {
+    Entry x; x.ds = ds; x.kind = kind; memcpy(x.k, k, sizeof(x.k)); x.ptr = ptr; x.av = av; e.push_back(x);
   }
 };
 
 int iak_square_tables(iak3d_ctx* ctx, const iak3d_ds* ds, const EvalPlan& pl, Slot* s, CovArgs* a, TableCache* cache = nullptr) {
   const int64_t nd = ds->ndIU, nx = ds->nxU;
   double* const avbase = s->d_phid + (size_t)NTAB_BUF * nd * nd;
-  for (int k = 0; k < 3; k++) a->T[k] = nullptr;
-  auto plain_table = [&](int k, int buf, const double** out) -> int {   // iaCovMatern on the unique intervals
+  for (int k = 0; k < 3; k++) { a->T[k] = nullptr; a->av[k] = nullptr; }
+  auto plain_table = [&](int k, int buf, const double** out, const double** avout) -> int {   // iaCovMatern on the unique intervals
     const IaPrm& P = pl.prm[k];
     const double key[6] = {P.psi, P.tau0, P.tau1, P.tau2, P.g11[1], P.g11[2]};     // (ad, nud, sd function) determine the table
-    const double* hit = cache ? cache->find(ds, 1, key) : nullptr;
+    const double* hit = cache ? cache->find(ds, 1, key, avout) : nullptr;
     if (hit != nullptr) { *out = hit; return 0; }
     double* T = s->d_phid + (size_t)buf * nd * nd;
     const int st = launch_iacov_table(ctx, P, ds->d_dIU, nd, ds->d_dIU, nd, T, avbase + (size_t)buf * nd);
     if (st != 0) return st;
-    *out = T;
-    if (cache) cache->add(ds, 1, key, T);
+    *out = T; *avout = avbase + (size_t)buf * nd;
+    if (cache) cache->add(ds, 1, key, T, *avout);
     return 0;
   };
   if (!pl.approx) {
     for (int k = 0; k < pl.ntab; k++) {
-      const int st = plain_table(k, k, &a->T[k]);
+      const int st = plain_table(k, k, &a->T[k], &a->av[k]);
       if (st != 0) return st;
     }
   } else {
     // setCApproxIAK3D (fitIAK3D.R:1919-2085): the stationary table, then avCor * avsd(I) * avsd(J) per component
     int ksrc = -1;
     for (int k = 0; k < pl.ntab; k++) if (pl.sd_type[k] == 0) ksrc = k;
-    const double* src = nullptr;
-    const int st0 = plain_table(ksrc >= 0 ? ksrc : 0, ksrc >= 0 ? ksrc : NTAB_BUF - 1, &src);
+    const double* src = nullptr; const double* srcav = nullptr;
+    const int st0 = plain_table(ksrc >= 0 ? ksrc : 0, ksrc >= 0 ? ksrc : NTAB_BUF - 1, &src, &srcav);
     if (st0 != 0) return st0;
-    if (ksrc >= 0) a->T[ksrc] = src;
+    if (ksrc >= 0) { a->T[ksrc] = src; a->av[ksrc] = srcav; }
     std::vector<double> sv;
     for (int k = 0; k < pl.ntab; k++) {
       if (pl.sd_type[k] == 0) continue;
@@ -451,7 +451,7 @@ int iak_square_tables(iak3d_ctx* ctx, const iak3d_ds* ds, const EvalPlan& pl, Sl
       double* T = s->d_phid + (size_t)k * nd * nd;
       const int st2 = launch_scale_table(ctx, src, d_s, nd, d_s, nd, 1, T, avbase + (size_t)k * nd);
       if (st2 != 0) return st2;
-      a->T[k] = T;
+      a->T[k] = T; a->av[k] = avbase + (size_t)k * nd;
     }
   }
   for (int c = 0; c < 3; c++) a->tidx[c] = pl.tidx[c];
@@ -473,6 +473,24 @@ int iak_square_tables(iak3d_ctx* ctx, const iak3d_ds* ds, const EvalPlan& pl, Sl
   a->xid_r = ds->d_xid; a->did_r = ds->d_did; a->xid_c = ds->d_xid; a->did_c = ds->d_did;
   a->nr = ds->n; a->nc = ds->n; a->nxU_r = nx; a->ndIU_r = nd;
   return 0;
+}
+
+// sigma2Vec - diag(C) of one evaluation into s->d_lncol[0..n)
+int iak_lnN_column(iak3d_ctx* ctx, const iak3d_ds* ds, const EvalPlan& pl, const CovArgs& a, Slot* s) {
+  const int64_t n = ds->n;
+  if (s->d_lncol == nullptr) CUDA_TRY(ctx, cudaMalloc(&s->d_lncol, (size_t)2 * n * sizeof(double)));
+  int st = launch_sigma2(ctx, pl, a.av, ds->d_did, n, s->d_lncol);
+  if (st != 0) return st;
+  st = launch_ckk(ctx, pl, a.T, ds->ndIU, ds->d_did, n, s->d_lncol + n);
+  if (st != 0) return st;
+  return launch_vec_sub(ctx, s->d_lncol, s->d_lncol + n, n, s->d_lncol);
+}
+
+extern "C" int iak3d_dataset_set_lnN_column(iak3d_ds* ds, int32_t col) {
+  if (!ds) return IAK3D_ERR_ARG;
+  if (col >= 64) { ds->ctx->err = "dataset_set_lnN_column: column out of range"; return IAK3D_ERR_ARG; }
+  ds->lncol = col < 0 ? -1 : col;
+  return IAK3D_OK;
 }
 
 // ================================================================================================
@@ -564,7 +582,7 @@ extern "C" int iak3d_cov_build(iak3d_ds* ds, const iak3d_pars* pars, double* C, 
     }
     if (sigma2Vec) {
       if (cudaMalloc(&ds2, (size_t)n * 8) != cudaSuccess) { ctx->err = "cov_build: allocation failed"; rc = IAK3D_ERR_CUDA; cudaGetLastError(); break; }
-      rc = launch_sigma2(ctx, pl, s->d_phid + (size_t)NTAB_BUF * ds->ndIU * ds->ndIU, ds->ndIU, ds->d_did, n, ds2);
+      rc = launch_sigma2(ctx, pl, a.av, ds->d_did, n, ds2);
       if (rc != 0) break;
       cudaMemcpyAsync(sigma2Vec, ds2, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
     }
@@ -573,6 +591,30 @@ extern "C" int iak3d_cov_build(iak3d_ds* ds, const iak3d_pars* pars, double* C, 
   } while (0);
   cudaFree(dC); cudaFree(ds2);
   return rc;
+}
+
+extern "C" int iak3d_cov_diag(iak3d_ds* ds, const iak3d_pars* pars, double* diagC) {
+  if (!ds || !pars || !diagC) return IAK3D_ERR_ARG;
+  iak3d_ctx* ctx = ds->ctx;
+  cudaSetDevice(ctx->device);
+  EvalPlan pl;
+  int st = iak_make_plan(ctx, pars, true, &pl);
+  if (st == 0) st = iak_plan_check_avsd(ctx, ds, &pl);
+  if (st != 0) return st;
+  if (pl.status != 0) return pl.status;
+  Slot* s = nullptr;
+  st = iak_get_slot(ds, 0, &s);
+  if (st != 0) return st;
+  CovArgs a;
+  st = iak_square_tables(ctx, ds, pl, s, &a);
+  if (st != 0) return st;
+  const int64_t n = ds->n;
+  if (s->d_lncol == nullptr) CUDA_TRY(ctx, cudaMalloc(&s->d_lncol, (size_t)2 * n * sizeof(double)));
+  st = launch_ckk(ctx, pl, a.T, ds->ndIU, ds->d_did, n, s->d_lncol + n);
+  if (st != 0) return st;
+  CUDA_TRY(ctx, cudaMemcpyAsync(diagC, s->d_lncol + n, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return IAK3D_OK;
 }
 
 // Cross-covariance tables between set 1 (given as unique tables + ids on the device) and a dataset (set 2).
@@ -852,7 +894,13 @@ extern "C" int iak3d_nll_terms_batch_enqueue(iak3d_ctx* ctx, int32_t count, iak3
   for (int i = 0; i < count; i++) {
     if (!live[i]) continue;
     Slot* s = b->slots[i];
-    st = launch_cov_factor_layout(ctx, cargs[i], dss[i]->d_W, q, s->n, s->Npad, s->ld, s->nCB, s->d_L);
+    if (dss[i]->lncol >= 0 && dss[i]->lncol < q) {
+      // lognormal data: column lncol of W is sigma2Vec - diag(C) of THIS evaluation (nrUpdatesIAK3DlnN.R:15, 194)
+      st = iak_lnN_column(ctx, dss[i], plans[i], cargs[i], s);
+      if (st != 0) return st;
+    }
+    st = launch_cov_factor_layout(ctx, cargs[i], dss[i]->d_W, q, s->n, s->Npad, s->ld, s->nCB, s->d_L,
+                                  dss[i]->lncol >= 0 ? s->d_lncol : nullptr, dss[i]->lncol);
     if (st != 0) return st;
   }
   CUDA_TRY(ctx, cudaEventRecord(ctx->evs[2], ctx->stream));

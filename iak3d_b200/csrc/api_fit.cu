@@ -53,6 +53,8 @@ struct iak3d_fit {
   std::vector<double> spl1U[3];  // spline sd basis of the map supports' unique intervals (nd1 x ncol), setCApproxIAK3D2
   double* d_s = nullptr;         // averaged-sd vectors: 3 x (nd1cap + ndIU2) cross + 3 x nd1cap self
   double* d_z = nullptr; double* d_v = nullptr; double* d_ckk = nullptr;
+  double* d_cz = nullptr; double* d_qf = nullptr; double* d_s2k = nullptr;   // CkhiCz_muhat, rowSums(CkhiC * Ckh), sigma2Veck
+  double* d_avself = nullptr;    // NTAB_BUF x nd1cap: avVarVec of the map supports' self tables
   int64_t cap_m = 0;
   // ---- panel workspace (one chunk) ----
   int64_t ldP = 0;
@@ -73,12 +75,13 @@ struct iak3d_fit {
 
 static void fit_free_job(iak3d_fit* f) {
   cudaFree(f->d_xy); cudaFree(f->d_X); cudaFree(f->d_did1); cudaFree(f->d_dIU1); cudaFree(f->d_z); cudaFree(f->d_v); cudaFree(f->d_ckk);
-  f->d_xy = f->d_X = f->d_dIU1 = f->d_z = f->d_v = f->d_ckk = nullptr; f->d_did1 = nullptr; f->cap_m = 0;
+  cudaFree(f->d_cz); cudaFree(f->d_qf); cudaFree(f->d_s2k);
+  f->d_xy = f->d_X = f->d_dIU1 = f->d_z = f->d_v = f->d_ckk = f->d_cz = f->d_qf = f->d_s2k = nullptr; f->d_did1 = nullptr; f->cap_m = 0;
 }
 static void fit_free_panel(iak3d_fit* f) {
   cudaFree(f->d_P); cudaFree(f->d_G); cudaFree(f->d_pflags); cudaFree(f->d_phix); cudaFree(f->d_same); cudaFree(f->d_T);
-  cudaFree(f->d_Tself); cudaFree(f->d_iota); cudaFree(f->d_tasks); cudaFree(f->d_s);
-  f->d_P = f->d_G = f->d_phix = f->d_T = f->d_Tself = f->d_s = nullptr; f->d_pflags = nullptr; f->d_same = nullptr; f->d_iota = nullptr;
+  cudaFree(f->d_Tself); cudaFree(f->d_iota); cudaFree(f->d_tasks); cudaFree(f->d_s); cudaFree(f->d_avself);
+  f->d_P = f->d_G = f->d_phix = f->d_T = f->d_Tself = f->d_s = f->d_avself = nullptr; f->d_pflags = nullptr; f->d_same = nullptr; f->d_iota = nullptr;
   f->d_tasks = nullptr; f->ldP = 0; f->nd1cap = 0; f->tasks_rows = 0;
 }
 
@@ -95,6 +98,11 @@ extern "C" int iak3d_fit_destroy(iak3d_fit* f) {
 }
 
 extern "C" int iak3d_fit_create(iak3d_ds* ds, const iak3d_pars* pars, const double* betahat, const double* vbetahat, iak3d_fit** out) {
+  return iak3d_fit_create_res(ds, pars, betahat, vbetahat, nullptr, out);
+}
+
+extern "C" int iak3d_fit_create_res(iak3d_ds* ds, const iak3d_pars* pars, const double* betahat, const double* vbetahat,
+                                    const double* z_muhat, iak3d_fit** out) {
   if (!ds || !pars || !out) return IAK3D_ERR_ARG;
   *out = nullptr;
   iak3d_ctx* ctx = ds->ctx;
@@ -111,7 +119,8 @@ extern "C" int iak3d_fit_create(iak3d_ds* ds, const iak3d_pars* pars, const doub
   const int64_t n = ds->n; const int p = f->p, q = f->q;
   // W2 = [X, z - X betahat]  (predictIAK3D.R:111,134)
   std::vector<double> W2(ds->h_W, ds->h_W + (size_t)n * q);
-  for (int64_t i = 0; i < n; i++) {
+  if (z_muhat != nullptr) memcpy(&W2[(size_t)p * n], z_muhat, (size_t)n * 8);
+  else for (int64_t i = 0; i < n; i++) {
     double mu = 0.0;
     for (int a = 0; a < p; a++) mu = mu + ds->h_W[(size_t)a * n + i] * betahat[a];
     W2[(size_t)p * n + i] = ds->h_W[(size_t)p * n + i] - mu;
@@ -212,7 +221,8 @@ static int fit_reserve_panel(iak3d_fit* f, int64_t rows, int64_t nd1) {
   }
   if (nd1 > f->nd1cap) {
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(f->d_T); cudaFree(f->d_Tself); cudaFree(f->d_s); f->d_T = f->d_Tself = f->d_s = nullptr;
+    cudaFree(f->d_T); cudaFree(f->d_Tself); cudaFree(f->d_s); cudaFree(f->d_avself); f->d_T = f->d_Tself = f->d_s = f->d_avself = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&f->d_avself, (size_t)NTAB_BUF * nd1 * 8));
     CUDA_TRY(ctx, cudaMalloc(&f->d_T, (size_t)NTAB_BUF * nd1 * f->ds->ndIU * 8));
     CUDA_TRY(ctx, cudaMalloc(&f->d_Tself, (size_t)NTAB_BUF * nd1 * nd1 * 8));
     CUDA_TRY(ctx, cudaMalloc(&f->d_s, (size_t)(3 * (nd1 + f->ds->ndIU) + 3 * nd1) * 8));
@@ -261,6 +271,9 @@ extern "C" int iak3d_predict_stage_spl(iak3d_fit* f, int64_t m, const double* xy
     CUDA_TRY(ctx, cudaMalloc(&f->d_z, (size_t)m * 8));
     CUDA_TRY(ctx, cudaMalloc(&f->d_v, (size_t)m * 8));
     CUDA_TRY(ctx, cudaMalloc(&f->d_ckk, (size_t)m * 8));
+    CUDA_TRY(ctx, cudaMalloc(&f->d_cz, (size_t)m * 8));
+    CUDA_TRY(ctx, cudaMalloc(&f->d_qf, (size_t)m * 8));
+    CUDA_TRY(ctx, cudaMalloc(&f->d_s2k, (size_t)m * 8));
     f->cap_m = m;
   }
   // unique depth intervals of the map supports (usually one per call: predictIAK3D.R:150)
@@ -306,23 +319,25 @@ extern "C" int iak3d_predict_enqueue(iak3d_fit* f) {
   // depth tables: cross (nd1 x nd2) and self (nd1 x nd1, for Ckk)
   CovArgs a;
   const double* Tself[3] = {nullptr, nullptr, nullptr};
+  const double* avself[3] = {nullptr, nullptr, nullptr};
   rc = iak_cross_depth_tables(ctx, ds, px, f->d_dIU1, f->h_dIU1.data(), nd1, f->spl1U, f->d_T, f->d_s, a.T);
   if (rc != 0) return rc;
   if (!ps.approx) {
     for (int k = 0; k < ps.ntab; k++) {
       double* Ts = f->d_Tself + (size_t)k * nd1 * nd1;
-      rc = launch_iacov_table(ctx, ps.prm[k], f->d_dIU1, nd1, f->d_dIU1, nd1, Ts, nullptr);
+      rc = launch_iacov_table(ctx, ps.prm[k], f->d_dIU1, nd1, f->d_dIU1, nd1, Ts, f->d_avself + (size_t)k * nd1);
       if (rc != 0) return rc;
-      Tself[k] = Ts;
+      Tself[k] = Ts; avself[k] = f->d_avself + (size_t)k * nd1;
     }
   } else {
     // Ckk = diag(setCApproxIAK3D(map supports)) (predictIAK3D.R:183; fitIAK3D.R:959-962)
     int ksrc = -1;
     for (int k = 0; k < ps.ntab; k++) if (ps.sd_type[k] == 0) ksrc = k;
-    double* src = f->d_Tself + (size_t)(ksrc >= 0 ? ksrc : NTAB_BUF - 1) * nd1 * nd1;
-    rc = launch_iacov_table(ctx, ps.prm[0], f->d_dIU1, nd1, f->d_dIU1, nd1, src, nullptr);
+    const int bsrc = ksrc >= 0 ? ksrc : NTAB_BUF - 1;
+    double* src = f->d_Tself + (size_t)bsrc * nd1 * nd1;
+    rc = launch_iacov_table(ctx, ps.prm[0], f->d_dIU1, nd1, f->d_dIU1, nd1, src, f->d_avself + (size_t)bsrc * nd1);
     if (rc != 0) return rc;
-    if (ksrc >= 0) Tself[ksrc] = src;
+    if (ksrc >= 0) { Tself[ksrc] = src; avself[ksrc] = f->d_avself + (size_t)bsrc * nd1; }
     std::vector<double> s1;
     for (int k = 0; k < ps.ntab; k++) {
       if (ps.sd_type[k] == 0) continue;
@@ -333,12 +348,14 @@ extern "C" int iak3d_predict_enqueue(iak3d_fit* f) {
       double* dsv = f->d_s + (size_t)3 * (nd1 + nd2) + (size_t)k * nd1;
       CUDA_TRY(ctx, cudaMemcpyAsync(dsv, s1.data(), (size_t)nd1 * 8, cudaMemcpyHostToDevice, ctx->stream));
       double* Ts = f->d_Tself + (size_t)k * nd1 * nd1;
-      rc = launch_scale_table(ctx, src, dsv, nd1, dsv, nd1, 1, Ts, nullptr);
+      rc = launch_scale_table(ctx, src, dsv, nd1, dsv, nd1, 1, Ts, f->d_avself + (size_t)k * nd1);
       if (rc != 0) return rc;
-      Tself[k] = Ts;
+      Tself[k] = Ts; avself[k] = f->d_avself + (size_t)k * nd1;
     }
   }
   rc = launch_ckk(ctx, ps, Tself, nd1, f->d_did1, m, f->d_ckk);
+  if (rc != 0) return rc;
+  rc = launch_sigma2(ctx, ps, avself, f->d_did1, m, f->d_s2k);
   if (rc != 0) return rc;
   for (int c = 0; c < 3; c++) a.tidx[c] = px.tidx[c];
   a.ntab = px.ntab;
@@ -368,7 +385,7 @@ extern "C" int iak3d_predict_enqueue(iak3d_fit* f) {
     rc = launch_tile_tasks(ctx, f->d_prob, f->d_tasks, f->ntasks, f->d_ticket);
     if (rc != 0) return rc;
     rc = launch_krige_finish(ctx, f->d_G, rowsP, f->q, f->d_X + r0, m, rows, f->d_ckk + r0, f->d_beta, f->d_vbeta, f->d_z + r0,
-                             f->d_v + r0);
+                             f->d_v + r0, f->d_cz + r0, f->d_qf + r0);
     if (rc != 0) return rc;
   }
   CUDA_TRY(ctx, cudaMemcpyAsync(f->h_status, f->d_status, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -386,6 +403,21 @@ extern "C" int iak3d_predict_fetch(iak3d_fit* f, double* z, double* v) {
   if (v) CUDA_TRY(ctx, cudaMemcpyAsync(v, f->d_v, (size_t)f->m * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   if (f->h_status[1] != 0) { ctx->err = "kriging: dependency wait timed out (internal error)"; return IAK3D_ERR_TIMEOUT; }
+  return IAK3D_OK;
+}
+
+extern "C" int iak3d_predict_fetch_terms(iak3d_fit* f, double* Ckk, double* sigma2Veck, double* CkhiCz_muhat, double* CkhiCChk) {
+  if (!f) return IAK3D_ERR_ARG;
+  iak3d_ctx* ctx = f->ctx;
+  if (!f->staged) { ctx->err = "predict_fetch_terms: nothing staged"; return IAK3D_ERR_ARG; }
+  cudaSetDevice(ctx->device);
+  if (f->m == 0) return IAK3D_OK;
+  const size_t bytes = (size_t)f->m * 8;
+  if (Ckk) CUDA_TRY(ctx, cudaMemcpyAsync(Ckk, f->d_ckk, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (sigma2Veck) CUDA_TRY(ctx, cudaMemcpyAsync(sigma2Veck, f->d_s2k, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (CkhiCz_muhat) CUDA_TRY(ctx, cudaMemcpyAsync(CkhiCz_muhat, f->d_cz, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (CkhiCChk) CUDA_TRY(ctx, cudaMemcpyAsync(CkhiCChk, f->d_qf, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return IAK3D_OK;
 }
 

@@ -67,6 +67,7 @@ struct Slot {
   int32_t* d_flags = nullptr;     // done[nRB*nCB] + invdone[nCB]
   double* d_logsum = nullptr;     // nCB
   double* d_G = nullptr;          // 64*64 Gram accumulator (WiAW)
+  double* d_lncol = nullptr;      // 2n: sigma2Vec - diag(C) (lognormal bias column of W) | scratch
   int32_t epoch = 0;              // flags are valid when == epoch
 };
 
@@ -79,6 +80,7 @@ struct iak3d_ds {
   std::vector<double> h_xU, h_dIU;       // nxU x 2, ndIU x 2 (column-major)
   std::vector<double> h_spl[3];          // XsdfdSplineU_{cd1,cxd0,cxd1}: ndIU x spl_ncol[c] column-major (iaCovMatern.R:520-539)
   int32_t spl_ncol[3] = {0, 0, 0};
+  int32_t lncol = -1;                    // column of W replaced by sigma2Vec - diag(C) at every evaluation (lognormal data)
   double* h_W = nullptr;                 // n x q column-major copy in PINNED host memory: staging of the H2D copy
   int32_t *d_xid = nullptr, *d_did = nullptr;
   double *d_xU = nullptr, *d_dIU = nullptr;   // column-major nxU x 2 / ndIU x 2
@@ -130,6 +132,7 @@ int hx_init(HxPrm* H, int modelx, double a, double nu);   // returns 2 when the 
 struct CovArgs {
   // value(i,j) = [same loc](cx0 + cxd0*T0) + kd1*Td + phix*(cx1 + cxd1*T1) + (i==j)*cme
   const double* T[3];      // distinct depth tables (may alias); T[tidx[c]] for c = cd1, cxd0, cxd1; tidx<0 = absent
+  const double* av[3] = {nullptr, nullptr, nullptr};   // avVarVec of each table on the row set (square builds only)
   int tidx[3];
   int ntab;
   const double* phix;      // horizontal table or nullptr (nugget)
@@ -139,12 +142,15 @@ struct CovArgs {
   int64_t nr, nc;          // live rows / cols
   int64_t nxU_r, ndIU_r;   // leading dims of tables (row-id extent)
 };
+// d_lncol / lncol: column `lncol` of W is taken from the vector d_lncol instead (lognormal bias column, see api.cu)
 int launch_cov_factor_layout(iak3d_ctx* ctx, const CovArgs& a, const double* d_W, int32_t q, int64_t n, int64_t Npad, int64_t ld,
-                             int32_t nCB, double* d_L);
+                             int32_t nCB, double* d_L, const double* d_lncol = nullptr, int lncol = -1);
+// out = a - b (n doubles)
+int launch_vec_sub(iak3d_ctx* ctx, const double* d_a, const double* d_b, int64_t n, double* d_out);
 // generic symmetric matrix (host-supplied C, optim_functions.R:268) + b' rows into the factor layout
 int launch_pack_factor_layout(iak3d_ctx* ctx, const double* d_C, int64_t n, const double* d_b, int32_t q, int64_t Npad,
                               int64_t ld, double* d_L);
-int launch_sigma2(iak3d_ctx* ctx, const EvalPlan& pl, const double* d_avvar /* NTAB_BUF x ndIU */, int64_t ndIU, const int32_t* d_did,
+int launch_sigma2(iak3d_ctx* ctx, const EvalPlan& pl, const double* const* d_av /* per table: avVarVec */, const int32_t* d_did,
                   int64_t n, double* d_out);
 // setCApproxIAK3D[2]: out(i,j) = (src(i,j) * s1(i)) * s2(j) (rectangular, fitIAK3D.R:2146) or, symmetric, the packed-upper
 // order of :1963  (src * s[max(i,j)]) * s[min(i,j)];  avvar1 = s1^2 when not null
@@ -185,4 +191,5 @@ int launch_backsolve(iak3d_ctx* ctx, const double* d_L, int64_t nRU, int64_t Npa
 int launch_peak(iak3d_ctx* ctx, int kind, double* tflops);
 // kriging epilogue (predictIAK3D.R:229-255): z, v from the bordered-row accumulators G (ldG x (q+1))
 int launch_krige_finish(iak3d_ctx* ctx, const double* d_G, int64_t ldG, int32_t q, const double* d_XMap, int64_t ldX, int64_t m,
-                        const double* d_Ckk, const double* d_beta, const double* d_vbeta, double* d_z, double* d_v);
+                        const double* d_Ckk, const double* d_beta, const double* d_vbeta, double* d_z, double* d_v,
+                        double* d_cz = nullptr, double* d_qf = nullptr);

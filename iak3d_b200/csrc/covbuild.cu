@@ -67,7 +67,8 @@ __device__ __forceinline__ double cov_value(const CovDev& a, int xi, int di, int
 // ---- factor-layout build: lower-triangular TM x TN tiles of the padded, BLOCKED factor buffer (common.cuh) ----
 // rows [0,n) data, [n,Npad) identity padding, [Npad,Npad+q) the W' rows (bordered system), rest zero.
 __global__ void __launch_bounds__(256) cov_factor_kernel(CovDev a, const double* __restrict__ W, int q, int64_t n,
-                                                         int64_t Npad, double* __restrict__ L, int64_t ld, int nCB) {
+                                                         int64_t Npad, double* __restrict__ L, int64_t ld, int nCB,
+                                                         const double* __restrict__ lncol_v, int lncol) {
   __shared__ __align__(16) int32_t s_xr[TM], s_dr[TM], s_xc[TN], s_dc[TN];
   __shared__ __align__(8) uint64_t bar;
   // decode (r, j) from the linear lower-triangular tile index: column-block j has row-blocks j/2 .. nRB-1
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(256) cov_factor_kernel(CovDev a, const double*
       if (i < c) val = 0.0;                                             // strictly upper: never read
       else if (c >= n) val = (i == c && c < Npad) ? 1.0 : 0.0;          // identity padding columns
       else if (i < n) val = cov_value(a, xi, di, xj, dj, i == c);
-      else if (i >= Npad && i < Npad + q) val = W[(int64_t)(i - Npad) * n + c];   // W' rows
+      else if (i >= Npad && i < Npad + q) val = (i - Npad == lncol) ? lncol_v[c] : W[(int64_t)(i - Npad) * n + c];   // W' rows
       else val = 0.0;
       v[e] = val;
     }
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(256) cov_factor_kernel(CovDev a, const double*
 }
 
 int launch_cov_factor_layout(iak3d_ctx* ctx, const CovArgs& h, const double* d_W, int32_t q, int64_t n, int64_t Npad, int64_t ld,
-                             int32_t nCB_, double* d_L) {
+                             int32_t nCB_, double* d_L, const double* d_lncol, int lncol) {
   CovDev a;
   for (int k = 0; k < 3; k++) { a.T[k] = h.T[k]; a.tidx[k] = h.tidx[k]; }
   a.ntab = h.ntab; a.phix = h.phix; a.same = h.same;
@@ -184,7 +185,7 @@ int launch_cov_factor_layout(iak3d_ctx* ctx, const CovArgs& h, const double* d_W
   for (int64_t c = 0; c < nCB; c++) tiles += nRB - c / 2;
   // (a variant that staged the depth-table columns of a tile in shared memory was measured 2x slower than these
   //  L1-served gathers at ndIU = 266 -- 140 us vs 68 us for n = 5000 -- and was dropped.)
-  cov_factor_kernel<<<(unsigned)tiles, 256, 0, ctx->stream>>>(a, d_W, q, n, Npad, d_L, ld, (int)nCB);
+  cov_factor_kernel<<<(unsigned)tiles, 256, 0, ctx->stream>>>(a, d_W, q, n, Npad, d_L, ld, (int)nCB, d_lncol, d_lncol ? lncol : -1);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return 0;
@@ -265,15 +266,14 @@ int launch_pack_factor_layout(iak3d_ctx* ctx, const double* d_C, int64_t n, cons
 }
 
 // ---- sigma2Vec (fitIAK3D.R:1083-1086) ------------------------------------------------------------------
-struct S2Dev { double cxd0, cxd1, cme, cx0, cx1, cd1; int t0, t1, td; int approx; };
-__global__ void sigma2_kernel(S2Dev a, const double* __restrict__ av, int64_t ndIU, const int32_t* __restrict__ did, int64_t n,
-                              double* __restrict__ out) {
+struct S2Dev { double cxd0, cxd1, cme, cx0, cx1, cd1; const double *av0, *av1, *avd; int approx; };
+__global__ void sigma2_kernel(S2Dev a, const int32_t* __restrict__ did, int64_t n, double* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int d = did[i];
-  const double a0 = a.t0 >= 0 ? av[(int64_t)a.t0 * ndIU + d] : 0.0;
-  const double a1 = a.t1 >= 0 ? av[(int64_t)a.t1 * ndIU + d] : 0.0;
-  const double ad = a.td >= 0 ? av[(int64_t)a.td * ndIU + d] : 0.0;
+  const double a0 = a.av0 ? a.av0[d] : 0.0;
+  const double a1 = a.av1 ? a.av1[d] : 0.0;
+  const double ad = a.avd ? a.avd[d] : 0.0;
   double v;
   if (a.approx) {                    // setCApproxIAK3D's order (fitIAK3D.R:2056)
     v = a.cx0 + a.cx1;
@@ -287,11 +287,23 @@ __global__ void sigma2_kernel(S2Dev a, const double* __restrict__ av, int64_t nd
   }
   out[i] = v;
 }
-int launch_sigma2(iak3d_ctx* ctx, const EvalPlan& pl, const double* d_avvar, int64_t ndIU, const int32_t* d_did, int64_t n,
-                  double* d_out) {
+int launch_sigma2(iak3d_ctx* ctx, const EvalPlan& pl, const double* const* d_av, const int32_t* d_did, int64_t n, double* d_out) {
   if (n == 0) return 0;
-  S2Dev a{pl.cxd0, pl.cxd1, pl.cme, pl.cx0, pl.cx1, pl.cd1, pl.tidx[1], pl.tidx[2], pl.tidx[0], pl.approx ? 1 : 0};
-  sigma2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(a, d_avvar, ndIU, d_did, n, d_out);
+  auto pick = [&](int t) -> const double* { return t >= 0 ? d_av[t] : nullptr; };
+  S2Dev a{pl.cxd0, pl.cxd1, pl.cme, pl.cx0, pl.cx1, pl.cd1, pick(pl.tidx[1]), pick(pl.tidx[2]), pick(pl.tidx[0]), pl.approx ? 1 : 0};
+  sigma2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(a, d_did, n, d_out);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return 0;
+}
+
+__global__ void vec_sub_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t n, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] - b[i];
+}
+int launch_vec_sub(iak3d_ctx* ctx, const double* d_a, const double* d_b, int64_t n, double* d_out) {
+  if (n == 0) return 0;
+  vec_sub_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_a, d_b, n, d_out);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return 0;
@@ -334,7 +346,8 @@ int launch_ckk(iak3d_ctx* ctx, const EvalPlan& pl, const double* const* d_Tself,
 //   z = XMap betahat + G(:,p);  v = Ckk - G(:,p+1) + (XMap - CkhiCX) vbetahat (XMap - CkhiCX)'
 __global__ void krige_finish_kernel(const double* __restrict__ G, int64_t ldG, int q, const double* __restrict__ XMap, int64_t ldX,
                                     int64_t m, const double* __restrict__ Ckk, const double* __restrict__ beta,
-                                    const double* __restrict__ vbeta, double* __restrict__ z, double* __restrict__ v) {
+                                    const double* __restrict__ vbeta, double* __restrict__ z, double* __restrict__ v,
+                                    double* __restrict__ cz, double* __restrict__ qf) {
   extern __shared__ double sh[];
   const int p = q - 1;
   double* sb = sh; double* sv = sh + p;
@@ -353,13 +366,16 @@ __global__ void krige_finish_kernel(const double* __restrict__ G, int64_t ldG, i
     quad = quad + (XMap[(int64_t)a * ldX + i] - G[(int64_t)a * ldG + i]) * s;
   }
   v[i] = Ckk[i] - G[(int64_t)q * ldG + i] + quad;
+  if (cz != nullptr) cz[i] = G[(int64_t)p * ldG + i];
+  if (qf != nullptr) qf[i] = G[(int64_t)q * ldG + i];
 }
 int launch_krige_finish(iak3d_ctx* ctx, const double* d_G, int64_t ldG, int32_t q, const double* d_XMap, int64_t ldX, int64_t m,
-                        const double* d_Ckk, const double* d_beta, const double* d_vbeta, double* d_z, double* d_v) {
+                        const double* d_Ckk, const double* d_beta, const double* d_vbeta, double* d_z, double* d_v, double* d_cz,
+                        double* d_qf) {
   if (m == 0) return 0;
   const int p = q - 1;
   krige_finish_kernel<<<(unsigned)((m + 127) / 128), 128, (size_t)(p + p * p) * sizeof(double), ctx->stream>>>(
-      d_G, ldG, q, d_XMap, ldX, m, d_Ckk, d_beta, d_vbeta, d_z, d_v);
+      d_G, ldG, q, d_XMap, ldX, m, d_Ckk, d_beta, d_vbeta, d_z, d_v, d_cz, d_qf);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return 0;

@@ -92,6 +92,10 @@ IAK3D_API int iak3d_dataset_ids(iak3d_ds* ds, int32_t* xid, int32_t* did);
  * (0 cd1, 1 cxd0, 2 cxd1) on the dataset's UNIQUE depth intervals (first-occurrence order), ndIU x ncol column-major,
  * ncol = sdfdType + 1.  Needed before any evaluation whose sdfdType[comp] > 0. */
 IAK3D_API int iak3d_dataset_set_sdfd_spline(iak3d_ds* ds, int32_t comp, int32_t ncol, const double* XsplU);
+/* Lognormal data (lnTfmdData = TRUE; nrUpdatesIAK3DlnN.R:11-16,194): column `col` (0-based) of W is overwritten on the
+ * device, at every evaluation, by sigma2Vec - diag(C) of that evaluation's parameters -- the bias term of the
+ * lognormal mean, which changes with the covariance parameters.  col < 0 switches this off (default). */
+IAK3D_API int iak3d_dataset_set_lnN_column(iak3d_ds* ds, int32_t col);
 
 /* ---- depth / horizontal kernels on unique pairs ---------------------------------------------
  * iaCovMatern2 (iaCovMatern.R:107-191): out is n1 x n2 column-major; avVar (n1) may be NULL
@@ -107,6 +111,8 @@ IAK3D_API int iak3d_spatial_cov(iak3d_ctx* ctx, int64_t m, const double* D, int3
  * setCIAK3D (fitIAK3D.R:955-1112): C (n x n, full symmetric, may be NULL) and sigma2Vec (n, may
  * be NULL). */
 IAK3D_API int iak3d_cov_build(iak3d_ds* ds, const iak3d_pars* pars, double* C, double* sigma2Vec);
+/* diag(setCIAK3D(pars)$C) only (n): what setmuIAK3D needs of C (fitIAK3D.R:921, 1261-1267) */
+IAK3D_API int iak3d_cov_diag(iak3d_ds* ds, const iak3d_pars* pars, double* diagC);
 /* setCIAK3D2 (fitIAK3D.R:1117-1252): cross-covariance between set 1 (n1 rows given here) and the
  * dataset (set 2); out is n1 x n, no cme (fitIAK3D.R:1243). */
 IAK3D_API int iak3d_cov_cross(iak3d_ds* ds2, const iak3d_pars* pars, int64_t n1, const double* xy1,
@@ -143,6 +149,10 @@ IAK3D_API int iak3d_nll_terms_batch_fetch(iak3d_ctx* ctx, double* lndetA, double
  * betahat (p), vbetahat (p x p).  Computes and keeps L = chol(C), iCX, iCz_muhat on the device. */
 IAK3D_API int iak3d_fit_create(iak3d_ds* ds, const iak3d_pars* pars, const double* betahat, const double* vbetahat,
                      iak3d_fit** out);
+/* the same with the residual z - muhat given by the caller (n): lognormal data, where muhat = setmuIAK3D(...)
+ * (fitIAK3D.R:1261-1267, 919-923) is not X betahat */
+IAK3D_API int iak3d_fit_create_res(iak3d_ds* ds, const iak3d_pars* pars, const double* betahat, const double* vbetahat,
+                         const double* z_muhat, iak3d_fit** out);
 IAK3D_API int iak3d_fit_destroy(iak3d_fit* fit);
 /* copies out what lmmFit carries: iCX (n x p), iCz_muhat (n), and optionally C and iC (n x n, NULL to skip) */
 IAK3D_API int iak3d_fit_get(iak3d_fit* fit, double* iCX, double* iCz_muhat, double* C, double* iC);
@@ -159,6 +169,11 @@ IAK3D_API int iak3d_predict_stage_spl(iak3d_fit* fit, int64_t m, const double* x
                             const double* const* Xspl1);
 IAK3D_API int iak3d_predict_enqueue(iak3d_fit* fit);
 IAK3D_API int iak3d_predict_fetch(iak3d_fit* fit, double* z, double* v);
+/* the pieces z and v are made of (predictIAK3D.R:183-208), each m long, any may be NULL: Ckk = diag(setCIAK3D(map)),
+ * sigma2Veck (its sigma2Vec), CkhiCz_muhat = Ckh iC (z - muhat), CkhiCChk = rowSums((Ckh iC) * Ckh).  Lognormal
+ * predictions (predictIAK3D.R:229-255, setmuIAK3D) and profilePredictIAK3D are assembled from these by the caller.
+ * Call after iak3d_predict_enqueue, before or after iak3d_predict_fetch. */
+IAK3D_API int iak3d_predict_fetch_terms(iak3d_fit* fit, double* Ckk, double* sigma2Veck, double* CkhiCz_muhat, double* CkhiCChk);
 
 /* ---- Newton-Raphson terms == gradHessIAK3D (nrUpdatesIAK3D.R:118-216) -----------------------
  * Components dA_i are the unit-variance terms of setCIAK3D in the order cx0, cx1, cd1, cxd0, cxd1,

@@ -918,9 +918,159 @@ def nllIAK3D_CL(pars, zData, XData, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sd
 
 
 # ---------------------------------------------------------------------------
+# lognormal data  (nrUpdatesIAK3DlnN.R:1-226; fitIAK3D.R:762-781, 1261-1328)
+# ---------------------------------------------------------------------------
+def calcbetavXbeta(vX, beta):
+    """fitIAK3D.R:1314-1328.  vX: (n p) x p stacked blocks; returns n x 1."""
+    beta = np.asarray(beta, float).reshape(-1, 1)
+    p = beta.shape[0]
+    if p == 0:
+        return np.zeros((0, 1))
+    vX = np.asarray(vX, float).reshape(-1, p)
+    n = vX.shape[0] // p
+    vXbeta = vX @ beta                                                  # :1317
+    out = np.zeros((n, 1))
+    for i in range(n):                                                  # tKTEMP %*% (kron(1_n, beta) * vXbeta), :1322-1323
+        out[i, 0] = float(np.sum(beta[:, 0] * vXbeta[i * p:(i + 1) * p, 0]))
+    return out
+
+
+def setmuIAK3D(XData, vXU, iU, beta, diagC, sigma2Vec):
+    """fitIAK3D.R:1261-1267 (iU 0-based)."""
+    beta = np.asarray(beta, float).reshape(-1, 1)
+    n = XData.shape[0]
+    bvb = calcbetavXbeta(vXU, beta[list(iU), 0]) if len(iU) else np.zeros((n, 1))
+    return XData @ beta + 0.5 * (np.asarray(sigma2Vec, float).reshape(n, 1) - np.asarray(diagC, float).reshape(n, 1) + bvb)
+
+
+def gradHessIAK3DlnN(zData, XData, vXU, iU, betaU, C, lndetC, TK, iXKiCXKXKiC, sigma2Vec):
+    """nrUpdatesIAK3DlnN.R:168-226, with the explicit n x n TK the reference forms (iU 0-based)."""
+    iU = list(iU); pU = len(iU)
+    n, p = XData.shape
+    iK = [j for j in range(p) if j not in iU]
+    betaU = np.asarray(betaU, float).reshape(-1, 1)
+    z = np.asarray(zData, float).reshape(n, 1)
+    betavXbeta = calcbetavXbeta(vXU, betaU[:, 0])                       # :186
+    XbetaU = XData[:, iU] @ betaU                                       # :188-192
+    resU = z - XbetaU - 0.5 * (np.asarray(sigma2Vec, float).reshape(n, 1) - np.diag(C).reshape(n, 1) + betavXbeta)   # :194
+    betahat = np.full((p, 1), np.nan)
+    betahat[iU, 0] = betaU[:, 0]
+    if iK:
+        betahat[iK, 0] = (iXKiCXKXKiC @ resU)[:, 0]                     # :199-201
+    vXUm = np.asarray(vXU, float).reshape(n * pU, pU)
+    dbetavXbeta = (vXUm @ betaU).reshape(n, pU)                         # :204-205
+    XUP = XData[:, iU] + dbetavXbeta                                    # :207
+    tmp = TK @ np.column_stack([resU, XUP])                             # :209
+    TKres, TKXUP = tmp[:, :1], tmp[:, 1:]
+    nll = float(0.5 * (n * math.log(2.0 * math.pi) + lndetC + (resU.T @ TKres)[0, 0]))   # :213
+    grad = -(XUP.T @ TKres)                                             # :215
+    vblocks = vXUm.reshape(n, pU, pU)
+    vXTKresU = np.einsum("iab,i->ba", vblocks, TKres[:, 0])             # :217-218 (column-major refill of a row-major vec)
+    fim = XUP.T @ TKXUP                                                 # :219,222
+    hess = -vXTKresU + fim                                              # :220
+    return dict(nll=nll, grad=grad, hess=hess, fim=fim, betahat=betahat)
+
+
+def nrUpdatesIAK3DlnN(zData, XData, vXU, iU, C, sigma2Vec):
+    """nrUpdatesIAK3DlnN.R:1-166 (iU 0-based).  The reference tests `checkHess$cholC` on the return value of solve()
+    (:109), which cannot run; as in the product the intended logic is restated: Newton step from the third update on,
+    Fisher scoring when that solve fails."""
+    iU = list(iU); pU = len(iU)
+    n, p = XData.shape
+    iK = [j for j in range(p) if j not in iU]
+    z = np.asarray(zData, float).reshape(n, 1)
+    s2 = np.asarray(sigma2Vec, float).reshape(n, 1)
+    if pU > 0:
+        W = np.column_stack([XData, z])                                 # :11-12
+    else:
+        W = np.column_stack([XData, z - 0.5 * (s2 - np.diag(C).reshape(n, 1))])   # :14
+    try:
+        R = sla.cholesky(C, lower=False, check_finite=False)
+    except sla.LinAlgError:
+        return dict(betahat=None, nll=float("nan"), errFlag=-123, noits=0)
+    iC = sla.cho_solve((R, False), np.eye(n), check_finite=False)       # :22 chol2inv(chol(C))
+    iCW = iC @ W
+    lndetC = 2.0 * float(np.sum(np.log(np.diag(R))))                    # :28 determinant(C)
+    WiCW = W.T @ iCW
+    WiCW = 0.5 * (WiCW + WiCW.T)                                        # :31
+    XiCX, XiCz, ziCz = WiCW[:p, :p], WiCW[:p, p:p + 1], float(WiCW[p, p])
+    if pU == 0:                                                         # :37-50
+        b = np.linalg.solve(XiCX, XiCz)
+        res = float(ziCz - 2.0 * (b.T @ XiCz)[0, 0] + (b.T @ XiCX @ b)[0, 0])
+        return dict(betahat=b, nll=0.5 * (n * math.log(2.0 * math.pi) + lndetC + res), fim=-XiCX, noits=0, errFlag=0, iC=iC)
+    betaU = np.linalg.solve(XiCX, XiCz)[iU].reshape(-1, 1)              # :60
+    if iK:
+        iX = np.linalg.solve(WiCW[np.ix_(iK, iK)], iCW[:, iK].T)        # :63
+        TK = iC - iCW[:, iK] @ iX                                       # :64
+    else:
+        iX, TK = None, iC
+    args = dict(zData=zData, XData=XData, vXU=vXU, iU=iU, C=C, lndetC=lndetC, TK=TK, iXKiCXKXKiC=iX, sigma2Vec=sigma2Vec)
+    sym = lambda M: 0.5 * (M + M.T)
+    t = gradHessIAK3DlnN(betaU=betaU, **args)
+    nllNew, grad, hess, fim, betahat = t["nll"], t["grad"], sym(t["hess"]), sym(t["fim"]), t["betahat"]
+    tol, noits, nllPrev = 1e-6, 0, math.inf
+    while noits < 20 and (nllNew < nllPrev - tol or noits < 4):         # :94
+        nllPrev = nllNew
+        step = None
+        if noits >= 2:
+            try:
+                step = np.linalg.solve(hess, grad)
+            except np.linalg.LinAlgError:
+                step = None
+        if step is None:
+            try:
+                step = np.linalg.solve(fim, grad)
+            except np.linalg.LinAlgError:
+                return dict(betahat=betahat, nll=nllNew, noits=noits, errFlag=1, iC=iC)
+        betaU = betaU - step
+        t = gradHessIAK3DlnN(betaU=betaU, **args)
+        nllNew, grad, hess, fim, betahat = t["nll"], t["grad"], sym(t["hess"]), sym(t["fim"]), t["betahat"]
+        noits += 1
+    rnd = tol * 10
+    return dict(betahat=betahat, nll=float(np.round(nllNew / rnd) * rnd), nll_unrounded=nllNew, grad=grad, hess=hess, fim=fim,
+                iC=iC, noits=noits, errFlag=2 if noits == 20 else 0)
+
+
+def nllIAK3D_lnN(pars, zData, XData, vXU, iU, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum,
+                 setupMats, parBnds, rtnAll=False, parsBTfmd=None):
+    """lnTfmdData = TRUE branch of nllIAK3D (fitIAK3D.R:762-781, 919-945); cxdhat = 1, C = A, ML only."""
+    zData = np.asarray(zData, float).reshape(-1)
+    XData = np.asarray(XData, float).reshape(zData.size, -1)
+    n, p = XData.shape
+    iU = [] if iU is None else list(iU)
+    if parsBTfmd is None:
+        parsBTfmd = readParsIAK3D(pars, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds,
+                                  lnTfmdData=True)
+    A, sigma2Vec = setCIAK3D(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, setupMats)
+    if A is None:
+        return dict(nll=BADNLL) if rtnAll else BADNLL
+    t = nrUpdatesIAK3DlnN(zData, XData, vXU, iU, A, sigma2Vec)
+    nll = t["nll"]
+    if not np.isfinite(nll):
+        return dict(nll=BADNLL) if rtnAll else BADNLL
+    if not rtnAll:
+        return nll
+    betahat = t["betahat"]
+    vXUTmp = np.zeros((n * p, p))                                       # :768-770
+    if iU:
+        v = np.asarray(vXU, float).reshape(n, len(iU), len(iU))
+        for i in range(n):
+            vXUTmp[np.ix_(i * p + np.array(iU), iU)] = v[i]
+    g = gradHessIAK3DlnN(zData, XData, vXUTmp, list(range(p)), betahat, A, 0.0, t["iC"], None, sigma2Vec)   # :771
+    vbetahat = np.linalg.inv(g["fim"])                                  # :773
+    muhat = setmuIAK3D(XData, vXU, iU, betahat, np.diag(A), sigma2Vec)  # :921
+    iC = np.linalg.inv(A)                                               # :931
+    iCXRes = iC @ np.column_stack([XData, zData.reshape(-1, 1) - muhat])
+    return dict(nll=nll, parsBTfmd=dict(parsBTfmd), betahat=betahat, vbetahat=vbetahat, cxdhat=1.0, C=A, sigma2Vec=sigma2Vec,
+                iCX=iCXRes[:, :p], iCz_muhat=iCXRes[:, p:p + 1], iC=iC, XData=XData, zData=zData, vXU=vXU, iU=iU,
+                lnTfmdData=True, noits=t["noits"], nll_unrounded=t.get("nll_unrounded", nll))
+
+
+# ---------------------------------------------------------------------------
 # kriging  (predictIAK3D.R:110-139, 179-208, 229-255, 272-284)
 # ---------------------------------------------------------------------------
-def predictIAK3D(xMap, dIMap, XMap_fn, lmmFit, modelx, sdfdTypes, cmeOpt, nxPerBatch=2000):
+def predictIAK3D(xMap, dIMap, XMap_fn, lmmFit, modelx, sdfdTypes, cmeOpt, nxPerBatch=2000, vXUMap_fn=None,
+                 rqrBTfmdPreds=True):
     """predictIAK3D.R:5-287 for compLikOptn = 0, lnTfmdData = FALSE.
 
     ``lmmFit`` = the ``rtnAll`` dict of :func:`nllIAK3D` plus xData, dIData.  ``XMap_fn(iDepth,
@@ -940,19 +1090,30 @@ def predictIAK3D(xMap, dIMap, XMap_fn, lmmFit, modelx, sdfdTypes, cmeOpt, nxPerB
             XMapThis = XMap_fn(i, idx)
             knots = lmmFit.get("sdfdKnots")
             sm = setupIAK3D(xMap[idx], dIThis, sdfdTypes, knots)        # :179
-            Ck, _ = setCIAK3D(P, modelx, *sdfdTypes, cmeOpt, sm)        # :183
+            Ck, s2k = setCIAK3D(P, modelx, *sdfdTypes, cmeOpt, sm)      # :183
             Ckk = np.diag(Ck)                                           # :189
             sm2 = setupIAK3D2(xMap[idx], dIThis, lmmFit["xData"], lmmFit["dIData"], sdfdTypes, knots)   # :192
             Ckh = setCIAK3D2(P, modelx, *sdfdTypes, cmeOpt, sm2)        # :197
             CkhiCX = Ckh @ iCX; CkhiCz = Ckh @ iCz; CkhiC = Ckh @ iC    # :202
             q = np.sum(CkhiC * Ckh, axis=1)                             # :208
+            if lmmFit.get("lnTfmdData", False):                         # :232, :251
+                vX = vXUMap_fn(i, idx) if len(lmmFit["iU"]) else None
+                mu = setmuIAK3D(XMapThis, vX, lmmFit["iU"], betahat, Ckk, s2k)
+                zMap[i, idx] = (mu + CkhiCz).ravel()
+                vMap[i, idx] = Ckk - q
+                continue
             mu = XMapThis @ betahat                                     # :230
             zMap[i, idx] = (mu + CkhiCz).ravel()                        # :240
             t = XMapThis - CkhiCX
             vMap[i, idx] = Ckk - q + np.sum(t * (vbetahat @ t.T).T, axis=1)   # :249
     with np.errstate(invalid="ignore"):
         s = np.sqrt(vMap)
-    return zMap, vMap, zMap - 1.645 * s, zMap + 1.645 * s               # :272-273
+    lo, hi = zMap - 1.645 * s, zMap + 1.645 * s                         # :272-273
+    if lmmFit.get("lnTfmdData", False) and rqrBTfmdPreds:               # :276-284
+        zMap = np.exp(zMap + 0.5 * vMap)
+        lo, hi = np.exp(lo), np.exp(hi)
+        vMap = (np.exp(vMap) - 1.0) * zMap ** 2
+    return zMap, vMap, lo, hi
 
 
 # ---------------------------------------------------------------------------

@@ -65,3 +65,16 @@ def spline_case_pars(kind, types, coefs, nud=0.5):
     elif P.get("cd1", 0.0) == 0.0:
         P["cd1"] = 0.15
     return P, modelx, types, cmeOpt
+
+
+def lognormal_case(n, seed, pU=2):
+    """Synthetic lognormal-data inputs: the last pU columns of X vary inside the sample supports (iU, 0-based) with
+    within-support covariance blocks vXU ((n pU) x pU, symmetric positive semi-definite)."""
+    ds = synth.make_dataset(n, seed)
+    rng = np.random.default_rng(seed + 99)
+    p = ds["XData"].shape[1]
+    iU = list(range(p - pU, p))
+    B = rng.standard_normal((n, pU, pU)) * 0.15
+    v = np.einsum("nij,nkj->nik", B, B) * (ds["dIData"][:, 1] - ds["dIData"][:, 0])[:, None, None]
+    z = 0.4 * ds["zData"] / max(np.std(ds["zData"]), 1e-9) + 1.0          # log-scale response
+    return ds, z, iU, v.reshape(n * pU, pU)
