@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libiak3d.so")
 OK, NOT_SPD, BAD_PARS = 0, 1, 2
 ERR_CUDA, ERR_ARG, ERR_TIMEOUT = -1, -2, -3
 MAX_SPL = 12          # IAK3D_MAX_SPL
+FIT_KEEP_CKHICX, FIT_CROSS_SQUARE = 1, 2
 MODELX = {"nugget": 0, "spherical": 1, "matern": 2, "wendland": 3}
 
 
@@ -53,6 +54,8 @@ _PROTOS = {
     "iak3d_cov_diag": (C.c_int, [_vp, C.POINTER(Pars), _dp]),
     "iak3d_fit_create_res": (C.c_int, [_vp, C.POINTER(Pars), _dp, _dp, _dp, C.POINTER(_vp)]),
     "iak3d_predict_fetch_terms": (C.c_int, [_vp, _dp, _dp, _dp, _dp]),
+    "iak3d_fit_set_option": (C.c_int, [_vp, _i32, _i32]),
+    "iak3d_predict_fetch_CkhiCX": (C.c_int, [_vp, _dp]),
     "iak3d_cov_cross_spl": (C.c_int, [_vp, C.POINTER(Pars), _i64, _dp, _dp, C.POINTER(_dp), _dp]),
     "iak3d_predict_stage_spl": (C.c_int, [_vp, _i64, _dp, _dp, _dp, C.POINTER(_dp)]),
     "iak3d_iacov": (C.c_int, [_vp, _i64, _dp, _i64, _dp, C.c_double, C.c_double, _i32, _dp, _dp, _dp]),

@@ -660,7 +660,7 @@ def gradnllIAK3D(pars, zData, XData, vXU=None, iU=None, modelx="matern", nud=0.5
 
 
 def nllIAK3D_CL(pars, zData, XData, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds, useReml,
-                compLikMats, parsBTfmd=None, rtnTerms=False, comm=None):
+                compLikMats, parsBTfmd=None, rtnTerms=False, comm=None, rtnAll=False):
     """compositeLikIAK3D.R:6-307.  `compLikMats` carries compLikOptn, listBlocks, subsetPairsAdj, subsetPairsNonadj and
     the per-unit device datasets made by :func:`setupIAK3D_CL` (first the adjacent pairs, then the single blocks --
     the order of iaCovMatern.R:551-575).  With `comm` (a parallel.BlockComm) the units are sharded across ranks and
@@ -686,7 +686,26 @@ def nllIAK3D_CL(pars, zData, XData, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sd
             S += w * _symm_upper(G[i].T); lnd_sum += w * lnd[i]
             if u["kind"] == "pair":
                 n_SUM += u["n"]
-    return cl_reduce_and_tail(S, lnd_sum, n_SUM, failed, n, p, optn, nB, useReml, comm, rtnTerms)
+    if not rtnAll:
+        return cl_reduce_and_tail(S, lnd_sum, n_SUM, failed, n, p, optn, nB, useReml, comm, rtnTerms)
+    # rtnAll (compositeLikIAK3D.R:231-256, 295-303): the fitted list predictIAK3D_CL works from
+    t = cl_reduce_and_tail(S, lnd_sum, n_SUM, failed, n, p, optn, nB, useReml, comm, True)
+    if not isinstance(t, dict):
+        return dict(nll=BADNLL, pars=pars, parsBTfmd=parsBTfmd)
+    cxdhat = t["cxdhat"]
+    fitted = dict(parsBTfmd)
+    for k in ("cx0", "cx1", "cd1", "cxd0", "cxd1"):
+        fitted[k] = cxdhat * fitted[k]
+    if cmeOpt == 1:
+        fitted["cme"] = cxdhat * fitted["cme"]
+    A = t["XziAXz_SUM"] / (nB - 1) if optn == 1 else t["XziAXz_SUM"]
+    if optn in (2, 3):
+        A = n * A / t["n_SUM"]                                          # XziAXz_APPROX, :238
+    vbetahat = cxdhat * np.linalg.inv(A[:p, :p])
+    return dict(nll=t["nll"], pars=pars, parsBTfmd=fitted, betahat=t["betahat"], vbetahat=vbetahat, cxdhat=cxdhat, XData=XData,
+                zData=zData, XziAXz_APPROX=A, XziAXz_SUM=t["XziAXz_SUM"], n_SUM=t["n_SUM"], compLikMats=compLikMats, modelx=modelx,
+                nud=nud, sdfdType_cd1=sdfdType_cd1, sdfdType_cxd0=sdfdType_cxd0, sdfdType_cxd1=sdfdType_cxd1, cmeOpt=cmeOpt,
+                lnTfmdData=False)
 
 
 def cl_reduce_and_tail(S, lnd_sum, n_SUM, failed, n, p, optn, nB, useReml, comm=None, rtnTerms=False):
@@ -726,7 +745,7 @@ def cl_plan_units(compLikMats, world=1):
     units = []
     if optn < 4:
         for (k, l) in np.asarray(compLikMats["subsetPairsAdj"]).reshape(-1, 2):
-            units.append(dict(kind="pair", weight=1.0, rows=np.concatenate([blocks[k], blocks[l]])))
+            units.append(dict(kind="pair", weight=1.0, rows=np.concatenate([blocks[k], blocks[l]]), pair=(int(k), int(l))))
     if optn in (1, 3):
         cnt = np.zeros(len(blocks))
         for (k, l) in np.asarray(compLikMats.get("subsetPairsNonadj", np.zeros((0, 2), int))).reshape(-1, 2):
@@ -784,6 +803,54 @@ def gradHessIAK3D(setupMats, parsBTfmd, modelx, sdfdTypes, lnvPars):
     if st != OK:
         return dict(nll=float("nan"))
     return dict(nll=nll.value, grad=grad, hess=hess, fim=fim, betahat=beta.reshape(-1, 1), vbetahat=vb)
+
+
+def nr_iterate(gh, lnvParInits, smallV):
+    """The iteration of nrUpdatesIAK3D (nrUpdatesIAK3D.R:1-116) around a gradient/Hessian callback `gh(lnvPars)`:
+    at least 4, at most 20 updates, the first two by Fisher scoring, log-variances below `smallV` that still move down
+    are snapped to -20 (:57-65), the final nll rounded to 1e-5 (:107-108).  The reference's Hessian branch tests
+    `checkHess$cholC` on the value of solve() (:44), which cannot run; the evident intent is implemented (Newton step from
+    the third update on, Fisher scoring if that solve fails)."""
+    lnv = np.asarray(lnvParInits, float).reshape(-1).copy()
+    t = gh(lnv)
+    if not np.isfinite(t["nll"]):
+        return dict(lnvPars=lnv, nll=float("nan"), noits=0, errFlag=1)
+    sym = lambda M: 0.5 * (M + M.T)
+    tol, noits, nllPrev = 1e-6, 0, math.inf
+    while noits < 20 and (t["nll"] < nllPrev - tol or noits < 4):
+        nllPrev = t["nll"]
+        step = None
+        if noits >= 2:
+            try:
+                step = np.linalg.solve(sym(t["hess"]), t["grad"])
+            except np.linalg.LinAlgError:
+                step = None
+        if step is None:
+            try:
+                step = np.linalg.solve(sym(t["fim"]), t["grad"])
+            except np.linalg.LinAlgError:
+                return dict(lnvPars=lnv, noits=noits, errFlag=1, **t)
+        small = (lnv < smallV) & (step > 0)
+        lnv = lnv - step
+        lnv[small] = -20.0
+        tn = gh(lnv)
+        if not np.isfinite(tn["nll"]):
+            return dict(lnvPars=lnv, noits=noits, errFlag=1, **t)
+        t = tn
+        noits += 1
+    out = dict(t)
+    out.update(lnvPars=lnv, nll_unrounded=t["nll"], nll=float(np.round(t["nll"] / 1e-5) * 1e-5), noits=noits,
+               errFlag=2 if noits == 20 else 0)
+    return out
+
+
+def nrUpdatesIAK3D(setupMats, parsBTfmd, modelx, sdfdTypes, lnvParInits, smallV=None):
+    """nrUpdatesIAK3D.R:1-116 with every gradHessIAK3D evaluation on the GPU (:func:`gradHessIAK3D`).  The dataset must
+    carry W = [X z]; smallV defaults to log(var(z) / 10000) (:5-7)."""
+    sm = setupMats
+    if smallV is None or (isinstance(smallV, float) and math.isnan(smallV)):
+        smallV = math.log(float(np.var(sm._W[:, -1], ddof=1)) / 10000.0)
+    return nr_iterate(lambda v: gradHessIAK3D(sm, parsBTfmd, modelx, sdfdTypes, v), lnvParInits, smallV)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -849,6 +916,14 @@ class KeptFit:
         self.ctx.check(self.ctx.lib.iak3d_predict_fetch(self.h, dptr(z), dptr(v)))
         return z, v
 
+    def set_option(self, option, value):
+        self.ctx.check(self.ctx.lib.iak3d_fit_set_option(self.h, int(option), int(value)))
+
+    def fetch_CkhiCX(self):
+        out = np.empty((self._m, self.p), order="F")
+        self.ctx.check(self.ctx.lib.iak3d_predict_fetch_CkhiCX(self.h, dptr(out)))
+        return out
+
     def fetch_terms(self):
         """Ckk, sigma2Veck, CkhiCz_muhat, CkhiCChk of the last enqueued batch (predictIAK3D.R:183-208)."""
         out = [np.empty(self._m) for _ in range(4)]
@@ -907,3 +982,89 @@ def predictIAK3D(xMap, dIMap, XMap_fn, lmmFit, nxPerBatch=2000, cells=None, vXUM
         lo, hi = np.exp(lo), np.exp(hi)
         vMap = (np.exp(vMap) - 1.0) * zMap ** 2
     return dict(zMap=zMap, vMap=vMap, pi90LMap=lo, pi90UMap=hi)
+
+
+# ---------------------------------------------------------------------------------------------
+# composite-likelihood block prediction (compositeLikIAK3D.R:471-607; dispatched at predictIAK3D.R:211-226)
+# ---------------------------------------------------------------------------------------------
+def getBlocksFromLocations(xMap, compLikMats):
+    """Nearest block centroid, first index on ties (compositeLikIAK3D.R:476-480)."""
+    cen = np.asarray(compLikMats["centroids"], float)
+    d2 = ((np.asarray(xMap, float)[:, None, :] - cen[None, :, :]) ** 2).sum(-1)
+    return np.sqrt(d2).argmin(axis=1)
+
+
+def predMatsIAK3D_CL_ByBlock(z_muhat, XData, xMap, dIMap, lmmFit):
+    """compositeLikIAK3D.R:471-607 (compLikOptn 1 and 4): for the map supports of block k, the kriging terms against the
+    data of every adjacent pair (k, l), averaged over the neighbours l.  Each pair is one kept factorisation on the
+    GPU -- the pair dataset the likelihood was fitted with -- shared by the map supports of both of its blocks.
+    -> dict(diagCkk, diagCkhiCChk, CkhiCX, CkhiCz_muhat)."""
+    cl = lmmFit["compLikMats"]
+    blocks = cl["listBlocks"]
+    pairs = np.asarray(cl["subsetPairsAdj"]).reshape(-1, 2)
+    xMap = np.asarray(xMap, float).reshape(-1, 2); dIMap = np.asarray(dIMap, float).reshape(-1, 2)
+    m, p = xMap.shape[0], XData.shape[1]
+    blockMap = getBlocksFromLocations(xMap, cl)
+    nadj = np.zeros(len(blocks))
+    for k, l in pairs:
+        nadj[k] += 1; nadj[l] += 1
+    used = np.unique(blockMap)
+    if np.any(nadj[used] == 0):
+        raise ValueError("Error - every block must have a neighbour - check this!")
+    unit_of = {}
+    for u in cl["units"]:
+        if u["kind"] == "pair":
+            unit_of[tuple(u["pair"])] = u
+    types = (lmmFit["sdfdType_cd1"], lmmFit["sdfdType_cxd0"], lmmFit["sdfdType_cxd1"])
+    Ckk = np.full(m, np.nan); q = np.zeros(m); cz = np.zeros(m); cx = np.zeros((m, p))
+    z_muhat = np.asarray(z_muhat, float).reshape(-1)
+    for k, l in pairs:
+        pts = np.nonzero((blockMap == k) | (blockMap == l))[0]
+        if pts.size == 0:
+            continue
+        u = unit_of.get((int(k), int(l)))
+        if u is None:
+            raise ValueError("composite-likelihood prediction: the pair dataset is not on this rank (setupIAK3D_CL)")
+        rows = u["rows"]
+        # parsBTfmd are the rescaled parameters; C is rebuilt from them (setCIAK3D of the joined supports, :540-552)
+        fit = KeptFit(u["setup"], lmmFit["parsBTfmd"], lmmFit["modelx"], types, lmmFit["cmeOpt"], np.zeros(p), np.eye(p), 1.0,
+                      z_muhat=z_muhat[rows])
+        try:
+            fit.set_option(_lib.FIT_KEEP_CKHICX, 1); fit.set_option(_lib.FIT_CROSS_SQUARE, 1)
+            fit.stage(xMap[pts], dIMap[pts], np.zeros((pts.size, p)))
+            fit.enqueue(); fit.fetch()
+            t = fit.fetch_terms()
+            Ckk[pts] = t["Ckk"]; q[pts] += t["CkhiCChk"]; cz[pts] += t["CkhiCz_muhat"]; cx[pts] += fit.fetch_CkhiCX()
+        finally:
+            fit.close()
+    w = nadj[blockMap]
+    return dict(diagCkk=Ckk, diagCkhiCChk=q / w, CkhiCX=cx / w[:, None], CkhiCz_muhat=cz / w)
+
+
+def predictIAK3D_CL(xMap, dIMap, XMap_fn, lmmFit, cells=None):
+    """predictIAK3D (predictIAK3D.R:5-287) when the model was fitted by composite likelihood with compLikOptn 1 or 4
+    (:211-226 -> predMatsIAK3D_CL_ByBlock).  `lmmFit` is the rtnAll dict of :func:`nllIAK3D_CL`.  The Eidsvik options
+    (2, 3 -> predMatsIAK3D_CLEV_ByBlock) are not built."""
+    optn = lmmFit["compLikMats"]["compLikOptn"]
+    if optn in (2, 3):
+        raise NotImplementedError("predMatsIAK3D_CLEV_ByBlock (compLikOptn 2, 3) is not built")
+    xMap = np.asarray(xMap, float).reshape(len(xMap), -1)
+    dIMap = np.round(np.asarray(dIMap, float).reshape(-1, 2), 2)
+    nd, nx = dIMap.shape[0], xMap.shape[0]
+    XData, betahat, vbetahat = lmmFit["XData"], lmmFit["betahat"], lmmFit["vbetahat"]
+    z_muhat = lmmFit["zData"].reshape(-1) - (XData @ betahat).reshape(-1)
+    idx_all = np.arange(nx) if cells is None else np.asarray(cells)
+    zMap = np.full((nd, nx), np.nan); vMap = np.full((nd, nx), np.nan)
+    for i in range(nd):
+        XM = np.asarray(XMap_fn(i, idx_all), float)
+        ok = ~np.isnan(XM.mean(axis=1))
+        if not ok.any():
+            continue
+        sel = idx_all[ok]
+        t = predMatsIAK3D_CL_ByBlock(z_muhat, XData, xMap[sel], np.repeat(dIMap[i:i + 1], sel.size, axis=0), lmmFit)
+        zMap[i, sel] = (XM[ok] @ betahat).reshape(-1) + t["CkhiCz_muhat"]
+        d = XM[ok] - t["CkhiCX"]
+        vMap[i, sel] = t["diagCkk"] - t["diagCkhiCChk"] + np.sum(d * (vbetahat @ d.T).T, axis=1)
+    with np.errstate(invalid="ignore"):
+        s_ = np.sqrt(vMap)
+    return dict(zMap=zMap, vMap=vMap, pi90LMap=zMap - 1.645 * s_, pi90UMap=zMap + 1.645 * s_)

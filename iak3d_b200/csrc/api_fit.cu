@@ -55,6 +55,8 @@ struct iak3d_fit {
   double* d_z = nullptr; double* d_v = nullptr; double* d_ckk = nullptr;
   double* d_cz = nullptr; double* d_qf = nullptr; double* d_s2k = nullptr;   // CkhiCz_muhat, rowSums(CkhiC * Ckh), sigma2Veck
   double* d_avself = nullptr;    // NTAB_BUF x nd1cap: avVarVec of the map supports' self tables
+  double* d_cx = nullptr; int64_t cx_cap = 0;   // m x p: Ckh iC X, kept when opt_keep_cx
+  int32_t opt_keep_cx = 0, opt_cross_square = 0;
   int64_t cap_m = 0;
   // ---- panel workspace (one chunk) ----
   int64_t ldP = 0;
@@ -75,7 +77,7 @@ struct iak3d_fit {
 
 static void fit_free_job(iak3d_fit* f) {
   cudaFree(f->d_xy); cudaFree(f->d_X); cudaFree(f->d_did1); cudaFree(f->d_dIU1); cudaFree(f->d_z); cudaFree(f->d_v); cudaFree(f->d_ckk);
-  cudaFree(f->d_cz); cudaFree(f->d_qf); cudaFree(f->d_s2k);
+  cudaFree(f->d_cz); cudaFree(f->d_qf); cudaFree(f->d_s2k); cudaFree(f->d_cx); f->d_cx = nullptr; f->cx_cap = 0;
   f->d_xy = f->d_X = f->d_dIU1 = f->d_z = f->d_v = f->d_ckk = f->d_cz = f->d_qf = f->d_s2k = nullptr; f->d_did1 = nullptr; f->cap_m = 0;
 }
 static void fit_free_panel(iak3d_fit* f) {
@@ -276,6 +278,12 @@ extern "C" int iak3d_predict_stage_spl(iak3d_fit* f, int64_t m, const double* xy
     CUDA_TRY(ctx, cudaMalloc(&f->d_s2k, (size_t)m * 8));
     f->cap_m = m;
   }
+  if (f->opt_keep_cx && (int64_t)m * p > f->cx_cap) {
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(f->d_cx); f->d_cx = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&f->d_cx, (size_t)m * p * 8));
+    f->cx_cap = (int64_t)m * p;
+  }
   // unique depth intervals of the map supports (usually one per call: predictIAK3D.R:150)
   std::vector<int32_t> did1; std::vector<double> dIU1;
   iak_unique_first(m, dIMap, dIMap + m, did1, dIU1);
@@ -314,7 +322,8 @@ extern "C" int iak3d_predict_enqueue(iak3d_fit* f) {
   Slot* s = f->slot;
   iak3d_ds* ds = f->ds;
   const int64_t nd1 = f->nd1, nd2 = ds->ndIU;
-  const EvalPlan& px = f->plan_x; const EvalPlan& ps = f->plan_kk;
+  // compositeLikIAK3D.R:540-552 builds Ckh as a block of setCIAK3D of the joined supports: the square plan (cd1 quirk, :1052)
+  const EvalPlan& px = f->opt_cross_square ? f->plan_kk : f->plan_x; const EvalPlan& ps = f->plan_kk;
   int rc;
   // depth tables: cross (nd1 x nd2) and self (nd1 x nd1, for Ckk)
   CovArgs a;
@@ -385,7 +394,7 @@ extern "C" int iak3d_predict_enqueue(iak3d_fit* f) {
     rc = launch_tile_tasks(ctx, f->d_prob, f->d_tasks, f->ntasks, f->d_ticket);
     if (rc != 0) return rc;
     rc = launch_krige_finish(ctx, f->d_G, rowsP, f->q, f->d_X + r0, m, rows, f->d_ckk + r0, f->d_beta, f->d_vbeta, f->d_z + r0,
-                             f->d_v + r0, f->d_cz + r0, f->d_qf + r0);
+                             f->d_v + r0, f->d_cz + r0, f->d_qf + r0, (f->opt_keep_cx && f->d_cx) ? f->d_cx + r0 : nullptr, m);
     if (rc != 0) return rc;
   }
   CUDA_TRY(ctx, cudaMemcpyAsync(f->h_status, f->d_status, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -417,6 +426,25 @@ extern "C" int iak3d_predict_fetch_terms(iak3d_fit* f, double* Ckk, double* sigm
   if (sigma2Veck) CUDA_TRY(ctx, cudaMemcpyAsync(sigma2Veck, f->d_s2k, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   if (CkhiCz_muhat) CUDA_TRY(ctx, cudaMemcpyAsync(CkhiCz_muhat, f->d_cz, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   if (CkhiCChk) CUDA_TRY(ctx, cudaMemcpyAsync(CkhiCChk, f->d_qf, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return IAK3D_OK;
+}
+
+extern "C" int iak3d_fit_set_option(iak3d_fit* f, int32_t option, int32_t value) {
+  if (!f) return IAK3D_ERR_ARG;
+  if (option == IAK3D_FIT_KEEP_CKHICX) f->opt_keep_cx = value ? 1 : 0;
+  else if (option == IAK3D_FIT_CROSS_SQUARE) f->opt_cross_square = value ? 1 : 0;
+  else { f->ctx->err = "fit_set_option: unknown option"; return IAK3D_ERR_ARG; }
+  return IAK3D_OK;
+}
+
+extern "C" int iak3d_predict_fetch_CkhiCX(iak3d_fit* f, double* CkhiCX) {
+  if (!f || !CkhiCX) return IAK3D_ERR_ARG;
+  iak3d_ctx* ctx = f->ctx;
+  if (!f->staged || !f->opt_keep_cx || !f->d_cx) { ctx->err = "predict_fetch_CkhiCX: set IAK3D_FIT_KEEP_CKHICX before staging"; return IAK3D_ERR_ARG; }
+  cudaSetDevice(ctx->device);
+  if (f->m == 0) return IAK3D_OK;
+  CUDA_TRY(ctx, cudaMemcpyAsync(CkhiCX, f->d_cx, (size_t)f->m * f->p * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return IAK3D_OK;
 }

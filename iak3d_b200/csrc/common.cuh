@@ -192,4 +192,4 @@ int launch_peak(iak3d_ctx* ctx, int kind, double* tflops);
 // kriging epilogue (predictIAK3D.R:229-255): z, v from the bordered-row accumulators G (ldG x (q+1))
 int launch_krige_finish(iak3d_ctx* ctx, const double* d_G, int64_t ldG, int32_t q, const double* d_XMap, int64_t ldX, int64_t m,
                         const double* d_Ckk, const double* d_beta, const double* d_vbeta, double* d_z, double* d_v,
-                        double* d_cz = nullptr, double* d_qf = nullptr);
+                        double* d_cz = nullptr, double* d_qf = nullptr, double* d_cx = nullptr, int64_t ldcx = 0);

@@ -347,7 +347,7 @@ int launch_ckk(iak3d_ctx* ctx, const EvalPlan& pl, const double* const* d_Tself,
 __global__ void krige_finish_kernel(const double* __restrict__ G, int64_t ldG, int q, const double* __restrict__ XMap, int64_t ldX,
                                     int64_t m, const double* __restrict__ Ckk, const double* __restrict__ beta,
                                     const double* __restrict__ vbeta, double* __restrict__ z, double* __restrict__ v,
-                                    double* __restrict__ cz, double* __restrict__ qf) {
+                                    double* __restrict__ cz, double* __restrict__ qf, double* __restrict__ cx, int64_t ldcx) {
   extern __shared__ double sh[];
   const int p = q - 1;
   double* sb = sh; double* sv = sh + p;
@@ -368,14 +368,15 @@ __global__ void krige_finish_kernel(const double* __restrict__ G, int64_t ldG, i
   v[i] = Ckk[i] - G[(int64_t)q * ldG + i] + quad;
   if (cz != nullptr) cz[i] = G[(int64_t)p * ldG + i];
   if (qf != nullptr) qf[i] = G[(int64_t)q * ldG + i];
+  if (cx != nullptr) for (int a = 0; a < p; a++) cx[(int64_t)a * ldcx + i] = G[(int64_t)a * ldG + i];
 }
 int launch_krige_finish(iak3d_ctx* ctx, const double* d_G, int64_t ldG, int32_t q, const double* d_XMap, int64_t ldX, int64_t m,
                         const double* d_Ckk, const double* d_beta, const double* d_vbeta, double* d_z, double* d_v, double* d_cz,
-                        double* d_qf) {
+                        double* d_qf, double* d_cx, int64_t ldcx) {
   if (m == 0) return 0;
   const int p = q - 1;
   krige_finish_kernel<<<(unsigned)((m + 127) / 128), 128, (size_t)(p + p * p) * sizeof(double), ctx->stream>>>(
-      d_G, ldG, q, d_XMap, ldX, m, d_Ckk, d_beta, d_vbeta, d_z, d_v, d_cz, d_qf);
+      d_G, ldG, q, d_XMap, ldX, m, d_Ckk, d_beta, d_vbeta, d_z, d_v, d_cz, d_qf, d_cx, ldcx);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return 0;

@@ -139,7 +139,7 @@ def make_blocks(xData, prof, n_blocks, seed):
     aset = {tuple(r) for r in adj}
     non = np.array([(i, j) for i in range(n_blocks) for j in range(i + 1, n_blocks) if (i, j) not in aset],
                    np.int64).reshape(-1, 2)
-    return dict(listBlocks=blocks, subsetPairsAdj=adj, subsetPairsNonadj=non)
+    return dict(listBlocks=blocks, subsetPairsAdj=adj, subsetPairsNonadj=non, centroids=cen)
 
 
 def make_grid(n_side, extent_km=100.0):

@@ -174,6 +174,15 @@ IAK3D_API int iak3d_predict_fetch(iak3d_fit* fit, double* z, double* v);
  * predictions (predictIAK3D.R:229-255, setmuIAK3D) and profilePredictIAK3D are assembled from these by the caller.
  * Call after iak3d_predict_enqueue, before or after iak3d_predict_fetch. */
 IAK3D_API int iak3d_predict_fetch_terms(iak3d_fit* fit, double* Ckk, double* sigma2Veck, double* CkhiCz_muhat, double* CkhiCChk);
+/* options of a kept fit, set before iak3d_predict_stage:
+ *  IAK3D_FIT_KEEP_CKHICX   keep Ckh iC X (m x p) of every batch for iak3d_predict_fetch_CkhiCX (composite-likelihood block
+ *                          prediction sums it over block pairs, compositeLikIAK3D.R:590-599);
+ *  IAK3D_FIT_CROSS_SQUARE  build Ckh like a block of setCIAK3D of the joined supports (compositeLikIAK3D.R:540-552), i.e.
+ *                          WITH the cd1 quirk of fitIAK3D.R:1052, instead of setCIAK3D2. */
+#define IAK3D_FIT_KEEP_CKHICX 1
+#define IAK3D_FIT_CROSS_SQUARE 2
+IAK3D_API int iak3d_fit_set_option(iak3d_fit* fit, int32_t option, int32_t value);
+IAK3D_API int iak3d_predict_fetch_CkhiCX(iak3d_fit* fit, double* CkhiCX /* m x p column-major */);
 
 /* ---- Newton-Raphson terms == gradHessIAK3D (nrUpdatesIAK3D.R:118-216) -----------------------
  * Components dA_i are the unit-variance terms of setCIAK3D in the order cx0, cx1, cd1, cxd0, cxd1,

@@ -913,7 +913,18 @@ def nllIAK3D_CL(pars, zData, XData, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sd
     if not np.isfinite(nll):
         nll = BADNLL
     if rtnTerms:
-        return dict(nll=nll, XziAXz_SUM=S, lndetA_SUM=lnd, n_SUM=n_SUM, cxdhat=cxdhat, betahat=t["betahat"])
+        out = dict(nll=nll, XziAXz_SUM=S, lndetA_SUM=lnd, n_SUM=n_SUM, cxdhat=cxdhat, betahat=t["betahat"])
+        # rtnAll pieces (:231-256): rescaled parameters and vbetahat
+        fitted = dict(parsBTfmd if parsBTfmd is not None else readParsIAK3D(pars, modelx, nud, sdfdType_cd1, sdfdType_cxd0,
+                                                                            sdfdType_cxd1, cmeOpt, prodSum, parBnds))
+        for k in ("cx0", "cx1", "cd1", "cxd0", "cxd1"):
+            fitted[k] = cxdhat * fitted[k]
+        if cmeOpt == 1:
+            fitted["cme"] = cxdhat * fitted["cme"]
+        A = n * XziAXz / n_SUM if optn in (2, 3) else XziAXz
+        out.update(parsBTfmd=fitted, vbetahat=cxdhat * np.linalg.inv(A[:p, :p]), XData=XData, zData=zData, xData=xData,
+                   dIData=dIData, compLikMats=compLikMats)
+        return out
     return nll
 
 
@@ -1117,6 +1128,60 @@ def predictIAK3D(xMap, dIMap, XMap_fn, lmmFit, modelx, sdfdTypes, cmeOpt, nxPerB
 
 
 # ---------------------------------------------------------------------------
+# composite-likelihood block prediction  (compositeLikIAK3D.R:471-607; predictIAK3D.R:211-255)
+# ---------------------------------------------------------------------------
+def predMatsIAK3D_CL_ByBlock(z_muhat, XData, xMap, dIMap, lmmFit, modelx, sdfdTypes, cmeOpt):
+    """compositeLikIAK3D.R:471-607, restated with the joined-support setCIAK3D of the `oldSetC` branch (:540-552)."""
+    cl = lmmFit["compLikMats"]
+    blocks = cl["listBlocks"]
+    cen = np.asarray(cl["centroids"], float)
+    pairs = np.asarray(cl["subsetPairsAdj"]).reshape(-1, 2)
+    blockMap = np.argmin(xyDist(xMap, cen), axis=1)                     # :476-480
+    m, p = xMap.shape[0], XData.shape[1]
+    Ckk = np.full(m, np.nan); q = np.full(m, np.nan); cz = np.full(m, np.nan); cx = np.full((m, p), np.nan)
+    for k in range(int(blockMap.max()) + 1):
+        pts = np.nonzero(blockMap == k)[0]
+        if pts.size == 0:
+            continue
+        adj = [int(b) for a, b in pairs if a == k] + [int(a) for a, b in pairs if b == k]   # :503-507
+        if not adj:
+            raise ValueError("Error - every block must have a neighbour - check this!")
+        qs = np.zeros(pts.size); czs = np.zeros(pts.size); cxs = np.zeros((pts.size, p))
+        for i, l in enumerate(adj):
+            rows = np.concatenate([blocks[k], blocks[l]])               # :528
+            sm = setupIAK3D(np.vstack([xMap[pts], lmmFit["xData"][rows]]), np.vstack([dIMap[pts], lmmFit["dIData"][rows]]))
+            Cj, _ = setCIAK3D(lmmFit["parsBTfmd"], modelx, *sdfdTypes, cmeOpt, sm)           # :545
+            if i == 0:
+                Ckk[pts] = np.diag(Cj)[:pts.size]                       # :549-551
+            Chk = Cj[pts.size:, :pts.size]; Ch = Cj[pts.size:, pts.size:]
+            iCChk = np.linalg.solve(Ch, Chk)                            # :588
+            qs += np.sum(Chk * iCChk, axis=0)                           # :590
+            cxs += iCChk.T @ XData[rows]                                # :593
+            czs += iCChk.T @ z_muhat[rows]                              # :594
+        q[pts] = qs / len(adj); cx[pts] = cxs / len(adj); cz[pts] = czs / len(adj)          # :598-600
+    return dict(diagCkk=Ckk, diagCkhiCChk=q, CkhiCX=cx, CkhiCz_muhat=cz)
+
+
+def predictIAK3D_CL(xMap, dIMap, XMap_fn, lmmFit, modelx, sdfdTypes, cmeOpt):
+    """predictIAK3D.R:5-287 for a composite-likelihood fit with compLikOptn 1 or 4 (:211-226)."""
+    xMap = np.asarray(xMap, float).reshape(len(xMap), -1)
+    dIMap = np.round(np.asarray(dIMap, float).reshape(-1, 2), 2)
+    nd, nx = dIMap.shape[0], xMap.shape[0]
+    XData, betahat, vbetahat = lmmFit["XData"], lmmFit["betahat"], lmmFit["vbetahat"]
+    z_muhat = lmmFit["zData"].reshape(-1) - (XData @ betahat).reshape(-1)
+    zMap = np.full((nd, nx), np.nan); vMap = np.full((nd, nx), np.nan)
+    for i in range(nd):
+        XM = XMap_fn(i, np.arange(nx))
+        t = predMatsIAK3D_CL_ByBlock(z_muhat, XData, xMap, np.repeat(dIMap[i:i + 1], nx, axis=0), lmmFit, modelx, sdfdTypes, cmeOpt)
+        zMap[i] = (XM @ betahat).reshape(-1) + t["CkhiCz_muhat"]
+        d = XM - t["CkhiCX"]
+        vMap[i] = t["diagCkk"] - t["diagCkhiCChk"] + np.sum(d * (vbetahat @ d.T).T, axis=1)
+    with np.errstate(invalid="ignore"):
+        s = np.sqrt(vMap)
+    return zMap, vMap, zMap - 1.645 * s, zMap + 1.645 * s
+
+
+# ---------------------------------------------------------------------------
 # Newton-Raphson on log-variances  (nrUpdatesIAK3D.R:118-216)
 # ---------------------------------------------------------------------------
 def gradHessIAK3D(dA: Sequence[np.ndarray], lnvPars, W):
@@ -1164,6 +1229,41 @@ def gradHessIAK3D(dA: Sequence[np.ndarray], lnvPars, W):
             fim[i, j] = fim[j, i] = 0.5 * tr
     nll = 0.5 * ((n - p) * math.log(2.0 * math.pi) + lndetC + lndetXiCX + zTz)
     return dict(nll=nll, grad=grad, hess=hess, fim=fim, betahat=betahat, vbetahat=iXiCX, C=C)
+
+
+def nrUpdatesIAK3D(dA, lnvParInits, W, smallV=None):
+    """nrUpdatesIAK3D.R:1-116.  (The `checkHess$cholC` test of :44 cannot run as written; the intended logic is
+    restated: Newton step from the third update on, Fisher scoring when that solve fails.)"""
+    W = np.asarray(W, float)
+    if smallV is None:
+        smallV = math.log(float(np.var(W[:, -1], ddof=1)) / 10000.0)    # :5-7
+    lnv = np.asarray(lnvParInits, float).reshape(-1).copy()
+    t = gradHessIAK3D(dA, lnv, W)
+    sym = lambda M: 0.5 * (M + M.T)
+    tol, noits, nllPrev = 1e-6, 0, math.inf
+    while noits < 20 and (t["nll"] < nllPrev - tol or noits < 4):       # :31
+        nllPrev = t["nll"]
+        step = None
+        if noits >= 2:                                                  # :35-52
+            try:
+                step = np.linalg.solve(sym(t["hess"]), t["grad"])
+            except np.linalg.LinAlgError:
+                step = None
+        if step is None:
+            try:
+                step = np.linalg.solve(sym(t["fim"]), t["grad"])
+            except np.linalg.LinAlgError:
+                return dict(lnvPars=lnv, noits=noits, errFlag=1, **t)
+        step = np.asarray(step, float).reshape(-1)
+        small = (lnv < smallV) & (step > 0)                             # :61
+        lnv = lnv - step                                                # :64
+        lnv[small] = -20.0                                              # :65
+        t = gradHessIAK3D(dA, lnv, W)
+        noits += 1
+    out = dict(t)
+    out.update(lnvPars=lnv, nll_unrounded=t["nll"], nll=float(np.round(t["nll"] / 1e-5) * 1e-5), noits=noits,
+               errFlag=2 if noits == 20 else 0)
+    return out
 
 
 def component_matrices(parsBTfmd, modelx, sdfdTypes, setupMats):

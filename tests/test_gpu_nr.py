@@ -66,3 +66,32 @@ def test_gradhess_not_spd(ctx):
     sm = iak.SetupMats(ds["xData"], ds["dIData"], W=W, ctx=ctx)
     got = iak.gradHessIAK3D(sm, P, modelx, types, np.array([-800.0] * 6))     # all variances underflow to 0
     assert np.isnan(got["nll"])
+
+
+@pytest.mark.parametrize("kind,ncomp,n", [("matern0.5", 6, 400), ("edgeroi", 5, 300)])
+def test_nrUpdates_iteration_vs_oracle(ctx, kind, ncomp, n):
+    """The whole Newton-Raphson iteration (nrUpdatesIAK3D.R:1-116): same number of updates, same optimum, small variances
+    snapped to -20.  The Edgeroi model has no cd1 component, so its dA[3] is a zero matrix and the FIM is singular: both
+    sides must leave at once with errFlag 1 (:74-78)."""
+    ds = synth.make_dataset(n, 6)
+    P, modelx, types, cmeOpt = case_pars(kind, False, 0.5)
+    W = np.column_stack([ds["XData"], ds["zData"]])
+    sm = iak.SetupMats(ds["xData"], ds["dIData"], W=W, ctx=ctx)
+    osm = orc.setupIAK3D(ds["xData"], ds["dIData"])
+    cxdhat = orc.nllIAK3D(None, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True, osm, PARBNDS, rtnAll=True, parsBTfmd=P)["cxdhat"]
+    keys = ["cx0", "cx1", "cd1", "cxd0", "cxd1", "cme"][:ncomp]
+    th0 = np.log([max(cxdhat * P[k], 1e-3) for k in keys]) + 0.2 * np.array([1, -1, 1, -1, 1, -1])[:ncomp]
+    got = iak.nrUpdatesIAK3D(sm, P, modelx, types, th0)
+    dA = orc.component_matrices(P, modelx, types, osm)[:ncomp]
+    want = orc.nrUpdatesIAK3D(dA, th0, W)
+    assert got["noits"] == want["noits"] and got["errFlag"] == want["errFlag"]
+    if want["errFlag"] == 1:
+        assert kind == "edgeroi" and want["noits"] == 0
+        return
+    assert want["noits"] >= 4
+    assert abs(got["nll_unrounded"] - want["nll_unrounded"]) <= 1e-8 * abs(want["nll_unrounded"])
+    assert abs(got["nll"] - want["nll"]) <= 1.01e-5
+    live = want["lnvPars"] > -19.0                              # snapped-to--20 variances sit on a flat likelihood
+    assert np.array_equal(live, got["lnvPars"] > -19.0)
+    assert np.max(np.abs(got["lnvPars"][live] - want["lnvPars"][live])) <= 1e-5
+    assert scaled_err(got["betahat"], want["betahat"]) <= 1e-7

@@ -116,3 +116,33 @@ def test_cl_single_block_equals_exact(ctx):
     cl = iak.setupIAK3D_CL(ds["xData"], ds["dIData"], ds["zData"], ds["XData"], blk, ctx=ctx)
     got = iak.nllIAK3D_CL(None, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True, PARBNDS, True, cl, parsBTfmd=P)
     assert got == exact
+
+
+@pytest.mark.parametrize("optn,useReml,kind,nonstat", [(1, True, "edgeroi", False), (4, True, "matern0.5", True), (1, False, "matern0.8", False)])
+def test_cl_block_prediction_vs_oracle(ctx, optn, useReml, kind, nonstat):
+    """predictIAK3D for a composite-likelihood fit (predictIAK3D.R:211-226 -> predMatsIAK3D_CL_ByBlock): every adjacent
+    pair is one kept factorisation; the non-stationary case exercises the square-build cd1 quirk inside Ckh."""
+    ds = synth.make_dataset(1300, 71)
+    P, modelx, types, cmeOpt = case_pars(kind, nonstat, 0.5)
+    blk = synth.make_blocks(ds["xData"], ds["prof"], 6, 71)
+    blk["compLikOptn"] = optn
+    cl = iak.setupIAK3D_CL(ds["xData"], ds["dIData"], ds["zData"], ds["XData"], blk, ctx=ctx)
+    if optn == 4:      # the fit uses single blocks only; prediction still needs the adjacent pairs (compositeLikIAK3D.R:503-507)
+        pr = dict(blk); pr["compLikOptn"] = 1
+        clp = iak.setupIAK3D_CL(ds["xData"], ds["dIData"], ds["zData"], ds["XData"], pr, ctx=ctx)
+    got = iak.nllIAK3D_CL(None, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True, PARBNDS, useReml, cl, parsBTfmd=P, rtnAll=True)
+    want = orc.nllIAK3D_CL(None, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True, PARBNDS, useReml, blk, ds["xData"],
+                           ds["dIData"], parsBTfmd=P, rtnTerms=True)
+    assert abs(got["nll"] - want["nll"]) <= TOL * abs(want["nll"])
+    assert scaled_err(got["vbetahat"], want["vbetahat"]) <= TOL
+    if optn == 4:
+        got["compLikMats"] = dict(got["compLikMats"]); got["compLikMats"]["units"] = clp["units"]
+    rng = np.random.default_rng(4)
+    xMap = np.vstack([rng.uniform(0, 100, (140, 2)), ds["xData"][::160]])
+    dIMap = synth.GSM_INTERVALS[[0, 3, 5]]
+    Xfn = lambda i, idx: synth.grid_design(xMap[idx], dIMap[i], 3)
+    pg = iak.predictIAK3D_CL(xMap, dIMap, Xfn, got)
+    zw, vw, lw, uw = orc.predictIAK3D_CL(xMap, dIMap, Xfn, want, modelx, types, cmeOpt)
+    assert scaled_err(pg["zMap"], zw) <= TOL
+    assert scaled_err(pg["vMap"], vw) <= TOL
+    assert scaled_err(pg["pi90LMap"], lw) <= TOL
