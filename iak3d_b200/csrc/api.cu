@@ -243,7 +243,7 @@ extern "C" int64_t iak3d_launch_count(iak3d_ctx* ctx) { return ctx ? ctx->launch
 static void free_slot(Slot* s) {
   if (!s) return;
   cudaFree(s->d_L); cudaFree(s->d_phix); cudaFree(s->d_phid); cudaFree(s->d_invd); cudaFree(s->d_flags);
-  cudaFree(s->d_logsum); cudaFree(s->d_G); cudaFree(s->d_lncol);
+  cudaFree(s->d_logsum); cudaFree(s->d_G); cudaFree(s->d_lncol); cudaFree(s->d_E);
   delete s;
 }
 
@@ -258,12 +258,14 @@ int iak_alloc_slot(iak3d_ctx* ctx, int64_t n, int32_t q, int64_t nxU, int64_t nd
   auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, std::max<size_t>(bytes, 16)); };
   A((void**)&s->d_L, (size_t)ubuf_doubles(s->ld, s->Npad) * sizeof(double));
   A((void**)&s->d_phix, (size_t)nxU * nxU * sizeof(double));
-  A((void**)&s->d_phid, (size_t)(NTAB_BUF * ndIU * ndIU + NTAB_BUF * ndIU + 3 * ndIU) * sizeof(double));
+  // tables | avVar vectors | avsd vectors | (16-byte aligned) combined tables of the factor build
+  A((void**)&s->d_phid, (size_t)(NTAB_BUF * ndIU * ndIU + round_up((NTAB_BUF + 3) * ndIU, 2) + 3 * ndIU * ndIU) * sizeof(double));
   A((void**)&s->d_invd, (size_t)s->nCB * INVD_BLOCK * sizeof(double));
   const size_t nflags = (size_t)s->nRB * s->nCB + s->nCB;
   A((void**)&s->d_flags, nflags * sizeof(int32_t));
   A((void**)&s->d_logsum, (size_t)s->nCB * sizeof(double));
   A((void**)&s->d_G, 64 * 64 * sizeof(double));
+  if (ndIU > 0) A((void**)&s->d_E, (size_t)2 * ndIU * round_up(n, 2) * sizeof(double));
   if (e == cudaSuccess) e = cudaMemsetAsync(s->d_flags, 0, nflags * sizeof(int32_t), ctx->stream);
   if (e != cudaSuccess) {
     ctx->err = std::string("slot allocation failed: ") + cudaGetErrorString(e);
@@ -414,6 +416,8 @@ int iak_square_tables(iak3d_ctx* ctx, const iak3d_ds* ds, const EvalPlan& pl, Sl
   const int64_t nd = ds->ndIU, nx = ds->nxU;
   double* const avbase = s->d_phid + (size_t)NTAB_BUF * nd * nd;
   for (int k = 0; k < 3; k++) { a->T[k] = nullptr; a->av[k] = nullptr; }
+  a->comb = s->d_phid + (size_t)NTAB_BUF * nd * nd + (size_t)round_up((NTAB_BUF + 3) * nd, 2);
+  a->Ebuf = s->d_E; a->E_shared = nullptr;
   auto plain_table = [&](int k, int buf, const double** out, const double** avout) -> int {   // iaCovMatern on the unique intervals
     const IaPrm& P = pl.prm[k];
     const double key[6] = {P.psi, P.tau0, P.tau1, P.tau2, P.g11[1], P.g11[2]};     // (ad, nud, sd function) determine the table
@@ -894,6 +898,13 @@ extern "C" int iak3d_nll_terms_batch_enqueue(iak3d_ctx* ctx, int32_t count, iak3
   for (int i = 0; i < count; i++) {
     if (!live[i]) continue;
     Slot* s = b->slots[i];
+    if (cov_one_table(cargs[i])) {           // the expansion depends on (dataset, table) only: share it inside the batch
+      for (int k = 0; k < i; k++)
+        if (live[k] && dss[k] == dss[i] && cov_one_table(cargs[k]) && cargs[k].T[0] == cargs[i].T[0]) {
+          cargs[i].E_shared = cargs[k].E_shared ? cargs[k].E_shared : cargs[k].Ebuf;
+          break;
+        }
+    }
     if (dss[i]->lncol >= 0 && dss[i]->lncol < q) {
       // lognormal data: column lncol of W is sigma2Vec - diag(C) of THIS evaluation (nrUpdatesIAK3DlnN.R:15, 194)
       st = iak_lnN_column(ctx, dss[i], plans[i], cargs[i], s);

@@ -68,6 +68,7 @@ struct Slot {
   double* d_logsum = nullptr;     // nCB
   double* d_G = nullptr;          // 64*64 Gram accumulator (WiAW)
   double* d_lncol = nullptr;      // 2n: sigma2Vec - diag(C) (lognormal bias column of W) | scratch
+  double* d_E = nullptr;          // 2 * ndIU * round_up(n,2): depth tables expanded along the rows (factor build)
   int32_t epoch = 0;              // flags are valid when == epoch
 };
 
@@ -133,6 +134,9 @@ struct CovArgs {
   // value(i,j) = [same loc](cx0 + cxd0*T0) + kd1*Td + phix*(cx1 + cxd1*T1) + (i==j)*cme
   const double* T[3];      // distinct depth tables (may alias); T[tidx[c]] for c = cd1, cxd0, cxd1; tidx<0 = absent
   const double* av[3] = {nullptr, nullptr, nullptr};   // avVarVec of each table on the row set (square builds only)
+  double* comb = nullptr;  // nd^2 doubles of per-evaluation workspace: S table of the factor build's generic path
+  double* Ebuf = nullptr;  // 2 * nd * round_up(n,2) doubles of per-evaluation workspace: depth tables expanded along the rows
+  const double* E_shared = nullptr;   // one-table case: the expansion another evaluation of the batch already made
   int tidx[3];
   int ntab;
   const double* phix;      // horizontal table or nullptr (nugget)
@@ -146,6 +150,7 @@ struct CovArgs {
 int launch_cov_factor_layout(iak3d_ctx* ctx, const CovArgs& a, const double* d_W, int32_t q, int64_t n, int64_t Npad, int64_t ld,
                              int32_t nCB, double* d_L, const double* d_lncol = nullptr, int lncol = -1);
 // out = a - b (n doubles)
+bool cov_one_table(const CovArgs& a);   // every present component reads depth table 0
 int launch_vec_sub(iak3d_ctx* ctx, const double* d_a, const double* d_b, int64_t n, double* d_out);
 // generic symmetric matrix (host-supplied C, optim_functions.R:268) + b' rows into the factor layout
 int launch_pack_factor_layout(iak3d_ctx* ctx, const double* d_C, int64_t n, const double* d_b, int32_t q, int64_t Npad,

@@ -31,10 +31,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
+bool cov_one_table(const CovArgs& h) {
+  for (int c = 0; c < 3; c++) if (h.tidx[c] > 0) return false;
+  return h.tidx[1] == 0;
+}
+
 struct CovDev {
   const double* T[3];
   int tidx[3];
   int ntab;
+  const double* comb;     // per-evaluation S(di,dj) = cx0 + cxd0*Phi_cxd0 table (nd^2), generic interior path
+  const double* E;        // depth tables expanded along the rows, see expand_tables_kernel: E[dj*ldE + i] (double or double2)
+  int64_t ldE;
+  int one_table;          // every present component reads the same depth table
   const double* phix;
   const uint8_t* same;
   double cx0, cx1, kd1, cxd0, cxd1, cme;
@@ -115,36 +124,59 @@ __global__ void __launch_bounds__(256) cov_factor_kernel(CovDev a, const double*
 
   if (R0 >= C0 + TN && R0 + TM <= n) {
     // ---- interior tile (the bulk of the matrix): strictly below the diagonal, all rows and columns are data.
-    // ncu showed the generic path issue-bound on integer / select work (ALU 54 %, ADU 47 %), not on memory: here all
-    // bounds checks are gone, table bases are resolved once, indices are 32-bit, equal-profile rows share the phi_x load.
-    const double* __restrict__ Td = a.tidx[0] >= 0 ? a.T[a.tidx[0] == 0 ? 0 : (a.tidx[0] == 1 ? 1 : 2)] : nullptr;
-    const double* __restrict__ T0 = a.tidx[1] >= 0 ? a.T[a.tidx[1] == 0 ? 0 : (a.tidx[1] == 1 ? 1 : 2)] : nullptr;
-    const double* __restrict__ T1 = a.tidx[2] >= 0 ? a.T[a.tidx[2] == 0 ? 0 : (a.tidx[2] == 1 ? 1 : 2)] : nullptr;
+    // ncu history of this path: (1) issue-bound on selects / 64-bit index arithmetic / six dependent FP64 operations per
+    // entry; (2) with the arithmetic folded into tables, bound by the L1 wavefronts of the depth-table GATHER -- the 64
+    // rows of a warp hit ~16 different cache lines of a table column.  Now the depth tables are first expanded along the
+    // rows (expand_tables_kernel: E[dj][i] = table[dj][did[i]], ndIU x n, a few % of the matrix), so that for a column
+    // c the values of all rows are CONTIGUOUS: one coalesced 16-byte load per thread and column.  An entry is
+    //     v = A(di,dj) + phi_x(xi,xj) * B(di,dj)  [+ S(di,dj) when the two rows share a profile]
+    // with A = kd1*Phi_cd1, B = cx1 + cxd1*Phi_cxd1, S = cx0 + cxd0*Phi_cxd0.  Rounding differs from the reference's
+    // term-by-term sums by an ulp; the tolerance on covariance entries is 1e-10.
     const double* __restrict__ phix = a.phix;
-    const int nd = (int)a.ndIU_r, nx = (int)a.nxU_r;
-    const double cx0 = a.cx0, cx1 = a.cx1, kd1 = a.kd1, cxd0 = a.cxd0, cxd1 = a.cxd1;
-    const bool t1_is_t0 = (T1 == T0), td_is_t0 = (Td == T0);
+    const unsigned nd = (unsigned)a.ndIU_r, nx = (unsigned)a.nxU_r;
+    const bool px_on = (phix != nullptr);
+    const int64_t ldE = a.ldE;
+    if (a.one_table) {
+      const double* __restrict__ Er = a.E + i0;
+      const double cx0 = a.cx0, cx1 = px_on ? a.cx1 : 0.0, kd1 = a.tidx[0] >= 0 ? a.kd1 : 0.0, cxd0 = a.cxd0, cxd1 = px_on ? a.cxd1 : 0.0;
 #pragma unroll 4
-    for (int cc = 0; cc < 16; cc++) {
-      const int lc = cg * 16 + cc;
-      const int xj = s_xc[lc], dj = s_dc[lc];
-      const unsigned tb = (unsigned)dj * (unsigned)nd;
-      double t0a = 0.0, t0b = 0.0, t1a = 0.0, t1b = 0.0, tda = 0.0, tdb = 0.0;
-      if (T0 != nullptr) { t0a = __ldg(T0 + tb + di0); t0b = __ldg(T0 + tb + di1); }
-      if (T1 != nullptr) { if (t1_is_t0) { t1a = t0a; t1b = t0b; } else { t1a = __ldg(T1 + tb + di0); t1b = __ldg(T1 + tb + di1); } }
-      if (Td != nullptr) { if (td_is_t0) { tda = t0a; tdb = t0b; } else { tda = __ldg(Td + tb + di0); tdb = __ldg(Td + tb + di1); } }
-      double va = 0.0, vb = 0.0;                        // off the diagonal: no cme; 0 + cx0 == cx0 exactly
-      if (xi0 == xj) { va = va + cx0; va = va + cxd0 * t0a; }
-      if (xi1 == xj) { vb = vb + cx0; vb = vb + cxd0 * t0b; }
-      if (Td != nullptr) { va = va + kd1 * tda; vb = vb + kd1 * tdb; }
-      if (phix != nullptr) {
-        const unsigned pb = (unsigned)xj * (unsigned)nx;
-        const double pa = __ldg(phix + pb + xi0);
-        const double pbv = (xi1 == xi0) ? pa : __ldg(phix + pb + xi1);
-        va = va + cx1 * pa; va = va + (cxd1 * pa) * t1a;
-        vb = vb + cx1 * pbv; vb = vb + (cxd1 * pbv) * t1b;
+      for (int cc = 0; cc < 16; cc++) {
+        const int lc = cg * 16 + cc;
+        const int xj = s_xc[lc];
+        const double2 t = __ldg(reinterpret_cast<const double2*>(Er + (int64_t)s_dc[lc] * ldE));
+        double pa = 0.0, pbv = 0.0;
+        if (px_on) {
+          const unsigned pb = (unsigned)xj * nx;
+          pa = __ldg(phix + pb + xi0);
+          pbv = (xi1 == xi0) ? pa : __ldg(phix + pb + xi1);
+        }
+        double va = fma(pa, fma(cxd1, t.x, cx1), kd1 * t.x);
+        double vb = fma(pbv, fma(cxd1, t.y, cx1), kd1 * t.y);
+        if (xi0 == xj) va += fma(cxd0, t.x, cx0);
+        if (xi1 == xj) vb += fma(cxd0, t.y, cx0);
+        *reinterpret_cast<double2*>(obase + cc * UL) = make_double2(va, vb);
       }
-      *reinterpret_cast<double2*>(obase + cc * UL) = make_double2(va, vb);
+    } else {
+      const double2* __restrict__ Er = reinterpret_cast<const double2*>(a.E) + i0;
+      const double* __restrict__ S = a.comb;
+#pragma unroll 4
+      for (int cc = 0; cc < 16; cc++) {
+        const int lc = cg * 16 + cc;
+        const int xj = s_xc[lc], dj = s_dc[lc];
+        const double2* e = Er + (int64_t)dj * ldE;
+        const double2 aba = __ldg(e), abb = __ldg(e + 1);
+        double pa = 0.0, pbv = 0.0;
+        if (px_on) {
+          const unsigned pb = (unsigned)xj * nx;
+          pa = __ldg(phix + pb + xi0);
+          pbv = (xi1 == xi0) ? pa : __ldg(phix + pb + xi1);
+        }
+        double va = fma(pa, aba.y, aba.x);
+        double vb = fma(pbv, abb.y, abb.x);
+        if (xi0 == xj) va += __ldg(S + (unsigned)dj * nd + di0);
+        if (xi1 == xj) vb += __ldg(S + (unsigned)dj * nd + di1);
+        *reinterpret_cast<double2*>(obase + cc * UL) = make_double2(va, vb);
+      }
     }
     return;
   }
@@ -172,6 +204,31 @@ __global__ void __launch_bounds__(256) cov_factor_kernel(CovDev a, const double*
   }
 }
 
+// Depth tables expanded along the rows for the interior tiles (coalesced instead of gathered loads):
+//   one table : E[dj*ldE + i]            = Phi[dj*nd + did[i]]
+//   generic   : E2[dj*ldE + i] (double2) = (kd1*Phi_cd1, cx1 + cxd1*Phi_cxd1)[dj*nd + did[i]],  S[dj*nd + di] = cx0 + cxd0*Phi_cxd0
+__global__ void expand_tables_kernel(CovDev a, int64_t n, int64_t ldE, double* __restrict__ E, double* __restrict__ Stab) {
+  const int64_t nd = a.ndIU_r;
+  const double* Td = a.tidx[0] >= 0 ? a.T[a.tidx[0]] : nullptr;
+  const double* T0 = a.tidx[1] >= 0 ? a.T[a.tidx[1]] : nullptr;
+  const double* T1 = (a.tidx[2] >= 0 && a.phix != nullptr) ? a.T[a.tidx[2]] : nullptr;
+  const int64_t total = nd * ldE;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t dj = idx / ldE, i = idx - dj * ldE;
+    const int64_t src = dj * nd + (i < n ? a.did_r[i] : 0);
+    if (a.one_table) {
+      E[idx] = a.T[0][src];
+    } else {
+      const double A = Td ? a.kd1 * Td[src] : 0.0;
+      const double B = a.phix != nullptr ? (T1 ? fma(a.cxd1, T1[src], a.cx1) : a.cx1) : 0.0;
+      reinterpret_cast<double2*>(E)[idx] = make_double2(A, B);
+    }
+  }
+  if (!a.one_table)
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nd * nd; i += (int64_t)gridDim.x * blockDim.x)
+      Stab[i] = T0 ? fma(a.cxd0, T0[i], a.cx0) : a.cx0;
+}
+
 int launch_cov_factor_layout(iak3d_ctx* ctx, const CovArgs& h, const double* d_W, int32_t q, int64_t n, int64_t Npad, int64_t ld,
                              int32_t nCB_, double* d_L, const double* d_lncol, int lncol) {
   CovDev a;
@@ -180,11 +237,24 @@ int launch_cov_factor_layout(iak3d_ctx* ctx, const CovArgs& h, const double* d_W
   a.cx0 = h.cx0; a.cx1 = h.cx1; a.kd1 = h.kd1; a.cxd0 = h.cxd0; a.cxd1 = h.cxd1; a.cme = h.cme;
   a.xid_r = h.xid_r; a.did_r = h.did_r; a.xid_c = h.xid_c; a.did_c = h.did_c;
   a.nr = h.nr; a.nc = h.nc; a.nxU_r = h.nxU_r; a.ndIU_r = h.ndIU_r;
+  a.comb = h.comb;
+  // one shared table: every present component points at table 0 (cxd0 is always present)
+  a.one_table = cov_one_table(h) ? 1 : 0;
+  a.ldE = round_up(n, 2);
   const int64_t nRB = ld / TM, nCB = nCB_;
   int64_t tiles = 0;
   for (int64_t c = 0; c < nCB; c++) tiles += nRB - c / 2;
-  // (a variant that staged the depth-table columns of a tile in shared memory was measured 2x slower than these
-  //  L1-served gathers at ndIU = 266 -- 140 us vs 68 us for n = 5000 -- and was dropped.)
+  if (h.E_shared != nullptr && a.one_table) {
+    a.E = h.E_shared;                       // another evaluation of this batch already expanded the same table
+  } else {
+    if (h.Ebuf == nullptr || h.comb == nullptr) { ctx->err = "cov_factor: expanded-table workspace missing"; return IAK3D_ERR_ARG; }
+    const int64_t total = h.ndIU_r * a.ldE;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+    expand_tables_kernel<<<blocks, 256, 0, ctx->stream>>>(a, n, a.ldE, h.Ebuf, h.comb);
+    ctx->launches++;
+    a.E = h.Ebuf;
+  }
   cov_factor_kernel<<<(unsigned)tiles, 256, 0, ctx->stream>>>(a, d_W, q, n, Npad, d_L, ld, (int)nCB, d_lncol, d_lncol ? lncol : -1);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
@@ -230,6 +300,7 @@ int launch_cov_rect(iak3d_ctx* ctx, const CovArgs& h, double* d_out, int64_t ld,
   a.cx0 = h.cx0; a.cx1 = h.cx1; a.kd1 = h.kd1; a.cxd0 = h.cxd0; a.cxd1 = h.cxd1; a.cme = h.cme;
   a.xid_r = h.xid_r; a.did_r = h.did_r; a.xid_c = h.xid_c; a.did_c = h.did_c;
   a.nr = h.nr; a.nc = h.nc; a.nxU_r = h.nxU_r; a.ndIU_r = h.ndIU_r;
+  a.comb = nullptr; a.one_table = 0; a.E = nullptr; a.ldE = 0;
   if (rows_total == 0 || cols_total == 0) return 0;
   dim3 grid((unsigned)((rows_total + TM - 1) / TM), (unsigned)((cols_total + TN - 1) / TN));
   if (grid.y > 65535) { ctx->err = "cov_rect: too many column tiles"; return IAK3D_ERR_ARG; }
