@@ -8,6 +8,8 @@
 // unique-pair tables of tables.cu, which stay L2-resident.  The pass is HBM-write-bound: 8 bytes per
 // entry, coalesced 16-byte stores down the (column-major) columns.  Row/column id tiles are staged
 // into shared memory with cp.async.bulk (TMA 1-D bulk copies, mbarrier completion).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -34,6 +36,26 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 bool cov_one_table(const CovArgs& h) {
   for (int c = 0; c < 3; c++) if (h.tidx[c] > 0) return false;
   return h.tidx[1] == 0;
+}
+
+// L2 residency: the matrix streams through L2 once (evict-first stores) so that it does not push out the small tables
+// every entry is made from (evict-last loads).  ncu on the version without hints: L2 hit rate 31 %, the kernel stalled on
+// table loads that went to HBM behind 1.6 GB of its own writes.  The loads are NOT volatile: the compiler must be free
+// to issue the loads of several columns before the first store (the kernel is bound by memory latency).
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p; asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p; asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ double ld_keep(const double* p, uint64_t pol) {
+  double v; asm("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol)); return v;
+}
+__device__ __forceinline__ double2 ld_keep2(const double2* p, uint64_t pol) {
+  double2 v; asm("ld.global.nc.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol)); return v;
+}
+__device__ __forceinline__ void st_stream2(double* p, double a, double b, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(p), "d"(a), "d"(b), "l"(pol) : "memory");
 }
 
 struct CovDev {
@@ -78,104 +100,105 @@ __device__ __forceinline__ double cov_value(const CovDev& a, int xi, int di, int
 __global__ void __launch_bounds__(256) cov_factor_kernel(CovDev a, const double* __restrict__ W, int q, int64_t n,
                                                          int64_t Npad, double* __restrict__ L, int64_t ld, int nCB,
                                                          const double* __restrict__ lncol_v, int lncol) {
-  __shared__ __align__(16) int32_t s_xr[TM], s_dr[TM], s_xc[TN], s_dc[TN];
-  __shared__ __align__(8) uint64_t bar;
-  // decode (r, j) from the linear lower-triangular tile index: column-block j has row-blocks j/2 .. nRB-1
+  // tile (r, j): column block j = blockIdx.y has row blocks j/2 .. nRB-1; CTAs beyond the last row block leave at once
   const int nRB = (int)(ld / TM);
-  int j = 0, r = 0;
-  {
-    int64_t t = blockIdx.x;   // tiles enumerated column-block by column-block
-    // tiles before column j: sum_{c<j} (nRB - c/2)
-    // solve by a short loop (nCB <= a few thousand; one thread per CTA would do, all do it redundantly)
-    int lo = 0, hi = nCB - 1;
-    auto before = [&](int64_t c) -> int64_t {   // number of tiles in columns [0,c)
-      const int64_t h = c / 2;                   // pairs of columns share the same first row-block
-      return c * (int64_t)nRB - (h * (h - 1) + (c & 1) * h);   // sum_{c'<c} floor(c'/2) = h(h-1) + (c odd ? h : 0)
-    };
-    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (before(mid) <= t) lo = mid; else hi = mid - 1; }
-    j = lo; r = (int)(t - before(j)) + j / 2;
-  }
+  const int j = blockIdx.y, r = (j >> 1) + blockIdx.x;
+  if (r >= nRB) return;
   const int64_t R0 = (int64_t)r * TM, C0 = (int64_t)j * TN;
   const int tid = threadIdx.x;
-  // stage the id tiles (TMA bulk copies when the whole tile is inside the data range)
-  const bool rows_in = (R0 + TM <= n), cols_in = (C0 + TN <= n);
-  if (tid == 0) { mbar_init(&bar, 1); }
-  __syncthreads();
-  if (tid == 0) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    uint32_t bytes = 0;
-    if (rows_in) bytes += 2 * TM * 4;
-    if (cols_in) bytes += 2 * TN * 4;
-    mbar_expect_tx(&bar, bytes);
-    if (rows_in) { bulk_g2s(s_xr, a.xid_r + R0, TM * 4, &bar); bulk_g2s(s_dr, a.did_r + R0, TM * 4, &bar); }
-    if (cols_in) { bulk_g2s(s_xc, a.xid_c + C0, TN * 4, &bar); bulk_g2s(s_dc, a.did_c + C0, TN * 4, &bar); }
-  }
-  if (!rows_in && tid < TM) { const int64_t i = R0 + tid; s_xr[tid] = i < n ? a.xid_r[i] : -1; s_dr[tid] = i < n ? a.did_r[i] : 0; }
-  if (!cols_in && tid < TN) { const int64_t c = C0 + tid; s_xc[tid] = c < n ? a.xid_c[c] : -1; s_dc[tid] = c < n ? a.did_c[c] : 0; }
-  __syncthreads();
-  mbar_wait(&bar, 0);
-
   const int rp = tid & 63, cg = tid >> 6;           // row pair (2 rows), column group (16 columns)
   const int lr = rp * 2;
   const int64_t i0 = R0 + lr;
-  const int xi0 = s_xr[lr], di0 = s_dr[lr], xi1 = s_xr[lr + 1], di1 = s_dr[lr + 1];
   // this thread's 16 columns lie in one unit: column half cg/2, columns (cg&1)*16.. of it; rows lr, lr+1 in row unit lr/64
   double* const obase = L + (((int64_t)(2 * j + (cg >> 1))) * (nRB * 2) + 2 * r + (lr >> 6)) * UNIT + ((cg & 1) * 16) * UL + (lr & 63);
 
   if (R0 >= C0 + TN && R0 + TM <= n) {
     // ---- interior tile (the bulk of the matrix): strictly below the diagonal, all rows and columns are data.
-    // ncu history of this path: (1) issue-bound on selects / 64-bit index arithmetic / six dependent FP64 operations per
-    // entry; (2) with the arithmetic folded into tables, bound by the L1 wavefronts of the depth-table GATHER -- the 64
-    // rows of a warp hit ~16 different cache lines of a table column.  Now the depth tables are first expanded along the
-    // rows (expand_tables_kernel: E[dj][i] = table[dj][did[i]], ndIU x n, a few % of the matrix), so that for a column
-    // c the values of all rows are CONTIGUOUS: one coalesced 16-byte load per thread and column.  An entry is
-    //     v = A(di,dj) + phi_x(xi,xj) * B(di,dj)  [+ S(di,dj) when the two rows share a profile]
-    // with A = kd1*Phi_cd1, B = cx1 + cxd1*Phi_cxd1, S = cx0 + cxd0*Phi_cxd0.  Rounding differs from the reference's
-    // term-by-term sums by an ulp; the tolerance on covariance entries is 1e-10.
+    // No shared memory, no barrier: every warp is independent.  A thread reads the ids of its 2 rows (one 8-byte load
+    // each for location and interval) and of its 16 columns (warp-uniform 16-byte loads), then per 8 columns issues
+    // all loads -- the row-expanded depth table E[dj][i] (expand_tables_kernel; coalesced 16 bytes per thread) and
+    // phi_x(xi, xj) (1-2 cache lines per warp) -- before any arithmetic or store: the kernel is bound by memory latency.
+    //     v = Phi * (kd1 + cxd1 phi_x) + cx1 phi_x   [+ cx0 + cxd0 Phi when the two rows share a profile: rare, warp-uniform test]
+    // Stores are evict-first and table loads evict-last, so that the matrix streaming through L2 does not push out the
+    // tables it is made from (ncu before the hints: L2 hit rate 31 %).  Rounding differs from the reference's term-by-term
+    // sums by an ulp; the tolerance on covariance entries is 1e-10.
+    // History (profiles/): v1 ~85 instructions per entry (selects, 64-bit index arithmetic, six dependent FP64 ops): issue-
+    // bound; v2 arithmetic folded into tables: bound by the L1 wavefronts of the depth-table GATHER; v3 tables expanded along
+    // the rows: L2 thrash + per-CTA id staging through TMA and a barrier (a third of all instructions was prologue).
+    // (A warp-specialised persistent variant with TMA-staged table segments and TMA bulk stores of whole units was
+    // measured 3x slower: 32 one-KB bulk copies per item cost ~2000 cycles of issue and one CTA per SM exposed latency.)
     const double* __restrict__ phix = a.phix;
     const unsigned nd = (unsigned)a.ndIU_r, nx = (unsigned)a.nxU_r;
     const bool px_on = (phix != nullptr);
     const int64_t ldE = a.ldE;
+    const uint64_t keep = policy_evict_last(), strm = policy_evict_first();
+    const int2 xx = __ldg(reinterpret_cast<const int2*>(a.xid_r + i0)), dd = __ldg(reinterpret_cast<const int2*>(a.did_r + i0));
+    const int xi0 = xx.x, xi1 = xx.y, di0 = dd.x, di1 = dd.y;
+    const int4* __restrict__ xc4 = reinterpret_cast<const int4*>(a.xid_c + C0 + cg * 16);
+    const int4* __restrict__ dc4 = reinterpret_cast<const int4*>(a.did_c + C0 + cg * 16);
+    const bool same_row_profile = (xi1 == xi0);
     if (a.one_table) {
       const double* __restrict__ Er = a.E + i0;
       const double cx0 = a.cx0, cx1 = px_on ? a.cx1 : 0.0, kd1 = a.tidx[0] >= 0 ? a.kd1 : 0.0, cxd0 = a.cxd0, cxd1 = px_on ? a.cxd1 : 0.0;
-#pragma unroll 4
-      for (int cc = 0; cc < 16; cc++) {
-        const int lc = cg * 16 + cc;
-        const int xj = s_xc[lc];
-        const double2 t = __ldg(reinterpret_cast<const double2*>(Er + (int64_t)s_dc[lc] * ldE));
-        double pa = 0.0, pbv = 0.0;
-        if (px_on) {
-          const unsigned pb = (unsigned)xj * nx;
-          pa = __ldg(phix + pb + xi0);
-          pbv = (xi1 == xi0) ? pa : __ldg(phix + pb + xi1);
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        int xjs[8], djs[8];
+        { const int4 u0 = __ldg(xc4 + 2 * h), u1 = __ldg(xc4 + 2 * h + 1), w0 = __ldg(dc4 + 2 * h), w1 = __ldg(dc4 + 2 * h + 1);
+          xjs[0] = u0.x; xjs[1] = u0.y; xjs[2] = u0.z; xjs[3] = u0.w; xjs[4] = u1.x; xjs[5] = u1.y; xjs[6] = u1.z; xjs[7] = u1.w;
+          djs[0] = w0.x; djs[1] = w0.y; djs[2] = w0.z; djs[3] = w0.w; djs[4] = w1.x; djs[5] = w1.y; djs[6] = w1.z; djs[7] = w1.w; }
+        double2 t[8]; double pa[8], pb[8];
+#pragma unroll
+        for (int cc = 0; cc < 8; cc++) {
+          t[cc] = ld_keep2(reinterpret_cast<const double2*>(Er + (int64_t)djs[cc] * ldE), keep);
+          pa[cc] = 0.0; pb[cc] = 0.0;
+          if (px_on) {      // (re-using phi_x across the consecutive columns of one profile was measured 20 % slower: it chains the loads)
+            const unsigned pbase = (unsigned)xjs[cc] * nx;
+            pa[cc] = ld_keep(phix + pbase + xi0, keep);
+            if (!same_row_profile) pb[cc] = ld_keep(phix + pbase + xi1, keep);
+          }
         }
-        double va = fma(pa, fma(cxd1, t.x, cx1), kd1 * t.x);
-        double vb = fma(pbv, fma(cxd1, t.y, cx1), kd1 * t.y);
-        if (xi0 == xj) va += fma(cxd0, t.x, cx0);
-        if (xi1 == xj) vb += fma(cxd0, t.y, cx0);
-        *reinterpret_cast<double2*>(obase + cc * UL) = make_double2(va, vb);
+#pragma unroll
+        for (int cc = 0; cc < 8; cc++) {
+          const double pbv = same_row_profile ? pa[cc] : pb[cc];
+          double va = fma(t[cc].x, fma(cxd1, pa[cc], kd1), cx1 * pa[cc]);
+          double vb = fma(t[cc].y, fma(cxd1, pbv, kd1), cx1 * pbv);
+          if (__any_sync(0xffffffffu, (xi0 == xjs[cc]) | (xi1 == xjs[cc]))) {     // rare: rows of the column's own profile
+            if (xi0 == xjs[cc]) va += fma(cxd0, t[cc].x, cx0);
+            if (xi1 == xjs[cc]) vb += fma(cxd0, t[cc].y, cx0);
+          }
+          st_stream2(obase + (h * 8 + cc) * UL, va, vb, strm);
+        }
       }
     } else {
       const double2* __restrict__ Er = reinterpret_cast<const double2*>(a.E) + i0;
       const double* __restrict__ S = a.comb;
-#pragma unroll 4
-      for (int cc = 0; cc < 16; cc++) {
-        const int lc = cg * 16 + cc;
-        const int xj = s_xc[lc], dj = s_dc[lc];
-        const double2* e = Er + (int64_t)dj * ldE;
-        const double2 aba = __ldg(e), abb = __ldg(e + 1);
-        double pa = 0.0, pbv = 0.0;
-        if (px_on) {
-          const unsigned pb = (unsigned)xj * nx;
-          pa = __ldg(phix + pb + xi0);
-          pbv = (xi1 == xi0) ? pa : __ldg(phix + pb + xi1);
+#pragma unroll
+      for (int h = 0; h < 4; h++) {
+        int xjs[4], djs[4];
+        { const int4 u0 = __ldg(xc4 + h), w0 = __ldg(dc4 + h);
+          xjs[0] = u0.x; xjs[1] = u0.y; xjs[2] = u0.z; xjs[3] = u0.w; djs[0] = w0.x; djs[1] = w0.y; djs[2] = w0.z; djs[3] = w0.w; }
+        double2 e0[4], e1[4]; double pa[4], pb[4];
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++) {
+          const double2* e = Er + (int64_t)djs[cc] * ldE;
+          e0[cc] = ld_keep2(e, keep); e1[cc] = ld_keep2(e + 1, keep);
+          pa[cc] = 0.0; pb[cc] = 0.0;
+          if (px_on) {      // (re-using phi_x across the consecutive columns of one profile was measured 20 % slower: it chains the loads)
+            const unsigned pbase = (unsigned)xjs[cc] * nx;
+            pa[cc] = ld_keep(phix + pbase + xi0, keep);
+            if (!same_row_profile) pb[cc] = ld_keep(phix + pbase + xi1, keep);
+          }
         }
-        double va = fma(pa, aba.y, aba.x);
-        double vb = fma(pbv, abb.y, abb.x);
-        if (xi0 == xj) va += __ldg(S + (unsigned)dj * nd + di0);
-        if (xi1 == xj) vb += __ldg(S + (unsigned)dj * nd + di1);
-        *reinterpret_cast<double2*>(obase + cc * UL) = make_double2(va, vb);
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++) {
+          const double pbv = same_row_profile ? pa[cc] : pb[cc];
+          double va = fma(pa[cc], e0[cc].y, e0[cc].x), vb = fma(pbv, e1[cc].y, e1[cc].x);
+          if (__any_sync(0xffffffffu, (xi0 == xjs[cc]) | (xi1 == xjs[cc]))) {
+            if (xi0 == xjs[cc]) va += __ldg(S + (unsigned)djs[cc] * nd + di0);
+            if (xi1 == xjs[cc]) vb += __ldg(S + (unsigned)djs[cc] * nd + di1);
+          }
+          st_stream2(obase + (h * 4 + cc) * UL, va, vb, strm);
+        }
       }
     }
     return;
@@ -186,16 +209,15 @@ __global__ void __launch_bounds__(256) cov_factor_kernel(CovDev a, const double*
   for (int cc = 0; cc < 16; cc++) {
     const int lc = cg * 16 + cc;
     const int64_t c = C0 + lc;
-    const int xj = s_xc[lc], dj = s_dc[lc];
+    const int xj = c < n ? a.xid_c[c] : -1, dj = c < n ? a.did_c[c] : 0;
     double v[2];
 #pragma unroll
     for (int e = 0; e < 2; e++) {
       const int64_t i = i0 + e;
-      const int xi = e ? xi1 : xi0, di = e ? di1 : di0;
       double val;
       if (i < c) val = 0.0;                                             // strictly upper: never read
       else if (c >= n) val = (i == c && c < Npad) ? 1.0 : 0.0;          // identity padding columns
-      else if (i < n) val = cov_value(a, xi, di, xj, dj, i == c);
+      else if (i < n) val = cov_value(a, a.xid_r[i], a.did_r[i], xj, dj, i == c);
       else if (i >= Npad && i < Npad + q) val = (i - Npad == lncol) ? lncol_v[c] : W[(int64_t)(i - Npad) * n + c];   // W' rows
       else val = 0.0;
       v[e] = val;
@@ -207,26 +229,27 @@ __global__ void __launch_bounds__(256) cov_factor_kernel(CovDev a, const double*
 // Depth tables expanded along the rows for the interior tiles (coalesced instead of gathered loads):
 //   one table : E[dj*ldE + i]            = Phi[dj*nd + did[i]]
 //   generic   : E2[dj*ldE + i] (double2) = (kd1*Phi_cd1, cx1 + cxd1*Phi_cxd1)[dj*nd + did[i]],  S[dj*nd + di] = cx0 + cxd0*Phi_cxd0
-__global__ void expand_tables_kernel(CovDev a, int64_t n, int64_t ldE, double* __restrict__ E, double* __restrict__ Stab) {
+__global__ void __launch_bounds__(256) expand_tables_kernel(CovDev a, int64_t n, int64_t ldE, double* __restrict__ E,
+                                                            double* __restrict__ Stab) {
+  // blockIdx.y = dj (one table column, 8 nd bytes: L1-resident), blockIdx.x walks the rows: coalesced id reads and writes
   const int64_t nd = a.ndIU_r;
-  const double* Td = a.tidx[0] >= 0 ? a.T[a.tidx[0]] : nullptr;
-  const double* T0 = a.tidx[1] >= 0 ? a.T[a.tidx[1]] : nullptr;
-  const double* T1 = (a.tidx[2] >= 0 && a.phix != nullptr) ? a.T[a.tidx[2]] : nullptr;
-  const int64_t total = nd * ldE;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t dj = idx / ldE, i = idx - dj * ldE;
-    const int64_t src = dj * nd + (i < n ? a.did_r[i] : 0);
+  const int64_t dj = blockIdx.y;
+  const double* Td = a.tidx[0] >= 0 ? a.T[a.tidx[0]] + dj * nd : nullptr;
+  const double* T0 = a.tidx[1] >= 0 ? a.T[a.tidx[1]] + dj * nd : nullptr;
+  const double* T1 = (a.tidx[2] >= 0 && a.phix != nullptr) ? a.T[a.tidx[2]] + dj * nd : nullptr;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < ldE; i += (int64_t)gridDim.x * blockDim.x) {
+    const int di = i < n ? a.did_r[i] : 0;
     if (a.one_table) {
-      E[idx] = a.T[0][src];
+      E[dj * ldE + i] = a.T[0][dj * nd + di];
     } else {
-      const double A = Td ? a.kd1 * Td[src] : 0.0;
-      const double B = a.phix != nullptr ? (T1 ? fma(a.cxd1, T1[src], a.cx1) : a.cx1) : 0.0;
-      reinterpret_cast<double2*>(E)[idx] = make_double2(A, B);
+      const double A = Td ? a.kd1 * Td[di] : 0.0;
+      const double B = a.phix != nullptr ? (T1 ? fma(a.cxd1, T1[di], a.cx1) : a.cx1) : 0.0;
+      reinterpret_cast<double2*>(E)[dj * ldE + i] = make_double2(A, B);
     }
   }
   if (!a.one_table)
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nd * nd; i += (int64_t)gridDim.x * blockDim.x)
-      Stab[i] = T0 ? fma(a.cxd0, T0[i], a.cx0) : a.cx0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nd; i += (int64_t)gridDim.x * blockDim.x)
+      Stab[dj * nd + i] = T0 ? fma(a.cxd0, T0[i], a.cx0) : a.cx0;
 }
 
 int launch_cov_factor_layout(iak3d_ctx* ctx, const CovArgs& h, const double* d_W, int32_t q, int64_t n, int64_t Npad, int64_t ld,
@@ -248,14 +271,17 @@ int launch_cov_factor_layout(iak3d_ctx* ctx, const CovArgs& h, const double* d_W
     a.E = h.E_shared;                       // another evaluation of this batch already expanded the same table
   } else {
     if (h.Ebuf == nullptr || h.comb == nullptr) { ctx->err = "cov_factor: expanded-table workspace missing"; return IAK3D_ERR_ARG; }
-    const int64_t total = h.ndIU_r * a.ldE;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
-    expand_tables_kernel<<<blocks, 256, 0, ctx->stream>>>(a, n, a.ldE, h.Ebuf, h.comb);
+    if (h.ndIU_r > 65535) { ctx->err = "cov_factor: more than 65535 unique depth intervals"; return IAK3D_ERR_ARG; }
+    unsigned bx = (unsigned)((a.ldE + 255) / 256);
+    if (bx > 64) bx = 64;
+    expand_tables_kernel<<<dim3(bx, (unsigned)h.ndIU_r), 256, 0, ctx->stream>>>(a, n, a.ldE, h.Ebuf, h.comb);
     ctx->launches++;
     a.E = h.Ebuf;
   }
-  cov_factor_kernel<<<(unsigned)tiles, 256, 0, ctx->stream>>>(a, d_W, q, n, Npad, d_L, ld, (int)nCB, d_lncol, d_lncol ? lncol : -1);
+  (void)tiles;
+  if (nCB > 65535) { ctx->err = "cov_factor: more than 65535 column blocks"; return IAK3D_ERR_ARG; }
+  dim3 grid((unsigned)nRB, (unsigned)nCB);              // CTAs past the last row block of their column block leave at once
+  cov_factor_kernel<<<grid, 256, 0, ctx->stream>>>(a, d_W, q, n, Npad, d_L, ld, (int)nCB, d_lncol, d_lncol ? lncol : -1);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return 0;
