@@ -210,16 +210,29 @@ def run_s5(args, rank, local_rank, world, comm):
         single_eval_ms=single_ms, single_eval_per_s=1e3 / single_ms,
         stage_ms=dict(tables=stage[0], cov_build=stage[1], factorise=stage[2], finish=stage[3]),
         roofline=dict(kernel="tile_task_kernel (tile Cholesky + bordered solves, FP64 DMMA)", bound="tensor", achieved=tf,
-                      peak=peaks["dmma"], unit="TFLOP/s", frac=tf / peaks["dmma"], traffic=None,
+                      peak=peaks["dmma"], unit="TFLOP/s", frac=tf / peaks["dmma"], traffic=ncu_traffic("tile_task_kernel", n, nb),
                       flops_per_launch=nb * n ** 3 / 3.0,
                       peak_source="FP64 mma.sync m8n8k4 microbenchmark run inside this bench (MEASURED_PEAKS.json holds no FP64 "
                                   "figure); DFMA microbenchmark = %.1f TFLOP/s" % peaks["dfma"]),
         roofline_cov_build=dict(kernel="cov_factor_kernel", bound="hbm", achieved=cov_gbs, peak=hbm_peak, unit="GB/s",
-                                frac=cov_gbs / hbm_peak, bytes_per_launch=8.0 * n * (n + 1) / 2.0, peak_source=hbm_src),
+                                frac=cov_gbs / hbm_peak, bytes_per_launch=8.0 * n * (n + 1) / 2.0, peak_source=hbm_src,
+                                traffic=ncu_traffic("cov_factor_kernel", n, 1),
+                                note="stage time of nb launches + nb table expansions; write-only peak of this layout measured at "
+                                     "7.0 TB/s (n = 20000) / 4.5 TB/s (n = 5000, one launch), scripts/micro/store_pattern.cu"),
         e2e=dict(value=evals / e2e_s, unit="evals/s", h2d_bytes_per_step=int(W.nbytes + nb * C.sizeof(Pars)),
                  d2h_bytes_per_step=int(nb * (2 + q * q) * 8)),
         gpu_launches=int(launches), clocks=clocks)
     return out, ctx
+
+
+def ncu_traffic(kernel, n, evals):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture, when one exists for exactly this shape."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic_r01.json")) as f:
+            e = json.load(f)[kernel]
+        return float(e["bytes"]) if (e["n"] == n and e["evals_per_launch"] == evals) else None
+    except Exception:
+        return None
 
 
 def measured_peak(key, fallback):

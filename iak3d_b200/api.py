@@ -984,6 +984,39 @@ def predictIAK3D(xMap, dIMap, XMap_fn, lmmFit, nxPerBatch=2000, cells=None, vXUM
     return dict(zMap=zMap, vMap=vMap, pi90LMap=lo, pi90UMap=hi)
 
 
+def profilePredictIAK3D(xMap, dIMap, XMap, lmmFit, vXUMap=None, rqrBTfmdPreds=True, rtnBigMats=False):
+    """predictIAK3D.R:292-504 for compLikOptn = 0: predictions for a full profile -- many depth intervals `dIMap` at ONE
+    location `xMap` -- with the design rows `XMap` given (makeXvX is an input of the hot path).  Returns what the reference
+    returns: zMap, vMap, pi90LMap, pi90UMap, XMap, muhatMap, Ckk and, with `rtnBigMats`, Ckh (setCIAK3D2) and iC."""
+    xMap = np.asarray(xMap, float).reshape(-1, 2)
+    if xMap.shape[0] != 1:
+        raise ValueError("Error - profilePredictIAK3D is for a single location at a time (ie xMap should have one row)!")
+    dIMap = np.round(np.asarray(dIMap, float).reshape(-1, 2), 2)        # :349
+    nd = dIMap.shape[0]
+    XMap = np.asarray(XMap, float).reshape(nd, -1)
+    xRep = np.repeat(xMap, nd, axis=0)                                  # :395-397
+    fit = lmmFit["fit"]
+    z, v = fit.predict(xRep, dIMap, XMap)
+    t = fit.fetch_terms()
+    lnN = bool(lmmFit.get("lnTfmdData", False))
+    if lnN:                                                             # :468-472, 488-491
+        muhat = setmuIAK3D(XMap, vXUMap, lmmFit["iU"], lmmFit["betahat"], t["Ckk"], t["sigma2Veck"]).reshape(-1)
+        z = muhat + t["CkhiCz_muhat"]; v = t["Ckk"] - t["CkhiCChk"]
+    else:
+        muhat = (XMap @ np.asarray(lmmFit["betahat"], float).reshape(-1, 1)).reshape(-1)
+    with np.errstate(invalid="ignore"):
+        s_ = np.sqrt(v)
+    lo, hi = z - 1.645 * s_, z + 1.645 * s_
+    if lnN and rqrBTfmdPreds:
+        z = np.exp(z + 0.5 * v); lo, hi = np.exp(lo), np.exp(hi); v = (np.exp(v) - 1.0) * z ** 2
+    out = dict(zMap=z, vMap=v, pi90LMap=lo, pi90UMap=hi, XMap=XMap, muhatMap=muhat, Ckk=t["Ckk"], lmmFit=lmmFit)
+    if rtnBigMats:
+        sm = lmmFit["setupMats"]
+        types = (lmmFit["sdfdType_cd1"], lmmFit["sdfdType_cxd0"], lmmFit["sdfdType_cxd1"])
+        out["Ckh"] = setCIAK3D2(lmmFit["parsBTfmd"], lmmFit["modelx"], *types, lmmFit["cmeOpt"], SetupMats2(xRep, dIMap, None, None, setup2=sm))
+        out["iC"] = fit.get_big(want_C=False, want_iC=True)[1]
+    return out
+
 # ---------------------------------------------------------------------------------------------
 # composite-likelihood block prediction (compositeLikIAK3D.R:471-607; dispatched at predictIAK3D.R:211-226)
 # ---------------------------------------------------------------------------------------------

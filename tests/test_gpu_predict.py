@@ -146,3 +146,22 @@ def test_cl_block_prediction_vs_oracle(ctx, optn, useReml, kind, nonstat):
     assert scaled_err(pg["zMap"], zw) <= TOL
     assert scaled_err(pg["vMap"], vw) <= TOL
     assert scaled_err(pg["pi90LMap"], lw) <= TOL
+
+
+def test_profilePredict_vs_oracle(ctx):
+    """profilePredictIAK3D (predictIAK3D.R:292-504): one location, a full profile of depth intervals, incl. Ckh and iC."""
+    ds = synth.make_dataset(450, 27)
+    got, want, modelx, types, cmeOpt = _fit_both(ctx, ds, "matern0.5", True, 0.5)
+    x1 = np.array([[41.3, 57.9]])
+    dI = np.array([[0.0, 0.05], [0.05, 0.13], [0.13, 0.27], [0.27, 0.61], [0.61, 1.04], [1.04, 1.5], [1.5, 2.0]])
+    X = synth.grid_design(np.repeat(x1, len(dI), axis=0), dI[0], 3)
+    for k in range(len(dI)):
+        X[k] = synth.grid_design(x1, dI[k], 3)[0]
+    pg = iak.profilePredictIAK3D(x1, dI, X, got, rtnBigMats=True)
+    zw, vw, lw, uw = orc.predictIAK3D(x1, dI, lambda i, idx: X[i:i + 1], want, modelx, types, cmeOpt)
+    assert scaled_err(pg["zMap"], zw[:, 0]) <= TOL and scaled_err(pg["vMap"], vw[:, 0]) <= TOL
+    assert scaled_err(pg["pi90UMap"], uw[:, 0]) <= TOL
+    sm2 = orc.setupIAK3D2(np.repeat(x1, len(dI), axis=0), dI, ds["xData"], ds["dIData"])
+    assert scaled_err(pg["Ckh"], orc.setCIAK3D2(want["parsBTfmd"], modelx, *types, cmeOpt, sm2)) <= 1e-10
+    assert scaled_err(pg["iC"], want["iC"]) <= 1e-7
+    assert scaled_err(pg["muhatMap"], (X @ want["betahat"]).ravel()) <= TOL
