@@ -9,24 +9,41 @@
 .iak3d_ref <- list(setupIAK3D = setupIAK3D, lndetANDinvCb = lndetANDinvCb, nllIAK3D = nllIAK3D)
 .iak3d_modelx <- c(nugget = 0, spherical = 1, matern = 2, wendland = 3)
 
+.iak3d_maxspl <- 12   # IAK3D_MAX_SPL
 .iak3d_pv <- function(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, quirk_scale = 1){
   tau <- function(v, t){ if(t == -1){ as.numeric(v)[1:2] }else{ c(0, 0) } }
+  spl <- function(v, t){ out <- numeric(.iak3d_maxspl) ; if(t > 0){ out[seq(t)] <- as.numeric(v)[seq(t)] } ; out }
   nz <- function(v){ if(is.null(v) || length(v) == 0 || is.na(v)) NaN else as.numeric(v) }
   c(.iak3d_modelx[[modelx]], cmeOpt, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, 1,
     nz(parsBTfmd$ax), nz(parsBTfmd$nux), nz(parsBTfmd$ad), nz(parsBTfmd$nud),
     parsBTfmd$cx0, parsBTfmd$cx1, parsBTfmd$cd1, parsBTfmd$cxd0, parsBTfmd$cxd1, parsBTfmd$cme,
     tau(parsBTfmd$sdfdPars_cd1, sdfdType_cd1), tau(parsBTfmd$sdfdPars_cxd0, sdfdType_cxd0),
-    tau(parsBTfmd$sdfdPars_cxd1, sdfdType_cxd1), quirk_scale)
+    tau(parsBTfmd$sdfdPars_cxd1, sdfdType_cxd1), quirk_scale,
+    spl(parsBTfmd$sdfdPars_cd1, sdfdType_cd1), spl(parsBTfmd$sdfdPars_cxd0, sdfdType_cxd0), spl(parsBTfmd$sdfdPars_cxd1, sdfdType_cxd1))
 }
 
-### setupIAK3D: the id vectors live on the device; spline sd functions (sdfdType > 0) fall back to the reference.
-setupIAK3D <- function(xData, dIData, ...){
-  args <- list(...)
-  types <- unlist(args[c('sdfdType_cd1', 'sdfdType_cxd0', 'sdfdType_cxd1')])
-  if(length(types) > 0 && max(types) > 0){ return(.iak3d_ref$setupIAK3D(xData = xData, dIData = dIData, ...)) }
+### setupIAK3D: the id vectors live on the device.  Spline sd functions (sdfdType > 0): the interval-averaged spline
+### bases on the unique depth intervals (iaCovMatern.R:520-539) are made here with the reference's own
+### makeXnsClampedUG0 and handed to the library, which then evaluates setCApproxIAK3D[2] on the device.
+.iak3d_spl_bases <- function(dI, types, sdfdKnots){
+  nm <- c('cd1', 'cxd0', 'cxd1')
+  lapply(seq(3), function(c){ if(types[c] > 0){
+    makeXnsClampedUG0(x = dI, bdryKnots = sdfdKnots$bdryKnots, intKnots = sdfdKnots[[paste0('intKnots_', nm[c])]], paramVs = 1) }else{ NULL } })
+}
+setupIAK3D <- function(xData, dIData, nDscPts = 0, partSetup = FALSE, sdfdType_cd1 = 0, sdfdType_cxd0 = 0, sdfdType_cxd1 = 0,
+                       sdfdKnots = NULL, siteIDData = NULL, XData = NULL, colnames4ssre = NULL){
+  if(!is.null(siteIDData)){ return(.iak3d_ref$setupIAK3D(xData, dIData, nDscPts, partSetup, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1,
+                                                         sdfdKnots, siteIDData, XData, colnames4ssre)) } # site-specific random effects: reference path
   xData <- as.matrix(xData) ; dIData <- as.matrix(dIData)
-  list(iak3d = .Call('iak3dR_dataset', xData, dIData, NULL), xData = xData, dIData = dIData, n = nrow(xData),
-       Kx = TRUE) # 'Kx' non-NULL: the reference's is.null(setupMats$Kx) guards (fitIAK3D.R:965) stay quiet
+  types <- c(sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1)
+  h <- .Call('iak3dR_dataset', xData, dIData, NULL)
+  if(max(types) > 0){
+    dIU <- dIData[!duplicated(dIData), , drop = FALSE]                 # first-occurrence order == the library's ids
+    B <- .iak3d_spl_bases(dIU, types, sdfdKnots)
+    for(c in seq(3)){ if(!is.null(B[[c]])){ .Call('iak3dR_set_sdfd_spline', h, as.integer(c - 1), B[[c]]) } }
+  }
+  list(iak3d = h, xData = xData, dIData = dIData, n = nrow(xData), sdfdTypes = types, sdfdKnots = sdfdKnots,
+       maxd = max(max(dIData), 2), Kx = TRUE) # 'Kx' non-NULL: the reference's is.null(setupMats$Kx) guards (fitIAK3D.R:965) stay quiet
 }
 
 lndetANDinvCb <- function(C, b = NULL){
@@ -45,12 +62,98 @@ setCIAK3D <- function(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_c
 
 setCIAK3D2 <- function(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, setupMats){
   ### setupMats from setupIAK3D2(): set 1 = rows (prediction supports), set 2 = the data (a device dataset)
-  .Call('iak3dR_cov_cross', setupMats$set2$iak3d,
-        .iak3d_pv(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt),
-        as.matrix(setupMats$xData), as.matrix(setupMats$dIData))
+  pv <- .iak3d_pv(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt)
+  if(max(sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1) > 0){               # setCApproxIAK3D2 (fitIAK3D.R:1121-1124)
+    return(.Call('iak3dR_cov_cross_spl', setupMats$set2$iak3d, pv, as.matrix(setupMats$xData), as.matrix(setupMats$dIData), setupMats$Xspl1))
+  }
+  .Call('iak3dR_cov_cross', setupMats$set2$iak3d, pv, as.matrix(setupMats$xData), as.matrix(setupMats$dIData))
 }
-setupIAK3D2 <- function(xData, dIData, xData2, dIData2, ...){
-  list(xData = as.matrix(xData), dIData = as.matrix(dIData), set2 = setupIAK3D(xData2, dIData2), Kx = TRUE)
+setupIAK3D2 <- function(xData, dIData, xData2, dIData2, sdfdType_cd1 = 0, sdfdType_cxd0 = 0, sdfdType_cxd1 = 0, sdfdKnots = NULL, ...){
+  types <- c(sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1)
+  list(xData = as.matrix(xData), dIData = as.matrix(dIData),
+       set2 = setupIAK3D(xData2, dIData2, sdfdType_cd1 = sdfdType_cd1, sdfdType_cxd0 = sdfdType_cxd0, sdfdType_cxd1 = sdfdType_cxd1, sdfdKnots = sdfdKnots),
+       Xspl1 = if(max(types) > 0) .iak3d_spl_bases(as.matrix(dIData), types, sdfdKnots) else list(NULL, NULL, NULL), Kx = TRUE)
+}
+
+### ---- lognormal data (lnTfmdData = TRUE): nrUpdatesIAK3DlnN on the Gram matrix of ONE bordered factorisation ----
+### F = [X, z, s, V_ab (a <= b over iU)], s = sigma2Vec - diag(C) filled on the device; G = F' iC F carries every product the
+### Newton iteration needs (u' iC v = cu' G cv, u' TK v = cu' GT cv); see iak3d_b200/api.py: lnN_design, nrUpdatesIAK3DlnN_gram.
+.iak3d_lnN_design <- function(XData, zData, vXU, iU){
+  n <- nrow(XData) ; pU <- length(iU)
+  prs <- if(pU > 0) do.call(rbind, lapply(seq(pU), function(a){ cbind(a, a:pU) })) else matrix(0, 0, 2)
+  V <- if(pU > 0) sapply(seq(nrow(prs)), function(k){ vXU[(seq(n) - 1) * pU + prs[k, 1], prs[k, 2]] }) else NULL
+  list(F = cbind(XData, zData, 0, V), pairs = prs)
+}
+.iak3d_nr_lnN <- function(G, lndetC, n, p, iU, prs){
+  G <- 0.5 * (G + t(G)) ; q <- nrow(G) ; pU <- length(iU) ; iK <- setdiff(seq(p), iU) ; zc <- p + 1 ; sc <- p + 2
+  e <- function(j){ v <- numeric(q) ; v[j] <- 1 ; v }
+  vcol <- function(a, b){ p + 2 + which(prs[, 1] == min(a, b) & prs[, 2] == max(a, b)) }
+  XiCX <- G[1:p, 1:p, drop = FALSE]
+  if(pU == 0){
+    cc <- e(zc) - 0.5 * e(sc) ; XiCz <- G[1:p, , drop = FALSE] %*% cc ; b <- solve(XiCX, XiCz)
+    res <- as.numeric(t(cc) %*% G %*% cc - 2 * t(b) %*% XiCz + t(b) %*% XiCX %*% b)
+    return(list(betahat = b, nll = 0.5 * (n * log(2 * pi) + lndetC + res), fim = -XiCX, noits = 0, errFlag = 0))
+  }
+  betaU <- solve(XiCX, G[1:p, zc])[iU]
+  if(length(iK) > 0){ GKK <- G[iK, iK, drop = FALSE] ; GT <- G - G[, iK, drop = FALSE] %*% solve(GKK, G[iK, , drop = FALSE]) }else{ GT <- G }
+  gh <- function(bU){
+    cres <- e(zc) - 0.5 * e(sc) ; Ca <- matrix(0, q, pU)
+    for(a in seq(pU)){
+      cres <- cres - bU[a] * e(iU[a]) ; ca <- e(iU[a])
+      for(b in seq(pU)){ ca <- ca + bU[b] * e(vcol(a, b)) ; cres <- cres - 0.5 * bU[a] * bU[b] * e(vcol(a, b)) }
+      Ca[, a] <- ca
+    }
+    Tres <- GT %*% cres
+    fim <- t(Ca) %*% GT %*% Ca
+    vT <- matrix(sapply(seq(pU), function(b){ sapply(seq(pU), function(a){ Tres[vcol(a, b)] }) }), pU, pU)
+    hess <- -vT + fim ; betahat <- matrix(NA, p, 1) ; betahat[iU] <- bU
+    if(length(iK) > 0){ betahat[iK] <- solve(GKK, G[iK, , drop = FALSE] %*% cres) }
+    list(nll = as.numeric(0.5 * (n * log(2 * pi) + lndetC + t(cres) %*% Tres)), grad = -t(Ca) %*% Tres,
+         hess = 0.5 * (hess + t(hess)), fim = 0.5 * (fim + t(fim)), betahat = betahat)
+  }
+  cur <- gh(betaU) ; tolNr <- 1E-6 ; noits <- 0 ; nllPrev <- Inf
+  while((noits < 20) & ((cur$nll < (nllPrev - tolNr)) | (noits < 4))){
+    nllPrev <- cur$nll
+    ### (nrUpdatesIAK3DlnN.R:109 tests `checkHess$cholC` on the value of solve(), which cannot run; intended logic:)
+    step <- if(noits >= 2) try(solve(cur$hess, cur$grad), silent = TRUE) else NULL
+    if(is.null(step) || is.character(step)){ step <- try(solve(cur$fim, cur$grad), silent = TRUE) }
+    if(is.character(step)){ return(c(cur, list(noits = noits, errFlag = 1))) }
+    betaU <- betaU - as.numeric(step) ; cur <- gh(betaU) ; noits <- noits + 1
+  }
+  cur$nll <- round(cur$nll / (tolNr * 10)) * (tolNr * 10)
+  c(cur, list(noits = noits, errFlag = if(noits == 20) 2 else 0))
+}
+.iak3d_nll_lnN <- function(pars, zData, XData, vXU, iU, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum,
+                           setupMats, parBnds, rtnAll, attachBigMats){
+  XData <- as.matrix(XData) ; n <- length(zData) ; p <- ncol(XData)
+  parsBTfmd <- readParsIAK3D(pars = pars, modelx = modelx, nud = nud, sdfdType_cd1 = sdfdType_cd1, sdfdType_cxd0 = sdfdType_cxd0,
+                             sdfdType_cxd1 = sdfdType_cxd1, cmeOpt = cmeOpt, prodSum = prodSum, parBnds = parBnds, lnTfmdData = TRUE)
+  pv <- .iak3d_pv(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt)
+  des <- .iak3d_lnN_design(XData, zData, vXU, iU) ; q <- ncol(des$F)
+  .Call('iak3dR_set_W', setupMats$iak3d, des$F) ; .Call('iak3dR_set_lnN_column', setupMats$iak3d, as.integer(p + 1))
+  tmp <- .Call('iak3dR_nll_terms', setupMats$iak3d, matrix(pv, ncol = 1))
+  .Call('iak3dR_set_lnN_column', setupMats$iak3d, as.integer(-1))
+  if(tmp[[1]][1] != 0){ if(rtnAll){ return(list(nll = 9E99, pars = pars, parsBTfmd = parsBTfmd, betahat = NA, vbetahat = NA, cxdhat = NA)) }else{ return(9E99) } }
+  G <- matrix(tmp[[3]][, 1], q, q)
+  nr <- .iak3d_nr_lnN(G, tmp[[2]][1], n, p, iU, des$pairs)
+  nll <- if(is.na(nr$nll) || is.infinite(nr$nll)) 9E99 else nr$nll
+  if(!rtnAll){ return(nll) }
+  ### vbetahat = solve(fim) with every column treated as varying and TK = iC (fitIAK3D.R:768-773)
+  Gs <- 0.5 * (G + t(G)) ; Ca <- diag(q)[, 1:p, drop = FALSE]
+  vcol <- function(a, b){ p + 2 + which(des$pairs[, 1] == min(a, b) & des$pairs[, 2] == max(a, b)) }
+  for(a in seq_along(iU)){ for(b in seq_along(iU)){ Ca[vcol(a, b), iU[a]] <- Ca[vcol(a, b), iU[a]] + nr$betahat[iU[b]] } }
+  vbetahat <- solve(t(Ca) %*% Gs %*% Ca)
+  s2 <- .Call('iak3dR_cov_build', setupMats$iak3d, pv, FALSE)[[3]] ; dC <- .Call('iak3dR_cov_diag', setupMats$iak3d, pv)[[2]]
+  muhat <- setmuIAK3D(XData = XData, vXU = vXU, iU = iU, beta = nr$betahat, diagC = dC, sigma2Vec = s2)
+  out <- list(nll = nll, pars = pars, parsBTfmd = parsBTfmd, betahat = nr$betahat, vbetahat = vbetahat, cxdhat = 1, sigma2Vec = s2,
+              XData = XData, vXU = vXU, iU = iU, diagC = dC)
+  .Call('iak3dR_set_W', setupMats$iak3d, cbind(XData, zData))
+  if(attachBigMats){
+    fit <- .Call('iak3dR_fit_res', setupMats$iak3d, pv, as.numeric(nr$betahat), as.matrix(vbetahat), as.numeric(zData - muhat))
+    sm <- .Call('iak3dR_fit_small', fit, as.integer(n), as.integer(p))
+    out$iak3dFit <- fit ; out$iCX <- sm[[1]] ; out$iCz_muhat <- sm[[2]]
+  }
+  out
 }
 
 ### the REML / ML tail of nllIAK3D (fitIAK3D.R:821-880) on the host: O(p^3)
@@ -69,9 +172,13 @@ setupIAK3D2 <- function(xData, dIData, xData2, dIData2, ...){
 
 nllIAK3D <- function(pars, zData, XData, vXU, iU, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum,
                      setupMats = NULL, parBnds, useReml, lnTfmdData, rtnAll = F, forCompLik = FALSE, attachBigMats = FALSE, nCores = 8){
-  if(lnTfmdData || is.null(setupMats$iak3d)){  # lognormal support / spline sd functions: reference path
+  if(is.null(setupMats$iak3d)){  # site-specific random effects: reference path
     return(.iak3d_ref$nllIAK3D(pars, zData, XData, vXU, iU, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum,
                                setupMats, parBnds, useReml, lnTfmdData, rtnAll, forCompLik, attachBigMats, nCores))
+  }
+  if(lnTfmdData){
+    return(.iak3d_nll_lnN(pars, zData, XData, vXU, iU, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum,
+                          setupMats, parBnds, rtnAll, attachBigMats))
   }
   XData <- as.matrix(XData) ; n <- length(zData) ; p <- ncol(XData)
   parsBTfmd <- readParsIAK3D(pars = pars, modelx = modelx, nud = nud, sdfdType_cd1 = sdfdType_cd1, sdfdType_cxd0 = sdfdType_cxd0,
@@ -132,3 +239,24 @@ gradnllIAK3D <- function(pars, zData, XData, vXU, iU, modelx, nud, sdfdType_cd1,
   g
 }
 gradnllIAK3D.mc <- gradnllIAK3D
+
+
+### ---- the per-batch body of predictIAK3D / profilePredictIAK3D (predictIAK3D.R:179-255, 440-491) ----
+### call instead of lines 179-208 + 229-255 when lmmFit$iak3dFit is present; returns list(z, v) before the back-transform
+iak3dPredictBatch <- function(lmmFit, xMapThis, dIMapThis, XMapThis, vXUMapThis = NULL){
+  types <- c(lmmFit$sdfdType_cd1, lmmFit$sdfdType_cxd0, lmmFit$sdfdType_cxd1)
+  spl <- if(max(types) > 0) .iak3d_spl_bases(as.matrix(dIMapThis), types, lmmFit$sdfdKnots) else NULL
+  tmp <- .Call('iak3dR_predict_terms', lmmFit$iak3dFit, as.matrix(xMapThis), as.matrix(dIMapThis), as.matrix(XMapThis), spl, FALSE)
+  if(!lmmFit$lnTfmdData){ return(list(z = tmp[[1]], v = tmp[[2]])) }
+  ### lognormal data: muhat from setmuIAK3D, no beta uncertainty in the variance (predictIAK3D.R:232, 251)
+  mu <- setmuIAK3D(XData = XMapThis, vXU = vXUMapThis, iU = lmmFit$iU, beta = lmmFit$betahat, diagC = tmp[[3]], sigma2Vec = tmp[[4]])
+  list(z = as.numeric(mu) + tmp[[5]], v = tmp[[3]] - tmp[[6]])
+}
+
+### gradHessIAK3D (nrUpdatesIAK3D.R:118-216) on the device; nrUpdatesIAK3D's loop (:1-116) runs unchanged around it
+gradHessIAK3D_gpu <- function(setupMats, parsBTfmd, modelx, sdfdTypes, lnvPars){
+  pv <- .iak3d_pv(parsBTfmd, modelx, sdfdTypes[1], sdfdTypes[2], sdfdTypes[3], if(length(lnvPars) == 6) 1 else 0) ; pv[6] <- 0
+  tmp <- .Call('iak3dR_gradhess', setupMats$iak3d, pv, as.numeric(lnvPars))
+  if(tmp[[1]] != 0){ return(list(nll = NA)) }
+  list(nll = tmp[[2]], grad = tmp[[3]], hess = tmp[[4]], fim = tmp[[5]], betahat = tmp[[6]], vbetahat = tmp[[7]])
+}

@@ -34,10 +34,15 @@ static void fit_finalizer(SEXP p) {
 }
 
 /* parsBTfmd (list from readParsIAK3D) + model switches -> struct iak3d_pars.  pv = c(modelx, cmeOpt, sdfdType_cd1,
- * sdfdType_cxd0, sdfdType_cxd1, quirk, ax, nux, ad, nud, cx0, cx1, cd1, cxd0, cxd1, cme, tau(3x2 row-major), quirk_scale) */
+ * sdfdType_cxd0, sdfdType_cxd1, quirk, ax, nux, ad, nud, cx0, cx1, cd1, cxd0, cxd1, cme, tau(3x2 row-major), quirk_scale,
+ * spline coefficients (3 x IAK3D_MAX_SPL row-major, zero padded)) */
+#define IAK3D_PV_LEN (23 + 3 * IAK3D_MAX_SPL)
+static void pars_from_ptr(const double* v, iak3d_pars* P);
 static void pars_from(SEXP pv, iak3d_pars* P) {
-  const double* v = REAL(pv);
-  if (LENGTH(pv) != 23) error("iak3d: parameter vector must have 23 entries");
+  if (LENGTH(pv) != IAK3D_PV_LEN) error("iak3d: parameter vector must have %d entries", IAK3D_PV_LEN);
+  pars_from_ptr(REAL(pv), P);
+}
+static void pars_from_ptr(const double* v, iak3d_pars* P) {
   memset(P, 0, sizeof(*P));
   P->modelx = (int32_t)v[0]; P->cmeOpt = (int32_t)v[1];
   P->sdfdType[0] = (int32_t)v[2]; P->sdfdType[1] = (int32_t)v[3]; P->sdfdType[2] = (int32_t)v[4];
@@ -46,6 +51,7 @@ static void pars_from(SEXP pv, iak3d_pars* P) {
   P->cx0 = v[10]; P->cx1 = v[11]; P->cd1 = v[12]; P->cxd0 = v[13]; P->cxd1 = v[14]; P->cme = v[15];
   for (int c = 0; c < 3; c++) { P->sdfdPars[c][0] = v[16 + 2 * c]; P->sdfdPars[c][1] = v[17 + 2 * c]; }
   P->quirk_scale = v[22];
+  for (int c = 0; c < 3; c++) for (int k = 0; k < IAK3D_MAX_SPL; k++) P->sdfdSpl[c][k] = v[23 + c * IAK3D_MAX_SPL + k];
 }
 
 /* setupIAK3D: xData (n x 2), dIData (n x 2, already rounded, fitIAK3D.R:127), W = cbind(X, z) or NULL */
@@ -67,8 +73,34 @@ SEXP iak3dR_set_W(SEXP dsp, SEXP W) {
   return R_NilValue;
 }
 
+/* spline sd functions: setupMats$XsdfdSplineU_{cd1,cxd0,cxd1} (ndIU x (sdfdType + 1)) of component comp (0, 1, 2) */
+SEXP iak3dR_set_sdfd_spline(SEXP dsp, SEXP comp, SEXP XsplU) {
+  int st = iak3d_dataset_set_sdfd_spline((iak3d_ds*)R_ExternalPtrAddr(dsp), asInteger(comp), ncols(XsplU), REAL(XsplU));
+  if (st != IAK3D_OK) error("iak3d_dataset_set_sdfd_spline: %s", iak3d_last_error(g_ctx));
+  return R_NilValue;
+}
+/* lognormal data: column (0-based) of W that the device overwrites with sigma2Vec - diag(C) at every evaluation; -1 = off */
+SEXP iak3dR_set_lnN_column(SEXP dsp, SEXP col) {
+  int st = iak3d_dataset_set_lnN_column((iak3d_ds*)R_ExternalPtrAddr(dsp), asInteger(col));
+  if (st != IAK3D_OK) error("iak3d_dataset_set_lnN_column: %s", iak3d_last_error(g_ctx));
+  return R_NilValue;
+}
+/* diag(setCIAK3D(pars)$C): list(status, diagC) */
+SEXP iak3dR_cov_diag(SEXP dsp, SEXP pv) {
+  iak3d_ds* ds = (iak3d_ds*)R_ExternalPtrAddr(dsp);
+  iak3d_pars P; pars_from(pv, &P);
+  int64_t n = 0; iak3d_dataset_info(ds, &n, NULL, NULL, NULL);
+  SEXP d = PROTECT(allocVector(REALSXP, (R_xlen_t)n));
+  int st = iak3d_cov_diag(ds, &P, REAL(d));
+  if (st < 0) error("iak3d_cov_diag: %s", iak3d_last_error(g_ctx));
+  SEXP out = PROTECT(allocVector(VECSXP, 2));
+  SET_VECTOR_ELT(out, 0, ScalarInteger(st)); SET_VECTOR_ELT(out, 1, d);
+  UNPROTECT(2);
+  return out;
+}
+
 /* nllIAK3D(..., forCompLik = TRUE) terms for `count` parameter vectors on one dataset (count = 1: a function value;
- * count = npar + 1: a forward-difference gradient).  pmat: 23 x count.  Returns list(status, lndetA, WiAW (q*q x count)). */
+ * count = npar + 1: a forward-difference gradient).  pmat: IAK3D_PV_LEN x count.  Returns list(status, lndetA, WiAW (q*q x count)). */
 SEXP iak3dR_nll_terms(SEXP dsp, SEXP pmat) {
   iak3d_ds* ds = (iak3d_ds*)R_ExternalPtrAddr(dsp);
   const int count = ncols(pmat);
@@ -76,13 +108,8 @@ SEXP iak3dR_nll_terms(SEXP dsp, SEXP pmat) {
   iak3d_dataset_info(ds, &n, NULL, NULL, &q);
   iak3d_pars* P = (iak3d_pars*)R_alloc(count, sizeof(iak3d_pars));
   iak3d_ds** dss = (iak3d_ds**)R_alloc(count, sizeof(iak3d_ds*));
-  for (int i = 0; i < count; i++) {
-    SEXP col = PROTECT(allocVector(REALSXP, 23));
-    memcpy(REAL(col), REAL(pmat) + 23 * (size_t)i, 23 * sizeof(double));
-    pars_from(col, &P[i]);
-    UNPROTECT(1);
-    dss[i] = ds;
-  }
+  if (nrows(pmat) != IAK3D_PV_LEN) error("iak3d: parameter matrix must have %d rows", IAK3D_PV_LEN);
+  for (int i = 0; i < count; i++) { pars_from_ptr(REAL(pmat) + IAK3D_PV_LEN * (size_t)i, &P[i]); dss[i] = ds; }
   SEXP status = PROTECT(allocVector(INTSXP, count));
   SEXP lndet = PROTECT(allocVector(REALSXP, count));
   SEXP G = PROTECT(allocMatrix(REALSXP, q * q, count));
@@ -140,6 +167,21 @@ SEXP iak3dR_cov_cross(SEXP dsp, SEXP pv, SEXP xy1, SEXP dI1) {
   return st == IAK3D_OK ? out : ScalarReal(NA_REAL);
 }
 
+/* setCApproxIAK3D2: the same with the spline bases of set 1 on its ROWS (list of 3: matrix n1 x (sdfdType + 1) or NULL) */
+SEXP iak3dR_cov_cross_spl(SEXP dsp, SEXP pv, SEXP xy1, SEXP dI1, SEXP spl) {
+  iak3d_ds* ds = (iak3d_ds*)R_ExternalPtrAddr(dsp);
+  iak3d_pars P; pars_from(pv, &P);
+  int64_t n = 0; iak3d_dataset_info(ds, &n, NULL, NULL, NULL);
+  const int n1 = nrows(xy1);
+  const double* sp[3];
+  for (int c = 0; c < 3; c++) { SEXP e = VECTOR_ELT(spl, c); sp[c] = isNull(e) ? NULL : REAL(e); }
+  SEXP out = PROTECT(allocMatrix(REALSXP, n1, (int)n));
+  int st = iak3d_cov_cross_spl(ds, &P, n1, REAL(xy1), REAL(dI1), sp, REAL(out));
+  if (st < 0) error("iak3d_cov_cross_spl: %s", iak3d_last_error(g_ctx));
+  UNPROTECT(1);
+  return st == IAK3D_OK ? out : ScalarReal(NA_REAL);
+}
+
 /* lndetANDinvCb(C, b): list(lndetC, invCb) with NA, NA on failure (optim_functions.R:292-294) */
 SEXP iak3dR_lndet_invCb(SEXP C, SEXP b) {
   const int n = nrows(C);
@@ -166,6 +208,22 @@ SEXP iak3dR_fit(SEXP dsp, SEXP pv, SEXP betahat, SEXP vbetahat) {
   UNPROTECT(1);
   return p;
 }
+/* the same with the residual z - muhat given (lognormal data: muhat = setmuIAK3D(...)) */
+SEXP iak3dR_fit_res(SEXP dsp, SEXP pv, SEXP betahat, SEXP vbetahat, SEXP z_muhat) {
+  iak3d_pars P; pars_from(pv, &P);
+  iak3d_fit* f = NULL;
+  int st = iak3d_fit_create_res((iak3d_ds*)R_ExternalPtrAddr(dsp), &P, REAL(betahat), REAL(vbetahat), REAL(z_muhat), &f);
+  if (st != IAK3D_OK) error("iak3d_fit_create_res: status %d %s", st, iak3d_last_error(g_ctx));
+  SEXP p = PROTECT(R_MakeExternalPtr(f, R_NilValue, dsp));
+  R_RegisterCFinalizerEx(p, fit_finalizer, TRUE);
+  UNPROTECT(1);
+  return p;
+}
+SEXP iak3dR_fit_option(SEXP fp, SEXP option, SEXP value) {
+  int st = iak3d_fit_set_option((iak3d_fit*)R_ExternalPtrAddr(fp), asInteger(option), asInteger(value));
+  if (st != IAK3D_OK) error("iak3d_fit_set_option: %s", iak3d_last_error(g_ctx));
+  return R_NilValue;
+}
 SEXP iak3dR_fit_small(SEXP fp, SEXP n_, SEXP p_) {              /* iCX, iCz_muhat */
   const int n = asInteger(n_), p = asInteger(p_);
   SEXP iCX = PROTECT(allocMatrix(REALSXP, n, p));
@@ -189,12 +247,55 @@ SEXP iak3dR_predict(SEXP fp, SEXP xyMap, SEXP dIMap, SEXP XMap) {
   return out;
 }
 
+/* kriging with all its pieces: list(z, v, Ckk, sigma2Veck, CkhiCz_muhat, CkhiCChk[, CkhiCX]); spl = list of 3 spline
+ * bases on the map supports (or NULL); wantCX needs iak3dR_fit_option(fit, 1, 1) beforehand */
+SEXP iak3dR_predict_terms(SEXP fp, SEXP xyMap, SEXP dIMap, SEXP XMap, SEXP spl, SEXP wantCX) {
+  iak3d_fit* f = (iak3d_fit*)R_ExternalPtrAddr(fp);
+  const int m = nrows(xyMap), p = ncols(XMap);
+  const double* sp[3] = {NULL, NULL, NULL};
+  if (!isNull(spl)) for (int c = 0; c < 3; c++) { SEXP e = VECTOR_ELT(spl, c); sp[c] = isNull(e) ? NULL : REAL(e); }
+  int st = iak3d_predict_stage_spl(f, m, REAL(xyMap), REAL(dIMap), REAL(XMap), isNull(spl) ? NULL : sp);
+  if (st == IAK3D_OK) st = iak3d_predict_enqueue(f);
+  if (st != IAK3D_OK) error("iak3d_predict: %s", iak3d_last_error(g_ctx));
+  const int want = asLogical(wantCX);
+  SEXP out = PROTECT(allocVector(VECSXP, want ? 7 : 6));
+  for (int k = 0; k < 6; k++) SET_VECTOR_ELT(out, k, allocVector(REALSXP, m));
+  st = iak3d_predict_fetch(f, REAL(VECTOR_ELT(out, 0)), REAL(VECTOR_ELT(out, 1)));
+  if (st == IAK3D_OK) st = iak3d_predict_fetch_terms(f, REAL(VECTOR_ELT(out, 2)), REAL(VECTOR_ELT(out, 3)), REAL(VECTOR_ELT(out, 4)), REAL(VECTOR_ELT(out, 5)));
+  if (st == IAK3D_OK && want) { SET_VECTOR_ELT(out, 6, allocMatrix(REALSXP, m, p)); st = iak3d_predict_fetch_CkhiCX(f, REAL(VECTOR_ELT(out, 6))); }
+  if (st != IAK3D_OK) error("iak3d_predict_fetch: %s", iak3d_last_error(g_ctx));
+  UNPROTECT(1);
+  return out;
+}
+
+/* gradHessIAK3D (nrUpdatesIAK3D.R:118-216): list(status, nll, grad, hess, fim, betahat, vbetahat) */
+SEXP iak3dR_gradhess(SEXP dsp, SEXP pv, SEXP lnvPars) {
+  iak3d_ds* ds = (iak3d_ds*)R_ExternalPtrAddr(dsp);
+  iak3d_pars P; pars_from(pv, &P);
+  int32_t q = 0; iak3d_dataset_info(ds, NULL, NULL, NULL, &q);
+  const int m = LENGTH(lnvPars), p = q - 1;
+  SEXP out = PROTECT(allocVector(VECSXP, 7));
+  SET_VECTOR_ELT(out, 1, allocVector(REALSXP, 1)); SET_VECTOR_ELT(out, 2, allocVector(REALSXP, m));
+  SET_VECTOR_ELT(out, 3, allocMatrix(REALSXP, m, m)); SET_VECTOR_ELT(out, 4, allocMatrix(REALSXP, m, m));
+  SET_VECTOR_ELT(out, 5, allocMatrix(REALSXP, p, 1)); SET_VECTOR_ELT(out, 6, allocMatrix(REALSXP, p, p));
+  int st = iak3d_gradhess(ds, &P, m, REAL(lnvPars), REAL(VECTOR_ELT(out, 1)), REAL(VECTOR_ELT(out, 2)), REAL(VECTOR_ELT(out, 3)),
+                          REAL(VECTOR_ELT(out, 4)), REAL(VECTOR_ELT(out, 5)), REAL(VECTOR_ELT(out, 6)));
+  if (st < 0) error("iak3d_gradhess: %s", iak3d_last_error(g_ctx));
+  SET_VECTOR_ELT(out, 0, ScalarInteger(st));
+  UNPROTECT(1);
+  return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
   {"iak3dR_dataset", (DL_FUNC)&iak3dR_dataset, 3},       {"iak3dR_set_W", (DL_FUNC)&iak3dR_set_W, 2},
   {"iak3dR_nll_terms", (DL_FUNC)&iak3dR_nll_terms, 2},   {"iak3dR_nll_terms_iAW", (DL_FUNC)&iak3dR_nll_terms_iAW, 2},
   {"iak3dR_cov_build", (DL_FUNC)&iak3dR_cov_build, 3},   {"iak3dR_cov_cross", (DL_FUNC)&iak3dR_cov_cross, 4},
   {"iak3dR_lndet_invCb", (DL_FUNC)&iak3dR_lndet_invCb, 2}, {"iak3dR_fit", (DL_FUNC)&iak3dR_fit, 4},
   {"iak3dR_fit_small", (DL_FUNC)&iak3dR_fit_small, 3},   {"iak3dR_predict", (DL_FUNC)&iak3dR_predict, 4},
+  {"iak3dR_set_sdfd_spline", (DL_FUNC)&iak3dR_set_sdfd_spline, 3}, {"iak3dR_set_lnN_column", (DL_FUNC)&iak3dR_set_lnN_column, 2},
+  {"iak3dR_cov_diag", (DL_FUNC)&iak3dR_cov_diag, 2},     {"iak3dR_cov_cross_spl", (DL_FUNC)&iak3dR_cov_cross_spl, 5},
+  {"iak3dR_fit_res", (DL_FUNC)&iak3dR_fit_res, 5},       {"iak3dR_fit_option", (DL_FUNC)&iak3dR_fit_option, 3},
+  {"iak3dR_predict_terms", (DL_FUNC)&iak3dR_predict_terms, 6}, {"iak3dR_gradhess", (DL_FUNC)&iak3dR_gradhess, 3},
   {NULL, NULL, 0}};
 
 void R_init_iak3dR(DllInfo* dll) {

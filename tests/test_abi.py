@@ -55,6 +55,22 @@ def test_pars_struct_layout(tmp_path):
     assert _lib.MAX_SPL == 12
 
 
+def test_r_shim_compiles_against_the_header():
+    """r/r_shim.c (the .Call binding a maintainer builds where R exists) must agree with include/iak3d.h: syntax / type
+    check with gcc against minimal stand-ins of the R headers (tests/r_stub; R itself is not in this image)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not on PATH")
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "r_stub"), "-I",
+                        os.path.join(ROOT, "include"), os.path.join(ROOT, "r", "r_shim.c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = open(os.path.join(ROOT, "r", "r_shim.c")).read()
+    glue = open(os.path.join(ROOT, "r", "iak3d_cuda.R")).read()
+    for name in re.findall(r"\.Call\('(iak3dR_[A-Za-z0-9_]+)'", glue):
+        assert '{"%s"' % name in src, f"{name} is called from the R glue but not registered in r_shim.c"
+
+
 def test_sass_is_sm100a_with_tma_and_dmma():
     import shutil
     import subprocess
