@@ -216,8 +216,8 @@ def run_s5(args, rank, local_rank, world, comm):
                                   "figure); DFMA microbenchmark = %.1f TFLOP/s" % peaks["dfma"]),
         roofline_cov_build=dict(kernel="cov_factor_kernel", bound="hbm", achieved=cov_gbs, peak=hbm_peak, unit="GB/s",
                                 frac=cov_gbs / hbm_peak, bytes_per_launch=8.0 * n * (n + 1) / 2.0, peak_source=hbm_src,
-                                traffic=ncu_traffic("cov_factor_kernel", n, 1),
-                                note="stage time of nb launches + nb table expansions; write-only peak of this layout measured at "
+                                traffic=ncu_traffic("cov_factor_kernel", n, nb),
+                                note="stage time: one batched launch + the table expansion; write-only peak of this layout measured at "
                                      "7.0 TB/s (n = 20000) / 4.5 TB/s (n = 5000, one launch), scripts/micro/store_pattern.cu"),
         e2e=dict(value=evals / e2e_s, unit="evals/s", h2d_bytes_per_step=int(W.nbytes + nb * C.sizeof(Pars)),
                  d2h_bytes_per_step=int(nb * (2 + q * q) * 8)),

@@ -216,6 +216,7 @@ extern "C" int iak3d_ctx_destroy(iak3d_ctx* ctx) {
     delete b;
   }
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+  cudaFree(ctx->d_fbjobs);
   cudaFree(ctx->d_prof);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   for (int i = 0; i < 5; i++) cudaEventDestroy(ctx->evs[i]);
@@ -895,6 +896,8 @@ extern "C" int iak3d_nll_terms_batch_enqueue(iak3d_ctx* ctx, int32_t count, iak3
     if (st != 0) return st;
   }
   CUDA_TRY(ctx, cudaEventRecord(ctx->evs[1], ctx->stream));
+  std::vector<FactorBuildJob> jobs;
+  jobs.reserve((size_t)count);
   for (int i = 0; i < count; i++) {
     if (!live[i]) continue;
     Slot* s = b->slots[i];
@@ -910,10 +913,13 @@ extern "C" int iak3d_nll_terms_batch_enqueue(iak3d_ctx* ctx, int32_t count, iak3
       st = iak_lnN_column(ctx, dss[i], plans[i], cargs[i], s);
       if (st != 0) return st;
     }
-    st = launch_cov_factor_layout(ctx, cargs[i], dss[i]->d_W, q, s->n, s->Npad, s->ld, s->nCB, s->d_L,
-                                  dss[i]->lncol >= 0 ? s->d_lncol : nullptr, dss[i]->lncol);
-    if (st != 0) return st;
+    FactorBuildJob jb;
+    jb.a = cargs[i]; jb.d_W = dss[i]->d_W; jb.q = q; jb.n = s->n; jb.Npad = s->Npad; jb.ld = s->ld; jb.nCB = s->nCB; jb.d_L = s->d_L;
+    jb.d_lncol = dss[i]->lncol >= 0 ? s->d_lncol : nullptr; jb.lncol = dss[i]->lncol;
+    jobs.push_back(jb);
   }
+  st = launch_cov_factor_jobs(ctx, jobs.data(), (int)jobs.size());   // ONE launch for the whole batch
+  if (st != 0) return st;
   CUDA_TRY(ctx, cudaEventRecord(ctx->evs[2], ctx->stream));
   CUDA_TRY(ctx, cudaMemsetAsync(b->d_status, 0, (size_t)count * 2 * sizeof(int32_t), ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(b->d_probs, probs.data(), (size_t)count * sizeof(ProblemDesc), cudaMemcpyHostToDevice, ctx->stream));

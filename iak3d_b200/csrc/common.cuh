@@ -49,6 +49,7 @@ struct iak3d_ctx {
   struct Batch* batch = nullptr;
   double last_chol_flops = 0, last_cov_bytes = 0;
   bool stage_events_valid = false;
+  void* d_fbjobs = nullptr; size_t fbjobs_cap = 0;     // device copy of the covariance-build jobs of one launch
   long long* d_prof = nullptr; int64_t prof_cap = 0; int32_t prof_ntasks = 0;   // IAK3D_PROF=1 diagnostics
 };
 
@@ -146,6 +147,13 @@ struct CovArgs {
   int64_t nr, nc;          // live rows / cols
   int64_t nxU_r, ndIU_r;   // leading dims of tables (row-id extent)
 };
+// one covariance build into a factor buffer; a batch of them is ONE launch (launch_cov_factor_jobs)
+struct FactorBuildJob {
+  CovArgs a;
+  const double* d_W = nullptr; int32_t q = 0; int64_t n = 0, Npad = 0, ld = 0; int32_t nCB = 0; double* d_L = nullptr;
+  const double* d_lncol = nullptr; int lncol = -1;
+};
+int launch_cov_factor_jobs(iak3d_ctx* ctx, const FactorBuildJob* jobs, int count);
 // d_lncol / lncol: column `lncol` of W is taken from the vector d_lncol instead (lognormal bias column, see api.cu)
 int launch_cov_factor_layout(iak3d_ctx* ctx, const CovArgs& a, const double* d_W, int32_t q, int64_t n, int64_t Npad, int64_t ld,
                              int32_t nCB, double* d_L, const double* d_lncol = nullptr, int lncol = -1);

@@ -5,33 +5,15 @@
 //
 // The reference reaches this through two n(n+1)/2-long gather index vectors (iaCovMatern.R:473-481);
 // here each entry is formed directly from the row's (location id, interval id) pair and the small
-// unique-pair tables of tables.cu, which stay L2-resident.  The pass is HBM-write-bound: 8 bytes per
-// entry, coalesced 16-byte stores down the (column-major) columns.  Row/column id tiles are staged
-// into shared memory with cp.async.bulk (TMA 1-D bulk copies, mbarrier completion).
+// unique-pair tables of tables.cu.  The factor build (cov_factor_kernel) is HBM-write-bound: 8 bytes per
+// entry, 16-byte evict-first stores down the columns of the blocked layout, depth tables expanded along the
+// rows so that their loads are coalesced.  The rectangular builds (cov_rect_kernel: matrices returned to the
+// caller, kriging panels) keep the reference's term-by-term sums (cov_value).
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(
-          smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
 
 bool cov_one_table(const CovArgs& h) {
   for (int c = 0; c < 3; c++) if (h.tidx[c] > 0) return false;
@@ -97,13 +79,44 @@ __device__ __forceinline__ double cov_value(const CovDev& a, int xi, int di, int
 
 // ---- factor-layout build: lower-triangular TM x TN tiles of the padded, BLOCKED factor buffer (common.cuh) ----
 // rows [0,n) data, [n,Npad) identity padding, [Npad,Npad+q) the W' rows (bordered system), rest zero.
-__global__ void __launch_bounds__(256) cov_factor_kernel(CovDev a, const double* __restrict__ W, int q, int64_t n,
-                                                         int64_t Npad, double* __restrict__ L, int64_t ld, int nCB,
-                                                         const double* __restrict__ lncol_v, int lncol) {
-  // tile (r, j): column block j = blockIdx.y has row blocks j/2 .. nRB-1; CTAs beyond the last row block leave at once
+// One job per evaluation; a batch (the npar+1 evaluations of a forward-difference gradient, the block pairs of a
+// composite likelihood) is ONE launch with blockIdx.z = job, so that the tails of the small per-evaluation grids overlap.
+struct FbJob {
+  CovDev a;
+  const double* W; double* L; const double* lncol_v;
+  int64_t n, Npad, ld;
+  int q, nCB, lncol;
+  double* Ebuf; double* Stab; int expand;        // expand_tables_kernel: this job's own expansion (0: shares another job's)
+  int fold;                                      // grid layout, see cov_factor_kernel
+};
+
+__device__ __forceinline__ void cov_factor_body(const FbJob& J) {
+  // tile (r, j): column block j has row blocks j/2 .. nRB-1.  The triangle is folded: grid row y serves column block y
+  // and, with the CTAs that column does not need, its mirror nCB-1-y, so that (almost) no CTA is launched for nothing.
+  const int64_t ld = J.ld, n = J.n, Npad = J.Npad;
   const int nRB = (int)(ld / TM);
-  const int j = blockIdx.y, r = (j >> 1) + blockIdx.x;
-  if (r >= nRB) return;
+  int j = blockIdx.y, r;
+  {
+    const int nCBj = J.nCB, half = (nCBj + 1) >> 1;
+    if (!J.fold) {
+      if (j >= nCBj) return;
+      r = (j >> 1) + blockIdx.x;
+      if (r >= nRB) return;
+    } else if (j >= half) {
+      return;
+    } else if ((int)blockIdx.x < nRB - (j >> 1)) {
+      r = (j >> 1) + blockIdx.x;
+    } else {
+      const int jm = nCBj - 1 - j;
+      if (jm == j) return;                                             // the middle column of an odd count has no mirror
+      j = jm;
+      r = (j >> 1) + ((int)blockIdx.x - (nRB - ((nCBj - 1 - jm) >> 1)));
+      if (r >= nRB) return;
+    }
+  }
+  const CovDev& a = J.a;
+  const double* __restrict__ W = J.W; double* __restrict__ L = J.L; const double* __restrict__ lncol_v = J.lncol_v;
+  const int q = J.q, lncol = J.lncol;
   const int64_t R0 = (int64_t)r * TM, C0 = (int64_t)j * TN;
   const int tid = threadIdx.x;
   const int rp = tid & 63, cg = tid >> 6;           // row pair (2 rows), column group (16 columns)
@@ -226,14 +239,25 @@ __global__ void __launch_bounds__(256) cov_factor_kernel(CovDev a, const double*
   }
 }
 
+// two entry points for one body: a batch reads its job from an array in global memory (blockIdx.z = job); a single
+// evaluation (the large-n case) gets the job as a kernel parameter -- constant bank, measured 12 % faster at n = 20000.
+// Both are held to 80 registers (3 CTAs per SM): more resident warps beat more loads in flight per thread.
+__global__ void __launch_bounds__(256) cov_factor_kernel(const FbJob* __restrict__ jobs) { cov_factor_body(jobs[blockIdx.z]); }
+__global__ void __launch_bounds__(256, 3) cov_factor_kernel_one(const __grid_constant__ FbJob job) { cov_factor_body(job); }
+
 // Depth tables expanded along the rows for the interior tiles (coalesced instead of gathered loads):
 //   one table : E[dj*ldE + i]            = Phi[dj*nd + did[i]]
 //   generic   : E2[dj*ldE + i] (double2) = (kd1*Phi_cd1, cx1 + cxd1*Phi_cxd1)[dj*nd + did[i]],  S[dj*nd + di] = cx0 + cxd0*Phi_cxd0
-__global__ void __launch_bounds__(256) expand_tables_kernel(CovDev a, int64_t n, int64_t ldE, double* __restrict__ E,
-                                                            double* __restrict__ Stab) {
+__global__ void __launch_bounds__(256) expand_tables_kernel(const FbJob* __restrict__ jobs) {
   // blockIdx.y = dj (one table column, 8 nd bytes: L1-resident), blockIdx.x walks the rows: coalesced id reads and writes
+  const FbJob& J = jobs[blockIdx.z];
+  if (!J.expand) return;
+  const CovDev& a = J.a;
+  const int64_t n = J.n, ldE = a.ldE;
+  double* __restrict__ E = J.Ebuf; double* __restrict__ Stab = J.Stab;
   const int64_t nd = a.ndIU_r;
   const int64_t dj = blockIdx.y;
+  if (dj >= nd) return;
   const double* Td = a.tidx[0] >= 0 ? a.T[a.tidx[0]] + dj * nd : nullptr;
   const double* T0 = a.tidx[1] >= 0 ? a.T[a.tidx[1]] + dj * nd : nullptr;
   const double* T1 = (a.tidx[2] >= 0 && a.phix != nullptr) ? a.T[a.tidx[2]] + dj * nd : nullptr;
@@ -252,39 +276,84 @@ __global__ void __launch_bounds__(256) expand_tables_kernel(CovDev a, int64_t n,
       Stab[dj * nd + i] = T0 ? fma(a.cxd0, T0[i], a.cx0) : a.cx0;
 }
 
-int launch_cov_factor_layout(iak3d_ctx* ctx, const CovArgs& h, const double* d_W, int32_t q, int64_t n, int64_t Npad, int64_t ld,
-                             int32_t nCB_, double* d_L, const double* d_lncol, int lncol) {
-  CovDev a;
-  for (int k = 0; k < 3; k++) { a.T[k] = h.T[k]; a.tidx[k] = h.tidx[k]; }
-  a.ntab = h.ntab; a.phix = h.phix; a.same = h.same;
-  a.cx0 = h.cx0; a.cx1 = h.cx1; a.kd1 = h.kd1; a.cxd0 = h.cxd0; a.cxd1 = h.cxd1; a.cme = h.cme;
-  a.xid_r = h.xid_r; a.did_r = h.did_r; a.xid_c = h.xid_c; a.did_c = h.did_c;
-  a.nr = h.nr; a.nc = h.nc; a.nxU_r = h.nxU_r; a.ndIU_r = h.ndIU_r;
-  a.comb = h.comb;
-  // one shared table: every present component points at table 0 (cxd0 is always present)
-  a.one_table = cov_one_table(h) ? 1 : 0;
-  a.ldE = round_up(n, 2);
-  const int64_t nRB = ld / TM, nCB = nCB_;
-  int64_t tiles = 0;
-  for (int64_t c = 0; c < nCB; c++) tiles += nRB - c / 2;
-  if (h.E_shared != nullptr && a.one_table) {
-    a.E = h.E_shared;                       // another evaluation of this batch already expanded the same table
-  } else {
-    if (h.Ebuf == nullptr || h.comb == nullptr) { ctx->err = "cov_factor: expanded-table workspace missing"; return IAK3D_ERR_ARG; }
-    if (h.ndIU_r > 65535) { ctx->err = "cov_factor: more than 65535 unique depth intervals"; return IAK3D_ERR_ARG; }
-    unsigned bx = (unsigned)((a.ldE + 255) / 256);
-    if (bx > 64) bx = 64;
-    expand_tables_kernel<<<dim3(bx, (unsigned)h.ndIU_r), 256, 0, ctx->stream>>>(a, n, a.ldE, h.Ebuf, h.comb);
-    ctx->launches++;
-    a.E = h.Ebuf;
+static void covdev_from(const CovArgs& h, CovDev* a) {
+  for (int k = 0; k < 3; k++) { a->T[k] = h.T[k]; a->tidx[k] = h.tidx[k]; }
+  a->ntab = h.ntab; a->phix = h.phix; a->same = h.same;
+  a->cx0 = h.cx0; a->cx1 = h.cx1; a->kd1 = h.kd1; a->cxd0 = h.cxd0; a->cxd1 = h.cxd1; a->cme = h.cme;
+  a->xid_r = h.xid_r; a->did_r = h.did_r; a->xid_c = h.xid_c; a->did_c = h.did_c;
+  a->nr = h.nr; a->nc = h.nc; a->nxU_r = h.nxU_r; a->ndIU_r = h.ndIU_r;
+  a->comb = h.comb; a->E = nullptr; a->ldE = 0; a->one_table = 0;
+}
+
+int launch_cov_factor_jobs(iak3d_ctx* ctx, const FactorBuildJob* jobs, int count) {
+  if (count <= 0) return 0;
+  std::vector<FbJob> hj((size_t)count);
+  int64_t maxRB = 0, maxCB = 0, maxND = 0, maxLdE = 0;
+  int nexpand = 0;
+  const int fold = 1;
+  for (int i = 0; i < count; i++) {
+    const FactorBuildJob& b = jobs[i];
+    FbJob& J = hj[(size_t)i];
+    covdev_from(b.a, &J.a);
+    J.a.one_table = cov_one_table(b.a) ? 1 : 0;      // every present component points at table 0 (cxd0 is always present)
+    J.a.ldE = round_up(b.n, 2);
+    J.W = b.d_W; J.L = b.d_L; J.lncol_v = b.d_lncol; J.n = b.n; J.Npad = b.Npad; J.ld = b.ld; J.q = b.q; J.nCB = b.nCB;
+    J.lncol = b.d_lncol ? b.lncol : -1;
+    J.Ebuf = b.a.Ebuf; J.Stab = b.a.comb;
+    if (b.a.E_shared != nullptr && J.a.one_table) {
+      J.a.E = b.a.E_shared; J.expand = 0;            // another evaluation of this batch expands the same table
+    } else {
+      if (b.a.Ebuf == nullptr || b.a.comb == nullptr) { ctx->err = "cov_factor: expanded-table workspace missing"; return IAK3D_ERR_ARG; }
+      J.a.E = b.a.Ebuf; J.expand = 1; nexpand++;
+      maxND = std::max<int64_t>(maxND, b.a.ndIU_r); maxLdE = std::max<int64_t>(maxLdE, J.a.ldE);
+    }
+    {
+      const int64_t nRBj = b.ld / TM, nCBj = b.nCB;
+      J.fold = fold;
+      if (fold) {                                                    // folded triangle: rows(y) + rows(nCB-1-y)
+        int64_t gx = 0;
+        for (int64_t y = 0; y < (nCBj + 1) / 2; y++) {
+          const int64_t jm = nCBj - 1 - y;
+          gx = std::max<int64_t>(gx, (nRBj - y / 2) + (jm != y ? nRBj - jm / 2 : 0));
+        }
+        maxRB = std::max<int64_t>(maxRB, gx); maxCB = std::max<int64_t>(maxCB, (nCBj + 1) / 2);
+      } else {
+        maxRB = std::max<int64_t>(maxRB, nRBj); maxCB = std::max<int64_t>(maxCB, nCBj);
+      }
+    }
   }
-  (void)tiles;
-  if (nCB > 65535) { ctx->err = "cov_factor: more than 65535 column blocks"; return IAK3D_ERR_ARG; }
-  dim3 grid((unsigned)nRB, (unsigned)nCB);              // CTAs past the last row block of their column block leave at once
-  cov_factor_kernel<<<grid, 256, 0, ctx->stream>>>(a, d_W, q, n, Npad, d_L, ld, (int)nCB, d_lncol, d_lncol ? lncol : -1);
-  ctx->launches++;
+  if (maxCB > 65535 || maxND > 65535) { ctx->err = "cov_factor: more than 65535 column blocks / unique depth intervals"; return IAK3D_ERR_ARG; }
+  if ((size_t)count > ctx->fbjobs_cap) {
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_fbjobs); ctx->d_fbjobs = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_fbjobs, (size_t)count * sizeof(FbJob)));
+    ctx->fbjobs_cap = (size_t)count;
+  }
+  const FbJob* dj = static_cast<const FbJob*>(ctx->d_fbjobs);
+  for (int z0 = 0; z0 < count; z0 += 65535) {        // gridDim.z limit
+    const int zc = std::min(65535, count - z0);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_fbjobs, hj.data() + z0, (size_t)zc * sizeof(FbJob), cudaMemcpyHostToDevice, ctx->stream));
+    if (nexpand > 0) {
+      unsigned bx = (unsigned)((maxLdE + 255) / 256);
+      if (bx > 64) bx = 64;
+      expand_tables_kernel<<<dim3(bx, (unsigned)maxND, (unsigned)zc), 256, 0, ctx->stream>>>(dj);
+      ctx->launches++;
+    }
+    // CTAs past the last row block of their column block, or outside a smaller job of the batch, leave at once
+    if (count == 1) cov_factor_kernel_one<<<dim3((unsigned)maxRB, (unsigned)maxCB, 1), 256, 0, ctx->stream>>>(hj[0]);
+    else cov_factor_kernel<<<dim3((unsigned)maxRB, (unsigned)maxCB, (unsigned)zc), 256, 0, ctx->stream>>>(dj);
+    ctx->launches++;
+    if (z0 + 65535 < count) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // the job buffer is reused
+  }
   CUDA_TRY(ctx, cudaGetLastError());
   return 0;
+}
+
+int launch_cov_factor_layout(iak3d_ctx* ctx, const CovArgs& h, const double* d_W, int32_t q, int64_t n, int64_t Npad, int64_t ld,
+                             int32_t nCB_, double* d_L, const double* d_lncol, int lncol) {
+  FactorBuildJob b;
+  b.a = h; b.d_W = d_W; b.q = q; b.n = n; b.Npad = Npad; b.ld = ld; b.nCB = nCB_; b.d_L = d_L; b.d_lncol = d_lncol; b.lncol = lncol;
+  return launch_cov_factor_jobs(ctx, &b, 1);
 }
 
 // ---- rectangular / full build (setCIAK3D returning C, setCIAK3D2, prediction row panels) -------------
