@@ -93,3 +93,25 @@ def test_cl_pair_of_configs3_size_equals_exact(ctx):
     cl = iak.setupIAK3D_CL(ds["xData"], ds["dIData"], ds["zData"], ds["XData"], blk, ctx=ctx)
     got = iak.nllIAK3D_CL(None, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True, PARBNDS, True, cl, parsBTfmd=P)
     assert got == exact
+
+
+def test_edgeroi_shaped_example_driver_runs(ctx):
+    """examples/eg_edgeroi_shaped.py (the flow of egEdgeroi.R: optimIt fit -> predictIAK3D -> hold-out validation) end to end
+    on the GPU at a reduced size; the fitted objective must not be worse than the oracle's value at the same parameters."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from oracle import iak3d_oracle as orc
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "examples", "eg_edgeroi_shaped.py"), "--impl", "gpu", "--n", "350", "--grid", "8"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert np.isfinite(d["nll"]) and d["nll"] < 9e98 and d["fn_evals"] > 50 and d["gr_evals"] > 3
+    assert 0.5 <= d["holdout_in_pi90"] <= 1.0 and d["map_var_mean"] > 0
+    ds = synth.make_dataset(350 + 250, synth.SEEDS["E"])
+    fitr = ds["prof"] < ds["prof"].max() - 59
+    want = orc.nllIAK3D(np.array(d["pars"]), ds["zData"][fitr], ds["XData"][fitr], "spherical", 0.5, -9, 0, 0, 1, True,
+                        orc.setupIAK3D(ds["xData"][fitr], ds["dIData"][fitr]), PARBNDS)
+    assert abs(want - d["nll"]) <= 1e-8 * abs(want)
