@@ -517,29 +517,61 @@ def _small_chol_solve(A, b):
 
 
 def reml_tail(WiAW, lndetA, n, p, useReml=True, n_for_cxd=None, n_for_lndet=None):
-    """fitIAK3D.R:821-880 / compositeLikIAK3D.R:191-265.  -> dict(nll, betahat, cxdhat, lndetXiAX, resiAres)."""
-    XiAX = WiAW[:p, :p]; XiAz = WiAW[:p, p:p + 1]; ziAz = float(WiAW[p, p])
-    lndetXiAX, betahat = _small_chol_solve(XiAX, XiAz)
-    if not np.isfinite(lndetXiAX):
+    """fitIAK3D.R:821-880 / compositeLikIAK3D.R:191-265.  -> dict(nll, betahat, cxdhat, lndetXiAX, resiAres).  One element
+    of :func:`reml_tail_batch`, so that a single evaluation and the same evaluation inside a batch agree bit for bit."""
+    t = reml_tail_batch(np.asarray(WiAW, float)[None], np.array([lndetA], float), n, p, useReml, n_for_cxd, n_for_lndet, full=True)
+    if not t["ok"][0]:
         return dict(nll=BADNLL, betahat=None, cxdhat=float("nan"))
-    resiAres = float(ziAz - 2.0 * (betahat.T @ XiAz)[0, 0] + (betahat.T @ XiAX @ betahat)[0, 0])
-    if n_for_cxd is not None:
-        cxdhat = resiAres / n_for_cxd
-    else:
-        cxdhat = resiAres / (n - p) if useReml else resiAres / n
+    return dict(nll=float(t["nll"][0]), betahat=t["betahat"][0], cxdhat=float(t["cxdhat"][0]), lndetXiAX=float(t["lndetXiAX"][0]),
+                resiAres=float(t["resiAres"][0]))
+
+
+def reml_tail_batch(WiAW, lndetA, n, p, useReml=True, n_for_cxd=None, n_for_lndet=None, full=False):
+    """The closed-form REML / ML tail for a stack of evaluations (count x q x q, count) in one pass of batched NumPy calls:
+    the host tail of a forward-difference gradient costs as much as its device evaluations at Edgeroi size when it is
+    done one evaluation at a time.  -> nll (count,), BADNLL where the p x p system is not positive definite; with `full`
+    a dict of arrays (nll, ok, betahat, cxdhat, lndetXiAX, resiAres)."""
+    WiAW = np.asarray(WiAW, float); lndetA = np.asarray(lndetA, float)
+    cnt = WiAW.shape[0]
+    nll = np.full(cnt, BADNLL)
+    out = dict(nll=nll, ok=np.zeros(cnt, bool), betahat=np.full((cnt, p, 1), np.nan), cxdhat=np.full(cnt, np.nan),
+               lndetXiAX=np.full(cnt, np.nan), resiAres=np.full(cnt, np.nan))
+    XiAX = WiAW[:, :p, :p]; XiAz = WiAW[:, :p, p:p + 1]; ziAz = WiAW[:, p, p]
+    ok = np.all(np.isfinite(WiAW.reshape(cnt, -1)), axis=1)
+    Ls = np.zeros_like(XiAX)
+    for i in np.nonzero(ok)[0]:                       # cholesky has no batched failure mode: keep the loop, it is p x p
+        try:
+            Ls[i] = np.linalg.cholesky(XiAX[i])
+        except np.linalg.LinAlgError:
+            ok[i] = False
+    idx = np.nonzero(ok)[0]
+    if idx.size:
+        d = np.diagonal(Ls[idx], axis1=1, axis2=2)
+        idx = idx[np.all(np.isfinite(d) & (d > 0), axis=1)]
+    if idx.size == 0:
+        return out if full else nll
+    L = Ls[idx]
+    d = np.diagonal(L, axis1=1, axis2=2)
+    y = np.linalg.solve(L, XiAz[idx])
+    beta = np.linalg.solve(np.transpose(L, (0, 2, 1)), y)
+    lndetXiAX = 2.0 * np.sum(np.log(d), axis=1)
+    bXz = np.sum(beta * XiAz[idx], axis=(1, 2))
+    bXXb = np.sum(beta * (XiAX[idx] @ beta), axis=(1, 2))
+    res = ziAz[idx] - 2.0 * bXz + bXXb
     nn = n if n_for_lndet is None else n_for_lndet
     with np.errstate(invalid="ignore", divide="ignore"):
-        lndetC = lndetA + nn * np.log(cxdhat)
-        lndetXiCX = lndetXiAX - p * np.log(cxdhat)
-        resiCres = resiAres / cxdhat if cxdhat != 0 else float("nan")
-        if useReml:
-            nll = 0.5 * ((n - p) * math.log(2.0 * math.pi) + lndetC + lndetXiCX + resiCres)
+        if n_for_cxd is not None:
+            c = res / n_for_cxd
         else:
-            nll = 0.5 * (n * math.log(2.0 * math.pi) + lndetC + resiCres)
-    nll = float(nll)
-    if not np.isfinite(nll):
-        nll = BADNLL
-    return dict(nll=nll, betahat=betahat, cxdhat=cxdhat, lndetXiAX=lndetXiAX, resiAres=resiAres)
+            c = res / (n - p) if useReml else res / n
+        lndetC = lndetA[idx] + nn * np.log(c)
+        lndetXiCX = lndetXiAX - p * np.log(c)
+        resiCres = np.where(c != 0, res / c, np.nan)
+        v = 0.5 * ((n - p) * math.log(2.0 * math.pi) + lndetC + lndetXiCX + resiCres) if useReml else \
+            0.5 * (n * math.log(2.0 * math.pi) + lndetC + resiCres)
+    nll[idx] = np.where(np.isfinite(v), v, BADNLL)
+    out["ok"][idx] = True; out["betahat"][idx] = beta; out["cxdhat"][idx] = c; out["lndetXiAX"][idx] = lndetXiAX; out["resiAres"][idx] = res
+    return out if full else nll
 
 
 def nll_terms_batch(ctx, setups, parsList):
@@ -651,9 +683,10 @@ def gradnllIAK3D(pars, zData, XData, vXU=None, iU=None, modelx="matern", nud=0.5
         pb = readParsIAK3D(v, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds)
         structs.append(make_pars(pb, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt))
     lnd, G, st = nll_terms_batch(sm.ctx, [sm] * len(cand), structs)
-    vals = np.empty(len(cand))
-    for i in range(len(cand)):
-        vals[i] = reml_tail(_symm_upper(G[i].T), lnd[i], n, p, useReml)["nll"] if st[i] == OK else BADNLL
+    Gt = np.transpose(G, (0, 2, 1))
+    Gs = np.triu(Gt) + np.transpose(np.triu(Gt, 1), (0, 2, 1))           # forceSymmetric keeps the upper triangle (fitIAK3D.R:811)
+    Gs[st != OK] = np.nan
+    vals = reml_tail_batch(Gs, np.where(st == OK, lnd, np.nan), n, p, useReml)
     g = (vals[1:] - vals[0]) / delta
     g[~np.isfinite(g)] = 0.0
     return (g, vals[0]) if rtn_nll else g

@@ -93,3 +93,21 @@ def test_make_pars_struct():
     P2, modelx2, types2, _ = synth.default_pars("edgeroi")
     s2 = iak._lib.make_pars(P2, modelx2, *types2, 1)
     assert s2.modelx == 1 and s2.sdfdType[0] == -9 and np.isnan(s2.nux)
+
+
+def test_reml_tail_batch_equals_scalar_tail():
+    import numpy as np
+    from iak3d_b200 import api
+    rng = np.random.default_rng(4)
+    p, n, cnt = 5, 300, 6
+    W = []
+    for i in range(cnt):
+        B = rng.standard_normal((p + 1, p + 1)); W.append(B @ B.T + (p + 1) * np.eye(p + 1))
+    W = np.array(W); lnd = rng.uniform(-50, 50, cnt)
+    W[3, 0, 0] = -1.0                                # not positive definite -> BADNLL
+    for reml in (True, False):
+        got = api.reml_tail_batch(W, lnd, n, p, reml)
+        for i in range(cnt):
+            want = api.reml_tail(W[i], lnd[i], n, p, reml)["nll"]
+            assert got[i] == want or abs(got[i] - want) <= 1e-12 * abs(want)
+        assert got[3] == api.BADNLL
