@@ -271,6 +271,9 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
     int32_t* status = pb->status;
     const int64_t R0 = (int64_t)r * TM;
     const int nchunks = (mode == 2) ? pb->kchunks : j * (TN / KC);
+    // tasks of structurally triangular operands (the explicit inverse, gemm.cu) start their K-loop at chunk tk.w: the
+    // operand is zero before it.  0 for every factorisation / kriging task.
+    const int kstart = min(tk.w, nchunks);
     const double* __restrict__ Asrc = (mode == 2) ? pb->A : P;
     const int64_t nRUA = (mode == 2) ? pb->nRUA : nRUP;
     const uint32_t it0 = it;
@@ -291,7 +294,7 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
         bulk_g2s(At, Pt0, 2 * UNIT * 8, &at_bar);
         bulk_g2s(At + 2 * UNIT, Pt1, 2 * UNIT * 8, &at_bar);
         uint32_t itp = it0;
-        for (int c = 0; c < nchunks; c++, itp++) {
+        for (int c = kstart; c < nchunks; c++, itp++) {
           const int k = c >> 1;
           if ((c & 1) == 0 && mode != 2) {
             wait_flag(pb->doneP + (int64_t)r * nCB + k, epoch, status, abort_flag);
@@ -321,7 +324,7 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
 #pragma unroll
         for (int ni = 0; ni < 4; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
       uint32_t itc = it0;
-      for (int c = 0; c < nchunks; c++, itc++) {
+      for (int c = kstart; c < nchunks; c++, itc++) {
         const uint32_t s = itc % STAGES;
         if (prof && tid == 0) {
           const long long c0 = clock64();
@@ -357,7 +360,7 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
           const int u = idx / (UNIT / 2), w2 = idx % (UNIT / 2);
           reinterpret_cast<double2*>(((u >> 1) ? Pt1 : Pt0) + (u & 1) * UNIT)[w2] = reinterpret_cast<const double2*>(At + u * UNIT)[w2];
         }
-        it = it0 + nchunks;
+        it = it0 + (nchunks - kstart);
         at_phase ^= 1;
         __syncthreads();
         continue;
@@ -485,11 +488,11 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
       if (tid == 0) st_release(pb->doneP + (int64_t)r * nCB + j, epoch);
       if (prof && tid == 0) {
         prof[0] = tp0; prof[1] = tp1; prof[2] = tp2; prof[3] = tp3; prof[4] = tp4; prof[5] = (long long)gtime();
-        prof[6] = (nchunks > 0) ? s_tdep : tp0;
+        prof[6] = (nchunks > kstart) ? s_tdep : tp0;
         prof[7] = (kwait << 1) | (is_diag ? 1 : 0);     // cycles warp 0 spent waiting for operands in the K-loop
       }
     }
-    it = it0 + nchunks;
+    it = it0 + (nchunks - kstart);
     at_phase ^= 1;
     __syncthreads();
   }

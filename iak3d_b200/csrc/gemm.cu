@@ -100,12 +100,19 @@ struct DevBuf {
   template <class T> T* as() { return (T*)p; }
 };
 
-// all (r, j) tiles of a rows x cols output, column-major task order (mode 1 needs it; mode 2 does not care)
-int run_tiles(iak3d_ctx* ctx, const ProblemDesc& pd, int nRB, int nCB) {
+// (r, j) tiles of a rows x cols output, column-major task order (mode 1 needs it; mode 2 does not care).
+// tri = 0: all tiles, K-loop from 0.  tri = 1 (mode 1, identity panel: U = L^-T is upper triangular): only the tiles with
+// j >= 2r, K-loop from the row block's own first column (X(r,k) = 0 before it).  tri = 2 (mode 2, U U' with U upper
+// triangular, lower triangle of the symmetric result): only the tiles with r >= j/2, K-loop from the row block's first column.
+int run_tiles(iak3d_ctx* ctx, const ProblemDesc& pd, int nRB, int nCB, int tri = 0) {
   std::vector<int4> tasks;
   tasks.reserve((size_t)nRB * nCB);
   for (int j = 0; j < nCB; j++)
-    for (int r = 0; r < nRB; r++) tasks.push_back(make_int4(0, r, j, 0));
+    for (int r = 0; r < nRB; r++) {
+      if (tri == 1 && j < 2 * r) continue;
+      if (tri == 2 && r < j / 2) continue;
+      tasks.push_back(make_int4(0, r, j, tri ? r * (TM / UC) : 0));
+    }
   DevBuf d_tasks, d_prob, d_ticket;
   CUDA_TRY(ctx, d_tasks.alloc(tasks.size() * sizeof(int4)));
   CUDA_TRY(ctx, d_prob.alloc(sizeof(ProblemDesc)));
@@ -120,7 +127,7 @@ int run_tiles(iak3d_ctx* ctx, const ProblemDesc& pd, int nRB, int nCB) {
 
 // Out(rowsOut x colsOut, blocked) = use_cin * Out + alpha * A(rowsOut x K) B(colsOut x K)'   (all blocked, K multiple of 32)
 int gemm_nt(iak3d_ctx* ctx, const double* A, int64_t rowsA, const double* B, int64_t rowsB, double* Out, int64_t rowsOut,
-            int64_t colsOut, int64_t K, double alpha, int use_cin, int32_t* d_status) {
+            int64_t colsOut, int64_t K, double alpha, int use_cin, int32_t* d_status, int tri = 0) {
   ProblemDesc pd;
   memset(&pd, 0, sizeof(pd));
   pd.L = const_cast<double*>(B); pd.nRUL = rowsB / UR;
@@ -129,7 +136,14 @@ int gemm_nt(iak3d_ctx* ctx, const double* A, int64_t rowsA, const double* B, int
   pd.nCB = (int32_t)(colsOut / TN); pd.nRB = (int32_t)(rowsOut / TM);
   pd.mode = 2; pd.kchunks = (int32_t)(K / UC); pd.use_cin = use_cin; pd.alpha = alpha;
   pd.status = d_status;
-  return run_tiles(ctx, pd, pd.nRB, pd.nCB);
+  return run_tiles(ctx, pd, pd.nRB, pd.nCB, tri);
+}
+
+// upper triangle := transpose of the lower triangle (blocked layout)
+__global__ void mirror_lower_kernel(double* __restrict__ M, int64_t nRU, int64_t n) {
+  const int64_t c = blockIdx.y;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < c; i += (int64_t)gridDim.x * blockDim.x)
+    M[uidx(i, c, nRU)] = M[uidx(c, i, nRU)];
 }
 
 }  // namespace
@@ -159,12 +173,19 @@ int iak_inverse_blocked(iak3d_ctx* ctx, Slot* s, double** out, int64_t* rowsU_ou
   pd.L = s->d_L; pd.nRUL = s->ld / UR; pd.P = U.as<double>(); pd.nRUP = nRU; pd.invd = s->d_invd;
   pd.doneP = flags.as<int32_t>(); pd.nCB = s->nCB; pd.nRB = (int32_t)(rowsU / TM); pd.mode = 1; pd.epoch = 1;
   pd.w0 = (int32_t)s->Npad; pd.q = 0; pd.G = G.as<double>(); pd.ldG = rowsU; pd.status = status.as<int32_t>();
-  int rc = run_tiles(ctx, pd, pd.nRB, pd.nCB);
+  // U is upper triangular: only its non-zero tiles are computed, each K-loop starts at the tile's own row block
+  // (n^3/3 flops instead of n^3); the tiles below stay as the identity panel initialised them (zero)
+  int rc = run_tiles(ctx, pd, pd.nRB, pd.nCB, 1);
   if (rc != 0) return rc;
-  // iC = U U'
+  // iC = U U': lower triangle only, K from the row block on (n^3/3 flops instead of 2 n^3), then mirrored
   if (cudaMalloc(&iC, bytes) != cudaSuccess) { ctx->err = "inverse: allocation failed"; cudaGetLastError(); return IAK3D_ERR_CUDA; }
-  rc = gemm_nt(ctx, U.as<double>(), rowsU, U.as<double>(), rowsU, iC, rowsU, Npad, Npad, 1.0, 0, status.as<int32_t>());
+  rc = gemm_nt(ctx, U.as<double>(), rowsU, U.as<double>(), rowsU, iC, rowsU, Npad, Npad, 1.0, 0, status.as<int32_t>(), 2);
   if (rc != 0) { cudaFree(iC); return rc; }
+  {
+    dim3 grid((unsigned)std::min<int64_t>((Npad + 255) / 256, 64), (unsigned)Npad);
+    mirror_lower_kernel<<<grid, 256, 0, ctx->stream>>>(iC, nRU, Npad);
+    ctx->launches++;
+  }
   int32_t hs[2] = {0, 0};
   CUDA_TRY(ctx, cudaMemcpy(hs, status.p, sizeof(hs), cudaMemcpyDeviceToHost));
   if (hs[1] != 0) { cudaFree(iC); ctx->err = "inverse: dependency wait timed out (internal error)"; return IAK3D_ERR_TIMEOUT; }
