@@ -43,7 +43,7 @@ if do_nr:
     t0 = time.time()
     g = iak.gradHessIAK3D(sm, P, modelx, types, th)
     dt = time.time() - t0
-    flops = n ** 3 / 3.0 + n ** 3 + 2.0 * n ** 3 + 6 * 2.0 * n ** 3        # chol + L^-T + U U' + six T dC_i
+    flops = 3 * n ** 3 / 3.0 + 6 * 2.0 * n ** 3        # chol + L^-T + U U' (triangular-aware: n^3/3 each) + six T dC_i
     out.update(nr_wall_s=dt, nr_nll=g["nll"], nr_grad=list(map(float, g["grad"])), nr_tflops=flops / dt / 1e12)
     print(f"gradHess: {dt:.2f}s nll={g['nll']:.6f} ~{flops / dt / 1e12:.1f} TFLOP/s overall; grad={np.round(g['grad'], 4)}", flush=True)
     print("fim diag", np.round(np.diag(g["fim"]), 4))
