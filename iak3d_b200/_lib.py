@@ -67,6 +67,7 @@ _PROTOS = {
     "iak3d_nll_terms_batch": (C.c_int, [_vp, _i32, C.POINTER(_vp), C.POINTER(Pars), _dp, _dp, _ip]),
     "iak3d_nll_terms_batch_enqueue": (C.c_int, [_vp, _i32, C.POINTER(_vp), C.POINTER(Pars)]),
     "iak3d_nll_terms_batch_fetch": (C.c_int, [_vp, _dp, _dp, _ip]),
+    "iak3d_nll_grad": (C.c_int, [_vp, _i32, C.POINTER(Pars), _dp, _i32, _dp, _dp, _dp]),
     "iak3d_fit_create": (C.c_int, [_vp, C.POINTER(Pars), _dp, _dp, C.POINTER(_vp)]),
     "iak3d_fit_destroy": (C.c_int, [_vp]),
     "iak3d_fit_get": (C.c_int, [_vp, _dp, _dp, _dp, _dp]),

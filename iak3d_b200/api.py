@@ -662,9 +662,13 @@ def nllIAK3D(pars, zData, XData, vXU=None, iU=None, modelx="matern", nud=0.5, sd
 
 def gradnllIAK3D(pars, zData, XData, vXU=None, iU=None, modelx="matern", nud=0.5, sdfdType_cd1=0, sdfdType_cxd0=0,
                  sdfdType_cxd1=0, cmeOpt=0, prodSum=True, setupMats=None, parBnds=None, useReml=True, lnTfmdData=False,
-                 delta=1e-6, rtn_nll=False):
+                 delta=1e-6, rtn_nll=False, analytic=False):
     """Forward-difference gradient (fitIAK3D.R:1865-1886): the npar + 1 evaluations go to the GPU as ONE batch
-    (the reference forks them with mclapply, :1804).  NA differences become 0 (:1813)."""
+    (the reference forks them with mclapply, :1804).  NA differences become 0 (:1813).
+
+    `analytic=True` (not in the reference): the same candidates, but ONE factorisation, the explicit
+    inverse and one pass over it -- d nll / d theta_k = 1/2 sum_ij w_ij (A_k - A_0)_ij / delta (`iak3d_nll_grad`); the
+    differences are taken on the covariance ENTRIES, not on the likelihood, so no factorisation noise enters."""
     if lnTfmdData:
         raise NotImplementedError("lnTfmdData = TRUE is not on the accelerated path")
     sm = setupMats
@@ -682,6 +686,19 @@ def gradnllIAK3D(pars, zData, XData, vXU=None, iU=None, modelx="matern", nud=0.5
     for v in cand:
         pb = readParsIAK3D(v, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds)
         structs.append(make_pars(pb, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt))
+    if analytic:
+        parr = (Pars * len(cand))(*structs)
+        dl = f64(np.full(npar, float(delta)))
+        lnd1 = C.c_double(); G1 = np.empty((p + 1, p + 1), order="F"); gs = np.empty(npar)
+        st1 = sm.ctx.check(sm.ctx.lib.iak3d_nll_grad(sm.h, npar, parr, dptr(dl), 1 if useReml else 0, C.byref(lnd1), dptr(G1), dptr(gs)),
+                           allow=(NOT_SPD, BAD_PARS))
+        if st1 != OK:
+            return (np.zeros(npar), BADNLL) if rtn_nll else np.zeros(npar)
+        g = 0.5 * gs
+        g[~np.isfinite(g)] = 0.0
+        if not rtn_nll:
+            return g
+        return g, reml_tail(_symm_upper(np.array(G1)), lnd1.value, n, p, useReml)["nll"]
     lnd, G, st = nll_terms_batch(sm.ctx, [sm] * len(cand), structs)
     Gt = np.transpose(G, (0, 2, 1))
     Gs = np.triu(Gt) + np.transpose(np.triu(Gt, 1), (0, 2, 1))           # forceSymmetric keeps the upper triangle (fitIAK3D.R:811)

@@ -181,6 +181,8 @@ struct Batch {
   bool pending = false;
 };
 
+bool iak3d_ctx::batch_pending() const { return batch != nullptr && batch->pending; }
+
 extern "C" int iak3d_ctx_create(int device, iak3d_ctx** out) {
   if (out == nullptr) return IAK3D_ERR_ARG;
   *out = nullptr;
@@ -249,7 +251,8 @@ static void free_slot(Slot* s) {
 }
 
 // factor-buffer workspace for an n x n problem with q bordered rows (tables optional: nxU = ndIU = 0)
-int iak_alloc_slot(iak3d_ctx* ctx, int64_t n, int32_t q, int64_t nxU, int64_t ndIU, Slot** out) {
+// tables_only: no factor buffer (the perturbed parameter sets of the analytic gradient need tables, not matrices)
+int iak_alloc_slot(iak3d_ctx* ctx, int64_t n, int32_t q, int64_t nxU, int64_t ndIU, Slot** out, bool tables_only) {
   Slot* s = new Slot();
   s->n = n; s->q = q; s->nxU = nxU; s->ndIU = ndIU;
   s->Npad = round_up(std::max<int64_t>(n, 1), TN);
@@ -257,17 +260,19 @@ int iak_alloc_slot(iak3d_ctx* ctx, int64_t n, int32_t q, int64_t nxU, int64_t nd
   s->nCB = (int32_t)(s->Npad / TN); s->nRB = (int32_t)(s->ld / TM);
   cudaError_t e = cudaSuccess;
   auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, std::max<size_t>(bytes, 16)); };
-  A((void**)&s->d_L, (size_t)ubuf_doubles(s->ld, s->Npad) * sizeof(double));
+  if (!tables_only) A((void**)&s->d_L, (size_t)ubuf_doubles(s->ld, s->Npad) * sizeof(double));
   A((void**)&s->d_phix, (size_t)nxU * nxU * sizeof(double));
   // tables | avVar vectors | avsd vectors | (16-byte aligned) combined tables of the factor build
   A((void**)&s->d_phid, (size_t)(NTAB_BUF * ndIU * ndIU + round_up((NTAB_BUF + 3) * ndIU, 2) + 3 * ndIU * ndIU) * sizeof(double));
-  A((void**)&s->d_invd, (size_t)s->nCB * INVD_BLOCK * sizeof(double));
   const size_t nflags = (size_t)s->nRB * s->nCB + s->nCB;
-  A((void**)&s->d_flags, nflags * sizeof(int32_t));
-  A((void**)&s->d_logsum, (size_t)s->nCB * sizeof(double));
-  A((void**)&s->d_G, 64 * 64 * sizeof(double));
-  if (ndIU > 0) A((void**)&s->d_E, (size_t)2 * ndIU * round_up(n, 2) * sizeof(double));
-  if (e == cudaSuccess) e = cudaMemsetAsync(s->d_flags, 0, nflags * sizeof(int32_t), ctx->stream);
+  if (!tables_only) {
+    A((void**)&s->d_invd, (size_t)s->nCB * INVD_BLOCK * sizeof(double));
+    A((void**)&s->d_flags, nflags * sizeof(int32_t));
+    A((void**)&s->d_logsum, (size_t)s->nCB * sizeof(double));
+    A((void**)&s->d_G, 64 * 64 * sizeof(double));
+    if (ndIU > 0) A((void**)&s->d_E, (size_t)2 * ndIU * round_up(n, 2) * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->d_flags, 0, nflags * sizeof(int32_t), ctx->stream);
+  }
   if (e != cudaSuccess) {
     ctx->err = std::string("slot allocation failed: ") + cudaGetErrorString(e);
     free_slot(s);
@@ -351,6 +356,7 @@ extern "C" int iak3d_dataset_destroy(iak3d_ds* ds) {
   cudaSetDevice(ds->ctx->device);
   cudaStreamSynchronize(ds->ctx->stream);
   for (Slot* s : ds->slots) free_slot(s);
+  for (Slot* s : ds->tslots) free_slot(s);
   cudaFree(ds->d_xid); cudaFree(ds->d_did); cudaFree(ds->d_xU); cudaFree(ds->d_dIU); cudaFree(ds->d_W);
   if (ds->h_W) cudaFreeHost(ds->h_W);
   delete ds;
@@ -384,10 +390,21 @@ extern "C" int iak3d_dataset_set_sdfd_spline(iak3d_ds* ds, int32_t comp, int32_t
   return IAK3D_OK;
 }
 
+int iak_get_table_slot(iak3d_ds* ds, size_t k, Slot** out) {
+  while (ds->tslots.size() <= k) {
+    Slot* s = nullptr;
+    const int st = iak_alloc_slot(ds->ctx, ds->n, 0, ds->nxU, ds->ndIU, &s, true);
+    if (st != 0) return st;
+    ds->tslots.push_back(s);
+  }
+  *out = ds->tslots[k];
+  return 0;
+}
+
 int iak_get_slot(iak3d_ds* ds, size_t k, Slot** out) {
   while (ds->slots.size() <= k) {
     Slot* s = nullptr;
-    const int st = iak_alloc_slot(ds->ctx, ds->n, ds->q, ds->nxU, ds->ndIU, &s);
+    const int st = iak_alloc_slot(ds->ctx, ds->n, ds->q, ds->nxU, ds->ndIU, &s, false);
     if (st != 0) return st;
     ds->slots.push_back(s);
   }
@@ -412,6 +429,9 @@ struct TableCache {
     Entry x; x.ds = ds; x.kind = kind; memcpy(x.k, k, sizeof(x.k)); x.ptr = ptr; x.av = av; e.push_back(x);
   }
 };
+
+TableCache* iak_table_cache_new() { return new TableCache(); }
+void iak_table_cache_free(TableCache* c) { delete c; }
 
 int iak_square_tables(iak3d_ctx* ctx, const iak3d_ds* ds, const EvalPlan& pl, Slot* s, CovArgs* a, TableCache* cache = nullptr) {
   const int64_t nd = ds->ndIU, nx = ds->nxU;
@@ -1055,7 +1075,7 @@ extern "C" int iak3d_lndet_invCb(iak3d_ctx* ctx, int64_t n, const double* C, int
     for (int ps = 0; ps < npass && rc == 0; ps++) {
       const int q = nrhs > 0 ? std::min(64, nrhs - ps * 64) : 0;
       Slot* s = nullptr;
-      rc = iak_alloc_slot(ctx, n, q, 0, 0, &s);
+      rc = iak_alloc_slot(ctx, n, q, 0, 0, &s, false);
       if (rc != 0) break;
       made.push_back(s);
       rc = launch_pack_factor_layout(ctx, dC, n, db ? db + (size_t)ps * 64 * n : nullptr, q, s->Npad, s->ld, s->d_L);

@@ -16,7 +16,7 @@
 // from api.cu
 void iak_unique_first(int64_t n, const double* c0, const double* c1, std::vector<int32_t>& id, std::vector<double>& U);
 int iak_make_plan(iak3d_ctx* ctx, const iak3d_pars* p, bool square, EvalPlan* pl);
-int iak_alloc_slot(iak3d_ctx* ctx, int64_t n, int32_t q, int64_t nxU, int64_t ndIU, Slot** out);
+int iak_alloc_slot(iak3d_ctx* ctx, int64_t n, int32_t q, int64_t nxU, int64_t ndIU, Slot** out, bool tables_only = false);
 void iak_free_slot(Slot* s);
 struct TableCache;
 int iak_square_tables(iak3d_ctx* ctx, const iak3d_ds* ds, const EvalPlan& pl, Slot* s, CovArgs* a, TableCache* cache = nullptr);

@@ -47,6 +47,7 @@ struct iak3d_ctx {
   void* flush_buf = nullptr; size_t flush_bytes = 0;
   // batch state (nll_terms_batch_enqueue -> fetch)
   struct Batch* batch = nullptr;
+  bool batch_pending() const;
   double last_chol_flops = 0, last_cov_bytes = 0;
   bool stage_events_valid = false;
   void* d_fbjobs = nullptr; size_t fbjobs_cap = 0;     // device copy of the covariance-build jobs of one launch
@@ -92,6 +93,7 @@ struct iak3d_ds {
   int64_t ld = 0;       // rows of the factor buffer = round_up(Npad + q, TM)
   int32_t nCB = 0, nRB = 0;
   std::vector<Slot*> slots;
+  std::vector<Slot*> tslots;            // table-only slots (perturbed parameter sets of the analytic gradient)
 };
 
 // One covariance evaluation planned on the host from parsBTfmd (no device work).

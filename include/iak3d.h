@@ -144,6 +144,18 @@ IAK3D_API int iak3d_nll_terms_batch(iak3d_ctx* ctx, int32_t count, iak3d_ds* con
 IAK3D_API int iak3d_nll_terms_batch_enqueue(iak3d_ctx* ctx, int32_t count, iak3d_ds* const* ds, const iak3d_pars* pars);
 IAK3D_API int iak3d_nll_terms_batch_fetch(iak3d_ctx* ctx, double* lndetA, double* WiAW, int32_t* status);
 
+/* ---- analytic gradient of the profiled REML / ML objective (replaces the npar + 1 evaluations of gradnllIAK3D,
+ * fitIAK3D.R:1865-1886) --------------------------------------------------------------------------
+ * pars[0] = the parameters; pars[k], k = 1..npar = the parameters with the k-th UNCONSTRAINED parameter moved by
+ * delta[k-1] and passed through the host's transforms (readParsIAK3D) -- the candidates of the forward-difference
+ * gradient.  One factorisation + explicit inverse + one pass over the lower triangle return lndetA and WiAW of
+ * pars[0] (so the caller has the function value too) and
+ *     gsum[k-1] = sum_ij w_ij (A(pars[k]) - A(pars[0]))_ij / delta[k-1] ,   d nll / d theta_k = gsum[k-1] / 2 ,
+ * w = A^-1 - [REML] A^-1 X (X'A^-1 X)^-1 X'A^-1 - u u' / cxdhat,  u = A^-1 (z - X betahat).  gsum[k-1] is NaN for a
+ * candidate with invalid parameters (the reference's NA difference, set to 0 by the caller, fitIAK3D.R:1813). */
+IAK3D_API int iak3d_nll_grad(iak3d_ds* ds, int32_t npar, const iak3d_pars* pars, const double* delta, int32_t useReml,
+                   double* lndetA, double* WiAW, double* gsum);
+
 /* ---- kept fit == the big matrices of lmmFit (fitIAK3D.R:919-936; predictIAK3D.R:110-139) -----
  * pars are the RESCALED parameters (cxdhat folded in, fitIAK3D.R:857-863), so C = setCIAK3D(pars).
  * betahat (p), vbetahat (p x p).  Computes and keeps L = chol(C), iCX, iCz_muhat on the device. */

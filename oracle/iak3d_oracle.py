@@ -850,6 +850,37 @@ def nllIAK3D(pars, zData, XData, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdT
                 zData=zData)
 
 
+def gradnllIAK3D_analytic(pars, zData, XData, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum,
+                          setupMats, parBnds, useReml=True, delta=1e-6):
+    """Analytic gradient of the profiled objective (not in the reference, which differentiates nllIAK3D by forward
+    differences, fitIAK3D.R:1865-1886): d nll / d theta_k = 1/2 sum_ij w_ij (dA/dtheta_k)_ij with
+    w = A^-1 - [REML] A^-1 X (X'A^-1 X)^-1 X'A^-1 - u u'/cxdhat, u = A^-1 (z - X betahat); dA/dtheta_k by a forward
+    difference of the covariance ENTRIES at the same candidates the reference's gradient uses."""
+    pars = np.asarray(pars, float).reshape(-1)
+    zData = np.asarray(zData, float).reshape(-1)
+    XData = np.asarray(XData, float).reshape(zData.size, -1)
+    n, p = XData.shape
+    types = (sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1)
+    rd = lambda v: readParsIAK3D(v, modelx, nud, *types, cmeOpt, prodSum, parBnds)
+    A0, _ = setCIAK3D(rd(pars), modelx, *types, cmeOpt, setupMats)
+    iA = np.linalg.inv(A0)
+    Y = iA @ XData
+    M = XData.T @ Y
+    beta = np.linalg.solve(M, Y.T @ zData)
+    u = iA @ (zData - XData @ beta)
+    res = float((zData - XData @ beta) @ u)
+    c = res / (n - p) if useReml else res / n
+    w = iA - np.outer(u, u) / c
+    if useReml:
+        w = w - Y @ np.linalg.solve(M, Y.T)
+    g = np.zeros(pars.size)
+    for k in range(pars.size):
+        v = pars.copy(); v[k] += delta
+        Ak, _ = setCIAK3D(rd(v), modelx, *types, cmeOpt, setupMats)
+        g[k] = 0.0 if Ak is None else 0.5 * float(np.sum(w * (Ak - A0))) / delta
+    return g
+
+
 def nllIAK3D_CL(pars, zData, XData, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt,
                 prodSum, parBnds, useReml, compLikMats, xData, dIData, parsBTfmd=None, rtnTerms=False):
     """compositeLikIAK3D.R:6-307.  ``compLikMats`` = dict(compLikOptn, listBlocks (list of 0-based

@@ -142,3 +142,36 @@ def test_full_size_5k_against_lapack(ctx):
     assert scaled_err(got["WiAW"], want) <= TOL
     # size-independent property: A (A^-1 W) == W
     assert scaled_err(A @ got["iAW"], W) <= 1e-8
+
+
+@pytest.mark.parametrize("modelx,types,cmeOpt,pars,useReml", [
+    ("matern", (0, 0, 0), 1, [0.2, -1.3, 0.1, -2.2, -1.4, -1.9, 0.4, -3.0], True),
+    ("matern", (0, 0, 0), 1, [0.2, -1.3, 0.1, -2.2, -1.4, -1.9, 0.4, -3.0], False),
+    ("spherical", (-9, 0, 0), 1, [0.3, 0.1, -2.0, -1.2, 0.4, -3.0], True),
+    ("matern", (-1, -1, 0), 0, [0.1, 0.4, -0.2, -2.0, -1.5, -1.7, 0.3, -0.5, 0.2, -0.8, -0.1], True),
+    ("nugget", (0, 0, 0), 1, [0.1, -2.0, -1.7, -3.0], True),
+])
+def test_analytic_gradient_vs_oracle(ctx, modelx, types, cmeOpt, pars, useReml):
+    """iak3d_nll_grad (one factorisation + explicit inverse + one pass) against the oracle's dense formula; the returned
+    function value is the one nllIAK3D returns, bit for bit."""
+    ds = synth.make_dataset(520, 44)
+    pars = np.array(pars, float)
+    sm = iak.setupIAK3D(ds["xData"], ds["dIData"], ctx=ctx)
+    kw = dict(modelx=modelx, nud=0.5, sdfdType_cd1=types[0], sdfdType_cxd0=types[1], sdfdType_cxd1=types[2], cmeOpt=cmeOpt, prodSum=True,
+              setupMats=sm, parBnds=PARBNDS, useReml=useReml)
+    g, f0 = iak.gradnllIAK3D(pars, ds["zData"], ds["XData"], analytic=True, rtn_nll=True, **kw)
+    want = orc.gradnllIAK3D_analytic(pars, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True,
+                                     orc.setupIAK3D(ds["xData"], ds["dIData"]), PARBNDS, useReml=useReml)
+    assert np.max(np.abs(g - want)) <= 1e-6 * max(1.0, np.max(np.abs(want))), (g, want)
+    assert f0 == iak.nllIAK3D(pars, ds["zData"], ds["XData"], **kw)
+    gfd = iak.gradnllIAK3D(pars, ds["zData"], ds["XData"], **kw)          # the forward-difference batch it replaces
+    assert np.max(np.abs(g - gfd)) <= 2e-3 * max(1.0, np.max(np.abs(g)))
+
+
+def test_analytic_gradient_bad_candidate_gives_zero(ctx):
+    """A candidate outside the valid range (the reference's NA difference, fitIAK3D.R:1813) contributes 0."""
+    ds = synth.make_dataset(200, 45)
+    sm = iak.setupIAK3D(ds["xData"], ds["dIData"], ctx=ctx)
+    pars = np.array([0.2, 50.0, 0.1, -2.2, -1.4, -1.9, 0.4, -3.0])       # nux at its upper bound: logit saturates, still valid
+    g = iak.gradnllIAK3D(pars, ds["zData"], ds["XData"], analytic=True, modelx="matern", nud=0.5, cmeOpt=1, setupMats=sm, parBnds=PARBNDS)
+    assert np.all(np.isfinite(g))

@@ -185,3 +185,23 @@ def test_bessel_reference_values():
     x = np.array([0.01, 0.5, 2.0, 9.0, 40.0])
     assert relerr(ssp.kv(0.5, x), np.sqrt(np.pi / (2 * x)) * np.exp(-x)) < 1e-14
     assert relerr(ssp.kv(1.5, x), np.sqrt(np.pi / (2 * x)) * np.exp(-x) * (1 + 1 / x)) < 1e-14
+
+
+def test_analytic_gradient_formula_against_central_differences():
+    """The weights of the analytic gradient (oracle.gradnllIAK3D_analytic; product: iak3d_nll_grad): REML and ML, against
+    central differences of the oracle's own objective."""
+    import numpy as np
+    from iak3d_b200 import synth
+    from oracle import iak3d_oracle as orc
+    from helpers import PARBNDS
+    ds = synth.make_dataset(260, 33)
+    sm = orc.setupIAK3D(ds["xData"], ds["dIData"])
+    pars = np.array([0.2, -1.3, 0.1, -2.2, -1.4, -1.9, 0.4, -3.0])       # matern: ax, nux, ad, cx0, cx1, cd1, cxd1, cme
+    for useReml in (True, False):
+        f = lambda v: orc.nllIAK3D(v, ds["zData"], ds["XData"], "matern", 0.5, 0, 0, 0, 1, True, sm, PARBNDS, useReml=useReml)
+        g = orc.gradnllIAK3D_analytic(pars, ds["zData"], ds["XData"], "matern", 0.5, 0, 0, 0, 1, True, sm, PARBNDS, useReml=useReml)
+        for k in range(pars.size):
+            h = 1e-5
+            vp = pars.copy(); vp[k] += h; vm = pars.copy(); vm[k] -= h
+            cd = (f(vp) - f(vm)) / (2 * h)
+            assert abs(g[k] - cd) <= 2e-5 * max(1.0, abs(cd)), (useReml, k, g[k], cd)
