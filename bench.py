@@ -183,6 +183,20 @@ def run_s5(args, rank, local_rank, world, comm):
         ctx.check(lib.iak3d_nll_terms_batch_fetch(ctx.h, dptr(lnd), dptr(G), iptr(st)))
     single_ms = ctx.timer_stop() / reps
 
+    # ---- the same gradient by the analytic pass (iak3d_nll_grad; informational, not part of `value`) ----
+    kwg = dict(modelx=modelx, nud=0.5, sdfdType_cd1=types[0], sdfdType_cxd0=types[1], sdfdType_cxd1=types[2], cmeOpt=cmeOpt, prodSum=True,
+               setupMats=sm, parBnds=PARBNDS, useReml=True)
+    grad_ms = {}
+    for name, an in (("forward_difference_batch", False), ("analytic_pass", True)):
+        for w in range(2):
+            api.gradnllIAK3D(pars, ds["zData"], ds["XData"], analytic=an, **kwg)
+        ctx.sync(); t0 = time.perf_counter()
+        for k in range(reps):
+            gk = api.gradnllIAK3D(pars + 1e-4 * np.sin(k), ds["zData"], ds["XData"], analytic=an, **kwg)
+        ctx.sync(); grad_ms[name] = 1e3 * (time.perf_counter() - t0) / reps
+        grad_ms[name + "_norm"] = float(np.linalg.norm(gk))
+    sm.upload_W(W)
+
     # ---- end to end through the plugin call (e2e) ----
     for w in range(min(args.warmup, 3)):
         step_e2e(-1 - w)
@@ -208,7 +222,7 @@ def run_s5(args, rank, local_rank, world, comm):
                     evals_per_step=nb, step="one forward-difference gradient (npar+1 evaluations in one batch)",
                     parallelism="replicas only" if world > 1 else "1 GPU",
                     l2="working set (factor buffers %.0f MB) exceeds the 126 MB L2; no flush needed" % (nb * 8.0 * n * n / 1e6)),
-        single_eval_ms=single_ms, single_eval_per_s=1e3 / single_ms,
+        single_eval_ms=single_ms, single_eval_per_s=1e3 / single_ms, gradient_wall_ms=grad_ms,
         stage_ms=dict(tables=stage[0], cov_build=stage[1], factorise=stage[2], finish=stage[3]),
         roofline=dict(kernel="tile_task_kernel (tile Cholesky + bordered solves, FP64 DMMA)", bound="tensor", achieved=tf,
                       peak=peaks["dmma"], unit="TFLOP/s", frac=tf / peaks["dmma"], traffic=ncu_traffic("tile_task_kernel", n, nb),

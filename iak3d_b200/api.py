@@ -668,7 +668,8 @@ def gradnllIAK3D(pars, zData, XData, vXU=None, iU=None, modelx="matern", nud=0.5
 
     `analytic=True` (not in the reference): the same candidates, but ONE factorisation, the explicit
     inverse and one pass over it -- d nll / d theta_k = 1/2 sum_ij w_ij (A_k - A_0)_ij / delta (`iak3d_nll_grad`); the
-    differences are taken on the covariance ENTRIES, not on the likelihood, so no factorisation noise enters."""
+    differences are taken on the covariance ENTRIES, not on the likelihood, so no factorisation noise enters.
+    `analytic="auto"` picks it from n = 4000 on, where it is faster than the batch."""
     if lnTfmdData:
         raise NotImplementedError("lnTfmdData = TRUE is not on the accelerated path")
     sm = setupMats
@@ -686,6 +687,8 @@ def gradnllIAK3D(pars, zData, XData, vXU=None, iU=None, modelx="matern", nud=0.5
     for v in cand:
         pb = readParsIAK3D(v, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds)
         structs.append(make_pars(pb, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt))
+    if analytic == "auto":            # measured on B200: the pass pays from n ~ 4000 on (1.2x at 5000, 2.6x at 20000)
+        analytic = n >= 4000
     if analytic:
         parr = (Pars * len(cand))(*structs)
         dl = f64(np.full(npar, float(delta)))

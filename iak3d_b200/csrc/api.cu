@@ -357,6 +357,7 @@ extern "C" int iak3d_dataset_destroy(iak3d_ds* ds) {
   cudaStreamSynchronize(ds->ctx->stream);
   for (Slot* s : ds->slots) free_slot(s);
   for (Slot* s : ds->tslots) free_slot(s);
+  cudaFree(ds->d_gradU); cudaFree(ds->d_gradiC);
   cudaFree(ds->d_xid); cudaFree(ds->d_did); cudaFree(ds->d_xU); cudaFree(ds->d_dIU); cudaFree(ds->d_W);
   if (ds->h_W) cudaFreeHost(ds->h_W);
   delete ds;

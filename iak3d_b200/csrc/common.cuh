@@ -94,6 +94,7 @@ struct iak3d_ds {
   int32_t nCB = 0, nRB = 0;
   std::vector<Slot*> slots;
   std::vector<Slot*> tslots;            // table-only slots (perturbed parameter sets of the analytic gradient)
+  double* d_gradU = nullptr; double* d_gradiC = nullptr; size_t grad_bytes = 0;   // analytic gradient: L^-T and the explicit inverse (blocked), kept between calls
 };
 
 // One covariance evaluation planned on the host from parsBTfmd (no device work).

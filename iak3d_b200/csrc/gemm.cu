@@ -148,13 +148,64 @@ __global__ void mirror_lower_kernel(double* __restrict__ M, int64_t nRU, int64_t
 
 }  // namespace
 
-// iC (blocked, rowsU x Npad with rowsU = round_up(Npad, 128)) from a finished factor.  Caller frees *out with cudaFree.
-int iak_inverse_blocked(iak3d_ctx* ctx, Slot* s, double** out, int64_t* rowsU_out) {
+// out (n x q, column-major) = M W for the leading n x n part of a blocked (full, symmetric) matrix.  CTA = 128 rows x a
+// chunk of PP_CH columns (the chunk of W is staged in shared memory and read as a broadcast); the chunks' partial
+// sums are added in chunk order by a second kernel: deterministic.
+constexpr int PP_CH = 256;
+__global__ void __launch_bounds__(128) panel_product_kernel(const double* __restrict__ M, int64_t nRU, int64_t n, const double* __restrict__ W,
+                                                            int q, double* __restrict__ part /* [chunk][q][n] */) {
+  extern __shared__ double sw[];                     // PP_CH x q (column c of the chunk: sw[c * q + w])
+  const int64_t c0 = (int64_t)blockIdx.y * PP_CH;
+  const int cn = (int)((n - c0) < PP_CH ? (n - c0) : PP_CH);
+  for (int idx = threadIdx.x; idx < cn * q; idx += blockDim.x) { const int w = idx / cn, c = idx % cn; sw[c * q + w] = W[(int64_t)w * n + c0 + c]; }
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int w0 = 0; w0 < q; w0 += 16) {
+    double acc[16];
+#pragma unroll
+    for (int w = 0; w < 16; w++) acc[w] = 0.0;
+    for (int c = 0; c < cn; c++) {
+      const double m = M[uidx(i, c0 + c, nRU)];
+#pragma unroll
+      for (int w = 0; w < 16; w++) if (w0 + w < q) acc[w] = fma(m, sw[c * q + w0 + w], acc[w]);
+    }
+#pragma unroll
+    for (int w = 0; w < 16; w++) if (w0 + w < q) part[((int64_t)blockIdx.y * q + w0 + w) * n + i] = acc[w];
+  }
+}
+__global__ void panel_reduce_kernel(const double* __restrict__ part, int nchunk, int64_t nq, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  double s = 0.0;
+  for (int k = 0; k < nchunk; k++) s += part[(int64_t)k * nq + i];
+  out[i] = s;
+}
+int launch_panel_product(iak3d_ctx* ctx, const double* d_M, int64_t nRU, int64_t n, const double* d_W, int q, double* d_out) {
+  if (n == 0 || q == 0) return 0;
+  const int nchunk = (int)((n + PP_CH - 1) / PP_CH);
+  double* d_part = nullptr;
+  if (cudaMalloc(&d_part, (size_t)nchunk * q * n * sizeof(double)) != cudaSuccess) { ctx->err = "panel product: allocation failed"; cudaGetLastError(); return IAK3D_ERR_CUDA; }
+  panel_product_kernel<<<dim3((unsigned)((n + 127) / 128), (unsigned)nchunk), 128, (size_t)PP_CH * q * sizeof(double), ctx->stream>>>(d_M, nRU, n, d_W, q, d_part);
+  panel_reduce_kernel<<<(unsigned)(((int64_t)n * q + 255) / 256), 256, 0, ctx->stream>>>(d_part, nchunk, (int64_t)n * q, d_out);
+  ctx->launches += 2;
+  const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_part);
+  CUDA_TRY(ctx, e);
+  return 0;
+}
+
+// iC (blocked, rowsU x Npad with rowsU = round_up(Npad, 128)) from a finished factor.  With U_keep / iC_keep (both of
+// ubuf_doubles(rowsU, Npad) doubles, owned by the caller) nothing is allocated for the two big buffers and *out = iC_keep;
+// otherwise the caller frees *out with cudaFree.
+int iak_inverse_blocked(iak3d_ctx* ctx, Slot* s, double** out, int64_t* rowsU_out, double* U_keep, double* iC_keep) {
   const int64_t Npad = s->Npad, rowsU = round_up(Npad, TM), nRU = rowsU / UR;
   const size_t bytes = (size_t)ubuf_doubles(rowsU, Npad) * sizeof(double);
   DevBuf U, G, flags, status;
-  double* iC = nullptr;
-  CUDA_TRY(ctx, U.alloc(bytes));
+  double* iC = iC_keep;
+  if (U_keep != nullptr) { U.p = U_keep; }
+  else CUDA_TRY(ctx, U.alloc(bytes));
+  struct Release { DevBuf& b; bool keep; ~Release() { if (keep) b.p = nullptr; } } rel{U, U_keep != nullptr};
   CUDA_TRY(ctx, G.alloc((size_t)rowsU * sizeof(double)));
   const size_t nfl = (size_t)(rowsU / TM) * s->nCB;
   CUDA_TRY(ctx, flags.alloc(nfl * sizeof(int32_t)));
@@ -178,9 +229,9 @@ int iak_inverse_blocked(iak3d_ctx* ctx, Slot* s, double** out, int64_t* rowsU_ou
   int rc = run_tiles(ctx, pd, pd.nRB, pd.nCB, 1);
   if (rc != 0) return rc;
   // iC = U U': lower triangle only, K from the row block on (n^3/3 flops instead of 2 n^3), then mirrored
-  if (cudaMalloc(&iC, bytes) != cudaSuccess) { ctx->err = "inverse: allocation failed"; cudaGetLastError(); return IAK3D_ERR_CUDA; }
+  if (iC == nullptr && cudaMalloc(&iC, bytes) != cudaSuccess) { ctx->err = "inverse: allocation failed"; cudaGetLastError(); return IAK3D_ERR_CUDA; }
   rc = gemm_nt(ctx, U.as<double>(), rowsU, U.as<double>(), rowsU, iC, rowsU, Npad, Npad, 1.0, 0, status.as<int32_t>(), 2);
-  if (rc != 0) { cudaFree(iC); return rc; }
+  if (rc != 0) { if (iC_keep == nullptr) cudaFree(iC); return rc; }
   {
     dim3 grid((unsigned)std::min<int64_t>((Npad + 255) / 256, 64), (unsigned)Npad);
     mirror_lower_kernel<<<grid, 256, 0, ctx->stream>>>(iC, nRU, Npad);
@@ -188,14 +239,14 @@ int iak_inverse_blocked(iak3d_ctx* ctx, Slot* s, double** out, int64_t* rowsU_ou
   }
   int32_t hs[2] = {0, 0};
   CUDA_TRY(ctx, cudaMemcpy(hs, status.p, sizeof(hs), cudaMemcpyDeviceToHost));
-  if (hs[1] != 0) { cudaFree(iC); ctx->err = "inverse: dependency wait timed out (internal error)"; return IAK3D_ERR_TIMEOUT; }
+  if (hs[1] != 0) { if (iC_keep == nullptr) cudaFree(iC); ctx->err = "inverse: dependency wait timed out (internal error)"; return IAK3D_ERR_TIMEOUT; }
   *out = iC; *rowsU_out = rowsU;
   return 0;
 }
 
 int iak_inverse_from_factor(iak3d_ctx* ctx, Slot* s, double* d_iC /* n x n column-major */) {
   double* iCb = nullptr; int64_t rowsU = 0;
-  int rc = iak_inverse_blocked(ctx, s, &iCb, &rowsU);
+  int rc = iak_inverse_blocked(ctx, s, &iCb, &rowsU, nullptr, nullptr);
   if (rc != 0) return rc;
   dim3 grid((unsigned)((s->n + 255) / 256), (unsigned)s->n);
   unblock_kernel<<<grid, 256, 0, ctx->stream>>>(iCb, rowsU / UR, s->n, d_iC);
@@ -287,7 +338,7 @@ extern "C" int iak3d_gradhess(iak3d_ds* ds, const iak3d_pars* pars, int32_t ncom
     }
     // ---- T = iC - iCX (X'iCX)^-1 iCX'  (:183) ----
     int64_t rowsU = 0;
-    rc = iak_inverse_blocked(ctx, s, &iCb, &rowsU);
+    rc = iak_inverse_blocked(ctx, s, &iCb, &rowsU, nullptr, nullptr);
     if (rc != 0) break;
     const int64_t nRU = rowsU / UR, Npad = s->Npad;
     const size_t mbytes = (size_t)ubuf_doubles(rowsU, Npad) * sizeof(double);

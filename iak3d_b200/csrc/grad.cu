@@ -11,9 +11,11 @@
 // table loads per entry and no second factorisation; sets share tables (a perturbed variance changes no table at all),
 // so an entry loads each DISTINCT table once.  All parameters are handled in the same pass over A^-1.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 
 #include "common.cuh"
 
@@ -27,7 +29,8 @@ void iak_table_cache_free(TableCache* c);
 int iak_square_tables(iak3d_ctx* ctx, const iak3d_ds* ds, const EvalPlan& pl, Slot* s, CovArgs* a, TableCache* cache = nullptr);
 int iak_factor_slot(iak3d_ctx* ctx, Slot* s, int32_t* status_out, double* lndet_out, double* G_out);
 int iak_backsolve_to_host(iak3d_ctx* ctx, Slot* s, double* out_host, double* d_out_opt);
-int iak_inverse_blocked(iak3d_ctx* ctx, Slot* s, double** out, int64_t* rowsU_out);
+int iak_inverse_blocked(iak3d_ctx* ctx, Slot* s, double** out, int64_t* rowsU_out, double* U_keep, double* iC_keep);
+int launch_panel_product(iak3d_ctx* ctx, const double* d_M, int64_t nRU, int64_t n, const double* d_W, int q, double* d_out);
 
 namespace {
 
@@ -153,6 +156,10 @@ extern "C" int iak3d_nll_grad(iak3d_ds* ds, int32_t npar, const iak3d_pars* pars
   const int q = ds->q, p = q - 1;
   const double nanv = nan("");
   for (int k = 0; k < npar; k++) gsum[k] = nanv;
+  const bool prof = getenv("IAK3D_GRADPROF") != nullptr;
+  auto tnow = [&]() { if (prof) cudaStreamSynchronize(ctx->stream); return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  const auto t0 = tnow();
   // ---- plans and tables of the npar + 1 parameter sets (tables are shared wherever the parameters allow) ----
   std::vector<EvalPlan> plans((size_t)npar + 1);
   for (int k = 0; k <= npar; k++) {
@@ -174,6 +181,7 @@ extern "C" int iak3d_nll_grad(iak3d_ds* ds, int32_t npar, const iak3d_pars* pars
   }
   iak_table_cache_free(cache);
   if (rc != 0) return rc;
+  const auto t1 = tnow();
   // ---- base point: build, factorise, A^-1 W ----
   Slot* s = s0;
   rc = launch_cov_factor_layout(ctx, cargs[0], ds->d_W, q, s->n, s->Npad, s->ld, s->nCB, s->d_L);
@@ -185,8 +193,33 @@ extern "C" int iak3d_nll_grad(iak3d_ds* ds, int32_t npar, const iak3d_pars* pars
   if (status != 0) return status;
   if (lndetA) *lndetA = lnd;
   if (WiAW) memcpy(WiAW, G.data(), (size_t)q * q * sizeof(double));
+  const auto t2 = tnow();
+  // ---- explicit inverse (blocked, symmetric after the mirror); its two big buffers are kept with the dataset ----
+  {
+    const int64_t rowsU0 = round_up(s->Npad, TM);
+    const size_t bytes = (size_t)ubuf_doubles(rowsU0, s->Npad) * sizeof(double);
+    if (ds->grad_bytes != bytes) {
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      cudaFree(ds->d_gradU); cudaFree(ds->d_gradiC); ds->d_gradU = ds->d_gradiC = nullptr; ds->grad_bytes = 0;
+      CUDA_TRY(ctx, cudaMalloc(&ds->d_gradU, bytes));
+      CUDA_TRY(ctx, cudaMalloc(&ds->d_gradiC, bytes));
+      ds->grad_bytes = bytes;
+    }
+  }
+  double* iCb = nullptr; int64_t rowsU = 0;
+  rc = iak_inverse_blocked(ctx, s, &iCb, &rowsU, ds->d_gradU, ds->d_gradiC);
+  if (rc != 0) return rc;
+  const auto t3 = tnow();
+  // ---- A^-1 W = iC W: one pass over the inverse instead of a block back-substitution ----
   std::vector<double> iAW((size_t)n * q);
-  rc = iak_backsolve_to_host(ctx, s, iAW.data(), nullptr);
+  double* d_iAW = nullptr;
+  if (cudaMalloc(&d_iAW, (size_t)n * q * 8) != cudaSuccess) { ctx->err = "nll_grad: allocation failed"; cudaGetLastError(); return IAK3D_ERR_CUDA; }
+  rc = launch_panel_product(ctx, iCb, rowsU / UR, n, ds->d_W, q, d_iAW);
+  if (rc == 0) {
+    cudaMemcpyAsync(iAW.data(), d_iAW, (size_t)n * q * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "nll_grad: product failed"; rc = IAK3D_ERR_CUDA; }
+  }
+  cudaFree(d_iAW);
   if (rc != 0) return rc;
   // ---- p x p algebra on the host: betahat, cxdhat, Z = (A^-1 X) chol(M)^-T, u = A^-1 z - (A^-1 X) betahat ----
   std::vector<double> M((size_t)p * p), Lm((size_t)p * p), b((size_t)p), beta((size_t)p);
@@ -217,10 +250,8 @@ extern "C" int iak3d_nll_grad(iak3d_ds* ds, int32_t npar, const iak3d_pars* pars
       Zt[(size_t)a * n + i] = zv / Lm[(size_t)a * p + a];
     }
   }
-  // ---- explicit inverse (lower triangle of the blocked buffer is what the pass reads) ----
-  double* iCb = nullptr; int64_t rowsU = 0;
-  rc = iak_inverse_blocked(ctx, s, &iCb, &rowsU);
-  if (rc != 0) return rc;
+  const auto t4 = tnow();
+  const auto t5 = t4;
   // ---- distinct tables and the per-set coefficients ----
   GradArgs g;
   memset(&g, 0, sizeof(g));
@@ -254,7 +285,7 @@ extern "C" int iak3d_nll_grad(iak3d_ds* ds, int32_t npar, const iak3d_pars* pars
     g.set[g.nset++] = S;
     if (k > 0) setpar.push_back(k - 1);
   }
-  if (overflow) { cudaFree(iCb); ctx->err = "nll_grad: more distinct tables than the pass holds"; return IAK3D_ERR_ARG; }
+  if (overflow) { ctx->err = "nll_grad: more distinct tables than the pass holds"; return IAK3D_ERR_ARG; }
   double *dZt = nullptr, *du = nullptr, *dpart = nullptr;
   const int nRB = (int)((n + TM - 1) / TM), nCB = (int)((n + TN - 1) / TN);
   int64_t tiles = 0;
@@ -279,6 +310,9 @@ extern "C" int iak3d_nll_grad(iak3d_ds* ds, int32_t npar, const iak3d_pars* pars
       gsum[setpar[(size_t)sidx - 1]] = t;
     }
   } while (0);
-  cudaFree(dZt); cudaFree(du); cudaFree(dpart); cudaFree(iCb);
+  const auto t6 = tnow();
+  cudaFree(dZt); cudaFree(du); cudaFree(dpart);
+  if (prof) fprintf(stderr, "[gradprof] n=%lld: tables %.2f, build+factorise %.2f, inverse %.2f, iC W + host algebra %.2f, pass %.2f, free %.2f ms\n",
+                    (long long)n, ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t5, t6), ms(t6, tnow()));
   return rc;
 }

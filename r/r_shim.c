@@ -268,6 +268,24 @@ SEXP iak3dR_predict_terms(SEXP fp, SEXP xyMap, SEXP dIMap, SEXP XMap, SEXP spl, 
   return out;
 }
 
+/* analytic gradient of the profiled objective: pmat = IAK3D_PV_LEN x (npar + 1) candidates (column 1 = the point itself),
+ * delta (npar).  list(status, lndetA, WiAW (q x q), gsum (npar)); d nll / d theta = gsum / 2 */
+SEXP iak3dR_nll_grad(SEXP dsp, SEXP pmat, SEXP delta, SEXP useReml) {
+  iak3d_ds* ds = (iak3d_ds*)R_ExternalPtrAddr(dsp);
+  const int count = ncols(pmat), npar = count - 1;
+  int32_t q = 0; iak3d_dataset_info(ds, NULL, NULL, NULL, &q);
+  if (nrows(pmat) != IAK3D_PV_LEN || LENGTH(delta) != npar) error("iak3d: nll_grad needs %d x (npar + 1) parameters and npar steps", IAK3D_PV_LEN);
+  iak3d_pars* P = (iak3d_pars*)R_alloc(count, sizeof(iak3d_pars));
+  for (int i = 0; i < count; i++) pars_from_ptr(REAL(pmat) + IAK3D_PV_LEN * (size_t)i, &P[i]);
+  SEXP out = PROTECT(allocVector(VECSXP, 4));
+  SET_VECTOR_ELT(out, 1, allocVector(REALSXP, 1)); SET_VECTOR_ELT(out, 2, allocMatrix(REALSXP, q, q)); SET_VECTOR_ELT(out, 3, allocVector(REALSXP, npar));
+  int st = iak3d_nll_grad(ds, npar, P, REAL(delta), asLogical(useReml), REAL(VECTOR_ELT(out, 1)), REAL(VECTOR_ELT(out, 2)), REAL(VECTOR_ELT(out, 3)));
+  if (st < 0) error("iak3d_nll_grad: %s", iak3d_last_error(g_ctx));
+  SET_VECTOR_ELT(out, 0, ScalarInteger(st));
+  UNPROTECT(1);
+  return out;
+}
+
 /* gradHessIAK3D (nrUpdatesIAK3D.R:118-216): list(status, nll, grad, hess, fim, betahat, vbetahat) */
 SEXP iak3dR_gradhess(SEXP dsp, SEXP pv, SEXP lnvPars) {
   iak3d_ds* ds = (iak3d_ds*)R_ExternalPtrAddr(dsp);
@@ -296,6 +314,7 @@ static const R_CallMethodDef call_methods[] = {
   {"iak3dR_cov_diag", (DL_FUNC)&iak3dR_cov_diag, 2},     {"iak3dR_cov_cross_spl", (DL_FUNC)&iak3dR_cov_cross_spl, 5},
   {"iak3dR_fit_res", (DL_FUNC)&iak3dR_fit_res, 5},       {"iak3dR_fit_option", (DL_FUNC)&iak3dR_fit_option, 3},
   {"iak3dR_predict_terms", (DL_FUNC)&iak3dR_predict_terms, 6}, {"iak3dR_gradhess", (DL_FUNC)&iak3dR_gradhess, 3},
+  {"iak3dR_nll_grad", (DL_FUNC)&iak3dR_nll_grad, 4},
   {NULL, NULL, 0}};
 
 void R_init_iak3dR(DllInfo* dll) {
