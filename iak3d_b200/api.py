@@ -953,7 +953,7 @@ class KeptFit:
 
     def stage(self, xMap, dIMap, XMap):
         xMap = f64(np.asarray(xMap, float).reshape(-1, 2)); dIMap = f64(np.asarray(dIMap, float).reshape(-1, 2))
-        XMap = f64(np.asarray(XMap, float).reshape(xMap.shape[0], -1))
+        XMap = f64(np.asarray(XMap, float).reshape(xMap.shape[0], self.p))
         if max(self.sm.sdfdTypes) > 0:       # spline sd functions: basis on the map supports (setCApproxIAK3D2)
             spl = _sdfd_spline_bases(dIMap, self.sm.sdfdTypes, self.sm.sdfdKnots)
             self.ctx.check(self.ctx.lib.iak3d_predict_stage_spl(self.h, xMap.shape[0], dptr(xMap), dptr(dIMap), dptr(XMap), spl_ptrs(spl)))
