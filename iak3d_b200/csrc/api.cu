@@ -904,7 +904,7 @@ extern "C" int iak3d_nll_terms_batch_enqueue(iak3d_ctx* ctx, int32_t count, iak3
       CUDA_TRY(ctx, cudaMalloc(&ctx->d_prof, (size_t)b->ntasks * 8 * sizeof(long long)));
       ctx->prof_cap = b->ntasks;
     }
-    ctx->prof_ntasks = b->ntasks;
+    ctx->prof_ntasks = b->ntasks; ctx->d_prof_tasks = b->d_tasks;
     for (int i = 0; i < count; i++) probs[i].prof = ctx->d_prof;
   }
 
@@ -1154,7 +1154,7 @@ extern "C" int iak3d_last_task_profile(iak3d_ctx* ctx, int64_t* out, int64_t cap
   std::vector<int4> tasks((size_t)nt);
   std::vector<long long> tm((size_t)nt * 8);
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  CUDA_TRY(ctx, cudaMemcpy(tasks.data(), ctx->batch->d_tasks, (size_t)nt * sizeof(int4), cudaMemcpyDeviceToHost));
+  CUDA_TRY(ctx, cudaMemcpy(tasks.data(), ctx->d_prof_tasks, (size_t)nt * sizeof(int4), cudaMemcpyDeviceToHost));
   CUDA_TRY(ctx, cudaMemcpy(tm.data(), ctx->d_prof, (size_t)nt * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
   for (int64_t t = 0; t < nt; t++) {
     out[t * 11 + 0] = tasks[(size_t)t].x; out[t * 11 + 1] = tasks[(size_t)t].y; out[t * 11 + 2] = tasks[(size_t)t].z;

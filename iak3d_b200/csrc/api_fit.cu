@@ -30,7 +30,14 @@ int iak_cross_depth_tables(iak3d_ctx* ctx, const iak3d_ds* ds2, const EvalPlan& 
                            int64_t nd1, const std::vector<double>* spl1U, double* d_T, double* d_s, const double** Tout);
 void iak_spl_unique_rows(const double* Xrow, int64_t n1, int ncol, const std::vector<int32_t>& did1, int64_t nd1, std::vector<double>& out);
 
-constexpr int64_t PRED_CHUNK = 16384;   // prediction rows per panel (128 row blocks)
+// Prediction rows per panel: two 128-row blocks per persistent CTA (37888 rows on a B200).  Each row block is a serial
+// chain of column tasks (X_rj needs X_r,0..j-1), so the panel should hold more chains than CTAs; a taller panel also
+// amortises the panel build and the end-of-panel tail.  Bounded so that the panel stays below ~24 GB for large fits.
+static int64_t fit_chunk_rows(const iak3d_ctx* ctx, int64_t Npad) {
+  int64_t rows = (int64_t)2 * ctx->sm_count * TM;
+  while (rows > 16384 && (double)rows * (double)Npad * 8.0 > 24e9) rows -= (int64_t)ctx->sm_count * TM / 2;
+  return rows < 16384 ? 16384 : rows;
+}
 
 struct iak3d_fit {
   iak3d_ds* ds = nullptr;
@@ -298,6 +305,7 @@ extern "C" int iak3d_predict_stage_spl(iak3d_fit* f, int64_t m, const double* xy
   CUDA_TRY(ctx, cudaMemcpyAsync(f->d_dIU1, dIU1.data(), dIU1.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(f->d_did1, did1.data(), (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
   // coordinates: one (rows x 2) column-major block per chunk
+  const int64_t PRED_CHUNK = fit_chunk_rows(ctx, f->slot->Npad);
   for (int64_t r0 = 0; r0 < m; r0 += PRED_CHUNK) {
     const int64_t rows = std::min(PRED_CHUNK, m - r0);
     CUDA_TRY(ctx, cudaMemcpyAsync(f->d_xy + 2 * r0, xyMap + r0, (size_t)rows * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -371,6 +379,7 @@ extern "C" int iak3d_predict_enqueue(iak3d_fit* f) {
   a.cx0 = px.cx0; a.cx1 = px.cx1; a.kd1 = px.kd1; a.cxd0 = px.cxd0; a.cxd1 = px.cxd1; a.cme = 0.0;
   a.xid_c = ds->d_xid; a.did_c = ds->d_did; a.nc = ds->n; a.ndIU_r = nd1;
   CUDA_TRY(ctx, cudaMemsetAsync(f->d_status, 0, 2 * sizeof(int32_t), ctx->stream));
+  const int64_t PRED_CHUNK = fit_chunk_rows(ctx, s->Npad);
   for (int64_t r0 = 0; r0 < m; r0 += PRED_CHUNK) {
     const int64_t rows = std::min(PRED_CHUNK, m - r0);
     const int64_t rowsP = round_up(rows, TM);
@@ -390,6 +399,16 @@ extern "C" int iak3d_predict_enqueue(iak3d_fit* f) {
     pd.nCB = s->nCB; pd.nRB = (int32_t)(rowsP / TM); pd.mode = 1; pd.epoch = ++f->pepoch;
     pd.w0 = (int32_t)s->Npad; pd.q = f->q; pd.G = f->d_G; pd.ldG = rowsP; pd.logsum = nullptr; pd.status = f->d_status;
     pd.prof = nullptr;
+    if (getenv("IAK3D_PROF") != nullptr) {      // diagnostics: per-task timestamps of the last panel (iak3d_last_task_profile)
+      if (f->ntasks > ctx->prof_cap) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_prof); ctx->d_prof = nullptr;
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_prof, (size_t)f->ntasks * 8 * sizeof(long long)));
+        ctx->prof_cap = f->ntasks;
+      }
+      ctx->prof_ntasks = f->ntasks; ctx->d_prof_tasks = f->d_tasks;
+      pd.prof = ctx->d_prof;
+    }
     CUDA_TRY(ctx, cudaMemcpyAsync(f->d_prob, &pd, sizeof(pd), cudaMemcpyHostToDevice, ctx->stream));
     rc = launch_tile_tasks(ctx, f->d_prob, f->d_tasks, f->ntasks, f->d_ticket);
     if (rc != 0) return rc;

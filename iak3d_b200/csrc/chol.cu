@@ -453,29 +453,63 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
             }
           }
         } else {
-          // kriging rows: G(:,0..q-1) += X Yw', G(:,q) += rowsum(X^2); Yw = rows w0.. of the factor buffer
+          // kriging rows: G(:,0..q-1) += X Yw', G(:,q) += rowsum(X^2); Yw = rows w0.. of the factor buffer.
+          // On the tensor pipe: each warp owns 16 rows of the tile (two m8 tiles), the W rows are the B operand
+          // (element (w, c) at Ws[c*UL + w], the K-loop's fragment layout), 16 W rows per pass.
           for (int idx = tid; idx < q * TN; idx += NCW * 32) {
             const int w = idx % q, c = idx / q;
-            Ws[c * 64 + w] = __ldcg(L + uidx((int64_t)pb->w0 + w, (int64_t)j * TN + c, nRUL));
+            Ws[c * UL + w] = __ldcg(L + uidx((int64_t)pb->w0 + w, (int64_t)j * TN + c, nRUL));
           }
           consumer_bar();
-          if (tid < TM) {
-            double* G = pb->G + R0 + tid;
-            double ssq = 0.0;
-            for (int c = 0; c < TN; c++) { const double xv = At[AT_IDX(tid, c)]; ssq += xv * xv; }
-            G[(int64_t)q * pb->ldG] = (j == 0 ? 0.0 : __ldcg(G + (int64_t)q * pb->ldG)) + ssq;
+          {
+            const int row0 = warp * 16 + rq;                       // + 8*mi
+            double* const Gr = pb->G + R0 + row0;
+            const int64_t ldG = pb->ldG;
+            double ssq[2] = {0.0, 0.0};
             for (int wb = 0; wb < q; wb += 16) {
-              double g[16];
+              double g[2][2][2], gold[2][2][2];
 #pragma unroll
-              for (int w = 0; w < 16; w++) g[w] = 0.0;
-              for (int c = 0; c < TN; c++) {
-                const double xv = At[AT_IDX(tid, c)];
+              for (int mi = 0; mi < 2; mi++)
 #pragma unroll
-                for (int w = 0; w < 16; w++) g[w] += xv * Ws[c * 64 + ((wb + w) & 63)];
+                for (int ni = 0; ni < 2; ni++)
+#pragma unroll
+                  for (int e = 0; e < 2; e++) {
+                    g[mi][ni][e] = 0.0;
+                    const int col = wb + ni * 8 + kq * 2 + e;
+                    gold[mi][ni][e] = (j == 0 || col >= q) ? 0.0 : __ldcg(Gr + mi * 8 + (int64_t)col * ldG);
+                  }
+#pragma unroll 4
+              for (int k4 = 0; k4 < TN / 4; k4++) {
+                const int k = k4 * 4 + kq;
+                const double a0 = At[AT_IDX(row0, k)], a1 = At[AT_IDX(row0 + 8, k)];
+                const double b0 = Ws[k * UL + wb + rq], b1 = Ws[k * UL + wb + 8 + rq];
+                if (wb == 0) { ssq[0] = fma(a0, a0, ssq[0]); ssq[1] = fma(a1, a1, ssq[1]); }
+                dmma(g[0][0][0], g[0][0][1], a0, b0);
+                dmma(g[0][1][0], g[0][1][1], a0, b1);
+                dmma(g[1][0][0], g[1][0][1], a1, b0);
+                dmma(g[1][1][0], g[1][1][1], a1, b1);
               }
 #pragma unroll
-              for (int w = 0; w < 16; w++)
-                if (wb + w < q) G[(int64_t)(wb + w) * pb->ldG] = (j == 0 ? 0.0 : __ldcg(G + (int64_t)(wb + w) * pb->ldG)) + g[w];
+              for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 2; ni++)
+#pragma unroll
+                  for (int e = 0; e < 2; e++) {
+                    const int col = wb + ni * 8 + kq * 2 + e;
+                    if (col < q) Gr[mi * 8 + (int64_t)col * ldG] = gold[mi][ni][e] + g[mi][ni][e];
+                  }
+            }
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++) {                       // the four k-lanes of a row: fixed-order butterfly
+              ssq[mi] += __shfl_xor_sync(0xffffffffu, ssq[mi], 1);
+              ssq[mi] += __shfl_xor_sync(0xffffffffu, ssq[mi], 2);
+            }
+            if (kq == 0) {
+#pragma unroll
+              for (int mi = 0; mi < 2; mi++) {
+                double* Gq = Gr + mi * 8 + (int64_t)q * ldG;
+                *Gq = (j == 0 ? 0.0 : __ldcg(Gq)) + ssq[mi];
+              }
             }
           }
         }
@@ -489,7 +523,7 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
       if (prof && tid == 0) {
         prof[0] = tp0; prof[1] = tp1; prof[2] = tp2; prof[3] = tp3; prof[4] = tp4; prof[5] = (long long)gtime();
         prof[6] = (nchunks > kstart) ? s_tdep : tp0;
-        prof[7] = (kwait << 1) | (is_diag ? 1 : 0);     // cycles warp 0 spent waiting for operands in the K-loop
+        prof[7] = ((long long)blockIdx.x << 48) | (kwait << 1) | (is_diag ? 1 : 0);   // CTA | cycles warp 0 waited for operands in the K-loop | diag
       }
     }
     it = it0 + (nchunks - kstart);

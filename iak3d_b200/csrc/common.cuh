@@ -51,7 +51,7 @@ struct iak3d_ctx {
   double last_chol_flops = 0, last_cov_bytes = 0;
   bool stage_events_valid = false;
   void* d_fbjobs = nullptr; size_t fbjobs_cap = 0;     // device copy of the covariance-build jobs of one launch
-  long long* d_prof = nullptr; int64_t prof_cap = 0; int32_t prof_ntasks = 0;   // IAK3D_PROF=1 diagnostics
+  long long* d_prof = nullptr; int64_t prof_cap = 0; int32_t prof_ntasks = 0; const int4* d_prof_tasks = nullptr;   // IAK3D_PROF=1 diagnostics
 };
 
 constexpr int NTAB_BUF = 4;   // depth-table buffers of a slot: <= 3 tables in use + the stationary source of the approximation

@@ -50,5 +50,5 @@ rate = (T[m, 1] - T[m, 0]) / nch[m]
 print("K-loop us/chunk: min %.3f  p10 %.3f  median %.3f  mean %.3f  p90 %.3f" % (rate.min(), np.percentile(rate, 10), np.median(rate), rate.mean(), np.percentile(rate, 90)))
 busy = (T[:, 5] - T[:, 0]).sum(); span = T[:, 5].max()
 print("sum of task durations / (span x 148 SMs) = %.3f ; ideal MMA time for all chunks / (span x 148) = %.3f" % (busy / (span * 148), nch.sum() * 2.084 / (span * 148)))
-kw = (buf[:, 10] >> 1) / 1965.0   # us at 1965 MHz
+kw = ((buf[:, 10] >> 1) & ((1 << 47) - 1)) / 1965.0   # us at 1965 MHz
 print("K-loop operand-wait of warp 0: mean %.1f us per task = %.1f%% of the K-loop; per chunk %.3f us" % (kw[m].mean(), 100 * kw[m].sum() / (T[m, 1] - T[m, 0]).sum(), (kw[m] / nch[m]).mean()))

@@ -71,10 +71,11 @@ def test_kriging_is_exact_at_data_supports_without_measurement_error(ctx):
 
 
 def test_predict_chunking_and_nan_rows(ctx):
-    """More supports than one panel (16384) and NaN design rows (predictIAK3D.R:160-163)."""
+    """More supports than two panels (2 x 148 row blocks of 128 = 37888 rows each on a B200; the third reuses the first
+    panel's buffer while the second is being solved) and NaN design rows (predictIAK3D.R:160-163)."""
     ds = synth.make_dataset(300, 5)
     got, want, modelx, types, cmeOpt = _fit_both(ctx, ds, "edgeroi", False, 0.5)
-    xMap = synth.make_grid(135)[:18000]
+    xMap = synth.make_grid(300)[:80000]
     dIMap = synth.GSM_INTERVALS[2:3]
 
     def Xfn(i, idx):
@@ -82,7 +83,7 @@ def test_predict_chunking_and_nan_rows(ctx):
         X[idx % 1000 == 7, 2] = np.nan
         return X
     pg = iak.predictIAK3D(xMap, dIMap, Xfn, got)
-    sub = np.r_[0:50, 16350:16450, 17950:18000]
+    sub = np.r_[0:50, 16350:16450, 37850:37950, 75700:75850, 79950:80000]
     zw, vw, _, _ = orc.predictIAK3D(xMap[sub], dIMap, lambda i, idx: Xfn(i, sub[idx]), want, modelx, types, cmeOpt)
     okw = ~np.isnan(zw[0])
     assert np.array_equal(np.isnan(pg["zMap"][0, sub]), ~okw)
