@@ -13,6 +13,10 @@ $(OUT)/libiak3d.so: $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart_static -lpthread -ldl -lrt
 
 # closed forms round like the reference's operation order: no FMA contraction in the table / assembly kernels
+$(OUT):
+	mkdir -p $(OUT)
+$(OBJS): | $(OUT)
+
 $(OUT)/tables.o: $(CSRC)/tables.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) -fmad=false -c $< -o $@
 $(OUT)/covbuild.o: $(CSRC)/covbuild.cu $(HDRS)
