@@ -81,6 +81,16 @@ _PROTOS = {
     "iak3d_timer_stop": (C.c_int, [_vp, _dp]),
     "iak3d_flush_l2": (C.c_int, [_vp]),
     "iak3d_fp64_peak": (C.c_int, [_vp, _i32, _dp]),
+    "iak3d_mat_create": (C.c_int, [_vp, _i64, _i64, C.POINTER(_vp)]),
+    "iak3d_mat_destroy": (C.c_int, [_vp]),
+    "iak3d_mat_shape": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
+    "iak3d_mat_set": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _dp, _i64]),
+    "iak3d_mat_get": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _dp, _i64]),
+    "iak3d_mat_copy": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _i32, C.c_double, C.c_double]),
+    "iak3d_mat_gemm_nt": (C.c_int, [_vp, C.c_double, _vp, _vp, _i32]),
+    "iak3d_mat_spd_inverse": (C.c_int, [_vp, _ip]),
+    "iak3d_mat_cov_build": (C.c_int, [_vp, C.POINTER(Pars), _vp]),
+    "iak3d_mat_coldot": (C.c_int, [_vp, _vp, _dp]),
     "iak3d_last_stage_ms": (C.c_int, [_vp, _dp, _dp, _dp]),
     "iak3d_last_task_profile": (C.c_int, [_vp, C.POINTER(_i64), _i64, C.POINTER(_i64)]),
 }

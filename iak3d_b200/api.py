@@ -836,6 +836,7 @@ def setupIAK3D_CL(xData, dIData, zData, XData, compLikMats, ctx=None, rank=0, wo
     cl = dict(compLikMats)
     cl["units"] = out
     cl["n_units_total"] = len(units)
+    cl["xData"], cl["dIData"] = xData, dIData       # lmmFit$xData, lmmFit$dIData of the block predictors
     return cl
 
 
@@ -1127,13 +1128,117 @@ def predMatsIAK3D_CL_ByBlock(z_muhat, XData, xMap, dIMap, lmmFit):
     return dict(diagCkk=Ckk, diagCkhiCChk=q / w, CkhiCX=cx / w[:, None], CkhiCz_muhat=cz / w)
 
 
+def predMatsIAK3D_CLEV_ByBlock(z_muhat, XData, xMap, dIMap, lmmFit):
+    """compositeLikIAK3D.R:609-798 (compLikOptn 2 and 3, Eidsvik et al.): the map supports of block k are predicted
+    jointly from the pairwise conditionals with every adjacent block.  All matrices -- the joined-support covariance
+    C0klAll (:671), its sub-blocks, the pair inverses, A0, Bk0, J0 -- stay on the GPU as :class:`DeviceMat`; products run
+    on the tile engine (DMMA), `solve` / `chol2inv(chol(.))` are the factorisation + explicit inverse.  The
+    `loadFromFit` branch (:688-707) reads the same matrices from the fit object and is folded into the rebuild branch.
+    -> dict(zk, vk); X betahat is added by the caller (predictIAK3D.R:231-234)."""
+    from .devmat import DeviceMat, cov_mat
+    cl = lmmFit["compLikMats"]
+    blocks = cl["listBlocks"]
+    pairs = np.asarray(cl["subsetPairsAdj"]).reshape(-1, 2)
+    optn = cl["compLikOptn"]
+    xData = np.asarray(lmmFit.get("xData", cl.get("xData")), float); dIData = np.asarray(lmmFit.get("dIData", cl.get("dIData")), float)
+    xMap = np.asarray(xMap, float).reshape(-1, 2); dIMap = np.asarray(dIMap, float).reshape(-1, 2)
+    nx = xMap.shape[0]
+    types = (lmmFit["sdfdType_cd1"], lmmFit["sdfdType_cxd0"], lmmFit["sdfdType_cxd1"])
+    P = make_pars(lmmFit["parsBTfmd"], lmmFit["modelx"], *types, lmmFit["cmeOpt"])
+    ctx = cl["units"][0]["setup"].ctx if cl.get("units") else default_context()
+    z_muhat = np.asarray(z_muhat, float).reshape(-1)
+    blockMap = getBlocksFromLocations(xMap, cl)
+    zk = np.full(nx, np.nan); vk = np.full(nx, np.nan)
+    mm = DeviceMat.matmul_nt
+    for k in range(int(blockMap.max()) + 1):
+        pts = np.nonzero(blockMap == k)[0]
+        m = pts.size
+        if m == 0:
+            continue
+        adj = [int(b) for a, b in pairs if a == k] + [int(a) for a, b in pairs if b == k]   # getAdjacentBlocks, :817-827
+        if not adj:
+            raise ValueError("Error - every block must have a neighbour - check this!")
+        iDatak = np.asarray(blocks[k]); nk = iDatak.size
+        datL = [np.asarray(blocks[l]) for l in adj]
+        i2L, cnt = [], m + nk
+        for d in datL:
+            i2L.append((cnt, d.size)); cnt += d.size
+        rows = np.concatenate([iDatak] + datL)
+        sm = SetupMats(np.vstack([xMap[pts], xData[rows]]), np.vstack([dIMap[pts], dIData[rows]]), ctx=ctx, sdfdType_cd1=types[0],
+                       sdfdType_cxd0=types[1], sdfdType_cxd1=types[2], sdfdKnots=lmmFit.get("sdfdKnots"))      # :668
+        Call = cov_mat(sm, P)                                                                                # :671
+        sm.close()
+        if Call is None:
+            raise ValueError("predMatsIAK3D_CLEV_ByBlock: invalid covariance parameters")
+        C0k = Call.sub(0, 0, m + nk, m + nk)                           # :680
+        C00 = Call.sub(0, 0, m, m)
+        A0 = DeviceMat(m, m, ctx); b0 = DeviceMat(m, 1, ctx); Bk0 = DeviceMat(m, m + nk, ctx)
+        QL = []
+        for d, (s2, n2) in zip(datL, i2L):                             # :692-745
+            kl = [(m, nk), (s2, n2)]
+            iS = Call.gather_blocks(kl, kl).spd_inverse()              # solve(Ckl_klThis, .), :717
+            C0kl = Call.gather_blocks([(0, m)], kl)                    # C0klAll[i0, c(i1,i2)]
+            Tt = mm(C0kl, iS)                                          # t(iCkl_kl_Ckl_0This)
+            iS.close()
+            IF = DeviceMat(m, m, ctx).assign(C00).gemm_nt(C0kl, Tt, alpha=-1.0, accumulate=True)   # :720
+            C0kl.close()
+            iIF = IF.symmetrised().spd_inverse()                       # :722-725
+            IF.close()
+            T = Tt.t(); Tt.close()
+            Q12 = mm(iIF, T, alpha=-1.0)                               # :726
+            T.close()
+            QL.append(Q12.sub(0, nk, m, n2))                           # :730
+            zrow = DeviceMat.from_host(z_muhat[np.concatenate([iDatak, d])].reshape(1, -1), ctx)
+            A0.assign(iIF, beta=1.0)                                   # :737-739
+            b0.gemm_nt(Q12, zrow, alpha=-1.0, accumulate=True)
+            Bk0.assign(iIF, beta=1.0)
+            Bk0.assign(Q12, dc0=m, nr=m, nc=nk, beta=1.0)
+            for M in (iIF, Q12, zrow):
+                M.close()
+        if optn == 3:                                                  # :748-770: non-adjacent pairs taken as independent
+            nnon = float(len(blocks) - len(adj) - 1)
+            iCkk = Call.sub(m, m, nk, nk).spd_inverse()
+            C0_k = Call.sub(0, m, m, nk)
+            C0kiC = mm(C0_k, iCkk)
+            IF = DeviceMat(m, m, ctx).assign(C00).gemm_nt(C0kiC, C0_k, alpha=-1.0, accumulate=True)
+            iIF = IF.symmetrised().spd_inverse()
+            C0kiCt = C0kiC.t()
+            iIFC = mm(iIF, C0kiCt)
+            zrow = DeviceMat.from_host(z_muhat[iDatak].reshape(1, -1), ctx)
+            A0.assign(iIF, alpha=nnon, beta=1.0)
+            b0.gemm_nt(iIFC, zrow, alpha=nnon, accumulate=True)
+            Bk0.assign(iIF, alpha=nnon, beta=1.0)
+            Bk0.assign(iIFC, dc0=m, alpha=-nnon, beta=1.0)
+            for M in (iCkk, C0_k, C0kiC, IF, iIF, C0kiCt, iIFC, zrow):
+                M.close()
+        BC = mm(Bk0, C0k)                                              # C0k_0k is symmetric: Bk0 %*% C0k_0k
+        J0 = mm(BC, Bk0)                                               # :772
+        BC.close()
+        for a, (s2a, n2a) in enumerate(i2L):                           # :773-781
+            Cl = Call.sub(s2a, 0, n2a, m + nk)                         # t(C0k_lList[[a]]) by symmetry of C0klAll
+            BCl = mm(Bk0, Cl); Cl.close()
+            J0.gemm_nt(BCl, QL[a], alpha=2.0, accumulate=True); BCl.close()
+            for b_, (s2b, n2b) in enumerate(i2L):
+                Cba = Call.sub(s2b, s2a, n2b, n2a)                     # t(C0klAll[i2a, i2b])
+                QC = mm(QL[a], Cba); Cba.close()
+                J0.gemm_nt(QC, QL[b_], accumulate=True); QC.close()
+        iA0 = A0.symmetrised().spd_inverse()                           # :784-788
+        J0s = J0.symmetrised()
+        b0t = b0.t()
+        zkd = mm(iA0, b0t)                                             # :790
+        zk[pts] = zkd.to_host().reshape(-1)
+        JA = mm(J0s, iA0)
+        vk[pts] = iA0.coldot(JA)                                       # :795
+        for M in [Call, C0k, C00, A0, b0, Bk0, J0, iA0, J0s, b0t, zkd, JA] + QL:
+            M.close()
+    return dict(zk=zk, vk=vk)
+
+
 def predictIAK3D_CL(xMap, dIMap, XMap_fn, lmmFit, cells=None):
     """predictIAK3D (predictIAK3D.R:5-287) when the model was fitted by composite likelihood with compLikOptn 1 or 4
-    (:211-226 -> predMatsIAK3D_CL_ByBlock).  `lmmFit` is the rtnAll dict of :func:`nllIAK3D_CL`.  The Eidsvik options
-    (2, 3 -> predMatsIAK3D_CLEV_ByBlock) are not built."""
+    (:211-226 -> predMatsIAK3D_CL_ByBlock) or with the Eidsvik options 2 or 3 (-> predMatsIAK3D_CLEV_ByBlock, no
+    fixed-effect term in the variance, :231-234).  `lmmFit` is the rtnAll dict of :func:`nllIAK3D_CL`."""
     optn = lmmFit["compLikMats"]["compLikOptn"]
-    if optn in (2, 3):
-        raise NotImplementedError("predMatsIAK3D_CLEV_ByBlock (compLikOptn 2, 3) is not built")
     xMap = np.asarray(xMap, float).reshape(len(xMap), -1)
     dIMap = np.round(np.asarray(dIMap, float).reshape(-1, 2), 2)
     nd, nx = dIMap.shape[0], xMap.shape[0]
@@ -1147,6 +1252,11 @@ def predictIAK3D_CL(xMap, dIMap, XMap_fn, lmmFit, cells=None):
         if not ok.any():
             continue
         sel = idx_all[ok]
+        if optn in (2, 3):
+            t = predMatsIAK3D_CLEV_ByBlock(z_muhat, XData, xMap[sel], np.repeat(dIMap[i:i + 1], sel.size, axis=0), lmmFit)
+            zMap[i, sel] = (XM[ok] @ betahat).reshape(-1) + t["zk"]
+            vMap[i, sel] = t["vk"]
+            continue
         t = predMatsIAK3D_CL_ByBlock(z_muhat, XData, xMap[sel], np.repeat(dIMap[i:i + 1], sel.size, axis=0), lmmFit)
         zMap[i, sel] = (XM[ok] @ betahat).reshape(-1) + t["CkhiCz_muhat"]
         d = XM[ok] - t["CkhiCX"]

@@ -148,6 +148,12 @@ __global__ void mirror_lower_kernel(double* __restrict__ M, int64_t nRU, int64_t
 
 }  // namespace
 
+// mat.cu: the plain product on caller-owned blocked matrices
+int iak_gemm_nt(iak3d_ctx* ctx, const double* A, int64_t rowsA, const double* B, int64_t rowsB, double* Out, int64_t rowsOut,
+                int64_t colsOut, int64_t K, double alpha, int use_cin, int32_t* d_status) {
+  return gemm_nt(ctx, A, rowsA, B, rowsB, Out, rowsOut, colsOut, K, alpha, use_cin, d_status, 0);
+}
+
 // out (n x q, column-major) = M W for the leading n x n part of a blocked (full, symmetric) matrix.  CTA = 128 rows x a
 // chunk of PP_CH columns (the chunk of W is staged in shared memory and read as a broadcast); the chunks' partial
 // sums are added in chunk order by a second kernel: deterministic.

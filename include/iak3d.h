@@ -203,6 +203,32 @@ IAK3D_API int iak3d_predict_fetch_CkhiCX(iak3d_fit* fit, double* CkhiCX /* m x p
 IAK3D_API int iak3d_gradhess(iak3d_ds* ds, const iak3d_pars* pars, int32_t ncomp, const double* lnvPars,
                    double* nll, double* grad, double* hess, double* fim, double* betahat, double* vbetahat);
 
+/* ---- device-resident dense matrices ------------------------------------------------------------
+ * The Eidsvik composite-likelihood block predictor predMatsIAK3D_CLEV_ByBlock (compositeLikIAK3D.R:609-798) is dense
+ * algebra on matrices as large as (map supports + block data): `%*%` (:717-779), chol2inv(chol(.)) (:725, :755, :763,
+ * :788), sub-block indexing C0klAll[c(i1,i2), i0] (:680-731), 0.5 * (A + t(A)) (:722, :759, :784-785) and
+ * colSums(A * B) (:795).  These entry points are those operations on matrices that stay on the GPU; the joined-support
+ * covariance C0klAll (:671) is built there by iak3d_mat_cov_build.  Shapes are logical (unpadded); sub-blocks are
+ * (row0, col0, nrows, ncols), zero-based.  All calls are synchronous on the context's stream. */
+typedef struct iak3d_mat iak3d_mat;
+IAK3D_API int iak3d_mat_create(iak3d_ctx* ctx, int64_t rows, int64_t cols, iak3d_mat** out);      /* zero-filled */
+IAK3D_API int iak3d_mat_destroy(iak3d_mat* M);
+IAK3D_API int iak3d_mat_shape(const iak3d_mat* M, int64_t* rows, int64_t* cols);
+/* host column-major (leading dimension ld) -> sub-block, and back */
+IAK3D_API int iak3d_mat_set(iak3d_mat* M, int64_t r0, int64_t c0, int64_t nr, int64_t nc, const double* src, int64_t ld);
+IAK3D_API int iak3d_mat_get(const iak3d_mat* M, int64_t r0, int64_t c0, int64_t nr, int64_t nc, double* dst, int64_t ld);
+/* D[dr0+i, dc0+j] = beta * D[dr0+i, dc0+j] + alpha * S[sr0+i, sc0+j]  (transpose != 0: S[sr0+j, sc0+i]); D != S */
+IAK3D_API int iak3d_mat_copy(iak3d_mat* D, int64_t dr0, int64_t dc0, const iak3d_mat* S, int64_t sr0, int64_t sc0,
+                             int64_t nr, int64_t nc, int32_t transpose, double alpha, double beta);
+/* C = (accumulate ? C : 0) + alpha * A %*% t(B);  A: rows(C) x K, B: cols(C) x K; C aliases neither operand */
+IAK3D_API int iak3d_mat_gemm_nt(iak3d_mat* C, double alpha, const iak3d_mat* A, const iak3d_mat* B, int32_t accumulate);
+/* M := chol2inv(chol(M)) for a symmetric M; *status = IAK3D_NOT_SPD (M unchanged) where R's chol() stops */
+IAK3D_API int iak3d_mat_spd_inverse(iak3d_mat* M, int32_t* status);
+/* M (n x n) := setCIAK3D(...)$C of the dataset's supports (fitIAK3D.R:1005-1100); IAK3D_BAD_PARS like iak3d_cov_build */
+IAK3D_API int iak3d_mat_cov_build(iak3d_ds* ds, const iak3d_pars* pars, iak3d_mat* M);
+/* out[j] = sum_i A[i,j] * B[i,j]  ==  colSums(A * B) */
+IAK3D_API int iak3d_mat_coldot(const iak3d_mat* A, const iak3d_mat* B, double* out);
+
 /* ---- measurement helpers (bench.py) ---------------------------------------------------------- */
 IAK3D_API int iak3d_sync(iak3d_ctx* ctx);
 IAK3D_API int iak3d_timer_start(iak3d_ctx* ctx);                 /* cudaEventRecord on the context stream */

@@ -1193,8 +1193,86 @@ def predMatsIAK3D_CL_ByBlock(z_muhat, XData, xMap, dIMap, lmmFit, modelx, sdfdTy
     return dict(diagCkk=Ckk, diagCkhiCChk=q, CkhiCX=cx, CkhiCz_muhat=cz)
 
 
+def _chol2inv(A):
+    """chol2inv(chol(A)) of the reference: raises for a non-SPD matrix like R's chol."""
+    L = np.linalg.cholesky(A)
+    Li = sla.solve_triangular(L, np.eye(A.shape[0]), lower=True)
+    return Li.T @ Li
+
+
+def predMatsIAK3D_CLEV_ByBlock(z_muhat, XData, xMap, dIMap, lmmFit, modelx, sdfdTypes, cmeOpt):
+    """compositeLikIAK3D.R:609-798 (compLikOptn 2 and 3, Eidsvik et al.): the map supports of block k are predicted
+    JOINTLY from the pairwise conditionals with every adjacent block l.  The `loadFromFit` branch (:688-707) reads the
+    same matrices from the fit object, so only the rebuild branch is restated.  -> (zk, vk); X betahat is added by the
+    caller (predictIAK3D.R:231-234)."""
+    cl = lmmFit["compLikMats"]
+    blocks = cl["listBlocks"]
+    cen = np.asarray(cl["centroids"], float)
+    pairs = np.asarray(cl["subsetPairsAdj"]).reshape(-1, 2)
+    optn = cl["compLikOptn"]
+    blockMap = np.argmin(xyDist(xMap, cen), axis=1)                     # :613
+    nx = xMap.shape[0]
+    zk = np.full(nx, np.nan); vk = np.full(nx, np.nan)
+    z_muhat = np.asarray(z_muhat, float).reshape(-1)
+    for k in range(int(blockMap.max()) + 1):                            # :625
+        pts = np.nonzero(blockMap == k)[0]
+        m = pts.size
+        if m == 0:
+            continue
+        adj = [int(b) for a, b in pairs if a == k] + [int(a) for a, b in pairs if b == k]   # :636, :817-827
+        if not adj:
+            raise ValueError("Error - every block must have a neighbour - check this!")
+        iDatak = np.asarray(blocks[k]); nk = iDatak.size
+        i0 = np.arange(m); i1 = m + np.arange(nk)
+        i2L, datL, cnt = [], [], m + nk
+        for l in adj:                                                   # :651-663
+            d = np.asarray(blocks[l]); datL.append(d); i2L.append(cnt + np.arange(d.size)); cnt += d.size
+        rows = np.concatenate([iDatak] + datL)
+        sm = setupIAK3D(np.vstack([xMap[pts], lmmFit["xData"][rows]]), np.vstack([dIMap[pts], lmmFit["dIData"][rows]]))   # :668
+        Call, _ = setCIAK3D(lmmFit["parsBTfmd"], modelx, *sdfdTypes, cmeOpt, sm)                                          # :671
+        i01 = np.concatenate([i0, i1])
+        C0k = Call[np.ix_(i01, i01)]                                    # :680
+        A0 = np.zeros((m, m)); b0 = np.zeros(m); Bk0 = np.zeros((m, m + nk))
+        QL, CL_ = [], []
+        for d, i2 in zip(datL, i2L):                                    # :692-745
+            i12 = np.concatenate([i1, i2])
+            Skl = Call[np.ix_(i12, i12)]
+            Ckl0 = Call[np.ix_(i12, i0)]
+            T = np.linalg.solve(Skl, Ckl0)                              # :717
+            C0IF = C0k[np.ix_(i0, i0)] - Call[np.ix_(i0, i12)] @ T      # :720
+            C0IF = 0.5 * (C0IF + C0IF.T)
+            iC0IF = _chol2inv(C0IF)                                     # :725
+            Q12 = -iC0IF @ T.T                                          # :726
+            QL.append(Q12[:, nk:]); CL_.append(Call[np.ix_(i01, i2)])   # :730-731
+            A0 += iC0IF
+            b0 += -Q12 @ z_muhat[np.concatenate([iDatak, d])]           # :734
+            Bk0 += np.hstack([iC0IF, Q12[:, :nk]])                      # :735
+        if optn == 3:                                                   # :748-770
+            nnon = len(blocks) - len(adj) - 1
+            iCkk = _chol2inv(C0k[np.ix_(i1, i1)])
+            C0kiC = C0k[np.ix_(i0, i1)] @ iCkk
+            IF = C0k[np.ix_(i0, i0)] - C0kiC @ C0k[np.ix_(i1, i0)]
+            IF = 0.5 * (IF + IF.T)
+            iIF = _chol2inv(IF)
+            iIFC = iIF @ C0kiC
+            A0 += nnon * iIF
+            b0 += nnon * (iIFC @ z_muhat[iDatak])
+            Bk0[:, :m] += nnon * iIF
+            Bk0[:, m:] -= nnon * iIFC
+        J0 = Bk0 @ C0k @ Bk0.T                                          # :772
+        for a, i2a in enumerate(i2L):
+            J0 = J0 + 2 * Bk0 @ CL_[a] @ QL[a].T                        # :775
+            for b_, i2b in enumerate(i2L):
+                J0 = J0 + QL[a] @ Call[np.ix_(i2a, i2b)] @ QL[b_].T     # :779
+        A0 = 0.5 * (A0 + A0.T); J0 = 0.5 * (J0 + J0.T)                  # :784-785
+        iA0 = _chol2inv(A0)                                             # :788
+        zk[pts] = iA0 @ b0                                              # :790
+        vk[pts] = np.sum(iA0 * (J0 @ iA0), axis=0)                      # :795
+    return zk, vk
+
+
 def predictIAK3D_CL(xMap, dIMap, XMap_fn, lmmFit, modelx, sdfdTypes, cmeOpt):
-    """predictIAK3D.R:5-287 for a composite-likelihood fit with compLikOptn 1 or 4 (:211-226)."""
+    """predictIAK3D.R:5-287 for a composite-likelihood fit (:211-226: compLikOptn 2, 3 -> CLEV, else CL by block)."""
     xMap = np.asarray(xMap, float).reshape(len(xMap), -1)
     dIMap = np.round(np.asarray(dIMap, float).reshape(-1, 2), 2)
     nd, nx = dIMap.shape[0], xMap.shape[0]
@@ -1203,6 +1281,12 @@ def predictIAK3D_CL(xMap, dIMap, XMap_fn, lmmFit, modelx, sdfdTypes, cmeOpt):
     zMap = np.full((nd, nx), np.nan); vMap = np.full((nd, nx), np.nan)
     for i in range(nd):
         XM = XMap_fn(i, np.arange(nx))
+        if lmmFit["compLikMats"]["compLikOptn"] in (2, 3):              # predictIAK3D.R:211-217, 231-234
+            zk, vk = predMatsIAK3D_CLEV_ByBlock(z_muhat, XData, xMap, np.repeat(dIMap[i:i + 1], nx, axis=0), lmmFit, modelx, sdfdTypes,
+                                                cmeOpt)
+            zMap[i] = (XM @ betahat).reshape(-1) + zk
+            vMap[i] = vk
+            continue
         t = predMatsIAK3D_CL_ByBlock(z_muhat, XData, xMap, np.repeat(dIMap[i:i + 1], nx, axis=0), lmmFit, modelx, sdfdTypes, cmeOpt)
         zMap[i] = (XM @ betahat).reshape(-1) + t["CkhiCz_muhat"]
         d = XM - t["CkhiCX"]

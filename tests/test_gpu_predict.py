@@ -149,6 +149,33 @@ def test_cl_block_prediction_vs_oracle(ctx, optn, useReml, kind, nonstat):
     assert scaled_err(pg["pi90LMap"], lw) <= TOL
 
 
+@pytest.mark.parametrize("optn,kind,nonstat,nblocks", [(2, "edgeroi", False, 6), (3, "edgeroi", False, 6), (2, "matern0.5", True, 4),
+                                                       (3, "matern0.8", False, 2)])
+def test_clev_block_prediction_vs_oracle(ctx, optn, kind, nonstat, nblocks):
+    """predictIAK3D for a composite-likelihood fit with the Eidsvik options (predictIAK3D.R:211-217 ->
+    predMatsIAK3D_CLEV_ByBlock, compositeLikIAK3D.R:609-798): joint prediction of each block's map supports from the
+    pairwise conditionals, all matrices on the device."""
+    ds = synth.make_dataset(1300, 73)
+    P, modelx, types, cmeOpt = case_pars(kind, nonstat, 0.5)
+    blk = synth.make_blocks(ds["xData"], ds["prof"], nblocks, 73)
+    blk["compLikOptn"] = optn
+    cl = iak.setupIAK3D_CL(ds["xData"], ds["dIData"], ds["zData"], ds["XData"], blk, ctx=ctx)
+    got = iak.nllIAK3D_CL(None, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True, PARBNDS, False, cl, parsBTfmd=P, rtnAll=True)
+    want = orc.nllIAK3D_CL(None, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True, PARBNDS, False, blk, ds["xData"],
+                           ds["dIData"], parsBTfmd=P, rtnTerms=True)
+    assert abs(got["nll"] - want["nll"]) <= TOL * abs(want["nll"])
+    rng = np.random.default_rng(5)
+    xMap = np.vstack([rng.uniform(0, 100, (170, 2)), ds["xData"][::200]])
+    dIMap = synth.GSM_INTERVALS[[1, 4]]
+    Xfn = lambda i, idx: synth.grid_design(xMap[idx], dIMap[i], 3)
+    pg = iak.predictIAK3D_CL(xMap, dIMap, Xfn, got)
+    zw, vw, lw, uw = orc.predictIAK3D_CL(xMap, dIMap, Xfn, want, modelx, types, cmeOpt)
+    assert np.all(vw > 0)
+    assert scaled_err(pg["zMap"], zw) <= TOL
+    assert scaled_err(pg["vMap"], vw) <= TOL
+    assert scaled_err(pg["pi90UMap"], uw) <= TOL
+
+
 def test_profilePredict_vs_oracle(ctx):
     """profilePredictIAK3D (predictIAK3D.R:292-504): one location, a full profile of depth intervals, incl. Ckh and iC."""
     ds = synth.make_dataset(450, 27)
