@@ -278,3 +278,85 @@ gradHessIAK3D_gpu <- function(setupMats, parsBTfmd, modelx, sdfdTypes, lnvPars){
   if(tmp[[1]] != 0){ return(list(nll = NA)) }
   list(nll = tmp[[2]], grad = tmp[[3]], hess = tmp[[4]], fim = tmp[[5]], betahat = tmp[[6]], vbetahat = tmp[[7]])
 }
+
+
+### ---- predMatsIAK3D_CLEV_ByBlock (compositeLikIAK3D.R:609-798) with every large matrix kept on the device ----
+### Thin R handles over iak3d_mat_*: m$new / m$sub / m$mm are `matrix(0, .)`, `M[rows, cols]` and `A %*% t(B)` of the
+### reference; chol2inv(chol(.)) and solve(.) are iak3dR_mat_spd_inverse.  Same arguments and return value as the reference.
+.iak3d_m <- list(
+  new = function(nr, nc){ .Call('iak3dR_mat', nr, nc, NULL) },
+  from = function(A){ .Call('iak3dR_mat', 0, 0, as.matrix(A)) },
+  get = function(M, r0, c0, nr, nc){ .Call('iak3dR_mat_get', M, as.numeric(c(r0, c0, nr, nc))) },
+  copy = function(D, S, dr0 = 0, dc0 = 0, sr0 = 0, sc0 = 0, nr, nc, tr = 0, alpha = 1, beta = 0){
+    .Call('iak3dR_mat_copy', D, S, as.numeric(c(dr0, dc0, sr0, sc0, nr, nc, tr, alpha, beta))) ; D },
+  sub = function(S, r0, c0, nr, nc, tr = 0, alpha = 1){
+    D <- if(tr == 1){ .Call('iak3dR_mat', nc, nr, NULL) }else{ .Call('iak3dR_mat', nr, nc, NULL) }
+    if(tr == 1){ .iak3d_m$copy(D, S, sr0 = r0, sc0 = c0, nr = nc, nc = nr, tr = 1, alpha = alpha) }else{
+      .iak3d_m$copy(D, S, sr0 = r0, sc0 = c0, nr = nr, nc = nc, alpha = alpha) } },
+  gather = function(S, rr, cc){   # S[c(rows...), c(cols...)] for lists of c(start0, length)
+    D <- .Call('iak3dR_mat', sum(sapply(rr, `[`, 2)), sum(sapply(cc, `[`, 2)), NULL) ; ro <- 0
+    for(r in rr){ co <- 0
+      for(k in cc){ if(r[2] > 0 && k[2] > 0){ .iak3d_m$copy(D, S, ro, co, r[1], k[1], r[2], k[2]) } ; co <- co + k[2] }
+      ro <- ro + r[2] }
+    D },
+  sym = function(S, n){ D <- .Call('iak3dR_mat', n, n, NULL)
+    .iak3d_m$copy(D, S, nr = n, nc = n, alpha = 0.5) ; .iak3d_m$copy(D, S, nr = n, nc = n, tr = 1, alpha = 0.5, beta = 1) },
+  mm = function(A, B, nr, nc, alpha = 1){ D <- .Call('iak3dR_mat', nr, nc, NULL) ; .Call('iak3dR_mat_gemm_nt', D, alpha, A, B, 0L) ; D },
+  acc = function(D, A, B, alpha = 1){ .Call('iak3dR_mat_gemm_nt', D, alpha, A, B, 1L) ; D },
+  inv = function(M){ .Call('iak3dR_mat_spd_inverse', M) ; M })
+
+predMatsIAK3D_CLEV_ByBlock <- function(z_muhat , XData , xMap , dIMap , iData = seq(length(z_muhat)) , lmmFit){
+  m_ <- .iak3d_m
+  blockMap <- getBlocksFromLocations(xMap = xMap , compLikMats = lmmFit$compLikMats)
+  zk <- vk <- matrix(NA , length(blockMap) , 1)
+  pv <- .iak3d_pv(lmmFit$parsBTfmd, lmmFit$modelx, lmmFit$sdfdType_cd1, lmmFit$sdfdType_cxd0, lmmFit$sdfdType_cxd1, lmmFit$cmeOpt)
+  for (iBlock in 1:max(blockMap)){
+    iMapThis <- which(blockMap == iBlock) ; m <- length(iMapThis)
+    if(m == 0){ next }
+    iBlocksAdj <- getAdjacentBlocks(iBlock = iBlock , compLikMats = lmmFit$compLikMats)
+    iDatak <- intersect(lmmFit$compLikMats$listBlocks[[iBlock]]$i , iData) ; nk <- length(iDatak)
+    iDatalList <- lapply(iBlocksAdj, function(l){ intersect(lmmFit$compLikMats$listBlocks[[l]]$i , iData) })
+    nl <- sapply(iDatalList, length) ; s2 <- m + nk + cumsum(c(0, nl))[seq_along(nl)]          # zero-based starts of the i2 ranges
+    iThis <- c(iDatak , unlist(iDatalList))
+    sm <- setupIAK3D(xData = rbind(xMap[iMapThis,,drop=FALSE] , lmmFit$xData[iThis,,drop=FALSE]) ,
+                     dIData = rbind(dIMap[iMapThis,,drop=FALSE] , as.matrix(lmmFit$dIData[iThis,,drop=FALSE])) , nDscPts = 0 ,
+                     sdfdType_cd1 = lmmFit$sdfdType_cd1 , sdfdType_cxd0 = lmmFit$sdfdType_cxd0 , sdfdType_cxd1 = lmmFit$sdfdType_cxd1 ,
+                     sdfdKnots = lmmFit$sdfdKnots)
+    Call <- .Call('iak3dR_mat_cov_build', sm$iak3d, pv)                                          # C0klAll, :671
+    C0k <- m_$sub(Call, 0, 0, m + nk, m + nk) ; C00 <- m_$sub(Call, 0, 0, m, m)
+    A0 <- m_$new(m, m) ; b0 <- m_$new(m, 1) ; Bk0 <- m_$new(m, m + nk) ; QL <- list()
+    for(i in seq_along(iBlocksAdj)){
+      kl <- list(c(m, nk), c(s2[i], nl[i])) ; nkl <- nk + nl[i]
+      iS <- m_$inv(m_$gather(Call, kl, kl))                                                      # :717
+      C0kl <- m_$gather(Call, list(c(0, m)), kl)
+      Tt <- m_$mm(C0kl, iS, m, nkl)
+      IF <- m_$acc(m_$copy(m_$new(m, m), C00, nr = m, nc = m), C0kl, Tt, alpha = -1)             # :720
+      iIF <- m_$inv(m_$sym(IF, m))                                                               # :722-725
+      Q12 <- m_$mm(iIF, m_$sub(Tt, 0, 0, m, nkl, tr = 1), m, nkl, alpha = -1)                    # :726
+      QL[[i]] <- m_$sub(Q12, 0, nk, m, nl[i])
+      m_$copy(A0, iIF, nr = m, nc = m, beta = 1)
+      m_$acc(b0, Q12, m_$from(matrix(z_muhat[c(iDatak , iDatalList[[i]])], nrow = 1)), alpha = -1)
+      m_$copy(Bk0, iIF, nr = m, nc = m, beta = 1) ; m_$copy(Bk0, Q12, dc0 = m, nr = m, nc = nk, beta = 1)
+    }
+    if(lmmFit$compLikMats$compLikOptn == 3){                                                     # :748-770
+      nnon <- length(lmmFit$compLikMats$listBlocks) - length(iBlocksAdj) - 1
+      iCkk <- m_$inv(m_$sub(Call, m, m, nk, nk)) ; C0_k <- m_$sub(Call, 0, m, m, nk)
+      C0kiC <- m_$mm(C0_k, iCkk, m, nk)
+      iIF <- m_$inv(m_$sym(m_$acc(m_$copy(m_$new(m, m), C00, nr = m, nc = m), C0kiC, C0_k, alpha = -1), m))
+      iIFC <- m_$mm(iIF, m_$sub(C0kiC, 0, 0, m, nk, tr = 1), m, nk)
+      m_$copy(A0, iIF, nr = m, nc = m, alpha = nnon, beta = 1)
+      m_$acc(b0, iIFC, m_$from(matrix(z_muhat[iDatak], nrow = 1)), alpha = nnon)
+      m_$copy(Bk0, iIF, nr = m, nc = m, alpha = nnon, beta = 1) ; m_$copy(Bk0, iIFC, dc0 = m, nr = m, nc = nk, alpha = -nnon, beta = 1)
+    }
+    J0 <- m_$mm(m_$mm(Bk0, C0k, m, m + nk), Bk0, m, m)                                           # :772
+    for(i in seq_along(iBlocksAdj)){
+      m_$acc(J0, m_$mm(Bk0, m_$sub(Call, s2[i], 0, nl[i], m + nk), m, nl[i]), QL[[i]], alpha = 2)
+      for(j in seq_along(iBlocksAdj)){
+        m_$acc(J0, m_$mm(QL[[i]], m_$sub(Call, s2[j], s2[i], nl[j], nl[i]), m, nl[j]), QL[[j]]) }
+    }
+    iA0 <- m_$inv(m_$sym(A0, m)) ; J0s <- m_$sym(J0, m)                                          # :784-788
+    zk[iMapThis,1] <- m_$get(m_$mm(iA0, m_$sub(b0, 0, 0, m, 1, tr = 1), m, 1), 0, 0, m, 1)
+    vk[iMapThis,1] <- .Call('iak3dR_mat_coldot', iA0, m_$mm(J0s, iA0, m, m))
+  }
+  return(list('zk' = zk , 'vk' = vk))
+}

@@ -304,6 +304,83 @@ SEXP iak3dR_gradhess(SEXP dsp, SEXP pv, SEXP lnvPars) {
   return out;
 }
 
+/* ---- device-resident matrices (iak3d_mat_*): the algebra of predMatsIAK3D_CLEV_ByBlock, compositeLikIAK3D.R:609-798 ---- */
+static void mat_finalizer(SEXP p) {
+  iak3d_mat* M = (iak3d_mat*)R_ExternalPtrAddr(p);
+  if (M) { iak3d_mat_destroy(M); R_ClearExternalPtr(p); }
+}
+static SEXP mat_wrap(iak3d_mat* M) {
+  SEXP p = PROTECT(R_MakeExternalPtr(M, R_NilValue, R_NilValue));
+  R_RegisterCFinalizerEx(p, mat_finalizer, TRUE);
+  UNPROTECT(1);
+  return p;
+}
+#define MAT(p) ((iak3d_mat*)R_ExternalPtrAddr(p))
+/* matrix(0, rows, cols) on the device, or as.matrix(init) when init is not NULL */
+SEXP iak3dR_mat(SEXP rows, SEXP cols, SEXP init) {
+  iak3d_mat* M = NULL;
+  const int64_t nr = isNull(init) ? (int64_t)asReal(rows) : nrows(init), nc = isNull(init) ? (int64_t)asReal(cols) : ncols(init);
+  int st = iak3d_mat_create(ctx_get(), nr, nc, &M);
+  if (st == IAK3D_OK && !isNull(init)) st = iak3d_mat_set(M, 0, 0, nr, nc, REAL(init), nr);
+  if (st != IAK3D_OK) { if (M) iak3d_mat_destroy(M); error("iak3d_mat_create: %s", iak3d_last_error(g_ctx)); }
+  return mat_wrap(M);
+}
+/* as.matrix(M[r0 + 1:nr, c0 + 1:nc]) */
+SEXP iak3dR_mat_get(SEXP Mp, SEXP blk) {
+  const double* b = REAL(blk);
+  const int64_t r0 = (int64_t)b[0], c0 = (int64_t)b[1], nr = (int64_t)b[2], nc = (int64_t)b[3];
+  SEXP out = PROTECT(allocMatrix(REALSXP, (int)nr, (int)nc));
+  int st = iak3d_mat_get(MAT(Mp), r0, c0, nr, nc, REAL(out), nr);
+  if (st != IAK3D_OK) error("iak3d_mat_get: %s", iak3d_last_error(g_ctx));
+  UNPROTECT(1);
+  return out;
+}
+/* D[dr0.., dc0..] <- beta * D[..] + alpha * S[sr0.., sc0..] (t(.) when tr); blk = c(dr0, dc0, sr0, sc0, nr, nc, tr, alpha, beta) */
+SEXP iak3dR_mat_copy(SEXP Dp, SEXP Sp, SEXP blk) {
+  const double* b = REAL(blk);
+  int st = iak3d_mat_copy(MAT(Dp), (int64_t)b[0], (int64_t)b[1], MAT(Sp), (int64_t)b[2], (int64_t)b[3], (int64_t)b[4], (int64_t)b[5],
+                          (int32_t)b[6], b[7], b[8]);
+  if (st != IAK3D_OK) error("iak3d_mat_copy: %s", iak3d_last_error(g_ctx));
+  return R_NilValue;
+}
+/* C <- (acc ? C : 0) + alpha * A %*% t(B) */
+SEXP iak3dR_mat_gemm_nt(SEXP Cp, SEXP alpha, SEXP Ap, SEXP Bp, SEXP acc) {
+  int st = iak3d_mat_gemm_nt(MAT(Cp), asReal(alpha), MAT(Ap), MAT(Bp), asInteger(acc));
+  if (st != IAK3D_OK) error("iak3d_mat_gemm_nt: %s", iak3d_last_error(g_ctx));
+  return R_NilValue;
+}
+/* M <- chol2inv(chol(M)); stops like chol() when M is not positive definite */
+SEXP iak3dR_mat_spd_inverse(SEXP Mp) {
+  int32_t status = 0;
+  int st = iak3d_mat_spd_inverse(MAT(Mp), &status);
+  if (st < 0) error("iak3d_mat_spd_inverse: %s", iak3d_last_error(g_ctx));
+  if (status != 0) error("the leading minor is not positive definite");
+  return R_NilValue;
+}
+/* setCIAK3D(...)$C of the dataset as a device matrix; NULL for invalid parameters (R: C = NA) */
+SEXP iak3dR_mat_cov_build(SEXP dsp, SEXP pv) {
+  iak3d_ds* ds = (iak3d_ds*)R_ExternalPtrAddr(dsp);
+  iak3d_pars P; pars_from(pv, &P);
+  int64_t n = 0;
+  iak3d_dataset_info(ds, &n, NULL, NULL, NULL);
+  iak3d_mat* M = NULL;
+  int st = iak3d_mat_create(ctx_get(), n, n, &M);
+  if (st == IAK3D_OK) st = iak3d_mat_cov_build(ds, &P, M);
+  if (st == IAK3D_BAD_PARS) { iak3d_mat_destroy(M); return R_NilValue; }
+  if (st != IAK3D_OK) { if (M) iak3d_mat_destroy(M); error("iak3d_mat_cov_build: %s", iak3d_last_error(g_ctx)); }
+  return mat_wrap(M);
+}
+/* colSums(A * B) */
+SEXP iak3dR_mat_coldot(SEXP Ap, SEXP Bp) {
+  int64_t nc = 0;
+  iak3d_mat_shape(MAT(Ap), NULL, &nc);
+  SEXP out = PROTECT(allocVector(REALSXP, (R_xlen_t)nc));
+  int st = iak3d_mat_coldot(MAT(Ap), MAT(Bp), REAL(out));
+  if (st != IAK3D_OK) error("iak3d_mat_coldot: %s", iak3d_last_error(g_ctx));
+  UNPROTECT(1);
+  return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
   {"iak3dR_dataset", (DL_FUNC)&iak3dR_dataset, 3},       {"iak3dR_set_W", (DL_FUNC)&iak3dR_set_W, 2},
   {"iak3dR_nll_terms", (DL_FUNC)&iak3dR_nll_terms, 2},   {"iak3dR_nll_terms_iAW", (DL_FUNC)&iak3dR_nll_terms_iAW, 2},
@@ -315,6 +392,10 @@ static const R_CallMethodDef call_methods[] = {
   {"iak3dR_fit_res", (DL_FUNC)&iak3dR_fit_res, 5},       {"iak3dR_fit_option", (DL_FUNC)&iak3dR_fit_option, 3},
   {"iak3dR_predict_terms", (DL_FUNC)&iak3dR_predict_terms, 6}, {"iak3dR_gradhess", (DL_FUNC)&iak3dR_gradhess, 3},
   {"iak3dR_nll_grad", (DL_FUNC)&iak3dR_nll_grad, 4},
+  {"iak3dR_mat", (DL_FUNC)&iak3dR_mat, 3},               {"iak3dR_mat_get", (DL_FUNC)&iak3dR_mat_get, 2},
+  {"iak3dR_mat_copy", (DL_FUNC)&iak3dR_mat_copy, 3},     {"iak3dR_mat_gemm_nt", (DL_FUNC)&iak3dR_mat_gemm_nt, 5},
+  {"iak3dR_mat_spd_inverse", (DL_FUNC)&iak3dR_mat_spd_inverse, 1}, {"iak3dR_mat_cov_build", (DL_FUNC)&iak3dR_mat_cov_build, 2},
+  {"iak3dR_mat_coldot", (DL_FUNC)&iak3dR_mat_coldot, 2},
   {NULL, NULL, 0}};
 
 void R_init_iak3dR(DllInfo* dll) {
