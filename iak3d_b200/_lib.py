@@ -83,6 +83,7 @@ _PROTOS = {
     "iak3d_fp64_peak": (C.c_int, [_vp, _i32, _dp]),
     "iak3d_mat_create": (C.c_int, [_vp, _i64, _i64, C.POINTER(_vp)]),
     "iak3d_mat_destroy": (C.c_int, [_vp]),
+    "iak3d_mat_trim": (C.c_int, [_vp]),
     "iak3d_mat_shape": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "iak3d_mat_set": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _dp, _i64]),
     "iak3d_mat_get": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _dp, _i64]),

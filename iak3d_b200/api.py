@@ -1231,6 +1231,7 @@ def predMatsIAK3D_CLEV_ByBlock(z_muhat, XData, xMap, dIMap, lmmFit):
         vk[pts] = iA0.coldot(JA)                                       # :795
         for M in [Call, C0k, C00, A0, b0, Bk0, J0, iA0, J0s, b0t, zkd, JA] + QL:
             M.close()
+    ctx.check(ctx.lib.iak3d_mat_trim(ctx.h))
     return dict(zk=zk, vk=vk)
 
 

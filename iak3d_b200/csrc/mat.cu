@@ -108,6 +108,21 @@ __global__ void mat_coldot_kernel(const double* __restrict__ A, int64_t nRUa, co
   if (lane == 0) out[j] = s;
 }
 
+// Matrices come and go by the hundred per prediction block: stream-ordered allocation from the device's default pool,
+// kept cached (no release at synchronisation points), so that create / destroy neither synchronise nor reach the driver.
+cudaError_t pool_alloc(iak3d_ctx* ctx, void** p, size_t bytes) {
+  static int configured_device = -1;
+  if (configured_device != ctx->device) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    configured_device = ctx->device;
+  }
+  return cudaMallocAsync(p, bytes, ctx->stream);
+}
+
 bool in_range(const iak3d_mat* M, int64_t r0, int64_t c0, int64_t nr, int64_t nc) {
   return r0 >= 0 && c0 >= 0 && nr >= 0 && nc >= 0 && r0 + nr <= M->rows && c0 + nc <= M->cols;
 }
@@ -120,13 +135,13 @@ extern "C" int iak3d_mat_create(iak3d_ctx* ctx, int64_t rows, int64_t cols, iak3
   iak3d_mat* M = new iak3d_mat();
   M->ctx = ctx; M->rows = rows; M->cols = cols;
   M->prow = round_up(rows, TM); M->pcol = round_up(cols, TN);
-  if (cudaMalloc(&M->d, M->bytes()) != cudaSuccess) {
+  if (pool_alloc(ctx, (void**)&M->d, M->bytes()) != cudaSuccess) {
     cudaGetLastError(); delete M;
     ctx->err = "mat_create: allocation failed";
     return IAK3D_ERR_CUDA;
   }
   const cudaError_t e = cudaMemsetAsync(M->d, 0, M->bytes(), ctx->stream);
-  if (e != cudaSuccess) { cudaFree(M->d); delete M; ctx->err = std::string("mat_create: ") + cudaGetErrorString(e); return IAK3D_ERR_CUDA; }
+  if (e != cudaSuccess) { cudaFreeAsync(M->d, ctx->stream); delete M; ctx->err = std::string("mat_create: ") + cudaGetErrorString(e); return IAK3D_ERR_CUDA; }
   *out = M;
   return IAK3D_OK;
 }
@@ -134,9 +149,20 @@ extern "C" int iak3d_mat_create(iak3d_ctx* ctx, int64_t rows, int64_t cols, iak3
 extern "C" int iak3d_mat_destroy(iak3d_mat* M) {
   if (!M) return IAK3D_OK;
   cudaSetDevice(M->ctx->device);
-  cudaStreamSynchronize(M->ctx->stream);
-  cudaFree(M->d);
+  cudaFreeAsync(M->d, M->ctx->stream);          // stream-ordered: pending kernels on the stream finish first
   delete M;
+  return IAK3D_OK;
+}
+
+// Hands the cached matrix memory back to the driver (end of a prediction call: the factor buffers of a large fit are
+// plain allocations and must be able to use it).
+extern "C" int iak3d_mat_trim(iak3d_ctx* ctx) {
+  if (!ctx) return IAK3D_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaMemPool_t pool;
+  CUDA_TRY(ctx, cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+  CUDA_TRY(ctx, cudaMemPoolTrimTo(pool, 0));
   return IAK3D_OK;
 }
 

@@ -213,6 +213,8 @@ IAK3D_API int iak3d_gradhess(iak3d_ds* ds, const iak3d_pars* pars, int32_t ncomp
 typedef struct iak3d_mat iak3d_mat;
 IAK3D_API int iak3d_mat_create(iak3d_ctx* ctx, int64_t rows, int64_t cols, iak3d_mat** out);      /* zero-filled */
 IAK3D_API int iak3d_mat_destroy(iak3d_mat* M);
+/* matrices are allocated stream-ordered from a cached pool; this returns the cache to the driver */
+IAK3D_API int iak3d_mat_trim(iak3d_ctx* ctx);
 IAK3D_API int iak3d_mat_shape(const iak3d_mat* M, int64_t* rows, int64_t* cols);
 /* host column-major (leading dimension ld) -> sub-block, and back */
 IAK3D_API int iak3d_mat_set(iak3d_mat* M, int64_t r0, int64_t c0, int64_t nr, int64_t nc, const double* src, int64_t ld);

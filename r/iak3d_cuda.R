@@ -357,6 +357,8 @@ predMatsIAK3D_CLEV_ByBlock <- function(z_muhat , XData , xMap , dIMap , iData = 
     iA0 <- m_$inv(m_$sym(A0, m)) ; J0s <- m_$sym(J0, m)                                          # :784-788
     zk[iMapThis,1] <- m_$get(m_$mm(iA0, m_$sub(b0, 0, 0, m, 1, tr = 1), m, 1), 0, 0, m, 1)
     vk[iMapThis,1] <- .Call('iak3dR_mat_coldot', iA0, m_$mm(J0s, iA0, m, m))
+    rm(Call, C0k, C00, A0, b0, Bk0, QL, J0, iA0, J0s) ; gc(FALSE)       # finalizers release the device matrices of this block
   }
+  .Call('iak3dR_mat_trim')
   return(list('zk' = zk , 'vk' = vk))
 }

@@ -370,6 +370,11 @@ SEXP iak3dR_mat_cov_build(SEXP dsp, SEXP pv) {
   if (st != IAK3D_OK) { if (M) iak3d_mat_destroy(M); error("iak3d_mat_cov_build: %s", iak3d_last_error(g_ctx)); }
   return mat_wrap(M);
 }
+/* end of a prediction call: return the cached matrix memory to the driver */
+SEXP iak3dR_mat_trim(void) {
+  if (iak3d_mat_trim(ctx_get()) != IAK3D_OK) error("iak3d_mat_trim: %s", iak3d_last_error(g_ctx));
+  return R_NilValue;
+}
 /* colSums(A * B) */
 SEXP iak3dR_mat_coldot(SEXP Ap, SEXP Bp) {
   int64_t nc = 0;
@@ -395,7 +400,7 @@ static const R_CallMethodDef call_methods[] = {
   {"iak3dR_mat", (DL_FUNC)&iak3dR_mat, 3},               {"iak3dR_mat_get", (DL_FUNC)&iak3dR_mat_get, 2},
   {"iak3dR_mat_copy", (DL_FUNC)&iak3dR_mat_copy, 3},     {"iak3dR_mat_gemm_nt", (DL_FUNC)&iak3dR_mat_gemm_nt, 5},
   {"iak3dR_mat_spd_inverse", (DL_FUNC)&iak3dR_mat_spd_inverse, 1}, {"iak3dR_mat_cov_build", (DL_FUNC)&iak3dR_mat_cov_build, 2},
-  {"iak3dR_mat_coldot", (DL_FUNC)&iak3dR_mat_coldot, 2},
+  {"iak3dR_mat_coldot", (DL_FUNC)&iak3dR_mat_coldot, 2}, {"iak3dR_mat_trim", (DL_FUNC)&iak3dR_mat_trim, 0},
   {NULL, NULL, 0}};
 
 void R_init_iak3dR(DllInfo* dll) {
