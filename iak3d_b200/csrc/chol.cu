@@ -118,6 +118,27 @@ __device__ __forceinline__ void warp_mma_k4(double (&acc)[4][4][2], const double
     for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
 }
 
+// E3 helper: k-steps [kbeg, kend) of X = tile * inv(L_jj)' for the column tiles NLO..3 of this warp (tcol: their 8-column
+// tile indices).  A element (row, k) at Ab0[(k>>5)*2*UNIT + (k&31)*UL + mi*8], B element (col, k) at Bb0[k*LDB_S + 8*tile].
+template <int NLO>
+__device__ __forceinline__ void solve_segment(double (&x)[4][4][2], const double* __restrict__ Ab0, const double* __restrict__ Bb0,
+                                              const int (&tcol)[4], int kbeg, int kend) {
+#pragma unroll 2
+  for (int k0 = kbeg; k0 < kend; k0 += 4) {
+    const double* Ab = Ab0 + (k0 >> 5) * 2 * UNIT + (k0 & 31) * UL;
+    const double* Bb = Bb0 + k0 * LDB_S;
+    double a[4], b[4];
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++) a[mi] = Ab[mi * 8];
+#pragma unroll
+    for (int ni = NLO; ni < 4; ni++) b[ni] = Bb[tcol[ni] * 8];
+#pragma unroll
+    for (int ni = NLO; ni < 4; ni++)
+#pragma unroll
+      for (int mi = 0; mi < 4; mi++) dmma(x[mi][ni][0], x[mi][ni][1], a[mi], b[ni]);
+  }
+}
+
 // 1/sqrt(x) for a positive finite pivot: MUFU seed + two Newton steps (relative error ~1e-16); rsqrt() from the
 // math library carries special-case handling that sits on the column-to-column dependency chain.
 __device__ __forceinline__ double fast_rsqrt(double x) {
@@ -342,6 +363,26 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
       }
       // ---- E1: tile = A - acc (in shared memory) ----
       if (prof && tid == 0) tp1 = (long long)gtime();
+      const bool is_diag = (mode == 0) && (r == (j >> 1));
+      if (mode != 2 && !is_diag) {
+        // the inverted diagonal block goes to stage 0 (Ys), free once every consumer has left the K-loop; fetched now so
+        // that the copy runs under E1.  A finished factor (mode 1) needs no wait: its blocks were published long ago.
+        consumer_bar();
+        if (tid == 0) {
+          if (mode == 0) wait_flag(pb->invdone + j, epoch, status, abort_flag);
+          asm volatile("fence.proxy.async;" ::: "memory");
+          const bool wfetch = (mode == 1) && (pb->q > 0);
+          mbar_expect_tx(&inv_bar, (INVD_BLOCK + (wfetch ? 2 * UNIT : 0)) * 8);
+          bulk_g2s(Ys, pb->invd + (int64_t)j * INVD_BLOCK, INVD_BLOCK * 8, &inv_bar);
+          if (wfetch) {
+            // kriging epilogue: the two units of the factor buffer that hold the W rows (w0 is a multiple of 64) under
+            // this column block go to stage 1 as they lie -- a unit is already the B-operand layout [k*UL + row]
+            const int64_t wu = (int64_t)pb->w0 / UR;
+            bulk_g2s(Ws, L + ((int64_t)(2 * j) * nRUL + wu) * UNIT, UNIT * 8, &inv_bar);
+            bulk_g2s(Ws + UNIT, L + ((int64_t)(2 * j + 1) * nRUL + wu) * UNIT, UNIT * 8, &inv_bar);
+          }
+        }
+      }
       mbar_wait(&at_bar, at_phase, status, abort_flag);
       if (mode == 2) {
         // ---- plain product: tile = use_cin * tile + alpha * acc, stored straight back; no dependencies to publish ----
@@ -377,7 +418,6 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
       if (prof && tid == 0) tp2 = (long long)gtime();
       // ---- E2: diagonal block or fetch of the inverted diagonal block ----
       int row_lo = 0;
-      const bool is_diag = (mode == 0) && (r == (j >> 1));
       if (is_diag) {
         const int off = (j & 1) * TN;
         potf2_inv(At, off, Ys, s_comm, tid, pb->logsum + j, status);
@@ -396,39 +436,39 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
         if (tid == 0) st_release(pb->invdone + j, epoch);
         row_lo = off + TN;
       } else {
-        // a finished factor (mode 1) needs no wait: its inverse diagonal blocks were published long ago
-        if (tid == 0) {
-          if (mode == 0) wait_flag(pb->invdone + j, epoch, status, abort_flag);
-          asm volatile("fence.proxy.async;" ::: "memory");
-          mbar_expect_tx(&inv_bar, INVD_BLOCK * 8);
-          bulk_g2s(Ys, pb->invd + (int64_t)j * INVD_BLOCK, INVD_BLOCK * 8, &inv_bar);
-        }
         mbar_wait(&inv_bar, inv_phase, status, abort_flag);
         inv_phase ^= 1;
       }
       if (prof && tid == 0) tp3 = (long long)gtime();
       if (row_lo < TM) {
         // ---- E3: X = tile * inv(L_jj)' on the tensor pipe (k runs over the tile's 64 columns: two column halves) ----
+        // inv(L_jj)' is upper triangular: the 8-column tile t of X needs k < 8(t+1) only.  The eight column tiles are
+        // dealt to the two column warps as {0,3,4,7} and {1,2,5,6}, so both run 36 of the 64 (tile, k4) steps.
         double x[4][4][2];
 #pragma unroll
         for (int mi = 0; mi < 4; mi++)
 #pragma unroll
           for (int ni = 0; ni < 4; ni++) { x[mi][ni][0] = 0.0; x[mi][ni][1] = 0.0; }
+        int tcol[4];
 #pragma unroll
-        for (int ch = 0; ch < 2; ch++) {
-#pragma unroll 4
-          for (int k4 = 0; k4 < KC / 4; k4++)
-            warp_mma_k4(x, At + ch * 2 * UNIT, aoff, Ys + ch * KC * LDB_S, boff, k4 * 4, lane);
-        }
+        for (int ni = 0; ni < 4; ni++) tcol[ni] = 4 * (ni >> 1) + ((ni & 1) ? (3 - wn) : wn);
+        // four segments of k with a fixed set of live tiles each (tiles are sorted by extent): no branch inside a step
+        const double* Ab0 = At + kq * UL + aoff;
+        const double* Bb0 = Ys + kq * LDB_S + rq;
+        solve_segment<0>(x, Ab0, Bb0, tcol, 0, 8 * (tcol[0] + 1));
+        solve_segment<1>(x, Ab0, Bb0, tcol, 8 * (tcol[0] + 1), 8 * (tcol[1] + 1));
+        solve_segment<2>(x, Ab0, Bb0, tcol, 8 * (tcol[1] + 1), 8 * (tcol[2] + 1));
+        solve_segment<3>(x, Ab0, Bb0, tcol, 8 * (tcol[2] + 1), 8 * (tcol[3] + 1));
         consumer_bar();
 #pragma unroll
         for (int mi = 0; mi < 4; mi++)
 #pragma unroll
           for (int ni = 0; ni < 4; ni++) {
-            const int row = wm * 32 + mi * 8 + rq, col = wn * 32 + ni * 8 + kq * 2;
+            const int row = wm * 32 + mi * 8 + rq, col = tcol[ni] * 8 + kq * 2;
             if (row >= row_lo) { At[AT_IDX(row, col)] = x[mi][ni][0]; At[AT_IDX(row, col + 1)] = x[mi][ni][1]; }
           }
         consumer_bar();
+        if (prof && tid == 0 && mode == 1) s_tdep = (long long)gtime();     // mode 1 has no dependency stamp: end of E3 instead
         // ---- E4: copy-out of row halves [row_lo/64, 2): whole units, coalesced 16-byte stores ----
         {
           const int rh0 = row_lo >> 6, nun = (2 - rh0) * 2;       // units to store
@@ -455,12 +495,7 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
         } else {
           // kriging rows: G(:,0..q-1) += X Yw', G(:,q) += rowsum(X^2); Yw = rows w0.. of the factor buffer.
           // On the tensor pipe: each warp owns 16 rows of the tile (two m8 tiles), the W rows are the B operand
-          // (element (w, c) at Ws[c*UL + w], the K-loop's fragment layout), 16 W rows per pass.
-          for (int idx = tid; idx < q * TN; idx += NCW * 32) {
-            const int w = idx % q, c = idx / q;
-            Ws[c * UL + w] = __ldcg(L + uidx((int64_t)pb->w0 + w, (int64_t)j * TN + c, nRUL));
-          }
-          consumer_bar();
+          // (fetched with the inverse diagonal block: element (w, c) at Ws[(c>>5)*UNIT + (c&31)*UL + w]), 16 W rows per pass.
           {
             const int row0 = warp * 16 + rq;                       // + 8*mi
             double* const Gr = pb->G + R0 + row0;
@@ -482,7 +517,8 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
               for (int k4 = 0; k4 < TN / 4; k4++) {
                 const int k = k4 * 4 + kq;
                 const double a0 = At[AT_IDX(row0, k)], a1 = At[AT_IDX(row0 + 8, k)];
-                const double b0 = Ws[k * UL + wb + rq], b1 = Ws[k * UL + wb + 8 + rq];
+                const double* wk = Ws + (k >> 5) * UNIT + (k & 31) * UL + wb + rq;
+                const double b0 = wk[0], b1 = wk[8];
                 if (wb == 0) { ssq[0] = fma(a0, a0, ssq[0]); ssq[1] = fma(a1, a1, ssq[1]); }
                 dmma(g[0][0][0], g[0][0][1], a0, b0);
                 dmma(g[0][1][0], g[0][1][1], a0, b1);

@@ -40,6 +40,8 @@ mm = nch >= 20
 rate = d[mm, 0] / nch[mm]
 print("K-loop us/chunk: p10 %.3f median %.3f mean %.3f p90 %.3f; operand wait %.1f%% of the K-loop" %
       (np.percentile(rate, 10), np.median(rate), rate.mean(), np.percentile(rate, 90), 100 * kw[mm].sum() / d[mm, 0].sum()))
+e3 = (buf[:, 9] - t0) / 1e3          # mode 1: slot 6 holds the end of E3 (the solve against the inverse diagonal block)
+print("E3 (solve) %.2f us, E4+E5 (copy-out, border reduction) %.2f us" % ((e3 - T[:, 3]).mean(), (T[:, 4] - e3).mean()))
 gaps = []
 for c in np.unique(cta):
     i = np.where(cta == c)[0]
