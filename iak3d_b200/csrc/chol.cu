@@ -345,6 +345,9 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
 #pragma unroll
         for (int ni = 0; ni < 4; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
       uint32_t itc = it0;
+      // diagonal tile of an odd column block: its upper 64 rows lie above the diagonal block and are never stored; the
+      // four warps that own them leave the tensor pipe to the other four
+      const bool dead_rows = (mode == 0) && (r == (j >> 1)) && ((j & 1) != 0) && (wm < 2);
       for (int c = kstart; c < nchunks; c++, itc++) {
         const uint32_t s = itc % STAGES;
         if (prof && tid == 0) {
@@ -356,8 +359,10 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
         }
         const double* As = smem + s * STAGE_D;
         const double* Bs = As + A_STAGE;
+        if (!dead_rows) {
 #pragma unroll
-        for (int k4 = 0; k4 < KC / 4; k4++) warp_mma_k4(acc, As, aoff, Bs, boff, k4 * 4, lane);
+          for (int k4 = 0; k4 < KC / 4; k4++) warp_mma_k4(acc, As, aoff, Bs, boff, k4 * 4, lane);
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[s]);
       }
