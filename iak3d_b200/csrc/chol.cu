@@ -154,65 +154,27 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
   return y;
 }
 
-template <int CI>
-__device__ __forceinline__ void potf2_step(int cb, int br, int bc, bool live, double (&d)[4][4], double (&y)[4][4],
-                                           double* __restrict__ colbuf, double* __restrict__ yrow, double* __restrict__ pivs,
-                                           bool& bad) {
-  const int c = 4 * cb + CI, buf = (CI & 1) * 64;
-  if (bc == cb && br >= cb) {
-#pragma unroll
-    for (int i = 0; i < 4; i++) colbuf[buf + 4 * br + i] = d[i][CI];
-  }
-  if (br == cb && bc <= cb) {
-#pragma unroll
-    for (int jj = 0; jj < 4; jj++) yrow[buf + 4 * bc + jj] = y[CI][jj];
-  }
-  consumer_bar();
-  if (live && br >= cb) {
-    const double piv = colbuf[buf + c];
-    if (!(piv > 0.0) || isinf(piv)) bad = true;
-    const double rs = fast_rsqrt(piv);
-    if (br == cb && bc == cb) pivs[c] = piv;
-    double li[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) li[i] = (4 * br + i > c) ? colbuf[buf + 4 * br + i] * rs : 0.0;
-    if (bc >= cb) {          // columns beyond c exist in this block: rank-1 update of the trailing matrix
-      double lj[4];
-#pragma unroll
-      for (int jj = 0; jj < 4; jj++) lj[jj] = (4 * bc + jj > c) ? colbuf[buf + 4 * bc + jj] * rs : 0.0;
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int jj = 0; jj < 4; jj++) d[i][jj] -= li[i] * lj[jj];
-    }
-    if (bc <= cb) {          // columns up to c exist in this block: forward substitution of the inverse
-      double yk[4];
-#pragma unroll
-      for (int jj = 0; jj < 4; jj++) yk[jj] = (4 * bc + jj <= c) ? yrow[buf + 4 * bc + jj] * rs : 0.0;
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int jj = 0; jj < 4; jj++) y[i][jj] -= li[i] * yk[jj];
-      if (br == cb) {        // row c of the inverse is final
-#pragma unroll
-        for (int jj = 0; jj < 4; jj++) y[CI][jj] = yk[jj];
-      }
-    }
-    if (bc == cb) {          // column c of L is final
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const int r = 4 * br + i;
-        d[i][CI] = (r > c) ? li[i] : ((r == c) ? piv * rs : 0.0);
-      }
-    }
-  }
+// ---- diagonal block, 4 columns per step ------------------------------------------------------------------------------
+// potf2 fused with the inverse of the factor.  Thread (br, bc) of a 16 x 16 grid owns the 4 x 4 blocks d of A/L and y of
+// the inverse; a step is four columns: the owner of the diagonal 4 x 4 block factorises it in registers (the only serial rsqrt chain), the
+// panel below it and the block row of the inverse left of it are finished by substitution against that 4 x 4 factor,
+// and every other block takes one rank-4 update.  Two block barriers per four columns (the column-by-column version of
+// the first half of the round needed four and an exchange per column: 53.8k cycles per block against 40.0k).  scratch: 2 x BLK4_BUF doubles (double-buffered by step parity).
+constexpr int BLK4_L = 0;                 // l10 l20 l30 l21 l31 l32 r0 r1 r2 r3 (16 reserved)
+constexpr int BLK4_P = 16;                // panel: [64 rows][4]
+constexpr int BLK4_Y = 16 + 256;          // inverse block row: [4][64]
+constexpr int BLK4_BUF = 16 + 256 + 256;
+
+__device__ __forceinline__ void blk4_subst_row(const double (&l)[6], const double (&r)[4], double& v0, double& v1, double& v2, double& v3) {
+  // (v0 v1 v2 v3) := (v0 v1 v2 v3) inv(L44)'  <=>  forward substitution along the four entries
+  v0 = v0 * r[0];
+  v1 = (v1 - v0 * l[0]) * r[1];
+  v2 = (v2 - v0 * l[1] - v1 * l[3]) * r[2];
+  v3 = (v3 - v0 * l[2] - v1 * l[4] - v2 * l[5]) * r[3];
 }
 
-__device__ void potf2_inv(double* __restrict__ At, int off, double* __restrict__ Ys, double* __restrict__ comm /* 4*64+64 doubles */,
-                          int tid, double* logsum_out, int32_t* status) {
-  double* colbuf = comm;            // [2][64]
-  double* yrow = comm + 128;        // [2][64]
-  double* pivs = comm + 256;        // [64]
+__device__ void potf2_inv_blk4(double* __restrict__ At, int off, double* __restrict__ Ys, double* __restrict__ scratch,
+                               double* __restrict__ pivs /* 64 */, int tid, double* logsum_out, int32_t* status) {
   const int br = tid >> 4, bc = tid & 15;
   const bool live = (bc <= br);
   double d[4][4], y[4][4];
@@ -226,10 +188,91 @@ __device__ void potf2_inv(double* __restrict__ At, int off, double* __restrict__
   bool bad = false;
 #pragma unroll 1
   for (int cb = 0; cb < TN / 4; cb++) {
-    potf2_step<0>(cb, br, bc, live, d, y, colbuf, yrow, pivs, bad);
-    potf2_step<1>(cb, br, bc, live, d, y, colbuf, yrow, pivs, bad);
-    potf2_step<2>(cb, br, bc, live, d, y, colbuf, yrow, pivs, bad);
-    potf2_step<3>(cb, br, bc, live, d, y, colbuf, yrow, pivs, bad);
+    double* buf = scratch + (cb & 1) * BLK4_BUF;
+    if (br == cb && bc == cb) {
+      // ---- 4 x 4 factor in registers: l = (l10 l20 l30 l21 l31 l32), r = 1 / diag ----
+      double l[6], r[4], pv[4];
+      pv[0] = d[0][0]; r[0] = fast_rsqrt(pv[0]);
+      l[0] = d[1][0] * r[0]; l[1] = d[2][0] * r[0]; l[2] = d[3][0] * r[0];
+      pv[1] = d[1][1] - l[0] * l[0]; r[1] = fast_rsqrt(pv[1]);
+      l[3] = (d[2][1] - l[1] * l[0]) * r[1]; l[4] = (d[3][1] - l[2] * l[0]) * r[1];
+      pv[2] = d[2][2] - l[1] * l[1] - l[3] * l[3]; r[2] = fast_rsqrt(pv[2]);
+      l[5] = (d[3][2] - l[2] * l[1] - l[4] * l[3]) * r[2];
+      pv[3] = d[3][3] - l[2] * l[2] - l[4] * l[4] - l[5] * l[5]; r[3] = fast_rsqrt(pv[3]);
+#pragma unroll
+      for (int k = 0; k < 4; k++) { if (!(pv[k] > 0.0) || isinf(pv[k])) bad = true; pivs[4 * cb + k] = pv[k]; }
+#pragma unroll
+      for (int k = 0; k < 6; k++) buf[BLK4_L + k] = l[k];
+#pragma unroll
+      for (int k = 0; k < 4; k++) buf[BLK4_L + 6 + k] = r[k];
+      // L44 replaces d; the diagonal block of the inverse is inv(L44): substitution applied to the identity's columns
+      d[0][0] = pv[0] * r[0]; d[0][1] = 0.0; d[0][2] = 0.0; d[0][3] = 0.0;
+      d[1][0] = l[0]; d[1][1] = pv[1] * r[1]; d[1][2] = 0.0; d[1][3] = 0.0;
+      d[2][0] = l[1]; d[2][1] = l[3]; d[2][2] = pv[2] * r[2]; d[2][3] = 0.0;
+      d[3][0] = l[2]; d[3][1] = l[4]; d[3][2] = l[5]; d[3][3] = pv[3] * r[3];
+#pragma unroll
+      for (int jj = 0; jj < 4; jj++) {
+        blk4_subst_row(l, r, y[0][jj], y[1][jj], y[2][jj], y[3][jj]);
+#pragma unroll
+        for (int k = 0; k < 4; k++) buf[BLK4_Y + k * 64 + 4 * bc + jj] = y[k][jj];
+      }
+    }
+    consumer_bar();
+    if (live && (bc == cb) != (br == cb)) {
+      double l[6], r[4];
+#pragma unroll
+      for (int k = 0; k < 6; k++) l[k] = buf[BLK4_L + k];
+#pragma unroll
+      for (int k = 0; k < 4; k++) r[k] = buf[BLK4_L + 6 + k];
+      if (bc == cb) {       // panel block below the diagonal block: rows of d times inv(L44)'
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          blk4_subst_row(l, r, d[i][0], d[i][1], d[i][2], d[i][3]);
+#pragma unroll
+          for (int k = 0; k < 4; k++) buf[BLK4_P + (4 * br + i) * 4 + k] = d[i][k];
+        }
+      } else {              // block row cb of the inverse, left of the diagonal: inv(L44) times the columns of y
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+          blk4_subst_row(l, r, y[0][jj], y[1][jj], y[2][jj], y[3][jj]);
+#pragma unroll
+          for (int k = 0; k < 4; k++) buf[BLK4_Y + k * 64 + 4 * bc + jj] = y[k][jj];
+        }
+      }
+    }
+    consumer_bar();
+    if (live && br > cb) {
+      double pr[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) pr[i][k] = buf[BLK4_P + (4 * br + i) * 4 + k];
+      if (bc > cb) {        // trailing block: d -= P_br P_bc'
+        double pc[4][4];
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++)
+#pragma unroll
+          for (int k = 0; k < 4; k++) pc[jj][k] = buf[BLK4_P + (4 * bc + jj) * 4 + k];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int jj = 0; jj < 4; jj++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) d[i][jj] -= pr[i][k] * pc[jj][k];
+      } else {              // inverse block (br, bc <= cb): y -= P_br Y(cb, bc)
+        double yb[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+          for (int jj = 0; jj < 4; jj++) yb[k][jj] = buf[BLK4_Y + k * 64 + 4 * bc + jj];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int jj = 0; jj < 4; jj++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) y[i][jj] -= pr[i][k] * yb[k][jj];
+      }
+    }
   }
   // ---- write L (zeros above the diagonal) and the inverse back to shared memory ----
 #pragma unroll
@@ -425,7 +468,7 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
       int row_lo = 0;
       if (is_diag) {
         const int off = (j & 1) * TN;
-        potf2_inv(At, off, Ys, s_comm, tid, pb->logsum + j, status);
+        potf2_inv_blk4(At, off, Ys, smem + 2 * STAGE_D, s_comm + 256, tid, pb->logsum + j, status);   // scratch: stage 2, drained
         double* invd = pb->invd + (int64_t)j * INVD_BLOCK;       // stored with the padded stride: one bulk copy reloads it
         for (int idx = tid; idx < INVD_BLOCK / 2; idx += NCW * 32)
           reinterpret_cast<double2*>(invd)[idx] = reinterpret_cast<const double2*>(Ys)[idx];

@@ -1,4 +1,4 @@
-// Micro-benchmark of potf2_inv (chol.cu) on one CTA: cycles per call, and a breakdown by disabling parts.
+// Micro-benchmark of potf2_inv_blk4 (chol.cu) on one CTA: cycles per call, and a breakdown by disabling parts.
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I. scripts/micro/potf2_bench.cu -o gpurun_out/potf2_bench
 #include "../../iak3d_b200/csrc/chol.cu"
 
@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bench_kernel(const double* A, dou
     consumer_bar();
     const long long t0 = clock64();
     double ls;
-    potf2_inv(At, 0, Ys, s_comm, tid, &ls, status);
+    potf2_inv_blk4(At, 0, Ys, smem + 2 * STAGE_D, s_comm + 256, tid, &ls, status);
     consumer_bar();
     total += clock64() - t0;
     if (r == reps - 1 && tid == 0) out[64 * 64 * 2] = ls;
