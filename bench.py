@@ -342,8 +342,13 @@ def main():
         import bench_extra
         out, ctx = bench_extra.run(args, rank, local_rank, world, comm)
     if rank == 0:
-        if world == 1 and not args.no_cpu_baseline and args.workload == "s5":
-            out["cpu_baseline"] = cpu_baseline_s5(args.n)
+        if world == 1 and not args.no_cpu_baseline:
+            if args.workload == "s5":
+                out["cpu_baseline"] = cpu_baseline_s5(args.n)
+            elif args.workload == "krige":
+                out["cpu_baseline"] = bench_extra.cpu_baseline_krige(args.n)
+            else:
+                out["cpu_baseline"] = bench_extra.cpu_baseline_cl(args.n if args.n != 5000 else 200000)
         print(json.dumps(out), flush=True)
     ctx.close()
     if world > 1:

@@ -140,6 +140,57 @@ def _krige(args, rank, local_rank, world, comm):
     return out, ctx
 
 
+def cpu_baseline_krige(n, sample=2000):
+    """The oracle's predictIAK3D (setCIAK3D2 + Ckh %*% [iCX, iCz, iC], predictIAK3D.R:179-255) on a bounded sample of the
+    grid, host cores; the fit it predicts from (one nllIAK3D with rtnAll) is outside the timed region like on the GPU."""
+    import os
+    from oracle import iak3d_oracle as orc
+    from iak3d_b200 import synth
+    ds = synth.make_dataset(n, synth.SEEDS["S5"])
+    P, modelx, types, cmeOpt = synth.default_pars("edgeroi")
+    sm = orc.setupIAK3D(ds["xData"], ds["dIData"])
+    fit = orc.nllIAK3D(None, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True, sm, PARBNDS, useReml=True, rtnAll=True, parsBTfmd=P)
+    fit["xData"], fit["dIData"] = ds["xData"], ds["dIData"]
+    side = int(np.ceil(np.sqrt(1000000)))
+    xMap = synth.make_grid(side)[:sample]
+    dI = synth.GSM_INTERVALS[1:2]
+    Xfn = lambda i, idx: synth.grid_design(xMap[idx], dI[i], synth.SEEDS["P1M"])
+    orc.predictIAK3D(xMap[:200], dI, lambda i, idx: Xfn(i, idx), fit, modelx, types, cmeOpt)
+    t0 = time.perf_counter()
+    orc.predictIAK3D(xMap, dI, Xfn, fit, modelx, types, cmeOpt)
+    dt = time.perf_counter() - t0
+    return dict(value=sample / dt, unit="preds/s", cores=os.cpu_count(), kind="port",
+                sample=f"{sample} grid cells x 1 depth interval against the same n={n} fit by oracle/iak3d_oracle.predictIAK3D (NumPy/SciPy, "
+                       "OpenBLAS threads = host cores); R is not installed, so this is a port, not the R reference")
+
+
+def cpu_baseline_cl(n, npairs=3):
+    """The oracle's per-pair work of nllIAK3D_CL (setCIAK3D + Cholesky terms of one adjacent pair, compositeLikIAK3D.R:54-64)
+    on a bounded sample of the pairs, scaled to the whole evaluation by the pairs' n^3."""
+    import os
+    from oracle import iak3d_oracle as orc
+    from iak3d_b200 import synth
+    nblocks = max(4, int(round(n / 2000.0)))
+    ds = synth.make_dataset(n, synth.SEEDS["CL200"])
+    blk = synth.make_blocks(ds["xData"], ds["prof"], nblocks, synth.SEEDS["CL200"])
+    P, modelx, types, cmeOpt = synth.default_pars("edgeroi")
+    pairs = np.asarray(blk["subsetPairsAdj"]).reshape(-1, 2)
+    sizes = np.array([len(blk["listBlocks"][a]) + len(blk["listBlocks"][b]) for a, b in pairs], float)
+    pick = np.argsort(np.abs(sizes - np.median(sizes)))[:npairs]
+    dt = 0.0
+    for k in pick:
+        rows = np.concatenate([blk["listBlocks"][pairs[k][0]], blk["listBlocks"][pairs[k][1]]])
+        sm = orc.setupIAK3D(ds["xData"][rows], ds["dIData"][rows])
+        t0 = time.perf_counter()
+        orc.nllIAK3D(None, ds["zData"][rows], ds["XData"][rows], modelx, 0.5, *types, cmeOpt, True, sm, PARBNDS, useReml=False,
+                     forCompLik=True, parsBTfmd=P)
+        dt += time.perf_counter() - t0
+    est = dt * float(np.sum(sizes ** 3)) / float(np.sum(sizes[pick] ** 3))
+    return dict(value=1.0 / est, unit="evals/s", cores=os.cpu_count(), kind="port",
+                sample=f"{npairs} median-sized adjacent pairs of the {len(pairs)} (oracle/iak3d_oracle.nllIAK3D, forCompLik) timed on the host "
+                       f"cores and scaled by sum n_kl^3 to one whole evaluation ({est:.1f} s); setup of the pair datasets excluded as on the GPU")
+
+
 def run(args, rank, local_rank, world, comm):
     if args.workload == "cl":
         return _cl(args, rank, local_rank, world, comm)
