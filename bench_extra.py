@@ -99,6 +99,8 @@ def _krige(args, rank, local_rank, world, comm):
     xy = np.tile(xMap, (nd, 1))
     dI = np.repeat(synth.GSM_INTERVALS, m, axis=0)
     X = np.vstack([synth.grid_design(xMap, synth.GSM_INTERVALS[i], synth.SEEDS["P1M"]) for i in range(nd)])
+    # R matrices are column-major; hand the plugin call the layout the reference would (no transposition inside the timed call)
+    xy, dI, X = np.asfortranarray(xy), np.asfortranarray(dI), np.asfortranarray(X)
     k = fit["fit"]
     peak = ctx.fp64_peak(1)
     k.stage(xy, dI, X)

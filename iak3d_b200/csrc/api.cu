@@ -44,8 +44,11 @@ void iak_unique_first(int64_t n, const double* c0, const double* c1, std::vector
   map.reserve((size_t)std::min<int64_t>(n, 1 << 22));
   std::vector<double> u0, u1;
   id.resize((size_t)n);
+  Key2 prev{0, 0}; int32_t prev_id = -1;               // runs of equal keys (a prediction grid is ordered interval by interval)
   for (int64_t i = 0; i < n; i++) {
     const Key2 k{dbits(c0[i]), dbits(c1[i])};
+    if (prev_id >= 0 && k.a == prev.a && k.b == prev.b) { id[(size_t)i] = prev_id; continue; }
+    prev = k;
     auto it = map.find(k);
     if (it == map.end()) {
       const int32_t v = (int32_t)u0.size();
@@ -55,6 +58,7 @@ void iak_unique_first(int64_t n, const double* c0, const double* c1, std::vector
     } else {
       id[(size_t)i] = it->second;
     }
+    prev_id = id[(size_t)i];
   }
   const size_t nu = u0.size();
   U.resize(2 * nu);
