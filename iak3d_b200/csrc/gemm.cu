@@ -119,7 +119,7 @@ int run_tiles(iak3d_ctx* ctx, const ProblemDesc& pd, int nRB, int nCB, int tri =
   CUDA_TRY(ctx, d_ticket.alloc(2 * sizeof(int32_t)));
   CUDA_TRY(ctx, cudaMemcpyAsync(d_tasks.p, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(d_prob.p, &pd, sizeof(pd), cudaMemcpyHostToDevice, ctx->stream));
-  const int st = launch_tile_tasks(ctx, d_prob.as<ProblemDesc>(), d_tasks.as<int4>(), (int32_t)tasks.size(), d_ticket.as<int32_t>());
+  const int st = launch_tile_tasks(ctx, d_prob.as<ProblemDesc>(), d_tasks.as<int4>(), (int32_t)tasks.size(), d_ticket.as<int32_t>(), pd.mode);
   if (st != 0) return st;
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
