@@ -389,7 +389,7 @@ extern "C" int iak3d_predict_enqueue(iak3d_fit* f) {
     a.phix = px.has_phix ? f->d_phix : nullptr;
     a.same = f->d_same;
     a.xid_r = f->d_iota; a.did_r = f->d_did1 + r0; a.nr = rows; a.nxU_r = rows;
-    rc = launch_cov_rect(ctx, a, f->d_P, rowsP, rowsP, s->Npad, 0, /*blocked=*/1);
+    rc = launch_cov_panel(ctx, a, f->d_P, rowsP, s->Npad);
     if (rc != 0) return rc;
     rc = fit_panel_tasks(f, rowsP);
     if (rc != 0) return rc;

@@ -177,6 +177,9 @@ int launch_ckk(iak3d_ctx* ctx, const EvalPlan& pl, const double* const* d_Tself 
 // blocked != 0: d_out is a blocked buffer (uidx) with rows_total rows; otherwise plain column-major with leading dim ld
 int launch_cov_rect(iak3d_ctx* ctx, const CovArgs& a, double* d_out, int64_t ld, int64_t rows_total, int64_t cols_total,
                     int symmetric_square, int blocked = 0);
+// kriging panel: blocked output, rows = prediction supports at their own locations (xid_r[i] == i); falls back to
+// launch_cov_rect when the row count is odd
+int launch_cov_panel(iak3d_ctx* ctx, const CovArgs& a, double* d_out, int64_t rows_total, int64_t cols_total);
 
 // ---- factorisation (chol.cu) -------------------------------------------------------------------
 struct ProblemDesc {

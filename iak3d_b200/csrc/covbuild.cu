@@ -387,6 +387,69 @@ __global__ void __launch_bounds__(256) cov_rect_kernel(CovDev a, double* __restr
   }
 }
 
+// Kriging panel (blocked layout): every row is a prediction support at its own location (xid_r[i] == i), so the two
+// rows a thread owns are adjacent in the phi_x / same-location tables as well as in the output unit: 16-byte loads and one
+// 16-byte evict-first store per column.  Same term order as cov_value.  nr and a.nxU_r even (the caller checks).
+__global__ void __launch_bounds__(256) cov_panel_kernel(CovDev a, double* __restrict__ out, int64_t rows_total, int64_t cols_total) {
+  __shared__ int32_t s_xc[TN], s_dc[TN];
+  const int64_t R0 = (int64_t)blockIdx.x * TM, C0 = (int64_t)blockIdx.y * TN;
+  const int tid = threadIdx.x;
+  if (tid < TN) { const int64_t c = C0 + tid; s_xc[tid] = c < a.nc ? a.xid_c[c] : -1; s_dc[tid] = c < a.nc ? a.did_c[c] : 0; }
+  __syncthreads();
+  const uint64_t strm = policy_evict_first();
+  const int rp = tid & 63, cg = tid >> 6;
+  const int64_t i0 = R0 + rp * 2;
+  if (i0 >= rows_total) return;
+  const bool live = i0 < a.nr;                              // nr even: both rows or neither
+  const int d0 = live ? a.did_r[i0] : 0, d1 = live ? a.did_r[i0 + 1] : 0;
+  const int64_t nRU = rows_total >> 6;
+  auto pick = [&](const double (&t)[3], int k) -> double { return k == 0 ? t[0] : (k == 1 ? t[1] : (k == 2 ? t[2] : 0.0)); };
+#pragma unroll 4
+  for (int cc = 0; cc < 16; cc++) {
+    const int lc = cg * 16 + cc;
+    const int64_t c = C0 + lc;
+    if (c >= cols_total) break;
+    double v0 = 0.0, v1 = 0.0;
+    const int xj = s_xc[lc], dj = s_dc[lc];
+    if (live && xj >= 0) {
+      double ta[3], tb[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        ta[k] = (k < a.ntab) ? __ldg(a.T[k] + (int64_t)dj * a.ndIU_r + d0) : 0.0;
+        tb[k] = (k < a.ntab) ? ((d1 == d0) ? ta[k] : __ldg(a.T[k] + (int64_t)dj * a.ndIU_r + d1)) : 0.0;
+      }
+      const uchar2 sm = *reinterpret_cast<const uchar2*>(a.same + (int64_t)xj * a.nxU_r + i0);
+      if (sm.x) { v0 = v0 + a.cx0; v0 = v0 + a.cxd0 * pick(ta, a.tidx[1]); }
+      if (sm.y) { v1 = v1 + a.cx0; v1 = v1 + a.cxd0 * pick(tb, a.tidx[1]); }
+      if (a.tidx[0] >= 0) { v0 = v0 + a.kd1 * pick(ta, a.tidx[0]); v1 = v1 + a.kd1 * pick(tb, a.tidx[0]); }
+      if (a.phix != nullptr) {
+        const double2 px = __ldg(reinterpret_cast<const double2*>(a.phix + (int64_t)xj * a.nxU_r + i0));
+        v0 = v0 + a.cx1 * px.x; v0 = v0 + (a.cxd1 * px.x) * pick(ta, a.tidx[2]);
+        v1 = v1 + a.cx1 * px.y; v1 = v1 + (a.cxd1 * px.y) * pick(tb, a.tidx[2]);
+      }
+    }
+    st_stream2(out + uidx(i0, c, nRU), v0, v1, strm);
+  }
+}
+
+int launch_cov_panel(iak3d_ctx* ctx, const CovArgs& h, double* d_out, int64_t rows_total, int64_t cols_total) {
+  if ((h.nr & 1) || (h.nxU_r & 1) || h.same == nullptr) return launch_cov_rect(ctx, h, d_out, rows_total, rows_total, cols_total, 0, 1);
+  CovDev a;
+  for (int k = 0; k < 3; k++) { a.T[k] = h.T[k]; a.tidx[k] = h.tidx[k]; }
+  a.ntab = h.ntab; a.phix = h.phix; a.same = h.same;
+  a.cx0 = h.cx0; a.cx1 = h.cx1; a.kd1 = h.kd1; a.cxd0 = h.cxd0; a.cxd1 = h.cxd1; a.cme = h.cme;
+  a.xid_r = h.xid_r; a.did_r = h.did_r; a.xid_c = h.xid_c; a.did_c = h.did_c;
+  a.nr = h.nr; a.nc = h.nc; a.nxU_r = h.nxU_r; a.ndIU_r = h.ndIU_r;
+  a.comb = nullptr; a.one_table = 0; a.E = nullptr; a.ldE = 0;
+  if (rows_total == 0 || cols_total == 0) return 0;
+  dim3 grid((unsigned)((rows_total + TM - 1) / TM), (unsigned)((cols_total + TN - 1) / TN));
+  if (grid.y > 65535) { ctx->err = "cov_panel: too many column tiles"; return IAK3D_ERR_ARG; }
+  cov_panel_kernel<<<grid, 256, 0, ctx->stream>>>(a, d_out, rows_total, cols_total);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return 0;
+}
+
 int launch_cov_rect(iak3d_ctx* ctx, const CovArgs& h, double* d_out, int64_t ld, int64_t rows_total, int64_t cols_total,
                     int symmetric_square, int blocked) {
   CovDev a;

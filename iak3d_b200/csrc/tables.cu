@@ -5,6 +5,8 @@
 // index vectors (fitIAK3D.R:1038-1074).  We keep that split: these kernels do the exp / Bessel work
 // on the (small) unique sets; covbuild.cu expands by id.  This translation unit is compiled with
 // -fmad=false so that the closed forms round like the reference's operation order.
+#include <algorithm>
+
 #include "common.cuh"
 
 __global__ void iacov_table_kernel(IaPrm P, const double* __restrict__ dI1, int64_t n1,
@@ -88,6 +90,29 @@ __global__ void phix_table_kernel(HxPrm H, const double* __restrict__ x1, int64_
   }
 }
 
+// rectangular case without the 64-bit index split: blockIdx.y = location of set 2, threads run down the rows of set 1
+__global__ void __launch_bounds__(256) phix_rect_kernel(HxPrm H, const double* __restrict__ x1, int64_t n1, const double* __restrict__ x2,
+                                                        int64_t n2, int64_t j0, double* __restrict__ out, uint8_t* __restrict__ zero) {
+  __shared__ double s_rt[4 * IAK_BK_NRT];
+  const bool bessel = (H.modelx == 2 && H.half == 0);
+  if (bessel) {
+    for (int i = 1 + threadIdx.x; i < IAK_BK_NRT; i += blockDim.x) iak_besselk_table(H.nu, s_rt, i);
+    __syncthreads();
+  }
+  const double* rt = bessel ? s_rt : nullptr;
+  const int64_t j = j0 + blockIdx.y;
+  const double xj = x2[j], yj = x2[n2 + j];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n1; i += (int64_t)gridDim.x * blockDim.x) {
+    const double dx = x1[i] - xj, dy = x1[n1 + i] - yj;
+    double D = 0.0;
+    D = D + dx * dx;
+    D = D + dy * dy;
+    D = sqrt(D);
+    if (out != nullptr) out[j * n1 + i] = iak_phix(D, &H, rt);
+    if (zero != nullptr) zero[j * n1 + i] = (D == 0.0) ? 1 : 0;
+  }
+}
+
 int launch_phix_table(iak3d_ctx* ctx, const HxPrm& H, const double* d_x1, int64_t n1, const double* d_x2, int64_t n2,
                       double* d_out, uint8_t* d_zero) {
   const int64_t total = n1 * n2;
@@ -95,6 +120,16 @@ int launch_phix_table(iak3d_ctx* ctx, const HxPrm& H, const double* d_x1, int64_
   int blocks = (int)((total + 255) / 256);
   if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
   const int symmetric = (d_x1 == d_x2 && n1 == n2 && d_zero == nullptr) ? 1 : 0;
+  if (!symmetric && n1 >= 1024) {
+    const unsigned gx = (unsigned)std::min<int64_t>((n1 + 255) / 256, 64);
+    for (int64_t j0 = 0; j0 < n2; j0 += 65535) {
+      const unsigned gy = (unsigned)std::min<int64_t>(65535, n2 - j0);
+      phix_rect_kernel<<<dim3(gx, gy), 256, 0, ctx->stream>>>(H, d_x1, n1, d_x2, n2, j0, d_out, d_zero);
+      ctx->launches++;
+      CUDA_TRY(ctx, cudaGetLastError());
+    }
+    return 0;
+  }
   phix_table_kernel<<<blocks, 256, 0, ctx->stream>>>(H, d_x1, n1, d_x2, n2, d_out, d_zero, symmetric);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
