@@ -758,7 +758,7 @@ def nllIAK3D_CL(pars, zData, XData, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sd
     return dict(nll=t["nll"], pars=pars, parsBTfmd=fitted, betahat=t["betahat"], vbetahat=vbetahat, cxdhat=cxdhat, XData=XData,
                 zData=zData, XziAXz_APPROX=A, XziAXz_SUM=t["XziAXz_SUM"], n_SUM=t["n_SUM"], compLikMats=compLikMats, modelx=modelx,
                 nud=nud, sdfdType_cd1=sdfdType_cd1, sdfdType_cxd0=sdfdType_cxd0, sdfdType_cxd1=sdfdType_cxd1, cmeOpt=cmeOpt,
-                lnTfmdData=False)
+                lnTfmdData=False, sdfdKnots=compLikMats.get("sdfdKnots"))
 
 
 def cl_reduce_and_tail(S, lnd_sum, n_SUM, failed, n, p, optn, nB, useReml, comm=None, rtnTerms=False):
@@ -817,7 +817,8 @@ def cl_plan_units(compLikMats, world=1):
     return units
 
 
-def setupIAK3D_CL(xData, dIData, zData, XData, compLikMats, ctx=None, rank=0, world=1):
+def setupIAK3D_CL(xData, dIData, zData, XData, compLikMats, ctx=None, rank=0, world=1, sdfdType_cd1=0, sdfdType_cxd0=0,
+                  sdfdType_cxd1=0, sdfdKnots=None):
     """iaCovMatern.R:551-575 + the unit weights of compositeLikIAK3D.R:42-179, as a list of device datasets owned by
     this rank (see :func:`cl_plan_units`)."""
     ctx = ctx or default_context()
@@ -830,13 +831,15 @@ def setupIAK3D_CL(xData, dIData, zData, XData, compLikMats, ctx=None, rank=0, wo
             continue
         rows = u["rows"]
         W = np.column_stack([XData[rows], zData[rows]])
-        u["setup"] = SetupMats(xData[rows], dIData[rows], W=W, ctx=ctx)
+        u["setup"] = SetupMats(xData[rows], dIData[rows], W=W, ctx=ctx, sdfdType_cd1=sdfdType_cd1, sdfdType_cxd0=sdfdType_cxd0,
+                               sdfdType_cxd1=sdfdType_cxd1, sdfdKnots=sdfdKnots)
         u["n"] = len(rows)
         out.append(u)
     cl = dict(compLikMats)
     cl["units"] = out
     cl["n_units_total"] = len(units)
     cl["xData"], cl["dIData"] = xData, dIData       # lmmFit$xData, lmmFit$dIData of the block predictors
+    cl["sdfdKnots"] = sdfdKnots
     return cl
 
 

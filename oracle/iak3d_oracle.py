@@ -882,8 +882,8 @@ def gradnllIAK3D_analytic(pars, zData, XData, modelx, nud, sdfdType_cd1, sdfdTyp
 
 
 def nllIAK3D_CL(pars, zData, XData, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt,
-                prodSum, parBnds, useReml, compLikMats, xData, dIData, parsBTfmd=None, rtnTerms=False):
-    """compositeLikIAK3D.R:6-307.  ``compLikMats`` = dict(compLikOptn, listBlocks (list of 0-based
+                prodSum, parBnds, useReml, compLikMats, xData, dIData, parsBTfmd=None, rtnTerms=False, sdfdKnots=None):
+    """compositeLikIAK3D.R:6-307 (the per-unit setups of setupIAK3D_CL, iaCovMatern.R:551-575, carry the sd-function types).  ``compLikMats`` = dict(compLikOptn, listBlocks (list of 0-based
     row-index arrays), subsetPairsAdj (k x 2, 0-based), subsetPairsNonadj (k x 2, 0-based))."""
     zData = np.asarray(zData, float).reshape(-1)
     XData = np.asarray(XData, float).reshape(zData.size, -1)
@@ -893,7 +893,7 @@ def nllIAK3D_CL(pars, zData, XData, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sd
     S = np.zeros((p + 1, p + 1)); lnd = 0.0; n_SUM = 0
 
     def one(rows):
-        sm = setupIAK3D(xData[rows], dIData[rows])
+        sm = setupIAK3D(xData[rows], dIData[rows], (sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1), sdfdKnots)
         return nllIAK3D(pars, zData[rows], XData[rows], modelx, nud, sdfdType_cd1, sdfdType_cxd0,
                         sdfdType_cxd1, cmeOpt, prodSum, sm, parBnds, useReml, forCompLik=True,
                         parsBTfmd=parsBTfmd)
@@ -1180,7 +1180,8 @@ def predMatsIAK3D_CL_ByBlock(z_muhat, XData, xMap, dIMap, lmmFit, modelx, sdfdTy
         qs = np.zeros(pts.size); czs = np.zeros(pts.size); cxs = np.zeros((pts.size, p))
         for i, l in enumerate(adj):
             rows = np.concatenate([blocks[k], blocks[l]])               # :528
-            sm = setupIAK3D(np.vstack([xMap[pts], lmmFit["xData"][rows]]), np.vstack([dIMap[pts], lmmFit["dIData"][rows]]))
+            sm = setupIAK3D(np.vstack([xMap[pts], lmmFit["xData"][rows]]), np.vstack([dIMap[pts], lmmFit["dIData"][rows]]), sdfdTypes,
+                            lmmFit.get("sdfdKnots"))
             Cj, _ = setCIAK3D(lmmFit["parsBTfmd"], modelx, *sdfdTypes, cmeOpt, sm)           # :545
             if i == 0:
                 Ckk[pts] = np.diag(Cj)[:pts.size]                       # :549-551
@@ -1228,7 +1229,8 @@ def predMatsIAK3D_CLEV_ByBlock(z_muhat, XData, xMap, dIMap, lmmFit, modelx, sdfd
         for l in adj:                                                   # :651-663
             d = np.asarray(blocks[l]); datL.append(d); i2L.append(cnt + np.arange(d.size)); cnt += d.size
         rows = np.concatenate([iDatak] + datL)
-        sm = setupIAK3D(np.vstack([xMap[pts], lmmFit["xData"][rows]]), np.vstack([dIMap[pts], lmmFit["dIData"][rows]]))   # :668
+        sm = setupIAK3D(np.vstack([xMap[pts], lmmFit["xData"][rows]]), np.vstack([dIMap[pts], lmmFit["dIData"][rows]]), sdfdTypes,
+                        lmmFit.get("sdfdKnots"))                                                                        # :668
         Call, _ = setCIAK3D(lmmFit["parsBTfmd"], modelx, *sdfdTypes, cmeOpt, sm)                                          # :671
         i01 = np.concatenate([i0, i1])
         C0k = Call[np.ix_(i01, i01)]                                    # :680

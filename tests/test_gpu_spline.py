@@ -107,3 +107,29 @@ def test_fd_gradient_batch_with_spline_sd(ctx):
         assert abs(g[i] - (okw(v) - w0) / 1e-6) <= 2e-3 * max(1.0, abs(g[i]))     # differences of 1e-8-accurate values / 1e-6
     singles = [iak.nllIAK3D(v, ds["zData"], ds["XData"], **kw) for v in (pars,)]
     assert singles[0] == f0                                  # batched == single, bit for bit
+
+
+@pytest.mark.parametrize("optn,useReml", [(1, True), (2, False)])
+def test_composite_likelihood_with_spline_sd_functions(ctx, optn, useReml):
+    """setupIAK3D_CL carries the sd-function types and knots to every unit (iaCovMatern.R:551-575); the block predictors
+    (compositeLikIAK3D.R:471-798) rebuild their joined-support setups with them."""
+    label, kind, types, coefs = SPLINE_CASES[0]
+    ds = synth.make_dataset(900, 83)
+    P, modelx, types, cmeOpt = spline_case_pars(kind, types, coefs, 0.5)
+    blk = synth.make_blocks(ds["xData"], ds["prof"], 4, 83)
+    blk["compLikOptn"] = optn
+    cl = iak.setupIAK3D_CL(ds["xData"], ds["dIData"], ds["zData"], ds["XData"], blk, ctx=ctx, sdfdType_cd1=types[0], sdfdType_cxd0=types[1],
+                           sdfdType_cxd1=types[2], sdfdKnots=SPLINE_KNOTS)
+    got = iak.nllIAK3D_CL(None, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True, PARBNDS, useReml, cl, parsBTfmd=P, rtnAll=True)
+    want = orc.nllIAK3D_CL(None, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True, PARBNDS, useReml, blk, ds["xData"],
+                           ds["dIData"], parsBTfmd=P, rtnTerms=True, sdfdKnots=SPLINE_KNOTS)
+    assert abs(got["nll"] - want["nll"]) <= TOL * abs(want["nll"])
+    want["sdfdKnots"] = SPLINE_KNOTS
+    rng = np.random.default_rng(6)
+    xMap = rng.uniform(0, 100, (90, 2))
+    dIMap = synth.GSM_INTERVALS[[0, 4]]
+    Xfn = lambda i, idx: synth.grid_design(xMap[idx], dIMap[i], 3)
+    pg = iak.predictIAK3D_CL(xMap, dIMap, Xfn, got)
+    zw, vw, lw, uw = orc.predictIAK3D_CL(xMap, dIMap, Xfn, want, modelx, types, cmeOpt)
+    assert scaled_err(pg["zMap"], zw) <= TOL
+    assert scaled_err(pg["vMap"], vw) <= TOL
