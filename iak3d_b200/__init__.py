@@ -7,7 +7,7 @@ fails loudly when the library or an sm_100-class GPU is missing (there is no CPU
 from ._lib import EXPORTS, LIB_PATH, Context, Iak3dError, default_context, load  # noqa: F401
 from .api import (calcbetavXbeta, lnN_design, makeXnsClampedUG0, nrUpdatesIAK3DlnN_gram, setmuIAK3D, nrUpdatesIAK3D, nr_iterate, predictIAK3D_CL, profilePredictIAK3D, predMatsIAK3D_CL_ByBlock, predMatsIAK3D_CLEV_ByBlock, getBlocksFromLocations,  # noqa: F401
                   BADNLL, KeptFit, SetupMats, SetupMats2, cl_plan_units, cl_reduce_and_tail, gradHessIAK3D, gradnllIAK3D, iaCovMatern2, lndetANDinvCb, logitab,  # noqa: F401
-                  nll_terms_batch, nllIAK3D, nllIAK3D_CL, predictIAK3D, readParsIAK3D, reml_tail, reml_tail_batch, setCIAK3D, setCIAK3D2,
+                  nll_terms_batch, nllIAK3D, nllIAK3D_CL, gradnllIAK3D_CL, predictIAK3D, readParsIAK3D, reml_tail, reml_tail_batch, setCIAK3D, setCIAK3D2,
                   setupIAK3D, setupIAK3D2, setupIAK3D_CL, spatialCovIAK3D, tauTfm)
 from .devmat import DeviceMat, cov_mat  # noqa: F401
 from . import parallel, synth  # noqa: F401

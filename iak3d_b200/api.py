@@ -761,6 +761,24 @@ def nllIAK3D_CL(pars, zData, XData, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sd
                 lnTfmdData=False, sdfdKnots=compLikMats.get("sdfdKnots"))
 
 
+def gradnllIAK3D_CL(pars, zData, XData, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds, useReml,
+                    compLikMats, comm=None, delta=1e-6, rtn_nll=False):
+    """Forward-difference gradient of the composite likelihood (gradnllIAK3D_CL[.mc], fitIAK3D.R:1819-1911): npar + 1
+    evaluations of :func:`nllIAK3D_CL`, each one batched launch over this rank's units (the reference forks the
+    parameter sets with mclapply); NA differences become 0 (:1813)."""
+    pars = np.asarray(pars, float).reshape(-1)
+    vals = np.empty(pars.size + 1)
+    for k in range(pars.size + 1):
+        v = pars.copy()
+        if k > 0:
+            v[k - 1] += delta
+        vals[k] = nllIAK3D_CL(v, zData, XData, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds, useReml,
+                              compLikMats, comm=comm)
+    g = (vals[1:] - vals[0]) / delta
+    g[~np.isfinite(g)] = 0.0
+    return (g, vals[0]) if rtn_nll else g
+
+
 def cl_reduce_and_tail(S, lnd_sum, n_SUM, failed, n, p, optn, nB, useReml, comm=None, rtnTerms=False):
     """The exchange step of the composite likelihood -- Reduce('+') over the workers, compositeLikIAK3D.R:63-64 -- as
     one all-reduce of (p+1)^2 + 3 doubles, then the closed-form tail (:181-265) on every rank."""

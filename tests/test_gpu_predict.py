@@ -176,6 +176,24 @@ def test_clev_block_prediction_vs_oracle(ctx, optn, kind, nonstat, nblocks):
     assert scaled_err(pg["pi90UMap"], uw) <= TOL
 
 
+def test_cl_forward_difference_gradient_vs_oracle(ctx):
+    """gradnllIAK3D_CL (fitIAK3D.R:1819-1911): npar + 1 composite-likelihood evaluations, NA -> 0."""
+    ds = synth.make_dataset(700, 67)
+    blk = synth.make_blocks(ds["xData"], ds["prof"], 4, 67)
+    blk["compLikOptn"] = 1
+    modelx, types, cmeOpt = "matern", (0, 0, 0), 1
+    cl = iak.setupIAK3D_CL(ds["xData"], ds["dIData"], ds["zData"], ds["XData"], blk, ctx=ctx)
+    p0 = np.array([0.2, -1.3, 0.1, -2.2, -1.4, -1.9, 0.4, -3.0])
+    g, f0 = iak.gradnllIAK3D_CL(p0, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True, PARBNDS, True, cl, rtn_nll=True)
+    fw = lambda v: orc.nllIAK3D_CL(v, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True, PARBNDS, True, blk, ds["xData"],
+                                   ds["dIData"])
+    w0 = fw(p0)
+    assert abs(f0 - w0) <= TOL * abs(w0)
+    gw = np.array([(fw(p0 + 1e-6 * np.eye(len(p0))[k]) - w0) / 1e-6 for k in range(len(p0))])
+    # forward differences of values that agree to ~1e-12 relative: compare at the noise floor of the difference
+    assert np.max(np.abs(g - gw)) <= 2e-2 * max(1.0, np.max(np.abs(gw)))
+
+
 def test_profilePredict_vs_oracle(ctx):
     """profilePredictIAK3D (predictIAK3D.R:292-504): one location, a full profile of depth intervals, incl. Ckh and iC."""
     ds = synth.make_dataset(450, 27)
