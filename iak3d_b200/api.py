@@ -671,7 +671,21 @@ def gradnllIAK3D(pars, zData, XData, vXU=None, iU=None, modelx="matern", nud=0.5
     differences are taken on the covariance ENTRIES, not on the likelihood, so no factorisation noise enters.
     `analytic="auto"` picks it from n = 4000 on, where it is faster than the batch."""
     if lnTfmdData:
-        raise NotImplementedError("lnTfmdData = TRUE is not on the accelerated path")
+        # nothing is profiled in lognormal mode (fitIAK3D.R:147-155): every candidate is a full nllIAK3D with its own
+        # Newton-Raphson for beta -- one bordered factorisation each.  The values are the reference's (rounded to 1e-5,
+        # :160-161), and so is the difference quotient.
+        pars = np.asarray(pars, float).reshape(-1)
+        vals = np.empty(pars.size + 1)
+        for k in range(pars.size + 1):
+            v = pars.copy()
+            if k > 0:
+                v[k - 1] += delta
+            vals[k] = nllIAK3D(v, zData, XData, vXU=vXU, iU=iU, modelx=modelx, nud=nud, sdfdType_cd1=sdfdType_cd1,
+                               sdfdType_cxd0=sdfdType_cxd0, sdfdType_cxd1=sdfdType_cxd1, cmeOpt=cmeOpt, prodSum=prodSum,
+                               setupMats=setupMats, parBnds=parBnds, useReml=useReml, lnTfmdData=True)
+        g = (vals[1:] - vals[0]) / delta
+        g[~np.isfinite(g)] = 0.0
+        return (g, vals[0]) if rtn_nll else g
     sm = setupMats
     pars = np.asarray(pars, float).reshape(-1)
     zData = np.asarray(zData, float).reshape(-1)

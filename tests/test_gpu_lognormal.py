@@ -79,3 +79,21 @@ def test_lognormal_predictions(ctx, pU, backtransform):
     assert scaled_err(pg["pi90LMap"], lw) <= 1e-7 and scaled_err(pg["pi90UMap"], uw) <= 1e-7
     if backtransform:
         assert np.all(pg["zMap"] > 0)
+
+
+def test_lognormal_forward_difference_gradient(ctx):
+    """gradnllIAK3D with lnTfmdData = TRUE (fitIAK3D.R:1865-1886): nothing is profiled, every candidate is a full
+    evaluation with its own Newton-Raphson; values (and therefore the quotient) live on the reference's 1e-5 grid."""
+    ds, z, iU, vXU = lognormal_case(300, 9, pU=2)
+    p0 = np.array([0.2, -1.3, 0.1, -1.5, -1.2, -1.9, -0.8, -1.0, -2.5])
+    sm = iak.setupIAK3D(ds["xData"], ds["dIData"], ctx=ctx)
+    kw = dict(vXU=vXU, iU=iU, modelx="matern", nud=0.5, cmeOpt=1, prodSum=True, setupMats=sm, parBnds=PARBNDS, useReml=False, lnTfmdData=True)
+    g, f0 = iak.gradnllIAK3D(p0, z, ds["XData"], rtn_nll=True, **kw)
+    osm = orc.setupIAK3D(ds["xData"], ds["dIData"])
+    fw = lambda v: orc.nllIAK3D_lnN(v, z, ds["XData"], vXU, iU, "matern", 0.5, 0, 0, 0, 1, True, osm, PARBNDS)
+    w0 = fw(p0)
+    assert abs(f0 - w0) <= 1.01e-5
+    gw = np.array([(fw(p0 + 1e-6 * np.eye(len(p0))[k]) - w0) / 1e-6 for k in range(len(p0))])
+    assert np.all(np.isfinite(g))
+    # both quotients are differences of values rounded to 1e-5, divided by 1e-6: they can differ by one grid step (10)
+    assert np.max(np.abs(g - gw)) <= 10.0 + 1e-6
