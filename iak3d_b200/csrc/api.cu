@@ -231,6 +231,33 @@ extern "C" int iak3d_ctx_destroy(iak3d_ctx* ctx) {
   return IAK3D_OK;
 }
 
+cudaError_t iak_pool_alloc(iak3d_ctx* ctx, void** p, size_t bytes) {
+  static int configured_device = -1;
+  if (configured_device != ctx->device) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    configured_device = ctx->device;
+  }
+  return cudaMallocAsync(p, std::max<size_t>(bytes, 16), ctx->stream);
+}
+void iak_pool_free(iak3d_ctx* ctx, void* p) {
+  if (p) cudaFreeAsync(p, ctx->stream);
+}
+cudaError_t iak_malloc(iak3d_ctx* ctx, void** p, size_t bytes) {
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    e = cudaMalloc(p, bytes);
+  }
+  return e;
+}
+
 extern "C" const char* iak3d_last_error(iak3d_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 extern "C" int iak3d_device_info(iak3d_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, int64_t* total_mem) {
@@ -263,7 +290,7 @@ int iak_alloc_slot(iak3d_ctx* ctx, int64_t n, int32_t q, int64_t nxU, int64_t nd
   s->ld = round_up(s->Npad + q, TM);
   s->nCB = (int32_t)(s->Npad / TN); s->nRB = (int32_t)(s->ld / TM);
   cudaError_t e = cudaSuccess;
-  auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, std::max<size_t>(bytes, 16)); };
+  auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = iak_malloc(ctx, p, std::max<size_t>(bytes, 16)); };
   if (!tables_only) A((void**)&s->d_L, (size_t)ubuf_doubles(s->ld, s->Npad) * sizeof(double));
   A((void**)&s->d_phix, (size_t)nxU * nxU * sizeof(double));
   // tables | avVar vectors | avsd vectors | (16-byte aligned) combined tables of the factor build

@@ -213,7 +213,7 @@ static int fit_reserve_panel(iak3d_fit* f, int64_t rows, int64_t nd1) {
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(f->d_P); cudaFree(f->d_G); cudaFree(f->d_pflags); cudaFree(f->d_phix); cudaFree(f->d_same); cudaFree(f->d_iota);
     f->d_P = f->d_G = f->d_phix = nullptr; f->d_pflags = nullptr; f->d_same = nullptr; f->d_iota = nullptr; f->ldP = 0;
-    CUDA_TRY(ctx, cudaMalloc(&f->d_P, (size_t)ubuf_doubles(ldP, s->Npad) * 8));
+    CUDA_TRY(ctx, iak_malloc(ctx, (void**)&f->d_P, (size_t)ubuf_doubles(ldP, s->Npad) * 8));
     CUDA_TRY(ctx, cudaMalloc(&f->d_G, (size_t)ldP * (f->q + 1) * 8));
     const size_t nfl = (size_t)(ldP / TM) * s->nCB;
     CUDA_TRY(ctx, cudaMalloc(&f->d_pflags, nfl * 4));

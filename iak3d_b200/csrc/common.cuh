@@ -125,6 +125,15 @@ struct EvalPlan {
     }                                                                                         \
   } while (0)
 
+// ---- stream-ordered scratch memory (api.cu) ----
+// Temporaries that come and go with every call (task lists, partial sums, device matrices): cudaMallocAsync on the
+// context's stream from the device's default pool, kept cached, so that neither allocation nor release synchronises.
+cudaError_t iak_pool_alloc(iak3d_ctx* ctx, void** p, size_t bytes);
+void iak_pool_free(iak3d_ctx* ctx, void* p);
+// cudaMalloc for the long-lived buffers; when it fails the cached scratch pool is handed back to the driver and the
+// allocation retried once
+cudaError_t iak_malloc(iak3d_ctx* ctx, void** p, size_t bytes);
+
 // ---- table kernels (tables.cu) ----------------------------------------------------------------
 int launch_iacov_table(iak3d_ctx* ctx, const IaPrm& P, const double* d_dI1, int64_t n1, const double* d_dI2,
                        int64_t n2, double* d_out /* n1 x n2 col-major: out[j*n1+i] */, double* d_avvar1);

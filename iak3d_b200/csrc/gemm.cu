@@ -93,10 +93,11 @@ __global__ void __launch_bounds__(256) trace_pair_kernel(const double* __restric
   if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
 }
 
-struct DevBuf {
+struct DevBuf {                       // stream-ordered scratch (iak_pool_alloc); a kept buffer (ctx == nullptr) is not released
   void* p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
-  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 16)); }
+  iak3d_ctx* ctx = nullptr;
+  ~DevBuf() { if (p && ctx) iak_pool_free(ctx, p); }
+  cudaError_t alloc(iak3d_ctx* c, size_t bytes) { ctx = c; return iak_pool_alloc(c, &p, bytes); }
   template <class T> T* as() { return (T*)p; }
 };
 
@@ -114,9 +115,9 @@ int run_tiles(iak3d_ctx* ctx, const ProblemDesc& pd, int nRB, int nCB, int tri =
       tasks.push_back(make_int4(0, r, j, tri ? r * (TM / UC) : 0));
     }
   DevBuf d_tasks, d_prob, d_ticket;
-  CUDA_TRY(ctx, d_tasks.alloc(tasks.size() * sizeof(int4)));
-  CUDA_TRY(ctx, d_prob.alloc(sizeof(ProblemDesc)));
-  CUDA_TRY(ctx, d_ticket.alloc(2 * sizeof(int32_t)));
+  CUDA_TRY(ctx, d_tasks.alloc(ctx, tasks.size() * sizeof(int4)));
+  CUDA_TRY(ctx, d_prob.alloc(ctx, sizeof(ProblemDesc)));
+  CUDA_TRY(ctx, d_ticket.alloc(ctx, 2 * sizeof(int32_t)));
   CUDA_TRY(ctx, cudaMemcpyAsync(d_tasks.p, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(d_prob.p, &pd, sizeof(pd), cudaMemcpyHostToDevice, ctx->stream));
   const int st = launch_tile_tasks(ctx, d_prob.as<ProblemDesc>(), d_tasks.as<int4>(), (int32_t)tasks.size(), d_ticket.as<int32_t>(), pd.mode);
@@ -191,12 +192,12 @@ int launch_panel_product(iak3d_ctx* ctx, const double* d_M, int64_t nRU, int64_t
   if (n == 0 || q == 0) return 0;
   const int nchunk = (int)((n + PP_CH - 1) / PP_CH);
   double* d_part = nullptr;
-  if (cudaMalloc(&d_part, (size_t)nchunk * q * n * sizeof(double)) != cudaSuccess) { ctx->err = "panel product: allocation failed"; cudaGetLastError(); return IAK3D_ERR_CUDA; }
+  if (iak_pool_alloc(ctx, (void**)&d_part, (size_t)nchunk * q * n * sizeof(double)) != cudaSuccess) { ctx->err = "panel product: allocation failed"; cudaGetLastError(); return IAK3D_ERR_CUDA; }
   panel_product_kernel<<<dim3((unsigned)((n + 127) / 128), (unsigned)nchunk), 128, (size_t)PP_CH * q * sizeof(double), ctx->stream>>>(d_M, nRU, n, d_W, q, d_part);
   panel_reduce_kernel<<<(unsigned)(((int64_t)n * q + 255) / 256), 256, 0, ctx->stream>>>(d_part, nchunk, (int64_t)n * q, d_out);
   ctx->launches += 2;
   const cudaError_t e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_part);
+  iak_pool_free(ctx, d_part);
   CUDA_TRY(ctx, e);
   return 0;
 }
@@ -210,12 +211,12 @@ int iak_inverse_blocked(iak3d_ctx* ctx, Slot* s, double** out, int64_t* rowsU_ou
   DevBuf U, G, flags, status;
   double* iC = iC_keep;
   if (U_keep != nullptr) { U.p = U_keep; }
-  else CUDA_TRY(ctx, U.alloc(bytes));
+  else CUDA_TRY(ctx, U.alloc(ctx, bytes));
   struct Release { DevBuf& b; bool keep; ~Release() { if (keep) b.p = nullptr; } } rel{U, U_keep != nullptr};
-  CUDA_TRY(ctx, G.alloc((size_t)rowsU * sizeof(double)));
+  CUDA_TRY(ctx, G.alloc(ctx, (size_t)rowsU * sizeof(double)));
   const size_t nfl = (size_t)(rowsU / TM) * s->nCB;
-  CUDA_TRY(ctx, flags.alloc(nfl * sizeof(int32_t)));
-  CUDA_TRY(ctx, status.alloc(2 * sizeof(int32_t)));
+  CUDA_TRY(ctx, flags.alloc(ctx, nfl * sizeof(int32_t)));
+  CUDA_TRY(ctx, status.alloc(ctx, 2 * sizeof(int32_t)));
   CUDA_TRY(ctx, cudaMemsetAsync(flags.p, 0, nfl * sizeof(int32_t), ctx->stream));
   CUDA_TRY(ctx, cudaMemsetAsync(status.p, 0, 2 * sizeof(int32_t), ctx->stream));
   {
@@ -235,7 +236,7 @@ int iak_inverse_blocked(iak3d_ctx* ctx, Slot* s, double** out, int64_t* rowsU_ou
   int rc = run_tiles(ctx, pd, pd.nRB, pd.nCB, 1);
   if (rc != 0) return rc;
   // iC = U U': lower triangle only, K from the row block on (n^3/3 flops instead of 2 n^3), then mirrored
-  if (iC == nullptr && cudaMalloc(&iC, bytes) != cudaSuccess) { ctx->err = "inverse: allocation failed"; cudaGetLastError(); return IAK3D_ERR_CUDA; }
+  if (iC == nullptr && iak_malloc(ctx, (void**)&iC, bytes) != cudaSuccess) { ctx->err = "inverse: allocation failed"; cudaGetLastError(); return IAK3D_ERR_CUDA; }
   rc = gemm_nt(ctx, U.as<double>(), rowsU, U.as<double>(), rowsU, iC, rowsU, Npad, Npad, 1.0, 0, status.as<int32_t>(), 2);
   if (rc != 0) { if (iC_keep == nullptr) cudaFree(iC); return rc; }
   {
@@ -350,19 +351,19 @@ extern "C" int iak3d_gradhess(iak3d_ds* ds, const iak3d_pars* pars, int32_t ncom
     const size_t mbytes = (size_t)ubuf_doubles(rowsU, Npad) * sizeof(double);
     DevBuf dA1, dB1, pA, pB, dTz, dz, du, dv, dr, dpart, dstatus, dC;
     const size_t pbytes = (size_t)ubuf_doubles(rowsU, TN) * sizeof(double);     // rowsU x 64 panel (K = 32 uses the first unit column)
-    cudaError_t e = dA1.alloc((size_t)n * p * 8);
-    if (e == cudaSuccess) e = dB1.alloc((size_t)n * p * 8);
-    if (e == cudaSuccess) e = pA.alloc(pbytes);
-    if (e == cudaSuccess) e = pB.alloc(pbytes);
-    if (e == cudaSuccess) e = dTz.alloc((size_t)n * 8);
-    if (e == cudaSuccess) e = dz.alloc((size_t)n * 8);
-    if (e == cudaSuccess) e = du.alloc((size_t)n * 8);
-    if (e == cudaSuccess) e = dv.alloc((size_t)n * 8);
-    if (e == cudaSuccess) e = dr.alloc((size_t)n * 8);
+    cudaError_t e = dA1.alloc(ctx, (size_t)n * p * 8);
+    if (e == cudaSuccess) e = dB1.alloc(ctx, (size_t)n * p * 8);
+    if (e == cudaSuccess) e = pA.alloc(ctx, pbytes);
+    if (e == cudaSuccess) e = pB.alloc(ctx, pbytes);
+    if (e == cudaSuccess) e = dTz.alloc(ctx, (size_t)n * 8);
+    if (e == cudaSuccess) e = dz.alloc(ctx, (size_t)n * 8);
+    if (e == cudaSuccess) e = du.alloc(ctx, (size_t)n * 8);
+    if (e == cudaSuccess) e = dv.alloc(ctx, (size_t)n * 8);
+    if (e == cudaSuccess) e = dr.alloc(ctx, (size_t)n * 8);
     const int nblk = (int)((n + 31) / 32);
-    if (e == cudaSuccess) e = dpart.alloc((size_t)nblk * 8);
-    if (e == cudaSuccess) e = dstatus.alloc(2 * sizeof(int32_t));
-    if (e == cudaSuccess) e = dC.alloc(mbytes);
+    if (e == cudaSuccess) e = dpart.alloc(ctx, (size_t)nblk * 8);
+    if (e == cudaSuccess) e = dstatus.alloc(ctx, 2 * sizeof(int32_t));
+    if (e == cudaSuccess) e = dC.alloc(ctx, mbytes);
     if (e != cudaSuccess) { ctx->err = std::string("gradhess: allocation failed: ") + cudaGetErrorString(e); cudaGetLastError(); rc = IAK3D_ERR_CUDA; break; }
     cudaMemsetAsync(dstatus.p, 0, 2 * sizeof(int32_t), ctx->stream);
     cudaMemcpyAsync(dA1.p, A1.data(), (size_t)n * p * 8, cudaMemcpyHostToDevice, ctx->stream);
@@ -397,7 +398,7 @@ extern "C" int iak3d_gradhess(iak3d_ds* ds, const iak3d_pars* pars, int32_t ncom
       matvec_rows_kernel<<<rb, 128, 0, ctx->stream>>>(dC.as<double>(), nRU, n, dTz.as<double>(), du.as<double>());
       ctx->launches++;
       cudaMemcpyAsync(hu.data(), du.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
-      if (cudaMalloc(&Mi[i], mbytes) != cudaSuccess) { ctx->err = "gradhess: allocation failed (M_i)"; cudaGetLastError(); rc = IAK3D_ERR_CUDA; break; }
+      if (iak_malloc(ctx, (void**)&Mi[i], mbytes) != cudaSuccess) { ctx->err = "gradhess: allocation failed (M_i)"; cudaGetLastError(); rc = IAK3D_ERR_CUDA; break; }
       rc = gemm_nt(ctx, T, rowsU, dC.as<double>(), rowsU, Mi[i], rowsU, Npad, Npad, 1.0, 0, dstatus.as<int32_t>());
       if (rc != 0) break;
       double t = 0.0;

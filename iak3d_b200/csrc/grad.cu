@@ -201,8 +201,8 @@ extern "C" int iak3d_nll_grad(iak3d_ds* ds, int32_t npar, const iak3d_pars* pars
     if (ds->grad_bytes != bytes) {
       CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
       cudaFree(ds->d_gradU); cudaFree(ds->d_gradiC); ds->d_gradU = ds->d_gradiC = nullptr; ds->grad_bytes = 0;
-      CUDA_TRY(ctx, cudaMalloc(&ds->d_gradU, bytes));
-      CUDA_TRY(ctx, cudaMalloc(&ds->d_gradiC, bytes));
+      CUDA_TRY(ctx, iak_malloc(ctx, (void**)&ds->d_gradU, bytes));
+      CUDA_TRY(ctx, iak_malloc(ctx, (void**)&ds->d_gradiC, bytes));
       ds->grad_bytes = bytes;
     }
   }
@@ -213,13 +213,13 @@ extern "C" int iak3d_nll_grad(iak3d_ds* ds, int32_t npar, const iak3d_pars* pars
   // ---- A^-1 W = iC W: one pass over the inverse instead of a block back-substitution ----
   std::vector<double> iAW((size_t)n * q);
   double* d_iAW = nullptr;
-  if (cudaMalloc(&d_iAW, (size_t)n * q * 8) != cudaSuccess) { ctx->err = "nll_grad: allocation failed"; cudaGetLastError(); return IAK3D_ERR_CUDA; }
+  if (iak_pool_alloc(ctx, (void**)&d_iAW, (size_t)n * q * 8) != cudaSuccess) { ctx->err = "nll_grad: allocation failed"; cudaGetLastError(); return IAK3D_ERR_CUDA; }
   rc = launch_panel_product(ctx, iCb, rowsU / UR, n, ds->d_W, q, d_iAW);
   if (rc == 0) {
     cudaMemcpyAsync(iAW.data(), d_iAW, (size_t)n * q * 8, cudaMemcpyDeviceToHost, ctx->stream);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "nll_grad: product failed"; rc = IAK3D_ERR_CUDA; }
   }
-  cudaFree(d_iAW);
+  iak_pool_free(ctx, d_iAW);
   if (rc != 0) return rc;
   // ---- p x p algebra on the host: betahat, cxdhat, Z = (A^-1 X) chol(M)^-T, u = A^-1 z - (A^-1 X) betahat ----
   std::vector<double> M((size_t)p * p), Lm((size_t)p * p), b((size_t)p), beta((size_t)p);
@@ -292,8 +292,8 @@ extern "C" int iak3d_nll_grad(iak3d_ds* ds, int32_t npar, const iak3d_pars* pars
   for (int c = 0; c < nCB; c++) tiles += nRB - c / 2;
   do {
     if (g.nset <= 1) break;
-    if (cudaMalloc(&dZt, Zt.size() * 8) != cudaSuccess || cudaMalloc(&du, (size_t)n * 8) != cudaSuccess ||
-        cudaMalloc(&dpart, (size_t)tiles * (GR_MAXSET - 1) * 8) != cudaSuccess) { ctx->err = "nll_grad: allocation failed"; rc = IAK3D_ERR_CUDA; cudaGetLastError(); break; }
+    if (iak_pool_alloc(ctx, (void**)&dZt, Zt.size() * 8) != cudaSuccess || iak_pool_alloc(ctx, (void**)&du, (size_t)n * 8) != cudaSuccess ||
+        iak_pool_alloc(ctx, (void**)&dpart, (size_t)tiles * (GR_MAXSET - 1) * 8) != cudaSuccess) { ctx->err = "nll_grad: allocation failed"; rc = IAK3D_ERR_CUDA; cudaGetLastError(); break; }
     cudaMemcpyAsync(dZt, Zt.data(), Zt.size() * 8, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(du, u.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
     g.xid = ds->d_xid; g.did = ds->d_did; g.n = n; g.nd = ds->ndIU; g.nx = ds->nxU;
@@ -311,7 +311,7 @@ extern "C" int iak3d_nll_grad(iak3d_ds* ds, int32_t npar, const iak3d_pars* pars
     }
   } while (0);
   const auto t6 = tnow();
-  cudaFree(dZt); cudaFree(du); cudaFree(dpart);
+  iak_pool_free(ctx, dZt); iak_pool_free(ctx, du); iak_pool_free(ctx, dpart);
   if (prof) fprintf(stderr, "[gradprof] n=%lld: tables %.2f, build+factorise %.2f, inverse %.2f, iC W + host algebra %.2f, pass %.2f, free %.2f ms\n",
                     (long long)n, ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t5, t6), ms(t6, tnow()));
   return rc;

@@ -108,21 +108,6 @@ __global__ void mat_coldot_kernel(const double* __restrict__ A, int64_t nRUa, co
   if (lane == 0) out[j] = s;
 }
 
-// Matrices come and go by the hundred per prediction block: stream-ordered allocation from the device's default pool,
-// kept cached (no release at synchronisation points), so that create / destroy neither synchronise nor reach the driver.
-cudaError_t pool_alloc(iak3d_ctx* ctx, void** p, size_t bytes) {
-  static int configured_device = -1;
-  if (configured_device != ctx->device) {
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
-      uint64_t keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    configured_device = ctx->device;
-  }
-  return cudaMallocAsync(p, bytes, ctx->stream);
-}
-
 bool in_range(const iak3d_mat* M, int64_t r0, int64_t c0, int64_t nr, int64_t nc) {
   return r0 >= 0 && c0 >= 0 && nr >= 0 && nc >= 0 && r0 + nr <= M->rows && c0 + nc <= M->cols;
 }
@@ -135,13 +120,13 @@ extern "C" int iak3d_mat_create(iak3d_ctx* ctx, int64_t rows, int64_t cols, iak3
   iak3d_mat* M = new iak3d_mat();
   M->ctx = ctx; M->rows = rows; M->cols = cols;
   M->prow = round_up(rows, TM); M->pcol = round_up(cols, TN);
-  if (pool_alloc(ctx, (void**)&M->d, M->bytes()) != cudaSuccess) {
+  if (iak_pool_alloc(ctx, (void**)&M->d, M->bytes()) != cudaSuccess) {
     cudaGetLastError(); delete M;
     ctx->err = "mat_create: allocation failed";
     return IAK3D_ERR_CUDA;
   }
   const cudaError_t e = cudaMemsetAsync(M->d, 0, M->bytes(), ctx->stream);
-  if (e != cudaSuccess) { cudaFreeAsync(M->d, ctx->stream); delete M; ctx->err = std::string("mat_create: ") + cudaGetErrorString(e); return IAK3D_ERR_CUDA; }
+  if (e != cudaSuccess) { iak_pool_free(ctx, M->d); delete M; ctx->err = std::string("mat_create: ") + cudaGetErrorString(e); return IAK3D_ERR_CUDA; }
   *out = M;
   return IAK3D_OK;
 }
@@ -149,7 +134,7 @@ extern "C" int iak3d_mat_create(iak3d_ctx* ctx, int64_t rows, int64_t cols, iak3
 extern "C" int iak3d_mat_destroy(iak3d_mat* M) {
   if (!M) return IAK3D_OK;
   cudaSetDevice(M->ctx->device);
-  cudaFreeAsync(M->d, M->ctx->stream);          // stream-ordered: pending kernels on the stream finish first
+  iak_pool_free(M->ctx, M->d);                  // stream-ordered: pending kernels on the stream finish first
   delete M;
   return IAK3D_OK;
 }
@@ -180,7 +165,7 @@ extern "C" int iak3d_mat_set(iak3d_mat* M, int64_t r0, int64_t c0, int64_t nr, i
   if (nr == 0 || nc == 0) return IAK3D_OK;
   cudaSetDevice(ctx->device);
   double* stage = nullptr;
-  if (cudaMalloc(&stage, (size_t)nr * nc * 8) != cudaSuccess) { cudaGetLastError(); ctx->err = "mat_set: allocation failed"; return IAK3D_ERR_CUDA; }
+  if (iak_pool_alloc(ctx, (void**)&stage, (size_t)nr * nc * 8) != cudaSuccess) { cudaGetLastError(); ctx->err = "mat_set: allocation failed"; return IAK3D_ERR_CUDA; }
   cudaError_t e = cudaMemcpy2DAsync(stage, (size_t)nr * 8, src, (size_t)ld * 8, (size_t)nr * 8, (size_t)nc, cudaMemcpyHostToDevice, ctx->stream);
   for (int64_t j0 = 0; j0 < nc && e == cudaSuccess; j0 += 65535) {
     const int64_t ncj = std::min<int64_t>(65535, nc - j0);
@@ -190,7 +175,7 @@ extern "C" int iak3d_mat_set(iak3d_mat* M, int64_t r0, int64_t c0, int64_t nr, i
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(stage);
+  iak_pool_free(ctx, stage);
   CUDA_TRY(ctx, e);
   return IAK3D_OK;
 }
@@ -202,7 +187,7 @@ extern "C" int iak3d_mat_get(const iak3d_mat* M, int64_t r0, int64_t c0, int64_t
   if (nr == 0 || nc == 0) return IAK3D_OK;
   cudaSetDevice(ctx->device);
   double* stage = nullptr;
-  if (cudaMalloc(&stage, (size_t)nr * nc * 8) != cudaSuccess) { cudaGetLastError(); ctx->err = "mat_get: allocation failed"; return IAK3D_ERR_CUDA; }
+  if (iak_pool_alloc(ctx, (void**)&stage, (size_t)nr * nc * 8) != cudaSuccess) { cudaGetLastError(); ctx->err = "mat_get: allocation failed"; return IAK3D_ERR_CUDA; }
   cudaError_t e = cudaSuccess;
   for (int64_t j0 = 0; j0 < nc && e == cudaSuccess; j0 += 65535) {
     const int64_t ncj = std::min<int64_t>(65535, nc - j0);
@@ -214,7 +199,7 @@ extern "C" int iak3d_mat_get(const iak3d_mat* M, int64_t r0, int64_t c0, int64_t
   if (e == cudaSuccess)
     e = cudaMemcpy2DAsync(dst, (size_t)ld * 8, stage, (size_t)nr * 8, (size_t)nr * 8, (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(stage);
+  iak_pool_free(ctx, stage);
   CUDA_TRY(ctx, e);
   return IAK3D_OK;
 }
@@ -247,12 +232,12 @@ extern "C" int iak3d_mat_gemm_nt(iak3d_mat* Cm, double alpha, const iak3d_mat* A
   if (Cm == A || Cm == B) { ctx->err = "mat_gemm_nt: the result must not alias an operand"; return IAK3D_ERR_ARG; }
   cudaSetDevice(ctx->device);
   int32_t* d_status = nullptr;
-  if (cudaMalloc(&d_status, 2 * sizeof(int32_t)) != cudaSuccess) { cudaGetLastError(); ctx->err = "mat_gemm_nt: allocation failed"; return IAK3D_ERR_CUDA; }
+  if (iak_pool_alloc(ctx, (void**)&d_status, 2 * sizeof(int32_t)) != cudaSuccess) { cudaGetLastError(); ctx->err = "mat_gemm_nt: allocation failed"; return IAK3D_ERR_CUDA; }
   cudaMemsetAsync(d_status, 0, 2 * sizeof(int32_t), ctx->stream);
   int rc = iak_gemm_nt(ctx, A->d, A->prow, B->d, B->prow, Cm->d, Cm->prow, Cm->pcol, A->pcol, alpha, accumulate ? 1 : 0, d_status);
   int32_t hs[2] = {0, 0};
   if (rc == 0 && cudaMemcpy(hs, d_status, sizeof(hs), cudaMemcpyDeviceToHost) != cudaSuccess) { ctx->err = "mat_gemm_nt: status copy failed"; rc = IAK3D_ERR_CUDA; }
-  cudaFree(d_status);
+  iak_pool_free(ctx, d_status);
   if (rc == 0 && hs[1] != 0) { ctx->err = "mat_gemm_nt: wait timed out (internal error)"; rc = IAK3D_ERR_TIMEOUT; }
   return rc;
 }
@@ -320,13 +305,13 @@ extern "C" int iak3d_mat_coldot(const iak3d_mat* A, const iak3d_mat* B, double* 
   if (A->rows != B->rows || A->cols != B->cols) { ctx->err = "mat_coldot: shapes differ"; return IAK3D_ERR_ARG; }
   cudaSetDevice(ctx->device);
   double* d_out = nullptr;
-  if (cudaMalloc(&d_out, (size_t)A->cols * 8) != cudaSuccess) { cudaGetLastError(); ctx->err = "mat_coldot: allocation failed"; return IAK3D_ERR_CUDA; }
+  if (iak_pool_alloc(ctx, (void**)&d_out, (size_t)A->cols * 8) != cudaSuccess) { cudaGetLastError(); ctx->err = "mat_coldot: allocation failed"; return IAK3D_ERR_CUDA; }
   mat_coldot_kernel<<<(unsigned)((A->cols * 32 + 255) / 256), 256, 0, ctx->stream>>>(A->d, A->nRU(), B->d, B->nRU(), A->rows, A->cols, d_out);
   ctx->launches++;
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)A->cols * 8, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_out);
+  iak_pool_free(ctx, d_out);
   CUDA_TRY(ctx, e);
   return IAK3D_OK;
 }

@@ -241,7 +241,7 @@ gradnllIAK3D <- function(pars, zData, XData, vXU, iU, modelx, nud, sdfdType_cd1,
 gradnllIAK3D.mc <- gradnllIAK3D
 
 ### the same gradient by ONE factorisation + explicit inverse + one pass over it (iak3d_nll_grad; not in the reference).
-### Faster than the batch from n ~ 4000 on (B200: 1.2x at 5000, 2.6x at 20000); pass as `gr` to optimIt in place of gradnllIAK3D.
+### Faster than the batch from n ~ 4000 on (B200: 1.7x at 5000, 2.8x at 20000); pass as `gr` to optimIt in place of gradnllIAK3D.
 gradnllIAK3D_analytic <- function(pars, zData, XData, vXU, iU, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum,
                                   setupMats, parBnds, useReml, lnTfmdData, ...){
   XData <- as.matrix(XData) ; delta <- 1E-6
