@@ -213,7 +213,8 @@ struct ProblemDesc {
 };
 int chol_configure(iak3d_ctx* ctx);
 int launch_tile_tasks(iak3d_ctx* ctx, const ProblemDesc* d_problems, const int4* d_tasks, int32_t ntasks, int32_t* d_ticket /* 2 ints */,
-                      int mode /* the mode of every problem of the launch */);
+                      int mode /* the mode of every problem of the launch */,
+                      int latency_bound = 0 /* one factorisation alone: use the look-ahead diagonal-block kernel */);
 int launch_finish(iak3d_ctx* ctx, const ProblemDesc* d_problems, int32_t count, double* d_results, int32_t stride);
 // X = L^-T Y for the q bordered rows of a finished blocked factor; d_X: Npad x q column-major out
 int launch_backsolve(iak3d_ctx* ctx, const double* d_L, int64_t nRU, int64_t Npad, const double* d_invd, int32_t q, double* d_X);
