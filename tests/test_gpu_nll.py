@@ -175,3 +175,37 @@ def test_analytic_gradient_bad_candidate_gives_zero(ctx):
     pars = np.array([0.2, 50.0, 0.1, -2.2, -1.4, -1.9, 0.4, -3.0])       # nux at its upper bound: logit saturates, still valid
     g = iak.gradnllIAK3D(pars, ds["zData"], ds["XData"], analytic=True, modelx="matern", nud=0.5, cmeOpt=1, setupMats=sm, parBnds=PARBNDS)
     assert np.all(np.isfinite(g))
+
+
+def test_library_matches_frozen_end_to_end_cases(ctx):
+    """tests/golden/oracle_cases.json (scripts/make_golden.py): covariance entries, REML / ML terms, profiled estimates and
+    kriging output of three small seeded cases through the C ABI against the committed values."""
+    import json, os, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "..", "scripts"))
+    import make_golden
+    with open(os.path.join(here, "golden", "oracle_cases.json")) as f:
+        gold = json.load(f)
+    for case, want in zip(make_golden.CASES, gold["cases"]):
+        name, n, seed, kind, nonstat, nud, useReml = case
+        ds = synth.make_dataset(n, seed)
+        P, modelx, types, cmeOpt = case_pars(kind, nonstat, nud)
+        sm = iak.setupIAK3D(ds["xData"], ds["dIData"], ctx=ctx)
+        kw = dict(modelx=modelx, nud=nud, sdfdType_cd1=types[0], sdfdType_cxd0=types[1], sdfdType_cxd1=types[2], cmeOpt=cmeOpt, setupMats=sm,
+                  parBnds=PARBNDS, useReml=useReml, parsBTfmd=P)
+        t = iak.nllIAK3D(None, ds["zData"], ds["XData"], forCompLik=True, **kw)
+        assert abs(t["lndetA"] - want["lndetA"]) <= 1e-8 * abs(want["lndetA"]), name
+        assert scaled_err(t["WiAW"], np.asarray(want["WiAW"])) <= 1e-8, name
+        fit = iak.nllIAK3D(None, ds["zData"], ds["XData"], rtnAll=True, attachBigMats=True, **kw)
+        assert abs(fit["nll"] - want["nll"]) <= 1e-8 * abs(want["nll"]), name
+        assert abs(fit["cxdhat"] - want["cxdhat"]) <= 1e-8 * want["cxdhat"], name
+        assert scaled_err(np.asarray(fit["betahat"]).reshape(-1), np.asarray(want["betahat"])) <= 1e-8, name
+        cov = iak.setCIAK3D(P, modelx, *types, cmeOpt, sm)
+        for i, j, c in want["C_entries"]:
+            assert abs(cov["C"][int(i), int(j)] - c) <= 1e-10 * abs(c), (name, i, j)
+        assert relerr(cov["sigma2Vec"][:4], np.asarray(want["sigma2Vec_head"])) <= 1e-12, name
+        xMap = synth.make_grid(4)[:12]
+        dIMap = synth.GSM_INTERVALS[[0, 3]]
+        pg = iak.predictIAK3D(xMap, dIMap, lambda i, idx: synth.grid_design(xMap[idx], dIMap[i], 3), fit)
+        assert scaled_err(pg["zMap"], np.asarray(want["zMap"])) <= 1e-8, name
+        assert scaled_err(pg["vMap"], np.asarray(want["vMap"])) <= 1e-8, name

@@ -205,3 +205,23 @@ def test_analytic_gradient_formula_against_central_differences():
             vp = pars.copy(); vp[k] += h; vm = pars.copy(); vm[k] -= h
             cd = (f(vp) - f(vm)) / (2 * h)
             assert abs(g[k] - cd) <= 2e-5 * max(1.0, abs(cd)), (useReml, k, g[k], cd)
+
+
+def test_oracle_matches_frozen_end_to_end_cases():
+    """tests/golden/oracle_cases.json (scripts/make_golden.py): the oracle must not drift from the values the GPU path is
+    also checked against."""
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "..", "scripts"))
+    import make_golden
+    with open(os.path.join(HERE, "golden", "oracle_cases.json")) as f:
+        gold = json.load(f)
+    for case, want in zip(make_golden.CASES, gold["cases"]):
+        got = make_golden.compute(case)
+        assert got["name"] == want["name"]
+        for k in ("lndetA", "nll", "cxdhat"):
+            assert abs(got[k] - want[k]) <= 1e-11 * abs(want[k]), (case[0], k)
+        for k in ("WiAW", "betahat", "zMap", "vMap", "sigma2Vec_head"):
+            a, b = np.asarray(got[k], float), np.asarray(want[k], float)
+            assert np.max(np.abs(a - b)) <= 1e-10 * np.max(np.abs(b)), (case[0], k)
+        for (i, j, c), (_, _, cw) in zip(got["C_entries"], want["C_entries"]):
+            assert abs(c - cw) <= 1e-13 * abs(cw)
