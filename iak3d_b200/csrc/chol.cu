@@ -139,7 +139,7 @@ __device__ __forceinline__ void solve_segment(double (&x)[4][4][2], const double
   }
 }
 
-// 1/sqrt(x) for a positive finite pivot: MUFU seed + two Newton steps (relative error ~1e-16); rsqrt() from the
+// 1/sqrt(x) for a positive finite pivot: MUFU seed + two Newton steps (max relative error 1.24 ulp); rsqrt() from the
 // math library carries special-case handling that sits on the column-to-column dependency chain.
 __device__ __forceinline__ double fast_rsqrt(double x) {
   double y;
@@ -149,9 +149,7 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
   y = fma(y, e, y);
   e = fma(-hx * y, y, 0.5);
   y = fma(y, e, y);
-  e = fma(-hx * y, y, 0.5);
-  y = fma(y, e, y);
-  return y;
+  return y;                             // seed 9e-7 -> 1.2e-12 -> 1.24 ulp; a third step changes nothing (scripts/micro/rsqrt_acc.cu)
 }
 
 // ---- diagonal block, 4 columns per step ------------------------------------------------------------------------------
