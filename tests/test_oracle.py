@@ -225,3 +225,53 @@ def test_oracle_matches_frozen_end_to_end_cases():
             assert np.max(np.abs(a - b)) <= 1e-10 * np.max(np.abs(b)), (case[0], k)
         for (i, j, c), (_, _, cw) in zip(got["C_entries"], want["C_entries"]):
             assert abs(c - cw) <= 1e-13 * abs(cw)
+
+
+def _two_block_case(optn):
+    ds = synth.make_dataset(400, 61)
+    P, modelx, types, cmeOpt = case_pars("edgeroi", False, 0.5)
+    blk = synth.make_blocks(ds["xData"], ds["prof"], 2, 61)
+    blk["compLikOptn"] = optn
+    lmm = dict(compLikMats=blk, xData=ds["xData"], dIData=ds["dIData"], parsBTfmd=P)
+    z = ds["zData"].reshape(-1) - ds["zData"].mean()
+    xMap = synth.make_grid(6)[:30]
+    dIMap = np.repeat(synth.GSM_INTERVALS[1:2], 30, axis=0)
+    return ds, P, modelx, types, cmeOpt, blk, lmm, z, xMap, dIMap
+
+
+def _exact_simple_kriging(ds, P, modelx, types, cmeOpt, rows, xm, dm, z):
+    sm = orc.setupIAK3D(np.vstack([xm, ds["xData"][rows]]), np.vstack([dm, ds["dIData"][rows]]))
+    Cj, _ = orc.setCIAK3D(P, modelx, *types, cmeOpt, sm)
+    m = xm.shape[0]
+    T = np.linalg.solve(Cj[m:, m:], Cj[m:, :m])
+    return T.T @ z[rows], np.diag(Cj[:m, :m] - Cj[:m, m:] @ T)
+
+
+def test_eidsvik_block_predictor_with_one_pair_is_exact_kriging():
+    """Pins the restatement of predMatsIAK3D_CLEV_ByBlock (compositeLikIAK3D.R:609-798) independently of its own algebra:
+    with two blocks there is one pair, the composite likelihood IS the full likelihood of the joined data, and the
+    Eidsvik predictor (A0, b0, Bk0, J0 and the sandwich invA0 J0 invA0) must collapse to simple kriging from all data --
+    prediction and conditional variance."""
+    ds, P, modelx, types, cmeOpt, blk, lmm, z, xMap, dIMap = _two_block_case(2)
+    zk, vk = orc.predMatsIAK3D_CLEV_ByBlock(z, ds["XData"], xMap, dIMap, lmm, modelx, types, cmeOpt)
+    bm = np.argmin(orc.xyDist(xMap, np.asarray(blk["centroids"])), axis=1)
+    for k in (0, 1):
+        pts = np.nonzero(bm == k)[0]
+        rows = np.concatenate([blk["listBlocks"][k], blk["listBlocks"][1 - k]])
+        ze, ve = _exact_simple_kriging(ds, P, modelx, types, cmeOpt, rows, xMap[pts], dIMap[pts], z)
+        assert np.max(np.abs(zk[pts] - ze)) <= 1e-11 * np.max(np.abs(ze))
+        assert np.max(np.abs(vk[pts] - ve) / ve) <= 1e-11
+
+
+def test_pairwise_block_predictor_with_one_pair_is_exact_kriging():
+    """Same collapse for predMatsIAK3D_CL_ByBlock (compositeLikIAK3D.R:471-607): one neighbour, so the average over the
+    neighbours is the kriging term of the single pair."""
+    ds, P, modelx, types, cmeOpt, blk, lmm, z, xMap, dIMap = _two_block_case(1)
+    t = orc.predMatsIAK3D_CL_ByBlock(z, ds["XData"], xMap, dIMap, lmm, modelx, types, cmeOpt)
+    bm = np.argmin(orc.xyDist(xMap, np.asarray(blk["centroids"])), axis=1)
+    for k in (0, 1):
+        pts = np.nonzero(bm == k)[0]
+        rows = np.concatenate([blk["listBlocks"][k], blk["listBlocks"][1 - k]])
+        ze, ve = _exact_simple_kriging(ds, P, modelx, types, cmeOpt, rows, xMap[pts], dIMap[pts], z)
+        assert np.max(np.abs(t["CkhiCz_muhat"][pts] - ze)) <= 1e-11 * np.max(np.abs(ze))
+        assert np.max(np.abs((t["diagCkk"][pts] - t["diagCkhiCChk"][pts]) - ve) / ve) <= 1e-10
