@@ -2,15 +2,18 @@
 """bench.py -- REML log-likelihood evaluations per second on the 5k-interval single-block workload
 (BASELINE.json configs[1]) and the other hot-path workloads, on N B200s of one node.
 
-    python bench.py --gpus N --steps K --warmup W [--workload s5|cl|krige] [--impl ours|reference]
+    python bench.py --gpus N --steps K --warmup W [--workload all|s5|cl|krige] [--impl ours|reference]
 
 A step (default workload `s5`) is one forward-difference gradient of the REML objective as the optimiser asks for
 it (gradnllIAK3D, fitIAK3D.R:1865-1886): npar + 1 likelihood evaluations -- covariance build + Cholesky + solves
 each -- sent to the GPU as one batch.  `value` times the library calls with the dataset resident in HBM; `e2e`
 goes through the reference-facing call with host buffers (W re-uploaded from host memory each step, results read
 back, REML tail on the host).  Single-block REML does not shard ("replicas only"), so --gpus N runs N
-independent replicas and reports weak scaling; `--workload cl` and `--workload krige` are the workloads that shard.
-One JSON line on stdout (rank 0).
+independent replicas and reports weak scaling.  The two workloads that DO shard -- the 200k-interval composite likelihood
+(configs[3]) and block kriging of the 1M-cell grid (configs[4]) -- run after it in the same call (default `--workload all`)
+and are reported as the sub-records `cl200` and `p1m` of the same JSON line: value, ms_per_step, roofline, e2e, per-rank
+unit counts and the time of the all-reduce, at whatever N the call was launched with (strong scaling: total work fixed).
+`--workload cl|krige|s5` runs one of them alone.  One JSON line on stdout (rank 0).
 """
 from __future__ import annotations
 
@@ -102,6 +105,15 @@ def s5_inputs(n):
                      float(api.logitab(P["ad"], *PARBNDS["adBnds"])), np.log(P["cx0"]), np.log(P["cx1"]), np.log(P["cd1"]),
                      float(api.logitab(P["cxd1"], *PARBNDS["sxd1Bnds"])), np.log(P["cme"])])
     return ds, pars, modelx, types, cmeOpt
+
+
+def s5_config(n, p, nxU, ndIU, modelx, types, cmeOpt, nb, world):
+    """`config` of the S5 line -- one function for both arms, so that the reference arm describes the same workload"""
+    return dict(workload=f"synthetic {n}-interval single-block REML: iaCovMatern build + Cholesky loglik (BASELINE configs[1])",
+                n=n, p=p, nxU=int(nxU), ndIU=int(ndIU), modelx=modelx, nux=0.5, nud=0.5, sdfdTypes=list(types), cmeOpt=cmeOpt,
+                evals_per_step=nb, step="one forward-difference gradient (npar+1 evaluations: gradnllIAK3D, fitIAK3D.R:1865-1886)",
+                parallelism="replicas only" if world > 1 else "1 GPU",
+                l2="working set (factor buffers %.0f MB) exceeds the 126 MB L2; no flush needed" % (nb * 8.0 * n * n / 1e6))
 
 
 def fd_candidates(pars, step_no, delta=1e-6):
@@ -220,11 +232,7 @@ def run_s5(args, rank, local_rank, world, comm):
     out = dict(
         metric=METRIC, value=value, unit="evals/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-        config=dict(workload=f"synthetic {n}-interval single-block REML: iaCovMatern build + Cholesky loglik (BASELINE configs[1])",
-                    n=n, p=p, nxU=sm.nxU, ndIU=sm.ndIU, modelx=modelx, nux=0.5, nud=0.5, sdfdTypes=list(types), cmeOpt=cmeOpt,
-                    evals_per_step=nb, step="one forward-difference gradient (npar+1 evaluations in one batch)",
-                    parallelism="replicas only" if world > 1 else "1 GPU",
-                    l2="working set (factor buffers %.0f MB) exceeds the 126 MB L2; no flush needed" % (nb * 8.0 * n * n / 1e6)),
+        config=s5_config(n, p, sm.nxU, sm.ndIU, modelx, types, cmeOpt, nb, world),
         single_eval_ms=single_ms, single_eval_per_s=1e3 / single_ms, gradient_wall_ms=grad_ms,
         stage_ms=dict(tables=stage[0], cov_build=stage[1], factorise=stage[2], finish=stage[3]),
         roofline=dict(kernel="tile_task_kernel (tile Cholesky + bordered solves, FP64 DMMA)", bound="tensor", achieved=tf,
@@ -246,7 +254,8 @@ def run_s5(args, rank, local_rank, world, comm):
 def ncu_traffic(kernel, n, evals):
     """DRAM bytes per launch of `kernel` from the committed ncu capture, when one exists for exactly this shape."""
     try:
-        with open(os.path.join(ROOT, "profiles", "traffic_r01.json")) as f:
+        path = next(pth for pth in (os.path.join(ROOT, "profiles", f"traffic_r0{r}.json") for r in (2, 1)) if os.path.exists(pth))
+        with open(path) as f:
             e = json.load(f)[kernel]
         return float(e["bytes"]) if (e["n"] == n and e["evals_per_launch"] == evals) else None
     except Exception:
@@ -261,57 +270,93 @@ def measured_peak(key, fallback):
         return fallback, "fallback (B200_PROFILING.md)"
 
 
+def host_threads():
+    """Give the host BLAS every core of the box and say how many that is.  torchrun exports OMP_NUM_THREADS=1 to its
+    workers, which OpenBLAS reads when it is loaded -- threadpoolctl overrides it at run time."""
+    cores = os.cpu_count() or 1
+    info = dict(cores=cores, blas="unknown", blas_threads=None)
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=cores)
+        libs = [d for d in threadpool_info() if d.get("user_api") == "blas"]
+        if libs:
+            info.update(blas=f"{libs[0].get('internal_api')} {libs[0].get('version')}", blas_threads=int(libs[0].get("num_threads", 0)))
+    except Exception as e:                      # noqa: BLE001
+        info["note"] = f"threadpoolctl unavailable ({e})"
+    return info
+
+
+def oracle_s5(n):
+    """The reference algorithm's CPU implementation of one S5 evaluation (oracle port; R is not installed on the GPU box:
+    profiles/r_probe_gpubox_r02.txt) and the shapes of its setup."""
+    from oracle import iak3d_oracle as orc
+    ds, pars, modelx, types, cmeOpt = s5_inputs(n)
+    sm = orc.setupIAK3D(ds["xData"], ds["dIData"])
+
+    def f(v):
+        return orc.nllIAK3D(v, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True, sm, PARBNDS, useReml=True)
+    return f, pars, ds, modelx, types, cmeOpt, int(np.max(sm["xid"])) + 1, int(np.max(sm["did"])) + 1
+
+
 def cpu_baseline_s5(n, budget_s=20.0):
     """The oracle (NumPy/SciPy port of the reference algorithm; R is not installed) on the host cores."""
-    from oracle import iak3d_oracle as orc
-    from iak3d_b200 import synth
-    ds = synth.make_dataset(n, synth.SEEDS["S5"])
-    P, modelx, types, cmeOpt = synth.default_pars("matern0.5")
-    sm = orc.setupIAK3D(ds["xData"], ds["dIData"])
-    f = lambda: orc.nllIAK3D(None, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True, sm, PARBNDS, useReml=True, parsBTfmd=P)
-    f()
+    th = host_threads()
+    f, pars, *_ = oracle_s5(n)
+    f(pars)
     t0 = time.perf_counter(); k = 0
     while True:
-        f(); k += 1
+        f(fd_candidates(pars, k)[k % (pars.size + 1)]); k += 1
         if time.perf_counter() - t0 > budget_s or k >= 20:
             break
     dt = time.perf_counter() - t0
-    return dict(value=k / dt, unit="evals/s", cores=os.cpu_count(), kind="port",
-                sample=f"{k} single evaluations of the same n={n} workload by oracle/iak3d_oracle.nllIAK3D (NumPy/SciPy, OpenBLAS "
-                       f"threads = host cores); R is not installed, so this is a port, not the R reference")
+    return dict(value=k / dt, unit="evals/s", cores=th["blas_threads"] or th["cores"], kind="port", blas=th["blas"],
+                sample=f"{k} single evaluations of the same n={n} workload by oracle/iak3d_oracle.nllIAK3D (NumPy/SciPy, {th['blas']} with "
+                       f"{th['blas_threads']} threads on {th['cores']} host cores); R is not installed on the box, so this is a port, not the R "
+                       "reference")
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference algorithm's CPU implementation (oracle port) on the host cores."""
+    """--impl reference: the reference's CPU implementation of the SAME step on the host cores -- gradnllIAK3D's serial loop
+    over the npar + 1 candidates (fitIAK3D.R:1865-1886), each a full nllIAK3D (covariance build + Cholesky + REML tail) by
+    the oracle port.  Same config, warm-up and step definition as the repo arm; rank 0 alone runs it."""
     if rank != 0:
         return None
-    from oracle import iak3d_oracle as orc
-    from iak3d_b200 import synth
+    th = host_threads()
     n = args.n
-    ds = synth.make_dataset(n, synth.SEEDS["S5"])
-    P, modelx, types, cmeOpt = synth.default_pars("matern0.5")
-    sm = orc.setupIAK3D(ds["xData"], ds["dIData"])
-    f = lambda: orc.nllIAK3D(None, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True, sm, PARBNDS, useReml=True, parsBTfmd=P)
-    t0 = time.perf_counter(); f(); t1 = time.perf_counter() - t0
-    warm = max(0, min(args.warmup, 1))
-    budget = 150.0
-    steps = int(max(1, min(args.steps, budget // max(t1, 1e-3))))
-    for _ in range(warm):
-        f()
+    f, pars, ds, modelx, types, cmeOpt, nxU, ndIU = oracle_s5(n)
+    nb = pars.size + 1
+    t0 = time.perf_counter(); f(pars); t1 = time.perf_counter() - t0
+    budget = 240.0                                  # bounded: the whole run ends within a few minutes
+    total = args.steps + args.warmup
+    steps, warm = args.steps, args.warmup
+    if total * nb * t1 > budget:                    # keep the step definition, shorten the run, and say so
+        warm = max(0, min(args.warmup, 1))
+        steps = int(max(1, min(args.steps, (budget / (nb * max(t1, 1e-3))) - warm)))
+    for w in range(warm):
+        for v in fd_candidates(pars, -1 - w):
+            f(v)
     t0 = time.perf_counter()
-    for _ in range(steps):
-        f()
+    for k in range(steps):
+        vals = [f(v) for v in fd_candidates(pars, k)]
     dt = time.perf_counter() - t0
-    v = steps / dt
-    cb = dict(value=v, unit="evals/s", cores=os.cpu_count(), kind="port",
-              sample=f"{steps} single evaluations (one of the npar+1 evaluations of a step each) of the n={n} workload, oracle port "
-                     "(NumPy/SciPy + OpenBLAS, all host cores); the reference is R and R is not installed")
+    assert all(np.isfinite(v) and v < 1e90 for v in vals)
+    v = steps * nb / dt
+    cb = dict(value=v, unit="evals/s", cores=th["blas_threads"] or th["cores"], kind="port", blas=th["blas"],
+              sample=f"{steps} steps of {nb} evaluations (one forward-difference gradient each) of the n={n} workload, oracle port "
+                     f"(NumPy/SciPy, {th['blas']} with {th['blas_threads']} threads on {th['cores']} host cores); the reference is R and R "
+                     "is not installed on the box (profiles/r_probe_gpubox_r02.txt)")
     return dict(impl="reference", metric=METRIC, value=v, unit="evals/s", n_gpus=world, steps=steps, steps_requested=args.steps,
                 warmup=warm, ms_per_step=1e3 * dt / steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
-                data="synthetic",
-                config=dict(workload=f"synthetic {n}-interval single-block REML: iaCovMatern build + Cholesky loglik (BASELINE configs[1])",
-                            n=n, p=ds["XData"].shape[1]),
+                data="synthetic", config=s5_config(n, ds["XData"].shape[1], nxU, ndIU, modelx, types, cmeOpt, nb, world),
                 cpu_baseline=cb, e2e=dict(value=v, unit="evals/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+
+
+def sub_args(args, steps, warmup, **kw):
+    a = argparse.Namespace(**vars(args))
+    a.steps, a.warmup = steps, warmup
+    for k, v in kw.items():
+        setattr(a, k, v)
+    return a
 
 
 def main():
@@ -320,9 +365,10 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="s5", choices=["s5", "cl", "krige"])
+    ap.add_argument("--workload", default="all", choices=["all", "s5", "cl", "krige"])
     ap.add_argument("--nobs", dest="n", type=int, default=5000, help="observations (torchrun's parser trips over a bare --n)")
-    ap.add_argument("--cells", type=int, default=1000000, help="grid cells of --workload krige")
+    ap.add_argument("--cl-nobs", dest="cl_n", type=int, default=200000, help="observations of the composite-likelihood workload")
+    ap.add_argument("--cells", type=int, default=1000000, help="grid cells of the kriging workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -336,21 +382,35 @@ def main():
         return 0
     parallel.init()
     comm = parallel.BlockComm()
-    if args.workload == "s5":
+    import bench_extra
+    cpu = (rank == 0 and world == 1 and not args.no_cpu_baseline)
+    if args.workload in ("all", "s5"):
         out, ctx = run_s5(args, rank, local_rank, world, comm)
+        ctx.close()
+        if cpu:
+            out["cpu_baseline"] = cpu_baseline_s5(args.n)
+        if args.workload == "all":
+            # the workloads that shard: a few steps each (one composite-likelihood evaluation is 286 factorisations of ~4000,
+            # one kriging step 6e6 predictions), sized so that the whole call stays within minutes at any N
+            sub, ctx = bench_extra.run(sub_args(args, max(2, min(args.steps, 5)), 3, workload="cl", n=args.cl_n), rank, local_rank, world, comm)
+            ctx.close()
+            if cpu:
+                sub["cpu_baseline"] = bench_extra.cpu_baseline_cl(args.cl_n)
+            out["cl200"] = sub
+            sub, ctx = bench_extra.run(sub_args(args, max(1, min(args.steps, 2)), 3, workload="krige"), rank, local_rank, world, comm)
+            ctx.close()
+            if cpu:
+                sub["cpu_baseline"] = bench_extra.cpu_baseline_krige(args.n)
+            out["p1m"] = sub
     else:
-        import bench_extra
+        if args.workload == "cl" and args.n == 5000:
+            args.n = args.cl_n
         out, ctx = bench_extra.run(args, rank, local_rank, world, comm)
+        ctx.close()
+        if cpu:
+            out["cpu_baseline"] = bench_extra.cpu_baseline_krige(args.n) if args.workload == "krige" else bench_extra.cpu_baseline_cl(args.n)
     if rank == 0:
-        if world == 1 and not args.no_cpu_baseline:
-            if args.workload == "s5":
-                out["cpu_baseline"] = cpu_baseline_s5(args.n)
-            elif args.workload == "krige":
-                out["cpu_baseline"] = bench_extra.cpu_baseline_krige(args.n)
-            else:
-                out["cpu_baseline"] = bench_extra.cpu_baseline_cl(args.n if args.n != 5000 else 200000)
         print(json.dumps(out), flush=True)
-    ctx.close()
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

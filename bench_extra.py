@@ -20,7 +20,7 @@ from bench import PARBNDS, ClockSampler, measured_peak
 def _cl(args, rank, local_rank, world, comm):
     import iak3d_b200 as iak
     from iak3d_b200 import api, synth
-    n = args.n if args.n != 5000 else 200000
+    n = args.n
     nblocks = max(4, int(round(n / 2000.0)))
     ctx = iak.Context(local_rank)
     ds = synth.make_dataset(n, synth.SEEDS["CL200"])
@@ -30,51 +30,79 @@ def _cl(args, rank, local_rank, world, comm):
     cl = iak.setupIAK3D_CL(ds["xData"], ds["dIData"], ds["zData"], ds["XData"], blk, ctx=ctx, rank=rank, world=world)
     sizes = [u["n"] for u in cl["units"]]
     p = ds["XData"].shape[1]
+    tm = {}
 
     def step(k):
         P = dict(P0); P["ax"] = P0["ax"] * (1.0 + 1e-3 * np.sin(0.7 * k)); P["cme"] = P0["cme"] * (1.0 + 1e-3 * np.cos(0.3 * k))
-        return iak.nllIAK3D_CL(None, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True, PARBNDS, False, cl, parsBTfmd=P, comm=comm)
+        return iak.nllIAK3D_CL(None, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True, PARBNDS, False, cl, parsBTfmd=P, comm=comm,
+                               timings=tm)
 
     peak = ctx.fp64_peak(1)
     for w in range(args.warmup):
         v = step(-1 - w)
     assert np.isfinite(v) and v < 1e90
+    tm.clear()
     clk = ClockSampler(local_rank)
     comm.barrier(); ctx.sync()
     l0 = ctx.launch_count(); clk.start()
     stage = np.zeros(4)
+    t0 = time.perf_counter()
     ctx.timer_start()
     for k in range(args.steps):
         step(k)
         if cl["units"]:
             stage += np.array(ctx.last_stage_ms()[0])
     ms = ctx.timer_stop()
+    wall = time.perf_counter() - t0
     comm.barrier(); ctx.sync()
     clocks = clk.stop()
     launches = ctx.launch_count() - l0
+    ms_rank = comm.gather_scalar(ms / args.steps)
     ms = float(comm.allreduce_max(np.array([ms]))[0])
+    wall = float(comm.allreduce_max(np.array([wall]))[0])
     flops_rank = sum(float(s) ** 3 / 3.0 for s in sizes)
     flops = float(comm.allreduce_sum(np.array([flops_rank]))[0])
     stage /= args.steps
+    fac_rank = comm.gather_scalar(stage[2]); pre_rank = comm.gather_scalar(stage[0] + stage[1]); units_rank = comm.gather_scalar(len(sizes))
+    rows_rank = comm.gather_scalar(sum(sizes))
     tf_rank = flops_rank / max(stage[2], 1e-9) / 1e9
+    # the optimiser's gradient call: npar + 1 composite-likelihood evaluations as batched launches + ONE all-reduce
+    pars = np.array([float(api.logitab(P0["ax"], *PARBNDS["axBnds"])), float(api.logitab(P0["ad"], *PARBNDS["adBnds"])), np.log(P0["cx0"]),
+                     np.log(P0["cx1"]), float(api.logitab(P0["cxd1"], *PARBNDS["sxd1Bnds"])), np.log(P0["cme"])])
+    gargs = (ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True, PARBNDS, False, cl)
+    tg = {}
+    iak.gradnllIAK3D_CL(pars, *gargs, comm=comm)
+    comm.barrier(); ctx.sync(); t0 = time.perf_counter()
+    g = iak.gradnllIAK3D_CL(pars * (1 + 1e-6), *gargs, comm=comm, timings=tg)
+    grad_s = float(comm.allreduce_max(np.array([time.perf_counter() - t0]))[0])
+    assert np.all(np.isfinite(g))
+    calls = max(tm.get("allreduce_calls", 0), 1)
     out = dict(metric="composite-likelihood evals/sec at n obs", value=args.steps / (ms * 1e-3), unit="evals/s", n_gpus=world,
                steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong",
                vs_baseline=None, dtype="f64", data="synthetic",
                config=dict(workload=f"synthetic {n}-interval composite likelihood, {nblocks} Voronoi blocks, compLikOptn=2 "
                                     "(adjacent pairs, ML) (BASELINE configs[3])", n=n, p=p, blocks=nblocks,
-                           block_pairs=int(cl["n_units_total"]), pairs_this_rank=len(sizes), mean_pair_size=float(np.mean(sizes)) if sizes else 0,
-                           parallelism=f"block pairs over {world} GPU(s), one all-reduce of {(p + 1) ** 2 + 3} doubles per evaluation",
+                           block_pairs=int(cl["n_units_total"]), mean_pair_size=float(np.mean(sizes)) if sizes else 0,
+                           parallelism=f"block pairs over {world} GPU(s) (LPT on n^3), sums formed on the device, one all-reduce of "
+                                       f"{(p + 1) ** 2 + 2} doubles per evaluation",
                            l2="per-rank factor buffers exceed the 126 MB L2; no flush needed"),
                units_per_s=int(cl["n_units_total"]) * args.steps / (ms * 1e-3),
+               per_rank=dict(pairs=[int(x) for x in units_rank], rows=[int(x) for x in rows_rank], ms_per_step=[float(x) for x in ms_rank],
+                             factorise_ms=[float(x) for x in fac_rank], tables_build_ms=[float(x) for x in pre_rank]),
+               allreduce=dict(us_per_eval=tm.get("allreduce_us", 0.0) / calls, calls_per_eval=1 if world > 1 else 0,
+                              doubles=(p + 1) ** 2 + 2, where="NCCL on the device buffer the library summed into; one D2H after it"),
+               gradient=dict(ms=1e3 * grad_s, evals=int(pars.size + 1), evals_per_s=(pars.size + 1) / grad_s,
+                             allreduce_calls=int(tg.get("allreduce_calls", 0)), allreduce_us=float(tg.get("allreduce_us", 0.0)),
+                             what="gradnllIAK3D_CL: npar + 1 evaluations as (units x parameter sets) batched launches + ONE all-reduce"),
                stage_ms=dict(tables=stage[0], cov_build=stage[1], factorise=stage[2], finish=stage[3]),
                roofline=dict(kernel="tile_task_kernel (rank 0's share)", bound="tensor", achieved=tf_rank, peak=peak, unit="TFLOP/s",
                              frac=tf_rank / peak, traffic=None, flops_per_launch=flops_rank,
                              peak_source="FP64 DMMA microbenchmark in this run"),
                whole_job_tflops=flops * args.steps / (ms * 1e-3) / 1e12,
-               e2e=dict(value=args.steps / (ms * 1e-3), unit="evals/s", h2d_bytes_per_step=int(len(sizes) * 192),
-                        d2h_bytes_per_step=int(len(sizes) * (2 + (p + 1) ** 2) * 8),
-                        note="the timed call IS the reference-facing call (nllIAK3D_CL with host parameters, host result); "
-                             "block data are resident like setupMats"),
+               e2e=dict(value=args.steps / wall, unit="evals/s", h2d_bytes_per_step=int(len(sizes) * (192 + 12)),
+                        d2h_bytes_per_step=int(((p + 1) ** 2 + 2) * 8),
+                        note="wall clock of the reference-facing call (nllIAK3D_CL: host parameters in, host nll out, all-reduce "
+                             "included); block data are resident like setupMats"),
                gpu_launches=int(launches), clocks=clocks)
     return out, ctx
 
@@ -124,18 +152,20 @@ def _krige(args, rank, local_rank, world, comm):
     for s in range(args.steps):
         z2, v2 = k.predict(xy, dI, X)
     e2e_s = float(comm.allreduce_max(np.array([time.perf_counter() - t0]))[0])
+    cells_rank = comm.gather_scalar(m)
     preds = cells * nd * args.steps
     tf = (m * nd * float(n) ** 2) * args.steps / (ms * 1e-3) / 1e12
     out = dict(metric="kriging preds/sec", value=preds / (ms * 1e-3), unit="preds/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
                config=dict(workload=f"block kriging of a {cells}-cell grid x {nd} GlobalSoilMap intervals with variances against the "
                                     f"{n}-interval fit (BASELINE configs[4])", n=n, p=ds["XData"].shape[1], cells=cells, intervals=nd,
-                           cells_this_rank=m, parallelism=f"grid tiles over {world} GPU(s), no data-path collective",
+                           parallelism=f"grid tiles over {world} GPU(s), no data-path collective",
                            l2="each 16384-support panel (0.7 GB) exceeds the 126 MB L2; no flush needed"),
                roofline=dict(kernel="tile_task_kernel, mode 1 (rank 0's tile)", bound="tensor", achieved=tf, peak=peak, unit="TFLOP/s",
                              frac=tf / peak, traffic=None, flops_per_launch=16384.0 * n * n,
                              note="n^2 flops per prediction (X = Ckh L^-T); the reference's Ckh %*% iC costs 2 n^2",
                              peak_source="FP64 DMMA microbenchmark in this run"),
+               per_rank=dict(cells=[int(x) for x in cells_rank]), allreduce=dict(us_per_eval=0.0, calls_per_eval=0, where="no collective in the data path"),
                e2e=dict(value=preds / e2e_s, unit="preds/s", h2d_bytes_per_step=int(xy.nbytes + dI.nbytes + X.nbytes),
                         d2h_bytes_per_step=int(2 * m * nd * 8)),
                gpu_launches=int(launches), clocks=clocks)

@@ -51,6 +51,8 @@ _PROTOS = {
     "iak3d_dataset_ids": (C.c_int, [_vp, _ip, _ip]),
     "iak3d_dataset_set_sdfd_spline": (C.c_int, [_vp, _i32, _i32, _dp]),
     "iak3d_dataset_set_lnN_column": (C.c_int, [_vp, _i32]),
+    "iak3d_factor_build_fetch": (C.c_int, [_vp, C.POINTER(Pars), _i32, _dp, _dp]),
+    "iak3d_predict_panel_fetch": (C.c_int, [_vp, _i64, _dp, _i64, C.POINTER(_i64)]),
     "iak3d_cov_diag": (C.c_int, [_vp, C.POINTER(Pars), _dp]),
     "iak3d_fit_create_res": (C.c_int, [_vp, C.POINTER(Pars), _dp, _dp, _dp, C.POINTER(_vp)]),
     "iak3d_predict_fetch_terms": (C.c_int, [_vp, _dp, _dp, _dp, _dp]),
@@ -67,6 +69,8 @@ _PROTOS = {
     "iak3d_nll_terms_batch": (C.c_int, [_vp, _i32, C.POINTER(_vp), C.POINTER(Pars), _dp, _dp, _ip]),
     "iak3d_nll_terms_batch_enqueue": (C.c_int, [_vp, _i32, C.POINTER(_vp), C.POINTER(Pars)]),
     "iak3d_nll_terms_batch_fetch": (C.c_int, [_vp, _dp, _dp, _ip]),
+    "iak3d_nll_terms_batch_wsum": (C.c_int, [_vp, _i32, C.POINTER(_vp), C.POINTER(Pars), _dp, _ip, _i32, _vp, _dp]),
+    "iak3d_dataset_slot_bytes": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "iak3d_nll_grad": (C.c_int, [_vp, _i32, C.POINTER(Pars), _dp, _i32, _dp, _dp, _dp]),
     "iak3d_fit_create": (C.c_int, [_vp, C.POINTER(Pars), _dp, _dp, C.POINTER(_vp)]),
     "iak3d_fit_destroy": (C.c_int, [_vp]),

@@ -30,7 +30,8 @@ BADNLL = 9e99   # fitIAK3D.R:685
 def logitab(z, a=0.0, b=1.0, invt=False):
     z = np.asarray(z, dtype=float)
     if invt:
-        return (1.0 / (1.0 + np.exp(-z))) * (b - a) + a
+        with np.errstate(over="ignore"):
+            return (1.0 / (1.0 + np.exp(-z))) * (b - a) + a
     u = (z - a) / (b - a)
     return np.log(u / (1.0 - u))
 
@@ -45,7 +46,8 @@ def tauTfm(parsIn, parBnds, invt=False):
     maxd = parBnds["maxd"]
     if invt:
         t2 = float(logitab(v[1], lo, hi, invt=True))
-        return np.array([(1.0 - math.exp(v[0])) / (1.0 - math.exp(-t2 * maxd)), t2])
+        with np.errstate(over="ignore", invalid="ignore"):
+            return np.array([float((1.0 - np.exp(v[0])) / (1.0 - np.exp(-t2 * maxd))), t2])
     return np.array([math.log(1.0 - v[0] * (1.0 - math.exp(-v[1] * maxd))), float(logitab(v[1], lo, hi))])
 
 
@@ -53,7 +55,13 @@ def readParsIAK3D(pars, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1,
     """Unconstrained optimiser vector -> parsBTfmd (natural scale), in the reference's consumption order."""
     v = list(np.asarray(pars, dtype=float).reshape(-1))
     take = lambda: v.pop(0)
-    ev = lambda: 1e-8 + math.exp(take())
+
+    def exp_(x):      # R's exp(): Inf on overflow (-> parsOK = FALSE -> badnll, fitIAK3D.R:718-741, 885), never an exception
+        try:
+            return math.exp(x)
+        except OverflowError:
+            return math.inf
+    ev = lambda: 1e-8 + exp_(take())
     if modelx not in ("matern", "wendland", "spherical", "nugget"):
         raise ValueError("unknown modelx")
     nugget = modelx == "nugget"
@@ -88,7 +96,7 @@ def readParsIAK3D(pars, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1,
             sd.append(np.zeros(0))
         else:
             raise ValueError("sdfd option not yet programmed")
-    cme = math.exp(take()) if cmeOpt == 1 else 0.0
+    cme = exp_(take()) if cmeOpt == 1 else 0.0
     out = dict(ax=ax, nux=nux, ad=ad, nud=nud, cx0=cx0, cx1=cx1, cd1=cd1, cxd0=cxd0, cxd1=cxd1,
                sdfdPars_cd1=sd[0], sdfdPars_cxd0=sd[1], sdfdPars_cxd1=sd[2], cme=cme)
     if v:
@@ -272,6 +280,21 @@ def setCIAK3D(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cme
     if st == BAD_PARS:
         return dict(C=None, sigma2Vec=None)
     return dict(C=Cm, sigma2Vec=s2)
+
+
+def factor_build_fetch(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, setupMats, batched=False, rtnW=False):
+    """setCIAK3D as the likelihood's factor build forms it (`cov_factor_kernel` into the blocked factor buffer -- the
+    kernel the covariance roofline is quoted on), copied back as a full symmetric matrix.  For the parity tests: the
+    reference-facing :func:`setCIAK3D` goes through the term-by-term rectangular kernel instead.  None for invalid
+    parameters; with `rtnW` also the bordered W' rows (q x n) as laid out by the kernel."""
+    sm = setupMats
+    P = make_pars(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt)
+    A = np.empty((sm.n, sm.n), order="F")
+    Wr = np.empty((sm.q, sm.n), order="F") if (rtnW and sm.q > 0) else None
+    st = sm.ctx.check(sm.ctx.lib.iak3d_factor_build_fetch(sm.h, C.byref(P), 1 if batched else 0, dptr(A), dptr(Wr)), allow=(BAD_PARS,))
+    if st == BAD_PARS:
+        return None
+    return (A, Wr) if rtnW else A
 
 
 def setCIAK3D2(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, setupMats):
@@ -709,13 +732,14 @@ def gradnllIAK3D(pars, zData, XData, vXU=None, iU=None, modelx="matern", nud=0.5
         lnd1 = C.c_double(); G1 = np.empty((p + 1, p + 1), order="F"); gs = np.empty(npar)
         st1 = sm.ctx.check(sm.ctx.lib.iak3d_nll_grad(sm.h, npar, parr, dptr(dl), 1 if useReml else 0, C.byref(lnd1), dptr(G1), dptr(gs)),
                            allow=(NOT_SPD, BAD_PARS))
-        if st1 != OK:
-            return (np.zeros(npar), BADNLL) if rtn_nll else np.zeros(npar)
-        g = 0.5 * gs
-        g[~np.isfinite(g)] = 0.0
-        if not rtn_nll:
-            return g
-        return g, reml_tail(_symm_upper(np.array(G1)), lnd1.value, n, p, useReml)["nll"]
+        if st1 == OK:
+            g = 0.5 * gs
+            g[~np.isfinite(g)] = 0.0
+            if not rtn_nll:
+                return g
+            return g, reml_tail(_symm_upper(np.array(G1)), lnd1.value, n, p, useReml)["nll"]
+        # the base point failed (not positive definite / invalid): fall through to the batch, whose failure behaviour is the
+        # reference's -- (badnll - nll0) / delta per failed candidate, 0 where the difference is NA (fitIAK3D.R:1812-1813)
     lnd, G, st = nll_terms_batch(sm.ctx, [sm] * len(cand), structs)
     Gt = np.transpose(G, (0, 2, 1))
     Gs = np.triu(Gt) + np.transpose(np.triu(Gt, 1), (0, 2, 1))           # forceSymmetric keeps the upper triangle (fitIAK3D.R:811)
@@ -726,8 +750,76 @@ def gradnllIAK3D(pars, zData, XData, vXU=None, iU=None, modelx="matern", nud=0.5
     return (g, vals[0]) if rtn_nll else g
 
 
+def cl_terms_sets(units, structs, q, comm=None, timings=None):
+    """The device side of composite-likelihood evaluations for `len(structs)` parameter sets at once
+    (compositeLikIAK3D.R:49-93, 105-155 for each set): every (unit of this rank, parameter set) pair is one problem of a
+    batched launch, the per-unit terms are summed on the device per parameter set (`iak3d_nll_terms_batch_wsum`), and ONE
+    all-reduce of nsets x (q^2 + 2) doubles combines the ranks (compositeLikIAK3D.R:63-64, Reduce('+')).  The sets are sent
+    in as many launches as device memory allows (a factor buffer per problem in flight).
+    -> array (nsets, q*q + 2): [sum w forceSymmetric(WiAW) (column-major), sum w lndetA, number of failed units].
+
+    A rank whose device call raises still takes part in the all-reduce (with NaN), so that the others do not hang in
+    NCCL; every rank raises afterwards."""
+    nsets, qq = len(structs), q * q
+    width = qq + 2
+    dev = comm.device_buffer(nsets * width) if (comm is not None and comm.world > 1) else None   # torch CUDA tensor or None
+    host = np.zeros((nsets, width))
+    err = None
+    t_dev0 = None
+    if units:
+        ctx = units[0]["setup"].ctx
+        try:
+            sb, fr = C.c_int64(), C.c_int64()
+            need = 0
+            for u in units:
+                ctx.check(ctx.lib.iak3d_dataset_slot_bytes(u["setup"].h, C.byref(sb), C.byref(fr)))
+                need += sb.value
+            g = int(max(1, min(nsets, (0.7 * ctx.device_info()["total_mem"]) // max(need, 1))))
+            wts = f64(np.array([u["weight"] for u in units], float))
+            for s0 in range(0, nsets, g):
+                s1 = min(nsets, s0 + g)
+                cnt = len(units) * (s1 - s0)
+                dsarr = (C.c_void_p * cnt)(*[u["setup"].h for _ in range(s0, s1) for u in units])
+                parr = (Pars * cnt)(*[structs[k] for k in range(s0, s1) for _ in units])
+                w = f64(np.tile(wts, s1 - s0))
+                grp = np.repeat(np.arange(s1 - s0, dtype=np.int32), len(units))
+                dptr_out = None if dev is None else C.c_void_p(dev.data_ptr() + s0 * width * 8)
+                hptr = dptr(host[s0:s1]) if dev is None else None
+                ctx.check(ctx.lib.iak3d_nll_terms_batch_wsum(ctx.h, cnt, dsarr, parr, dptr(w), iptr(grp), s1 - s0, dptr_out, hptr))
+        except Exception as e:                      # noqa: BLE001 -- re-raised below, after the collective
+            err = e
+    if comm is None or comm.world == 1:
+        if err is not None:
+            raise err
+        return host
+    if dev is None:                                 # gloo (CPU tests of the host logic): host buffer through the same exchange
+        if err is not None:
+            host[:] = np.nan
+        out = comm.allreduce_sum(host.reshape(-1)).reshape(nsets, width)
+    else:
+        if not units:
+            dev[:nsets * width].zero_()
+        if err is not None:
+            dev[:nsets * width].fill_(float("nan"))
+        out = comm.allreduce_device(nsets * width, timings).reshape(nsets, width)
+    if err is not None:
+        raise err
+    if np.any(np.isnan(out)):
+        raise Iak3dError("composite likelihood: another rank failed during the evaluation (see its log)")
+    return out
+
+
+def _cl_n_sum(compLikMats):
+    """n_SUM of compositeLikIAK3D.R:64,83: the observations of all adjacent pairs -- known to every rank from the block
+    lists, so it needs no exchange."""
+    if compLikMats["compLikOptn"] >= 4:
+        return 0.0
+    blocks = compLikMats["listBlocks"]
+    return float(sum(len(blocks[k]) + len(blocks[l]) for (k, l) in np.asarray(compLikMats["subsetPairsAdj"]).reshape(-1, 2)))
+
+
 def nllIAK3D_CL(pars, zData, XData, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds, useReml,
-                compLikMats, parsBTfmd=None, rtnTerms=False, comm=None, rtnAll=False):
+                compLikMats, parsBTfmd=None, rtnTerms=False, comm=None, rtnAll=False, timings=None):
     """compositeLikIAK3D.R:6-307.  `compLikMats` carries compLikOptn, listBlocks, subsetPairsAdj, subsetPairsNonadj and
     the per-unit device datasets made by :func:`setupIAK3D_CL` (first the adjacent pairs, then the single blocks --
     the order of iaCovMatern.R:551-575).  With `comm` (a parallel.BlockComm) the units are sharded across ranks and
@@ -740,23 +832,13 @@ def nllIAK3D_CL(pars, zData, XData, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sd
     if parsBTfmd is None:
         parsBTfmd = readParsIAK3D(pars, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds)
     P = make_pars(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt)
-    units = compLikMats["units"]               # list of dict(kind, weight, n, setup) owned by this rank
-    S = np.zeros((p + 1, p + 1)); lnd_sum = 0.0; n_SUM = 0.0; failed = 0.0
-    if units:
-        ctx = units[0]["setup"].ctx
-        lnd, G, st = nll_terms_batch(ctx, [u["setup"] for u in units], [P] * len(units))
-        for i, u in enumerate(units):
-            if st[i] != OK:
-                failed = 1.0
-                continue
-            w = u["weight"]
-            S += w * _symm_upper(G[i].T); lnd_sum += w * lnd[i]
-            if u["kind"] == "pair":
-                n_SUM += u["n"]
+    t = cl_terms_sets(compLikMats["units"], [P], p + 1, comm, timings)[0]
+    S = t[:(p + 1) ** 2].reshape(p + 1, p + 1); lnd_sum, failed = t[-2], t[-1]
+    n_SUM = _cl_n_sum(compLikMats)
     if not rtnAll:
-        return cl_reduce_and_tail(S, lnd_sum, n_SUM, failed, n, p, optn, nB, useReml, comm, rtnTerms)
+        return cl_reduce_and_tail(S, lnd_sum, n_SUM, failed, n, p, optn, nB, useReml, None, rtnTerms)
     # rtnAll (compositeLikIAK3D.R:231-256, 295-303): the fitted list predictIAK3D_CL works from
-    t = cl_reduce_and_tail(S, lnd_sum, n_SUM, failed, n, p, optn, nB, useReml, comm, True)
+    t = cl_reduce_and_tail(S, lnd_sum, n_SUM, failed, n, p, optn, nB, useReml, None, True)
     if not isinstance(t, dict):
         return dict(nll=BADNLL, pars=pars, parsBTfmd=parsBTfmd)
     cxdhat = t["cxdhat"]
@@ -776,18 +858,28 @@ def nllIAK3D_CL(pars, zData, XData, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sd
 
 
 def gradnllIAK3D_CL(pars, zData, XData, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds, useReml,
-                    compLikMats, comm=None, delta=1e-6, rtn_nll=False):
-    """Forward-difference gradient of the composite likelihood (gradnllIAK3D_CL[.mc], fitIAK3D.R:1819-1911): npar + 1
-    evaluations of :func:`nllIAK3D_CL`, each one batched launch over this rank's units (the reference forks the
-    parameter sets with mclapply); NA differences become 0 (:1813)."""
+                    compLikMats, comm=None, delta=1e-6, rtn_nll=False, timings=None):
+    """Forward-difference gradient of the composite likelihood (gradnllIAK3D_CL[.mc], fitIAK3D.R:1819-1911): the npar + 1
+    composite-likelihood evaluations are (units x parameter sets) problems of batched launches and ONE all-reduce of
+    (npar + 1) x ((p+1)^2 + 2) doubles (the reference forks the parameter sets with mclapply, each a serial or forked loop
+    over the pairs); NA differences become 0 (:1813)."""
     pars = np.asarray(pars, float).reshape(-1)
-    vals = np.empty(pars.size + 1)
+    zData = np.asarray(zData, float).reshape(-1)
+    XData = np.asarray(XData, float).reshape(zData.size, -1)
+    n, p = XData.shape
+    optn = compLikMats["compLikOptn"]
+    nB = len(compLikMats["listBlocks"])
+    structs = []
     for k in range(pars.size + 1):
         v = pars.copy()
         if k > 0:
             v[k - 1] += delta
-        vals[k] = nllIAK3D_CL(v, zData, XData, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds, useReml,
-                              compLikMats, comm=comm)
+        pb = readParsIAK3D(v, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds)
+        structs.append(make_pars(pb, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt))
+    T = cl_terms_sets(compLikMats["units"], structs, p + 1, comm, timings)
+    n_SUM = _cl_n_sum(compLikMats)
+    vals = np.array([cl_reduce_and_tail(t[:(p + 1) ** 2].reshape(p + 1, p + 1), t[-2], n_SUM, t[-1], n, p, optn, nB, useReml)
+                     for t in T])
     g = (vals[1:] - vals[0]) / delta
     g[~np.isfinite(g)] = 0.0
     return (g, vals[0]) if rtn_nll else g
@@ -1004,6 +1096,15 @@ class KeptFit:
         z = np.empty(self._m); v = np.empty(self._m)
         self.ctx.check(self.ctx.lib.iak3d_predict_fetch(self.h, dptr(z), dptr(v)))
         return z, v
+
+    def panel_fetch(self, chunk=0):
+        """Ckh (setCIAK3D2 of the staged map supports of one chunk against the data) as the predictor's panel kernels
+        build it, before the solve overwrites it -- parity tests."""
+        rows = C.c_int64()
+        cap = min(self._m, 4 * 148 * 128)                    # a chunk never holds more supports than this
+        flat = np.empty(cap * self.sm.n)
+        self.ctx.check(self.ctx.lib.iak3d_predict_panel_fetch(self.h, int(chunk), dptr(flat), cap, C.byref(rows)))
+        return flat[:rows.value * self.sm.n].reshape(rows.value, self.sm.n, order="F")
 
     def set_option(self, option, value):
         self.ctx.check(self.ctx.lib.iak3d_fit_set_option(self.h, int(option), int(value)))

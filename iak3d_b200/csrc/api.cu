@@ -650,6 +650,52 @@ extern "C" int iak3d_cov_build(iak3d_ds* ds, const iak3d_pars* pars, double* C, 
   return rc;
 }
 
+// setCIAK3D as the factor build forms it (cov_factor_kernel into the blocked factor buffer), copied back un-blocked
+extern "C" int iak3d_factor_build_fetch(iak3d_ds* ds, const iak3d_pars* pars, int32_t batched, double* A, double* Wrows) {
+  if (!ds || !pars || !A) return IAK3D_ERR_ARG;
+  iak3d_ctx* ctx = ds->ctx;
+  cudaSetDevice(ctx->device);
+  if (ctx->batch_pending()) { ctx->err = "factor_build_fetch: a batch is pending"; return IAK3D_ERR_ARG; }
+  EvalPlan pl;
+  int st = iak_make_plan(ctx, pars, true, &pl);
+  if (st == 0) st = iak_plan_check_avsd(ctx, ds, &pl);
+  if (st != 0) return st;
+  if (pl.status != 0) return pl.status;
+  const int njobs = batched ? 2 : 1;
+  std::vector<FactorBuildJob> jobs((size_t)njobs);
+  Slot* s = nullptr;
+  for (int k = 0; k < njobs; k++) {
+    st = iak_get_slot(ds, (size_t)k, &s);
+    if (st != 0) return st;
+    CovArgs a;
+    st = iak_square_tables(ctx, ds, pl, s, &a);
+    if (st != 0) return st;
+    FactorBuildJob& jb = jobs[(size_t)k];
+    jb.a = a; jb.d_W = ds->d_W; jb.q = ds->q; jb.n = s->n; jb.Npad = s->Npad; jb.ld = s->ld; jb.nCB = s->nCB; jb.d_L = s->d_L;
+  }
+  st = launch_cov_factor_jobs(ctx, jobs.data(), njobs);
+  if (st != 0) return st;
+  const int64_t n = ds->n;
+  double* d_out = nullptr; double* d_w = nullptr;
+  int rc = IAK3D_OK;
+  do {
+    if (iak_pool_alloc(ctx, (void**)&d_out, (size_t)n * n * 8) != cudaSuccess) { ctx->err = "factor_build_fetch: allocation failed"; rc = IAK3D_ERR_CUDA; cudaGetLastError(); break; }
+    rc = launch_unblock_rect(ctx, s->d_L, s->ld / UR, 0, n, n, 1, d_out, n);
+    if (rc != 0) break;
+    cudaMemcpyAsync(A, d_out, (size_t)n * n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (Wrows && ds->q > 0) {
+      if (iak_pool_alloc(ctx, (void**)&d_w, (size_t)ds->q * n * 8) != cudaSuccess) { ctx->err = "factor_build_fetch: allocation failed"; rc = IAK3D_ERR_CUDA; cudaGetLastError(); break; }
+      rc = launch_unblock_rect(ctx, s->d_L, s->ld / UR, s->Npad, ds->q, n, 0, d_w, ds->q);
+      if (rc != 0) break;
+      cudaMemcpyAsync(Wrows, d_w, (size_t)ds->q * n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ctx->err = std::string("factor_build_fetch: ") + cudaGetErrorString(e); rc = IAK3D_ERR_CUDA; }
+  } while (0);
+  iak_pool_free(ctx, d_out); iak_pool_free(ctx, d_w);
+  return rc;
+}
+
 extern "C" int iak3d_cov_diag(iak3d_ds* ds, const iak3d_pars* pars, double* diagC) {
   if (!ds || !pars || !diagC) return IAK3D_ERR_ARG;
   iak3d_ctx* ctx = ds->ctx;
@@ -1017,6 +1063,80 @@ extern "C" int iak3d_nll_terms_batch(iak3d_ctx* ctx, int32_t count, iak3d_ds* co
   const int st = iak3d_nll_terms_batch_enqueue(ctx, count, ds, pars);
   if (st != 0) return st;
   return iak3d_nll_terms_batch_fetch(ctx, lndetA, WiAW, status);
+}
+
+// ---- weighted on-device sum of a batch's terms (the composite likelihood's exchange buffer) ----
+// one block per group; thread e owns entry e of the q x q sum and walks the units in order: deterministic
+__global__ void wsum_kernel(const double* __restrict__ results, int stride, int count, const double* __restrict__ weight,
+                            const int32_t* __restrict__ group, const int32_t* __restrict__ plan_bad, int q, double* __restrict__ out) {
+  const int g = blockIdx.x, qq = q * q;
+  double* o = out + (int64_t)g * (qq + 2);
+  for (int e = threadIdx.x; e < qq + 2; e += blockDim.x) {
+    double s = 0.0;
+    for (int i = 0; i < count; i++) {
+      if (group[i] != g) continue;
+      const double* r = results + (int64_t)i * stride;
+      const bool bad = plan_bad[i] != 0 || r[1] != 0.0 || !isfinite(r[0]);
+      if (e == qq + 1) { s += bad ? 1.0 : 0.0; continue; }
+      if (bad) continue;
+      if (e == qq) { s += weight[i] * r[0]; continue; }
+      const int a = e % q, b = e / q;                        // column-major (a, b); keep the upper triangle: G(min, max)
+      const int lo = a < b ? a : b, hi = a < b ? b : a;
+      s += weight[i] * r[2 + (int64_t)hi * q + lo];
+    }
+    o[e] = s;
+  }
+}
+
+extern "C" int iak3d_nll_terms_batch_wsum(iak3d_ctx* ctx, int32_t count, iak3d_ds* const* ds, const iak3d_pars* pars,
+                                          const double* weight, const int32_t* group, int32_t ngroups, double* d_out, double* h_out) {
+  if (!ctx || !weight || !group || ngroups <= 0 || (!d_out && !h_out)) return IAK3D_ERR_ARG;
+  for (int i = 0; i < count; i++) if (group[i] < 0 || group[i] >= ngroups) { ctx->err = "batch_wsum: group out of range"; return IAK3D_ERR_ARG; }
+  int st = iak3d_nll_terms_batch_enqueue(ctx, count, ds, pars);
+  if (st != 0) return st;
+  Batch* b = ctx->batch;
+  b->pending = false;
+  const int q = b->q, qq = q * q;
+  double* d_w = nullptr; int32_t* d_g = nullptr; int32_t* d_bad = nullptr; double* d_own = nullptr;
+  int rc = IAK3D_OK;
+  do {
+    cudaError_t e = iak_pool_alloc(ctx, (void**)&d_w, (size_t)count * 8);
+    if (e == cudaSuccess && !d_out) { e = iak_pool_alloc(ctx, (void**)&d_own, (size_t)ngroups * (qq + 2) * 8); d_out = d_own; }
+    if (e == cudaSuccess) e = iak_pool_alloc(ctx, (void**)&d_g, (size_t)count * 4);
+    if (e == cudaSuccess) e = iak_pool_alloc(ctx, (void**)&d_bad, (size_t)count * 4);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_w, weight, (size_t)count * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_g, group, (size_t)count * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_bad, b->plan_status.data(), (size_t)count * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { ctx->err = std::string("batch_wsum: ") + cudaGetErrorString(e); rc = IAK3D_ERR_CUDA; cudaGetLastError(); break; }
+    wsum_kernel<<<ngroups, 128, 0, ctx->stream>>>(b->d_results, b->stride, count, d_w, d_g, d_bad, q, d_out);
+    ctx->launches++;
+    if (h_out) cudaMemcpyAsync(h_out, d_out, (size_t)ngroups * (qq + 2) * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ctx->err = std::string("batch_wsum: ") + cudaGetErrorString(e); rc = IAK3D_ERR_CUDA; break; }
+    for (int i = 0; i < count; i++)
+      if (b->plan_status[i] == 0 && ((int)b->h_results[(size_t)i * b->stride + 1] & 2)) {
+        ctx->err = "factorisation: dependency wait timed out (internal error)"; rc = IAK3D_ERR_TIMEOUT; break;
+      }
+  } while (0);
+  cudaStreamSynchronize(ctx->stream);
+  iak_pool_free(ctx, d_w); iak_pool_free(ctx, d_g); iak_pool_free(ctx, d_bad); iak_pool_free(ctx, d_own);
+  return rc;
+}
+
+extern "C" int iak3d_dataset_slot_bytes(iak3d_ds* ds, int64_t* slot_bytes, int64_t* free_bytes) {
+  if (!ds) return IAK3D_ERR_ARG;
+  cudaSetDevice(ds->ctx->device);
+  if (slot_bytes) {
+    const int64_t nd = ds->ndIU, nx = ds->nxU;
+    *slot_bytes = 8 * (ubuf_doubles(ds->ld, ds->Npad) + nx * nx + (NTAB_BUF + 3) * nd * nd + 2 * nd * round_up(ds->n, 2) +
+                       (int64_t)ds->nCB * INVD_BLOCK) + 4 * ((int64_t)ds->nRB * ds->nCB + ds->nCB);
+  }
+  if (free_bytes) {
+    size_t fr = 0, tot = 0;
+    CUDA_TRY(ds->ctx, cudaMemGetInfo(&fr, &tot));
+    *free_bytes = (int64_t)fr;
+  }
+  return IAK3D_OK;
 }
 
 // iAW = A^-1 W from the slot's factor (rows Npad.. hold Y' = (L^-1 W)').  out: n x q column-major (host).

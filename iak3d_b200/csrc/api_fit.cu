@@ -319,22 +319,17 @@ extern "C" int iak3d_predict_stage_spl(iak3d_fit* f, int64_t m, const double* xy
   return IAK3D_OK;
 }
 
-extern "C" int iak3d_predict_enqueue(iak3d_fit* f) {
-  if (!f) return IAK3D_ERR_ARG;
+// depth tables of the staged job -- cross (nd1 x nd2) and self (nd1 x nd1, for Ckk) -- Ckk, sigma2Veck, and the part of
+// the panel's CovArgs that does not change from chunk to chunk
+static int fit_prepare_job(iak3d_fit* f, CovArgs* ap) {
   iak3d_ctx* ctx = f->ctx;
-  if (!f->staged) { ctx->err = "predict_enqueue: nothing staged"; return IAK3D_ERR_ARG; }
-  cudaSetDevice(ctx->device);
-  f->enqueued = true;
   const int64_t m = f->m;
-  if (m == 0) return IAK3D_OK;
-  Slot* s = f->slot;
   iak3d_ds* ds = f->ds;
   const int64_t nd1 = f->nd1, nd2 = ds->ndIU;
   // compositeLikIAK3D.R:540-552 builds Ckh as a block of setCIAK3D of the joined supports: the square plan (cd1 quirk, :1052)
   const EvalPlan& px = f->opt_cross_square ? f->plan_kk : f->plan_x; const EvalPlan& ps = f->plan_kk;
   int rc;
-  // depth tables: cross (nd1 x nd2) and self (nd1 x nd1, for Ckk)
-  CovArgs a;
+  CovArgs& a = *ap;
   const double* Tself[3] = {nullptr, nullptr, nullptr};
   const double* avself[3] = {nullptr, nullptr, nullptr};
   rc = iak_cross_depth_tables(ctx, ds, px, f->d_dIU1, f->h_dIU1.data(), nd1, f->spl1U, f->d_T, f->d_s, a.T);
@@ -378,18 +373,68 @@ extern "C" int iak3d_predict_enqueue(iak3d_fit* f) {
   a.ntab = px.ntab;
   a.cx0 = px.cx0; a.cx1 = px.cx1; a.kd1 = px.kd1; a.cxd0 = px.cxd0; a.cxd1 = px.cxd1; a.cme = 0.0;
   a.xid_c = ds->d_xid; a.did_c = ds->d_did; a.nc = ds->n; a.ndIU_r = nd1;
+  return 0;
+}
+
+// the cross-covariance panel Ckh of map rows [r0, r0 + rows) in the blocked layout (rowsP x Npad, zero padded)
+static int fit_build_panel(iak3d_fit* f, CovArgs& a, int64_t r0, int64_t rows, int64_t rowsP) {
+  iak3d_ctx* ctx = f->ctx;
+  iak3d_ds* ds = f->ds;
+  const EvalPlan& px = f->opt_cross_square ? f->plan_kk : f->plan_x;
+  // horizontal tables of this chunk: every map row is its own location
+  int rc = launch_phix_table(ctx, px.H, f->d_xy + 2 * r0, rows, ds->d_xU, ds->nxU, px.has_phix ? f->d_phix : nullptr, f->d_same);
+  if (rc != 0) return rc;
+  a.phix = px.has_phix ? f->d_phix : nullptr;
+  a.same = f->d_same;
+  a.xid_r = f->d_iota; a.did_r = f->d_did1 + r0; a.nr = rows; a.nxU_r = rows;
+  return launch_cov_panel(ctx, a, f->d_P, rowsP, f->slot->Npad);
+}
+
+extern "C" int iak3d_predict_panel_fetch(iak3d_fit* f, int64_t chunk, double* Ckh, int64_t cap_rows, int64_t* rows_out) {
+  if (!f || !Ckh || chunk < 0) return IAK3D_ERR_ARG;
+  iak3d_ctx* ctx = f->ctx;
+  if (!f->staged) { ctx->err = "predict_panel_fetch: nothing staged"; return IAK3D_ERR_ARG; }
+  cudaSetDevice(ctx->device);
+  const int64_t PRED_CHUNK = fit_chunk_rows(ctx, f->slot->Npad);
+  const int64_t r0 = chunk * PRED_CHUNK;
+  if (r0 >= f->m) { ctx->err = "predict_panel_fetch: no such chunk"; return IAK3D_ERR_ARG; }
+  const int64_t rows = std::min(PRED_CHUNK, f->m - r0), rowsP = round_up(rows, TM), n = f->ds->n;
+  if (rows_out) *rows_out = rows;
+  if (cap_rows < rows) { ctx->err = "predict_panel_fetch: output too small"; return IAK3D_ERR_ARG; }
+  CovArgs a;
+  int rc = fit_prepare_job(f, &a);
+  if (rc != 0) return rc;
+  rc = fit_build_panel(f, a, r0, rows, rowsP);
+  if (rc != 0) return rc;
+  double* d_out = nullptr;
+  if (iak_pool_alloc(ctx, (void**)&d_out, (size_t)rows * n * 8) != cudaSuccess) { ctx->err = "predict_panel_fetch: allocation failed"; cudaGetLastError(); return IAK3D_ERR_CUDA; }
+  rc = launch_unblock_rect(ctx, f->d_P, rowsP / UR, 0, rows, n, 0, d_out, rows);
+  if (rc == 0) {
+    cudaMemcpyAsync(Ckh, d_out, (size_t)rows * n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "predict_panel_fetch: copy failed"; rc = IAK3D_ERR_CUDA; }
+  }
+  iak_pool_free(ctx, d_out);
+  return rc;
+}
+
+extern "C" int iak3d_predict_enqueue(iak3d_fit* f) {
+  if (!f) return IAK3D_ERR_ARG;
+  iak3d_ctx* ctx = f->ctx;
+  if (!f->staged) { ctx->err = "predict_enqueue: nothing staged"; return IAK3D_ERR_ARG; }
+  cudaSetDevice(ctx->device);
+  f->enqueued = true;
+  const int64_t m = f->m;
+  if (m == 0) return IAK3D_OK;
+  Slot* s = f->slot;
+  CovArgs a;
+  int rc = fit_prepare_job(f, &a);
+  if (rc != 0) return rc;
   CUDA_TRY(ctx, cudaMemsetAsync(f->d_status, 0, 2 * sizeof(int32_t), ctx->stream));
   const int64_t PRED_CHUNK = fit_chunk_rows(ctx, s->Npad);
   for (int64_t r0 = 0; r0 < m; r0 += PRED_CHUNK) {
     const int64_t rows = std::min(PRED_CHUNK, m - r0);
     const int64_t rowsP = round_up(rows, TM);
-    // horizontal tables of this chunk: every map row is its own location
-    rc = launch_phix_table(ctx, px.H, f->d_xy + 2 * r0, rows, ds->d_xU, ds->nxU, px.has_phix ? f->d_phix : nullptr, f->d_same);
-    if (rc != 0) return rc;
-    a.phix = px.has_phix ? f->d_phix : nullptr;
-    a.same = f->d_same;
-    a.xid_r = f->d_iota; a.did_r = f->d_did1 + r0; a.nr = rows; a.nxU_r = rows;
-    rc = launch_cov_panel(ctx, a, f->d_P, rowsP, s->Npad);
+    rc = fit_build_panel(f, a, r0, rows, rowsP);
     if (rc != 0) return rc;
     rc = fit_panel_tasks(f, rowsP);
     if (rc != 0) return rc;

@@ -190,6 +190,9 @@ int launch_cov_rect(iak3d_ctx* ctx, const CovArgs& a, double* d_out, int64_t ld,
 // launch_cov_rect when the row count is odd
 int launch_cov_panel(iak3d_ctx* ctx, const CovArgs& a, double* d_out, int64_t rows_total, int64_t cols_total);
 
+int launch_unblock_rect(iak3d_ctx* ctx, const double* d_B, int64_t nRU, int64_t r0, int64_t nr, int64_t nc, int mirror, double* d_out,
+                        int64_t ld);
+
 // ---- factorisation (chol.cu) -------------------------------------------------------------------
 struct ProblemDesc {
   double* L; int64_t nRUL;       // factor storage (blocked, nRUL row units); B operand + diagonal blocks

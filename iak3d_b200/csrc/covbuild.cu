@@ -323,6 +323,12 @@ int launch_cov_factor_jobs(iak3d_ctx* ctx, const FactorBuildJob* jobs, int count
     }
   }
   if (maxCB > 65535 || maxND > 65535) { ctx->err = "cov_factor: more than 65535 column blocks / unique depth intervals"; return IAK3D_ERR_ARG; }
+  // the interior path indexes the nxU x nxU horizontal table (and the nd x nd S table) with 32-bit offsets
+  for (int i = 0; i < count; i++)
+    if (jobs[i].a.nxU_r > 65535 || jobs[i].a.ndIU_r > 65535) {
+      ctx->err = "cov_factor: more than 65535 unique locations or depth intervals in one block (32-bit table offsets)";
+      return IAK3D_ERR_ARG;
+    }
   if ((size_t)count > ctx->fbjobs_cap) {
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->d_fbjobs); ctx->d_fbjobs = nullptr;
@@ -489,6 +495,29 @@ int launch_pack_factor_layout(iak3d_ctx* ctx, const double* d_C, int64_t n, cons
   dim3 grid((unsigned)((ld + 255) / 256), (unsigned)Npad);
   if (Npad > 65535) { ctx->err = "pack_factor: more than 65535 columns"; return IAK3D_ERR_ARG; }
   pack_factor_kernel<<<grid, 256, 0, ctx->stream>>>(d_C, n, d_b, q, Npad, ld, d_L);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return 0;
+}
+
+// ---- blocked buffer -> column-major (parity tests of the factor build and of the kriging panel) ----------------------
+// out[c*ld + i] = B(r0 + i, c) for i < nr, c < nc; mirror != 0: the entry of the lower triangle, B(max, min)
+__global__ void unblock_rect_kernel(const double* __restrict__ B, int64_t nRU, int64_t r0, int64_t nr, int64_t nc, int mirror,
+                                    double* __restrict__ out, int64_t ld) {
+  const int64_t c = blockIdx.y;
+  if (c >= nc) return;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nr; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t gi = r0 + i;
+    out[c * ld + i] = (mirror && gi < c) ? B[uidx(c, gi, nRU)] : B[uidx(gi, c, nRU)];
+  }
+}
+int launch_unblock_rect(iak3d_ctx* ctx, const double* d_B, int64_t nRU, int64_t r0, int64_t nr, int64_t nc, int mirror, double* d_out,
+                        int64_t ld) {
+  if (nr <= 0 || nc <= 0) return 0;
+  if (nc > 65535) { ctx->err = "unblock_rect: more than 65535 columns"; return IAK3D_ERR_ARG; }
+  unsigned bx = (unsigned)((nr + 255) / 256);
+  if (bx > 256) bx = 256;
+  unblock_rect_kernel<<<dim3(bx, (unsigned)nc), 256, 0, ctx->stream>>>(d_B, nRU, r0, nr, nc, mirror, d_out, ld);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return 0;

@@ -60,6 +60,38 @@ class BlockComm:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return t.cpu().numpy()
 
+    def device_buffer(self, k):
+        """Persistent float64 CUDA tensor of at least k elements on this rank's GPU (NCCL only; None otherwise): the
+        library writes the composite-likelihood sums straight into it (iak3d_nll_terms_batch_wsum) and NCCL reduces it in
+        place -- no host staging before the exchange."""
+        import torch
+        import torch.distributed as dist
+        if self.world == 1 or dist.get_backend() != "nccl":
+            return None
+        if getattr(self, "_dbuf", None) is None or self._dbuf.numel() < k:
+            self._dbuf = torch.zeros(max(int(k), 1024), dtype=torch.float64, device=torch.device("cuda", self.local_rank if self._dev is None else self._dev))
+            self._hbuf = torch.zeros(self._dbuf.numel(), dtype=torch.float64).pin_memory()
+            self._ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        return self._dbuf
+
+    def allreduce_device(self, k, timings=None):
+        """In-place NCCL all-reduce (sum) of the first k elements of the device buffer, then ONE device-to-host copy into
+        pinned memory.  `timings` (a dict) accumulates the device time of the collective in `allreduce_us`."""
+        import torch
+        import torch.distributed as dist
+        t = self._dbuf[:k]
+        if timings is not None:
+            self._ev[0].record()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        if timings is not None:
+            self._ev[1].record()
+        self._hbuf[:k].copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        if timings is not None:
+            timings["allreduce_us"] = timings.get("allreduce_us", 0.0) + 1e3 * self._ev[0].elapsed_time(self._ev[1])
+            timings["allreduce_calls"] = timings.get("allreduce_calls", 0) + 1
+        return self._hbuf[:k].numpy().copy()
+
     def allreduce_max(self, buf):
         if self.world == 1:
             return np.asarray(buf, dtype=np.float64)
@@ -67,6 +99,12 @@ class BlockComm:
         t = self._tensor(buf)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.cpu().numpy()
+
+    def gather_scalar(self, x):
+        """x of every rank, in rank order (one-hot all-reduce: bench.py's per-rank records)"""
+        v = np.zeros(self.world)
+        v[self.rank] = float(x)
+        return self.allreduce_sum(v)
 
     def barrier(self):
         if self.world > 1:

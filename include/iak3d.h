@@ -123,6 +123,14 @@ IAK3D_API int iak3d_cov_cross(iak3d_ds* ds2, const iak3d_pars* pars, int64_t n1,
 IAK3D_API int iak3d_cov_cross_spl(iak3d_ds* ds2, const iak3d_pars* pars, int64_t n1, const double* xy1,
                         const double* dI1, const double* const* Xspl1, double* out);
 
+/* The matrix the likelihood actually factorises: setCIAK3D (fitIAK3D.R:955-1112) as the FACTOR BUILD forms it --
+ * `cov_factor_kernel` into the blocked factor buffer, the kernel the covariance roofline is quoted on -- copied back as a
+ * full symmetric n x n column-major matrix (the lower triangle is what the kernel wrote, the upper triangle its mirror).
+ * batched != 0 sends two identical jobs through the batch entry point of the kernel (the job-array instantiation the
+ * forward-difference gradient and the composite likelihood use) and returns the second; 0 uses the single-job one.
+ * Wrows (q x n column-major, may be NULL) receives the bordered W' rows as the kernel laid them out.  Parity tests only. */
+IAK3D_API int iak3d_factor_build_fetch(iak3d_ds* ds, const iak3d_pars* pars, int32_t batched, double* A, double* Wrows);
+
 /* ---- factorisation --------------------------------------------------------------------------
  * lndetANDinvCb (optim_functions.R:268-312, methodSolveTEST == 1): chol(C), lndetC = 2 sum log diag,
  * invCb = C^-1 b (n x nrhs) or C^-1 itself when b == NULL (then invCb is n x n).  Returns
@@ -143,6 +151,22 @@ IAK3D_API int iak3d_nll_terms_batch(iak3d_ctx* ctx, int32_t count, iak3d_ds* con
 /* split form for device-resident timing: enqueue on the context stream, then fetch (sync + D2H). */
 IAK3D_API int iak3d_nll_terms_batch_enqueue(iak3d_ctx* ctx, int32_t count, iak3d_ds* const* ds, const iak3d_pars* pars);
 IAK3D_API int iak3d_nll_terms_batch_fetch(iak3d_ctx* ctx, double* lndetA, double* WiAW, int32_t* status);
+
+/* The exchange step of the composite likelihood made cheap (compositeLikIAK3D.R:63-64, Reduce('+') over the workers; 81-83):
+ * the same batch, but the per-unit terms never travel to the host -- they are summed on the device, unit i with weight[i]
+ * into group[i] (0 <= group[i] < ngroups: one group per parameter set, so that the npar + 1 composite-likelihood
+ * evaluations of a forward-difference gradient are ONE launch and ONE exchange):
+ *     out[g] = { sum_i w_i forceSymmetric(WiAW_i) (q*q, column-major; upper triangle kept, fitIAK3D.R:811),
+ *                sum_i w_i lndetA_i,  number of units of the group that failed (not SPD / invalid parameters) }
+ * in the fixed order of i (deterministic).  d_out is a DEVICE pointer to ngroups * (q*q + 2) doubles owned by the caller --
+ * the buffer a multi-GPU caller hands to ncclAllReduce next (the one entry point whose pointer is not a host pointer);
+ * h_out (may be NULL) receives a host copy; d_out may be NULL when only the host copy is wanted (single GPU).  The
+ * context's stream is synchronised before returning. */
+IAK3D_API int iak3d_nll_terms_batch_wsum(iak3d_ctx* ctx, int32_t count, iak3d_ds* const* ds, const iak3d_pars* pars,
+                               const double* weight, const int32_t* group, int32_t ngroups, double* d_out, double* h_out);
+/* bytes of device memory one more simultaneous evaluation of this dataset needs (a slot: factor buffer + tables), and the
+ * device memory currently free -- for callers that size their batches (composite-likelihood gradient) */
+IAK3D_API int iak3d_dataset_slot_bytes(iak3d_ds* ds, int64_t* slot_bytes, int64_t* free_bytes);
 
 /* ---- analytic gradient of the profiled REML / ML objective (replaces the npar + 1 evaluations of gradnllIAK3D,
  * fitIAK3D.R:1865-1886) --------------------------------------------------------------------------
@@ -186,6 +210,12 @@ IAK3D_API int iak3d_predict_fetch(iak3d_fit* fit, double* z, double* v);
  * predictions (predictIAK3D.R:229-255, setmuIAK3D) and profilePredictIAK3D are assembled from these by the caller.
  * Call after iak3d_predict_enqueue, before or after iak3d_predict_fetch. */
 IAK3D_API int iak3d_predict_fetch_terms(iak3d_fit* fit, double* Ckk, double* sigma2Veck, double* CkhiCz_muhat, double* CkhiCChk);
+/* The kriging panel as the predictor builds it: setCIAK3D2 (fitIAK3D.R:1117-1252) of chunk `chunk` of the staged map supports
+ * against the data, made by the product's panel kernels (`phix_rect_kernel` + `cov_panel_kernel`, or the odd-row-count
+ * fallback) in the blocked layout and copied back as rows x n column-major (rows = supports of that chunk; *rows_out).
+ * Call after iak3d_predict_stage.  Parity tests only. */
+IAK3D_API int iak3d_predict_panel_fetch(iak3d_fit* fit, int64_t chunk, double* Ckh, int64_t cap_rows, int64_t* rows_out);
+
 /* options of a kept fit, set before iak3d_predict_stage:
  *  IAK3D_FIT_KEEP_CKHICX   keep Ckh iC X (m x p) of every batch for iak3d_predict_fetch_CkhiCX (composite-likelihood block
  *                          prediction sums it over block pairs, compositeLikIAK3D.R:590-599);
