@@ -162,7 +162,12 @@ def run_s5(args, rank, local_rank, world, comm):
         Gt = np.transpose(G_, (0, 2, 1))
         return list(api.reml_tail_batch(np.triu(Gt) + np.transpose(np.triu(Gt, 1), (0, 2, 1)), lnd_, n, p, True))
 
-    peaks = dict(dfma=ctx.fp64_peak(0), dmma=ctx.fp64_peak(1))
+    peaks = dict(dfma=ctx.fp64_peak(0), dmma=ctx.fp64_peak(1), dfma_and_dmma_together=ctx.fp64_peak(2))
+    # a write-only stream (cudaMemsetAsync, 16 x 256 MiB): the ceiling of a kernel that only writes, as the covariance build does
+    ctx.flush_l2(); ctx.sync(); ctx.timer_start()
+    for _ in range(16):
+        ctx.flush_l2()
+    write_only_gbs = 16 * (256 << 20) / (ctx.timer_stop() * 1e-3) / 1e9
     for w in range(args.warmup):
         step_resident(-1 - w)
     assert np.all(st == 0), f"warm-up evaluations failed: {st}"
@@ -233,7 +238,7 @@ def run_s5(args, rank, local_rank, world, comm):
         metric=METRIC, value=value, unit="evals/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
         config=s5_config(n, p, sm.nxU, sm.ndIU, modelx, types, cmeOpt, nb, world),
-        single_eval_ms=single_ms, single_eval_per_s=1e3 / single_ms, gradient_wall_ms=grad_ms,
+        single_eval_ms=single_ms, single_eval_per_s=1e3 / single_ms, gradient_wall_ms=grad_ms, fp64_peaks_tflops=peaks,
         stage_ms=dict(tables=stage[0], cov_build=stage[1], factorise=stage[2], finish=stage[3]),
         roofline=dict(kernel="tile_task_kernel (tile Cholesky + bordered solves, FP64 DMMA)", bound="tensor", achieved=tf,
                       peak=peaks["dmma"], unit="TFLOP/s", frac=tf / peaks["dmma"], traffic=ncu_traffic("tile_task_kernel", n, nb),
@@ -242,9 +247,11 @@ def run_s5(args, rank, local_rank, world, comm):
                                   "figure); DFMA microbenchmark = %.1f TFLOP/s" % peaks["dfma"]),
         roofline_cov_build=dict(kernel="cov_factor_kernel", bound="hbm", achieved=cov_gbs, peak=hbm_peak, unit="GB/s",
                                 frac=cov_gbs / hbm_peak, bytes_per_launch=8.0 * n * (n + 1) / 2.0, peak_source=hbm_src,
-                                traffic=ncu_traffic("cov_factor_kernel", n, nb),
-                                note="stage time: one batched launch + the table expansion; write-only peak of this layout measured at "
-                                     "7.0 TB/s (n = 20000) / 4.5 TB/s (n = 5000, one launch), scripts/micro/store_pattern.cu"),
+                                traffic=ncu_traffic("cov_factor_kernel", n, nb), write_only_peak=write_only_gbs,
+                                frac_of_write_only=cov_gbs / write_only_gbs,
+                                note="stage time: one batched launch + the table expansion.  peak = the measured COPY bandwidth (read + write "
+                                     "bytes); the kernel only writes, write_only_peak = cudaMemsetAsync of 4 GiB in this run; history of the "
+                                     "kernel in profiles/cov_build_history_r02.txt"),
         e2e=dict(value=evals / e2e_s, unit="evals/s", h2d_bytes_per_step=int(W.nbytes + nb * C.sizeof(Pars)),
                  d2h_bytes_per_step=int(nb * (2 + q * q) * 8)),
         gpu_launches=int(launches), clocks=clocks)

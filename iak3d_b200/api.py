@@ -769,12 +769,16 @@ def cl_terms_sets(units, structs, q, comm=None, timings=None):
     if units:
         ctx = units[0]["setup"].ctx
         try:
-            sb, fr = C.c_int64(), C.c_int64()
-            need = 0
-            for u in units:
-                ctx.check(ctx.lib.iak3d_dataset_slot_bytes(u["setup"].h, C.byref(sb), C.byref(fr)))
-                need += sb.value
-            g = int(max(1, min(nsets, (0.7 * ctx.device_info()["total_mem"]) // max(need, 1))))
+            g = 1
+            if nsets > 1:                        # parameter sets per launch: a factor buffer per problem in flight must fit
+                need = 0
+                for u in units:
+                    if "slot_bytes" not in u:
+                        sb = C.c_int64()
+                        ctx.check(ctx.lib.iak3d_dataset_slot_bytes(u["setup"].h, C.byref(sb), None))
+                        u["slot_bytes"] = sb.value
+                    need += u["slot_bytes"]
+                g = int(max(1, min(nsets, (0.7 * ctx.device_info()["total_mem"]) // max(need, 1))))
             wts = f64(np.array([u["weight"] for u in units], float))
             for s0 in range(0, nsets, g):
                 s1 = min(nsets, s0 + g)

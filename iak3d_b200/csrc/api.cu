@@ -301,7 +301,7 @@ int iak_alloc_slot(iak3d_ctx* ctx, int64_t n, int32_t q, int64_t nxU, int64_t nd
     A((void**)&s->d_flags, nflags * sizeof(int32_t));
     A((void**)&s->d_logsum, (size_t)s->nCB * sizeof(double));
     A((void**)&s->d_G, 64 * 64 * sizeof(double));
-    if (ndIU > 0) A((void**)&s->d_E, (size_t)2 * ndIU * round_up(n, 2) * sizeof(double));
+    if (ndIU > 0) A((void**)&s->d_E, (size_t)2 * ndIU * round_up(n, 16) * sizeof(double));
     if (e == cudaSuccess) e = cudaMemsetAsync(s->d_flags, 0, nflags * sizeof(int32_t), ctx->stream);
   }
   if (e != cudaSuccess) {
@@ -1128,7 +1128,7 @@ extern "C" int iak3d_dataset_slot_bytes(iak3d_ds* ds, int64_t* slot_bytes, int64
   cudaSetDevice(ds->ctx->device);
   if (slot_bytes) {
     const int64_t nd = ds->ndIU, nx = ds->nxU;
-    *slot_bytes = 8 * (ubuf_doubles(ds->ld, ds->Npad) + nx * nx + (NTAB_BUF + 3) * nd * nd + 2 * nd * round_up(ds->n, 2) +
+    *slot_bytes = 8 * (ubuf_doubles(ds->ld, ds->Npad) + nx * nx + (NTAB_BUF + 3) * nd * nd + 2 * nd * round_up(ds->n, 16) +
                        (int64_t)ds->nCB * INVD_BLOCK) + 4 * ((int64_t)ds->nRB * ds->nCB + ds->nCB);
   }
   if (free_bytes) {
@@ -1292,7 +1292,7 @@ extern "C" int iak3d_flush_l2(iak3d_ctx* ctx) {
   return IAK3D_OK;
 }
 extern "C" int iak3d_fp64_peak(iak3d_ctx* ctx, int32_t kind, double* tflops) {
-  if (!ctx || !tflops || kind < 0 || kind > 1) return IAK3D_ERR_ARG;
+  if (!ctx || !tflops || kind < 0 || kind > 2) return IAK3D_ERR_ARG;
   cudaSetDevice(ctx->device);
   return launch_peak(ctx, kind, tflops);
 }

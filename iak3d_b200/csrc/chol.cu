@@ -879,6 +879,36 @@ __global__ void __launch_bounds__(256) peak_dmma_kernel(double* out, int iters) 
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// kind 2: are the two FP64 paths one pipe?  Even warps issue DMMA, odd warps DFMA, 8 independent chains each.  If the
+// combined rate exceeds either peak alone the pipes are separate and a mixed kernel could use both.
+__global__ void __launch_bounds__(256) peak_mixed_kernel(double* out, int iters) {
+  double s = 0.0;
+  if (((threadIdx.x >> 5) & 1) == 0) {
+    double acc[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+    const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) dmma(acc[i][0], acc[i][1], a, b);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += acc[i][0] + acc[i][1];
+  } else {
+    double a[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+    const double b = 1.0000001, c = 1e-12;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) a[i] = fma(a[i], b, c);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += a[i];
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace
 
 int chol_configure(iak3d_ctx* ctx) {
@@ -944,7 +974,8 @@ int launch_peak(iak3d_ctx* ctx, int kind, double* tflops) {
   for (int rep = 0; rep < 4; rep++) {
     CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
     if (kind == 0) peak_dfma_kernel<<<blocks, threads, 0, ctx->stream>>>(d_out, iters);
-    else peak_dmma_kernel<<<blocks, threads, 0, ctx->stream>>>(d_out, iters);
+    else if (kind == 1) peak_dmma_kernel<<<blocks, threads, 0, ctx->stream>>>(d_out, iters);
+    else peak_mixed_kernel<<<blocks, threads, 0, ctx->stream>>>(d_out, iters);
     ctx->launches++;
     CUDA_TRY(ctx, cudaEventRecord(e1, ctx->stream));
     CUDA_TRY(ctx, cudaEventSynchronize(e1));
@@ -954,7 +985,8 @@ int launch_peak(iak3d_ctx* ctx, int kind, double* tflops) {
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
   double flops;
   if (kind == 0) flops = (double)blocks * threads * iters * 16.0 * 2.0;
-  else flops = (double)blocks * (threads / 32) * iters * 8.0 * (8.0 * 8.0 * 4.0 * 2.0);
+  else if (kind == 1) flops = (double)blocks * (threads / 32) * iters * 8.0 * (8.0 * 8.0 * 4.0 * 2.0);
+  else flops = 0.5 * (double)blocks * threads * iters * 16.0 * 2.0 + 0.5 * (double)blocks * (threads / 32) * iters * 8.0 * (8.0 * 8.0 * 4.0 * 2.0);
   *tflops = flops / (best * 1e-3) / 1e12;
   return 0;
 }

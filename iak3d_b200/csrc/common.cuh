@@ -70,7 +70,7 @@ struct Slot {
   double* d_logsum = nullptr;     // nCB
   double* d_G = nullptr;          // 64*64 Gram accumulator (WiAW)
   double* d_lncol = nullptr;      // 2n: sigma2Vec - diag(C) (lognormal bias column of W) | scratch
-  double* d_E = nullptr;          // 2 * ndIU * round_up(n,2): depth tables expanded along the rows (factor build)
+  double* d_E = nullptr;          // 2 * ndIU * round_up(n,16): depth tables expanded along the rows (factor build)
   int32_t epoch = 0;              // flags are valid when == epoch
 };
 
@@ -148,7 +148,7 @@ struct CovArgs {
   const double* T[3];      // distinct depth tables (may alias); T[tidx[c]] for c = cd1, cxd0, cxd1; tidx<0 = absent
   const double* av[3] = {nullptr, nullptr, nullptr};   // avVarVec of each table on the row set (square builds only)
   double* comb = nullptr;  // nd^2 doubles of per-evaluation workspace: S table of the factor build's generic path
-  double* Ebuf = nullptr;  // 2 * nd * round_up(n,2) doubles of per-evaluation workspace: depth tables expanded along the rows
+  double* Ebuf = nullptr;  // 2 * nd * round_up(n,16) doubles of per-evaluation workspace: depth tables expanded along the rows
   const double* E_shared = nullptr;   // one-table case: the expansion another evaluation of the batch already made
   int tidx[3];
   int ntab;

@@ -296,7 +296,7 @@ int launch_cov_factor_jobs(iak3d_ctx* ctx, const FactorBuildJob* jobs, int count
     FbJob& J = hj[(size_t)i];
     covdev_from(b.a, &J.a);
     J.a.one_table = cov_one_table(b.a) ? 1 : 0;      // every present component points at table 0 (cxd0 is always present)
-    J.a.ldE = round_up(b.n, 2);
+    J.a.ldE = round_up(b.n, 16);        // every table row starts on a 128-byte line (ncu: half-empty load wavefronts otherwise)
     J.W = b.d_W; J.L = b.d_L; J.lncol_v = b.d_lncol; J.n = b.n; J.Npad = b.Npad; J.ld = b.ld; J.q = b.q; J.nCB = b.nCB;
     J.lncol = b.d_lncol ? b.lncol : -1;
     J.Ebuf = b.a.Ebuf; J.Stab = b.a.comb;

@@ -200,6 +200,7 @@ int hx_init(HxPrm* H, int modelx, double a, double nu) {
     H->s = sqrt(2.0 * nu) / a;
     H->lconst = -(nu - 1.0) * log(2.0) - lgamma(nu);
     H->half = (nu == 0.5) ? 1 : (nu == 1.5) ? 3 : (nu == 2.5) ? 5 : 0;
+    if (H->half == 0) iak_bk_fit_init(&H->bk, nu);                        // order-dependent work of K_nu, once per table
   } else if (modelx == IAK3D_MODELX_WENDLAND) {
     if (!(a > 0.0 && nu >= 1.0 && nu <= 20.0)) return IAK3D_BAD_PARS;    // :379
     H->kf = (int)floor(nu); H->kc = (int)ceil(nu);

@@ -266,7 +266,8 @@ IAK3D_API int iak3d_sync(iak3d_ctx* ctx);
 IAK3D_API int iak3d_timer_start(iak3d_ctx* ctx);                 /* cudaEventRecord on the context stream */
 IAK3D_API int iak3d_timer_stop(iak3d_ctx* ctx, double* ms);      /* record + synchronize + elapsed */
 IAK3D_API int iak3d_flush_l2(iak3d_ctx* ctx);                    /* writes a 256 MiB scratch buffer */
-/* FP64 peak microbenchmarks: kind 0 = DFMA (vector), 1 = DMMA (mma.sync m8n8k4 f64). */
+/* FP64 peak microbenchmarks: kind 0 = DFMA (vector), 1 = DMMA (mma.sync m8n8k4 f64), 2 = both at once (alternate warps):
+ * a combined rate above either alone would mean two separate pipes -- measured: it is not. */
 IAK3D_API int iak3d_fp64_peak(iak3d_ctx* ctx, int32_t kind, double* tflops);
 /* per-stage device times (ms) of the last nll_terms_batch_enqueue: [0] table kernels, [1] covariance
  * build, [2] factorisation, [3] finish; and the algorithmic flop / byte counts of that launch. */

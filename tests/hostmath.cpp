@@ -25,6 +25,14 @@ double hm_besselk_rt(double nu, double x) {
   for (int i = 1; i < IAK_BK_NRT; i++) iak_besselk_table(nu, rt, i);
   return iak_besselk(nu, x, rt);
 }
+/* the Chebyshev-fit variant the device table kernels use for x >= 2 (order-dependent work done once, hx_init) */
+double hm_besselk_fit(double nu, double x) {
+  double rt[4 * IAK_BK_NRT];
+  for (int i = 1; i < IAK_BK_NRT; i++) iak_besselk_table(nu, rt, i);
+  BkFit F;
+  iak_bk_fit_init(&F, nu);
+  return iak_besselk(nu, x, rt, &F);
+}
 /* Matern / spherical only (the Wendland coefficients are prepared in tables.cu) */
 double hm_phix(double D, int modelx, double a, double nu) {
   HxPrm H;
@@ -32,6 +40,8 @@ double hm_phix(double D, int modelx, double a, double nu) {
   H.s = sqrt(2.0 * nu) / a;
   H.lconst = -(nu - 1.0) * log(2.0) - lgamma(nu);
   H.half = (nu == 0.5) ? 1 : (nu == 1.5) ? 3 : (nu == 2.5) ? 5 : 0;
+  H.bk.on = 0;
+  if (H.half == 0) iak_bk_fit_init(&H.bk, nu);
   return iak_phix(D, &H);
 }
 }

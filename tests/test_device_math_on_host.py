@@ -26,6 +26,7 @@ def hm():
     lib.hm_avvar.argtypes = [d, d, d, d, C.c_int, d, d, C.POINTER(d)]
     lib.hm_besselk.argtypes = [d, d]; lib.hm_besselk.restype = d
     lib.hm_besselk_rt.argtypes = [d, d]; lib.hm_besselk_rt.restype = d
+    lib.hm_besselk_fit.argtypes = [d, d]; lib.hm_besselk_fit.restype = d
     lib.hm_phix.argtypes = [d, C.c_int, d, d]; lib.hm_phix.restype = d
     return lib
 
@@ -102,6 +103,24 @@ def test_besselk_against_scipy(hm):
             worst = max(worst, abs(got - want) / want)
     assert worst <= 5e-13
     assert hm.hm_besselk(0.8, 800.0) == 0.0
+
+
+def test_besselk_chebyshev_fit_matches_continued_fraction(hm):
+    """The table kernels evaluate K_nu for x >= 2 from a per-order Chebyshev fit of the scaled continued-fraction values
+    (iak3d_math.h: BkFit): it must reproduce the continued fraction itself to a few ulp over the whole order range the
+    reference accepts (0.05 <= nu <= 20, iaCovMatern.R:354) and agree with SciPy like the original does."""
+    rng = np.random.default_rng(11)
+    for nu in (0.05, 0.31, 0.5000001, 0.8, 1.0, 1.49, 1.7, 2.2, 3.3, 5.0, 7.3, 12.1, 19.99, 20.0):
+        xs = np.concatenate([np.exp(rng.uniform(np.log(2.0), np.log(700.0), 1500)),
+                             [2.0, 2.0000001, 4.0, 8.0, 16.0, 15.9999, 16.0001, 700.0, 705.3]])
+        fit = np.array([hm.hm_besselk_fit(nu, x) for x in xs]); cf = np.array([hm.hm_besselk(nu, x) for x in xs])
+        m = cf > 1e-300
+        assert np.max(np.abs(fit[m] / cf[m] - 1.0)) <= 2e-14, nu
+        assert np.max(np.abs(fit[m] / ssp.kv(nu, xs[m]) - 1.0)) <= 5e-13, nu
+        assert hm.hm_besselk_fit(nu, 706.0) == 0.0                    # R's xmax_BESS_K cut-off is kept
+    # below x = 2 nothing changes (Temme's series)
+    for x in (1e-3, 0.5, 1.9999):
+        assert hm.hm_besselk_fit(0.8, x) == hm.hm_besselk_rt(0.8, x)
 
 
 def test_phix_against_oracle(hm):
