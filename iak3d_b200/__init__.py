@@ -10,4 +10,5 @@ from .api import (calcbetavXbeta, lnN_design, makeXnsClampedUG0, nrUpdatesIAK3Dl
                   nll_terms_batch, nllIAK3D, nllIAK3D_CL, gradnllIAK3D_CL, predictIAK3D, readParsIAK3D, reml_tail, reml_tail_batch, setCIAK3D, setCIAK3D2,
                   setupIAK3D, setupIAK3D2, setupIAK3D_CL, spatialCovIAK3D, tauTfm)
 from .devmat import DeviceMat, cov_mat  # noqa: F401
+from .design import DesignModel, makeXvX  # noqa: F401
 from . import parallel, synth  # noqa: F401

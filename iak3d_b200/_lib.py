@@ -96,6 +96,12 @@ _PROTOS = {
     "iak3d_mat_spd_inverse": (C.c_int, [_vp, _ip]),
     "iak3d_mat_cov_build": (C.c_int, [_vp, C.POINTER(Pars), _vp]),
     "iak3d_mat_coldot": (C.c_int, [_vp, _vp, _dp]),
+    "iak3d_design_create": (C.c_int, [_vp, _ip, _i64, _dp, _i64, C.POINTER(_vp)]),
+    "iak3d_design_destroy": (C.c_int, [_vp]),
+    "iak3d_design_info": (C.c_int, [_vp, _ip, _ip]),
+    "iak3d_design_eval": (C.c_int, [_vp, _i64, _dp, _dp, _dp, _dp, _dp]),
+    "iak3d_predict_stage_grid": (C.c_int, [_vp, _vp, _i64, _dp, _dp, _i64, _dp, _i64]),
+    "iak3d_predict_fetch_X": (C.c_int, [_vp, _dp]),
     "iak3d_last_stage_ms": (C.c_int, [_vp, _dp, _dp, _dp]),
     "iak3d_last_task_profile": (C.c_int, [_vp, C.POINTER(_i64), _i64, C.POINTER(_i64)]),
 }

@@ -1093,6 +1093,20 @@ class KeptFit:
             self.ctx.check(self.ctx.lib.iak3d_predict_stage(self.h, xMap.shape[0], dptr(xMap), dptr(dIMap), dptr(XMap)))
         self._m = xMap.shape[0]
 
+    def stage_grid(self, design, xCell, covCell, dIInt, nxPerBatch=2000):
+        """The whole map in one staging (predictIAK3D.R:144-155): ncell cells x nint intervals, design rows made on the
+        device by `design` (design.DesignModel == makeXvX).  Results come back interval-major: row i * ncell + c."""
+        xCell = f64(np.asarray(xCell, float).reshape(-1, 2)); dIInt = f64(np.asarray(dIInt, float).reshape(-1, 2))
+        ncell, nint = xCell.shape[0], dIInt.shape[0]
+        cv = f64(np.asarray(covCell, float).reshape(ncell, design.ncov)) if design.ncov > 0 else None
+        self.ctx.check(self.ctx.lib.iak3d_predict_stage_grid(self.h, design.h, ncell, dptr(xCell), dptr(cv), nint, dptr(dIInt), int(nxPerBatch)))
+        self._m = ncell * nint
+
+    def fetch_X(self):
+        X = np.empty((self._m, self.p), order="F")
+        self.ctx.check(self.ctx.lib.iak3d_predict_fetch_X(self.h, dptr(X)))
+        return X
+
     def enqueue(self):
         self.ctx.check(self.ctx.lib.iak3d_predict_enqueue(self.h))
 

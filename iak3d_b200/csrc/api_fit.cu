@@ -258,18 +258,9 @@ static int fit_panel_tasks(iak3d_fit* f, int64_t rowsP) {
   return 0;
 }
 
-extern "C" int iak3d_predict_stage(iak3d_fit* f, int64_t m, const double* xyMap, const double* dIMap, const double* XMap) {
-  return iak3d_predict_stage_spl(f, m, xyMap, dIMap, XMap, nullptr);
-}
-
-extern "C" int iak3d_predict_stage_spl(iak3d_fit* f, int64_t m, const double* xyMap, const double* dIMap, const double* XMap,
-                                       const double* const* Xspl1) {
-  if (!f || m < 0 || (m > 0 && (!xyMap || !dIMap || !XMap))) return IAK3D_ERR_ARG;
+// per-support buffers of a staged job
+static int fit_reserve_job(iak3d_fit* f, int64_t m) {
   iak3d_ctx* ctx = f->ctx;
-  cudaSetDevice(ctx->device);
-  f->staged = false; f->enqueued = false;
-  f->m = m;
-  if (m == 0) { f->staged = true; return IAK3D_OK; }
   const int p = f->p;
   if (m > f->cap_m) {
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -291,6 +282,23 @@ extern "C" int iak3d_predict_stage_spl(iak3d_fit* f, int64_t m, const double* xy
     CUDA_TRY(ctx, cudaMalloc(&f->d_cx, (size_t)m * p * 8));
     f->cx_cap = (int64_t)m * p;
   }
+  return 0;
+}
+
+extern "C" int iak3d_predict_stage(iak3d_fit* f, int64_t m, const double* xyMap, const double* dIMap, const double* XMap) {
+  return iak3d_predict_stage_spl(f, m, xyMap, dIMap, XMap, nullptr);
+}
+
+extern "C" int iak3d_predict_stage_spl(iak3d_fit* f, int64_t m, const double* xyMap, const double* dIMap, const double* XMap,
+                                       const double* const* Xspl1) {
+  if (!f || m < 0 || (m > 0 && (!xyMap || !dIMap || !XMap))) return IAK3D_ERR_ARG;
+  iak3d_ctx* ctx = f->ctx;
+  cudaSetDevice(ctx->device);
+  f->staged = false; f->enqueued = false;
+  f->m = m;
+  if (m == 0) { f->staged = true; return IAK3D_OK; }
+  const int p = f->p;
+  { const int rcj = fit_reserve_job(f, m); if (rcj != 0) return rcj; }
   // unique depth intervals of the map supports (usually one per call: predictIAK3D.R:150)
   std::vector<int32_t> did1; std::vector<double> dIU1;
   iak_unique_first(m, dIMap, dIMap + m, did1, dIU1);
@@ -316,6 +324,66 @@ extern "C" int iak3d_predict_stage_spl(iak3d_fit* f, int64_t m, const double* xy
   int rc = fit_reserve_panel(f, std::min(PRED_CHUNK, m), f->nd1);
   if (rc != 0) return rc;
   f->staged = true;
+  return IAK3D_OK;
+}
+
+// predictIAK3D's loops over depths and batches (predictIAK3D.R:144-155) for a whole grid in one staging: supports are
+// (interval i, cell c) at row i * ncell + c -- the layout of zMap / vMap (ndIMap x nxMap, row-major here) -- and their design
+// rows are made ON THE DEVICE by makeXvX (design.cu) from the per-cell covariates: 8 (2 + ncov) bytes per cell travel instead
+// of 8 (4 + p) per support.
+extern "C" int iak3d_predict_stage_grid(iak3d_fit* f, iak3d_design* g, int64_t ncell, const double* xyCell, const double* covCell,
+                                        int64_t nint, const double* dIInt, int64_t nxPerBatch) {
+  if (!f || !g || ncell < 0 || nint < 0) return IAK3D_ERR_ARG;
+  iak3d_ctx* ctx = f->ctx;
+  if (design_ctx(g) != ctx) { ctx->err = "predict_stage_grid: the design belongs to another context"; return IAK3D_ERR_ARG; }
+  if (design_p(g) != f->p) { ctx->err = "predict_stage_grid: the design has a different number of columns than the fit's X"; return IAK3D_ERR_ARG; }
+  for (int c = 0; c < 3; c++)
+    if (f->pars.sdfdType[c] > 0) { ctx->err = "predict_stage_grid: spline sd functions need iak3d_predict_stage_spl"; return IAK3D_ERR_ARG; }
+  const int64_t m = ncell * nint;
+  const int ncov = design_ncov(g);
+  if (m > 0 && (!xyCell || !dIInt || (ncov > 0 && !covCell))) return IAK3D_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  f->staged = false; f->enqueued = false;
+  f->m = m;
+  if (m == 0) { f->staged = true; return IAK3D_OK; }
+  { const int rcj = fit_reserve_job(f, m); if (rcj != 0) return rcj; }
+  f->nd1 = nint;
+  f->h_dIU1.assign(dIInt, dIInt + 2 * nint);
+  for (int c = 0; c < 3; c++) f->spl1U[c].clear();
+  cudaFree(f->d_dIU1); f->d_dIU1 = nullptr;
+  CUDA_TRY(ctx, cudaMalloc(&f->d_dIU1, (size_t)nint * 16));
+  CUDA_TRY(ctx, cudaMemcpyAsync(f->d_dIU1, dIInt, (size_t)nint * 16, cudaMemcpyHostToDevice, ctx->stream));
+  double *d_xyc = nullptr, *d_cov = nullptr;
+  int rc = IAK3D_OK;
+  do {
+    cudaError_t e = iak_pool_alloc(ctx, (void**)&d_xyc, (size_t)ncell * 16);
+    if (e == cudaSuccess && ncov > 0) e = iak_pool_alloc(ctx, (void**)&d_cov, (size_t)ncell * ncov * 8);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_xyc, xyCell, (size_t)ncell * 16, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && ncov > 0) e = cudaMemcpyAsync(d_cov, covCell, (size_t)ncell * ncov * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { ctx->err = std::string("predict_stage_grid: ") + cudaGetErrorString(e); cudaGetLastError(); rc = IAK3D_ERR_CUDA; break; }
+    const int64_t PRED_CHUNK = fit_chunk_rows(ctx, f->slot->Npad);
+    rc = launch_grid_supports(ctx, d_xyc, ncell, m, PRED_CHUNK, f->d_xy, f->d_did1);
+    if (rc != 0) break;
+    rc = launch_design_rows(ctx, g, m, ncell, nxPerBatch, d_cov, ncell, f->d_dIU1, nint, f->d_X, m, nullptr, nullptr);
+    if (rc != 0) break;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "predict_stage_grid: staging failed"; cudaGetLastError(); rc = IAK3D_ERR_CUDA; break; }
+    rc = fit_reserve_panel(f, std::min(PRED_CHUNK, m), f->nd1);
+  } while (0);
+  iak_pool_free(ctx, d_xyc); iak_pool_free(ctx, d_cov);
+  if (rc != 0) return rc;
+  f->staged = true;
+  return IAK3D_OK;
+}
+
+// the design rows of the staged job as the predictor will use them (m x p column-major); parity tests
+extern "C" int iak3d_predict_fetch_X(iak3d_fit* f, double* X) {
+  if (!f || !X) return IAK3D_ERR_ARG;
+  iak3d_ctx* ctx = f->ctx;
+  if (!f->staged) { ctx->err = "predict_fetch_X: nothing staged"; return IAK3D_ERR_ARG; }
+  cudaSetDevice(ctx->device);
+  if (f->m == 0) return IAK3D_OK;
+  CUDA_TRY(ctx, cudaMemcpyAsync(X, f->d_X, (size_t)f->m * f->p * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return IAK3D_OK;
 }
 

@@ -909,6 +909,8 @@ __global__ void __launch_bounds__(256) peak_mixed_kernel(double* out, int iters)
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+#include "chol_pair.cuh"
+
 }  // namespace
 
 int chol_configure(iak3d_ctx* ctx) {
@@ -916,12 +918,40 @@ int chol_configure(iak3d_ctx* ctx) {
   CUDA_TRY(ctx, cudaFuncSetAttribute(tile_task_kernel<-1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   CUDA_TRY(ctx, cudaFuncSetAttribute(tile_task_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   CUDA_TRY(ctx, cudaFuncSetAttribute(tile_task_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(tile_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(tile_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(tile_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+  // The pair engine's MMA warps grow to 216 registers with what the producer warpgroup gives back (setmaxnreg); that only
+  // adds up when the kernel is launched with exactly 128 registers per thread and two CTAs fit an SM.  Anything else
+  // (a different compiler, a smaller device) keeps the one-CTA engine rather than risk a warp waiting for registers.
+  ctx->engine = 1;
+  cudaFuncAttributes fa0, fa1, fa2;
+  CUDA_TRY(ctx, cudaFuncGetAttributes(&fa0, tile_pair_kernel<0>));
+  CUDA_TRY(ctx, cudaFuncGetAttributes(&fa1, tile_pair_kernel<1>));
+  CUDA_TRY(ctx, cudaFuncGetAttributes(&fa2, tile_pair_kernel<2>));
+  int per_sm = 0;
+  CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_pair_kernel<0>, NT2, SMEM2_BYTES));
+  if (fa0.numRegs == 128 && fa1.numRegs == 128 && fa2.numRegs == 128 && per_sm >= 2) ctx->engine = 2;
+  const char* e = getenv("IAK3D_ENGINE");
+  if (e && e[0] == '1') ctx->engine = 1;
+  if (e && e[0] == '3' && ctx->engine == 2) ctx->engine = 3;   // tests: single-problem launches through the pair engine too
   return 0;
 }
 
 int launch_tile_tasks(iak3d_ctx* ctx, const ProblemDesc* d_problems, const int4* d_tasks, int32_t ntasks, int32_t* d_ticket, int mode, int latency_bound) {
   if (ntasks <= 0) return 0;
   CUDA_TRY(ctx, cudaMemsetAsync(d_ticket, 0, 2 * sizeof(int32_t), ctx->stream));   // [0] ticket, [1] abort flag
+  if (ctx->engine == 3 || (ctx->engine == 2 && !(mode == 0 && latency_bound))) {
+    // throughput launches: two half-size CTAs per SM, one's epilogue under the other's K-loop (chol_pair.cuh)
+    int grid2 = 2 * ctx->sm_count;
+    if (grid2 > ntasks) grid2 = ntasks;
+    if (mode == 0) tile_pair_kernel<0><<<grid2, NT2, SMEM2_BYTES, ctx->stream>>>(d_problems, d_tasks, ntasks, d_ticket);
+    else if (mode == 1) tile_pair_kernel<1><<<grid2, NT2, SMEM2_BYTES, ctx->stream>>>(d_problems, d_tasks, ntasks, d_ticket);
+    else tile_pair_kernel<2><<<grid2, NT2, SMEM2_BYTES, ctx->stream>>>(d_problems, d_tasks, ntasks, d_ticket);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
+  }
   int grid = ctx->sm_count;
   if (grid > ntasks) grid = ntasks;
   if (mode == 0 && latency_bound) tile_task_kernel<-1, 1><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(d_problems, d_tasks, ntasks, d_ticket);

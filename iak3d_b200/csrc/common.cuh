@@ -43,6 +43,7 @@ struct iak3d_ctx {
   cudaEvent_t evs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // stage boundaries of the last batch
   std::string err;
   int64_t launches = 0;
+  int engine = 1;            // tile engine of throughput launches: 1 = one CTA per SM (chol.cu), 2 = CTA pairs (chol_pair.cuh)
   // scratch
   void* flush_buf = nullptr; size_t flush_bytes = 0;
   // batch state (nll_terms_batch_enqueue -> fetch)
@@ -192,6 +193,15 @@ int launch_cov_panel(iak3d_ctx* ctx, const CovArgs& a, double* d_out, int64_t ro
 
 int launch_unblock_rect(iak3d_ctx* ctx, const double* d_B, int64_t nRU, int64_t r0, int64_t nr, int64_t nc, int mirror, double* d_out,
                         int64_t ld);
+
+// ---- fixed-effect design matrix (design.cu) ------------------------------------------------------
+struct iak3d_design;
+int launch_design_rows(iak3d_ctx* ctx, const iak3d_design* g, int64_t m, int64_t ncell, int64_t batch, const double* d_covs, int64_t ldc,
+                       const double* d_dI, int64_t lddI, double* d_X, int64_t ldx, double* d_splmin, double* d_splmax);
+int launch_grid_supports(iak3d_ctx* ctx, const double* d_xyCell, int64_t ncell, int64_t m, int64_t chunk, double* d_xy, int32_t* d_did);
+int design_p(const iak3d_design* g);
+int design_ncov(const iak3d_design* g);
+iak3d_ctx* design_ctx(const iak3d_design* g);
 
 // ---- factorisation (chol.cu) -------------------------------------------------------------------
 struct ProblemDesc {

@@ -226,6 +226,45 @@ IAK3D_API int iak3d_predict_panel_fetch(iak3d_fit* fit, int64_t chunk, double* C
 IAK3D_API int iak3d_fit_set_option(iak3d_fit* fit, int32_t option, int32_t value);
 IAK3D_API int iak3d_predict_fetch_CkhiCX(iak3d_fit* fit, double* CkhiCX /* m x p column-major */);
 
+/* ---- fixed-effect design matrix of interval supports == makeXvX (makeXvX.R:1-708), lnTfmdData = FALSE -------------------
+ * predictIAK3D builds X for every (depth, batch) with makeXvX from the covariates of the map cells (predictIAK3D.R:155,
+ * :405); at 10^6 cells x 6 intervals that host-side matrix (and its upload) is what the kriging waits for.  A design object
+ * holds modelX + optionsModelX + nDiscPts + XLims flattened into two arrays (the host mirror iak3d_b200/design.py and the R
+ * glue build them):
+ *   ispec: type (0 'mlr' makeXvX.R:212-353, 1 'cubist' :360-434), p, ncov, nspl (dSpline.* columns), spl_kind (0 splines::bs,
+ *          1 makeXnsClampedUG0[,-1]: allKnotsd2X, cubist2XIAK3D.R:187-208), nint (internal knots), nDiscPts, has_lims, infBnds;
+ *          mlr:    per column  kind (0 no depth, 1 d, 2 d2, 3 d3, 4 dSpline), covariate column (-1 const; kind 4: spline
+ *                  index), position k among the K depth columns in the order id, idInt, id2, id2Int, id3, id3Int (-1 for the
+ *                  others): the reference recycles XLims over t(X[, depth columns]) from its first element, so entry
+ *                  (row i, k) is clamped by limit column (i K + k) mod p (makeXvX.R:327-328);
+ *          cubist: pc (rule columns), nRules, dcol (column of dIMidPts), number of distinct committees, nbreaks, nblocks;
+ *                  per rule  has_const, nconds, ncoef, per condition (variable, dir 0 '<=' 1 '>' 2 'in', set length), the
+ *                  coefficient variables; per rule column its committee block (-1 none); per block its rule range [r0, r1)
+ *   dspec: boundary knots b1, b2, the internal knots, XLims[1,], XLims[2,]; mlr: per column the factor level its dummy
+ *          indicates (NaN = numeric); cubist: per condition its threshold followed by its category set, then the sorted
+ *          distinct depth breaks (getAlldBreaks, cubist2XIAK3D.R:889-900).
+ * Capacities: p <= 64, <= 14 internal knots, <= 64 rules, <= 64 depth breaks. */
+typedef struct iak3d_design iak3d_design;
+IAK3D_API int iak3d_design_create(iak3d_ctx* ctx, const int32_t* ispec, int64_t nispec, const double* dspec, int64_t ndspec,
+                                  iak3d_design** out);
+IAK3D_API int iak3d_design_destroy(iak3d_design* design);
+IAK3D_API int iak3d_design_info(iak3d_design* design, int32_t* p, int32_t* ncov);
+/* X (m x p column-major) of m supports: covs m x ncov column-major (NULL when ncov == 0), dI m x 2.  splmin / splmax (m x nspl,
+ * may be NULL): mlr -- min / max of the non-zero point values of each spline column over the row's nDiscPts depths; cubist --
+ * splmin receives the trapezoid values of the spline columns (what XLims is taken from before they are replaced,
+ * makeXvX.R:406-430) */
+IAK3D_API int iak3d_design_eval(iak3d_design* design, int64_t m, const double* covs, const double* dI, double* X,
+                                double* splmin, double* splmax);
+/* The whole prediction grid in one staging (the loops of predictIAK3D.R:144-155): ncell map cells (xyCell ncell x 2,
+ * covCell ncell x ncov) x nint depth intervals (dIInt nint x 2); support (i, c) is row i * ncell + c of z, v (zMap / vMap
+ * are ndIMap x nxMap) and its design row is made on the device.  nxPerBatch (predictIAK3D's argument, 2000 by default; 0 =
+ * one batch) only matters when finite XLims apply to an mlr design: the reference's limit recycling (makeXvX.R:327-328)
+ * depends on a row's position inside its batch.  Then iak3d_predict_enqueue / _fetch as usual. */
+IAK3D_API int iak3d_predict_stage_grid(iak3d_fit* fit, iak3d_design* design, int64_t ncell, const double* xyCell,
+                                       const double* covCell, int64_t nint, const double* dIInt, int64_t nxPerBatch);
+/* the design rows of the staged job as the predictor uses them (m x p column-major); parity tests */
+IAK3D_API int iak3d_predict_fetch_X(iak3d_fit* fit, double* X);
+
 /* ---- Newton-Raphson terms == gradHessIAK3D (nrUpdatesIAK3D.R:118-216) -----------------------
  * Components dA_i are the unit-variance terms of setCIAK3D in the order cx0, cx1, cd1, cxd0, cxd1,
  * cme (ncomp = 5 or 6); lnvPars (ncomp) their log-variances.  Outputs: nll, grad (ncomp), hess and
