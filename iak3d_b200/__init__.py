@@ -11,4 +11,6 @@ from .api import (calcbetavXbeta, lnN_design, makeXnsClampedUG0, nrUpdatesIAK3Dl
                   setupIAK3D, setupIAK3D2, setupIAK3D_CL, spatialCovIAK3D, tauTfm)
 from .devmat import DeviceMat, cov_mat  # noqa: F401
 from .design import DesignModel, makeXvX  # noqa: F401
+from .blocks import (DevicePoints, balanceNeighbours, balanceNeighbours2, calcnPerCluster, setVoronoiBlocks,  # noqa: F401
+                     setVoronoiBlocksWrap)
 from . import parallel, synth  # noqa: F401

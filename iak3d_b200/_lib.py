@@ -80,6 +80,7 @@ _PROTOS = {
     "iak3d_predict_enqueue": (C.c_int, [_vp]),
     "iak3d_predict_fetch": (C.c_int, [_vp, _dp, _dp]),
     "iak3d_gradhess": (C.c_int, [_vp, C.POINTER(Pars), _i32, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "iak3d_gradhess_shard": (C.c_int, [_vp, C.POINTER(Pars), _i32, _dp, _i32, _i32, _dp, _dp, _dp, _dp, _dp, _dp]),
     "iak3d_sync": (C.c_int, [_vp]),
     "iak3d_timer_start": (C.c_int, [_vp]),
     "iak3d_timer_stop": (C.c_int, [_vp, _dp]),
@@ -102,6 +103,11 @@ _PROTOS = {
     "iak3d_design_eval": (C.c_int, [_vp, _i64, _dp, _dp, _dp, _dp, _dp]),
     "iak3d_predict_stage_grid": (C.c_int, [_vp, _vp, _i64, _dp, _dp, _i64, _dp, _i64]),
     "iak3d_predict_fetch_X": (C.c_int, [_vp, _dp]),
+    "iak3d_points_create": (C.c_int, [_vp, _i64, _dp, C.POINTER(_vp)]),
+    "iak3d_points_destroy": (C.c_int, [_vp]),
+    "iak3d_points_nearest": (C.c_int, [_vp, _i32, _dp, _ip, C.POINTER(_i64)]),
+    "iak3d_voronoi_seed": (C.c_int, [_i64, _dp, _i32, _i32, _ip, _dp]),
+    "iak3d_dirichlet_adjacency": (C.c_int, [_i32, _dp, _ip, _i64, C.POINTER(_i64)]),
     "iak3d_last_stage_ms": (C.c_int, [_vp, _dp, _dp, _dp]),
     "iak3d_last_task_profile": (C.c_int, [_vp, C.POINTER(_i64), _i64, C.POINTER(_i64)]),
 }

@@ -971,22 +971,34 @@ def setupIAK3D_CL(xData, dIData, zData, XData, compLikMats, ctx=None, rank=0, wo
     return cl
 
 
-def gradHessIAK3D(setupMats, parsBTfmd, modelx, sdfdTypes, lnvPars):
+def gradHessIAK3D(setupMats, parsBTfmd, modelx, sdfdTypes, lnvPars, comm=None):
     """nrUpdatesIAK3D.R:118-216 for C = sum_i exp(lnvPars[i]) dA_i with dA_i the unit-variance terms of setCIAK3D in the
     order cx0, cx1, cd1, cxd0, cxd1[, cme] (the `dA` list the reference is handed, :130-138).  The dataset must carry
-    W = [X z].  -> dict(nll, grad, hess, fim, betahat, vbetahat); nll is nan where chol fails."""
+    W = [X z].  -> dict(nll, grad, hess, fim, betahat, vbetahat); nll is nan where chol fails.
+
+    comm (parallel.BlockComm, world > 1): every rank holds the same dataset; the six T dC_i products and the 21 pair traces
+    are cut over the ranks by tile ownership and one all-reduce of ncomp + ncomp^2 doubles joins them."""
     sm = setupMats
     th = f64(np.asarray(lnvPars, float).reshape(-1))
     m = th.size
     p = sm.q - 1
     P = make_pars(parsBTfmd, modelx, *sdfdTypes, 1 if m == 6 else 0, quirk_cd1_unscaled=False)
     nll = C.c_double()
-    grad = np.empty(m); hess = np.empty((m, m), order="F"); fim = np.empty((m, m), order="F")
     beta = np.empty(p); vb = np.empty((p, p), order="F")
-    st = sm.ctx.check(sm.ctx.lib.iak3d_gradhess(sm.h, C.byref(P), m, dptr(th), C.byref(nll), dptr(grad), dptr(hess), dptr(fim),
-                                                dptr(beta), dptr(vb)), allow=(NOT_SPD, BAD_PARS))
-    if st != OK:
+    rank, world = (comm.rank, comm.world) if comm is not None else (0, 1)
+    zq = np.empty(m); qij = np.empty((m, m)); tr = np.zeros(m + m * m + 1)
+    st = sm.ctx.check(sm.ctx.lib.iak3d_gradhess_shard(sm.h, C.byref(P), m, dptr(th), rank, world, C.byref(nll), dptr(beta), dptr(vb),
+                                                      dptr(zq), dptr(qij), dptr(tr)), allow=(NOT_SPD, BAD_PARS))
+    tr[m + m * m] = 0.0 if st == OK else 1.0         # a failing rank must not leave the others in the all-reduce
+    if world > 1:
+        tr = comm.allreduce_sum(tr)
+    if tr[m + m * m] != 0.0:
         return dict(nll=float("nan"))
+    trM, trP = tr[:m], tr[m:m + m * m].reshape(m, m)
+    grad = 0.5 * (trM - zq)                          # :197
+    fim = 0.5 * trP                                  # :210
+    hess = 0.5 * (-trP + 2.0 * qij)                  # :198-207
+    hess[np.diag_indices(m)] += 0.5 * (trM - zq)
     return dict(nll=nll.value, grad=grad, hess=hess, fim=fim, betahat=beta.reshape(-1, 1), vbetahat=vb)
 
 
@@ -1228,11 +1240,10 @@ def profilePredictIAK3D(xMap, dIMap, XMap, lmmFit, vXUMap=None, rqrBTfmdPreds=Tr
 # ---------------------------------------------------------------------------------------------
 # composite-likelihood block prediction (compositeLikIAK3D.R:471-607; dispatched at predictIAK3D.R:211-226)
 # ---------------------------------------------------------------------------------------------
-def getBlocksFromLocations(xMap, compLikMats):
-    """Nearest block centroid, first index on ties (compositeLikIAK3D.R:476-480)."""
-    cen = np.asarray(compLikMats["centroids"], float)
-    d2 = ((np.asarray(xMap, float)[:, None, :] - cen[None, :, :]) ** 2).sum(-1)
-    return np.sqrt(d2).argmin(axis=1)
+def getBlocksFromLocations(xMap, compLikMats, ctx=None):
+    """Nearest block centroid, first index on ties (compositeLikIAK3D.R:803-812): one device pass (blocks.py)."""
+    from .blocks import getBlocksFromLocations as _g
+    return _g(xMap, compLikMats, ctx=ctx)
 
 
 def predMatsIAK3D_CL_ByBlock(z_muhat, XData, xMap, dIMap, lmmFit):

@@ -1021,7 +1021,9 @@ extern "C" int iak3d_nll_terms_batch_enqueue(iak3d_ctx* ctx, int32_t count, iak3
   CUDA_TRY(ctx, cudaEventRecord(ctx->evs[2], ctx->stream));
   CUDA_TRY(ctx, cudaMemsetAsync(b->d_status, 0, (size_t)count * 2 * sizeof(int32_t), ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(b->d_probs, probs.data(), (size_t)count * sizeof(ProblemDesc), cudaMemcpyHostToDevice, ctx->stream));
-  st = launch_tile_tasks(ctx, b->d_probs, b->d_tasks, b->ntasks, b->d_ticket, 0, /*latency_bound=*/count <= 2 ? 1 : 0);
+  int maxCB = 1;
+  for (int i = 0; i < count; i++) if (live[i]) maxCB = std::max(maxCB, (int)probs[i].nCB);
+  st = launch_tile_tasks(ctx, b->d_probs, b->d_tasks, b->ntasks, b->d_ticket, 0, /*latency_bound=*/count <= 2 ? 1 : 0, b->ntasks / maxCB);
   if (st != 0) return st;
   CUDA_TRY(ctx, cudaEventRecord(ctx->evs[3], ctx->stream));
   st = launch_finish(ctx, b->d_probs, count, b->d_results, b->stride);

@@ -523,7 +523,7 @@ extern "C" int iak3d_predict_enqueue(iak3d_fit* f) {
       pd.prof = ctx->d_prof;
     }
     CUDA_TRY(ctx, cudaMemcpyAsync(f->d_prob, &pd, sizeof(pd), cudaMemcpyHostToDevice, ctx->stream));
-    rc = launch_tile_tasks(ctx, f->d_prob, f->d_tasks, f->ntasks, f->d_ticket, 1);
+    rc = launch_tile_tasks(ctx, f->d_prob, f->d_tasks, f->ntasks, f->d_ticket, 1, 0, (int)(rowsP / TM));
     if (rc != 0) return rc;
     rc = launch_krige_finish(ctx, f->d_G, rowsP, f->q, f->d_X + r0, m, rows, f->d_ckk + r0, f->d_beta, f->d_vbeta, f->d_z + r0,
                              f->d_v + r0, f->d_cz + r0, f->d_qf + r0, (f->opt_keep_cx && f->d_cx) ? f->d_cx + r0 : nullptr, m);

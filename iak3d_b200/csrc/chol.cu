@@ -935,14 +935,19 @@ int chol_configure(iak3d_ctx* ctx) {
   const char* e = getenv("IAK3D_ENGINE");
   if (e && e[0] == '1') ctx->engine = 1;
   if (e && e[0] == '3' && ctx->engine == 2) ctx->engine = 3;   // tests: single-problem launches through the pair engine too
+  const char* w = getenv("IAK3D_PAIR_WIDTH");
+  if (w && atoi(w) > 0) ctx->pair_min_width = atoi(w);
   return 0;
 }
 
-int launch_tile_tasks(iak3d_ctx* ctx, const ProblemDesc* d_problems, const int4* d_tasks, int32_t ntasks, int32_t* d_ticket, int mode, int latency_bound) {
+int launch_tile_tasks(iak3d_ctx* ctx, const ProblemDesc* d_problems, const int4* d_tasks, int32_t ntasks, int32_t* d_ticket, int mode, int latency_bound, int width) {
   if (ntasks <= 0) return 0;
   CUDA_TRY(ctx, cudaMemsetAsync(d_ticket, 0, 2 * sizeof(int32_t), ctx->stream));   // [0] ticket, [1] abort flag
-  if (ctx->engine == 3 || (ctx->engine == 2 && !(mode == 0 && latency_bound))) {
-    // throughput launches: two half-size CTAs per SM, one's epilogue under the other's K-loop (chol_pair.cuh)
+  if (ctx->engine == 3 || (ctx->engine == 2 && !(mode == 0 && latency_bound) && width >= ctx->pair_min_width)) {
+    // throughput launches -- at least pair_min_width independent tasks per dependency step, i.e. enough to keep two CTAs per
+    // SM busy: two half-size CTAs per SM, one's epilogue under the other's K-loop (chol_pair.cuh).  Narrower launches are
+    // bound by the per-column critical path, which the full-size CTA (8 MMA warps on one tile) runs faster: measured at
+    // 9 x n = 2049 (width ~ 100) 18.2 vs 14.5 TFLOP/s, at 9 x n = 5000 (width ~ 270) 28.7 vs 30.3.
     int grid2 = 2 * ctx->sm_count;
     if (grid2 > ntasks) grid2 = ntasks;
     if (mode == 0) tile_pair_kernel<0><<<grid2, NT2, SMEM2_BYTES, ctx->stream>>>(d_problems, d_tasks, ntasks, d_ticket);

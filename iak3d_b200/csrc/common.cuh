@@ -43,6 +43,7 @@ struct iak3d_ctx {
   cudaEvent_t evs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // stage boundaries of the last batch
   std::string err;
   int64_t launches = 0;
+  int pair_min_width = 148;  // tasks per dependency step from which a throughput launch uses the CTA-pair engine
   int engine = 1;            // tile engine of throughput launches: 1 = one CTA per SM (chol.cu), 2 = CTA pairs (chol_pair.cuh)
   // scratch
   void* flush_buf = nullptr; size_t flush_bytes = 0;
@@ -227,7 +228,9 @@ struct ProblemDesc {
 int chol_configure(iak3d_ctx* ctx);
 int launch_tile_tasks(iak3d_ctx* ctx, const ProblemDesc* d_problems, const int4* d_tasks, int32_t ntasks, int32_t* d_ticket /* 2 ints */,
                       int mode /* the mode of every problem of the launch */,
-                      int latency_bound = 0 /* one factorisation alone: use the look-ahead diagonal-block kernel */);
+                      int latency_bound = 0 /* one factorisation alone: use the look-ahead diagonal-block kernel */,
+                      int width = 0 /* independent tasks per dependency step (column of a factorisation, row chains of a panel,
+                                       all tiles of a product): selects the CTA-pair engine for wide launches */);
 int launch_finish(iak3d_ctx* ctx, const ProblemDesc* d_problems, int32_t count, double* d_results, int32_t stride);
 // X = L^-T Y for the q bordered rows of a finished blocked factor; d_X: Npad x q column-major out
 int launch_backsolve(iak3d_ctx* ctx, const double* d_L, int64_t nRU, int64_t Npad, const double* d_invd, int32_t q, double* d_X);

@@ -51,29 +51,28 @@ __global__ void matvec_rows_kernel(const double* __restrict__ M, int64_t nRU, in
   for (int64_t b = 0; b < n; b++) s = fma(M[uidx(a, b, nRU)], __ldg(x + b), s);
   y[a] = s;
 }
-// y = M' x (warp per column, lanes stride the rows, fixed shuffle tree)
-__global__ void matvec_cols_kernel(const double* __restrict__ M, int64_t nRU, int64_t n, const double* __restrict__ x, double* __restrict__ y) {
-  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (b >= n) return;
-  double s = 0.0;
-  for (int64_t a = lane; a < n; a += 32) s = fma(M[uidx(a, b, nRU)], __ldg(x + a), s);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-  if (lane == 0) y[b] = s;
+// Sharding of the Newton-Raphson trace terms over GPUs: the n x n products M_i = T dC_i are cut into 128 x 128
+// super-tiles; the unordered pair {R, C} of super-tile indices -- i.e. tile (R, C) together with its transpose position (C, R),
+// which tr(M_i M_j) = sum_ab M_i[a,b] M_j[b,a] needs side by side -- belongs to rank (k mod world), k its index in the packed
+// lower triangle.  A rank computes and reads only its own tiles; the partial traces are summed by one all-reduce.
+__host__ __device__ __forceinline__ int tile_owner(int64_t R, int64_t Cc, int world) {
+  const int64_t hi = R > Cc ? R : Cc, lo = R > Cc ? Cc : R;
+  return (int)((hi * (hi + 1) / 2 + lo) % world);
 }
-// partial[blockIdx.x] = sum over a in this block's 32 rows, all b < n, of Mi(a,b) * Mj(b,a)   (Mj == nullptr: trace of Mi)
+// partial[blockIdx.x] = sum over a in this block's 32 rows, all b < n in super-tiles owned by `rank`, of Mi(a,b) * Mj(b,a)
+// (Mj == nullptr: trace of Mi, diagonal super-tiles only)
 __global__ void __launch_bounds__(256) trace_pair_kernel(const double* __restrict__ Mi, const double* __restrict__ Mj, int64_t nRU,
-                                                         int64_t n, double* __restrict__ partial) {
+                                                         int64_t n, double* __restrict__ partial, int rank, int world) {
   __shared__ double sj[32][33];
   __shared__ double red[256];
   const int64_t a0 = (int64_t)blockIdx.x * 32;
   const int tf = threadIdx.x & 31, ts = threadIdx.x >> 5;      // fast index 0..31, slow index 0..7
   double acc = 0.0;
   if (Mj == nullptr) {
-    if (threadIdx.x < 32) { const int64_t a = a0 + threadIdx.x; if (a < n) acc = Mi[uidx(a, a, nRU)]; }
+    if (threadIdx.x < 32 && tile_owner(a0 / TM, a0 / TM, world) == rank) { const int64_t a = a0 + threadIdx.x; if (a < n) acc = Mi[uidx(a, a, nRU)]; }
   } else {
     for (int64_t b0 = 0; b0 < n; b0 += 32) {
+      if (tile_owner(a0 / TM, b0 / TM, world) != rank) continue;      // uniform over the block
       // Mj block rows b0.. (fast), cols a0.. (slow) -> shared, then read transposed
       for (int s = ts; s < 32; s += 8) {
         const int64_t b = b0 + tf, a = a0 + s;
@@ -105,22 +104,25 @@ struct DevBuf {                       // stream-ordered scratch (iak_pool_alloc)
 // tri = 0: all tiles, K-loop from 0.  tri = 1 (mode 1, identity panel: U = L^-T is upper triangular): only the tiles with
 // j >= 2r, K-loop from the row block's own first column (X(r,k) = 0 before it).  tri = 2 (mode 2, U U' with U upper
 // triangular, lower triangle of the symmetric result): only the tiles with r >= j/2, K-loop from the row block's first column.
-int run_tiles(iak3d_ctx* ctx, const ProblemDesc& pd, int nRB, int nCB, int tri = 0) {
+int run_tiles(iak3d_ctx* ctx, const ProblemDesc& pd, int nRB, int nCB, int tri = 0, int rank = 0, int world = 1) {
   std::vector<int4> tasks;
   tasks.reserve((size_t)nRB * nCB);
   for (int j = 0; j < nCB; j++)
     for (int r = 0; r < nRB; r++) {
       if (tri == 1 && j < 2 * r) continue;
       if (tri == 2 && r < j / 2) continue;
+      if (world > 1 && tile_owner(r, j / 2, world) != rank) continue;      // 128 x 64 task (r, j) lies in super-tile (r, j / 2)
       tasks.push_back(make_int4(0, r, j, tri ? r * (TM / UC) : 0));
     }
+  if (tasks.empty()) return 0;
   DevBuf d_tasks, d_prob, d_ticket;
   CUDA_TRY(ctx, d_tasks.alloc(ctx, tasks.size() * sizeof(int4)));
   CUDA_TRY(ctx, d_prob.alloc(ctx, sizeof(ProblemDesc)));
   CUDA_TRY(ctx, d_ticket.alloc(ctx, 2 * sizeof(int32_t)));
   CUDA_TRY(ctx, cudaMemcpyAsync(d_tasks.p, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(d_prob.p, &pd, sizeof(pd), cudaMemcpyHostToDevice, ctx->stream));
-  const int st = launch_tile_tasks(ctx, d_prob.as<ProblemDesc>(), d_tasks.as<int4>(), (int32_t)tasks.size(), d_ticket.as<int32_t>(), pd.mode);
+  const int st = launch_tile_tasks(ctx, d_prob.as<ProblemDesc>(), d_tasks.as<int4>(), (int32_t)tasks.size(), d_ticket.as<int32_t>(), pd.mode, 0,
+                                   pd.mode == 2 ? (int)std::min<size_t>(tasks.size(), 1u << 30) : nRB);
   if (st != 0) return st;
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -128,7 +130,7 @@ int run_tiles(iak3d_ctx* ctx, const ProblemDesc& pd, int nRB, int nCB, int tri =
 
 // Out(rowsOut x colsOut, blocked) = use_cin * Out + alpha * A(rowsOut x K) B(colsOut x K)'   (all blocked, K multiple of 32)
 int gemm_nt(iak3d_ctx* ctx, const double* A, int64_t rowsA, const double* B, int64_t rowsB, double* Out, int64_t rowsOut,
-            int64_t colsOut, int64_t K, double alpha, int use_cin, int32_t* d_status, int tri = 0) {
+            int64_t colsOut, int64_t K, double alpha, int use_cin, int32_t* d_status, int tri = 0, int rank = 0, int world = 1) {
   ProblemDesc pd;
   memset(&pd, 0, sizeof(pd));
   pd.L = const_cast<double*>(B); pd.nRUL = rowsB / UR;
@@ -137,7 +139,7 @@ int gemm_nt(iak3d_ctx* ctx, const double* A, int64_t rowsA, const double* B, int
   pd.nCB = (int32_t)(colsOut / TN); pd.nRB = (int32_t)(rowsOut / TM);
   pd.mode = 2; pd.kchunks = (int32_t)(K / UC); pd.use_cin = use_cin; pd.alpha = alpha;
   pd.status = d_status;
-  return run_tiles(ctx, pd, pd.nRB, pd.nCB, tri);
+  return run_tiles(ctx, pd, pd.nRB, pd.nCB, tri, rank, world);
 }
 
 // upper triangle := transpose of the lower triangle (blocked layout)
@@ -283,9 +285,13 @@ static void host_chol_solve(int p, const double* L, const double* b, double* x) 
   for (int i = p - 1; i >= 0; i--) { double s = y[i]; for (int k = i + 1; k < p; k++) s -= L[(size_t)i * p + k] * x[k]; x[i] = s / L[(size_t)i * p + i]; }
 }
 
-extern "C" int iak3d_gradhess(iak3d_ds* ds, const iak3d_pars* pars, int32_t ncomp, const double* lnvPars, double* nll, double* grad,
-                              double* hess, double* fim, double* betahat, double* vbetahat) {
-  if (!ds || !pars || !lnvPars || !nll || !grad || !hess || !fim) return IAK3D_ERR_ARG;
+// The rank's share of gradHessIAK3D: everything O(n^2) and the factorisation / inverse are computed by every rank (T must
+// be whole wherever a tile of T dC_i is formed); the six n x n x n products and the 21 pair traces -- 12 n^3 of the 13 n^3
+// flops -- are cut by super-tile ownership.  tr_part = { this rank's part of tr(M_i) (m), of tr(M_i M_j) (m x m, both
+// triangles filled) }: summed over the ranks (one all-reduce of m + m^2 doubles) they give the traces of :197-210.
+extern "C" int iak3d_gradhess_shard(iak3d_ds* ds, const iak3d_pars* pars, int32_t ncomp, const double* lnvPars, int32_t rank, int32_t world,
+                                    double* nll, double* betahat, double* vbetahat, double* zTdCTz_out, double* qij_out, double* tr_part) {
+  if (!ds || !pars || !lnvPars || !nll || !zTdCTz_out || !qij_out || !tr_part || world < 1 || rank < 0 || rank >= world) return IAK3D_ERR_ARG;
   iak3d_ctx* ctx = ds->ctx;
   if (ncomp != 5 && ncomp != 6) { ctx->err = "gradhess: ncomp must be 5 or 6 (cx0, cx1, cd1, cxd0, cxd1[, cme])"; return IAK3D_ERR_ARG; }
   if (ds->q < 2) { ctx->err = "gradhess: the dataset needs W = [X z]"; return IAK3D_ERR_ARG; }
@@ -349,17 +355,15 @@ extern "C" int iak3d_gradhess(iak3d_ds* ds, const iak3d_pars* pars, int32_t ncom
     if (rc != 0) break;
     const int64_t nRU = rowsU / UR, Npad = s->Npad;
     const size_t mbytes = (size_t)ubuf_doubles(rowsU, Npad) * sizeof(double);
-    DevBuf dA1, dB1, pA, pB, dTz, dz, du, dv, dr, dpart, dstatus, dC;
+    DevBuf dA1, dB1, pA, pB, dTz, du, dv, dpart, dstatus, dC;
     const size_t pbytes = (size_t)ubuf_doubles(rowsU, TN) * sizeof(double);     // rowsU x 64 panel (K = 32 uses the first unit column)
     cudaError_t e = dA1.alloc(ctx, (size_t)n * p * 8);
     if (e == cudaSuccess) e = dB1.alloc(ctx, (size_t)n * p * 8);
     if (e == cudaSuccess) e = pA.alloc(ctx, pbytes);
     if (e == cudaSuccess) e = pB.alloc(ctx, pbytes);
     if (e == cudaSuccess) e = dTz.alloc(ctx, (size_t)n * 8);
-    if (e == cudaSuccess) e = dz.alloc(ctx, (size_t)n * 8);
     if (e == cudaSuccess) e = du.alloc(ctx, (size_t)n * 8);
     if (e == cudaSuccess) e = dv.alloc(ctx, (size_t)n * 8);
-    if (e == cudaSuccess) e = dr.alloc(ctx, (size_t)n * 8);
     const int nblk = (int)((n + 31) / 32);
     if (e == cudaSuccess) e = dpart.alloc(ctx, (size_t)nblk * 8);
     if (e == cudaSuccess) e = dstatus.alloc(ctx, 2 * sizeof(int32_t));
@@ -369,7 +373,6 @@ extern "C" int iak3d_gradhess(iak3d_ds* ds, const iak3d_pars* pars, int32_t ncom
     cudaMemcpyAsync(dA1.p, A1.data(), (size_t)n * p * 8, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(dB1.p, iCW.data(), (size_t)n * p * 8, cudaMemcpyHostToDevice, ctx->stream);      // iCX = first p columns
     cudaMemcpyAsync(dTz.p, Tz.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
-    cudaMemcpyAsync(dz.p, ds->h_W + (size_t)p * n, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
     {
       dim3 grid((unsigned)((rowsU + 255) / 256), TN);
       block_panel_kernel<<<grid, 256, 0, ctx->stream>>>(dA1.as<double>(), n, p, pA.as<double>(), nRU, rowsU);
@@ -388,7 +391,7 @@ extern "C" int iak3d_gradhess(iak3d_ds* ds, const iak3d_pars* pars, int32_t ncom
     std::vector<std::vector<double>> vv((size_t)m, std::vector<double>((size_t)n)), rr((size_t)m, std::vector<double>((size_t)n));
     std::vector<double> part((size_t)nblk), hu((size_t)n);
     const double cv[6][6] = {{1, 0, 0, 0, 0, 0}, {0, 1, 0, 0, 0, 0}, {0, 0, 1, 0, 0, 0}, {0, 0, 0, 1, 0, 0}, {0, 0, 0, 0, 1, 0}, {0, 0, 0, 0, 0, 1}};
-    const unsigned rb = (unsigned)((n + 127) / 128), wb = (unsigned)((n * 32 + 255) / 256);
+    const unsigned rb = (unsigned)((n + 127) / 128);
     for (int i = 0; i < m && rc == 0; i++) {
       CovArgs ai = a;
       ai.cx0 = cv[i][0] * pl.cx0; ai.cx1 = cv[i][1] * pl.cx1; ai.kd1 = cv[i][2] * pl.cd1; ai.cxd0 = cv[i][3] * pl.cxd0;
@@ -399,29 +402,32 @@ extern "C" int iak3d_gradhess(iak3d_ds* ds, const iak3d_pars* pars, int32_t ncom
       ctx->launches++;
       cudaMemcpyAsync(hu.data(), du.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
       if (iak_malloc(ctx, (void**)&Mi[i], mbytes) != cudaSuccess) { ctx->err = "gradhess: allocation failed (M_i)"; cudaGetLastError(); rc = IAK3D_ERR_CUDA; break; }
-      rc = gemm_nt(ctx, T, rowsU, dC.as<double>(), rowsU, Mi[i], rowsU, Npad, Npad, 1.0, 0, dstatus.as<int32_t>());
+      // v_i = M_i Tz = T (dC_i Tz) = T u_i and r_i = M_i' z = dC_i (T z) = u_i: two matrix-vector products on whole matrices,
+      // so that M_i itself is only needed where its traces are taken
+      matvec_rows_kernel<<<rb, 128, 0, ctx->stream>>>(T, nRU, n, du.as<double>(), dv.as<double>());
+      ctx->launches++;
+      cudaMemcpyAsync(vv[i].data(), dv.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+      rc = gemm_nt(ctx, T, rowsU, dC.as<double>(), rowsU, Mi[i], rowsU, Npad, Npad, 1.0, 0, dstatus.as<int32_t>(), 0, rank, world);
       if (rc != 0) break;
+      if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "gradhess: kernel failure"; rc = IAK3D_ERR_CUDA; break; }   // hu, vv[i]
       double t = 0.0;
       for (int64_t k = 0; k < n; k++) t += Tz[(size_t)k] * hu[(size_t)k];
       zTdCTz[i] = t;
-      trace_pair_kernel<<<nblk, 256, 0, ctx->stream>>>(Mi[i], nullptr, nRU, n, dpart.as<double>());
-      matvec_rows_kernel<<<rb, 128, 0, ctx->stream>>>(Mi[i], nRU, n, dTz.as<double>(), dv.as<double>());
-      matvec_cols_kernel<<<wb, 256, 0, ctx->stream>>>(Mi[i], nRU, n, dz.as<double>(), dr.as<double>());
-      ctx->launches += 3;
+      rr[i] = hu;
+      trace_pair_kernel<<<nblk, 256, 0, ctx->stream>>>(Mi[i], nullptr, nRU, n, dpart.as<double>(), rank, world);
+      ctx->launches++;
       cudaMemcpyAsync(part.data(), dpart.p, (size_t)nblk * 8, cudaMemcpyDeviceToHost, ctx->stream);
-      cudaMemcpyAsync(vv[i].data(), dv.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
-      cudaMemcpyAsync(rr[i].data(), dr.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
       if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "gradhess: kernel failure"; rc = IAK3D_ERR_CUDA; break; }
       t = 0.0;
       for (int k = 0; k < nblk; k++) t += part[(size_t)k];
       trM[i] = t;
     }
     if (rc != 0) break;
-    // ---- gradient, Hessian, Fisher information (:197-210), REML nll (:213) ----
-    for (int i = 0; i < m; i++) grad[i] = 0.5 * (trM[i] - zTdCTz[i]);
+    // ---- this rank's share of the traces; the quadratic forms (:197-210) ----
+    for (int i = 0; i < m; i++) { tr_part[i] = trM[i]; zTdCTz_out[i] = zTdCTz[i]; }
     for (int i = 0; i < m && rc == 0; i++)
       for (int j = i; j < m; j++) {
-        trace_pair_kernel<<<nblk, 256, 0, ctx->stream>>>(Mi[i], Mi[j], nRU, n, dpart.as<double>());
+        trace_pair_kernel<<<nblk, 256, 0, ctx->stream>>>(Mi[i], Mi[j], nRU, n, dpart.as<double>(), rank, world);
         ctx->launches++;
         // the context stream is non-blocking: a plain cudaMemcpy would not wait for the kernel
         cudaMemcpyAsync(part.data(), dpart.p, (size_t)nblk * 8, cudaMemcpyDeviceToHost, ctx->stream);
@@ -430,9 +436,8 @@ extern "C" int iak3d_gradhess(iak3d_ds* ds, const iak3d_pars* pars, int32_t ncom
         for (int k = 0; k < nblk; k++) tr += part[(size_t)k];
         double qij = 0.0;                                            // z' T dC_i T dC_j T z = (M_i' z) . (M_j Tz)
         for (int64_t k = 0; k < n; k++) qij += rr[i][(size_t)k] * vv[j][(size_t)k];
-        if (i == j) hess[(size_t)i * m + j] = 0.5 * (trM[i] - tr - zTdCTz[i] + 2.0 * qij);
-        else hess[(size_t)i * m + j] = hess[(size_t)j * m + i] = 0.5 * (-tr + 2.0 * qij);
-        fim[(size_t)i * m + j] = fim[(size_t)j * m + i] = 0.5 * tr;
+        qij_out[(size_t)i * m + j] = qij_out[(size_t)j * m + i] = qij;
+        tr_part[m + (size_t)i * m + j] = tr_part[m + (size_t)j * m + i] = tr;
       }
     if (rc != 0) break;
     int32_t hs[2] = {0, 0};
@@ -447,4 +452,24 @@ extern "C" int iak3d_gradhess(iak3d_ds* ds, const iak3d_pars* pars, int32_t ncom
   if (iCb) cudaFree(iCb);
   iak_free_slot(s);
   return rc;
+}
+
+// gradHessIAK3D on one GPU: the whole share, then the assembly of nrUpdatesIAK3D.R:197-210
+extern "C" int iak3d_gradhess(iak3d_ds* ds, const iak3d_pars* pars, int32_t ncomp, const double* lnvPars, double* nll, double* grad,
+                              double* hess, double* fim, double* betahat, double* vbetahat) {
+  if (!ds || !pars || !lnvPars || !nll || !grad || !hess || !fim) return IAK3D_ERR_ARG;
+  if (ncomp != 5 && ncomp != 6) { ds->ctx->err = "gradhess: ncomp must be 5 or 6 (cx0, cx1, cd1, cxd0, cxd1[, cme])"; return IAK3D_ERR_ARG; }
+  const int m = ncomp;
+  double zq[6], qij[36], tr[6 + 36];
+  const int rc = iak3d_gradhess_shard(ds, pars, ncomp, lnvPars, 0, 1, nll, betahat, vbetahat, zq, qij, tr);
+  if (rc != 0) return rc;
+  for (int i = 0; i < m; i++) grad[i] = 0.5 * (tr[i] - zq[i]);
+  for (int i = 0; i < m; i++)
+    for (int j = i; j < m; j++) {
+      const double t = tr[m + i * m + j], q2 = qij[i * m + j];
+      if (i == j) hess[(size_t)i * m + j] = 0.5 * (tr[i] - t - zq[i] + 2.0 * q2);
+      else hess[(size_t)i * m + j] = hess[(size_t)j * m + i] = 0.5 * (-t + 2.0 * q2);
+      fim[(size_t)i * m + j] = fim[(size_t)j * m + i] = 0.5 * t;
+    }
+  return IAK3D_OK;
 }

@@ -265,12 +265,41 @@ IAK3D_API int iak3d_predict_stage_grid(iak3d_fit* fit, iak3d_design* design, int
 /* the design rows of the staged job as the predictor uses them (m x p column-major); parity tests */
 IAK3D_API int iak3d_predict_fetch_X(iak3d_fit* fit, double* X);
 
+/* ---- composite-likelihood block construction == setVoronoiBlocks & co (compositeLikIAK3D.R:803-1133) ------------------
+ * Locations resident on the device for repeated nearest-centroid passes: D = xyDist(x, vcentres) (iaCovMatern.R:888-920) and
+ * which.min per row (first minimum; NaN centroids never win).  This is the Voronoi assignment of setVoronoiBlocks (:887-888),
+ * getBlocksFromLocations for the map cells (:803-812) and calcnPerCluster (:1033-1046), the objective balanceNeighbours2's
+ * random search evaluates thousands of times (:1048-1133).  block (m, 0-based, may be NULL), counts (nB, may be NULL). */
+typedef struct iak3d_points iak3d_points;
+IAK3D_API int iak3d_points_create(iak3d_ctx* ctx, int64_t m, const double* xy /* m x 2 */, iak3d_points** out);
+IAK3D_API int iak3d_points_destroy(iak3d_points* pts);
+IAK3D_API int iak3d_points_nearest(iak3d_points* pts, int32_t nB, const double* vcentres /* nB x 2 */, int32_t* block, int64_t* counts);
+/* greedy seeding of the block centroids (compositeLikIAK3D.R:840-884) from the nU unique locations (first-occurrence order);
+ * host algorithm, no device needed.  nBlocks = floor(nU / nPerBlock) (<= cap_blocks); vcentres nBlocks x 2 column-major. */
+IAK3D_API int iak3d_voronoi_seed(int64_t nU, const double* xU, int32_t nPerBlock, int32_t cap_blocks, int32_t* nBlocks,
+                                 double* vcentres);
+/* the pairs (ind1, ind2) of deldir(x, y)$dirsgs (compositeLikIAK3D.R:907-916; package deldir, not vendored by the reference):
+ * blocks whose Dirichlet tiles share an edge inside deldir's default window (bounding box + 10 % per side).  pairs: cap x 2
+ * ROW-major int32, i < j, sorted; host algorithm (Bowyer-Watson). */
+IAK3D_API int iak3d_dirichlet_adjacency(int32_t nB, const double* vcentres, int32_t* pairs, int64_t cap_pairs, int64_t* npairs);
+
 /* ---- Newton-Raphson terms == gradHessIAK3D (nrUpdatesIAK3D.R:118-216) -----------------------
  * Components dA_i are the unit-variance terms of setCIAK3D in the order cx0, cx1, cd1, cxd0, cxd1,
  * cme (ncomp = 5 or 6); lnvPars (ncomp) their log-variances.  Outputs: nll, grad (ncomp), hess and
  * fim (ncomp x ncomp), betahat (p), vbetahat (p x p). */
 IAK3D_API int iak3d_gradhess(iak3d_ds* ds, const iak3d_pars* pars, int32_t ncomp, const double* lnvPars,
                    double* nll, double* grad, double* hess, double* fim, double* betahat, double* vbetahat);
+
+/* The same over several GPUs (only worth it at n = 40 000): every rank holds the dataset and calls this with its
+ * rank; the factorisation, the inverse and everything O(n^2) are done by every rank (T = iC - iCX (X'iCX)^-1 X'iC must be
+ * whole wherever a tile of T dC_i is formed), while the ncomp products T dC_i and the ncomp (ncomp + 1) / 2 pair traces -- 12 n^3
+ * of the 13 n^3 flops -- are cut by ownership of 128 x 128 tile pairs {(R, C), (C, R)}.  Outputs identical on every rank:
+ * nll, betahat, vbetahat, zTdCTz (ncomp: z'T dC_i T z), qij (ncomp x ncomp: z'T dC_i T dC_j T z).  tr_part (ncomp + ncomp^2)
+ * = this rank's part of tr(T dC_i) and of tr(T dC_i T dC_j): ncclAllReduce(sum) it, then (nrUpdatesIAK3D.R:197-210)
+ *   grad_i = (tr_i - zTdCTz_i) / 2,  fim_ij = tr_ij / 2,  hess_ij = (-tr_ij + 2 qij_ij) / 2  (+ (tr_i - zTdCTz_i) / 2 on the diagonal). */
+IAK3D_API int iak3d_gradhess_shard(iak3d_ds* ds, const iak3d_pars* pars, int32_t ncomp, const double* lnvPars, int32_t rank,
+                                   int32_t world, double* nll, double* betahat, double* vbetahat, double* zTdCTz, double* qij,
+                                   double* tr_part);
 
 /* ---- device-resident dense matrices ------------------------------------------------------------
  * The Eidsvik composite-likelihood block predictor predMatsIAK3D_CLEV_ByBlock (compositeLikIAK3D.R:609-798) is dense

@@ -95,3 +95,36 @@ def test_nrUpdates_iteration_vs_oracle(ctx, kind, ncomp, n):
     assert np.array_equal(live, got["lnvPars"] > -19.0)
     assert np.max(np.abs(got["lnvPars"][live] - want["lnvPars"][live])) <= 1e-5
     assert scaled_err(got["betahat"], want["betahat"]) <= 1e-7
+
+
+class _FakeComm:
+    """One process playing every rank in turn: rank r's call returns its own share; the 'all-reduce' adds the stored shares
+    of the other ranks (computed beforehand with the same inputs)."""
+    def __init__(self, rank, world, others):
+        self.rank, self.world, self.others = rank, world, others
+    def allreduce_sum(self, buf):
+        self.mine = np.array(buf, float)
+        return self.mine + sum(self.others)
+
+
+@pytest.mark.parametrize("world,n", [(2, 400), (3, 700), (8, 1100)])
+def test_gradhess_shares_add_up(ctx, world, n):
+    """the trace terms of nrUpdatesIAK3D.R:197-210 cut over `world` ranks by tile-pair ownership."""
+    ds = synth.make_dataset(n, 6)
+    P, modelx, types, cmeOpt = case_pars("matern0.5", False, 0.5)
+    W = np.column_stack([ds["XData"], ds["zData"]])
+    sm = iak.SetupMats(ds["xData"], ds["dIData"], W=W, ctx=ctx)
+    th = np.log([max(P[k], 1e-3) for k in ["cx0", "cx1", "cd1", "cxd0", "cxd1", "cme"]])
+    whole = iak.gradHessIAK3D(sm, P, modelx, types, th)
+    shares = []
+    for r in range(world):
+        c = _FakeComm(r, world, [])
+        iak.gradHessIAK3D(sm, P, modelx, types, th, comm=c)
+        shares.append(c.mine)
+    assert all(np.any(s[:6 + 36] != 0) for s in shares[:min(world, 3)])          # every rank really owns tiles
+    for r in (0, world - 1):
+        c = _FakeComm(r, world, [s for k, s in enumerate(shares) if k != r])
+        got = iak.gradHessIAK3D(sm, P, modelx, types, th, comm=c)
+        for k in ("grad", "hess", "fim"):
+            assert scaled_err(got[k], whole[k]) <= 1e-11
+        assert got["nll"] == whole["nll"]
