@@ -766,6 +766,26 @@ def cl_terms_sets(units, structs, q, comm=None, timings=None):
     host = np.zeros((nsets, width))
     err = None
     t_dev0 = None
+    ctxs = []
+    for u in units:
+        if not any(u["setup"].ctx is c for c in ctxs):
+            ctxs.append(u["setup"].ctx)
+    if len(ctxs) > 1:
+        # several GPUs driven from THIS process (what an R session can do: no fork, no NCCL): one host thread per device inside
+        # the library (iak3d_nll_terms_batch_wsum_multi), per-device sums added on the host in device order
+        if comm is not None and comm.world > 1:
+            raise ValueError("units on several contexts cannot be combined with a multi-process communicator")
+        order = [u for c in ctxs for u in units if u["setup"].ctx is c]
+        counts = np.array([sum(1 for u in units if u["setup"].ctx is c) for c in ctxs], np.int32)
+        carr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+        dsarr = (C.c_void_p * len(order))(*[u["setup"].h for u in order])
+        w = f64(np.array([u["weight"] for u in order], float))
+        grp = np.zeros(len(order), np.int32)
+        for k in range(nsets):                     # one parameter set per call: a factor buffer per unit in flight
+            parr = (Pars * len(order))(*[structs[k]] * len(order))
+            ctxs[0].check(ctxs[0].lib.iak3d_nll_terms_batch_wsum_multi(len(ctxs), carr, iptr(counts), dsarr, parr, dptr(w), iptr(grp), 1,
+                                                                      q, dptr(host[k:k + 1])))
+        return host
     if units:
         ctx = units[0]["setup"].ctx
         try:
@@ -949,18 +969,19 @@ def setupIAK3D_CL(xData, dIData, zData, XData, compLikMats, ctx=None, rank=0, wo
                   sdfdType_cxd1=0, sdfdKnots=None):
     """iaCovMatern.R:551-575 + the unit weights of compositeLikIAK3D.R:42-179, as a list of device datasets owned by
     this rank (see :func:`cl_plan_units`)."""
+    multi = isinstance(ctx, (list, tuple))          # several GPUs from one process: units dealt to the contexts, all kept here
     ctx = ctx or default_context()
     xData = np.asarray(xData, float); dIData = np.asarray(dIData, float).reshape(-1, 2)
     zData = np.asarray(zData, float).reshape(-1); XData = np.asarray(XData, float).reshape(zData.size, -1)
-    units = cl_plan_units(compLikMats, world)
+    units = cl_plan_units(compLikMats, len(ctx) if multi else world)
     out = []
     for u in units:
-        if u["owner"] != rank:
+        if not multi and u["owner"] != rank:
             continue
         rows = u["rows"]
         W = np.column_stack([XData[rows], zData[rows]])
-        u["setup"] = SetupMats(xData[rows], dIData[rows], W=W, ctx=ctx, sdfdType_cd1=sdfdType_cd1, sdfdType_cxd0=sdfdType_cxd0,
-                               sdfdType_cxd1=sdfdType_cxd1, sdfdKnots=sdfdKnots)
+        u["setup"] = SetupMats(xData[rows], dIData[rows], W=W, ctx=ctx[u["owner"]] if multi else ctx, sdfdType_cd1=sdfdType_cd1,
+                               sdfdType_cxd0=sdfdType_cxd0, sdfdType_cxd1=sdfdType_cxd1, sdfdKnots=sdfdKnots)
         u["n"] = len(rows)
         out.append(u)
     cl = dict(compLikMats)

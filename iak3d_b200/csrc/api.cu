@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <thread>
 #include <unordered_map>
 
 #include "common.cuh"
@@ -930,7 +931,7 @@ static void fill_problem(ProblemDesc* pd, Slot* s, int32_t* d_status) {
   pd->invd = s->d_invd;
   pd->doneL = s->d_flags; pd->doneP = s->d_flags; pd->invdone = s->d_flags + (size_t)s->nRB * s->nCB;
   pd->nCB = s->nCB; pd->nRB = s->nRB; pd->mode = 0; pd->epoch = s->epoch;
-  pd->w0 = (int32_t)s->Npad; pd->q = s->q;
+  pd->w0 = (int32_t)s->Npad; pd->q = s->q; pd->nlive = (int32_t)s->n;
   pd->G = s->d_G; pd->ldG = s->q;
   pd->logsum = s->d_logsum; pd->status = d_status; pd->prof = nullptr;
 }
@@ -1123,6 +1124,33 @@ extern "C" int iak3d_nll_terms_batch_wsum(iak3d_ctx* ctx, int32_t count, iak3d_d
   cudaStreamSynchronize(ctx->stream);
   iak_pool_free(ctx, d_w); iak_pool_free(ctx, d_g); iak_pool_free(ctx, d_bad); iak_pool_free(ctx, d_own);
   return rc;
+}
+
+// The composite likelihood over several GPUs from ONE host process.  R is single-threaded and a CUDA context does not survive
+// fork() (the reference's mcmapply, compositeLikIAK3D.R:54), so the library runs one host thread per device: device d
+// evaluates its count[d] (dataset, parameter) units (datasets created on ctxs[d]) with iak3d_nll_terms_batch_wsum and the
+// per-device sums are added on the host in device order (deterministic).  h_out: ngroups * (q*q + 2) doubles.
+extern "C" int iak3d_nll_terms_batch_wsum_multi(int32_t ndev, iak3d_ctx* const* ctxs, const int32_t* count, iak3d_ds* const* ds,
+                                                const iak3d_pars* pars, const double* weight, const int32_t* group, int32_t ngroups,
+                                                int32_t q, double* h_out) {
+  if (ndev < 1 || !ctxs || !count || !h_out || ngroups <= 0 || q < 0) return IAK3D_ERR_ARG;
+  const size_t len = (size_t)ngroups * ((size_t)q * q + 2);
+  std::vector<std::vector<double>> part((size_t)ndev, std::vector<double>(len, 0.0));
+  std::vector<int> rc((size_t)ndev, 0);
+  std::vector<int64_t> off((size_t)ndev + 1, 0);
+  for (int d = 0; d < ndev; d++) { if (!ctxs[d] || count[d] < 0) return IAK3D_ERR_ARG; off[d + 1] = off[d] + count[d]; }
+  std::vector<std::thread> th;
+  for (int d = 0; d < ndev; d++) {
+    if (count[d] == 0) continue;
+    th.emplace_back([&, d]() {
+      const int64_t o = off[d];
+      rc[d] = iak3d_nll_terms_batch_wsum(ctxs[d], count[d], ds + o, pars + o, weight + o, group + o, ngroups, nullptr, part[d].data());
+    });
+  }
+  for (auto& t : th) t.join();
+  for (int d = 0; d < ndev; d++) if (rc[d] != 0) return rc[d];
+  for (size_t k = 0; k < len; k++) { double sum = 0.0; for (int d = 0; d < ndev; d++) sum += part[d][k]; h_out[k] = sum; }
+  return IAK3D_OK;
 }
 
 extern "C" int iak3d_dataset_slot_bytes(iak3d_ds* ds, int64_t* slot_bytes, int64_t* free_bytes) {

@@ -511,7 +511,7 @@ extern "C" int iak3d_predict_enqueue(iak3d_fit* f) {
     pd.doneL = nullptr; pd.doneP = f->d_pflags; pd.invdone = nullptr;
     pd.nCB = s->nCB; pd.nRB = (int32_t)(rowsP / TM); pd.mode = 1; pd.epoch = ++f->pepoch;
     pd.w0 = (int32_t)s->Npad; pd.q = f->q; pd.G = f->d_G; pd.ldG = rowsP; pd.logsum = nullptr; pd.status = f->d_status;
-    pd.prof = nullptr;
+    pd.prof = nullptr; pd.nlive = 0; pd.A = nullptr; pd.nRUA = 0; pd.kchunks = 0; pd.use_cin = 0; pd.alpha = 0.0;
     if (getenv("IAK3D_PROF") != nullptr) {      // diagnostics: per-task timestamps of the last panel (iak3d_last_task_profile)
       if (f->ntasks > ctx->prof_cap) {
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));

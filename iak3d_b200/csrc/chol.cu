@@ -21,6 +21,8 @@
 // Dependencies are per-tile epoch flags in global memory (release/acquire); tasks are claimed from
 // an atomic ticket in a topological order, so a waiting CTA only ever waits for a CTA
 // that already holds an earlier ticket: no deadlock, no co-residency requirement.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -810,42 +812,76 @@ __global__ void gather_border_kernel(const double* __restrict__ L, int64_t nRU, 
   if (c >= Npad) return;
   for (int w = 0; w < q; w++) Yw[c * q + w] = L[uidx(Npad + w, c, nRU)];
 }
-__global__ void backsolve_diag_kernel(const double* __restrict__ invd, int J, const double* __restrict__ Yw, int64_t ldY, int q,
-                                      double* __restrict__ X, int64_t ldX) {
-  // x_J (64 x q) = invL_JJ' * y_J ; thread (row i of x, rhs w)
-  __shared__ double ys[TN * 64];
-  const int tid = threadIdx.x;
-  for (int idx = tid; idx < TN * q; idx += blockDim.x) { const int c = idx / q, w = idx % q; ys[c * 64 + w] = Yw[(int64_t)(J * TN + c) * ldY + w]; }
-  __syncthreads();
-  const double* Li = invd + (int64_t)J * INVD_BLOCK;  // column-major 64x64 (stride LDB_S), lower
-  for (int idx = tid; idx < TN * q; idx += blockDim.x) {
-    const int i = idx % TN, w = idx / TN;
-    double s = 0.0;
-    for (int k = i; k < TN; k++) s += Li[(int64_t)i * LDB_S + k] * ys[k * 64 + w];   // (invL')(i,k) = invL(k,i)
-    X[(int64_t)w * ldX + J * TN + i] = s;
-  }
-}
-__global__ void backsolve_update_kernel(const double* __restrict__ L, int64_t nRU, int J, const double* __restrict__ X,
-                                        int64_t ldX, int q, double* __restrict__ Yw, int64_t ldY) {
-  // for column c < J*TN : y_c(w) -= sum_{i in block J} L(J*TN+i, c) * x_J(i, w)
-  __shared__ double xs[TN * 64];
-  const int tid = threadIdx.x;
-  for (int idx = tid; idx < TN * q; idx += blockDim.x) { const int i = idx % TN, w = idx / TN; xs[i * 64 + w] = X[(int64_t)w * ldX + J * TN + i]; }
-  __syncthreads();
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + tid;
-  if (c >= (int64_t)J * TN) return;
-  const double* col = L + uidx((int64_t)J * TN, c, nRU);     // 64 consecutive rows of one unit
-  for (int wb = 0; wb < q; wb += 16) {
-    double s[16];
-#pragma unroll
-    for (int w = 0; w < 16; w++) s[w] = 0.0;
+// One persistent kernel for the whole sweep.  Column block K is OWNED by CTA (K mod gridDim.x): the owner keeps y_K, applies
+// the updates  y_K -= L(J,K)' x_J  for J = nCB-1 ... K+1 in that order as the x_J are published (per-block flags, release /
+// acquire), then computes  x_K = inv(L_KK)' y_K  and publishes it.  At step J the owner of block J-1 serves that block
+// first and publishes x_{J-1} before it turns to its other blocks, so the chain x_J -> y_{J-1} -> x_{J-1} never waits behind
+// other work.  All CTAs are co-resident (the launcher caps the grid at the SM count); every wait is bounded.  Fixed summation
+// order: deterministic.  Shared memory: three 64 x (q + 1) arrays (x_J, the look-ahead x_{J-1}, y of the block being solved).
+__device__ __forceinline__ void bs_update_block(const double* __restrict__ L, int64_t nRU, int J, int K, const double* __restrict__ xs, int ldx,
+                                                int q, double* __restrict__ Yw, int c, int g) {
+  const double* col = L + uidx((int64_t)J * TN, (int64_t)K * TN + c, nRU);     // 64 consecutive rows of one unit
+  for (int w0 = g; w0 < q; w0 += 16) {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
     for (int i = 0; i < TN; i++) {
       const double l = col[i];
 #pragma unroll
-      for (int w = 0; w < 16; w++) s[w] += l * xs[i * 64 + ((wb + w) & 63)];
+      for (int e = 0; e < 4; e++) { const int w = w0 + 4 * e; if (w < q) acc[e] += l * xs[i * ldx + w]; }
     }
 #pragma unroll
-    for (int w = 0; w < 16; w++) if (wb + w < q) Yw[c * ldY + wb + w] -= s[w];
+    for (int e = 0; e < 4; e++) { const int w = w0 + 4 * e; if (w < q) Yw[(int64_t)(K * TN + c) * q + w] -= acc[e]; }
+  }
+}
+// x_K = inv(L_KK)' y_K into xo (shared) and X (global), then the flag; called by the whole CTA
+__device__ __forceinline__ void bs_solve_block(const double* __restrict__ invd, int K, const double* __restrict__ Yw, int q, double* __restrict__ ys,
+                                               double* __restrict__ xo, int ldx, double* __restrict__ X, int64_t Npad, int32_t* flags, int tid) {
+  const int c = tid & 63, g = tid >> 6;
+  __syncthreads();                                  // the block's updates (global) and earlier readers of ys / xo
+  for (int idx = tid; idx < TN * q; idx += 256) { const int k = idx / q, w = idx % q; ys[k * ldx + w] = Yw[(int64_t)(K * TN + k) * q + w]; }
+  __syncthreads();
+  const double* Li = invd + (int64_t)K * INVD_BLOCK;   // column-major 64 x 64 (stride LDB_S), lower: (invL')(c, k) = invL(k, c)
+  for (int w = g; w < q; w += 4) {
+    double s = 0.0;
+    for (int k = c; k < TN; k++) s += Li[(int64_t)c * LDB_S + k] * ys[k * ldx + w];
+    xo[c * ldx + w] = s;
+    X[(int64_t)w * Npad + K * TN + c] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) st_release(flags + K, 1);
+}
+__global__ void __launch_bounds__(256) backsolve_sweep_kernel(const double* __restrict__ L, int64_t nRU, int64_t Npad, int nCB,
+                                                              const double* __restrict__ invd, int q, double* __restrict__ Yw /* [col][q] */,
+                                                              double* __restrict__ X /* Npad x q col-major */, int32_t* __restrict__ flags,
+                                                              int32_t* __restrict__ status) {
+  extern __shared__ double bsm[];
+  const int ldx = q + 1;
+  double* xs = bsm; double* xn = bsm + TN * ldx; double* ys = bsm + 2 * TN * ldx;
+  const int tid = threadIdx.x, c = tid & 63, g = tid >> 6;
+  const int b = (int)blockIdx.x, G = (int)gridDim.x;
+  int32_t* abort_flag = status + 1;
+  bool have_next = false;                           // x_J is already in xn (computed and published during step J + 1)
+  for (int J = nCB - 1; J >= 0; J--) {
+    const bool mine = (J % G == b);
+    if (mine && !have_next) bs_solve_block(invd, J, Yw, q, ys, xn, ldx, X, Npad, flags, tid);
+    if (b >= J) break;                              // no owned block below J: this CTA is done
+    __syncthreads();
+    if (mine) {
+      for (int idx = tid; idx < TN * q; idx += 256) { const int i = idx / q, w = idx % q; xs[i * ldx + w] = xn[i * ldx + w]; }
+    } else {
+      if (tid == 0) wait_flag(flags + J, 1, status, abort_flag);
+      __syncthreads();
+      if (ld_volatile(abort_flag) != 0) return;
+      for (int idx = tid; idx < TN * q; idx += 256) { const int i = idx % TN, w = idx / TN; xs[i * ldx + w] = __ldcg(X + (int64_t)w * Npad + J * TN + i); }
+    }
+    __syncthreads();
+    have_next = false;
+    if ((J - 1) % G == b) {                         // critical block first, and its x at once
+      bs_update_block(L, nRU, J, J - 1, xs, ldx, q, Yw, c, g);
+      bs_solve_block(invd, J - 1, Yw, q, ys, xn, ldx, X, Npad, flags, tid);
+      have_next = true;
+    }
+    for (int K = b; K < J - 1; K += G) bs_update_block(L, nRU, J, K, xs, ldx, q, Yw, c, g);
   }
 }
 
@@ -918,6 +954,7 @@ int chol_configure(iak3d_ctx* ctx) {
   CUDA_TRY(ctx, cudaFuncSetAttribute(tile_task_kernel<-1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   CUDA_TRY(ctx, cudaFuncSetAttribute(tile_task_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   CUDA_TRY(ctx, cudaFuncSetAttribute(tile_task_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(backsolve_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * TN * 65 * (int)sizeof(double)));
   CUDA_TRY(ctx, cudaFuncSetAttribute(tile_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
   CUDA_TRY(ctx, cudaFuncSetAttribute(tile_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
   CUDA_TRY(ctx, cudaFuncSetAttribute(tile_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
@@ -977,24 +1014,22 @@ int launch_finish(iak3d_ctx* ctx, const ProblemDesc* d_problems, int32_t count, 
 }
 
 int launch_backsolve(iak3d_ctx* ctx, const double* d_L, int64_t nRU, int64_t Npad, const double* d_invd, int32_t q, double* d_X) {
-  // d_X: Npad x q column-major out
-  double* d_Yw = nullptr;
-  CUDA_TRY(ctx, cudaMalloc(&d_Yw, (size_t)q * Npad * sizeof(double)));
-  gather_border_kernel<<<(unsigned)((Npad + 127) / 128), 128, 0, ctx->stream>>>(d_L, nRU, Npad, q, d_Yw);
-  ctx->launches++;
+  // d_X: Npad x q column-major out.  Two launches, pooled scratch, no synchronisation: the caller's copy follows on the stream.
+  if (q <= 0 || q > 64) { ctx->err = "backsolve: 1 <= q <= 64"; return IAK3D_ERR_ARG; }
   const int nCB = (int)(Npad / TN);
-  for (int J = nCB - 1; J >= 0; J--) {
-    backsolve_diag_kernel<<<1, 256, 0, ctx->stream>>>(d_invd, J, d_Yw, q, q, d_X, Npad);
-    ctx->launches++;
-    if (J > 0) {
-      const int blocks = (J * TN + 127) / 128;
-      backsolve_update_kernel<<<blocks, 128, 0, ctx->stream>>>(d_L, nRU, J, d_X, Npad, q, d_Yw, q);
-      ctx->launches++;
-    }
+  double* d_Yw = nullptr; int32_t* d_fl = nullptr;
+  if (iak_pool_alloc(ctx, (void**)&d_Yw, (size_t)q * Npad * sizeof(double)) != cudaSuccess ||
+      iak_pool_alloc(ctx, (void**)&d_fl, ((size_t)nCB + 2) * sizeof(int32_t)) != cudaSuccess) {
+    iak_pool_free(ctx, d_Yw); ctx->err = "backsolve: allocation failed"; cudaGetLastError(); return IAK3D_ERR_CUDA;
   }
+  cudaMemsetAsync(d_fl, 0, ((size_t)nCB + 2) * sizeof(int32_t), ctx->stream);
+  gather_border_kernel<<<(unsigned)((Npad + 127) / 128), 128, 0, ctx->stream>>>(d_L, nRU, Npad, q, d_Yw);
+  const int grid = std::min(nCB, ctx->sm_count);
+  const size_t smem = (size_t)3 * TN * (q + 1) * sizeof(double);
+  backsolve_sweep_kernel<<<grid, 256, smem, ctx->stream>>>(d_L, nRU, Npad, nCB, d_invd, q, d_Yw, d_X, d_fl, d_fl + nCB);
+  ctx->launches += 2;
   const cudaError_t e = cudaGetLastError();
-  cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_Yw);
+  iak_pool_free(ctx, d_Yw); iak_pool_free(ctx, d_fl);
   CUDA_TRY(ctx, e);
   return 0;
 }

@@ -33,22 +33,30 @@ static_assert(INVD_BLOCK == 2 * UNIT, "inverse diagonal block = two units");
 __device__ __forceinline__ void pair_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NCW2 * 32) : "memory"); }
 __device__ __forceinline__ void task_bar() { asm volatile("bar.sync 2, %0;" ::"n"((NCW2 + 1) * 32) : "memory"); }
 
-// one k4 step of a warp's 32 x 64 sub-tile
-__device__ __forceinline__ void warp_mma2_k4(double (&acc)[4][8][2], const double* __restrict__ Ab, const double* __restrict__ Bb) {
-  double a[4], b[8];
+// one 32-deep chunk of a warp's CNT (1..4) live 8-row tiles x 64 columns; ao[mi] = offset of row tile mi inside a stage's A
+// part.  CNT is a template parameter, not a predicate: mma.sync under a per-instruction predicate makes the compiler put a
+// WARPSYNC in front of every DMMA (measured: 12.4 -> 13.9 ms for the S5 step).
+template <int CNT>
+__device__ __forceinline__ void warp_mma2_chunk(double (&acc)[4][8][2], const double* __restrict__ Ab, const int (&ao)[4],
+                                                const double* __restrict__ Bb) {
 #pragma unroll
-  for (int mi = 0; mi < 4; mi++) a[mi] = Ab[mi * 8];
+  for (int k4 = 0; k4 < KC / 4; k4++) {
+    double a[CNT], b[8];
 #pragma unroll
-  for (int ni = 0; ni < 8; ni++) b[ni] = Bb[ni * 8];
+    for (int mi = 0; mi < CNT; mi++) a[mi] = Ab[k4 * 4 * UL + ao[mi]];
 #pragma unroll
-  for (int ni = 0; ni < 8; ni++)
+    for (int ni = 0; ni < 8; ni++) b[ni] = Bb[k4 * 4 * UL + ni * 8];
 #pragma unroll
-    for (int mi = 0; mi < 4; mi++) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    for (int ni = 0; ni < 8; ni++)
+#pragma unroll
+      for (int mi = 0; mi < CNT; mi++) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+  }
 }
 
 // E3: the eight k of block KB of  X = T inv(L_jj)'  for the column tiles KB..7 (inv(L_jj)' is upper triangular)
 template <int KB>
-__device__ __forceinline__ void solve2_block(double (&x)[4][8][2], const double* __restrict__ Ta, const double* __restrict__ Yb) {
+__device__ __forceinline__ void solve2_block(double (&x)[4][8][2], const double* __restrict__ Ta, const int (&ao)[4],
+                                             const double* __restrict__ Yb) {
 #pragma unroll
   for (int h = 0; h < 2; h++) {
     const int k0 = KB * 8 + h * 4;
@@ -56,13 +64,13 @@ __device__ __forceinline__ void solve2_block(double (&x)[4][8][2], const double*
     const double* Bb = Yb + k0 * LDB_S;
     double a[4], b[8];
 #pragma unroll
-    for (int mi = 0; mi < 4; mi++) a[mi] = Ab[mi * 8];
+    for (int mi = 0; mi < 4; mi++) a[mi] = Ab[ao[mi]];
 #pragma unroll
     for (int ni = KB; ni < 8; ni++) b[ni] = Bb[ni * 8];
 #pragma unroll
     for (int ni = KB; ni < 8; ni++)
 #pragma unroll
-      for (int mi = 0; mi < 4; mi++) dmma(x[mi][ni][0], x[mi][ni][1], a[mi], b[ni]);
+      for (int mi = 0; mi < 4; mi++) dmma(x[mi][ni][0], x[mi][ni][1], a[mi], b[ni]);   // slots without a tile: computed, never stored
   }
 }
 
@@ -303,16 +311,50 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
       double* const Pt0 = P + ((int64_t)(2 * j) * nRUP + 2 * r) * UNIT;
       double* const Pt1 = P + ((int64_t)(2 * j + 1) * nRUP + 2 * r) * UNIT;
       const int kq = lane & 3, rq = lane >> 2;
-      const int aoff = (warp >> 1) * UNIT + (warp & 1) * 32 + rq;      // A fragment: unit of the row half + row in unit
       const bool is_diag = (mode == 0) && (r == (j >> 1));
+      // Row tiles (8 rows each, 16 per task) that carry data are DEALT to the four warps, so that a partly empty task costs
+      // every warp the same: rows above the diagonal block of an odd column's diagonal tile, the identity padding [n, Npad)
+      // and the rows behind the W rows never enter the K-loop (at n = 5000 the last row block holds 17 live rows of 128).
+      int tl[4], ao[4], cnt = 0;
+      {
+        unsigned live = 0xffffu;
+        if (mode == 0) {
+          const int nl = pb->nlive, w0 = pb->w0, wq = pb->q;
+          if (nl > 0) {
+            live = 0u;
+            for (int tt = 0; tt < 16; tt++) {
+              const int64_t g0 = R0 + 8 * tt;
+              if (g0 < nl || (g0 + 7 >= w0 && g0 < w0 + wq)) live |= 1u << tt;
+            }
+          }
+          if (is_diag && (j & 1)) live &= 0xff00u;        // upper 64 rows lie above the diagonal block
+          if (is_diag) live |= (j & 1) ? 0xff00u : 0x00ffu; // the diagonal block itself is always whole (identity padding included)
+        }
+        int k = 0;
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++) { tl[mi] = -1; }
+        for (int tt = 0; tt < 16; tt++)
+          if ((live >> tt) & 1u) {
+            if ((k & 3) == warp) {
+              const int slot = k >> 2;
+#pragma unroll
+              for (int mi = 0; mi < 4; mi++) if (mi == slot) tl[mi] = tt;
+              cnt = slot + 1;
+            }
+            k++;
+          }
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++) {
+          const int tt = tl[mi] < 0 ? 0 : tl[mi];
+          ao[mi] = (tt >> 3) * UNIT + (tt & 7) * 8 + rq;           // unit of the row half + row inside the unit
+        }
+      }
       double acc[4][8][2];
 #pragma unroll
       for (int mi = 0; mi < 4; mi++)
 #pragma unroll
         for (int ni = 0; ni < 8; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
       uint32_t itc = it0;
-      // diagonal tile of an odd column block: its upper 64 rows lie above the diagonal block and are never stored
-      const bool dead_rows = is_diag && ((j & 1) != 0) && (warp < 2);
       for (int c = kstart; c < nchunks; c++, itc++) {
         const uint32_t s = itc % STAGES2;
         if (prof && tid == 0) {
@@ -322,11 +364,13 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
         } else {
           mbar_wait(&full_bar[s], (itc / STAGES2) & 1, status, abort_flag);
         }
-        if (!dead_rows) {
-          const double* Ab = smem + s * STAGE_D + kq * UL + aoff;
+        {
+          const double* Ab = smem + s * STAGE_D + kq * UL;
           const double* Bb = smem + s * STAGE_D + A_STAGE + kq * UL + rq;
-#pragma unroll
-          for (int k4 = 0; k4 < KC / 4; k4++) warp_mma2_k4(acc, Ab + k4 * 4 * UL, Bb + k4 * 4 * UL);
+          if (cnt == 4) warp_mma2_chunk<4>(acc, Ab, ao, Bb);
+          else if (cnt == 3) warp_mma2_chunk<3>(acc, Ab, ao, Bb);
+          else if (cnt == 2) warp_mma2_chunk<2>(acc, Ab, ao, Bb);
+          else if (cnt == 1) warp_mma2_chunk<1>(acc, Ab, ao, Bb);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[s]);
@@ -354,7 +398,7 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
         for (int mi = 0; mi < 4; mi++)
 #pragma unroll
           for (int ni = 0; ni < 8; ni++) {
-            const int row = warp * 32 + mi * 8 + rq, col = ni * 8 + kq * 2;
+            const int row = tl[mi] * 8 + rq, col = ni * 8 + kq * 2;      // mode 2: every tile is live
             const int i0 = AT_IDX(row, col), i1 = AT_IDX(row, col + 1);
             T[i0] = (cin ? T[i0] : 0.0) + alpha * acc[mi][ni][0];
             T[i1] = (cin ? T[i1] : 0.0) + alpha * acc[mi][ni][1];
@@ -367,11 +411,13 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
       } else {
 #pragma unroll
         for (int mi = 0; mi < 4; mi++)
+          if (mi < cnt) {
 #pragma unroll
-          for (int ni = 0; ni < 8; ni++) {
-            const int row = warp * 32 + mi * 8 + rq, col = ni * 8 + kq * 2;
-            T[AT_IDX(row, col)] -= acc[mi][ni][0];
-            T[AT_IDX(row, col + 1)] -= acc[mi][ni][1];
+            for (int ni = 0; ni < 8; ni++) {
+              const int row = tl[mi] * 8 + rq, col = ni * 8 + kq * 2;
+              T[AT_IDX(row, col)] -= acc[mi][ni][0];
+              T[AT_IDX(row, col + 1)] -= acc[mi][ni][1];
+            }
           }
         if (prof && tid == 0) tp2 = (long long)gtime();
         // ---- E2: diagonal block, or the inverted diagonal block arrives ----
@@ -402,24 +448,33 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
         const bool wfetch = (mode == 1) && (pb->q > 0);
         if (row_lo < TM) {
           // ---- E3: X = tile * inv(L_jj)' on the tensor pipe; a warp reads and rewrites its own 32 rows of T ----
-          if (warp * 32 >= row_lo) {
+          // row tiles below the diagonal block (diagonal tiles: the block itself was finished by potf2)
+          int cnt3 = 0;
+#pragma unroll
+          for (int mi = 0; mi < 4; mi++) if (mi < cnt && tl[mi] * 8 >= row_lo) cnt3 = mi + 1;
+          int lo3 = 0;
+#pragma unroll
+          for (int mi = 0; mi < 4; mi++) if (mi < cnt && tl[mi] * 8 < row_lo) lo3 = mi + 1;     // dealt in ascending order: dead ones first
+          if (cnt3 > lo3) {
             double x[4][8][2];
 #pragma unroll
             for (int mi = 0; mi < 4; mi++)
 #pragma unroll
               for (int ni = 0; ni < 8; ni++) { x[mi][ni][0] = 0.0; x[mi][ni][1] = 0.0; }
-            const double* Ta = T + kq * UL + aoff;
+            const double* Ta = T + kq * UL;
             const double* Yb = Ys + kq * LDB_S + rq;
-            solve2_block<0>(x, Ta, Yb); solve2_block<1>(x, Ta, Yb); solve2_block<2>(x, Ta, Yb); solve2_block<3>(x, Ta, Yb);
-            solve2_block<4>(x, Ta, Yb); solve2_block<5>(x, Ta, Yb); solve2_block<6>(x, Ta, Yb); solve2_block<7>(x, Ta, Yb);
+            solve2_block<0>(x, Ta, ao, Yb); solve2_block<1>(x, Ta, ao, Yb); solve2_block<2>(x, Ta, ao, Yb); solve2_block<3>(x, Ta, ao, Yb);
+            solve2_block<4>(x, Ta, ao, Yb); solve2_block<5>(x, Ta, ao, Yb); solve2_block<6>(x, Ta, ao, Yb); solve2_block<7>(x, Ta, ao, Yb);
             __syncwarp();
 #pragma unroll
             for (int mi = 0; mi < 4; mi++)
+              if (mi >= lo3 && mi < cnt3) {
 #pragma unroll
-              for (int ni = 0; ni < 8; ni++) {
-                const int row = warp * 32 + mi * 8 + rq, col = ni * 8 + kq * 2;
-                T[AT_IDX(row, col)] = x[mi][ni][0];
-                T[AT_IDX(row, col + 1)] = x[mi][ni][1];
+                for (int ni = 0; ni < 8; ni++) {
+                  const int row = tl[mi] * 8 + rq, col = ni * 8 + kq * 2;
+                  T[AT_IDX(row, col)] = x[mi][ni][0];
+                  T[AT_IDX(row, col + 1)] = x[mi][ni][1];
+                }
               }
           }
           pair_bar();
@@ -462,8 +517,7 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
             mbar_wait(&inv_bar, inv_phase, status, abort_flag);
             inv_phase ^= 1;
             const double* Ws = Ys;
-            const int row0 = warp * 32 + rq;                       // + 8*mi
-            double* const Gr = pb->G + R0 + row0;
+            double* const Gr = pb->G + R0 + rq;                    // + 8 * tl[mi]: every tile of a kriging panel is live
             const int64_t ldG = pb->ldG;
             double ssq[4] = {0.0, 0.0, 0.0, 0.0};
             for (int wb = 0; wb < q; wb += 16) {
@@ -476,15 +530,15 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
                   for (int e = 0; e < 2; e++) {
                     g[mi][ni][e] = 0.0;
                     const int col = wb + ni * 8 + kq * 2 + e;
-                    gold[mi][ni][e] = (j == 0 || col >= q) ? 0.0 : __ldcg(Gr + mi * 8 + (int64_t)col * ldG);
+                    gold[mi][ni][e] = (j == 0 || col >= q) ? 0.0 : __ldcg(Gr + tl[mi] * 8 + (int64_t)col * ldG);
                   }
 #pragma unroll 4
               for (int k4 = 0; k4 < TN / 4; k4++) {
                 const int k = k4 * 4 + kq;
-                const double* tk_ = T + (k >> 5) * 2 * UNIT + (k & 31) * UL + aoff;
+                const double* tk_ = T + (k >> 5) * 2 * UNIT + (k & 31) * UL;
                 double a[4];
 #pragma unroll
-                for (int mi = 0; mi < 4; mi++) a[mi] = tk_[mi * 8];
+                for (int mi = 0; mi < 4; mi++) a[mi] = tk_[ao[mi]];
                 const double* wk = Ws + (k >> 5) * UNIT + (k & 31) * UL + wb + rq;
                 const double b0 = wk[0], b1 = wk[8];
                 if (wb == 0) {
@@ -504,7 +558,7 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
 #pragma unroll
                   for (int e = 0; e < 2; e++) {
                     const int col = wb + ni * 8 + kq * 2 + e;
-                    if (col < q) Gr[mi * 8 + (int64_t)col * ldG] = gold[mi][ni][e] + g[mi][ni][e];
+                    if (col < q) Gr[tl[mi] * 8 + (int64_t)col * ldG] = gold[mi][ni][e] + g[mi][ni][e];
                   }
             }
 #pragma unroll
@@ -515,7 +569,7 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
             if (kq == 0) {
 #pragma unroll
               for (int mi = 0; mi < 4; mi++) {
-                double* Gq = Gr + mi * 8 + (int64_t)q * ldG;
+                double* Gq = Gr + tl[mi] * 8 + (int64_t)q * ldG;
                 *Gq = (j == 0 ? 0.0 : __ldcg(Gq)) + ssq[mi];
               }
             }

@@ -219,6 +219,7 @@ struct ProblemDesc {
   double alpha;                  // mode 2: scale of the product
   int32_t epoch;
   int32_t w0, q;                 // W rows start (global row index in L) and count
+  int32_t nlive;                 // mode 0: rows [nlive, w0) are identity padding and rows >= w0 + q are empty (0: unknown, all rows live)
   double* G;                     // mode 0: q*q Gram; mode 1: rowsP x (q+1) accumulators
   int64_t ldG;
   double* logsum;                // nCB

@@ -164,6 +164,13 @@ IAK3D_API int iak3d_nll_terms_batch_fetch(iak3d_ctx* ctx, double* lndetA, double
  * context's stream is synchronised before returning. */
 IAK3D_API int iak3d_nll_terms_batch_wsum(iak3d_ctx* ctx, int32_t count, iak3d_ds* const* ds, const iak3d_pars* pars,
                                const double* weight, const int32_t* group, int32_t ngroups, double* d_out, double* h_out);
+/* The same over several GPUs from ONE host process: R is single-threaded and a CUDA context does not survive fork() (the
+ * reference's mcmapply over block pairs, compositeLikIAK3D.R:54), so the library runs one host thread per device.  Device d
+ * evaluates its count[d] units -- ds / pars / weight / group are the per-device lists concatenated in device order, the datasets
+ * of device d created on ctxs[d] -- and the per-device sums are added on the host in device order.  h_out: ngroups * (q*q + 2). */
+IAK3D_API int iak3d_nll_terms_batch_wsum_multi(int32_t ndev, iak3d_ctx* const* ctxs, const int32_t* count, iak3d_ds* const* ds,
+                                               const iak3d_pars* pars, const double* weight, const int32_t* group, int32_t ngroups,
+                                               int32_t q, double* h_out);
 /* bytes of device memory one more simultaneous evaluation of this dataset needs (a slot: factor buffer + tables), and the
  * device memory currently free -- for callers that size their batches (composite-likelihood gradient) */
 IAK3D_API int iak3d_dataset_slot_bytes(iak3d_ds* ds, int64_t* slot_bytes, int64_t* free_bytes);

@@ -112,3 +112,32 @@ def test_cl_two_ranks_share_one_gpu(ctx, optn, useReml):
     assert res[0][1] == res[1][1]                                   # both ranks hold the same value
     assert abs(res[0][1] - want) <= 1e-8 * abs(want)
     assert res[0][2] + res[1][2] == res[0][3] and min(res[0][2], res[1][2]) >= 1
+
+
+@pytest.mark.parametrize("optn,useReml", [(2, False), (1, True)])
+def test_cl_several_contexts_in_one_process(ctx, optn, useReml):
+    """What an R session can do: several device contexts driven from one process (a host thread per device inside the library,
+    iak3d_nll_terms_batch_wsum_multi).  The box has one GPU: both contexts sit on cuda:0."""
+    ds = synth.make_dataset(1500, 61)
+    P, modelx, types, cmeOpt = case_pars("edgeroi", False, 0.5)
+    blk = synth.make_blocks(ds["xData"], ds["prof"], 7, 61)
+    blk["compLikOptn"] = optn
+    ctx2 = iak.Context(0)
+    try:
+        cl1 = iak.setupIAK3D_CL(ds["xData"], ds["dIData"], ds["zData"], ds["XData"], blk, ctx=ctx)
+        cl2 = iak.setupIAK3D_CL(ds["xData"], ds["dIData"], ds["zData"], ds["XData"], blk, ctx=[ctx, ctx2])
+        assert len({id(u["setup"].ctx) for u in cl2["units"]}) == 2
+        args = (None, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True, PARBNDS, useReml)
+        v1 = iak.nllIAK3D_CL(*args, cl1, parsBTfmd=P)
+        v2 = iak.nllIAK3D_CL(*args, cl2, parsBTfmd=P)
+        want = orc.nllIAK3D_CL(None, ds["zData"], ds["XData"], modelx, 0.5, *types, cmeOpt, True, PARBNDS, useReml, blk, ds["xData"],
+                               ds["dIData"], parsBTfmd=P)
+        assert abs(v2 - want) <= 1e-8 * abs(want) and abs(v2 - v1) <= 1e-11 * abs(v1)
+        pars = _edgeroi_vector(P)
+        g1 = iak.gradnllIAK3D_CL(pars, *args[1:], cl1)
+        g2 = iak.gradnllIAK3D_CL(pars, *args[1:], cl2)
+        assert np.max(np.abs(g1 - g2)) <= 1e-3 * max(1.0, np.max(np.abs(g1)))
+    finally:
+        for u in cl2["units"]:
+            u["setup"].close()
+        ctx2.close()
