@@ -116,19 +116,31 @@ def _krige(args, rank, local_rank, world, comm):
     ds = synth.make_dataset(n, synth.SEEDS["S5"])
     P, modelx, types, cmeOpt = synth.default_pars("edgeroi")
     sm = iak.setupIAK3D(ds["xData"], ds["dIData"], ctx=ctx)
-    fit = iak.nllIAK3D(None, ds["zData"], ds["XData"], modelx=modelx, nud=0.5, sdfdType_cd1=types[0], sdfdType_cxd0=types[1],
+    # the trend model: makeXvX with modelX = c('const', 4 covariates, 'd', 'd2', 'd3') (makeXvX.R:294-353) -- p = 8 like the other
+    # workloads.  The design of the DATA rows is made by the same device code as the design of the map (iak.makeXvX).
+    names = ["const", "c1", "c2", "c3", "c4", "d", "d2", "d3"]
+    rngc = np.random.default_rng(synth.SEEDS["S5"] + 7)
+    covp = rngc.standard_normal((int(ds["prof"].max()) + 1, 4))[ds["prof"]]
+    XData = iak.makeXvX({f"c{i + 1}": covp[:, i] for i in range(4)}, ds["dIData"], names, nDiscPts=1000, XLims=None, ctx=ctx)["X"]
+    fit = iak.nllIAK3D(None, ds["zData"], XData, modelx=modelx, nud=0.5, sdfdType_cd1=types[0], sdfdType_cxd0=types[1],
                        sdfdType_cxd1=types[2], cmeOpt=cmeOpt, setupMats=sm, parBnds=PARBNDS, rtnAll=True, attachBigMats=True, parsBTfmd=P)
     side = int(np.ceil(np.sqrt(cells)))
     lo, hi = parallel.grid_tile(cells, rank, world)
     xMap = synth.make_grid(side)[lo:hi]
     m = hi - lo
     nd = len(synth.GSM_INTERVALS)
-    # one staged job per rank: its tile of cells x all six depth intervals (rows ordered interval by interval)
+    rngm = np.random.default_rng(synth.SEEDS["P1M"] + 7)
+    kk = rngm.uniform(0.02, 0.2, (4, 2)); ph = rngm.uniform(0, 2 * np.pi, 4)
+    covMap = np.asfortranarray(np.cos(xMap @ kk.T + ph[None, :]))             # covariates of the map cells (m x 4)
+    p8 = len(names)
+    XL = np.vstack([np.full(p8, -np.inf), np.full(p8, np.inf)])               # predictIAK3D.R:82-84 (constrainX4Pred = FALSE)
+    dm = iak.DesignModel(names, ["c1", "c2", "c3", "c4"], None, (), 0, 10, XL, ctx=ctx)
+    # the row-by-row staging the reference's loops imply (host-made X): kept as the comparison leg
     xy = np.tile(xMap, (nd, 1))
     dI = np.repeat(synth.GSM_INTERVALS, m, axis=0)
-    X = np.vstack([synth.grid_design(xMap, synth.GSM_INTERVALS[i], synth.SEEDS["P1M"]) for i in range(nd)])
-    # R matrices are column-major; hand the plugin call the layout the reference would (no transposition inside the timed call)
+    X = np.vstack([dm.eval(covMap, np.repeat(synth.GSM_INTERVALS[i:i + 1], m, axis=0)) for i in range(nd)])
     xy, dI, X = np.asfortranarray(xy), np.asfortranarray(dI), np.asfortranarray(X)
+    xMapF = np.asfortranarray(xMap)
     k = fit["fit"]
     peak = ctx.fp64_peak(1)
     k.stage(xy, dI, X)
@@ -147,11 +159,18 @@ def _krige(args, rank, local_rank, world, comm):
     clocks = clk.stop()
     launches = ctx.launch_count() - l0
     ms = float(comm.allreduce_max(np.array([ms]))[0])
-    # end to end through the plugin call: host arrays in, z and v out
+    # end to end through the plugin call: host arrays in, z and v out.  (1) the grid call: per-cell coordinates and covariates
+    # in, the design rows made on the device (iak3d_predict_stage_grid == predictIAK3D's loops with makeXvX inside);
+    # (2) the row-by-row call with a host-made design matrix (what round 1 measured)
+    comm.barrier(); t0 = time.perf_counter()
+    for s in range(args.steps):
+        k.stage_grid(dm, xMapF, covMap, synth.GSM_INTERVALS); k.enqueue(); z3, v3 = k.fetch()
+    e2e_grid_s = float(comm.allreduce_max(np.array([time.perf_counter() - t0]))[0])
     comm.barrier(); t0 = time.perf_counter()
     for s in range(args.steps):
         z2, v2 = k.predict(xy, dI, X)
     e2e_s = float(comm.allreduce_max(np.array([time.perf_counter() - t0]))[0])
+    assert np.allclose(z3, z2, rtol=1e-9, atol=1e-9) and np.allclose(v3, v2, rtol=1e-9, atol=1e-9)
     cells_rank = comm.gather_scalar(m)
     preds = cells * nd * args.steps
     tf = (m * nd * float(n) ** 2) * args.steps / (ms * 1e-3) / 1e12
@@ -166,8 +185,12 @@ def _krige(args, rank, local_rank, world, comm):
                              note="n^2 flops per prediction (X = Ckh L^-T); the reference's Ckh %*% iC costs 2 n^2",
                              peak_source="FP64 DMMA microbenchmark in this run"),
                per_rank=dict(cells=[int(x) for x in cells_rank]), allreduce=dict(us_per_eval=0.0, calls_per_eval=0, where="no collective in the data path"),
-               e2e=dict(value=preds / e2e_s, unit="preds/s", h2d_bytes_per_step=int(xy.nbytes + dI.nbytes + X.nbytes),
-                        d2h_bytes_per_step=int(2 * m * nd * 8)),
+               e2e=dict(value=preds / e2e_grid_s, unit="preds/s",
+                        h2d_bytes_per_step=int(xMapF.nbytes + covMap.nbytes + synth.GSM_INTERVALS.nbytes), d2h_bytes_per_step=int(2 * m * nd * 8),
+                        note="KeptFit.stage_grid + enqueue + fetch: cell coordinates and covariates in, design matrix made on the "
+                             "device (makeXvX, mlr model const + 4 covariates + d + d2 + d3), zMap and vMap out"),
+               e2e_host_design=dict(value=preds / e2e_s, unit="preds/s", h2d_bytes_per_step=int(xy.nbytes + dI.nbytes + X.nbytes),
+                                    d2h_bytes_per_step=int(2 * m * nd * 8), note="KeptFit.predict with a host-made m x p design matrix"),
                gpu_launches=int(launches), clocks=clocks)
     return out, ctx
 

@@ -336,8 +336,15 @@ def spatialCovIAK3D(D, pars, covModel="matern", ctx=None):
 # ---------------------------------------------------------------------------------------------
 # factorisation
 # ---------------------------------------------------------------------------------------------
-def lndetANDinvCb(Cm, b=None, ctx=None):
-    """-> dict(lndetC, invCb); (nan, None) where the reference returns (NA, NA)."""
+def lndetANDinvCb(Cm, b=None, ctx=None, methodSolveTEST=1):
+    """optim_functions.R:268-312 -> dict(lndetC, invCb); (nan, None) where the reference returns (NA, NA).
+
+    methodSolveTEST mirrors the reference's global of that name (:270; never set by the reference itself, default 1 = Cholesky).
+    Branch 0 (:272-289, solve() + determinant()) gives the same lndetC and invCb as branch 1 for every symmetric positive
+    definite C -- the only kind the likelihood path forms -- and is served by the same factorisation; where it would differ (an
+    indefinite but invertible C, which LU / Bunch-Kaufman can still solve) this implementation returns (NA, NA) like branch 1."""
+    if methodSolveTEST not in (0, 1):
+        raise ValueError("Error - enter valid methodSolveTEST!")
     ctx = ctx or default_context()
     Cm = f64(Cm)
     n = Cm.shape[0]

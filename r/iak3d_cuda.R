@@ -6,8 +6,15 @@
 ### and keeps everything else (readParsIAK3D, fitIAK3D, optimIt, makeXvX, ...) as the reference defines it.
 ### Forked workers cannot share a CUDA context: the glue forces the serial paths and batches those loops instead.
 
-.iak3d_ref <- list(setupIAK3D = setupIAK3D, lndetANDinvCb = lndetANDinvCb, nllIAK3D = nllIAK3D)
+.iak3d_ref <- list(setupIAK3D = setupIAK3D, lndetANDinvCb = lndetANDinvCb, nllIAK3D = nllIAK3D, nllIAK3D_CL = nllIAK3D_CL,
+                   setupIAK3D_CL = setupIAK3D_CL, makeXvX = makeXvX)
+### The only fits that stay on the reference's CPU path are those with site-specific random effects (siteIDData given:
+### listStructs4ssre, fitIAK3D.R:1091-1101), and they say so once; any other evaluation without a device handle is an error.
+.iak3d_state <- new.env()
+.iak3d_state$ssre_warned <- FALSE ; .iak3d_state$cl <- NULL
 .iak3d_modelx <- c(nugget = 0, spherical = 1, matern = 2, wendland = 3)
+### every matrix handed to .Call is a double matrix (as.matrix() of integer-valued coordinates or depths is INTSXP; the shim reads REAL())
+.iak3d_dbl <- function(x){ x <- as.matrix(x) ; storage.mode(x) <- 'double' ; x }
 
 .iak3d_maxspl <- 12   # IAK3D_MAX_SPL
 .iak3d_pv <- function(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, quirk_scale = 1){
@@ -32,9 +39,13 @@
 }
 setupIAK3D <- function(xData, dIData, nDscPts = 0, partSetup = FALSE, sdfdType_cd1 = 0, sdfdType_cxd0 = 0, sdfdType_cxd1 = 0,
                        sdfdKnots = NULL, siteIDData = NULL, XData = NULL, colnames4ssre = NULL){
-  if(!is.null(siteIDData)){ return(.iak3d_ref$setupIAK3D(xData, dIData, nDscPts, partSetup, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1,
-                                                         sdfdKnots, siteIDData, XData, colnames4ssre)) } # site-specific random effects: reference path
-  xData <- as.matrix(xData) ; dIData <- as.matrix(dIData)
+  if(!is.null(siteIDData)){   # site-specific random effects: the reference's CPU path, announced (INTEGRATION.md)
+    if(!.iak3d_state$ssre_warned){ message('iak3d: siteIDData given -- site-specific random effects are evaluated by the reference on the CPU') ; .iak3d_state$ssre_warned <- TRUE }
+    out <- .iak3d_ref$setupIAK3D(xData, dIData, nDscPts, partSetup, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, sdfdKnots, siteIDData, XData, colnames4ssre)
+    out$iak3d_cpu <- TRUE
+    return(out)
+  }
+  xData <- .iak3d_dbl(xData) ; dIData <- .iak3d_dbl(dIData)
   types <- c(sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1)
   h <- .Call('iak3dR_dataset', xData, dIData, NULL)
   if(max(types) > 0){
@@ -47,9 +58,9 @@ setupIAK3D <- function(xData, dIData, nDscPts = 0, partSetup = FALSE, sdfdType_c
 }
 
 lndetANDinvCb <- function(C, b = NULL){
-  C <- as.matrix(C)
+  C <- .iak3d_dbl(C)
   if(nrow(C) < 256){ return(.iak3d_ref$lndetANDinvCb(C, b)) } # the p x p systems stay on the host
-  tmp <- .Call('iak3dR_lndet_invCb', C, if(is.null(b)) NULL else as.matrix(b))
+  tmp <- .Call('iak3dR_lndet_invCb', C, if(is.null(b)) NULL else .iak3d_dbl(b))
   list(lndetC = tmp[[1]], invCb = tmp[[2]])
 }
 
@@ -64,13 +75,13 @@ setCIAK3D2 <- function(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_
   ### setupMats from setupIAK3D2(): set 1 = rows (prediction supports), set 2 = the data (a device dataset)
   pv <- .iak3d_pv(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt)
   if(max(sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1) > 0){               # setCApproxIAK3D2 (fitIAK3D.R:1121-1124)
-    return(.Call('iak3dR_cov_cross_spl', setupMats$set2$iak3d, pv, as.matrix(setupMats$xData), as.matrix(setupMats$dIData), setupMats$Xspl1))
+    return(.Call('iak3dR_cov_cross_spl', setupMats$set2$iak3d, pv, .iak3d_dbl(setupMats$xData), .iak3d_dbl(setupMats$dIData), setupMats$Xspl1))
   }
-  .Call('iak3dR_cov_cross', setupMats$set2$iak3d, pv, as.matrix(setupMats$xData), as.matrix(setupMats$dIData))
+  .Call('iak3dR_cov_cross', setupMats$set2$iak3d, pv, .iak3d_dbl(setupMats$xData), .iak3d_dbl(setupMats$dIData))
 }
 setupIAK3D2 <- function(xData, dIData, xData2, dIData2, sdfdType_cd1 = 0, sdfdType_cxd0 = 0, sdfdType_cxd1 = 0, sdfdKnots = NULL, ...){
   types <- c(sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1)
-  list(xData = as.matrix(xData), dIData = as.matrix(dIData),
+  list(xData = .iak3d_dbl(xData), dIData = .iak3d_dbl(dIData),
        set2 = setupIAK3D(xData2, dIData2, sdfdType_cd1 = sdfdType_cd1, sdfdType_cxd0 = sdfdType_cxd0, sdfdType_cxd1 = sdfdType_cxd1, sdfdKnots = sdfdKnots),
        Xspl1 = if(max(types) > 0) .iak3d_spl_bases(as.matrix(dIData), types, sdfdKnots) else list(NULL, NULL, NULL), Kx = TRUE)
 }
@@ -172,15 +183,25 @@ setupIAK3D2 <- function(xData, dIData, xData2, dIData2, sdfdType_cd1 = 0, sdfdTy
 
 nllIAK3D <- function(pars, zData, XData, vXU, iU, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum,
                      setupMats = NULL, parBnds, useReml, lnTfmdData, rtnAll = F, forCompLik = FALSE, attachBigMats = FALSE, nCores = 8){
-  if(is.null(setupMats$iak3d)){  # site-specific random effects: reference path
+  if(is.null(setupMats$iak3d)){
+    if(!isTRUE(setupMats$iak3d_cpu)){ stop('iak3d: setupMats carries no device dataset -- build it with the setupIAK3D of r/iak3d_cuda.R (there is no silent CPU fallback)') }
     return(.iak3d_ref$nllIAK3D(pars, zData, XData, vXU, iU, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum,
                                setupMats, parBnds, useReml, lnTfmdData, rtnAll, forCompLik, attachBigMats, nCores))
+  }
+  ### composite likelihood: the terms of this unit were computed with all the others in one batched launch (nllIAK3D_CL below)
+  if(forCompLik && !(rtnAll && attachBigMats) && !is.null(.iak3d_state$cl) && !is.null(setupMats$iak3d_unit)){
+    u <- .iak3d_state$cl$res ; k <- match(setupMats$iak3d_unit, .iak3d_state$cl$units) ; p <- ncol(as.matrix(XData))
+    if(!is.na(k)){
+      if(u[[1]][k] != 0){ return(list(pars = pars, parsBTfmd = .iak3d_state$cl$parsBTfmd, sigma2Vec = NA, WiAW = matrix(NA, p+1, p+1), lndetA = NA)) }
+      return(list(pars = pars, parsBTfmd = .iak3d_state$cl$parsBTfmd, sigma2Vec = NA,
+                  WiAW = as.matrix(forceSymmetric(Matrix(matrix(u[[3]][, k], p + 1, p + 1)))), lndetA = u[[2]][k]))
+    }
   }
   if(lnTfmdData){
     return(.iak3d_nll_lnN(pars, zData, XData, vXU, iU, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum,
                           setupMats, parBnds, rtnAll, attachBigMats))
   }
-  XData <- as.matrix(XData) ; n <- length(zData) ; p <- ncol(XData)
+  XData <- .iak3d_dbl(XData) ; zData <- as.numeric(zData) ; n <- length(zData) ; p <- ncol(XData)
   parsBTfmd <- readParsIAK3D(pars = pars, modelx = modelx, nud = nud, sdfdType_cd1 = sdfdType_cd1, sdfdType_cxd0 = sdfdType_cxd0,
                              sdfdType_cxd1 = sdfdType_cxd1, cmeOpt = cmeOpt, prodSum = prodSum, parBnds = parBnds, lnTfmdData = lnTfmdData)
   .Call('iak3dR_set_W', setupMats$iak3d, cbind(XData, zData))
@@ -223,7 +244,7 @@ nllIAK3D <- function(pars, zData, XData, vXU, iU, modelx, nud, sdfdType_cd1, sdf
 ### forks and cannot be used with CUDA)
 gradnllIAK3D <- function(pars, zData, XData, vXU, iU, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum,
                          setupMats, parBnds, useReml, lnTfmdData, ...){
-  XData <- as.matrix(XData) ; n <- length(zData) ; p <- ncol(XData) ; delta <- 1E-6
+  XData <- .iak3d_dbl(XData) ; zData <- as.numeric(zData) ; n <- length(zData) ; p <- ncol(XData) ; delta <- 1E-6
   .Call('iak3dR_set_W', setupMats$iak3d, cbind(XData, zData))
   cand <- cbind(pars, pars + delta * diag(length(pars)))
   pm <- apply(cand, 2, function(v){
@@ -244,7 +265,7 @@ gradnllIAK3D.mc <- gradnllIAK3D
 ### Faster than the batch from n ~ 4000 on (B200: 1.7x at 5000, 2.8x at 20000); pass as `gr` to optimIt in place of gradnllIAK3D.
 gradnllIAK3D_analytic <- function(pars, zData, XData, vXU, iU, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum,
                                   setupMats, parBnds, useReml, lnTfmdData, ...){
-  XData <- as.matrix(XData) ; delta <- 1E-6
+  XData <- .iak3d_dbl(XData) ; zData <- as.numeric(zData) ; delta <- 1E-6
   .Call('iak3dR_set_W', setupMats$iak3d, cbind(XData, zData))
   cand <- cbind(pars, pars + delta * diag(length(pars)))
   pm <- apply(cand, 2, function(v){
@@ -264,7 +285,7 @@ gradnllIAK3D_analytic <- function(pars, zData, XData, vXU, iU, modelx, nud, sdfd
 iak3dPredictBatch <- function(lmmFit, xMapThis, dIMapThis, XMapThis, vXUMapThis = NULL){
   types <- c(lmmFit$sdfdType_cd1, lmmFit$sdfdType_cxd0, lmmFit$sdfdType_cxd1)
   spl <- if(max(types) > 0) .iak3d_spl_bases(as.matrix(dIMapThis), types, lmmFit$sdfdKnots) else NULL
-  tmp <- .Call('iak3dR_predict_terms', lmmFit$iak3dFit, as.matrix(xMapThis), as.matrix(dIMapThis), as.matrix(XMapThis), spl, FALSE)
+  tmp <- .Call('iak3dR_predict_terms', lmmFit$iak3dFit, .iak3d_dbl(xMapThis), .iak3d_dbl(dIMapThis), .iak3d_dbl(XMapThis), spl, FALSE)
   if(!lmmFit$lnTfmdData){ return(list(z = tmp[[1]], v = tmp[[2]])) }
   ### lognormal data: muhat from setmuIAK3D, no beta uncertainty in the variance (predictIAK3D.R:232, 251)
   mu <- setmuIAK3D(XData = XMapThis, vXU = vXUMapThis, iU = lmmFit$iU, beta = lmmFit$betahat, diagC = tmp[[3]], sigma2Vec = tmp[[4]])
@@ -361,4 +382,149 @@ predMatsIAK3D_CLEV_ByBlock <- function(z_muhat , XData , xMap , dIMap , iData = 
   }
   .Call('iak3dR_mat_trim')
   return(list('zk' = zk , 'vk' = vk))
+}
+
+
+### ---- composite likelihood (compositeLikIAK3D.R:6-307) ----
+### The reference evaluates nllIAK3D(forCompLik = TRUE) once per block pair / block, forked with mcmapply (:54) or in a loop
+### (:86-104): here ALL units of one evaluation go through ONE batched launch (iak3dR_nll_terms_units; no A^-1 W
+### back-substitution), and the reference's own nllIAK3D_CL then runs serially over cached per-unit results, so its tail
+### (:181-307, compLikOptn 1-4) is untouched.  setupIAK3D_CL tags every unit's setupMats with its index.
+setupIAK3D_CL <- function(xData , dIData , nDscPts = 0 , partSetup = FALSE , compLikMats = NULL , sdfdType_cd1 = 0 , sdfdType_cxd0 = 0 ,
+                          sdfdType_cxd1 = 0 , sdfdKnots = NULL){
+  sm <- .iak3d_ref$setupIAK3D_CL(xData, dIData, nDscPts, partSetup, compLikMats, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, sdfdKnots)
+  for(i in seq_along(sm)){ if(!is.null(sm[[i]])){ sm[[i]]$iak3d_unit <- i } }
+  sm
+}
+nllIAK3D_CL <- function(pars , zData , XData , modelx , nud , sdfdType_cd1 , sdfdType_cxd0 , sdfdType_cxd1 , cmeOpt , prodSum , setupMats = NULL ,
+                        parBnds , useReml , compLikMats , parallel_nll_4cl = TRUE , rtnAll = F , attachBigMats = rtnAll , nCores = 1){
+  XData <- as.matrix(XData)
+  nP <- nrow(compLikMats$subsetPairsAdj) ; nB <- length(compLikMats$listBlocks) ; optn <- compLikMats$compLikOptn
+  rowsOf <- function(i){ if(i <= nP){ c(compLikMats$listBlocks[[compLikMats$subsetPairsAdj[i,1]]]$i , compLikMats$listBlocks[[compLikMats$subsetPairsAdj[i,2]]]$i)
+                         }else{ compLikMats$listBlocks[[i - nP]]$i } }
+  units <- c(if(optn < 4) seq(nP) else NULL , if(optn %in% c(1, 3, 4)) nP + seq(nB) else NULL)
+  units <- units[sapply(units, function(i){ !is.null(setupMats[[i]]$iak3d) })]
+  if(length(units) > 0 && !(rtnAll && attachBigMats)){
+    parsBTfmd <- readParsIAK3D(pars = pars, modelx = modelx, nud = nud, sdfdType_cd1 = sdfdType_cd1, sdfdType_cxd0 = sdfdType_cxd0,
+                               sdfdType_cxd1 = sdfdType_cxd1, cmeOpt = cmeOpt, prodSum = prodSum, parBnds = parBnds, lnTfmdData = FALSE)
+    for(i in units){ r <- rowsOf(i) ; .Call('iak3dR_set_W', setupMats[[i]]$iak3d, cbind(XData[r,,drop=FALSE], zData[r])) }
+    res <- .Call('iak3dR_nll_terms_units', lapply(units, function(i){ setupMats[[i]]$iak3d }),
+                 .iak3d_pv(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt))
+    .iak3d_state$cl <- list(units = units, res = res, parsBTfmd = parsBTfmd)
+    on.exit(.iak3d_state$cl <- NULL)
+  }
+  .iak3d_ref$nllIAK3D_CL(pars = pars, zData = zData, XData = XData, modelx = modelx, nud = nud, sdfdType_cd1 = sdfdType_cd1,
+                         sdfdType_cxd0 = sdfdType_cxd0, sdfdType_cxd1 = sdfdType_cxd1, cmeOpt = cmeOpt, prodSum = prodSum, setupMats = setupMats,
+                         parBnds = parBnds, useReml = useReml, compLikMats = compLikMats, parallel_nll_4cl = FALSE, rtnAll = rtnAll,
+                         attachBigMats = attachBigMats, nCores = 1)
+}
+
+### predMatsIAK3D_CL_ByBlock (compositeLikIAK3D.R:471-607): for the map supports of block k, the kriging terms against the data
+### of every adjacent pair (k, l), averaged over the neighbours.  Each pair is one kept factorisation on the device;
+### IAK3D_FIT_CROSS_SQUARE reproduces the reference's Ckh = block of setCIAK3D of the joined supports (:540-552).
+predMatsIAK3D_CL_ByBlock <- function(z_muhat , XData , xMap , dIMap , iData = seq(length(z_muhat)) , lmmFit){
+  XData <- as.matrix(XData) ; xMap <- as.matrix(xMap) ; dIMap <- as.matrix(dIMap)
+  blockMap <- getBlocksFromLocations(xMap = xMap , compLikMats = lmmFit$compLikMats)
+  nxMap <- length(blockMap) ; n <- length(z_muhat) ; p <- ncol(XData)
+  diagCkk <- diagCkhiCChk <- CkhiCz_muhat <- matrix(NA , nxMap , 1) ; CkhiCX <- matrix(NA , nxMap , p)
+  types <- c(lmmFit$sdfdType_cd1, lmmFit$sdfdType_cxd0, lmmFit$sdfdType_cxd1)
+  pv <- .iak3d_pv(lmmFit$parsBTfmd, lmmFit$modelx, types[1], types[2], types[3], lmmFit$cmeOpt)
+  for (iBlock in 1:max(blockMap)){
+    iMapThis <- which(blockMap == iBlock) ; m <- length(iMapThis)
+    if(m == 0){ next }
+    iBlocksAdj <- getAdjacentBlocks(iBlock = iBlock , compLikMats = lmmFit$compLikMats)
+    iDatak <- lmmFit$compLikMats$listBlocks[[iBlock]]$i
+    if(length(iData) < n){ iDatak <- intersect(iDatak , iData) }
+    spl <- if(max(types) > 0) .iak3d_spl_bases(dIMap[iMapThis,,drop=FALSE], types, lmmFit$sdfdKnots) else NULL
+    qS <- czS <- numeric(m) ; cxS <- matrix(0 , m , p)
+    for(i in seq_along(iBlocksAdj)){
+      iDatal <- lmmFit$compLikMats$listBlocks[[iBlocksAdj[i]]]$i
+      if(length(iData) < n){ iDatal <- intersect(iDatal , iData) }
+      iThis <- c(iDatak , iDatal)
+      sm <- setupIAK3D(xData = lmmFit$xData[iThis,,drop=FALSE] , dIData = as.matrix(lmmFit$dIData[iThis,,drop=FALSE]) , sdfdType_cd1 = types[1] ,
+                       sdfdType_cxd0 = types[2] , sdfdType_cxd1 = types[3] , sdfdKnots = lmmFit$sdfdKnots)
+      .Call('iak3dR_set_W', sm$iak3d, cbind(XData[iThis,,drop=FALSE], z_muhat[iThis]))
+      fit <- .Call('iak3dR_fit_res', sm$iak3d, pv, numeric(p), diag(p), as.numeric(z_muhat[iThis]))
+      .Call('iak3dR_fit_option', fit, 1L, 1L) ; .Call('iak3dR_fit_option', fit, 2L, 1L)     # keep Ckh iC X; Ckh as a block of the square C
+      tmp <- .Call('iak3dR_predict_terms', fit, xMap[iMapThis,,drop=FALSE], dIMap[iMapThis,,drop=FALSE], matrix(0, m, p), spl, TRUE)
+      if(i == 1){ diagCkk[iMapThis,1] <- tmp[[3]] }
+      qS <- qS + tmp[[6]] ; czS <- czS + tmp[[5]] ; cxS <- cxS + tmp[[7]]
+      rm(fit, sm)
+    }
+    diagCkhiCChk[iMapThis,1] <- qS / length(iBlocksAdj)
+    CkhiCX[iMapThis,] <- cxS / length(iBlocksAdj)
+    CkhiCz_muhat[iMapThis,1] <- czS / length(iBlocksAdj)
+  }
+  gc(FALSE)
+  return(list('diagCkk' = diagCkk , 'diagCkhiCChk' = diagCkhiCChk , 'CkhiCX' = CkhiCX , 'CkhiCz_muhat' = CkhiCz_muhat))
+}
+
+### ---- block construction (compositeLikIAK3D.R:803-1133): the distance / nearest-centroid passes on the device ----
+getBlocksFromLocations <- function(xMap , compLikMats){
+  vc <- do.call(rbind, lapply(compLikMats$listBlocks, function(b){ matrix(b$centroid, nrow = 1) }))
+  .Call('iak3dR_nearest_centroid', as.matrix(xMap) + 0, vc + 0, FALSE)[[1]]
+}
+calcnPerCluster <- function(vcentres , xU){
+  as.numeric(.Call('iak3dR_nearest_centroid', as.matrix(xU) + 0, as.matrix(vcentres) + 0, TRUE)[[2]])
+}
+### setVoronoiBlocks with its three slow steps replaced: greedy seeding (:853-884), Voronoi assignment (:887-888) and the
+### deldir adjacency (:907-916); balanceNeighbours / balanceNeighbours2 / setVoronoiBlocksWrap of the reference call it unchanged.
+setVoronoiBlocks <- function(x , nPerBlock = 50 , plotVor = F , vcentres = NULL){
+  x <- as.matrix(x) + 0
+  xU <- x[!duplicated(x),,drop=FALSE]
+  if(is.null(vcentres)){ vcentres <- .Call('iak3dR_voronoi_seed', xU, as.integer(nPerBlock)) }
+  nBlocks <- nrow(vcentres)
+  iBlock <- .Call('iak3dR_nearest_centroid', xU, vcentres + 0, FALSE)[[1]]
+  listBlocks <- list()
+  for(i in 1:nBlocks){
+    xUi <- xU[which(iBlock == i),,drop=FALSE]
+    listBlocks[[i]] <- list(centroid = vcentres[i,,drop=FALSE], xU = xUi,
+                            i = which(is.element(x[,1] , xUi[,1]) & is.element(x[,2] , xUi[,2])))
+  }
+  subsetPairsAdj <- .Call('iak3dR_dirichlet_adjacency', vcentres + 0)
+  key <- function(m){ if(is.null(m) || nrow(m) == 0) character(0) else paste(m[,1], m[,2]) }
+  allPairs <- if(nBlocks > 1) t(combn(nBlocks, 2)) else matrix(0L, 0, 2)
+  subsetPairsNonadj <- allPairs[!(key(allPairs) %in% key(subsetPairsAdj)),,drop=FALSE]
+  if(nrow(subsetPairsNonadj) == 0){ subsetPairsNonadj <- c() }
+  return(list('listBlocks' = listBlocks , 'subsetPairsAdj' = subsetPairsAdj , 'subsetPairsNonadj' = subsetPairsNonadj))
+}
+
+### ---- makeXvX on the device for prediction grids (makeXvX.R:294-353, 'mlr' with lnTfmdData = FALSE) ----
+### iak3dDesignMlr flattens modelX (+ allKnotsd, nDiscPts, XLims) into the specification of include/iak3d.h; Cubist designs are
+### flattened the same way from cubistModel$listRules / listCoeffs_iv / comms4XCubist (iak3d_b200/design.py shows the layout).
+iak3dDesignMlr <- function(namesX, covNames, covLevels = list(), allKnotsd = c(), nDiscPts = 10, XLims = NULL){
+  if(length(allKnotsd) > 0){ namesX <- namesX[!(namesX %in% c('d', 'd2', 'd3'))] }
+  p <- length(namesX) ; nint <- max(length(allKnotsd) - 2, 0)
+  ipS <- which(substr(namesX, 1, 8) == 'dSpline.') ; nspl <- length(ipS)
+  if(is.null(XLims)){ XL <- rbind(rep(-Inf, p), rep(Inf, p)) ; has <- 0L ; infB <- 1L
+  }else{ XL <- XLims ; has <- 1L ; infB <- as.integer((min(XL[1,]) == -Inf) & (max(XL[2,]) == Inf)) }
+  kind <- cov <- integer(p) ; level <- rep(NaN, p) ; l <- 2
+  for(j in seq(p)){
+    nm <- namesX[j] ; base <- NA
+    if(nm == 'const'){ kind[j] <- 0L }else if(nm == 'd'){ kind[j] <- 1L }else if(nm == 'd2'){ kind[j] <- 2L }else if(nm == 'd3'){ kind[j] <- 3L
+    }else if(substr(nm, 1, 8) == 'dSpline.'){ kind[j] <- 4L
+    }else if(substr(nm, 1, 3) == 'd2.'){ kind[j] <- 2L ; base <- substr(nm, 4, nchar(nm))
+    }else if(substr(nm, 1, 3) == 'd3.'){ kind[j] <- 3L ; base <- substr(nm, 4, nchar(nm))
+    }else if(substr(nm, 1, 2) == 'd.'){ kind[j] <- 1L ; base <- substr(nm, 3, nchar(nm))
+    }else{ kind[j] <- 0L ; base <- nm }
+    if(kind[j] == 4L){ cov[j] <- match(j, ipS) - 1L
+    }else if(is.na(base)){ cov[j] <- -1L
+    }else{
+      cov[j] <- match(base, covNames) - 1L
+      if(!is.null(covLevels[[base]])){ if(j == 1 || namesX[j] != namesX[j-1]){ l <- 2 } ; level[j] <- l ; l <- l + 1 }
+    }
+  }
+  ord <- c(which(namesX == 'd'), which(substr(namesX, 1, 2) == 'd.'), which(namesX == 'd2'), which(substr(namesX, 1, 3) == 'd2.'),
+           which(namesX == 'd3'), which(substr(namesX, 1, 3) == 'd3.'))
+  cpos <- rep(-1L, p) ; cpos[ord] <- seq_along(ord) - 1L
+  ispec <- c(0L, p, length(covNames), nspl, 0L, nint, as.integer(nDiscPts), has, infB, as.integer(rbind(kind, cov, cpos)))
+  dspec <- c(if(length(allKnotsd) > 0) allKnotsd[c(1, length(allKnotsd))] else c(0, 1), if(nint > 0) allKnotsd[2:(nint + 1)] else NULL,
+             XL[1,], XL[2,], level)
+  list(handle = .Call('iak3dR_design', as.integer(ispec), as.numeric(dspec)), namesX = namesX, covNames = covNames)
+}
+### predictIAK3D's double loop over depths and batches (predictIAK3D.R:144-255) in one call; returns list(zMap, vMap), ndIMap x nxMap
+iak3dPredictGrid <- function(lmmFit, design, xMap, covsMap, dIMap, nxPerBatch = 2000){
+  covM <- if(length(design$covNames) > 0) as.matrix(covsMap[, design$covNames, drop = FALSE]) + 0 else NULL
+  tmp <- .Call('iak3dR_predict_grid', lmmFit$iak3dFit, design$handle, as.matrix(xMap) + 0, covM, round(as.matrix(dIMap), digits = 2), nxPerBatch)
+  list(zMap = t(tmp[[1]]), vMap = t(tmp[[2]]))
 }

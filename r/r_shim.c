@@ -55,7 +55,14 @@ static void pars_from_ptr(const double* v, iak3d_pars* P) {
 }
 
 /* setupIAK3D: xData (n x 2), dIData (n x 2, already rounded, fitIAK3D.R:127), W = cbind(X, z) or NULL */
+static void need_real(SEXP x, const char* what) {
+  if (TYPEOF(x) != REALSXP) error("iak3d: %s must be a double matrix / vector (use storage.mode(x) <- 'double')", what);
+}
 SEXP iak3dR_dataset(SEXP xy, SEXP dI, SEXP W) {
+  need_real(xy, "xData"); need_real(dI, "dIData");
+  if (!isNull(W)) need_real(W, "W");
+  if (ncols(xy) != 2 || ncols(dI) != 2 || nrows(dI) != nrows(xy) || (!isNull(W) && nrows(W) != nrows(xy)))
+    error("iak3d: xData and dIData must be n x 2 and W n x q");
   const int64_t n = nrows(xy);
   iak3d_ds* ds = NULL;
   const int q = isNull(W) ? 0 : ncols(W);
@@ -68,6 +75,7 @@ SEXP iak3dR_dataset(SEXP xy, SEXP dI, SEXP W) {
 }
 
 SEXP iak3dR_set_W(SEXP dsp, SEXP W) {
+  need_real(W, "W");
   int st = iak3d_dataset_set_W((iak3d_ds*)R_ExternalPtrAddr(dsp), REAL(W), ncols(W));
   if (st != IAK3D_OK) error("iak3d_dataset_set_W: %s", iak3d_last_error(g_ctx));
   return R_NilValue;
@@ -386,6 +394,115 @@ SEXP iak3dR_mat_coldot(SEXP Ap, SEXP Bp) {
   return out;
 }
 
+/* ---- composite likelihood: every unit (block pair / block) of compositeLikIAK3D.R:49-155 in ONE batched launch ----
+ * dslist: list of dataset handles (one per unit, W already set); pv: the parameter vector they share.
+ * Returns list(status (count), lndetA (count), WiAW (q*q x count)). */
+SEXP iak3dR_nll_terms_units(SEXP dslist, SEXP pv) {
+  const int count = LENGTH(dslist);
+  if (count < 1) error("iak3d: empty unit list");
+  iak3d_pars P0; pars_from(pv, &P0);
+  iak3d_pars* P = (iak3d_pars*)R_alloc(count, sizeof(iak3d_pars));
+  iak3d_ds** dss = (iak3d_ds**)R_alloc(count, sizeof(iak3d_ds*));
+  for (int i = 0; i < count; i++) { P[i] = P0; dss[i] = (iak3d_ds*)R_ExternalPtrAddr(VECTOR_ELT(dslist, i)); }
+  int32_t q = 0; int64_t n = 0;
+  iak3d_dataset_info(dss[0], &n, NULL, NULL, &q);
+  SEXP status = PROTECT(allocVector(INTSXP, count));
+  SEXP lndet = PROTECT(allocVector(REALSXP, count));
+  SEXP G = PROTECT(allocMatrix(REALSXP, q * q, count));
+  int st = iak3d_nll_terms_batch(ctx_get(), count, dss, P, REAL(lndet), REAL(G), (int32_t*)INTEGER(status));
+  if (st < 0) error("iak3d_nll_terms_batch: %s", iak3d_last_error(g_ctx));
+  SEXP out = PROTECT(allocVector(VECSXP, 3));
+  SET_VECTOR_ELT(out, 0, status); SET_VECTOR_ELT(out, 1, lndet); SET_VECTOR_ELT(out, 2, G);
+  UNPROTECT(4);
+  return out;
+}
+
+/* ---- makeXvX on the device (makeXvX.R:1; include/iak3d.h: iak3d_design_*) ---- */
+static void design_finalizer(SEXP p) {
+  iak3d_design* g = (iak3d_design*)R_ExternalPtrAddr(p);
+  if (g) { iak3d_design_destroy(g); R_ClearExternalPtr(p); }
+}
+SEXP iak3dR_design(SEXP ispec, SEXP dspec) {     /* integer and double parts of the flat specification */
+  iak3d_design* g = NULL;
+  int st = iak3d_design_create(ctx_get(), (const int32_t*)INTEGER(ispec), LENGTH(ispec), REAL(dspec), LENGTH(dspec), &g);
+  if (st != IAK3D_OK) error("iak3d_design_create: %s", iak3d_last_error(g_ctx));
+  SEXP p = PROTECT(R_MakeExternalPtr(g, R_NilValue, R_NilValue));
+  R_RegisterCFinalizerEx(p, design_finalizer, TRUE);
+  UNPROTECT(1);
+  return p;
+}
+SEXP iak3dR_design_eval(SEXP gp, SEXP covs, SEXP dI) {          /* covs: m x ncov (or NULL), dI: m x 2 -> X (m x p) */
+  iak3d_design* g = (iak3d_design*)R_ExternalPtrAddr(gp);
+  int32_t p = 0, ncov = 0;
+  iak3d_design_info(g, &p, &ncov);
+  const int m = nrows(dI);
+  SEXP X = PROTECT(allocMatrix(REALSXP, m, p));
+  int st = iak3d_design_eval(g, m, isNull(covs) ? NULL : REAL(covs), REAL(dI), REAL(X), NULL, NULL);
+  if (st != IAK3D_OK) error("iak3d_design_eval: %s", iak3d_last_error(g_ctx));
+  UNPROTECT(1);
+  return X;
+}
+/* the whole map of predictIAK3D in one staging: list(zMap, vMap), each ndIMap x nxMap like the reference's */
+SEXP iak3dR_predict_grid(SEXP fp, SEXP gp, SEXP xyCell, SEXP covCell, SEXP dIInt, SEXP nxPerBatch) {
+  iak3d_fit* f = (iak3d_fit*)R_ExternalPtrAddr(fp);
+  iak3d_design* g = (iak3d_design*)R_ExternalPtrAddr(gp);
+  const int ncell = nrows(xyCell), nint = nrows(dIInt);
+  int st = iak3d_predict_stage_grid(f, g, ncell, REAL(xyCell), isNull(covCell) ? NULL : REAL(covCell), nint, REAL(dIInt), (int64_t)asReal(nxPerBatch));
+  if (st == IAK3D_OK) st = iak3d_predict_enqueue(f);
+  if (st != IAK3D_OK) error("iak3d_predict_stage_grid: %s", iak3d_last_error(g_ctx));
+  SEXP zt = PROTECT(allocMatrix(REALSXP, ncell, nint));           /* support (i, c) is element i * ncell + c: t(zMap) */
+  SEXP vt = PROTECT(allocMatrix(REALSXP, ncell, nint));
+  st = iak3d_predict_fetch(f, REAL(zt), REAL(vt));
+  if (st != IAK3D_OK) error("iak3d_predict_fetch: %s", iak3d_last_error(g_ctx));
+  SEXP out = PROTECT(allocVector(VECSXP, 2));
+  SET_VECTOR_ELT(out, 0, zt); SET_VECTOR_ELT(out, 1, vt);
+  UNPROTECT(3);
+  return out;
+}
+
+/* ---- block construction (compositeLikIAK3D.R:803-1133) ---- */
+SEXP iak3dR_nearest_centroid(SEXP xy, SEXP vcentres, SEXP wantCounts) {   /* 1-based block of every location [, counts] */
+  iak3d_points* P = NULL;
+  const int m = nrows(xy), nB = nrows(vcentres);
+  int st = iak3d_points_create(ctx_get(), m, REAL(xy), &P);
+  if (st != IAK3D_OK) error("iak3d_points_create: %s", iak3d_last_error(g_ctx));
+  SEXP blk = PROTECT(allocVector(INTSXP, m));
+  SEXP cnt = PROTECT(allocVector(REALSXP, nB));
+  int64_t* c64 = (int64_t*)R_alloc(nB, sizeof(int64_t));
+  st = iak3d_points_nearest(P, nB, REAL(vcentres), (int32_t*)INTEGER(blk), asLogical(wantCounts) ? c64 : NULL);
+  iak3d_points_destroy(P);
+  if (st != IAK3D_OK) error("iak3d_points_nearest: %s", iak3d_last_error(g_ctx));
+  for (int i = 0; i < m; i++) INTEGER(blk)[i] += 1;
+  for (int b = 0; b < nB; b++) REAL(cnt)[b] = asLogical(wantCounts) ? (double)c64[b] : 0.0;
+  SEXP out = PROTECT(allocVector(VECSXP, 2));
+  SET_VECTOR_ELT(out, 0, blk); SET_VECTOR_ELT(out, 1, cnt);
+  UNPROTECT(3);
+  return out;
+}
+SEXP iak3dR_voronoi_seed(SEXP xU, SEXP nPerBlock) {                 /* vcentres (nBlocks x 2) */
+  const int nU = nrows(xU), npb = asInteger(nPerBlock);
+  const int nB = nU / (npb > 0 ? npb : 1);
+  if (nB < 1) error("iak3d: fewer unique locations than nPerBlock");
+  SEXP vc = PROTECT(allocMatrix(REALSXP, nB, 2));
+  int32_t got = 0;
+  int st = iak3d_voronoi_seed(nU, REAL(xU), npb, nB, &got, REAL(vc));
+  if (st != IAK3D_OK) error("iak3d_voronoi_seed failed (status %d)", st);
+  UNPROTECT(1);
+  return vc;
+}
+SEXP iak3dR_dirichlet_adjacency(SEXP vcentres) {                    /* subsetPairsAdj: npairs x 2, 1-based, i < j */
+  const int nB = nrows(vcentres);
+  const int cap = 3 * nB + 3;
+  int32_t* pr = (int32_t*)R_alloc(2 * (size_t)cap, sizeof(int32_t));
+  int64_t np = 0;
+  int st = iak3d_dirichlet_adjacency(nB, REAL(vcentres), pr, cap, &np);
+  if (st != IAK3D_OK) error("iak3d_dirichlet_adjacency failed (status %d)", st);
+  SEXP out = PROTECT(allocMatrix(INTSXP, (int)np, 2));
+  for (int k = 0; k < (int)np; k++) { INTEGER(out)[k] = pr[2 * k] + 1; INTEGER(out)[(int)np + k] = pr[2 * k + 1] + 1; }
+  UNPROTECT(1);
+  return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
   {"iak3dR_dataset", (DL_FUNC)&iak3dR_dataset, 3},       {"iak3dR_set_W", (DL_FUNC)&iak3dR_set_W, 2},
   {"iak3dR_nll_terms", (DL_FUNC)&iak3dR_nll_terms, 2},   {"iak3dR_nll_terms_iAW", (DL_FUNC)&iak3dR_nll_terms_iAW, 2},
@@ -401,6 +518,11 @@ static const R_CallMethodDef call_methods[] = {
   {"iak3dR_mat_copy", (DL_FUNC)&iak3dR_mat_copy, 3},     {"iak3dR_mat_gemm_nt", (DL_FUNC)&iak3dR_mat_gemm_nt, 5},
   {"iak3dR_mat_spd_inverse", (DL_FUNC)&iak3dR_mat_spd_inverse, 1}, {"iak3dR_mat_cov_build", (DL_FUNC)&iak3dR_mat_cov_build, 2},
   {"iak3dR_mat_coldot", (DL_FUNC)&iak3dR_mat_coldot, 2}, {"iak3dR_mat_trim", (DL_FUNC)&iak3dR_mat_trim, 0},
+  {"iak3dR_nll_terms_units", (DL_FUNC)&iak3dR_nll_terms_units, 2},
+  {"iak3dR_design", (DL_FUNC)&iak3dR_design, 2},         {"iak3dR_design_eval", (DL_FUNC)&iak3dR_design_eval, 3},
+  {"iak3dR_predict_grid", (DL_FUNC)&iak3dR_predict_grid, 6},
+  {"iak3dR_nearest_centroid", (DL_FUNC)&iak3dR_nearest_centroid, 3}, {"iak3dR_voronoi_seed", (DL_FUNC)&iak3dR_voronoi_seed, 2},
+  {"iak3dR_dirichlet_adjacency", (DL_FUNC)&iak3dR_dirichlet_adjacency, 1},
   {NULL, NULL, 0}};
 
 void R_init_iak3dR(DllInfo* dll) {
