@@ -240,8 +240,9 @@ def run_s5(args, rank, local_rank, world, comm):
         config=s5_config(n, p, sm.nxU, sm.ndIU, modelx, types, cmeOpt, nb, world),
         single_eval_ms=single_ms, single_eval_per_s=1e3 / single_ms, gradient_wall_ms=grad_ms, fp64_peaks_tflops=peaks,
         stage_ms=dict(tables=stage[0], cov_build=stage[1], factorise=stage[2], finish=stage[3]),
-        roofline=dict(kernel="tile_task_kernel (tile Cholesky + bordered solves, FP64 DMMA)", bound="tensor", achieved=tf,
-                      peak=peaks["dmma"], unit="TFLOP/s", frac=tf / peaks["dmma"], traffic=ncu_traffic("tile_task_kernel", n, nb),
+        roofline=dict(kernel="tile_pair_kernel<0> (tile Cholesky + bordered solves, FP64 DMMA; two half-size CTAs per SM, chol_pair.cuh)",
+                      bound="tensor", achieved=tf,
+                      peak=peaks["dmma"], unit="TFLOP/s", frac=tf / peaks["dmma"], traffic=ncu_traffic("tile_pair_kernel", n, nb),
                       flops_per_launch=nb * n ** 3 / 3.0,
                       peak_source="FP64 mma.sync m8n8k4 microbenchmark run inside this bench (MEASURED_PEAKS.json holds no FP64 "
                                   "figure); DFMA microbenchmark = %.1f TFLOP/s" % peaks["dfma"]),

@@ -95,7 +95,7 @@ def _cl(args, rank, local_rank, world, comm):
                              allreduce_calls=int(tg.get("allreduce_calls", 0)), allreduce_us=float(tg.get("allreduce_us", 0.0)),
                              what="gradnllIAK3D_CL: npar + 1 evaluations as (units x parameter sets) batched launches + ONE all-reduce"),
                stage_ms=dict(tables=stage[0], cov_build=stage[1], factorise=stage[2], finish=stage[3]),
-               roofline=dict(kernel="tile_task_kernel (rank 0's share)", bound="tensor", achieved=tf_rank, peak=peak, unit="TFLOP/s",
+               roofline=dict(kernel="tile_pair_kernel<0> (rank 0's share)", bound="tensor", achieved=tf_rank, peak=peak, unit="TFLOP/s",
                              frac=tf_rank / peak, traffic=None, flops_per_launch=flops_rank,
                              peak_source="FP64 DMMA microbenchmark in this run"),
                whole_job_tflops=flops * args.steps / (ms * 1e-3) / 1e12,
@@ -180,7 +180,7 @@ def _krige(args, rank, local_rank, world, comm):
                                     f"{n}-interval fit (BASELINE configs[4])", n=n, p=ds["XData"].shape[1], cells=cells, intervals=nd,
                            parallelism=f"grid tiles over {world} GPU(s), no data-path collective",
                            l2="each 16384-support panel (0.7 GB) exceeds the 126 MB L2; no flush needed"),
-               roofline=dict(kernel="tile_task_kernel, mode 1 (rank 0's tile)", bound="tensor", achieved=tf, peak=peak, unit="TFLOP/s",
+               roofline=dict(kernel="tile_pair_kernel<1> (kriging panels; rank 0's tile)", bound="tensor", achieved=tf, peak=peak, unit="TFLOP/s",
                              frac=tf / peak, traffic=None, flops_per_launch=16384.0 * n * n,
                              note="n^2 flops per prediction (X = Ckh L^-T); the reference's Ckh %*% iC costs 2 n^2",
                              peak_source="FP64 DMMA microbenchmark in this run"),

@@ -122,7 +122,8 @@ def test_cl_several_contexts_in_one_process(ctx, optn, useReml):
     P, modelx, types, cmeOpt = case_pars("edgeroi", False, 0.5)
     blk = synth.make_blocks(ds["xData"], ds["prof"], 7, 61)
     blk["compLikOptn"] = optn
-    ctx2 = iak.Context(0)
+    import torch
+    ctx2 = iak.Context(1 if torch.cuda.device_count() > 1 else 0)       # a second GPU when the box has one
     try:
         cl1 = iak.setupIAK3D_CL(ds["xData"], ds["dIData"], ds["zData"], ds["XData"], blk, ctx=ctx)
         cl2 = iak.setupIAK3D_CL(ds["xData"], ds["dIData"], ds["zData"], ds["XData"], blk, ctx=[ctx, ctx2])
