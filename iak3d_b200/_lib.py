@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libiak3d.so")
 OK, NOT_SPD, BAD_PARS = 0, 1, 2
 ERR_CUDA, ERR_ARG, ERR_TIMEOUT = -1, -2, -3
 MAX_SPL = 12          # IAK3D_MAX_SPL
+MAX_SSRE = 8          # IAK3D_MAX_SSRE
 FIT_KEEP_CKHICX, FIT_CROSS_SQUARE = 1, 2
 MODELX = {"nugget": 0, "spherical": 1, "matern": 2, "wendland": 3}
 
@@ -29,6 +30,7 @@ class Pars(C.Structure):
         ("cx0", C.c_double), ("cx1", C.c_double), ("cd1", C.c_double), ("cxd0", C.c_double), ("cxd1", C.c_double),
         ("cme", C.c_double), ("sdfdPars", (C.c_double * 2) * 3), ("quirk_scale", C.c_double),
         ("sdfdSpl", (C.c_double * MAX_SPL) * 3),
+        ("nssre", C.c_int32), ("reserved_", C.c_int32), ("cssre", C.c_double * MAX_SSRE),
     ]
 
 
@@ -51,6 +53,9 @@ _PROTOS = {
     "iak3d_dataset_ids": (C.c_int, [_vp, _ip, _ip]),
     "iak3d_dataset_set_sdfd_spline": (C.c_int, [_vp, _i32, _i32, _dp]),
     "iak3d_dataset_set_lnN_column": (C.c_int, [_vp, _i32]),
+    "iak3d_dataset_set_ssre": (C.c_int, [_vp, _i32, _ip, _dp]),
+    "iak3d_cov_cross_ssre": (C.c_int, [_vp, C.POINTER(Pars), _i64, _dp, _dp, _ip, _dp, _dp]),
+    "iak3d_predict_stage_ssre": (C.c_int, [_vp, _i64, _dp, _dp, _dp, _ip, _dp]),
     "iak3d_factor_build_fetch": (C.c_int, [_vp, C.POINTER(Pars), _i32, _dp, _dp]),
     "iak3d_predict_panel_fetch": (C.c_int, [_vp, _i64, _dp, _i64, C.POINTER(_i64)]),
     "iak3d_cov_diag": (C.c_int, [_vp, C.POINTER(Pars), _dp]),
@@ -170,6 +175,14 @@ def make_pars(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cme
                 raise ValueError(f"{k} must hold sdfdType = {types[i]} (<= {MAX_SPL}) spline coefficients")
             for e in range(types[i]):
                 P.sdfdSpl[i][e] = float(v[e])
+    cs = parsBTfmd.get("cssre") if hasattr(parsBTfmd, "get") else None
+    if cs is not None and np.size(cs) > 0:          # site-specific random effects (fitIAK3D.R:1413)
+        cs = np.asarray(cs, float).reshape(-1)
+        if cs.size > MAX_SSRE:
+            raise ValueError(f"at most {MAX_SSRE} site-specific random-effect terms")
+        P.nssre = cs.size
+        for e in range(cs.size):
+            P.cssre[e] = float(cs[e])
     return P
 
 

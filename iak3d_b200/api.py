@@ -172,7 +172,8 @@ def _sdfd_spline_bases(dI, sdfdTypes, sdfdKnots):
 class SetupMats:
     """`setupMats` of the reference as a device-resident dataset handle (iak3d_ds)."""
 
-    def __init__(self, xData, dIData, W=None, ctx=None, sdfdType_cd1=0, sdfdType_cxd0=0, sdfdType_cxd1=0, sdfdKnots=None):
+    def __init__(self, xData, dIData, W=None, ctx=None, sdfdType_cd1=0, sdfdType_cxd0=0, sdfdType_cxd1=0, sdfdKnots=None,
+                 siteIDData=None, XData=None, cols4ssre=None):
         self.ctx = ctx or default_context()
         self.xData = f64(np.asarray(xData, float).reshape(len(xData), -1))
         if self.xData.shape[1] != 2:
@@ -205,6 +206,17 @@ class SetupMats:
             for c, B in enumerate(self.XsdfdSplineU):
                 if B is not None:
                     self.ctx.check(self.ctx.lib.iak3d_dataset_set_sdfd_spline(self.h, c, B.shape[1], dptr(B)))
+        self.nssre, self.site_codes, self.cols4ssre = 0, None, None
+        if siteIDData is not None:                         # site-specific random effects (iaCovMatern.R:440-460)
+            X = np.asarray(XData, float).reshape(self.n, -1)
+            if not np.all(X[:, 0] == 1):
+                raise ValueError("Error - the lmer-type mixed-effects option (if siteIDData given) only works if first column of X is 1s!")
+            self.cols4ssre = [int(c) for c in cols4ssre]
+            self.site_codes = {}
+            sid = site_ids(siteIDData, self.site_codes)
+            Xs = f64(X[:, self.cols4ssre])
+            self.ctx.check(self.ctx.lib.iak3d_dataset_set_ssre(self.h, Xs.shape[1], iptr(sid), dptr(Xs)))
+            self.nssre = Xs.shape[1]
 
     def set_W(self, W):
         W = f64(W)
@@ -238,22 +250,43 @@ class SetupMats:
             pass
 
 
-def setupIAK3D(xData, dIData, ctx=None, sdfdType_cd1=0, sdfdType_cxd0=0, sdfdType_cxd1=0, sdfdKnots=None, **_ignored):
+def site_ids(labels, codes):
+    """Site labels (any hashable) -> int32 ids; `codes` (label -> id) is extended in place, so that the data and the map
+    supports of one fit share their numbering (equal ids = same site; predictIAK3D.R:15-18 compares the labels as characters)."""
+    out = np.empty(len(labels), np.int32)
+    for i, lab in enumerate(np.asarray(labels).tolist()):
+        key = str(lab)
+        if key not in codes:
+            codes[key] = len(codes)
+        out[i] = codes[key]
+    return out
+
+
+def setupIAK3D(xData, dIData, ctx=None, sdfdType_cd1=0, sdfdType_cxd0=0, sdfdType_cxd1=0, sdfdKnots=None, siteIDData=None, XData=None,
+               colnames4ssre=None, **_ignored):
+    """iaCovMatern.R:413-548.  colnames4ssre: 0-based columns of XData (the reference's names) of the site-specific random effects."""
     return SetupMats(xData, dIData, ctx=ctx, sdfdType_cd1=sdfdType_cd1, sdfdType_cxd0=sdfdType_cxd0, sdfdType_cxd1=sdfdType_cxd1,
-                     sdfdKnots=sdfdKnots)
+                     sdfdKnots=sdfdKnots, siteIDData=siteIDData, XData=XData, cols4ssre=colnames4ssre)
 
 
 class SetupMats2:
     """setupIAK3D2: set 1 (rows of the result) stays on the host, set 2 is a resident dataset."""
 
     def __init__(self, xData, dIData, xData2, dIData2, ctx=None, setup2=None, sdfdType_cd1=0, sdfdType_cxd0=0, sdfdType_cxd1=0,
-                 sdfdKnots=None):
+                 sdfdKnots=None, siteIDData=None, XData=None, siteIDData2=None, XData2=None, cols4ssre=None):
         self.x1 = f64(np.asarray(xData, float).reshape(len(xData), -1))
         self.d1 = f64(np.asarray(dIData, float).reshape(-1, 2))
         types = (sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1)
         self.set2 = setup2 if setup2 is not None else SetupMats(xData2, dIData2, ctx=ctx, sdfdType_cd1=sdfdType_cd1,
                                                                 sdfdType_cxd0=sdfdType_cxd0, sdfdType_cxd1=sdfdType_cxd1,
-                                                                sdfdKnots=sdfdKnots)
+                                                                sdfdKnots=sdfdKnots, siteIDData=siteIDData2, XData=XData2,
+                                                                cols4ssre=cols4ssre)
+        self.sid1 = self.Xs1 = None
+        if siteIDData is not None:           # iaCovMatern.R:645-663: both sets carry site ids, or neither
+            if self.set2.nssre == 0:
+                raise ValueError("Error - for setupIAK3D2 define both or neither of siteIDData and siteIDData2!")
+            self.sid1 = site_ids(siteIDData, self.set2.site_codes)
+            self.Xs1 = f64(np.asarray(XData, float).reshape(self.x1.shape[0], -1)[:, self.set2.cols4ssre])
         if setup2 is not None and sdfdKnots is None:
             sdfdKnots, types = setup2.sdfdKnots, setup2.sdfdTypes
         # spline basis on the rows of set 1 (XsdfdSplineU_* expanded by Kd, iaCovMatern.R:627-645)
@@ -261,10 +294,11 @@ class SetupMats2:
 
 
 def setupIAK3D2(xData, dIData, xData2, dIData2, ctx=None, sdfdType_cd1=0, sdfdType_cxd0=0, sdfdType_cxd1=0, sdfdKnots=None,
-                setup2=None, **_ignored):
+                setup2=None, siteIDData=None, XData=None, siteIDData2=None, XData2=None, colnames4ssre=None, **_ignored):
     """`setup2`: an existing SetupMats of set 2 (then xData2 / dIData2 are not re-uploaded)."""
     return SetupMats2(xData, dIData, xData2, dIData2, ctx=ctx, setup2=setup2, sdfdType_cd1=sdfdType_cd1, sdfdType_cxd0=sdfdType_cxd0,
-                      sdfdType_cxd1=sdfdType_cxd1, sdfdKnots=sdfdKnots)
+                      sdfdType_cxd1=sdfdType_cxd1, sdfdKnots=sdfdKnots, siteIDData=siteIDData, XData=XData, siteIDData2=siteIDData2,
+                      XData2=XData2, cols4ssre=colnames4ssre)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -303,7 +337,12 @@ def setCIAK3D2(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cm
     n1, n2 = sm.x1.shape[0], sm.set2.n
     out = np.empty((n1, n2), order="F")
     ctx = sm.set2.ctx
-    if max(sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1) > 0:     # setCApproxIAK3D2, fitIAK3D.R:1121-1124
+    if sm.set2.nssre > 0:                                      # site-specific random effects, fitIAK3D.R:1233-1240
+        if getattr(sm, "sid1", None) is None:
+            raise ValueError("Error - for setupIAK3D2 define both or neither of siteIDData and siteIDData2!")
+        st = ctx.check(ctx.lib.iak3d_cov_cross_ssre(sm.set2.h, C.byref(P), n1, dptr(sm.x1), dptr(sm.d1), iptr(sm.sid1), dptr(sm.Xs1),
+                                                    dptr(out)), allow=(BAD_PARS,))
+    elif max(sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1) > 0:     # setCApproxIAK3D2, fitIAK3D.R:1121-1124
         st = ctx.check(ctx.lib.iak3d_cov_cross_spl(sm.set2.h, C.byref(P), n1, dptr(sm.x1), dptr(sm.d1), spl_ptrs(sm.Xspl1),
                                                    dptr(out)), allow=(BAD_PARS,))
     else:
@@ -674,6 +713,8 @@ def nllIAK3D(pars, zData, XData, vXU=None, iU=None, modelx="matern", nud=0.5, sd
         parsBTfmd[k] = cxdhat * parsBTfmd[k]
     if cmeOpt == 1:
         parsBTfmd["cme"] = cxdhat * parsBTfmd["cme"]
+    if parsBTfmd.get("cssre") is not None:                         # :863
+        parsBTfmd["cssre"] = cxdhat * np.asarray(parsBTfmd["cssre"], float)
     vbetahat = cxdhat * np.linalg.inv(WiAW[:p, :p])                # :870
     s2 = setCIAK3D(unscaled, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, sm, rtnC=False)["sigma2Vec"]
     out = dict(nll=t["nll"], pars=pars, parsBTfmd=parsBTfmd, betahat=betahat, vbetahat=vbetahat, cxdhat=cxdhat,
@@ -732,7 +773,7 @@ def gradnllIAK3D(pars, zData, XData, vXU=None, iU=None, modelx="matern", nud=0.5
         pb = readParsIAK3D(v, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds)
         structs.append(make_pars(pb, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt))
     if analytic == "auto":            # measured on B200: the pass pays from n ~ 4000 on (1.7x at 5000, 2.8x at 20000)
-        analytic = n >= 4000
+        analytic = n >= 4000 and getattr(sm, "nssre", 0) == 0      # site-specific random effects: forward differences
     if analytic:
         parr = (Pars * len(cand))(*structs)
         dl = f64(np.full(npar, float(delta)))
@@ -1118,14 +1159,22 @@ class KeptFit:
         self.ctx.check(self.ctx.lib.iak3d_fit_get(self.h, None, None, dptr(Cm), dptr(iC)))
         return Cm, iC
 
-    def predict(self, xMap, dIMap, XMap):
-        self.stage(xMap, dIMap, XMap)
+    def predict(self, xMap, dIMap, XMap, siteIDMap=None):
+        self.stage(xMap, dIMap, XMap, siteIDMap)
         self.enqueue()
         return self.fetch()
 
-    def stage(self, xMap, dIMap, XMap):
+    def stage(self, xMap, dIMap, XMap, siteIDMap=None):
         xMap = f64(np.asarray(xMap, float).reshape(-1, 2)); dIMap = f64(np.asarray(dIMap, float).reshape(-1, 2))
         XMap = f64(np.asarray(XMap, float).reshape(xMap.shape[0], self.p))
+        if self.sm.nssre > 0:                # site-specific random effects (predictIAK3D.R:9-18, 166-195)
+            if siteIDMap is None:
+                raise ValueError("Error - lmmFit was fitted with site-specific random effects (ie siteIDData given), but siteIDMap was null in the predict function!")
+            sid = site_ids(siteIDMap, self.sm.site_codes)
+            Xs = f64(XMap[:, self.sm.cols4ssre])
+            self.ctx.check(self.ctx.lib.iak3d_predict_stage_ssre(self.h, xMap.shape[0], dptr(xMap), dptr(dIMap), dptr(XMap), iptr(sid), dptr(Xs)))
+            self._m = xMap.shape[0]
+            return
         if max(self.sm.sdfdTypes) > 0:       # spline sd functions: basis on the map supports (setCApproxIAK3D2)
             spl = _sdfd_spline_bases(dIMap, self.sm.sdfdTypes, self.sm.sdfdKnots)
             self.ctx.check(self.ctx.lib.iak3d_predict_stage_spl(self.h, xMap.shape[0], dptr(xMap), dptr(dIMap), dptr(XMap), spl_ptrs(spl)))
@@ -1190,7 +1239,7 @@ class KeptFit:
             pass
 
 
-def predictIAK3D(xMap, dIMap, XMap_fn, lmmFit, nxPerBatch=2000, cells=None, vXUMap_fn=None, rqrBTfmdPreds=True):
+def predictIAK3D(xMap, dIMap, XMap_fn, lmmFit, nxPerBatch=2000, cells=None, vXUMap_fn=None, rqrBTfmdPreds=True, siteIDMap=None):
     """predictIAK3D.R:5-287 for compLikOptn = 0.  `lmmFit` is the rtnAll/attachBigMats dict of :func:`nllIAK3D`;
     `XMap_fn(iDepth, cellIdx)` supplies the design rows (makeXvX is an input of the hot path) and, for lognormal data,
     `vXUMap_fn(iDepth, cellIdx)` their within-support covariances ((m pU) x pU).  Rows of XMap containing NaN are skipped
@@ -1210,7 +1259,7 @@ def predictIAK3D(xMap, dIMap, XMap_fn, lmmFit, nxPerBatch=2000, cells=None, vXUM
             continue
         sel = idx_all[ok]
         dI = np.repeat(dIMap[i:i + 1], sel.size, axis=0)                # :150
-        z, v = fit.predict(xMap[sel], dI, XM[ok])
+        z, v = fit.predict(xMap[sel], dI, XM[ok], None if siteIDMap is None else np.asarray(siteIDMap)[sel])
         if lnN:                                                         # :229-255
             t = fit.fetch_terms()
             iU = lmmFit["iU"]

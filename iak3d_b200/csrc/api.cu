@@ -80,6 +80,9 @@ int iak_make_plan(iak3d_ctx* ctx, const iak3d_pars* p, bool square, EvalPlan* pl
   const bool nugget = (p->modelx == IAK3D_MODELX_NUGGET);
   pl->cx0 = p->cx0; pl->cx1 = nugget ? 0.0 : p->cx1; pl->cd1 = p->cd1; pl->cxd0 = p->cxd0; pl->cxd1 = nugget ? 0.0 : p->cxd1;
   pl->cme = p->cme;
+  if (p->nssre < 0 || p->nssre > IAK3D_MAX_SSRE) { ctx->err = "nssre out of range (0 .. IAK3D_MAX_SSRE)"; return IAK3D_ERR_ARG; }
+  pl->nssre = p->nssre;
+  for (int k = 0; k < p->nssre; k++) { pl->cssre[k] = p->cssre[k]; if (!isfinite(p->cssre[k])) { pl->status = IAK3D_BAD_PARS; return 0; } }
   // NA / Inf guards of nllIAK3D (fitIAK3D.R:718-741)
   const double vs[6] = {pl->cx0, pl->cx1, pl->cd1, pl->cxd0, pl->cxd1, pl->cme};
   for (double v : vs) if (!isfinite(v)) { pl->status = IAK3D_BAD_PARS; return 0; }
@@ -391,6 +394,7 @@ extern "C" int iak3d_dataset_destroy(iak3d_ds* ds) {
   for (Slot* s : ds->tslots) free_slot(s);
   cudaFree(ds->d_gradU); cudaFree(ds->d_gradiC);
   cudaFree(ds->d_xid); cudaFree(ds->d_did); cudaFree(ds->d_xU); cudaFree(ds->d_dIU); cudaFree(ds->d_W);
+  cudaFree(ds->d_sid); cudaFree(ds->d_Xs);
   if (ds->h_W) cudaFreeHost(ds->h_W);
   delete ds;
   return IAK3D_OK;
@@ -530,7 +534,30 @@ int iak_square_tables(iak3d_ctx* ctx, const iak3d_ds* ds, const EvalPlan& pl, Sl
   a->cx0 = pl.cx0; a->cx1 = pl.cx1; a->kd1 = pl.kd1; a->cxd0 = pl.cxd0; a->cxd1 = pl.cxd1; a->cme = pl.cme;
   a->xid_r = ds->d_xid; a->did_r = ds->d_did; a->xid_c = ds->d_xid; a->did_c = ds->d_did;
   a->nr = ds->n; a->nc = ds->n; a->nxU_r = nx; a->ndIU_r = nd;
+  a->nssre = 0;
+  if (pl.nssre > 0) {      // site-specific random effects (fitIAK3D.R:1091-1101)
+    if (ds->nssre != pl.nssre || !ds->d_sid) { ctx->err = "site-specific random effects: pars->nssre does not match iak3d_dataset_set_ssre"; return IAK3D_ERR_ARG; }
+    a->nssre = pl.nssre;
+    for (int k = 0; k < pl.nssre; k++) a->cssre[k] = pl.cssre[k];
+    a->sid_r = a->sid_c = ds->d_sid; a->Xs_r = a->Xs_c = ds->d_Xs; a->ldXs_r = a->ldXs_c = ds->n;
+  }
   return 0;
+}
+
+extern "C" int iak3d_dataset_set_ssre(iak3d_ds* ds, int32_t nssre, const int32_t* siteid, const double* Xs) {
+  if (!ds || nssre < 0 || nssre > IAK3D_MAX_SSRE || (nssre > 0 && (!siteid || !Xs))) return IAK3D_ERR_ARG;
+  iak3d_ctx* ctx = ds->ctx;
+  cudaSetDevice(ctx->device);
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(ds->d_sid); cudaFree(ds->d_Xs); ds->d_sid = nullptr; ds->d_Xs = nullptr; ds->nssre = 0;
+  if (nssre == 0) return IAK3D_OK;
+  CUDA_TRY(ctx, cudaMalloc(&ds->d_sid, (size_t)ds->n * 4));
+  CUDA_TRY(ctx, cudaMalloc(&ds->d_Xs, (size_t)ds->n * nssre * 8));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ds->d_sid, siteid, (size_t)ds->n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ds->d_Xs, Xs, (size_t)ds->n * nssre * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ds->nssre = nssre;
+  return IAK3D_OK;
 }
 
 // sigma2Vec - diag(C) of one evaluation into s->d_lncol[0..n)
@@ -541,6 +568,7 @@ int iak_lnN_column(iak3d_ctx* ctx, const iak3d_ds* ds, const EvalPlan& pl, const
   if (st != 0) return st;
   st = launch_ckk(ctx, pl, a.T, ds->ndIU, ds->d_did, n, s->d_lncol + n);
   if (st != 0) return st;
+  if (pl.nssre > 0) { ctx->err = "lognormal data with site-specific random effects: sigma2Vec is undefined (fitIAK3D.R:1092)"; return IAK3D_ERR_ARG; }
   return launch_vec_sub(ctx, s->d_lncol, s->d_lncol + n, n, s->d_lncol);
 }
 
@@ -643,6 +671,10 @@ extern "C" int iak3d_cov_build(iak3d_ds* ds, const iak3d_pars* pars, double* C, 
       rc = launch_sigma2(ctx, pl, a.av, ds->d_did, n, ds2);
       if (rc != 0) break;
       cudaMemcpyAsync(sigma2Vec, ds2, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+      if (pl.nssre > 0) {       // "sigma2Vec <- NA * sigma2Vec # just to remind that this shouldn't be used with ssre" (fitIAK3D.R:1092)
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "cov_build: copy failed"; rc = IAK3D_ERR_CUDA; break; }
+        for (int64_t i = 0; i < n; i++) sigma2Vec[i] = nan("");
+      }
     }
     const cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { ctx->err = std::string("cov_build: ") + cudaGetErrorString(e); rc = IAK3D_ERR_CUDA; }
@@ -715,6 +747,8 @@ extern "C" int iak3d_cov_diag(iak3d_ds* ds, const iak3d_pars* pars, double* diag
   const int64_t n = ds->n;
   if (s->d_lncol == nullptr) CUDA_TRY(ctx, cudaMalloc(&s->d_lncol, (size_t)2 * n * sizeof(double)));
   st = launch_ckk(ctx, pl, a.T, ds->ndIU, ds->d_did, n, s->d_lncol + n);
+  if (st != 0) return st;
+  st = launch_ssre_diag(ctx, a.nssre, a.cssre, a.Xs_r, a.ldXs_r, n, s->d_lncol + n);
   if (st != 0) return st;
   CUDA_TRY(ctx, cudaMemcpyAsync(diagC, s->d_lncol + n, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -823,8 +857,19 @@ int iak_cross_tables(iak3d_ctx* ctx, const iak3d_ds* ds2, const EvalPlan& pl, in
   return 0;
 }
 
+static int cov_cross_impl(iak3d_ds* ds2, const iak3d_pars* pars, int64_t n1, const double* xy1, const double* dI1,
+                          const double* const* Xspl1, const int32_t* siteid1, const double* Xs1, double* out);
 extern "C" int iak3d_cov_cross_spl(iak3d_ds* ds2, const iak3d_pars* pars, int64_t n1, const double* xy1, const double* dI1,
                                    const double* const* Xspl1, double* out) {
+  return cov_cross_impl(ds2, pars, n1, xy1, dI1, Xspl1, nullptr, nullptr, out);
+}
+extern "C" int iak3d_cov_cross_ssre(iak3d_ds* ds2, const iak3d_pars* pars, int64_t n1, const double* xy1, const double* dI1,
+                                    const int32_t* siteid1, const double* Xs1, double* out) {
+  if (pars && pars->nssre > 0 && (!siteid1 || !Xs1)) return IAK3D_ERR_ARG;
+  return cov_cross_impl(ds2, pars, n1, xy1, dI1, nullptr, siteid1, Xs1, out);
+}
+static int cov_cross_impl(iak3d_ds* ds2, const iak3d_pars* pars, int64_t n1, const double* xy1, const double* dI1,
+                          const double* const* Xspl1, const int32_t* siteid1, const double* Xs1, double* out) {
   if (!ds2 || !pars || n1 < 0 || (n1 > 0 && (!xy1 || !dI1 || !out))) return IAK3D_ERR_ARG;
   iak3d_ctx* ctx = ds2->ctx;
   cudaSetDevice(ctx->device);
@@ -840,10 +885,19 @@ extern "C" int iak3d_cov_cross_spl(iak3d_ds* ds2, const iak3d_pars* pars, int64_
   for (int c = 0; c < 3; c++)
     if (pars->sdfdType[c] > 0 && Xspl1 && Xspl1[c]) iak_spl_unique_rows(Xspl1[c], n1, pars->sdfdType[c] + 1, did1, (int64_t)dIU1.size() / 2, spl1U[c]);
   CrossBufs b; CovArgs a;
-  double* dout = nullptr;
+  double* dout = nullptr; int32_t* d_sid1 = nullptr; double* d_Xs1 = nullptr;
   int rc = iak_cross_tables(ctx, ds2, pl, n1, xid1, xU1, did1, dIU1, spl1U, &b, &a);
   do {
     if (rc != 0) break;
+    if (pl.nssre > 0) {       // setCIAK3D2 with siteIDData / siteIDData2 (fitIAK3D.R:1233-1240)
+      if (!siteid1 || !Xs1 || ds2->nssre != pl.nssre) { ctx->err = "cov_cross: site ids / columns of set 1 (iak3d_cov_cross_ssre) and iak3d_dataset_set_ssre are needed"; rc = IAK3D_ERR_ARG; break; }
+      if (cudaMalloc(&d_sid1, (size_t)n1 * 4) != cudaSuccess || cudaMalloc(&d_Xs1, (size_t)n1 * pl.nssre * 8) != cudaSuccess) { ctx->err = "cov_cross: allocation failed"; rc = IAK3D_ERR_CUDA; cudaGetLastError(); break; }
+      cudaMemcpyAsync(d_sid1, siteid1, (size_t)n1 * 4, cudaMemcpyHostToDevice, ctx->stream);
+      cudaMemcpyAsync(d_Xs1, Xs1, (size_t)n1 * pl.nssre * 8, cudaMemcpyHostToDevice, ctx->stream);
+      a.nssre = pl.nssre;
+      for (int k = 0; k < pl.nssre; k++) a.cssre[k] = pl.cssre[k];
+      a.sid_r = d_sid1; a.Xs_r = d_Xs1; a.ldXs_r = n1; a.sid_c = ds2->d_sid; a.Xs_c = ds2->d_Xs; a.ldXs_c = ds2->n;
+    }
     if (cudaMalloc(&dout, (size_t)n1 * ds2->n * 8) != cudaSuccess) { ctx->err = "cov_cross: allocation failed"; rc = IAK3D_ERR_CUDA; cudaGetLastError(); break; }
     rc = launch_cov_rect(ctx, a, dout, n1, n1, ds2->n, 0);
     if (rc != 0) break;
@@ -852,7 +906,7 @@ extern "C" int iak3d_cov_cross_spl(iak3d_ds* ds2, const iak3d_pars* pars, int64_
     if (e != cudaSuccess) { ctx->err = std::string("cov_cross: ") + cudaGetErrorString(e); rc = IAK3D_ERR_CUDA; }
   } while (0);
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(dout);
+  cudaFree(dout); cudaFree(d_sid1); cudaFree(d_Xs1);
   iak_cross_free(&b);
   return rc;
 }

@@ -55,6 +55,7 @@ struct iak3d_fit {
   double* d_xy = nullptr;        // per chunk: rows x 2 column-major blocks
   double* d_X = nullptr;         // m x p column-major
   int32_t* d_did1 = nullptr;     // m
+  int32_t* d_sidMap = nullptr; double* d_XsMap = nullptr; int64_t ssre_cap = 0; bool ssre_staged = false;   // site ids / ssre columns of the map supports
   double* d_dIU1 = nullptr;      // nd1 x 2
   std::vector<double> h_dIU1;    // host copy
   std::vector<double> spl1U[3];  // spline sd basis of the map supports' unique intervals (nd1 x ncol), setCApproxIAK3D2
@@ -85,6 +86,7 @@ struct iak3d_fit {
 static void fit_free_job(iak3d_fit* f) {
   cudaFree(f->d_xy); cudaFree(f->d_X); cudaFree(f->d_did1); cudaFree(f->d_dIU1); cudaFree(f->d_z); cudaFree(f->d_v); cudaFree(f->d_ckk);
   cudaFree(f->d_cz); cudaFree(f->d_qf); cudaFree(f->d_s2k); cudaFree(f->d_cx); f->d_cx = nullptr; f->cx_cap = 0;
+  cudaFree(f->d_sidMap); cudaFree(f->d_XsMap); f->d_sidMap = nullptr; f->d_XsMap = nullptr; f->ssre_cap = 0; f->ssre_staged = false;
   f->d_xy = f->d_X = f->d_dIU1 = f->d_z = f->d_v = f->d_ckk = f->d_cz = f->d_qf = f->d_s2k = nullptr; f->d_did1 = nullptr; f->cap_m = 0;
 }
 static void fit_free_panel(iak3d_fit* f) {
@@ -289,12 +291,35 @@ extern "C" int iak3d_predict_stage(iak3d_fit* f, int64_t m, const double* xyMap,
   return iak3d_predict_stage_spl(f, m, xyMap, dIMap, XMap, nullptr);
 }
 
+extern "C" int iak3d_predict_stage_ssre(iak3d_fit* f, int64_t m, const double* xyMap, const double* dIMap, const double* XMap,
+                                        const int32_t* siteidMap, const double* XsMap) {
+  if (!f) return IAK3D_ERR_ARG;
+  const int ns = f->plan_sq.nssre;
+  if (ns > 0 && m > 0 && (!siteidMap || !XsMap)) { f->ctx->err = "predict_stage_ssre: the fit has site-specific random effects: siteidMap and XsMap are needed"; return IAK3D_ERR_ARG; }
+  int rc = iak3d_predict_stage_spl(f, m, xyMap, dIMap, XMap, nullptr);
+  if (rc != 0 || ns == 0 || m == 0) return rc;
+  iak3d_ctx* ctx = f->ctx;
+  f->staged = false;
+  if (m > f->ssre_cap) {
+    cudaFree(f->d_sidMap); cudaFree(f->d_XsMap); f->d_sidMap = nullptr; f->d_XsMap = nullptr; f->ssre_cap = 0;
+    CUDA_TRY(ctx, cudaMalloc(&f->d_sidMap, (size_t)m * 4));
+    CUDA_TRY(ctx, cudaMalloc(&f->d_XsMap, (size_t)m * IAK3D_MAX_SSRE * 8));
+    f->ssre_cap = m;
+  }
+  CUDA_TRY(ctx, cudaMemcpyAsync(f->d_sidMap, siteidMap, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(f->d_XsMap, XsMap, (size_t)m * ns * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  f->ssre_staged = true;
+  f->staged = true;
+  return IAK3D_OK;
+}
+
 extern "C" int iak3d_predict_stage_spl(iak3d_fit* f, int64_t m, const double* xyMap, const double* dIMap, const double* XMap,
                                        const double* const* Xspl1) {
   if (!f || m < 0 || (m > 0 && (!xyMap || !dIMap || !XMap))) return IAK3D_ERR_ARG;
   iak3d_ctx* ctx = f->ctx;
   cudaSetDevice(ctx->device);
-  f->staged = false; f->enqueued = false;
+  f->staged = false; f->enqueued = false; f->ssre_staged = false;
   f->m = m;
   if (m == 0) { f->staged = true; return IAK3D_OK; }
   const int p = f->p;
@@ -435,12 +460,20 @@ static int fit_prepare_job(iak3d_fit* f, CovArgs* ap) {
   }
   rc = launch_ckk(ctx, ps, Tself, nd1, f->d_did1, m, f->d_ckk);
   if (rc != 0) return rc;
+  if (ps.nssre > 0) {     // Ckk = diag(setCIAK3D(map supports)) with their own site structures (predictIAK3D.R:179-189)
+    if (!f->ssre_staged) { ctx->err = "kriging: the fit has site-specific random effects: stage with iak3d_predict_stage_ssre"; return IAK3D_ERR_ARG; }
+    rc = launch_ssre_diag(ctx, ps.nssre, ps.cssre, f->d_XsMap, m, m, f->d_ckk);
+    if (rc != 0) return rc;
+  }
   rc = launch_sigma2(ctx, ps, avself, f->d_did1, m, f->d_s2k);
   if (rc != 0) return rc;
   for (int c = 0; c < 3; c++) a.tidx[c] = px.tidx[c];
   a.ntab = px.ntab;
   a.cx0 = px.cx0; a.cx1 = px.cx1; a.kd1 = px.kd1; a.cxd0 = px.cxd0; a.cxd1 = px.cxd1; a.cme = 0.0;
   a.xid_c = ds->d_xid; a.did_c = ds->d_did; a.nc = ds->n; a.ndIU_r = nd1;
+  a.nssre = px.nssre;
+  for (int k = 0; k < px.nssre; k++) a.cssre[k] = px.cssre[k];
+  a.sid_c = ds->d_sid; a.Xs_c = ds->d_Xs; a.ldXs_c = ds->n;
   return 0;
 }
 
@@ -455,6 +488,7 @@ static int fit_build_panel(iak3d_fit* f, CovArgs& a, int64_t r0, int64_t rows, i
   a.phix = px.has_phix ? f->d_phix : nullptr;
   a.same = f->d_same;
   a.xid_r = f->d_iota; a.did_r = f->d_did1 + r0; a.nr = rows; a.nxU_r = rows;
+  if (a.nssre > 0) { a.sid_r = f->d_sidMap + r0; a.Xs_r = f->d_XsMap + r0; a.ldXs_r = f->m; }
   return launch_cov_panel(ctx, a, f->d_P, rowsP, f->slot->Npad);
 }
 

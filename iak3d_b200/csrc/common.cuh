@@ -86,6 +86,8 @@ struct iak3d_ds {
   std::vector<double> h_spl[3];          // XsdfdSplineU_{cd1,cxd0,cxd1}: ndIU x spl_ncol[c] column-major (iaCovMatern.R:520-539)
   int32_t spl_ncol[3] = {0, 0, 0};
   int32_t lncol = -1;                    // column of W replaced by sigma2Vec - diag(C) at every evaluation (lognormal data)
+  int32_t nssre = 0;                     // site-specific random effects: columns of d_Xs, site id of every row
+  int32_t* d_sid = nullptr; double* d_Xs = nullptr;
   double* h_W = nullptr;                 // n x q column-major copy in PINNED host memory: staging of the H2D copy
   int32_t *d_xid = nullptr, *d_did = nullptr;
   double *d_xU = nullptr, *d_dIU = nullptr;   // column-major nxU x 2 / ndIU x 2
@@ -114,6 +116,7 @@ struct EvalPlan {
   int sd_comp[3] = {0, 0, 0};            // component (0 cd1, 1 cxd0, 2 cxd1) whose spline basis applies
   double sd_coef[3][IAK3D_MAX_SPL] = {}; // (tau1, tau2) or the spline coefficients
   double cx0 = 0, cx1 = 0, cd1 = 0, kd1 = 0, cxd0 = 0, cxd1 = 0, cme = 0;
+  int nssre = 0; double cssre[IAK3D_MAX_SSRE] = {};
 };
 
 #define CUDA_TRY(ctx, expr)                                                                   \
@@ -160,6 +163,13 @@ struct CovArgs {
   const int32_t *xid_r, *did_r, *xid_c, *did_c;   // row ids / col ids
   int64_t nr, nc;          // live rows / cols
   int64_t nxU_r, ndIU_r;   // leading dims of tables (row-id extent)
+  // site-specific random effects (listStructs4ssre, iaCovMatern.R:440-460, 645-663; added at fitIAK3D.R:1091-1101, 1233-1240):
+  //   value(i, j) += [site_r(i) == site_c(j)] * sum_k cssre[k] Xs_r(i, k) Xs_c(j, k)
+  int nssre = 0;
+  double cssre[IAK3D_MAX_SSRE] = {};
+  const int32_t *sid_r = nullptr, *sid_c = nullptr;
+  const double *Xs_r = nullptr, *Xs_c = nullptr;   // column-major, leading dimensions ldXs_r / ldXs_c
+  int64_t ldXs_r = 0, ldXs_c = 0;
 };
 // one covariance build into a factor buffer; a batch of them is ONE launch (launch_cov_factor_jobs)
 struct FactorBuildJob {
@@ -192,6 +202,8 @@ int launch_cov_rect(iak3d_ctx* ctx, const CovArgs& a, double* d_out, int64_t ld,
 // launch_cov_rect when the row count is odd
 int launch_cov_panel(iak3d_ctx* ctx, const CovArgs& a, double* d_out, int64_t rows_total, int64_t cols_total);
 
+// diag[i] += sum_k cssre[k] Xs(i, k)^2  (the ssre part of a diagonal: Ckk of map supports, diag(C))
+int launch_ssre_diag(iak3d_ctx* ctx, int nssre, const double* cssre, const double* d_Xs, int64_t ldXs, int64_t m, double* d_diag);
 int launch_unblock_rect(iak3d_ctx* ctx, const double* d_B, int64_t nRU, int64_t r0, int64_t nr, int64_t nc, int mirror, double* d_out,
                         int64_t ld);
 

@@ -285,6 +285,65 @@ static void covdev_from(const CovArgs& h, CovDev* a) {
   a->comb = h.comb; a->E = nullptr; a->ldE = 0; a->one_table = 0;
 }
 
+// ---- site-specific random effects: post-pass over a finished build (CovArgs.nssre > 0) ----------------------------------
+struct SsreDev {
+  int nssre; double c[IAK3D_MAX_SSRE];
+  const int32_t *sid_r, *sid_c; const double *Xr, *Xc; int64_t ldr, ldc;
+};
+static SsreDev ssre_from(const CovArgs& h) {
+  SsreDev s;
+  s.nssre = h.nssre;
+  for (int k = 0; k < IAK3D_MAX_SSRE; k++) s.c[k] = h.cssre[k];
+  s.sid_r = h.sid_r; s.sid_c = h.sid_c; s.Xr = h.Xs_r; s.Xc = h.Xs_c; s.ldr = h.ldXs_r; s.ldc = h.ldXs_c;
+  return s;
+}
+// out(i, j) += [sid_r(i) == sid_c(j)] sum_k c_k Xr(i,k) Xc(j,k) for i < nr, j < nc (lower != 0: i >= j only); blocked (uidx with nRU)
+// or column-major with leading dimension ld.  The terms are added one by one like the reference's loop over ip (:1096-1099).
+__global__ void __launch_bounds__(256) ssre_add_kernel(SsreDev s, double* __restrict__ out, int64_t nr, int64_t nc, int lower, int blocked,
+                                                       int64_t nRU, int64_t ld) {
+  const int64_t j = blockIdx.y;
+  if (j >= nc) return;
+  const int32_t sj = s.sid_c[j];
+  double xc[IAK3D_MAX_SSRE];
+  for (int k = 0; k < s.nssre; k++) xc[k] = s.Xc[(int64_t)k * s.ldc + j];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nr; i += (int64_t)gridDim.x * blockDim.x) {
+    if (lower && i < j) continue;
+    if (s.sid_r[i] != sj) continue;
+    double* o = blocked ? out + uidx(i, j, nRU) : out + j * ld + i;
+    double v = *o;
+    for (int k = 0; k < s.nssre; k++) v = v + (s.Xr[(int64_t)k * s.ldr + i] * xc[k]) * s.c[k];
+    *o = v;
+  }
+}
+static int launch_ssre_add(iak3d_ctx* ctx, const CovArgs& h, double* d_out, int64_t nr, int64_t nc, int lower, int blocked, int64_t nRU, int64_t ld) {
+  if (h.nssre <= 0 || nr <= 0 || nc <= 0) return 0;
+  if (!h.sid_r || !h.sid_c || !h.Xs_r || !h.Xs_c) { ctx->err = "site-specific random effects: site ids / columns missing for one of the two sets"; return IAK3D_ERR_ARG; }
+  if (nc > 65535) { ctx->err = "ssre: more than 65535 columns"; return IAK3D_ERR_ARG; }
+  unsigned bx = (unsigned)((nr + 255) / 256);
+  if (bx > 64) bx = 64;
+  ssre_add_kernel<<<dim3(bx, (unsigned)nc), 256, 0, ctx->stream>>>(ssre_from(h), d_out, nr, nc, lower, blocked, nRU, ld);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return 0;
+}
+__global__ void ssre_diag_kernel(int nssre, SsreDev s, const double* __restrict__ Xs, int64_t ldXs, int64_t m, double* __restrict__ diag) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  double v = diag[i];
+  for (int k = 0; k < nssre; k++) { const double x = Xs[(int64_t)k * ldXs + i]; v = v + (x * x) * s.c[k]; }
+  diag[i] = v;
+}
+int launch_ssre_diag(iak3d_ctx* ctx, int nssre, const double* cssre, const double* d_Xs, int64_t ldXs, int64_t m, double* d_diag) {
+  if (nssre <= 0 || m <= 0) return 0;
+  SsreDev s; s.nssre = nssre;
+  for (int k = 0; k < IAK3D_MAX_SSRE; k++) s.c[k] = k < nssre ? cssre[k] : 0.0;
+  s.sid_r = s.sid_c = nullptr; s.Xr = s.Xc = nullptr; s.ldr = s.ldc = 0;
+  ssre_diag_kernel<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(nssre, s, d_Xs, ldXs, m, d_diag);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return 0;
+}
+
 int launch_cov_factor_jobs(iak3d_ctx* ctx, const FactorBuildJob* jobs, int count) {
   if (count <= 0) return 0;
   std::vector<FbJob> hj((size_t)count);
@@ -352,6 +411,11 @@ int launch_cov_factor_jobs(iak3d_ctx* ctx, const FactorBuildJob* jobs, int count
     if (z0 + 65535 < count) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // the job buffer is reused
   }
   CUDA_TRY(ctx, cudaGetLastError());
+  for (int i = 0; i < count; i++) {
+    const FactorBuildJob& b = jobs[i];
+    const int rc = launch_ssre_add(ctx, b.a, b.d_L, b.n, b.n, 1, 1, b.ld / UR, 0);
+    if (rc != 0) return rc;
+  }
   return 0;
 }
 
@@ -453,7 +517,7 @@ int launch_cov_panel(iak3d_ctx* ctx, const CovArgs& h, double* d_out, int64_t ro
   cov_panel_kernel<<<grid, 256, 0, ctx->stream>>>(a, d_out, rows_total, cols_total);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
-  return 0;
+  return launch_ssre_add(ctx, h, d_out, h.nr, h.nc, 0, 1, rows_total / UR, 0);
 }
 
 int launch_cov_rect(iak3d_ctx* ctx, const CovArgs& h, double* d_out, int64_t ld, int64_t rows_total, int64_t cols_total,
@@ -471,7 +535,7 @@ int launch_cov_rect(iak3d_ctx* ctx, const CovArgs& h, double* d_out, int64_t ld,
   cov_rect_kernel<<<grid, 256, 0, ctx->stream>>>(a, d_out, ld, rows_total, cols_total, symmetric_square, blocked);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
-  return 0;
+  return launch_ssre_add(ctx, h, d_out, h.nr, h.nc, 0, blocked, rows_total / UR, ld);
 }
 
 // ---- generic symmetric input (lndetANDinvCb called with a caller-built C, optim_functions.R:268) ------

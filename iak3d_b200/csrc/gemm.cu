@@ -304,6 +304,7 @@ extern "C" int iak3d_gradhess_shard(iak3d_ds* ds, const iak3d_pars* pars, int32_
   for (int i = 0; i < m; i++) var[i] = exp(lnvPars[i]);
   P.cx0 = var[0]; P.cx1 = var[1]; P.cd1 = var[2]; P.cxd0 = var[3]; P.cxd1 = var[4]; P.cme = var[5];
   P.quirk_cd1_unscaled = 0;
+  P.nssre = 0;                 // nrUpdatesIAK3D's components are the six terms of setCIAK3D (nrUpdatesIAK3D.R:130-138)
   EvalPlan pl;
   int rc = iak_make_plan(ctx, &P, true, &pl);
   if (rc == 0) rc = iak_plan_check_avsd(ctx, ds, &pl);

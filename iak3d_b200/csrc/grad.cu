@@ -166,6 +166,7 @@ extern "C" int iak3d_nll_grad(iak3d_ds* ds, int32_t npar, const iak3d_pars* pars
     int st = iak_make_plan(ctx, &pars[k], true, &plans[(size_t)k]);
     if (st == 0) st = iak_plan_check_avsd(ctx, ds, &plans[(size_t)k]);
     if (st != 0) return st;
+    if (plans[(size_t)k].nssre > 0) { ctx->err = "nll_grad: the analytic gradient does not cover site-specific random effects (use the forward-difference batch)"; return IAK3D_ERR_ARG; }
   }
   if (plans[0].status != 0) return plans[0].status;
   Slot* s0 = nullptr;

@@ -46,6 +46,8 @@ extern "C" {
 
 /* largest number of internal knots of a spline sd function (sdfdType > 0, fitIAK3D.R:1490-1495) */
 #define IAK3D_MAX_SPL 12
+/* largest number of site-specific random-effect terms (colnames4ssre, iaCovMatern.R:440-460) */
+#define IAK3D_MAX_SSRE 8
 
 /* parsBTfmd + the model switches that select terms (fitIAK3D.R:1405-1408, 955-956). */
 typedef struct iak3d_pars {
@@ -63,6 +65,9 @@ typedef struct iak3d_pars {
                               the kept C = cxdhat * A of a fit (fitIAK3D.R:871) */
   double sdfdSpl[3][IAK3D_MAX_SPL]; /* spline coefficients of a component with sdfdType k > 0 (the k free parameters;
                               iasdfd multiplies the basis by c(1, sdfdPars), fitIAK3D.R:1458) */
+  int32_t nssre;           /* site-specific random effects (parsBTfmd$cssre, fitIAK3D.R:1413): number of terms, 0 = none */
+  int32_t reserved_;
+  double cssre[IAK3D_MAX_SSRE]; /* their variances: C += cssre[k] * listStructs4ssre[[k]] (fitIAK3D.R:1091-1101, 1233-1240) */
 } iak3d_pars;
 
 typedef struct iak3d_ctx iak3d_ctx;   /* one per GPU: stream, workspaces, error text */
@@ -97,6 +102,14 @@ IAK3D_API int iak3d_dataset_set_sdfd_spline(iak3d_ds* ds, int32_t comp, int32_t 
  * lognormal mean, which changes with the covariance parameters.  col < 0 switches this off (default). */
 IAK3D_API int iak3d_dataset_set_lnN_column(iak3d_ds* ds, int32_t col);
 
+/* Site-specific random effects (the lmer-type option, siteIDData given: iaCovMatern.R:440-460).  listStructs4ssre[[k]] is
+ * block diagonal over sites with blocks X[site, cn_k] X[site, cn_k]'; it is never formed: the dataset keeps the site id of
+ * every row (int32, equal ids = same site; the caller maps its labels) and the nssre columns Xs = X[, colnames4ssre]
+ * (n x nssre column-major), and every covariance built from the dataset adds
+ *     [site(i) == site(j)] * sum_k pars->cssre[k] Xs(i, k) Xs(j, k).
+ * nssre = 0 clears.  sigma2Vec is not defined with ssre (the reference sets it to NA, fitIAK3D.R:1092): NaN. */
+IAK3D_API int iak3d_dataset_set_ssre(iak3d_ds* ds, int32_t nssre, const int32_t* siteid, const double* Xs);
+
 /* ---- depth / horizontal kernels on unique pairs ---------------------------------------------
  * iaCovMatern2 (iaCovMatern.R:107-191): out is n1 x n2 column-major; avVar (n1) may be NULL
  * (avVarVec of set 1, iaCovMatern.R:53-54).  sdfdType in {0,-1}. */
@@ -122,6 +135,11 @@ IAK3D_API int iak3d_cov_cross(iak3d_ds* ds2, const iak3d_pars* pars, int64_t n1,
  * NULL for a component whose sdfdType is not > 0. */
 IAK3D_API int iak3d_cov_cross_spl(iak3d_ds* ds2, const iak3d_pars* pars, int64_t n1, const double* xy1,
                         const double* dI1, const double* const* Xspl1, double* out);
+
+/* setCIAK3D2 with site-specific random effects (siteIDData / XData of set 1 and siteIDData2 / XData2 of the dataset,
+ * iaCovMatern.R:645-663; fitIAK3D.R:1233-1240): siteid1 (n1), Xs1 (n1 x nssre) describe the rows given here. */
+IAK3D_API int iak3d_cov_cross_ssre(iak3d_ds* ds2, const iak3d_pars* pars, int64_t n1, const double* xy1, const double* dI1,
+                                   const int32_t* siteid1, const double* Xs1, double* out);
 
 /* The matrix the likelihood actually factorises: setCIAK3D (fitIAK3D.R:955-1112) as the FACTOR BUILD forms it --
  * `cov_factor_kernel` into the blocked factor buffer, the kernel the covariance roofline is quoted on -- copied back as a
@@ -210,6 +228,10 @@ IAK3D_API int iak3d_predict_stage(iak3d_fit* fit, int64_t m, const double* xyMap
 /* with spline sd functions: Xspl1[c] = basis of component c on the m map supports (m x (sdfdType[c]+1)) or NULL */
 IAK3D_API int iak3d_predict_stage_spl(iak3d_fit* fit, int64_t m, const double* xyMap, const double* dIMap, const double* XMap,
                             const double* const* Xspl1);
+/* with site-specific random effects: site ids (m) and Xs = XMap[, colnames4ssre] (m x nssre) of the map supports
+ * (predictIAK3D.R:166-195: siteIDMapThis, XMapThis handed to setupIAK3D / setupIAK3D2) */
+IAK3D_API int iak3d_predict_stage_ssre(iak3d_fit* fit, int64_t m, const double* xyMap, const double* dIMap, const double* XMap,
+                             const int32_t* siteidMap, const double* XsMap);
 IAK3D_API int iak3d_predict_enqueue(iak3d_fit* fit);
 IAK3D_API int iak3d_predict_fetch(iak3d_fit* fit, double* z, double* v);
 /* the pieces z and v are made of (predictIAK3D.R:183-208), each m long, any may be NULL: Ckk = diag(setCIAK3D(map)),

@@ -495,8 +495,20 @@ def _spline_bases(dIU, sdfdTypes, sdfdKnots):
     return out
 
 
-def setupIAK3D(xData, dIData, sdfdTypes=(0, 0, 0), sdfdKnots=None):
-    """iaCovMatern.R:413-548.  Kx/Kd incidence matrices are represented by id vectors."""
+def _structs4ssre(siteIDData, XData, siteIDData2, XData2, cols4ssre):
+    """iaCovMatern.R:440-460 (square) / :645-663 (rectangular): one n1 x n2 structure per column of colnames4ssre, block-wise
+    X[site, cn] %*% t(X2[site, cn]) over the sites the two sets share.  Dense here (the reference's sparseMatrix)."""
+    s1 = np.asarray(siteIDData); s2 = np.asarray(siteIDData2)
+    X1 = np.asarray(XData, float); X2 = np.asarray(XData2, float)
+    if not (np.all(X1[:, 0] == 1) and np.all(X2[:, 0] == 1)):
+        raise ValueError("the lmer-type mixed-effects option only works if first column of X is 1s")
+    same = (s1[:, None] == s2[None, :])
+    return [np.where(same, np.outer(X1[:, c], X2[:, c]), 0.0) for c in cols4ssre]
+
+
+def setupIAK3D(xData, dIData, sdfdTypes=(0, 0, 0), sdfdKnots=None, siteIDData=None, XData=None, cols4ssre=None):
+    """iaCovMatern.R:413-548.  Kx/Kd incidence matrices are represented by id vectors.  cols4ssre: 0-based columns of
+    XData named by colnames4ssre (site-specific random effects, :440-460)."""
     xData = np.asarray(xData, float).reshape(len(xData), -1)
     dIData = np.asarray(dIData, float).reshape(-1, 2)
     xU, xid = _unique_first(xData)
@@ -505,10 +517,13 @@ def setupIAK3D(xData, dIData, sdfdTypes=(0, 0, 0), sdfdKnots=None):
               maxd=max(float(dIU.max()), 2.0), n=xData.shape[0], sdfdKnots=sdfdKnots)
     if max(sdfdTypes) > 0:
         sm["XsdfdSplineU"] = _spline_bases(dIU, sdfdTypes, sdfdKnots)
+    if siteIDData is not None:
+        sm["listStructs4ssre"] = _structs4ssre(siteIDData, XData, siteIDData, XData, cols4ssre)
     return sm
 
 
-def setupIAK3D2(xData, dIData, xData2, dIData2, sdfdTypes=(0, 0, 0), sdfdKnots=None):
+def setupIAK3D2(xData, dIData, xData2, dIData2, sdfdTypes=(0, 0, 0), sdfdKnots=None, siteIDData=None, XData=None,
+                siteIDData2=None, XData2=None, cols4ssre=None):
     """iaCovMatern.R:581-678."""
     xData = np.asarray(xData, float).reshape(len(xData), -1)
     xData2 = np.asarray(xData2, float).reshape(len(xData2), -1)
@@ -521,6 +536,10 @@ def setupIAK3D2(xData, dIData, xData2, dIData2, sdfdTypes=(0, 0, 0), sdfdKnots=N
     if max(sdfdTypes) > 0:
         sm["XsdfdSplineU"] = _spline_bases(dIU, sdfdTypes, sdfdKnots)
         sm["XsdfdSplineU2"] = _spline_bases(dIU2, sdfdTypes, sdfdKnots)
+    if (siteIDData is None) != (siteIDData2 is None):                  # :665-667
+        raise ValueError("for setupIAK3D2 define both or neither of siteIDData and siteIDData2")
+    if siteIDData is not None:
+        sm["listStructs4ssre"] = _structs4ssre(siteIDData, XData, siteIDData2, XData2, cols4ssre)
     return sm
 
 
@@ -591,8 +610,15 @@ def setCIAK3D(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cme
     av_cxd1 = cxd1[1] if cxd1 is not None else 0.0
     s2 = (p["cxd0"] * cxd0[1] + p["cxd1"] * av_cxd1 + p["cme"] + p["cx0"] + p["cx1"]
           + p["cd1"] * av_cd1)                                         # :1083
-    s2 = np.broadcast_to(s2, (setupMats["dIU"].shape[0],))[did]        # :1086
-    return C, np.array(s2)
+    s2 = np.array(np.broadcast_to(s2, (setupMats["dIU"].shape[0],))[did])   # :1086
+    if setupMats.get("listStructs4ssre") is not None:                  # :1091-1101
+        s2 = np.full_like(s2, np.nan)
+        cs = np.asarray(p["cssre"], float).reshape(-1)
+        if cs.size != len(setupMats["listStructs4ssre"]):
+            raise ValueError("parsBTfmd$cssre is the wrong length")
+        for ip, S in enumerate(setupMats["listStructs4ssre"]):
+            C = C + S * cs[ip]
+    return C, s2
 
 
 def setCIAK3D2(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, setupMats):
@@ -629,6 +655,10 @@ def setCIAK3D2(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cm
         K = phix1[xid[:, None], xid2[None, :]]
         C = C + p["cx1"] * K                                           # :1219
         C = C + p["cxd1"] * K * cxd1[0][dd]                            # :1222/1224
+    if setupMats.get("listStructs4ssre") is not None:                  # :1233-1240
+        cs = np.asarray(p["cssre"], float).reshape(-1)
+        for ip, S in enumerate(setupMats["listStructs4ssre"]):
+            C = C + S * cs[ip]
     return C
 
 
@@ -839,6 +869,8 @@ def nllIAK3D(pars, zData, XData, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdT
         parsBTfmd[k] = cxdhat * parsBTfmd[k]
     if cmeOpt == 1:
         parsBTfmd["cme"] = cxdhat * parsBTfmd["cme"]
+    if parsBTfmd.get("cssre") is not None:                              # :863
+        parsBTfmd["cssre"] = cxdhat * np.asarray(parsBTfmd["cssre"], float)
     vbetahat = cxdhat * np.linalg.inv(WiAW[:p, :p])                     # :870
     C = cxdhat * A
     muhat = XData @ betahat
@@ -1112,7 +1144,7 @@ def nllIAK3D_lnN(pars, zData, XData, vXU, iU, modelx, nud, sdfdType_cd1, sdfdTyp
 # kriging  (predictIAK3D.R:110-139, 179-208, 229-255, 272-284)
 # ---------------------------------------------------------------------------
 def predictIAK3D(xMap, dIMap, XMap_fn, lmmFit, modelx, sdfdTypes, cmeOpt, nxPerBatch=2000, vXUMap_fn=None,
-                 rqrBTfmdPreds=True):
+                 rqrBTfmdPreds=True, siteIDMap=None):
     """predictIAK3D.R:5-287 for compLikOptn = 0, lnTfmdData = FALSE.
 
     ``lmmFit`` = the ``rtnAll`` dict of :func:`nllIAK3D` plus xData, dIData.  ``XMap_fn(iDepth,
@@ -1131,6 +1163,20 @@ def predictIAK3D(xMap, dIMap, XMap_fn, lmmFit, modelx, sdfdTypes, cmeOpt, nxPerB
             dIThis = np.repeat(dIMap[i:i + 1], idx.size, axis=0)        # :150
             XMapThis = XMap_fn(i, idx)
             knots = lmmFit.get("sdfdKnots")
+            if lmmFit.get("siteIDData") is not None:                    # :9-18, 166-195: site-specific random effects
+                sidThis = np.asarray(siteIDMap)[idx]; c4 = lmmFit["cols4ssre"]
+                sm = setupIAK3D(xMap[idx], dIThis, sdfdTypes, knots, siteIDData=sidThis, XData=XMapThis, cols4ssre=c4)
+                Ck, s2k = setCIAK3D(P, modelx, *sdfdTypes, cmeOpt, sm)
+                Ckk = np.diag(Ck)
+                sm2 = setupIAK3D2(xMap[idx], dIThis, lmmFit["xData"], lmmFit["dIData"], sdfdTypes, knots, siteIDData=sidThis,
+                                  XData=XMapThis, siteIDData2=lmmFit["siteIDData"], XData2=lmmFit["XData"], cols4ssre=c4)
+                Ckh = setCIAK3D2(P, modelx, *sdfdTypes, cmeOpt, sm2)
+                CkhiCX = Ckh @ iCX; CkhiCz = Ckh @ iCz; CkhiC = Ckh @ iC
+                q = np.sum(CkhiC * Ckh, axis=1)
+                zMap[i, idx] = (XMapThis @ betahat + CkhiCz).ravel()
+                t = XMapThis - CkhiCX
+                vMap[i, idx] = Ckk - q + np.sum(t * (vbetahat @ t.T).T, axis=1)
+                continue
             sm = setupIAK3D(xMap[idx], dIThis, sdfdTypes, knots)        # :179
             Ck, s2k = setCIAK3D(P, modelx, *sdfdTypes, cmeOpt, sm)      # :183
             Ckk = np.diag(Ck)                                           # :189

@@ -8,8 +8,7 @@
 
 .iak3d_ref <- list(setupIAK3D = setupIAK3D, lndetANDinvCb = lndetANDinvCb, nllIAK3D = nllIAK3D, nllIAK3D_CL = nllIAK3D_CL,
                    setupIAK3D_CL = setupIAK3D_CL, makeXvX = makeXvX)
-### The only fits that stay on the reference's CPU path are those with site-specific random effects (siteIDData given:
-### listStructs4ssre, fitIAK3D.R:1091-1101), and they say so once; any other evaluation without a device handle is an error.
+### An evaluation whose setupMats carries no device handle is an error, never a silent CPU evaluation.
 .iak3d_state <- new.env()
 .iak3d_state$ssre_warned <- FALSE ; .iak3d_state$cl <- NULL
 .iak3d_modelx <- c(nugget = 0, spherical = 1, matern = 2, wendland = 3)
@@ -26,7 +25,8 @@
     parsBTfmd$cx0, parsBTfmd$cx1, parsBTfmd$cd1, parsBTfmd$cxd0, parsBTfmd$cxd1, parsBTfmd$cme,
     tau(parsBTfmd$sdfdPars_cd1, sdfdType_cd1), tau(parsBTfmd$sdfdPars_cxd0, sdfdType_cxd0),
     tau(parsBTfmd$sdfdPars_cxd1, sdfdType_cxd1), quirk_scale,
-    spl(parsBTfmd$sdfdPars_cd1, sdfdType_cd1), spl(parsBTfmd$sdfdPars_cxd0, sdfdType_cxd0), spl(parsBTfmd$sdfdPars_cxd1, sdfdType_cxd1))
+    spl(parsBTfmd$sdfdPars_cd1, sdfdType_cd1), spl(parsBTfmd$sdfdPars_cxd0, sdfdType_cxd0), spl(parsBTfmd$sdfdPars_cxd1, sdfdType_cxd1),
+    length(parsBTfmd$cssre), c(as.numeric(parsBTfmd$cssre), numeric(8))[1:8])   # site-specific random effects (fitIAK3D.R:1413)
 }
 
 ### setupIAK3D: the id vectors live on the device.  Spline sd functions (sdfdType > 0): the interval-averaged spline
@@ -39,21 +39,22 @@
 }
 setupIAK3D <- function(xData, dIData, nDscPts = 0, partSetup = FALSE, sdfdType_cd1 = 0, sdfdType_cxd0 = 0, sdfdType_cxd1 = 0,
                        sdfdKnots = NULL, siteIDData = NULL, XData = NULL, colnames4ssre = NULL){
-  if(!is.null(siteIDData)){   # site-specific random effects: the reference's CPU path, announced (INTEGRATION.md)
-    if(!.iak3d_state$ssre_warned){ message('iak3d: siteIDData given -- site-specific random effects are evaluated by the reference on the CPU') ; .iak3d_state$ssre_warned <- TRUE }
-    out <- .iak3d_ref$setupIAK3D(xData, dIData, nDscPts, partSetup, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, sdfdKnots, siteIDData, XData, colnames4ssre)
-    out$iak3d_cpu <- TRUE
-    return(out)
-  }
   xData <- .iak3d_dbl(xData) ; dIData <- .iak3d_dbl(dIData)
   types <- c(sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1)
   h <- .Call('iak3dR_dataset', xData, dIData, NULL)
+  siteLevels <- NULL
+  if(!is.null(siteIDData)){   # site-specific random effects (iaCovMatern.R:440-460): the structures are never formed, see iak3d.h
+    if(!all(XData[,1] == 1)){ stop('Error - the lmer-type mixed-effects option (if siteIDData given) only works if first column of X is 1s!') }
+    siteLevels <- unique(as.character(siteIDData))
+    .Call('iak3dR_set_ssre', h, as.integer(match(as.character(siteIDData), siteLevels) - 1L), .iak3d_dbl(XData[, colnames4ssre, drop = FALSE]))
+  }
   if(max(types) > 0){
     dIU <- dIData[!duplicated(dIData), , drop = FALSE]                 # first-occurrence order == the library's ids
     B <- .iak3d_spl_bases(dIU, types, sdfdKnots)
     for(c in seq(3)){ if(!is.null(B[[c]])){ .Call('iak3dR_set_sdfd_spline', h, as.integer(c - 1), B[[c]]) } }
   }
   list(iak3d = h, xData = xData, dIData = dIData, n = nrow(xData), sdfdTypes = types, sdfdKnots = sdfdKnots,
+       siteLevels = siteLevels, colnames4ssre = colnames4ssre, listStructs4ssre = if(is.null(siteIDData)) NULL else as.list(colnames4ssre),
        maxd = max(max(dIData), 2), Kx = TRUE) # 'Kx' non-NULL: the reference's is.null(setupMats$Kx) guards (fitIAK3D.R:965) stay quiet
 }
 
@@ -184,9 +185,7 @@ setupIAK3D2 <- function(xData, dIData, xData2, dIData2, sdfdType_cd1 = 0, sdfdTy
 nllIAK3D <- function(pars, zData, XData, vXU, iU, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum,
                      setupMats = NULL, parBnds, useReml, lnTfmdData, rtnAll = F, forCompLik = FALSE, attachBigMats = FALSE, nCores = 8){
   if(is.null(setupMats$iak3d)){
-    if(!isTRUE(setupMats$iak3d_cpu)){ stop('iak3d: setupMats carries no device dataset -- build it with the setupIAK3D of r/iak3d_cuda.R (there is no silent CPU fallback)') }
-    return(.iak3d_ref$nllIAK3D(pars, zData, XData, vXU, iU, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum,
-                               setupMats, parBnds, useReml, lnTfmdData, rtnAll, forCompLik, attachBigMats, nCores))
+    stop('iak3d: setupMats carries no device dataset -- build it with the setupIAK3D of r/iak3d_cuda.R (there is no silent CPU fallback)')
   }
   ### composite likelihood: the terms of this unit were computed with all the others in one batched launch (nllIAK3D_CL below)
   if(forCompLik && !(rtnAll && attachBigMats) && !is.null(.iak3d_state$cl) && !is.null(setupMats$iak3d_unit)){
@@ -225,6 +224,7 @@ nllIAK3D <- function(pars, zData, XData, vXU, iU, modelx, nud, sdfdType_cd1, sdf
   cxdhat <- tl$cxdhat
   for(k in c('cx0', 'cx1', 'cd1', 'cxd0', 'cxd1')){ parsBTfmd[[k]] <- cxdhat * parsBTfmd[[k]] }
   if(cmeOpt == 1){ parsBTfmd$cme <- cxdhat * parsBTfmd$cme }
+  if(!is.null(parsBTfmd$cssre)){ parsBTfmd$cssre <- cxdhat * parsBTfmd$cssre }           # fitIAK3D.R:863
   vbetahat <- cxdhat * solve(tl$XiAX)
   out <- list(nll = tl$nll, pars = pars, parsBTfmd = parsBTfmd, betahat = tl$betahat, vbetahat = vbetahat, cxdhat = cxdhat,
               XData = XData, vXU = vXU, iU = iU)
@@ -527,4 +527,14 @@ iak3dPredictGrid <- function(lmmFit, design, xMap, covsMap, dIMap, nxPerBatch = 
   covM <- if(length(design$covNames) > 0) as.matrix(covsMap[, design$covNames, drop = FALSE]) + 0 else NULL
   tmp <- .Call('iak3dR_predict_grid', lmmFit$iak3dFit, design$handle, as.matrix(xMap) + 0, covM, round(as.matrix(dIMap), digits = 2), nxPerBatch)
   list(zMap = t(tmp[[1]]), vMap = t(tmp[[2]]))
+}
+
+### kriging of map supports with site-specific random effects (predictIAK3D.R:166-195): site labels of the map are matched
+### against the levels the fit's setupMats recorded; unseen sites get new codes (no shared structure with any datum)
+iak3dPredictBatchSsre <- function(lmmFit, xMapThis, dIMapThis, XMapThis, siteIDMapThis){
+  lev <- lmmFit$setupMats$siteLevels ; lab <- as.character(siteIDMapThis)
+  code <- match(lab, lev) ; new <- is.na(code) ; code[new] <- length(lev) + match(lab[new], unique(lab[new]))
+  tmp <- .Call('iak3dR_predict_ssre', lmmFit$iak3dFit, .iak3d_dbl(xMapThis), .iak3d_dbl(dIMapThis), .iak3d_dbl(XMapThis),
+               as.integer(code - 1L), .iak3d_dbl(as.matrix(XMapThis)[, lmmFit$setupMats$colnames4ssre, drop = FALSE]))
+  list(z = tmp[[1]], v = tmp[[2]])
 }

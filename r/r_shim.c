@@ -35,8 +35,8 @@ static void fit_finalizer(SEXP p) {
 
 /* parsBTfmd (list from readParsIAK3D) + model switches -> struct iak3d_pars.  pv = c(modelx, cmeOpt, sdfdType_cd1,
  * sdfdType_cxd0, sdfdType_cxd1, quirk, ax, nux, ad, nud, cx0, cx1, cd1, cxd0, cxd1, cme, tau(3x2 row-major), quirk_scale,
- * spline coefficients (3 x IAK3D_MAX_SPL row-major, zero padded)) */
-#define IAK3D_PV_LEN (23 + 3 * IAK3D_MAX_SPL)
+ * spline coefficients (3 x IAK3D_MAX_SPL row-major, zero padded), nssre, cssre (IAK3D_MAX_SSRE, zero padded)) */
+#define IAK3D_PV_LEN (23 + 3 * IAK3D_MAX_SPL + 1 + IAK3D_MAX_SSRE)
 static void pars_from_ptr(const double* v, iak3d_pars* P);
 static void pars_from(SEXP pv, iak3d_pars* P) {
   if (LENGTH(pv) != IAK3D_PV_LEN) error("iak3d: parameter vector must have %d entries", IAK3D_PV_LEN);
@@ -52,6 +52,8 @@ static void pars_from_ptr(const double* v, iak3d_pars* P) {
   for (int c = 0; c < 3; c++) { P->sdfdPars[c][0] = v[16 + 2 * c]; P->sdfdPars[c][1] = v[17 + 2 * c]; }
   P->quirk_scale = v[22];
   for (int c = 0; c < 3; c++) for (int k = 0; k < IAK3D_MAX_SPL; k++) P->sdfdSpl[c][k] = v[23 + c * IAK3D_MAX_SPL + k];
+  P->nssre = (int32_t)v[23 + 3 * IAK3D_MAX_SPL];            /* site-specific random effects: count, then the variances */
+  for (int k = 0; k < IAK3D_MAX_SSRE; k++) P->cssre[k] = v[24 + 3 * IAK3D_MAX_SPL + k];
 }
 
 /* setupIAK3D: xData (n x 2), dIData (n x 2, already rounded, fitIAK3D.R:127), W = cbind(X, z) or NULL */
@@ -503,6 +505,43 @@ SEXP iak3dR_dirichlet_adjacency(SEXP vcentres) {                    /* subsetPai
   return out;
 }
 
+/* ---- site-specific random effects (siteIDData given; iaCovMatern.R:440-460): site id (integer codes, equal = same site) and
+ * the columns XData[, colnames4ssre] of every row ---- */
+SEXP iak3dR_set_ssre(SEXP dsp, SEXP siteid, SEXP Xs) {
+  need_real(Xs, "XData[, colnames4ssre]");
+  if (TYPEOF(siteid) != INTSXP) error("iak3d: site ids must be integer codes");
+  int st = iak3d_dataset_set_ssre((iak3d_ds*)R_ExternalPtrAddr(dsp), ncols(Xs), (const int32_t*)INTEGER(siteid), REAL(Xs));
+  if (st != IAK3D_OK) error("iak3d_dataset_set_ssre: %s", iak3d_last_error(g_ctx));
+  return R_NilValue;
+}
+SEXP iak3dR_cov_cross_ssre(SEXP dsp, SEXP pv, SEXP xy1, SEXP dI1, SEXP siteid1, SEXP Xs1) {
+  iak3d_ds* ds = (iak3d_ds*)R_ExternalPtrAddr(dsp);
+  iak3d_pars P; pars_from(pv, &P);
+  int64_t n = 0; iak3d_dataset_info(ds, &n, NULL, NULL, NULL);
+  const int n1 = nrows(xy1);
+  SEXP out = PROTECT(allocMatrix(REALSXP, n1, (int)n));
+  int st = iak3d_cov_cross_ssre(ds, &P, n1, REAL(xy1), REAL(dI1), (const int32_t*)INTEGER(siteid1), REAL(Xs1), REAL(out));
+  if (st < 0) error("iak3d_cov_cross_ssre: %s", iak3d_last_error(g_ctx));
+  UNPROTECT(1);
+  return st == 0 ? out : R_NilValue;
+}
+/* kriging of map supports that carry site ids: list(z, v) */
+SEXP iak3dR_predict_ssre(SEXP fp, SEXP xyMap, SEXP dIMap, SEXP XMap, SEXP siteid, SEXP Xs) {
+  iak3d_fit* f = (iak3d_fit*)R_ExternalPtrAddr(fp);
+  const int m = nrows(xyMap);
+  int st = iak3d_predict_stage_ssre(f, m, REAL(xyMap), REAL(dIMap), REAL(XMap), (const int32_t*)INTEGER(siteid), REAL(Xs));
+  if (st == IAK3D_OK) st = iak3d_predict_enqueue(f);
+  if (st != IAK3D_OK) error("iak3d_predict_stage_ssre: %s", iak3d_last_error(g_ctx));
+  SEXP z = PROTECT(allocVector(REALSXP, m));
+  SEXP v = PROTECT(allocVector(REALSXP, m));
+  st = iak3d_predict_fetch(f, REAL(z), REAL(v));
+  if (st != IAK3D_OK) error("iak3d_predict_fetch: %s", iak3d_last_error(g_ctx));
+  SEXP out = PROTECT(allocVector(VECSXP, 2));
+  SET_VECTOR_ELT(out, 0, z); SET_VECTOR_ELT(out, 1, v);
+  UNPROTECT(3);
+  return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
   {"iak3dR_dataset", (DL_FUNC)&iak3dR_dataset, 3},       {"iak3dR_set_W", (DL_FUNC)&iak3dR_set_W, 2},
   {"iak3dR_nll_terms", (DL_FUNC)&iak3dR_nll_terms, 2},   {"iak3dR_nll_terms_iAW", (DL_FUNC)&iak3dR_nll_terms_iAW, 2},
@@ -523,6 +562,8 @@ static const R_CallMethodDef call_methods[] = {
   {"iak3dR_predict_grid", (DL_FUNC)&iak3dR_predict_grid, 6},
   {"iak3dR_nearest_centroid", (DL_FUNC)&iak3dR_nearest_centroid, 3}, {"iak3dR_voronoi_seed", (DL_FUNC)&iak3dR_voronoi_seed, 2},
   {"iak3dR_dirichlet_adjacency", (DL_FUNC)&iak3dR_dirichlet_adjacency, 1},
+  {"iak3dR_set_ssre", (DL_FUNC)&iak3dR_set_ssre, 3},     {"iak3dR_cov_cross_ssre", (DL_FUNC)&iak3dR_cov_cross_ssre, 6},
+  {"iak3dR_predict_ssre", (DL_FUNC)&iak3dR_predict_ssre, 6},
   {NULL, NULL, 0}};
 
 void R_init_iak3dR(DllInfo* dll) {

@@ -275,3 +275,31 @@ def test_pairwise_block_predictor_with_one_pair_is_exact_kriging():
         ze, ve = _exact_simple_kriging(ds, P, modelx, types, cmeOpt, rows, xMap[pts], dIMap[pts], z)
         assert np.max(np.abs(t["CkhiCz_muhat"][pts] - ze)) <= 1e-11 * np.max(np.abs(ze))
         assert np.max(np.abs((t["diagCkk"][pts] - t["diagCkhiCChk"][pts]) - ve) / ve) <= 1e-10
+
+
+def test_ssre_structures_are_block_diagonal_outer_products():
+    """listStructs4ssre (iaCovMatern.R:440-460): C += cssre_k * blockdiag_over_sites(X[site, k] X[site, k]')."""
+    from iak3d_b200 import synth
+    ds = synth.make_dataset(200, 7)
+    site = np.array([int(p) // 2 for p in ds["prof"]])
+    cols = [0, 6]
+    sm = orc.setupIAK3D(ds["xData"], ds["dIData"], siteIDData=site, XData=ds["XData"], cols4ssre=cols)
+    P, modelx, types, cmeOpt = synth.default_pars("matern0.5")
+    P = dict(P); P["nud"] = 0.5; P["cssre"] = np.array([0.3, 0.02])
+    C1, s2 = orc.setCIAK3D(P, modelx, *types, cmeOpt, sm)
+    C0, _ = orc.setCIAK3D(P, modelx, *types, cmeOpt, orc.setupIAK3D(ds["xData"], ds["dIData"]))
+    D = C1 - C0
+    Z = np.zeros_like(D)
+    for s_ in np.unique(site):
+        m = site == s_
+        for k, c in enumerate(cols):
+            Z[np.ix_(m, m)] += P["cssre"][k] * np.outer(ds["XData"][m, c], ds["XData"][m, c])
+    assert np.max(np.abs(D - Z)) <= 1e-13 * np.max(np.abs(Z)) and np.isnan(s2).all()
+    # the rectangular structures of a set against itself are the square ones
+    sm2 = orc.setupIAK3D2(ds["xData"], ds["dIData"], ds["xData"], ds["dIData"], siteIDData=site, XData=ds["XData"], siteIDData2=site,
+                          XData2=ds["XData"], cols4ssre=cols)
+    C2 = orc.setCIAK3D2(P, modelx, *types, cmeOpt, sm2)
+    assert np.max(np.abs(C2 + P["cme"] * np.eye(200) - C1)) <= 1e-12 * np.max(np.abs(C1))       # compositeLikIAK3D.R:382's check
+    # readParsIAK3D: whatever follows the model's own parameters are log site variances (fitIAK3D.R:1413)
+    pb = orc.readParsIAK3D(np.array([0.1, 0.2, -1.0, -2.0, -1.5, -3.0, -4.0]), "spherical", 0.5, -9, 0, 0, 0, True, PARBNDS)
+    assert np.allclose(pb["cssre"], np.exp([-3.0, -4.0]))
