@@ -107,6 +107,7 @@ _PROTOS = {
     "iak3d_design_destroy": (C.c_int, [_vp]),
     "iak3d_design_info": (C.c_int, [_vp, _ip, _ip]),
     "iak3d_design_eval": (C.c_int, [_vp, _i64, _dp, _dp, _dp, _dp, _dp]),
+    "iak3d_design_eval_lnN": (C.c_int, [_vp, _i64, _dp, _dp, _i32, _ip, _dp, _dp, _dp, _dp]),
     "iak3d_predict_stage_grid": (C.c_int, [_vp, _vp, _i64, _dp, _dp, _i64, _dp, _i64]),
     "iak3d_predict_fetch_X": (C.c_int, [_vp, _dp]),
     "iak3d_points_create": (C.c_int, [_vp, _i64, _dp, C.POINTER(_vp)]),

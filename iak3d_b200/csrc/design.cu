@@ -13,6 +13,8 @@
 // Compiled with -fmad=false: products and sums round like the reference's operation order.
 #include <math.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 constexpr int DES_MAXP = 64, DES_MAXRULES = 64, DES_MAXCONDS = 256, DES_MAXCOEF = 256, DES_MAXSET = 256, DES_MAXBRK = 64;
@@ -266,6 +268,76 @@ __global__ void __launch_bounds__(128) design_rows_kernel(const DesignDev* __res
   for (int j = 0; j < p; j++) X[(int64_t)j * ldx + i] = mw[j];
 }
 
+// ---- lnTfmdData = TRUE (makeXvX.R:246-290 'mlr', :437-557 'cubist'): a support is discretised into nDiscPts point depths; X =
+// column means of the point designs, vXU = their sample covariance (R's var(): two passes, n - 1) on the columns iU that vary
+// inside a support.  Limits act on the point values.  One thread per support; the covariance block is accumulated in the
+// output itself (vXU is (m pU) x pU column-major: element (i pU + a, b)).
+__device__ void point_row(const DesignDev& D, const double* __restrict__ covs, int64_t ldc, int64_t ci, double d, bool clamp, double* __restrict__ x,
+                          double* __restrict__ sp) {
+  if (D.type == 1) {
+    cubist_row(D, covs, ldc, ci, d, x);
+  } else {
+    if (D.nspl > 0) bs_point(D, d, sp);
+    for (int j = 0; j < D.p; j++) {
+      const int kd = D.kind[j];
+      if (kd == 4) { x[j] = sp[D.cov[j]]; continue; }
+      double base = 1.0;
+      if (D.cov[j] >= 0) {
+        const double c = covs[(int64_t)D.cov[j] * ldc + ci];
+        base = isnan(D.level[j]) ? c : ((c == D.level[j]) ? 1.0 : 0.0);
+      }
+      x[j] = kd == 0 ? base : (kd == 1 ? base * d : (kd == 2 ? base * (d * d) : base * pow(d, 3.0)));
+    }
+  }
+  if (clamp) for (int j = 0; j < D.p; j++) x[j] = clamp_nz(x[j], D.lims[0][j], D.lims[1][j]);
+}
+__device__ __forceinline__ double point_depth(const DesignDev& D, double a, double b, int t, double by) {
+  if (D.type == 1) return a + ((double)t * by) * (b - a);           // dIData[,1] + seq(0, 1, 1 / (nDiscPts - 1)) * (dL - dU), :497
+  if (D.nDiscPts <= 1) return 0.5 * (a + b);
+  const double x = a + (double)t * by;                              // seq(dU, dL, by), :250
+  return x > b ? b : x;
+}
+__global__ void __launch_bounds__(128) design_lnN_kernel(const DesignDev* __restrict__ Dp, int64_t m, const double* __restrict__ covs, int64_t ldc,
+                                                         const double* __restrict__ dI, const int32_t* __restrict__ iU, int pU,
+                                                         double* __restrict__ X, double* __restrict__ vXU, double* __restrict__ pmin,
+                                                         double* __restrict__ pmax) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const DesignDev& D = *Dp;
+  const double a = dI[i], b = dI[m + i];
+  const bool clamp = D.has_lims && !D.infBnds;
+  int npts = D.nDiscPts; double by;
+  if (D.type == 1) by = 1.0 / (double)(D.nDiscPts - 1);
+  else if (D.nDiscPts > 1) { by = (b - a) / (double)(D.nDiscPts - 1); npts = (int)floor((b - a) / by + 1e-10) + 1; }
+  else by = 0.0;
+  double x[DES_MAXP], mean[DES_MAXP], sp[DES_MAXSPL];
+  const int p = D.p;
+  for (int j = 0; j < p; j++) mean[j] = 0.0;
+  if (pmin) for (int j = 0; j < p; j++) { pmin[(int64_t)j * m + i] = nanv(); pmax[(int64_t)j * m + i] = nanv(); }
+  for (int t = 0; t < npts; t++) {
+    point_row(D, covs, ldc, i, point_depth(D, a, b, t, by), clamp, x, sp);
+    for (int j = 0; j < p; j++) {
+      mean[j] += x[j];
+      if (pmin && x[j] != 0.0) {          // minNonZero / maxNonZero over the point values (:274-276)
+        double* mn = pmin + (int64_t)j * m + i; double* mx = pmax + (int64_t)j * m + i;
+        if (isnan(*mn) || x[j] < *mn) *mn = x[j];
+        if (isnan(*mx) || x[j] > *mx) *mx = x[j];
+      }
+    }
+  }
+  for (int j = 0; j < p; j++) { mean[j] = mean[j] / (double)npts; X[(int64_t)j * m + i] = mean[j]; }
+  const int64_t ldv = m * pU;
+  for (int aa = 0; aa < pU; aa++) for (int bb = 0; bb < pU; bb++) vXU[(int64_t)bb * ldv + i * pU + aa] = 0.0;
+  for (int t = 0; t < npts; t++) {
+    point_row(D, covs, ldc, i, point_depth(D, a, b, t, by), clamp, x, sp);
+    for (int aa = 0; aa < pU; aa++) {
+      const double da = x[iU[aa]] - mean[iU[aa]];
+      for (int bb = 0; bb < pU; bb++) vXU[(int64_t)bb * ldv + i * pU + aa] += da * (x[iU[bb]] - mean[iU[bb]]);
+    }
+  }
+  for (int aa = 0; aa < pU; aa++) for (int bb = 0; bb < pU; bb++) vXU[(int64_t)bb * ldv + i * pU + aa] /= (double)(npts - 1);
+}
+
 // per-chunk (rows x 2) coordinate blocks and interval ids of a grid job (api_fit.cu's staging layout)
 __global__ void grid_supports_kernel(const double* __restrict__ xyCell, int64_t ncell, int64_t m, int64_t chunk,
                                      double* __restrict__ xy, int32_t* __restrict__ did) {
@@ -426,5 +498,45 @@ extern "C" int iak3d_design_eval(iak3d_design* g, int64_t m, const double* covs,
     if (e != cudaSuccess) { ctx->err = std::string("design_eval: ") + cudaGetErrorString(e); cudaGetLastError(); rc = IAK3D_ERR_CUDA; }
   } while (0);
   iak_pool_free(ctx, d_c); iak_pool_free(ctx, d_dI); iak_pool_free(ctx, d_X); iak_pool_free(ctx, d_mn); iak_pool_free(ctx, d_mx);
+  return rc;
+}
+
+extern "C" int iak3d_design_eval_lnN(iak3d_design* g, int64_t m, const double* covs, const double* dI, int32_t pU, const int32_t* iU, double* X,
+                                     double* vXU, double* pmin, double* pmax) {
+  if (!g || m < 0 || pU < 0 || (m > 0 && (!dI || !X || (pU > 0 && (!iU || !vXU)))) || (g->h.ncov > 0 && m > 0 && !covs)) return IAK3D_ERR_ARG;
+  iak3d_ctx* ctx = g->ctx;
+  cudaSetDevice(ctx->device);
+  if (m == 0) return IAK3D_OK;
+  const int p = g->h.p, ncov = g->h.ncov;
+  for (int k = 0; k < pU; k++) if (iU[k] < 0 || iU[k] >= p) { ctx->err = "design_eval_lnN: iU out of range"; return IAK3D_ERR_ARG; }
+  if (g->h.nDiscPts < 2) { ctx->err = "design_eval_lnN: nDiscPts >= 2"; return IAK3D_ERR_ARG; }
+  double *d_c = nullptr, *d_dI = nullptr, *d_X = nullptr, *d_V = nullptr, *d_mn = nullptr, *d_mx = nullptr; int32_t* d_iU = nullptr;
+  int rc = IAK3D_OK;
+  const bool want_lim = pmin && pmax;
+  do {
+    cudaError_t e = cudaSuccess;
+    if (ncov > 0) e = iak_pool_alloc(ctx, (void**)&d_c, (size_t)m * ncov * 8);
+    if (e == cudaSuccess) e = iak_pool_alloc(ctx, (void**)&d_dI, (size_t)m * 16);
+    if (e == cudaSuccess) e = iak_pool_alloc(ctx, (void**)&d_X, (size_t)m * p * 8);
+    if (e == cudaSuccess) e = iak_pool_alloc(ctx, (void**)&d_V, (size_t)std::max<int64_t>(m * pU * pU, 1) * 8);
+    if (e == cudaSuccess) e = iak_pool_alloc(ctx, (void**)&d_iU, (size_t)std::max(pU, 1) * 4);
+    if (e == cudaSuccess && want_lim) e = iak_pool_alloc(ctx, (void**)&d_mn, (size_t)m * p * 8);
+    if (e == cudaSuccess && want_lim) e = iak_pool_alloc(ctx, (void**)&d_mx, (size_t)m * p * 8);
+    if (e == cudaSuccess && ncov > 0) e = cudaMemcpyAsync(d_c, covs, (size_t)m * ncov * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_dI, dI, (size_t)m * 16, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && pU > 0) e = cudaMemcpyAsync(d_iU, iU, (size_t)pU * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { ctx->err = std::string("design_eval_lnN: ") + cudaGetErrorString(e); cudaGetLastError(); rc = IAK3D_ERR_CUDA; break; }
+    design_lnN_kernel<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(g->d, m, d_c, m, d_dI, d_iU, pU, d_X, d_V, d_mn, d_mx);
+    ctx->launches++;
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(X, d_X, (size_t)m * p * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && pU > 0) e = cudaMemcpyAsync(vXU, d_V, (size_t)m * pU * pU * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && want_lim) e = cudaMemcpyAsync(pmin, d_mn, (size_t)m * p * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && want_lim) e = cudaMemcpyAsync(pmax, d_mx, (size_t)m * p * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ctx->err = std::string("design_eval_lnN: ") + cudaGetErrorString(e); cudaGetLastError(); rc = IAK3D_ERR_CUDA; }
+  } while (0);
+  iak_pool_free(ctx, d_c); iak_pool_free(ctx, d_dI); iak_pool_free(ctx, d_X); iak_pool_free(ctx, d_V); iak_pool_free(ctx, d_iU);
+  iak_pool_free(ctx, d_mn); iak_pool_free(ctx, d_mx);
   return rc;
 }

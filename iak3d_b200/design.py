@@ -164,6 +164,18 @@ class DesignModel:
         self.ctx.check(self.ctx.lib.iak3d_design_eval(self.h, m, dptr(cv), dptr(dI), dptr(X), dptr(mn), dptr(mx)))
         return (X, mn, mx) if want_spline_limits else X
 
+    def eval_lnN(self, covs, dIData, iU, want_limits=False):
+        """lnTfmdData = TRUE: X (m x p) and vXU ((m pU) x pU) of m supports; iU = 0-based columns that vary inside a support."""
+        dI = f64(np.asarray(dIData, float).reshape(-1, 2))
+        m = dI.shape[0]
+        cv = f64(np.asarray(covs, float).reshape(m, self.ncov)) if self.ncov > 0 else None
+        iU = np.ascontiguousarray(np.asarray(iU, np.int32).reshape(-1)); pU = iU.size
+        X = np.empty((m, self.p), order="F"); V = np.empty((m * pU, pU), order="F")
+        mn = np.empty((m, self.p), order="F") if want_limits else None
+        mx = np.empty((m, self.p), order="F") if want_limits else None
+        self.ctx.check(self.ctx.lib.iak3d_design_eval_lnN(self.h, m, dptr(cv), dptr(dI), pU, _lib.iptr(iU), dptr(X), dptr(V), dptr(mn), dptr(mx)))
+        return (X, V, mn, mx) if want_limits else (X, V)
+
     def close(self):
         if getattr(self, "h", None) is not None and self.h.value:
             self.ctx.lib.iak3d_design_destroy(self.h)
@@ -189,8 +201,6 @@ def makeXvX(covData=None, dIData=None, modelX=0, allKnotsd=(), opt_dSpline=0, iU
     """makeXvX (makeXvX.R:1): design matrix of interval supports.  covData: dict name -> column (mlr; factor covariates as
     integer codes with covLevels[name] = number of levels) or an n x nvars array in modelX['namesDataFit'] order (cubist).
     lnTfmdData = TRUE (the within-support covariance vXU) is not built on the device."""
-    if lnTfmdData:
-        raise NotImplementedError("makeXvX on the device covers lnTfmdData = FALSE (vXU stays on the host)")
     dI = np.asarray(dIData, float).reshape(-1, 2)
     n = dI.shape[0]
     cubist = isinstance(modelX, dict)
@@ -198,6 +208,25 @@ def makeXvX(covData=None, dIData=None, modelX=0, allKnotsd=(), opt_dSpline=0, iU
     dm = DesignModel(modelX, covNames, covLevels, allKnotsd, opt_dSpline, nDiscPts, XLims, ctx=ctx)
     try:
         cv = _cov_matrix(covData, covNames, n)
+        if lnTfmdData:
+            # makeXvX.R:246-290 ('mlr'), :437-557 ('cubist'): point designs at nDiscPts depths -> mean and var(); iU (:566-600)
+            nm = dm.namesX
+            if iU is None:
+                iU = (list(range(dm.p)) if cubist else
+                      [j for j, s_ in enumerate(nm) if s_ in ("d", "d2") or s_.startswith(("d.", "d2.", "d3.", "dSpline."))])
+            iU = [int(j) for j in iU]
+            if XLims is not None:
+                X, V = dm.eval_lnN(cv, dI, iU)
+                XL = np.array(XLims, float)
+            else:
+                X, V, mn, mx = dm.eval_lnN(cv, dI, iU, want_limits=True)
+                with np.errstate(all="ignore"):
+                    lo = np.where(np.all(np.isnan(mn), axis=0), np.inf, np.nanmin(np.where(np.isnan(mn), np.inf, mn), axis=0))
+                    hi = np.where(np.all(np.isnan(mx), axis=0), -np.inf, np.nanmax(np.where(np.isnan(mx), -np.inf, mx), axis=0))
+                XL = np.vstack([lo, hi])
+                for j in dm.ipSpline:
+                    XL[0, j], XL[1, j] = -np.inf, np.inf                # folded into the (-Inf, Inf) the spline columns start with (:176-179)
+            return dict(X=np.asarray(X), vXU=np.asarray(V), iU=iU, namesX=nm, XLims=XL)
         if XLims is not None:
             X = dm.eval(cv, dI)
             XL = np.array(XLims, float)

@@ -284,6 +284,13 @@ IAK3D_API int iak3d_design_info(iak3d_design* design, int32_t* p, int32_t* ncov)
  * makeXvX.R:406-430) */
 IAK3D_API int iak3d_design_eval(iak3d_design* design, int64_t m, const double* covs, const double* dI, double* X,
                                 double* splmin, double* splmax);
+/* lnTfmdData = TRUE (makeXvX.R:246-290, 437-600): X = column means of the point designs at the support's nDiscPts depths, vXU =
+ * their sample covariance (R's var()) on the pU columns iU (0-based) that vary inside a support -- (m pU) x pU column-major,
+ * block i at rows i pU .. i pU + pU - 1 (the layout setmuIAK3D / calcbetavXbeta read, fitIAK3D.R:1261-1328).  Limits act on
+ * the point values; pmin / pmax (m x p, may be NULL) = min / max of each column's non-zero point values per support (NaN when
+ * all are zero), from which a caller in set-limits mode forms XLims (:274-276). */
+IAK3D_API int iak3d_design_eval_lnN(iak3d_design* design, int64_t m, const double* covs, const double* dI, int32_t pU,
+                                    const int32_t* iU, double* X, double* vXU, double* pmin, double* pmax);
 /* The whole prediction grid in one staging (the loops of predictIAK3D.R:144-155): ncell map cells (xyCell ncell x 2,
  * covCell ncell x ncov) x nint depth intervals (dIInt nint x 2); support (i, c) is row i * ncell + c of z, v (zMap / vMap
  * are ndIMap x nxMap) and its design row is made on the device.  nxPerBatch (predictIAK3D's argument, 2000 by default; 0 =

@@ -3,6 +3,8 @@
 Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this module; the product (iak3d_b200/) never does.
 
 What is restated (NumPy loops in the reference's own order of operations):
+  makeXvX_lnN        makeXvX.R:246-290 ('mlr') and :437-600 ('cubist') with lnTfmdData = TRUE: X = means and vXU = var() of the point
+                     designs at nDiscPts depths per support, reduced to the columns iU that vary inside a support
   makeXvX            makeXvX.R:1-708, the two branches with lnTfmdData = FALSE that predictIAK3D reaches (predictIAK3D.R:155):
                        * 'mlr'    (:212-353, the "quicker version" :294-353)  const / covariate / factor-dummy columns times
                                    the depth moments of the interval, B-spline-of-depth columns averaged over nDiscPts points
@@ -21,9 +23,10 @@ pivot whose position changed between R versions; this module returns NaN there.
 Reference quirks kept (each one is what the R code computes, not what its comments say):
   * the 'd2' / 'd3' columns multiply by  a^2 + ab + b^2  and  a^3 + a^2 b + a b^2 + b^3  WITHOUT the 1/3 and 1/4 of the interval
     means (makeXvX.R:303, 308);
-  * when limits are applied in the mlr branch the lower / upper limits are recycled over the depth-dependent columns from the
-    START of XLims (llim = XLims[1,] against t(X[, id123Tmp]), makeXvX.R:327-328), i.e. the k-th depth column (in the order
-    id, idInt, id2, id2Int, id3, id3Int) is clamped by the limits of column ((k-1) mod p) + 1, not by its own;
+  * when limits are applied in the mlr branch the lower / upper limits are recycled over t(X[, depth columns]) from the START of
+    XLims (llim = XLims[1,] against t(X[, id123Tmp]), makeXvX.R:327-328), i.e. entry (row i, k-th depth column in the order id,
+    idInt, id2, id2Int, id3, id3Int; 0-based) is clamped by the limits of column (i K + k) mod p, not by its own;
+  * one -Inf lower and one +Inf upper limit anywhere in XLims switch ALL clamping off (infBnds, :190-194);
   * limits never move exact zeros (replaceZeros = FALSE).
 
 Parity status: unpinned against R (no R here, no fixtures in the reference); pinned by construction checks in
@@ -184,6 +187,110 @@ def mlr_names(modelX, covNames, covLevels):
         if modelX > o:
             names.append(uni)
     return names
+
+
+def _rvar(XT):
+    """R's var() of the rows of XT: (n - 1)-denominator sample covariance, two-pass."""
+    m = XT.mean(axis=0)
+    Z = XT - m[None, :]
+    return (Z.T @ Z) / (XT.shape[0] - 1)
+
+
+def makeXvX_lnN(covData, dIData, modelX, allKnotsd=(), opt_dSpline=0, nDiscPts=100, XLims=None, covLevels=None, iU=None):
+    """lnTfmdData = TRUE (makeXvX.R:246-290 for 'mlr', :437-557 for 'cubist'): every support is discretised into nDiscPts point
+    depths; X = column means of the point designs, vXU = their sample covariance (var()), reduced to the columns iU that
+    vary inside a support (:566-600).  Limits act on the POINT values (set mode: min / max of the non-zero point values).
+    Returns dict(X, vXU ((n pU) x pU), iU (0-based), XLims, namesX)."""
+    dI = np.asarray(dIData, float).reshape(-1, 2)
+    n = dI.shape[0]
+    covLevels = covLevels or {}
+    allKnotsd = np.asarray(allKnotsd if allKnotsd is not None else (), float).reshape(-1)
+    is_cubist = isinstance(modelX, dict)
+    if is_cubist:
+        namesX = list(modelX["namesX"])
+    elif isinstance(modelX, (int, float)):
+        namesX = mlr_names(modelX, list(covData.keys()) if covData else [], covLevels)
+    else:
+        namesX = list(modelX)
+    if allKnotsd.size > 0 and not is_cubist:
+        namesX = [nm for nm in namesX if nm not in ("d", "d2", "d3")]
+    intKnots, bdry = allKnotsd[1:-1], ((allKnotsd[0], allKnotsd[-1]) if allKnotsd.size else (0.0, 1.0))
+    p = len(namesX)
+    ipSpline = [j for j, nm in enumerate(namesX) if nm.startswith("dSpline.")] if allKnotsd.size > 0 else []
+    if XLims is None:
+        setXLims = True
+        XLims = np.empty((2, p)); XLims[0] = np.inf; XLims[1] = -np.inf
+        XLims[0, ipSpline] = -np.inf; XLims[1, ipSpline] = np.inf
+        infBnds = False
+    else:
+        setXLims = False
+        XLims = np.array(XLims, float)
+        infBnds = bool(np.min(XLims[0]) == -np.inf and np.max(XLims[1]) == np.inf)
+    X = np.full((n, p), np.nan); V = np.full((n, p, p), np.nan)
+    if not is_cubist:
+        idx = lambda pred: [j for j, nm in enumerate(namesX) if pred(nm)]
+        id1 = idx(lambda s: s == "d"); id2 = idx(lambda s: s == "d2"); id3 = idx(lambda s: s == "d3")
+        idInt = idx(lambda s: s.startswith("d.")); id2Int = idx(lambda s: s.startswith("d2.")); id3Int = idx(lambda s: s.startswith("d3."))
+        idSpline = idx(lambda s: s.startswith("dSpline."))
+        names_d = list(namesX)
+        for j in id1 + id2 + id3 + idSpline: names_d[j] = "const"
+        for j in idInt: names_d[j] = names_d[j][2:]
+        for j in id2Int + id3Int: names_d[j] = names_d[j][3:]
+        X_d = np.full((n, p), np.nan)
+        lvl = 2
+        for j in range(p):
+            if names_d[j] == "const":
+                X_d[:, j] = 1.0
+            else:
+                c = np.asarray(covData[names_d[j]])
+                if covLevels.get(names_d[j]):
+                    if j == 0 or namesX[j] != namesX[j - 1]:
+                        lvl = 2
+                    X_d[:, j] = (c == lvl).astype(float); lvl += 1
+                else:
+                    X_d[:, j] = c.astype(float)
+        for i in range(n):
+            dd = seq_by(dI[i, 0], dI[i, 1], nDiscPts)
+            XT = np.repeat(X_d[i:i + 1], dd.size, axis=0)                              # :248
+            if id1: XT[:, id1] = XT[:, id1] * dd[:, None]
+            if id2: XT[:, id2] = XT[:, id2] * (dd ** 2)[:, None]
+            if id3: XT[:, id3] = XT[:, id3] * (dd ** 3)[:, None]
+            if idInt: XT[:, idInt] = XT[:, idInt] * dd[:, None]
+            if id2Int: XT[:, id2Int] = XT[:, id2Int] * (dd ** 2)[:, None]
+            if id3Int: XT[:, id3Int] = XT[:, id3Int] * (dd ** 3)[:, None]
+            if idSpline: XT[:, idSpline] = XT[:, idSpline] * bs_basis(dd, intKnots, bdry)
+            if setXLims:
+                XLims[0] = [minNonZero(np.append(XT[:, j], XLims[0, j])) for j in range(p)]
+                XLims[1] = [maxNonZero(np.append(XT[:, j], XLims[1, j])) for j in range(p)]
+            elif not infBnds:
+                XT = replaceLT(XT, XLims[0][None, :], replaceZeros=False)
+                XT = replaceGT(XT, XLims[1][None, :], replaceZeros=False)
+            X[i] = XT.mean(axis=0)
+            V[i] = _rvar(XT)
+        if iU is None:
+            iU = [j for j, nm in enumerate(namesX) if nm in ("d", "d2") or nm.startswith("d.") or nm.startswith("d2.")
+                  or nm.startswith("d3.") or nm.startswith("dSpline.")]               # :570 ('d3' itself is not listed there)
+    else:
+        cm = dict(modelX); cm["allKnotsd"] = allKnotsd; cm["opt_dSpline"] = opt_dSpline
+        D = np.array(covData, float)
+        lin = np.arange(nDiscPts) * (1.0 / (nDiscPts - 1))                             # seq(0, 1, 1 / (nDiscPts - 1))
+        for i in range(n):
+            dd = dI[i, 0] + lin * (dI[i, 1] - dI[i, 0])
+            Di = np.repeat(D[i:i + 1], nDiscPts, axis=0); Di[:, cm["dcol"]] = dd
+            XT, _ = cubist2XGivenSetup(cm, Di)
+            if setXLims:
+                XLims[0] = [minNonZero(np.append(XT[:, j], XLims[0, j])) for j in range(p)]
+                XLims[1] = [maxNonZero(np.append(XT[:, j], XLims[1, j])) for j in range(p)]
+            elif not infBnds:
+                XT = replaceLT(XT, XLims[0][None, :], replaceZeros=False)
+                XT = replaceGT(XT, XLims[1][None, :], replaceZeros=False)
+            X[i] = XT.mean(axis=0)
+            V[i] = _rvar(XT - X[i][None, :])
+        if iU is None:
+            iU = list(range(p))
+    iU = [int(j) for j in iU]
+    vXU = V[:, iU][:, :, iU].reshape(n * len(iU), len(iU))
+    return dict(X=X, vXU=vXU, iU=iU, XLims=XLims, namesX=namesX)
 
 
 def makeXvX(covData, dIData, modelX, allKnotsd=(), opt_dSpline=0, nDiscPts=100, XLims=None, covLevels=None):

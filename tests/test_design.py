@@ -109,3 +109,17 @@ def test_cubist_committee_normalisation():
     m = mat[:, 0] == 1
     assert np.allclose(X[m, j_const_r1], 1.0 / cnt1[m] / 2.0)
     assert np.all(X[~m, j_const_r1] == 0.0)
+
+
+def test_lognormal_branch_is_mean_and_sample_covariance_of_point_designs():
+    cov, levels, dI = mlr_case(15, 9, factor=False)
+    out = mx.makeXvX_lnN(cov, dI, 1, nDiscPts=10)
+    names = out["namesX"]; iU = out["iU"]
+    assert [names[j] for j in iU] == ["d", "d.elev", "d.twi"]
+    for i in (0, 6, 14):
+        dd = np.linspace(dI[i, 0], dI[i, 1], 10)
+        pts = np.column_stack([np.ones(10), np.full(10, cov["elev"][i]), np.full(10, cov["twi"][i]), dd, dd * cov["elev"][i], dd * cov["twi"][i]])
+        assert np.allclose(out["X"][i], pts.mean(axis=0), rtol=1e-13)
+        assert np.allclose(out["vXU"][3 * i:3 * i + 3], np.cov(pts[:, iU].T), rtol=1e-10, atol=1e-18)
+    # the interval mean of d agrees with the closed form of the other branch; d2 does not (that branch's moment lacks its 1/3)
+    assert np.allclose(out["X"][:, 3], mx.makeXvX(cov, dI, 1)["X"][:, 3], rtol=1e-13)

@@ -131,3 +131,45 @@ def test_grid_kriging_with_the_design_made_on_the_device(ctx):
     assert scaled_err(zg.reshape(len(dIMap), -1), zw) <= 1e-8
     assert scaled_err(vg.reshape(len(dIMap), -1), vw) <= 1e-8
     dm.close()
+
+
+@pytest.mark.parametrize("modelX,nDisc", [(1.5, 100), (3, 10)])
+def test_mlr_lognormal_branch(ctx, modelX, nDisc):
+    """lnTfmdData = TRUE (makeXvX.R:246-290): means and var() of the point designs; vXU on the depth-dependent columns."""
+    cov, levels, dI = mlr_case(260, 41)
+    want = mx.makeXvX_lnN(cov, dI, modelX, covLevels=levels, nDiscPts=nDisc)
+    got = iak.makeXvX(cov, dI, modelX, covLevels=levels, nDiscPts=nDisc, lnTfmdData=True, ctx=ctx)
+    assert got["iU"] == want["iU"] and got["namesX"] == want["namesX"]
+    assert col_err(got["X"], want["X"]) <= TOLX
+    assert got["vXU"].shape == want["vXU"].shape
+    assert np.max(np.abs(got["vXU"] - want["vXU"])) <= 1e-11 * np.max(np.abs(want["vXU"]))
+    assert np.allclose(got["XLims"], want["XLims"], rtol=1e-12, atol=0)
+    # given limits clamp the POINT values
+    L = np.vstack([np.quantile(want["X"], 0.2, axis=0) - 0.5, np.quantile(want["X"], 0.8, axis=0) + 0.5])
+    want = mx.makeXvX_lnN(cov, dI, modelX, covLevels=levels, nDiscPts=nDisc, XLims=L)
+    got = iak.makeXvX(cov, dI, modelX, covLevels=levels, nDiscPts=nDisc, lnTfmdData=True, XLims=L, ctx=ctx)
+    assert col_err(got["X"], want["X"]) <= TOLX
+    assert np.max(np.abs(got["vXU"] - want["vXU"])) <= 1e-11 * max(np.max(np.abs(want["vXU"])), 1e-300)
+
+
+def test_mlr_lognormal_with_bspline_columns(ctx):
+    cov, levels, dI = mlr_case(120, 42, factor=False)
+    names = ["const", "elev", "d.twi"] + [f"dSpline.{k + 1}" for k in range(6)]
+    want = mx.makeXvX_lnN(cov, dI, names, allKnotsd=ALLKNOTS, nDiscPts=20)
+    got = iak.makeXvX(cov, dI, names, allKnotsd=ALLKNOTS, nDiscPts=20, lnTfmdData=True, ctx=ctx)
+    assert got["iU"] == want["iU"] == [2, 3, 4, 5, 6, 7, 8]
+    assert col_err(got["X"], want["X"]) <= TOLX
+    assert np.max(np.abs(got["vXU"] - want["vXU"])) <= 1e-11 * np.max(np.abs(want["vXU"]))
+
+
+@pytest.mark.parametrize("opt", [0, 1])
+def test_cubist_lognormal_branch(ctx, opt):
+    """makeXvX.R:437-600: the rule design at nDiscPts depths per support; iU = every column."""
+    cm = cubist_model(True, opt)
+    D, dI = cubist_data(150, 43)
+    want = mx.makeXvX_lnN(D, dI, cm, allKnotsd=ALLKNOTS, opt_dSpline=opt, nDiscPts=10)
+    got = iak.makeXvX(D, dI, cm, allKnotsd=ALLKNOTS, opt_dSpline=opt, nDiscPts=10, lnTfmdData=True, ctx=ctx)
+    assert got["iU"] == list(range(len(cm["namesX"])))
+    assert col_err(got["X"], want["X"]) <= TOLX
+    assert np.max(np.abs(got["vXU"] - want["vXU"])) <= 1e-11 * np.max(np.abs(want["vXU"]))
+    assert np.allclose(got["XLims"], want["XLims"], rtol=1e-12, atol=0)
