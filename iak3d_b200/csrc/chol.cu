@@ -173,6 +173,8 @@ __device__ __forceinline__ void blk4_subst_row(const double (&l)[6], const doubl
   v3 = (v3 - v0 * l[2] - v1 * l[4] - v2 * l[5]) * r[3];
 }
 
+// ALIAS: scratch overlaps Ys (the pair engine has no spare stage): one more barrier before the inverse is written there
+template <bool ALIAS = false>
 __device__ void potf2_inv_blk4(double* __restrict__ At, int off, double* __restrict__ Ys, double* __restrict__ scratch,
                                double* __restrict__ pivs /* 64 */, int tid, double* logsum_out, int32_t* status) {
   const int br = tid >> 4, bc = tid & 15;
@@ -275,6 +277,7 @@ __device__ void potf2_inv_blk4(double* __restrict__ At, int off, double* __restr
     }
   }
   // ---- write L (zeros above the diagonal) and the inverse back to shared memory ----
+  if (ALIAS) consumer_bar();
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -639,7 +642,7 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
       if (is_diag) {
         const int off = (j & 1) * TN;
         if (LOOKAHEAD) potf2_inv_la(At, off, Ys, smem + 2 * STAGE_D, s_comm + 256, tid, pb->logsum + j, status);
-        else potf2_inv_blk4(At, off, Ys, smem + 2 * STAGE_D, s_comm + 256, tid, pb->logsum + j, status);   // scratch: stage 2, drained
+        else potf2_inv_blk4<false>(At, off, Ys, smem + 2 * STAGE_D, s_comm + 256, tid, pb->logsum + j, status);   // scratch: stage 2, drained
         double* invd = pb->invd + (int64_t)j * INVD_BLOCK;       // stored with the padded stride: one bulk copy reloads it
         for (int idx = tid; idx < INVD_BLOCK / 2; idx += NCW * 32)
           reinterpret_cast<double2*>(invd)[idx] = reinterpret_cast<const double2*>(Ys)[idx];
@@ -945,6 +948,7 @@ __global__ void __launch_bounds__(256) peak_mixed_kernel(double* out, int iters)
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+constexpr int PAIR_WARPS_DEFAULT = 4;     // MMA warps per CTA of the pair engine (IAK3D_PAIR_WARPS = 4 | 8 overrides)
 #include "chol_pair.cuh"
 
 }  // namespace
@@ -955,20 +959,36 @@ int chol_configure(iak3d_ctx* ctx) {
   CUDA_TRY(ctx, cudaFuncSetAttribute(tile_task_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   CUDA_TRY(ctx, cudaFuncSetAttribute(tile_task_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   CUDA_TRY(ctx, cudaFuncSetAttribute(backsolve_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * TN * 65 * (int)sizeof(double)));
-  CUDA_TRY(ctx, cudaFuncSetAttribute(tile_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-  CUDA_TRY(ctx, cudaFuncSetAttribute(tile_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-  CUDA_TRY(ctx, cudaFuncSetAttribute(tile_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(tile_pair_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(tile_pair_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(tile_pair_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(tile_pair_kernel<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(tile_pair_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(tile_pair_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
   // The pair engine's MMA warps grow to 216 registers with what the producer warpgroup gives back (setmaxnreg); that only
   // adds up when the kernel is launched with exactly 128 registers per thread and two CTAs fit an SM.  Anything else
   // (a different compiler, a smaller device) keeps the one-CTA engine rather than risk a warp waiting for registers.
   ctx->engine = 1;
   cudaFuncAttributes fa0, fa1, fa2;
-  CUDA_TRY(ctx, cudaFuncGetAttributes(&fa0, tile_pair_kernel<0>));
-  CUDA_TRY(ctx, cudaFuncGetAttributes(&fa1, tile_pair_kernel<1>));
-  CUDA_TRY(ctx, cudaFuncGetAttributes(&fa2, tile_pair_kernel<2>));
   int per_sm = 0;
-  CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_pair_kernel<0>, NT2, SMEM2_BYTES));
-  if (fa0.numRegs == 128 && fa1.numRegs == 128 && fa2.numRegs == 128 && per_sm >= 2) ctx->engine = 2;
+  const char* pw = getenv("IAK3D_PAIR_WARPS");
+  ctx->pair_warps = (pw && pw[0] == '4') ? 4 : ((pw && pw[0] == '8') ? 8 : PAIR_WARPS_DEFAULT);
+  for (int attempt = 0; attempt < 2 && ctx->engine == 1; attempt++) {
+    if (ctx->pair_warps == 8) {       // 384-thread CTAs: 80 registers per thread at launch, 104 / 32 after the split
+      CUDA_TRY(ctx, cudaFuncGetAttributes(&fa0, tile_pair_kernel<0, 8>));
+      CUDA_TRY(ctx, cudaFuncGetAttributes(&fa1, tile_pair_kernel<1, 8>));
+      CUDA_TRY(ctx, cudaFuncGetAttributes(&fa2, tile_pair_kernel<2, 8>));
+      CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_pair_kernel<0, 8>, 384, SMEM2_BYTES));
+      if (fa0.numRegs == 80 && fa1.numRegs == 80 && fa2.numRegs == 80 && per_sm >= 2) ctx->engine = 2; else ctx->pair_warps = 4;
+    } else {                          // 256-thread CTAs: 128 at launch, 216 / 40 after the split
+      CUDA_TRY(ctx, cudaFuncGetAttributes(&fa0, tile_pair_kernel<0, 4>));
+      CUDA_TRY(ctx, cudaFuncGetAttributes(&fa1, tile_pair_kernel<1, 4>));
+      CUDA_TRY(ctx, cudaFuncGetAttributes(&fa2, tile_pair_kernel<2, 4>));
+      CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_pair_kernel<0, 4>, 256, SMEM2_BYTES));
+      if (fa0.numRegs == 128 && fa1.numRegs == 128 && fa2.numRegs == 128 && per_sm >= 2) ctx->engine = 2;
+      break;
+    }
+  }
   const char* e = getenv("IAK3D_ENGINE");
   if (e && e[0] == '1') ctx->engine = 1;
   if (e && e[0] == '3' && ctx->engine == 2) ctx->engine = 3;   // tests: single-problem launches through the pair engine too
@@ -987,9 +1007,15 @@ int launch_tile_tasks(iak3d_ctx* ctx, const ProblemDesc* d_problems, const int4*
     // 9 x n = 2049 (width ~ 100) 18.2 vs 14.5 TFLOP/s, at 9 x n = 5000 (width ~ 270) 28.7 vs 30.3.
     int grid2 = 2 * ctx->sm_count;
     if (grid2 > ntasks) grid2 = ntasks;
-    if (mode == 0) tile_pair_kernel<0><<<grid2, NT2, SMEM2_BYTES, ctx->stream>>>(d_problems, d_tasks, ntasks, d_ticket);
-    else if (mode == 1) tile_pair_kernel<1><<<grid2, NT2, SMEM2_BYTES, ctx->stream>>>(d_problems, d_tasks, ntasks, d_ticket);
-    else tile_pair_kernel<2><<<grid2, NT2, SMEM2_BYTES, ctx->stream>>>(d_problems, d_tasks, ntasks, d_ticket);
+    if (ctx->pair_warps == 8) {
+      if (mode == 0) tile_pair_kernel<0, 8><<<grid2, 384, SMEM2_BYTES, ctx->stream>>>(d_problems, d_tasks, ntasks, d_ticket);
+      else if (mode == 1) tile_pair_kernel<1, 8><<<grid2, 384, SMEM2_BYTES, ctx->stream>>>(d_problems, d_tasks, ntasks, d_ticket);
+      else tile_pair_kernel<2, 8><<<grid2, 384, SMEM2_BYTES, ctx->stream>>>(d_problems, d_tasks, ntasks, d_ticket);
+    } else {
+      if (mode == 0) tile_pair_kernel<0, 4><<<grid2, 256, SMEM2_BYTES, ctx->stream>>>(d_problems, d_tasks, ntasks, d_ticket);
+      else if (mode == 1) tile_pair_kernel<1, 4><<<grid2, 256, SMEM2_BYTES, ctx->stream>>>(d_problems, d_tasks, ntasks, d_ticket);
+      else tile_pair_kernel<2, 4><<<grid2, 256, SMEM2_BYTES, ctx->stream>>>(d_problems, d_tasks, ntasks, d_ticket);
+    }
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return 0;

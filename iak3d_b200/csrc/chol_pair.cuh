@@ -23,21 +23,23 @@
 //
 // Single-problem launches (the optimiser's line searches: latency, not throughput) keep tile_task_kernel<-1, 1>.
 
-constexpr int NCW2 = 4;                       // MMA warps: 32 rows x 64 columns each
-constexpr int NT2 = 256;                      // 2 warpgroups: MMA | producer (+ 3 warps that only donate registers)
+// NW = MMA warps per CTA: 4 (32 rows x 64 columns each, 128 accumulator registers; 216 / 40 registers) or 8 (16 rows each;
+// 104 / 32 registers; 384-thread CTAs launched with 80 registers per thread).  One DMMA warp per sub-partition cannot keep
+// its share of the pipe full on its own (a warp issues a DMMA every ~32 cycles, the pipe takes one every 16), which shows
+// whenever the partner CTA is in an epilogue; with NW = 8 a CTA has two warps per sub-partition.
 constexpr int STAGES2 = 2;
 constexpr int SMEM2_BYTES = STAGES2 * STAGE_D * 8;      // 104,448 B = 6 units
 static_assert(STAGES2 * STAGE_D == 6 * UNIT, "epilogue map needs six units");
 static_assert(INVD_BLOCK == 2 * UNIT, "inverse diagonal block = two units");
 
-__device__ __forceinline__ void pair_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NCW2 * 32) : "memory"); }
-__device__ __forceinline__ void task_bar() { asm volatile("bar.sync 2, %0;" ::"n"((NCW2 + 1) * 32) : "memory"); }
+template <int NW> __device__ __forceinline__ void pair_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory"); }
+template <int NW> __device__ __forceinline__ void task_bar() { asm volatile("bar.sync 2, %0;" ::"n"((NW + 1) * 32) : "memory"); }
 
 // one 32-deep chunk of a warp's CNT (1..4) live 8-row tiles x 64 columns; ao[mi] = offset of row tile mi inside a stage's A
 // part.  CNT is a template parameter, not a predicate: mma.sync under a per-instruction predicate makes the compiler put a
 // WARPSYNC in front of every DMMA (measured: 12.4 -> 13.9 ms for the S5 step).
-template <int CNT>
-__device__ __forceinline__ void warp_mma2_chunk(double (&acc)[4][8][2], const double* __restrict__ Ab, const int (&ao)[4],
+template <int MI, int CNT>
+__device__ __forceinline__ void warp_mma2_chunk(double (&acc)[MI][8][2], const double* __restrict__ Ab, const int (&ao)[MI],
                                                 const double* __restrict__ Bb) {
 #pragma unroll
   for (int k4 = 0; k4 < KC / 4; k4++) {
@@ -54,23 +56,23 @@ __device__ __forceinline__ void warp_mma2_chunk(double (&acc)[4][8][2], const do
 }
 
 // E3: the eight k of block KB of  X = T inv(L_jj)'  for the column tiles KB..7 (inv(L_jj)' is upper triangular)
-template <int KB>
-__device__ __forceinline__ void solve2_block(double (&x)[4][8][2], const double* __restrict__ Ta, const int (&ao)[4],
+template <int MI, int KB>
+__device__ __forceinline__ void solve2_block(double (&x)[MI][8][2], const double* __restrict__ Ta, const int (&ao)[MI],
                                              const double* __restrict__ Yb) {
 #pragma unroll
   for (int h = 0; h < 2; h++) {
     const int k0 = KB * 8 + h * 4;
     const double* Ab = Ta + (k0 >> 5) * 2 * UNIT + (k0 & 31) * UL;
     const double* Bb = Yb + k0 * LDB_S;
-    double a[4], b[8];
+    double a[MI], b[8];
 #pragma unroll
-    for (int mi = 0; mi < 4; mi++) a[mi] = Ab[ao[mi]];
+    for (int mi = 0; mi < MI; mi++) a[mi] = Ab[ao[mi]];
 #pragma unroll
     for (int ni = KB; ni < 8; ni++) b[ni] = Bb[ni * 8];
 #pragma unroll
     for (int ni = KB; ni < 8; ni++)
 #pragma unroll
-      for (int mi = 0; mi < 4; mi++) dmma(x[mi][ni][0], x[mi][ni][1], a[mi], b[ni]);   // slots without a tile: computed, never stored
+      for (int mi = 0; mi < MI; mi++) dmma(x[mi][ni][0], x[mi][ni][1], a[mi], b[ni]);   // slots without a tile: computed, never stored
   }
 }
 
@@ -125,7 +127,7 @@ __device__ void potf2_inv_blk4_h2(double* __restrict__ At, int off, double* __re
         }
       }
     }
-    pair_bar();
+    pair_bar<4>();
     {
       double l[6], r[4];
 #pragma unroll
@@ -154,7 +156,7 @@ __device__ void potf2_inv_blk4_h2(double* __restrict__ At, int off, double* __re
         }
       }
     }
-    pair_bar();
+    pair_bar<4>();
 #pragma unroll
     for (int h = 0; h < 2; h++) {
       const int br = b2 + 8 * h;
@@ -190,7 +192,7 @@ __device__ void potf2_inv_blk4_h2(double* __restrict__ At, int off, double* __re
       }
     }
   }
-  pair_bar();               // the scratch may alias Ys
+  pair_bar<4>();               // the scratch may alias Ys
 #pragma unroll
   for (int h = 0; h < 2; h++) {
     const int br = b2 + 8 * h;
@@ -204,7 +206,7 @@ __device__ void potf2_inv_blk4_h2(double* __restrict__ At, int off, double* __re
       }
   }
   if (bad) atomicExch(status, 1);
-  pair_bar();
+  pair_bar<4>();
   if (tid < 32) {   // log-determinant of the block: fixed-order tree, deterministic
     double v = log(pivs[tid]) + log(pivs[tid + 32]);
 #pragma unroll
@@ -213,9 +215,10 @@ __device__ void potf2_inv_blk4_h2(double* __restrict__ At, int off, double* __re
   }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(NT2, 2)
+template <int MODE, int NW>
+__global__ void __launch_bounds__((NW + 4) * 32, 2)
 tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__ tasks, int ntasks, int32_t* ticket) {
+  constexpr int MI = 16 / NW;                   // 8-row tiles per MMA warp
   extern __shared__ __align__(128) double smem[];
   double* const T = smem;                       // epilogue: the task's own tile, 4 units  [col half][row half]
   double* const Ys = smem + 4 * UNIT;           // epilogue: inverse diagonal block (2 units)
@@ -229,7 +232,7 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < STAGES2; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NCW2); }
+    for (int s = 0; s < STAGES2; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NW); }
     mbar_init(&at_bar, 1);
     mbar_init(&inv_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -240,13 +243,14 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
   uint32_t it = 0;          // pipeline chunk counter, identical in every thread
   // The two roles never share code after this point: ptxas budgets registers per branch of a setmaxnreg pair only when
   // the branches do not merge again.
-  if (warp >= NCW2) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp > NCW2) return;
+  if (warp >= NW) {
+    if constexpr (NW == 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    if (warp > NW) return;
     // ===================== producer warp: tickets + TMA bulk copies, issued by one lane =====================
     while (true) {
       if (lane == 0) s_task = (ld_volatile(abort_flag) != 0) ? ntasks : atomicAdd(ticket, 1);
-      task_bar();
+      task_bar<NW>();
       const int t = s_task;
       if (t >= ntasks) break;
       const int4 tk = tasks[t];
@@ -283,15 +287,16 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
         }
         __syncwarp();
       it = it0 + (nchunks - kstart);
-      task_bar();
+      task_bar<NW>();
     }
     return;
   }
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+  if constexpr (NW == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
   // ===================== MMA warps: DMMA K-loop + epilogue =====================
   uint32_t at_phase = 0, inv_phase = 0;
   while (true) {
-    task_bar();
+    task_bar<NW>();
     const int t = s_task;
     if (t >= ntasks) break;
     const int4 tk = tasks[t];
@@ -315,7 +320,7 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
       // Row tiles (8 rows each, 16 per task) that carry data are DEALT to the four warps, so that a partly empty task costs
       // every warp the same: rows above the diagonal block of an odd column's diagonal tile, the identity padding [n, Npad)
       // and the rows behind the W rows never enter the K-loop (at n = 5000 the last row block holds 17 live rows of 128).
-      int tl[4], ao[4], cnt = 0;
+      int tl[MI], ao[MI], cnt = 0;
       {
         unsigned live = 0xffffu;
         if (mode == 0) {
@@ -332,26 +337,26 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
         }
         int k = 0;
 #pragma unroll
-        for (int mi = 0; mi < 4; mi++) { tl[mi] = -1; }
+        for (int mi = 0; mi < MI; mi++) { tl[mi] = -1; }
         for (int tt = 0; tt < 16; tt++)
           if ((live >> tt) & 1u) {
-            if ((k & 3) == warp) {
-              const int slot = k >> 2;
+            if ((k % NW) == warp) {
+              const int slot = k / NW;
 #pragma unroll
-              for (int mi = 0; mi < 4; mi++) if (mi == slot) tl[mi] = tt;
+              for (int mi = 0; mi < MI; mi++) if (mi == slot) tl[mi] = tt;
               cnt = slot + 1;
             }
             k++;
           }
 #pragma unroll
-        for (int mi = 0; mi < 4; mi++) {
+        for (int mi = 0; mi < MI; mi++) {
           const int tt = tl[mi] < 0 ? 0 : tl[mi];
           ao[mi] = (tt >> 3) * UNIT + (tt & 7) * 8 + rq;           // unit of the row half + row inside the unit
         }
       }
-      double acc[4][8][2];
+      double acc[MI][8][2];
 #pragma unroll
-      for (int mi = 0; mi < 4; mi++)
+      for (int mi = 0; mi < MI; mi++)
 #pragma unroll
         for (int ni = 0; ni < 8; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
       uint32_t itc = it0;
@@ -367,17 +372,22 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
         {
           const double* Ab = smem + s * STAGE_D + kq * UL;
           const double* Bb = smem + s * STAGE_D + A_STAGE + kq * UL + rq;
-          if (cnt == 4) warp_mma2_chunk<4>(acc, Ab, ao, Bb);
-          else if (cnt == 3) warp_mma2_chunk<3>(acc, Ab, ao, Bb);
-          else if (cnt == 2) warp_mma2_chunk<2>(acc, Ab, ao, Bb);
-          else if (cnt == 1) warp_mma2_chunk<1>(acc, Ab, ao, Bb);
+          if constexpr (MI == 4) {
+            if (cnt == 4) warp_mma2_chunk<MI, 4>(acc, Ab, ao, Bb);
+            else if (cnt == 3) warp_mma2_chunk<MI, 3>(acc, Ab, ao, Bb);
+            else if (cnt == 2) warp_mma2_chunk<MI, 2>(acc, Ab, ao, Bb);
+            else if (cnt == 1) warp_mma2_chunk<MI, 1>(acc, Ab, ao, Bb);
+          } else {
+            if (cnt == 2) warp_mma2_chunk<MI, 2>(acc, Ab, ao, Bb);
+            else if (cnt == 1) warp_mma2_chunk<MI, 1>(acc, Ab, ao, Bb);
+          }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[s]);
       }
       if (prof && tid == 0) tp1 = (long long)gtime();
       // ---- the ring has drained: fetch the task's own tile (and the inverse diagonal block) into it ----
-      pair_bar();
+      pair_bar<NW>();
       if (tid == 0) {
         mbar_expect_tx(&at_bar, 4 * UNIT * 8);
         bulk_g2s(T, Pt0, 2 * UNIT * 8, &at_bar);
@@ -395,7 +405,7 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
       if (mode == 2) {
         const double alpha = pb->alpha; const bool cin = pb->use_cin != 0;
 #pragma unroll
-        for (int mi = 0; mi < 4; mi++)
+        for (int mi = 0; mi < MI; mi++)
 #pragma unroll
           for (int ni = 0; ni < 8; ni++) {
             const int row = tl[mi] * 8 + rq, col = ni * 8 + kq * 2;      // mode 2: every tile is live
@@ -403,14 +413,14 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
             T[i0] = (cin ? T[i0] : 0.0) + alpha * acc[mi][ni][0];
             T[i1] = (cin ? T[i1] : 0.0) + alpha * acc[mi][ni][1];
           }
-        pair_bar();
-        for (int idx = tid; idx < 4 * (UNIT / 2); idx += NCW2 * 32) {
+        pair_bar<NW>();
+        for (int idx = tid; idx < 4 * (UNIT / 2); idx += NW * 32) {
           const int u = idx / (UNIT / 2), w2 = idx % (UNIT / 2);
           reinterpret_cast<double2*>(((u >> 1) ? Pt1 : Pt0) + (u & 1) * UNIT)[w2] = reinterpret_cast<const double2*>(T + u * UNIT)[w2];
         }
       } else {
 #pragma unroll
-        for (int mi = 0; mi < 4; mi++)
+        for (int mi = 0; mi < MI; mi++)
           if (mi < cnt) {
 #pragma unroll
             for (int ni = 0; ni < 8; ni++) {
@@ -424,19 +434,20 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
         int row_lo = 0;
         if (is_diag) {
           const int off = (j & 1) * TN;
-          pair_bar();
-          potf2_inv_blk4_h2(T, off, Ys, Ys, s_pivs, tid, pb->logsum + j, status);
+          pair_bar<NW>();
+          if constexpr (NW == 4) potf2_inv_blk4_h2(T, off, Ys, Ys, s_pivs, tid, pb->logsum + j, status);
+          else potf2_inv_blk4<true>(T, off, Ys, Ys, s_pivs, tid, pb->logsum + j, status);
           double* invd = pb->invd + (int64_t)j * INVD_BLOCK;
-          for (int idx = tid; idx < INVD_BLOCK / 2; idx += NCW2 * 32)
+          for (int idx = tid; idx < INVD_BLOCK / 2; idx += NW * 32)
             reinterpret_cast<double2*>(invd)[idx] = reinterpret_cast<const double2*>(Ys)[idx];
-          for (int idx = tid; idx < UNIT; idx += NCW2 * 32) {        // UNIT double2 = the two units (column halves) of L_jj
+          for (int idx = tid; idx < UNIT; idx += NW * 32) {        // UNIT double2 = the two units (column halves) of L_jj
             const int ch = idx / (UNIT / 2), w2 = idx % (UNIT / 2);
             const double2 v = reinterpret_cast<const double2*>(T + (ch * 2 + (off >> 6)) * UNIT)[w2];
             reinterpret_cast<double2*>((ch ? Pt1 : Pt0) + (off >> 6) * UNIT)[w2] = v;
           }
           __threadfence();
           asm volatile("fence.proxy.async;" ::: "memory");   // later readers fetch this block with the TMA engine
-          pair_bar();
+          pair_bar<NW>();
           if (tid == 0) st_release(pb->invdone + j, epoch);
           row_lo = off + TN;
         } else {
@@ -451,23 +462,23 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
           // row tiles below the diagonal block (diagonal tiles: the block itself was finished by potf2)
           int cnt3 = 0;
 #pragma unroll
-          for (int mi = 0; mi < 4; mi++) if (mi < cnt && tl[mi] * 8 >= row_lo) cnt3 = mi + 1;
+          for (int mi = 0; mi < MI; mi++) if (mi < cnt && tl[mi] * 8 >= row_lo) cnt3 = mi + 1;
           int lo3 = 0;
 #pragma unroll
-          for (int mi = 0; mi < 4; mi++) if (mi < cnt && tl[mi] * 8 < row_lo) lo3 = mi + 1;     // dealt in ascending order: dead ones first
+          for (int mi = 0; mi < MI; mi++) if (mi < cnt && tl[mi] * 8 < row_lo) lo3 = mi + 1;     // dealt in ascending order: dead ones first
           if (cnt3 > lo3) {
-            double x[4][8][2];
+            double x[MI][8][2];
 #pragma unroll
-            for (int mi = 0; mi < 4; mi++)
+            for (int mi = 0; mi < MI; mi++)
 #pragma unroll
               for (int ni = 0; ni < 8; ni++) { x[mi][ni][0] = 0.0; x[mi][ni][1] = 0.0; }
             const double* Ta = T + kq * UL;
             const double* Yb = Ys + kq * LDB_S + rq;
-            solve2_block<0>(x, Ta, ao, Yb); solve2_block<1>(x, Ta, ao, Yb); solve2_block<2>(x, Ta, ao, Yb); solve2_block<3>(x, Ta, ao, Yb);
-            solve2_block<4>(x, Ta, ao, Yb); solve2_block<5>(x, Ta, ao, Yb); solve2_block<6>(x, Ta, ao, Yb); solve2_block<7>(x, Ta, ao, Yb);
+            solve2_block<MI, 0>(x, Ta, ao, Yb); solve2_block<MI, 1>(x, Ta, ao, Yb); solve2_block<MI, 2>(x, Ta, ao, Yb); solve2_block<MI, 3>(x, Ta, ao, Yb);
+            solve2_block<MI, 4>(x, Ta, ao, Yb); solve2_block<MI, 5>(x, Ta, ao, Yb); solve2_block<MI, 6>(x, Ta, ao, Yb); solve2_block<MI, 7>(x, Ta, ao, Yb);
             __syncwarp();
 #pragma unroll
-            for (int mi = 0; mi < 4; mi++)
+            for (int mi = 0; mi < MI; mi++)
               if (mi >= lo3 && mi < cnt3) {
 #pragma unroll
                 for (int ni = 0; ni < 8; ni++) {
@@ -477,7 +488,7 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
                 }
               }
           }
-          pair_bar();
+          pair_bar<NW>();
           if (wfetch && tid == 0) {
             // kriging epilogue: the two units of the factor buffer that hold the W rows under this column block replace
             // the inverse diagonal block (every warp is past its solve)
@@ -491,7 +502,7 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
           // ---- E4: copy-out of row halves [row_lo/64, 2): whole units, coalesced 16-byte stores ----
           {
             const int rh0 = row_lo >> 6, nun = (2 - rh0) * 2;
-            for (int idx = tid; idx < nun * (UNIT / 2); idx += NCW2 * 32) {
+            for (int idx = tid; idx < nun * (UNIT / 2); idx += NW * 32) {
               const int u = idx / (UNIT / 2), w2 = idx % (UNIT / 2);
               const int ch = u / (2 - rh0), rh = rh0 + u % (2 - rh0);
               const double2 v = reinterpret_cast<const double2*>(T + (ch * 2 + rh) * UNIT)[w2];
@@ -503,7 +514,7 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
           if (mode == 0) {
             const int wl0 = pb->w0 - (int)R0;
             if (q > 0 && wl0 >= row_lo && wl0 < TM) {
-              for (int e = tid; e < q * q; e += NCW2 * 32) {
+              for (int e = tid; e < q * q; e += NW * 32) {
                 const int a = e % q, b = e / q;
                 double s = 0.0;
                 for (int c = 0; c < TN; c++) s += T[AT_IDX(wl0 + a, c)] * T[AT_IDX(wl0 + b, c)];
@@ -519,11 +530,13 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
             const double* Ws = Ys;
             double* const Gr = pb->G + R0 + rq;                    // + 8 * tl[mi]: every tile of a kriging panel is live
             const int64_t ldG = pb->ldG;
-            double ssq[4] = {0.0, 0.0, 0.0, 0.0};
-            for (int wb = 0; wb < q; wb += 16) {
-              double g[4][2][2], gold[4][2][2];
+            double ssq[MI];
 #pragma unroll
-              for (int mi = 0; mi < 4; mi++)
+            for (int mi = 0; mi < MI; mi++) ssq[mi] = 0.0;
+            for (int wb = 0; wb < q; wb += 16) {
+              double g[MI][2][2], gold[MI][2][2];
+#pragma unroll
+              for (int mi = 0; mi < MI; mi++)
 #pragma unroll
                 for (int ni = 0; ni < 2; ni++)
 #pragma unroll
@@ -536,23 +549,23 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
               for (int k4 = 0; k4 < TN / 4; k4++) {
                 const int k = k4 * 4 + kq;
                 const double* tk_ = T + (k >> 5) * 2 * UNIT + (k & 31) * UL;
-                double a[4];
+                double a[MI];
 #pragma unroll
-                for (int mi = 0; mi < 4; mi++) a[mi] = tk_[ao[mi]];
+                for (int mi = 0; mi < MI; mi++) a[mi] = tk_[ao[mi]];
                 const double* wk = Ws + (k >> 5) * UNIT + (k & 31) * UL + wb + rq;
                 const double b0 = wk[0], b1 = wk[8];
                 if (wb == 0) {
 #pragma unroll
-                  for (int mi = 0; mi < 4; mi++) ssq[mi] = fma(a[mi], a[mi], ssq[mi]);
+                  for (int mi = 0; mi < MI; mi++) ssq[mi] = fma(a[mi], a[mi], ssq[mi]);
                 }
 #pragma unroll
-                for (int mi = 0; mi < 4; mi++) {
+                for (int mi = 0; mi < MI; mi++) {
                   dmma(g[mi][0][0], g[mi][0][1], a[mi], b0);
                   dmma(g[mi][1][0], g[mi][1][1], a[mi], b1);
                 }
               }
 #pragma unroll
-              for (int mi = 0; mi < 4; mi++)
+              for (int mi = 0; mi < MI; mi++)
 #pragma unroll
                 for (int ni = 0; ni < 2; ni++)
 #pragma unroll
@@ -562,13 +575,13 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
                   }
             }
 #pragma unroll
-            for (int mi = 0; mi < 4; mi++) {                       // the four k-lanes of a row: fixed-order butterfly
+            for (int mi = 0; mi < MI; mi++) {                       // the four k-lanes of a row: fixed-order butterfly
               ssq[mi] += __shfl_xor_sync(0xffffffffu, ssq[mi], 1);
               ssq[mi] += __shfl_xor_sync(0xffffffffu, ssq[mi], 2);
             }
             if (kq == 0) {
 #pragma unroll
-              for (int mi = 0; mi < 4; mi++) {
+              for (int mi = 0; mi < MI; mi++) {
                 double* Gq = Gr + tl[mi] * 8 + (int64_t)q * ldG;
                 *Gq = (j == 0 ? 0.0 : __ldcg(Gq)) + ssq[mi];
               }
@@ -579,7 +592,7 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
         if (prof && tid == 0) tp4 = (long long)gtime();
         __threadfence();
         asm volatile("fence.proxy.async;" ::: "memory");     // the tile is re-read by other CTAs' TMA bulk copies
-        pair_bar();
+        pair_bar<NW>();
         if (tid == 0) st_release(pb->doneP + (int64_t)r * nCB + j, epoch);
         if (prof && tid == 0) {
           prof[0] = tp0; prof[1] = tp1; prof[2] = tp2; prof[3] = tp3; prof[4] = tp4; prof[5] = (long long)gtime();
@@ -588,6 +601,6 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
         }
       }
     it = it0 + (nchunks - kstart);
-    task_bar();
+    task_bar<NW>();
   }
 }

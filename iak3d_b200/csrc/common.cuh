@@ -43,6 +43,7 @@ struct iak3d_ctx {
   cudaEvent_t evs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // stage boundaries of the last batch
   std::string err;
   int64_t launches = 0;
+  int pair_warps = 4;        // MMA warps per CTA of the pair engine
   int pair_min_width = 148;  // tasks per dependency step from which a throughput launch uses the CTA-pair engine
   int engine = 1;            // tile engine of throughput launches: 1 = one CTA per SM (chol.cu), 2 = CTA pairs (chol_pair.cuh)
   // scratch
