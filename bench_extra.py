@@ -90,7 +90,9 @@ def _cl(args, rank, local_rank, world, comm):
                per_rank=dict(pairs=[int(x) for x in units_rank], rows=[int(x) for x in rows_rank], ms_per_step=[float(x) for x in ms_rank],
                              factorise_ms=[float(x) for x in fac_rank], tables_build_ms=[float(x) for x in pre_rank]),
                allreduce=dict(us_per_eval=tm.get("allreduce_us", 0.0) / calls, calls_per_eval=1 if world > 1 else 0,
-                              doubles=(p + 1) ** 2 + 2, where="NCCL on the device buffer the library summed into; one D2H after it"),
+                              doubles=(p + 1) ** 2 + 2, kind=tm.get("allreduce_kind", "none"),
+                              where="on the device buffer the library summed into, one D2H after it; kind 'peer' = the library's own "
+                                    "kernel over CUDA-IPC mailboxes (NVLink loads, rank-ordered sum), 'nccl' = ncclAllReduce"),
                gradient=dict(ms=1e3 * grad_s, evals=int(pars.size + 1), evals_per_s=(pars.size + 1) / grad_s,
                              allreduce_calls=int(tg.get("allreduce_calls", 0)), allreduce_us=float(tg.get("allreduce_us", 0.0)),
                              what="gradnllIAK3D_CL: npar + 1 evaluations as (units x parameter sets) batched launches + ONE all-reduce"),

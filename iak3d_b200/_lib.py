@@ -76,6 +76,10 @@ _PROTOS = {
     "iak3d_nll_terms_batch_fetch": (C.c_int, [_vp, _dp, _dp, _ip]),
     "iak3d_nll_terms_batch_wsum": (C.c_int, [_vp, _i32, C.POINTER(_vp), C.POINTER(Pars), _dp, _ip, _i32, _vp, _dp]),
     "iak3d_nll_terms_batch_wsum_multi": (C.c_int, [_i32, C.POINTER(_vp), _ip, C.POINTER(_vp), C.POINTER(Pars), _dp, _ip, _i32, _i32, _dp]),
+    "iak3d_peer_create": (C.c_int, [_vp, _i32, _i32, _i32, C.POINTER(_vp), _vp]),
+    "iak3d_peer_connect": (C.c_int, [_vp, _vp]),
+    "iak3d_peer_allreduce": (C.c_int, [_vp, _vp, _i32, _dp, _dp]),
+    "iak3d_peer_destroy": (C.c_int, [_vp]),
     "iak3d_dataset_slot_bytes": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "iak3d_nll_grad": (C.c_int, [_vp, _i32, C.POINTER(Pars), _dp, _i32, _dp, _dp, _dp]),
     "iak3d_fit_create": (C.c_int, [_vp, C.POINTER(Pars), _dp, _dp, C.POINTER(_vp)]),

@@ -810,7 +810,10 @@ def cl_terms_sets(units, structs, q, comm=None, timings=None):
     NCCL; every rank raises afterwards."""
     nsets, qq = len(structs), q * q
     width = qq + 2
-    dev = comm.device_buffer(nsets * width) if (comm is not None and comm.world > 1) else None   # torch CUDA tensor or None
+    dev = None
+    if comm is not None and comm.world > 1:
+        comm.attach_peer(units[0]["setup"].ctx if units else None)    # first call only: map the peers' mailboxes (collective)
+        dev = comm.device_buffer(nsets * width)                       # torch CUDA tensor, or None (gloo without peers: host sums)
     host = np.zeros((nsets, width))
     err = None
     t_dev0 = None

@@ -262,30 +262,30 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
       const int kstart = min(tk.w, nchunks);
       const uint32_t it0 = it;
       if (lane == 0) {
-          const double* __restrict__ L = pb->L; const int64_t nRUL = pb->nRUL;
-          const double* __restrict__ Asrc = (mode == 2) ? pb->A : pb->P;
-          const int64_t nRUA = (mode == 2) ? pb->nRUA : pb->nRUP;
-          const int nCB = pb->nCB, epoch = pb->epoch;
-          // the previous task's epilogue wrote the ring through the generic proxy (ordered by the end-of-task barrier)
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          uint32_t itp = it0;
-          for (int c = kstart; c < nchunks; c++, itp++) {
-            const int k = c >> 1;
-            if ((c & 1) == 0 && mode != 2) {
-              wait_flag(pb->doneP + (int64_t)r * nCB + k, epoch, status, abort_flag);
-              if (mode == 0) wait_flag(pb->doneL + (int64_t)(j >> 1) * nCB + k, epoch, status, abort_flag);
-              asm volatile("fence.proxy.async;" ::: "memory");
-              if (pb->prof && k == j - 1) s_tdep = (long long)gtime();
-            }
-            const uint32_t s = itp % STAGES2, use = itp / STAGES2;
-            if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1, status, abort_flag);
-            mbar_expect_tx(&full_bar[s], STAGE_D * 8);
-            double* As = smem + s * STAGE_D;
-            bulk_g2s(As, Asrc + ((int64_t)c * nRUA + 2 * r) * UNIT, A_STAGE * 8, &full_bar[s]);
-            bulk_g2s(As + A_STAGE, L + ((int64_t)c * nRUL + j) * UNIT, B_STAGE * 8, &full_bar[s]);
+        const double* __restrict__ L = pb->L; const int64_t nRUL = pb->nRUL;
+        const double* __restrict__ Asrc = (mode == 2) ? pb->A : pb->P;
+        const int64_t nRUA = (mode == 2) ? pb->nRUA : pb->nRUP;
+        const int nCB = pb->nCB, epoch = pb->epoch;
+        // the previous task's epilogue wrote the ring through the generic proxy (ordered by the end-of-task barrier)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        uint32_t itp = it0;
+        for (int c = kstart; c < nchunks; c++, itp++) {
+          const int k = c >> 1;
+          if ((c & 1) == 0 && mode != 2) {
+            wait_flag(pb->doneP + (int64_t)r * nCB + k, epoch, status, abort_flag);
+            if (mode == 0) wait_flag(pb->doneL + (int64_t)(j >> 1) * nCB + k, epoch, status, abort_flag);
+            asm volatile("fence.proxy.async;" ::: "memory");
+            if (pb->prof && k == j - 1) s_tdep = (long long)gtime();
           }
+          const uint32_t s = itp % STAGES2, use = itp / STAGES2;
+          if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1, status, abort_flag);
+          mbar_expect_tx(&full_bar[s], STAGE_D * 8);
+          double* As = smem + s * STAGE_D;
+          bulk_g2s(As, Asrc + ((int64_t)c * nRUA + 2 * r) * UNIT, A_STAGE * 8, &full_bar[s]);
+          bulk_g2s(As + A_STAGE, L + ((int64_t)c * nRUL + j) * UNIT, B_STAGE * 8, &full_bar[s]);
         }
-        __syncwarp();
+      }
+      __syncwarp();
       it = it0 + (nchunks - kstart);
       task_bar<NW>();
     }
@@ -307,299 +307,299 @@ tile_pair_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
     const int nchunks = (mode == 2) ? pb->kchunks : j * (TN / KC);
     const int kstart = min(tk.w, nchunks);
     const uint32_t it0 = it;
-      double* __restrict__ P = pb->P; const int64_t nRUP = pb->nRUP;
-      const int nCB = pb->nCB, epoch = pb->epoch;
-      const int64_t R0 = (int64_t)r * TM;
-      long long* prof = pb->prof ? pb->prof + (int64_t)t * 8 : nullptr;
-      long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0, tp4 = 0, kwait = 0;
-      if (prof && tid == 0) tp0 = (long long)gtime();
-      double* const Pt0 = P + ((int64_t)(2 * j) * nRUP + 2 * r) * UNIT;
-      double* const Pt1 = P + ((int64_t)(2 * j + 1) * nRUP + 2 * r) * UNIT;
-      const int kq = lane & 3, rq = lane >> 2;
-      const bool is_diag = (mode == 0) && (r == (j >> 1));
-      // Row tiles (8 rows each, 16 per task) that carry data are DEALT to the four warps, so that a partly empty task costs
-      // every warp the same: rows above the diagonal block of an odd column's diagonal tile, the identity padding [n, Npad)
-      // and the rows behind the W rows never enter the K-loop (at n = 5000 the last row block holds 17 live rows of 128).
-      int tl[MI], ao[MI], cnt = 0;
-      {
-        unsigned live = 0xffffu;
-        if (mode == 0) {
-          const int nl = pb->nlive, w0 = pb->w0, wq = pb->q;
-          if (nl > 0) {
-            live = 0u;
-            for (int tt = 0; tt < 16; tt++) {
-              const int64_t g0 = R0 + 8 * tt;
-              if (g0 < nl || (g0 + 7 >= w0 && g0 < w0 + wq)) live |= 1u << tt;
-            }
+    double* __restrict__ P = pb->P; const int64_t nRUP = pb->nRUP;
+    const int nCB = pb->nCB, epoch = pb->epoch;
+    const int64_t R0 = (int64_t)r * TM;
+    long long* prof = pb->prof ? pb->prof + (int64_t)t * 8 : nullptr;
+    long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0, tp4 = 0, kwait = 0;
+    if (prof && tid == 0) tp0 = (long long)gtime();
+    double* const Pt0 = P + ((int64_t)(2 * j) * nRUP + 2 * r) * UNIT;
+    double* const Pt1 = P + ((int64_t)(2 * j + 1) * nRUP + 2 * r) * UNIT;
+    const int kq = lane & 3, rq = lane >> 2;
+    const bool is_diag = (mode == 0) && (r == (j >> 1));
+    // Row tiles (8 rows each, 16 per task) that carry data are DEALT to the four warps, so that a partly empty task costs
+    // every warp the same: rows above the diagonal block of an odd column's diagonal tile, the identity padding [n, Npad)
+    // and the rows behind the W rows never enter the K-loop (at n = 5000 the last row block holds 17 live rows of 128).
+    int tl[MI], ao[MI], cnt = 0;
+    {
+      unsigned live = 0xffffu;
+      if (mode == 0) {
+        const int nl = pb->nlive, w0 = pb->w0, wq = pb->q;
+        if (nl > 0) {
+          live = 0u;
+          for (int tt = 0; tt < 16; tt++) {
+            const int64_t g0 = R0 + 8 * tt;
+            if (g0 < nl || (g0 + 7 >= w0 && g0 < w0 + wq)) live |= 1u << tt;
           }
-          if (is_diag && (j & 1)) live &= 0xff00u;        // upper 64 rows lie above the diagonal block
-          if (is_diag) live |= (j & 1) ? 0xff00u : 0x00ffu; // the diagonal block itself is always whole (identity padding included)
         }
-        int k = 0;
+        if (is_diag && (j & 1)) live &= 0xff00u;        // upper 64 rows lie above the diagonal block
+        if (is_diag) live |= (j & 1) ? 0xff00u : 0x00ffu; // the diagonal block itself is always whole (identity padding included)
+      }
+      int k = 0;
 #pragma unroll
-        for (int mi = 0; mi < MI; mi++) { tl[mi] = -1; }
-        for (int tt = 0; tt < 16; tt++)
-          if ((live >> tt) & 1u) {
-            if ((k % NW) == warp) {
-              const int slot = k / NW;
+      for (int mi = 0; mi < MI; mi++) { tl[mi] = -1; }
+      for (int tt = 0; tt < 16; tt++)
+        if ((live >> tt) & 1u) {
+          if ((k % NW) == warp) {
+            const int slot = k / NW;
 #pragma unroll
-              for (int mi = 0; mi < MI; mi++) if (mi == slot) tl[mi] = tt;
-              cnt = slot + 1;
-            }
-            k++;
+            for (int mi = 0; mi < MI; mi++) if (mi == slot) tl[mi] = tt;
+            cnt = slot + 1;
           }
+          k++;
+        }
 #pragma unroll
-        for (int mi = 0; mi < MI; mi++) {
-          const int tt = tl[mi] < 0 ? 0 : tl[mi];
-          ao[mi] = (tt >> 3) * UNIT + (tt & 7) * 8 + rq;           // unit of the row half + row inside the unit
+      for (int mi = 0; mi < MI; mi++) {
+        const int tt = tl[mi] < 0 ? 0 : tl[mi];
+        ao[mi] = (tt >> 3) * UNIT + (tt & 7) * 8 + rq;           // unit of the row half + row inside the unit
+      }
+    }
+    double acc[MI][8][2];
+#pragma unroll
+    for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+      for (int ni = 0; ni < 8; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+    uint32_t itc = it0;
+    for (int c = kstart; c < nchunks; c++, itc++) {
+      const uint32_t s = itc % STAGES2;
+      if (prof && tid == 0) {
+        const long long c0 = clock64();
+        mbar_wait(&full_bar[s], (itc / STAGES2) & 1, status, abort_flag);
+        kwait += clock64() - c0;
+      } else {
+        mbar_wait(&full_bar[s], (itc / STAGES2) & 1, status, abort_flag);
+      }
+      {
+        const double* Ab = smem + s * STAGE_D + kq * UL;
+        const double* Bb = smem + s * STAGE_D + A_STAGE + kq * UL + rq;
+        if constexpr (MI == 4) {
+          if (cnt == 4) warp_mma2_chunk<MI, 4>(acc, Ab, ao, Bb);
+          else if (cnt == 3) warp_mma2_chunk<MI, 3>(acc, Ab, ao, Bb);
+          else if (cnt == 2) warp_mma2_chunk<MI, 2>(acc, Ab, ao, Bb);
+          else if (cnt == 1) warp_mma2_chunk<MI, 1>(acc, Ab, ao, Bb);
+        } else {
+          if (cnt == 2) warp_mma2_chunk<MI, 2>(acc, Ab, ao, Bb);
+          else if (cnt == 1) warp_mma2_chunk<MI, 1>(acc, Ab, ao, Bb);
         }
       }
-      double acc[MI][8][2];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
+    if (prof && tid == 0) tp1 = (long long)gtime();
+    // ---- the ring has drained: fetch the task's own tile (and the inverse diagonal block) into it ----
+    pair_bar<NW>();
+    if (tid == 0) {
+      mbar_expect_tx(&at_bar, 4 * UNIT * 8);
+      bulk_g2s(T, Pt0, 2 * UNIT * 8, &at_bar);
+      bulk_g2s(T + 2 * UNIT, Pt1, 2 * UNIT * 8, &at_bar);
+      if (mode != 2 && !is_diag) {
+        if (mode == 0) wait_flag(pb->invdone + j, epoch, status, abort_flag);
+        asm volatile("fence.proxy.async;" ::: "memory");
+        mbar_expect_tx(&inv_bar, INVD_BLOCK * 8);
+        bulk_g2s(Ys, pb->invd + (int64_t)j * INVD_BLOCK, INVD_BLOCK * 8, &inv_bar);
+      }
+    }
+    mbar_wait(&at_bar, at_phase, status, abort_flag);
+    at_phase ^= 1;
+    // ---- E1: tile = A - acc (each warp touches its own 32 rows only) ----
+    if (mode == 2) {
+      const double alpha = pb->alpha; const bool cin = pb->use_cin != 0;
 #pragma unroll
       for (int mi = 0; mi < MI; mi++)
 #pragma unroll
-        for (int ni = 0; ni < 8; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
-      uint32_t itc = it0;
-      for (int c = kstart; c < nchunks; c++, itc++) {
-        const uint32_t s = itc % STAGES2;
-        if (prof && tid == 0) {
-          const long long c0 = clock64();
-          mbar_wait(&full_bar[s], (itc / STAGES2) & 1, status, abort_flag);
-          kwait += clock64() - c0;
-        } else {
-          mbar_wait(&full_bar[s], (itc / STAGES2) & 1, status, abort_flag);
+        for (int ni = 0; ni < 8; ni++) {
+          const int row = tl[mi] * 8 + rq, col = ni * 8 + kq * 2;      // mode 2: every tile is live
+          const int i0 = AT_IDX(row, col), i1 = AT_IDX(row, col + 1);
+          T[i0] = (cin ? T[i0] : 0.0) + alpha * acc[mi][ni][0];
+          T[i1] = (cin ? T[i1] : 0.0) + alpha * acc[mi][ni][1];
         }
-        {
-          const double* Ab = smem + s * STAGE_D + kq * UL;
-          const double* Bb = smem + s * STAGE_D + A_STAGE + kq * UL + rq;
-          if constexpr (MI == 4) {
-            if (cnt == 4) warp_mma2_chunk<MI, 4>(acc, Ab, ao, Bb);
-            else if (cnt == 3) warp_mma2_chunk<MI, 3>(acc, Ab, ao, Bb);
-            else if (cnt == 2) warp_mma2_chunk<MI, 2>(acc, Ab, ao, Bb);
-            else if (cnt == 1) warp_mma2_chunk<MI, 1>(acc, Ab, ao, Bb);
-          } else {
-            if (cnt == 2) warp_mma2_chunk<MI, 2>(acc, Ab, ao, Bb);
-            else if (cnt == 1) warp_mma2_chunk<MI, 1>(acc, Ab, ao, Bb);
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);
-      }
-      if (prof && tid == 0) tp1 = (long long)gtime();
-      // ---- the ring has drained: fetch the task's own tile (and the inverse diagonal block) into it ----
       pair_bar<NW>();
-      if (tid == 0) {
-        mbar_expect_tx(&at_bar, 4 * UNIT * 8);
-        bulk_g2s(T, Pt0, 2 * UNIT * 8, &at_bar);
-        bulk_g2s(T + 2 * UNIT, Pt1, 2 * UNIT * 8, &at_bar);
-        if (mode != 2 && !is_diag) {
-          if (mode == 0) wait_flag(pb->invdone + j, epoch, status, abort_flag);
-          asm volatile("fence.proxy.async;" ::: "memory");
-          mbar_expect_tx(&inv_bar, INVD_BLOCK * 8);
-          bulk_g2s(Ys, pb->invd + (int64_t)j * INVD_BLOCK, INVD_BLOCK * 8, &inv_bar);
-        }
+      for (int idx = tid; idx < 4 * (UNIT / 2); idx += NW * 32) {
+        const int u = idx / (UNIT / 2), w2 = idx % (UNIT / 2);
+        reinterpret_cast<double2*>(((u >> 1) ? Pt1 : Pt0) + (u & 1) * UNIT)[w2] = reinterpret_cast<const double2*>(T + u * UNIT)[w2];
       }
-      mbar_wait(&at_bar, at_phase, status, abort_flag);
-      at_phase ^= 1;
-      // ---- E1: tile = A - acc (each warp touches its own 32 rows only) ----
-      if (mode == 2) {
-        const double alpha = pb->alpha; const bool cin = pb->use_cin != 0;
+    } else {
 #pragma unroll
-        for (int mi = 0; mi < MI; mi++)
+      for (int mi = 0; mi < MI; mi++)
+        if (mi < cnt) {
 #pragma unroll
           for (int ni = 0; ni < 8; ni++) {
-            const int row = tl[mi] * 8 + rq, col = ni * 8 + kq * 2;      // mode 2: every tile is live
-            const int i0 = AT_IDX(row, col), i1 = AT_IDX(row, col + 1);
-            T[i0] = (cin ? T[i0] : 0.0) + alpha * acc[mi][ni][0];
-            T[i1] = (cin ? T[i1] : 0.0) + alpha * acc[mi][ni][1];
+            const int row = tl[mi] * 8 + rq, col = ni * 8 + kq * 2;
+            T[AT_IDX(row, col)] -= acc[mi][ni][0];
+            T[AT_IDX(row, col + 1)] -= acc[mi][ni][1];
           }
-        pair_bar<NW>();
-        for (int idx = tid; idx < 4 * (UNIT / 2); idx += NW * 32) {
-          const int u = idx / (UNIT / 2), w2 = idx % (UNIT / 2);
-          reinterpret_cast<double2*>(((u >> 1) ? Pt1 : Pt0) + (u & 1) * UNIT)[w2] = reinterpret_cast<const double2*>(T + u * UNIT)[w2];
         }
+      if (prof && tid == 0) tp2 = (long long)gtime();
+      // ---- E2: diagonal block, or the inverted diagonal block arrives ----
+      int row_lo = 0;
+      if (is_diag) {
+        const int off = (j & 1) * TN;
+        pair_bar<NW>();
+        if constexpr (NW == 4) potf2_inv_blk4_h2(T, off, Ys, Ys, s_pivs, tid, pb->logsum + j, status);
+        else potf2_inv_blk4<true>(T, off, Ys, Ys, s_pivs, tid, pb->logsum + j, status);
+        double* invd = pb->invd + (int64_t)j * INVD_BLOCK;
+        for (int idx = tid; idx < INVD_BLOCK / 2; idx += NW * 32)
+          reinterpret_cast<double2*>(invd)[idx] = reinterpret_cast<const double2*>(Ys)[idx];
+        for (int idx = tid; idx < UNIT; idx += NW * 32) {        // UNIT double2 = the two units (column halves) of L_jj
+          const int ch = idx / (UNIT / 2), w2 = idx % (UNIT / 2);
+          const double2 v = reinterpret_cast<const double2*>(T + (ch * 2 + (off >> 6)) * UNIT)[w2];
+          reinterpret_cast<double2*>((ch ? Pt1 : Pt0) + (off >> 6) * UNIT)[w2] = v;
+        }
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");   // later readers fetch this block with the TMA engine
+        pair_bar<NW>();
+        if (tid == 0) st_release(pb->invdone + j, epoch);
+        row_lo = off + TN;
       } else {
+        mbar_wait(&inv_bar, inv_phase, status, abort_flag);
+        inv_phase ^= 1;
+        __syncwarp();
+      }
+      if (prof && tid == 0) tp3 = (long long)gtime();
+      const bool wfetch = (mode == 1) && (pb->q > 0);
+      if (row_lo < TM) {
+        // ---- E3: X = tile * inv(L_jj)' on the tensor pipe; a warp reads and rewrites its own 32 rows of T ----
+        // row tiles below the diagonal block (diagonal tiles: the block itself was finished by potf2)
+        int cnt3 = 0;
 #pragma unroll
-        for (int mi = 0; mi < MI; mi++)
-          if (mi < cnt) {
+        for (int mi = 0; mi < MI; mi++) if (mi < cnt && tl[mi] * 8 >= row_lo) cnt3 = mi + 1;
+        int lo3 = 0;
 #pragma unroll
-            for (int ni = 0; ni < 8; ni++) {
-              const int row = tl[mi] * 8 + rq, col = ni * 8 + kq * 2;
-              T[AT_IDX(row, col)] -= acc[mi][ni][0];
-              T[AT_IDX(row, col + 1)] -= acc[mi][ni][1];
+        for (int mi = 0; mi < MI; mi++) if (mi < cnt && tl[mi] * 8 < row_lo) lo3 = mi + 1;     // dealt in ascending order: dead ones first
+        if (cnt3 > lo3) {
+          double x[MI][8][2];
+#pragma unroll
+          for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 8; ni++) { x[mi][ni][0] = 0.0; x[mi][ni][1] = 0.0; }
+          const double* Ta = T + kq * UL;
+          const double* Yb = Ys + kq * LDB_S + rq;
+          solve2_block<MI, 0>(x, Ta, ao, Yb); solve2_block<MI, 1>(x, Ta, ao, Yb); solve2_block<MI, 2>(x, Ta, ao, Yb); solve2_block<MI, 3>(x, Ta, ao, Yb);
+          solve2_block<MI, 4>(x, Ta, ao, Yb); solve2_block<MI, 5>(x, Ta, ao, Yb); solve2_block<MI, 6>(x, Ta, ao, Yb); solve2_block<MI, 7>(x, Ta, ao, Yb);
+          __syncwarp();
+#pragma unroll
+          for (int mi = 0; mi < MI; mi++)
+            if (mi >= lo3 && mi < cnt3) {
+#pragma unroll
+              for (int ni = 0; ni < 8; ni++) {
+                const int row = tl[mi] * 8 + rq, col = ni * 8 + kq * 2;
+                T[AT_IDX(row, col)] = x[mi][ni][0];
+                T[AT_IDX(row, col + 1)] = x[mi][ni][1];
+              }
+            }
+        }
+        pair_bar<NW>();
+        if (wfetch && tid == 0) {
+          // kriging epilogue: the two units of the factor buffer that hold the W rows under this column block replace
+          // the inverse diagonal block (every warp is past its solve)
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          const int64_t wu = (int64_t)pb->w0 / UR;
+          mbar_expect_tx(&inv_bar, 2 * UNIT * 8);
+          bulk_g2s(Ys, pb->L + ((int64_t)(2 * j) * pb->nRUL + wu) * UNIT, UNIT * 8, &inv_bar);
+          bulk_g2s(Ys + UNIT, pb->L + ((int64_t)(2 * j + 1) * pb->nRUL + wu) * UNIT, UNIT * 8, &inv_bar);
+        }
+        if (prof && tid == 0 && mode == 1) s_tdep = (long long)gtime();
+        // ---- E4: copy-out of row halves [row_lo/64, 2): whole units, coalesced 16-byte stores ----
+        {
+          const int rh0 = row_lo >> 6, nun = (2 - rh0) * 2;
+          for (int idx = tid; idx < nun * (UNIT / 2); idx += NW * 32) {
+            const int u = idx / (UNIT / 2), w2 = idx % (UNIT / 2);
+            const int ch = u / (2 - rh0), rh = rh0 + u % (2 - rh0);
+            const double2 v = reinterpret_cast<const double2*>(T + (ch * 2 + rh) * UNIT)[w2];
+            reinterpret_cast<double2*>((ch ? Pt1 : Pt0) + rh * UNIT)[w2] = v;
+          }
+        }
+        // ---- E5: border reductions (ordered by the flag chain => deterministic, no atomics) ----
+        const int q = pb->q;
+        if (mode == 0) {
+          const int wl0 = pb->w0 - (int)R0;
+          if (q > 0 && wl0 >= row_lo && wl0 < TM) {
+            for (int e = tid; e < q * q; e += NW * 32) {
+              const int a = e % q, b = e / q;
+              double s = 0.0;
+              for (int c = 0; c < TN; c++) s += T[AT_IDX(wl0 + a, c)] * T[AT_IDX(wl0 + b, c)];
+              double* G = pb->G + e;            // __ldcg: the previous column's CTA wrote it through L2
+              *G = (j == 0 ? 0.0 : __ldcg(G)) + s;
             }
           }
-        if (prof && tid == 0) tp2 = (long long)gtime();
-        // ---- E2: diagonal block, or the inverted diagonal block arrives ----
-        int row_lo = 0;
-        if (is_diag) {
-          const int off = (j & 1) * TN;
-          pair_bar<NW>();
-          if constexpr (NW == 4) potf2_inv_blk4_h2(T, off, Ys, Ys, s_pivs, tid, pb->logsum + j, status);
-          else potf2_inv_blk4<true>(T, off, Ys, Ys, s_pivs, tid, pb->logsum + j, status);
-          double* invd = pb->invd + (int64_t)j * INVD_BLOCK;
-          for (int idx = tid; idx < INVD_BLOCK / 2; idx += NW * 32)
-            reinterpret_cast<double2*>(invd)[idx] = reinterpret_cast<const double2*>(Ys)[idx];
-          for (int idx = tid; idx < UNIT; idx += NW * 32) {        // UNIT double2 = the two units (column halves) of L_jj
-            const int ch = idx / (UNIT / 2), w2 = idx % (UNIT / 2);
-            const double2 v = reinterpret_cast<const double2*>(T + (ch * 2 + (off >> 6)) * UNIT)[w2];
-            reinterpret_cast<double2*>((ch ? Pt1 : Pt0) + (off >> 6) * UNIT)[w2] = v;
-          }
-          __threadfence();
-          asm volatile("fence.proxy.async;" ::: "memory");   // later readers fetch this block with the TMA engine
-          pair_bar<NW>();
-          if (tid == 0) st_release(pb->invdone + j, epoch);
-          row_lo = off + TN;
-        } else {
+        } else if (wfetch) {
+          // kriging rows: G(:,0..q-1) += X Yw', G(:,q) += rowsum(X^2) on the tensor pipe: the warp's 32 rows are four
+          // m8 tiles, the W rows the B operand (element (w, c) at Ws[(c>>5)*UNIT + (c&31)*UL + w]), 16 W rows per pass
           mbar_wait(&inv_bar, inv_phase, status, abort_flag);
           inv_phase ^= 1;
-          __syncwarp();
-        }
-        if (prof && tid == 0) tp3 = (long long)gtime();
-        const bool wfetch = (mode == 1) && (pb->q > 0);
-        if (row_lo < TM) {
-          // ---- E3: X = tile * inv(L_jj)' on the tensor pipe; a warp reads and rewrites its own 32 rows of T ----
-          // row tiles below the diagonal block (diagonal tiles: the block itself was finished by potf2)
-          int cnt3 = 0;
+          const double* Ws = Ys;
+          double* const Gr = pb->G + R0 + rq;                    // + 8 * tl[mi]: every tile of a kriging panel is live
+          const int64_t ldG = pb->ldG;
+          double ssq[MI];
 #pragma unroll
-          for (int mi = 0; mi < MI; mi++) if (mi < cnt && tl[mi] * 8 >= row_lo) cnt3 = mi + 1;
-          int lo3 = 0;
-#pragma unroll
-          for (int mi = 0; mi < MI; mi++) if (mi < cnt && tl[mi] * 8 < row_lo) lo3 = mi + 1;     // dealt in ascending order: dead ones first
-          if (cnt3 > lo3) {
-            double x[MI][8][2];
+          for (int mi = 0; mi < MI; mi++) ssq[mi] = 0.0;
+          for (int wb = 0; wb < q; wb += 16) {
+            double g[MI][2][2], gold[MI][2][2];
 #pragma unroll
             for (int mi = 0; mi < MI; mi++)
 #pragma unroll
-              for (int ni = 0; ni < 8; ni++) { x[mi][ni][0] = 0.0; x[mi][ni][1] = 0.0; }
-            const double* Ta = T + kq * UL;
-            const double* Yb = Ys + kq * LDB_S + rq;
-            solve2_block<MI, 0>(x, Ta, ao, Yb); solve2_block<MI, 1>(x, Ta, ao, Yb); solve2_block<MI, 2>(x, Ta, ao, Yb); solve2_block<MI, 3>(x, Ta, ao, Yb);
-            solve2_block<MI, 4>(x, Ta, ao, Yb); solve2_block<MI, 5>(x, Ta, ao, Yb); solve2_block<MI, 6>(x, Ta, ao, Yb); solve2_block<MI, 7>(x, Ta, ao, Yb);
-            __syncwarp();
+              for (int ni = 0; ni < 2; ni++)
 #pragma unroll
-            for (int mi = 0; mi < MI; mi++)
-              if (mi >= lo3 && mi < cnt3) {
-#pragma unroll
-                for (int ni = 0; ni < 8; ni++) {
-                  const int row = tl[mi] * 8 + rq, col = ni * 8 + kq * 2;
-                  T[AT_IDX(row, col)] = x[mi][ni][0];
-                  T[AT_IDX(row, col + 1)] = x[mi][ni][1];
+                for (int e = 0; e < 2; e++) {
+                  g[mi][ni][e] = 0.0;
+                  const int col = wb + ni * 8 + kq * 2 + e;
+                  gold[mi][ni][e] = (j == 0 || col >= q) ? 0.0 : __ldcg(Gr + tl[mi] * 8 + (int64_t)col * ldG);
                 }
-              }
-          }
-          pair_bar<NW>();
-          if (wfetch && tid == 0) {
-            // kriging epilogue: the two units of the factor buffer that hold the W rows under this column block replace
-            // the inverse diagonal block (every warp is past its solve)
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            const int64_t wu = (int64_t)pb->w0 / UR;
-            mbar_expect_tx(&inv_bar, 2 * UNIT * 8);
-            bulk_g2s(Ys, pb->L + ((int64_t)(2 * j) * pb->nRUL + wu) * UNIT, UNIT * 8, &inv_bar);
-            bulk_g2s(Ys + UNIT, pb->L + ((int64_t)(2 * j + 1) * pb->nRUL + wu) * UNIT, UNIT * 8, &inv_bar);
-          }
-          if (prof && tid == 0 && mode == 1) s_tdep = (long long)gtime();
-          // ---- E4: copy-out of row halves [row_lo/64, 2): whole units, coalesced 16-byte stores ----
-          {
-            const int rh0 = row_lo >> 6, nun = (2 - rh0) * 2;
-            for (int idx = tid; idx < nun * (UNIT / 2); idx += NW * 32) {
-              const int u = idx / (UNIT / 2), w2 = idx % (UNIT / 2);
-              const int ch = u / (2 - rh0), rh = rh0 + u % (2 - rh0);
-              const double2 v = reinterpret_cast<const double2*>(T + (ch * 2 + rh) * UNIT)[w2];
-              reinterpret_cast<double2*>((ch ? Pt1 : Pt0) + rh * UNIT)[w2] = v;
-            }
-          }
-          // ---- E5: border reductions (ordered by the flag chain => deterministic, no atomics) ----
-          const int q = pb->q;
-          if (mode == 0) {
-            const int wl0 = pb->w0 - (int)R0;
-            if (q > 0 && wl0 >= row_lo && wl0 < TM) {
-              for (int e = tid; e < q * q; e += NW * 32) {
-                const int a = e % q, b = e / q;
-                double s = 0.0;
-                for (int c = 0; c < TN; c++) s += T[AT_IDX(wl0 + a, c)] * T[AT_IDX(wl0 + b, c)];
-                double* G = pb->G + e;            // __ldcg: the previous column's CTA wrote it through L2
-                *G = (j == 0 ? 0.0 : __ldcg(G)) + s;
-              }
-            }
-          } else if (wfetch) {
-            // kriging rows: G(:,0..q-1) += X Yw', G(:,q) += rowsum(X^2) on the tensor pipe: the warp's 32 rows are four
-            // m8 tiles, the W rows the B operand (element (w, c) at Ws[(c>>5)*UNIT + (c&31)*UL + w]), 16 W rows per pass
-            mbar_wait(&inv_bar, inv_phase, status, abort_flag);
-            inv_phase ^= 1;
-            const double* Ws = Ys;
-            double* const Gr = pb->G + R0 + rq;                    // + 8 * tl[mi]: every tile of a kriging panel is live
-            const int64_t ldG = pb->ldG;
-            double ssq[MI];
-#pragma unroll
-            for (int mi = 0; mi < MI; mi++) ssq[mi] = 0.0;
-            for (int wb = 0; wb < q; wb += 16) {
-              double g[MI][2][2], gold[MI][2][2];
-#pragma unroll
-              for (int mi = 0; mi < MI; mi++)
-#pragma unroll
-                for (int ni = 0; ni < 2; ni++)
-#pragma unroll
-                  for (int e = 0; e < 2; e++) {
-                    g[mi][ni][e] = 0.0;
-                    const int col = wb + ni * 8 + kq * 2 + e;
-                    gold[mi][ni][e] = (j == 0 || col >= q) ? 0.0 : __ldcg(Gr + tl[mi] * 8 + (int64_t)col * ldG);
-                  }
 #pragma unroll 4
-              for (int k4 = 0; k4 < TN / 4; k4++) {
-                const int k = k4 * 4 + kq;
-                const double* tk_ = T + (k >> 5) * 2 * UNIT + (k & 31) * UL;
-                double a[MI];
+            for (int k4 = 0; k4 < TN / 4; k4++) {
+              const int k = k4 * 4 + kq;
+              const double* tk_ = T + (k >> 5) * 2 * UNIT + (k & 31) * UL;
+              double a[MI];
 #pragma unroll
-                for (int mi = 0; mi < MI; mi++) a[mi] = tk_[ao[mi]];
-                const double* wk = Ws + (k >> 5) * UNIT + (k & 31) * UL + wb + rq;
-                const double b0 = wk[0], b1 = wk[8];
-                if (wb == 0) {
+              for (int mi = 0; mi < MI; mi++) a[mi] = tk_[ao[mi]];
+              const double* wk = Ws + (k >> 5) * UNIT + (k & 31) * UL + wb + rq;
+              const double b0 = wk[0], b1 = wk[8];
+              if (wb == 0) {
 #pragma unroll
-                  for (int mi = 0; mi < MI; mi++) ssq[mi] = fma(a[mi], a[mi], ssq[mi]);
-                }
-#pragma unroll
-                for (int mi = 0; mi < MI; mi++) {
-                  dmma(g[mi][0][0], g[mi][0][1], a[mi], b0);
-                  dmma(g[mi][1][0], g[mi][1][1], a[mi], b1);
-                }
+                for (int mi = 0; mi < MI; mi++) ssq[mi] = fma(a[mi], a[mi], ssq[mi]);
               }
-#pragma unroll
-              for (int mi = 0; mi < MI; mi++)
-#pragma unroll
-                for (int ni = 0; ni < 2; ni++)
-#pragma unroll
-                  for (int e = 0; e < 2; e++) {
-                    const int col = wb + ni * 8 + kq * 2 + e;
-                    if (col < q) Gr[tl[mi] * 8 + (int64_t)col * ldG] = gold[mi][ni][e] + g[mi][ni][e];
-                  }
-            }
-#pragma unroll
-            for (int mi = 0; mi < MI; mi++) {                       // the four k-lanes of a row: fixed-order butterfly
-              ssq[mi] += __shfl_xor_sync(0xffffffffu, ssq[mi], 1);
-              ssq[mi] += __shfl_xor_sync(0xffffffffu, ssq[mi], 2);
-            }
-            if (kq == 0) {
 #pragma unroll
               for (int mi = 0; mi < MI; mi++) {
-                double* Gq = Gr + tl[mi] * 8 + (int64_t)q * ldG;
-                *Gq = (j == 0 ? 0.0 : __ldcg(Gq)) + ssq[mi];
+                dmma(g[mi][0][0], g[mi][0][1], a[mi], b0);
+                dmma(g[mi][1][0], g[mi][1][1], a[mi], b1);
               }
+            }
+#pragma unroll
+            for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+              for (int ni = 0; ni < 2; ni++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                  const int col = wb + ni * 8 + kq * 2 + e;
+                  if (col < q) Gr[tl[mi] * 8 + (int64_t)col * ldG] = gold[mi][ni][e] + g[mi][ni][e];
+                }
+          }
+#pragma unroll
+          for (int mi = 0; mi < MI; mi++) {                       // the four k-lanes of a row: fixed-order butterfly
+            ssq[mi] += __shfl_xor_sync(0xffffffffu, ssq[mi], 1);
+            ssq[mi] += __shfl_xor_sync(0xffffffffu, ssq[mi], 2);
+          }
+          if (kq == 0) {
+#pragma unroll
+            for (int mi = 0; mi < MI; mi++) {
+              double* Gq = Gr + tl[mi] * 8 + (int64_t)q * ldG;
+              *Gq = (j == 0 ? 0.0 : __ldcg(Gq)) + ssq[mi];
             }
           }
         }
-        // ---- E6: publish ----
-        if (prof && tid == 0) tp4 = (long long)gtime();
-        __threadfence();
-        asm volatile("fence.proxy.async;" ::: "memory");     // the tile is re-read by other CTAs' TMA bulk copies
-        pair_bar<NW>();
-        if (tid == 0) st_release(pb->doneP + (int64_t)r * nCB + j, epoch);
-        if (prof && tid == 0) {
-          prof[0] = tp0; prof[1] = tp1; prof[2] = tp2; prof[3] = tp3; prof[4] = tp4; prof[5] = (long long)gtime();
-          prof[6] = (nchunks > kstart) ? s_tdep : tp0;
-          prof[7] = ((long long)blockIdx.x << 48) | (kwait << 1) | (is_diag ? 1 : 0);
-        }
       }
+      // ---- E6: publish ----
+      if (prof && tid == 0) tp4 = (long long)gtime();
+      __threadfence();
+      asm volatile("fence.proxy.async;" ::: "memory");     // the tile is re-read by other CTAs' TMA bulk copies
+      pair_bar<NW>();
+      if (tid == 0) st_release(pb->doneP + (int64_t)r * nCB + j, epoch);
+      if (prof && tid == 0) {
+        prof[0] = tp0; prof[1] = tp1; prof[2] = tp2; prof[3] = tp3; prof[4] = tp4; prof[5] = (long long)gtime();
+        prof[6] = (nchunks > kstart) ? s_tdep : tp0;
+        prof[7] = ((long long)blockIdx.x << 48) | (kwait << 1) | (is_diag ? 1 : 0);
+      }
+    }
     it = it0 + (nchunks - kstart);
     task_bar<NW>();
   }

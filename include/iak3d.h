@@ -189,6 +189,21 @@ IAK3D_API int iak3d_nll_terms_batch_wsum(iak3d_ctx* ctx, int32_t count, iak3d_ds
 IAK3D_API int iak3d_nll_terms_batch_wsum_multi(int32_t ndev, iak3d_ctx* const* ctxs, const int32_t* count, iak3d_ds* const* ds,
                                                const iak3d_pars* pars, const double* weight, const int32_t* group, int32_t ngroups,
                                                int32_t q, double* h_out);
+/* ---- the exchange step over NVLink peer memory (one process per GPU) -----------------------------------------------------
+ * The all-reduce of the composite-likelihood sums (compositeLikIAK3D.R:63-64) moves ~700 bytes: its cost is the latency of the
+ * collective.  Instead of a library call, every rank owns a small mailbox in device memory that its peers map through CUDA IPC;
+ * one single-CTA kernel per rank publishes its values, waits for the peers' flags and adds all mailboxes in rank order (the same
+ * bits on every rank).  iak3d_peer_create returns this rank's 64-byte IPC handle; the caller exchanges the handles of all ranks
+ * (any side channel: torch.distributed all_gather, MPI, a file) and passes them, in rank order, to iak3d_peer_connect.
+ * iak3d_peer_allreduce sums n <= max_doubles doubles in place at the DEVICE pointer d_buf (e.g. the d_out of
+ * iak3d_nll_terms_batch_wsum) on the context's stream and synchronises it.  world <= 16. */
+typedef struct iak3d_peer iak3d_peer;
+IAK3D_API int iak3d_peer_create(iak3d_ctx* ctx, int32_t rank, int32_t world, int32_t max_doubles, iak3d_peer** out, void* handle_out);
+IAK3D_API int iak3d_peer_connect(iak3d_peer* peer, const void* handles /* world x 64 bytes, rank order */);
+IAK3D_API int iak3d_peer_allreduce(iak3d_peer* peer, double* d_buf, int32_t n, double* h_out /* host copy of the sums, or NULL */,
+                                   double* us /* device time of the exchange, or NULL */);
+IAK3D_API int iak3d_peer_destroy(iak3d_peer* peer);
+
 /* bytes of device memory one more simultaneous evaluation of this dataset needs (a slot: factor buffer + tables), and the
  * device memory currently free -- for callers that size their batches (composite-likelihood gradient) */
 IAK3D_API int iak3d_dataset_slot_bytes(iak3d_ds* ds, int64_t* slot_bytes, int64_t* free_bytes);
