@@ -4,7 +4,7 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden
 CSRC      := iak3d_b200/csrc
 OUT       := iak3d_b200/lib
-OBJS      := $(OUT)/api.o $(OUT)/api_fit.o $(OUT)/tables.o $(OUT)/covbuild.o $(OUT)/chol.o $(OUT)/gemm.o $(OUT)/grad.o $(OUT)/mat.o $(OUT)/design.o $(OUT)/voronoi.o $(OUT)/peer.o
+OBJS      := $(OUT)/api.o $(OUT)/api_fit.o $(OUT)/tables.o $(OUT)/covbuild.o $(OUT)/chol.o $(OUT)/gemm.o $(OUT)/grad.o $(OUT)/mat.o $(OUT)/design.o $(OUT)/voronoi.o $(OUT)/peer.o $(OUT)/tail.o
 HDRS      := $(CSRC)/common.cuh $(CSRC)/chol_pair.cuh $(CSRC)/iak3d_math.h include/iak3d.h
 
 all: $(OUT)/libiak3d.so tests/_hostmath.so

@@ -76,6 +76,8 @@ _PROTOS = {
     "iak3d_nll_terms_batch_fetch": (C.c_int, [_vp, _dp, _dp, _ip]),
     "iak3d_nll_terms_batch_wsum": (C.c_int, [_vp, _i32, C.POINTER(_vp), C.POINTER(Pars), _dp, _ip, _i32, _vp, _dp]),
     "iak3d_nll_terms_batch_wsum_multi": (C.c_int, [_i32, C.POINTER(_vp), _ip, C.POINTER(_vp), C.POINTER(Pars), _dp, _ip, _i32, _i32, _dp]),
+    "iak3d_reml_tail": (C.c_int, [_dp, C.c_double, C.c_int64, _i32, _i32, C.c_double, C.c_double, _dp, _dp, _dp, _dp, _dp, C.POINTER(_i32)]),
+    "iak3d_nll_reml": (C.c_int, [_vp, C.POINTER(Pars), _i32, _dp, _dp, _dp, _dp, _dp, C.POINTER(_i32)]),
     "iak3d_peer_create": (C.c_int, [_vp, _i32, _i32, _i32, C.POINTER(_vp), _vp]),
     "iak3d_peer_connect": (C.c_int, [_vp, _vp]),
     "iak3d_peer_allreduce": (C.c_int, [_vp, _vp, _i32, _dp, _dp]),

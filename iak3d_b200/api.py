@@ -19,7 +19,7 @@ import math
 import numpy as np
 
 from . import _lib
-from ._lib import BAD_PARS, NOT_SPD, OK, Context, Iak3dError, Pars, default_context, dptr, f64, iptr, make_pars, spl_ptrs
+from ._lib import BAD_PARS, NOT_SPD, OK, Context, Iak3dError, Pars, default_context, dptr, f64, iptr, load, make_pars, spl_ptrs
 
 BADNLL = 9e99   # fitIAK3D.R:685
 
@@ -596,51 +596,29 @@ def reml_tail(WiAW, lndetA, n, p, useReml=True, n_for_cxd=None, n_for_lndet=None
 
 
 def reml_tail_batch(WiAW, lndetA, n, p, useReml=True, n_for_cxd=None, n_for_lndet=None, full=False):
-    """The closed-form REML / ML tail for a stack of evaluations (count x q x q, count) in one pass of batched NumPy calls:
-    the host tail of a forward-difference gradient costs as much as its device evaluations at Edgeroi size when it is
-    done one evaluation at a time.  -> nll (count,), BADNLL where the p x p system is not positive definite; with `full`
-    a dict of arrays (nll, ok, betahat, cxdhat, lndetXiAX, resiAres)."""
-    WiAW = np.asarray(WiAW, float); lndetA = np.asarray(lndetA, float)
+    """The closed-form REML / ML tail for a stack of evaluations (count x q x q, count): one call of the library's host routine
+    per evaluation (`iak3d_reml_tail`, csrc/tail.cu -- O(p^3) C++, a few microseconds; the NumPy version of round 1 cost
+    0.18 ms per evaluation, a fifth of an Edgeroi-size evaluation).  A single evaluation and the same evaluation inside a
+    batch go through the same arithmetic, so they agree bit for bit.  -> nll (count,), BADNLL where the p x p system is not
+    positive definite; with `full` a dict of arrays (nll, ok, betahat, cxdhat, lndetXiAX, resiAres)."""
+    lib = load()
+    WiAW = np.ascontiguousarray(WiAW, dtype=np.float64); lndetA = np.asarray(lndetA, float).reshape(-1)
     cnt = WiAW.shape[0]
-    nll = np.full(cnt, BADNLL)
-    out = dict(nll=nll, ok=np.zeros(cnt, bool), betahat=np.full((cnt, p, 1), np.nan), cxdhat=np.full(cnt, np.nan),
-               lndetXiAX=np.full(cnt, np.nan), resiAres=np.full(cnt, np.nan))
-    XiAX = WiAW[:, :p, :p]; XiAz = WiAW[:, :p, p:p + 1]; ziAz = WiAW[:, p, p]
-    ok = np.all(np.isfinite(WiAW.reshape(cnt, -1)), axis=1)
-    Ls = np.zeros_like(XiAX)
-    for i in np.nonzero(ok)[0]:                       # cholesky has no batched failure mode: keep the loop, it is p x p
-        try:
-            Ls[i] = np.linalg.cholesky(XiAX[i])
-        except np.linalg.LinAlgError:
-            ok[i] = False
-    idx = np.nonzero(ok)[0]
-    if idx.size:
-        d = np.diagonal(Ls[idx], axis1=1, axis2=2)
-        idx = idx[np.all(np.isfinite(d) & (d > 0), axis=1)]
-    if idx.size == 0:
-        return out if full else nll
-    L = Ls[idx]
-    d = np.diagonal(L, axis1=1, axis2=2)
-    y = np.linalg.solve(L, XiAz[idx])
-    beta = np.linalg.solve(np.transpose(L, (0, 2, 1)), y)
-    lndetXiAX = 2.0 * np.sum(np.log(d), axis=1)
-    bXz = np.sum(beta * XiAz[idx], axis=(1, 2))
-    bXXb = np.sum(beta * (XiAX[idx] @ beta), axis=(1, 2))
-    res = ziAz[idx] - 2.0 * bXz + bXXb
-    nn = n if n_for_lndet is None else n_for_lndet
-    with np.errstate(invalid="ignore", divide="ignore"):
-        if n_for_cxd is not None:
-            c = res / n_for_cxd
-        else:
-            c = res / (n - p) if useReml else res / n
-        lndetC = lndetA[idx] + nn * np.log(c)
-        lndetXiCX = lndetXiAX - p * np.log(c)
-        resiCres = np.where(c != 0, res / c, np.nan)
-        v = 0.5 * ((n - p) * math.log(2.0 * math.pi) + lndetC + lndetXiCX + resiCres) if useReml else \
-            0.5 * (n * math.log(2.0 * math.pi) + lndetC + resiCres)
-    nll[idx] = np.where(np.isfinite(v), v, BADNLL)
-    out["ok"][idx] = True; out["betahat"][idx] = beta; out["cxdhat"][idx] = c; out["lndetXiAX"][idx] = lndetXiAX; out["resiAres"][idx] = res
-    return out if full else nll
+    q = p + 1
+    nll = np.empty(cnt)
+    beta = np.full((cnt, p, 1), np.nan); cxd = np.empty(cnt); ldx = np.empty(cnt); res = np.empty(cnt); ok = np.zeros(cnt, np.int32)
+    nc = -1.0 if n_for_cxd is None else float(n_for_cxd)
+    nl = -1.0 if n_for_lndet is None else float(n_for_lndet)
+    # the routine reads the upper triangle of a column-major matrix: hand it the transposed copy of the C-ordered stack
+    Wt = np.ascontiguousarray(np.transpose(WiAW, (0, 2, 1)))
+    for k in range(cnt):
+        st = lib.iak3d_reml_tail(dptr(Wt[k]), float(lndetA[k]), int(n), int(p), 1 if useReml else 0, nc, nl, dptr(nll[k:]), dptr(beta[k]),
+                                 dptr(cxd[k:]), dptr(ldx[k:]), dptr(res[k:]), iptr(ok[k:]))
+        if st != 0:
+            raise Iak3dError("reml_tail: bad arguments")
+    if not full:
+        return nll
+    return dict(nll=nll, ok=ok.astype(bool), betahat=beta, cxdhat=cxd, lndetXiAX=ldx, resiAres=res)
 
 
 def nll_terms_batch(ctx, setups, parsList):
@@ -684,6 +662,10 @@ def nllIAK3D(pars, zData, XData, vXU=None, iU=None, modelx="matern", nud=0.5, sd
     sm.set_W(np.column_stack([XData, zData]))                      # W <- cbind(XData, zData), :757
     P = make_pars(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt)
     ctx = sm.ctx
+    if not (rtnAll or forCompLik):                                  # what an optimiser calls: one library call, device + host tail
+        v, stt = C.c_double(), C.c_int32()
+        ctx.check(ctx.lib.iak3d_nll_reml(sm.h, C.byref(P), 1 if useReml else 0, C.byref(v), None, None, None, None, C.byref(stt)))
+        return BADNLL if stt.value != OK else v.value
     lnd = C.c_double(); G = np.empty((p + 1, p + 1), order="F")
     want_iAW = forCompLik or (rtnAll and not attachBigMats)
     iAW = np.empty((n, p + 1), order="F") if want_iAW else None

@@ -460,6 +460,260 @@ __device__ void potf2_inv_la(double* __restrict__ At, int off, double* __restric
   }
 }
 
+// ---- diagonal block, warp-specialised (single-problem launches) ---------------------------------------------------------
+// The per-column critical path of a single evaluation is this routine (23 of the 35 us between two diagonal blocks at
+// n = 1200 ... 5000 with potf2_inv_la), and there most cycles were not the pivot chain but what surrounded it: two
+// block-wide barriers and three shared-memory round trips per four columns, and -- in every warp -- the panel, inverse-row
+// and trailing-update branches executed one after the other (divergence).  Here the chain is ONE warp running ONE
+// instruction stream:
+//   chain warp (warp 0): lane l owns rows l and l + 32 of the current four-column panel.  Per step: every lane factorises
+//     the 4 x 4 diagonal block redundantly (no broadcast), substitutes its own two panel rows, publishes them (final L, and
+//     transposed for the helpers), then applies this step's rank-4 update to the NEXT panel itself -- whose earlier updates
+//     the helpers deposited a step ago -- and to the next diagonal block (again redundantly in every lane).
+//   helper warps (1..7): thread <-> one 4 x 4 block (br, bc <= br) held in registers: the trailing block T(br, bc) until its
+//     column is handed to the chain warp (deposit, two steps ahead of the chain), the block Y(br, bc) of the inverse
+//     afterwards.  Both updates are the same instruction stream,  u -= P_br * Q,  Q = P_bc' or the finished row block of the
+//     inverse, selected by a pointer.
+// The chain never waits for a helper that is not at least a step ahead: arrive / sync pairs on named barriers (ids 3..6,
+// alternating by step parity), one helper-only barrier (7) between the inverse row and its use.
+constexpr int CH_LR = 0;                  // l10 l20 l30 l21 l31 l32 | r0..r3   (16 reserved)
+constexpr int CH_PT = 16;                 // this step's panel, transposed: [4][64]
+constexpr int CH_NB = 16 + 256;           // next panel column as deposited by the helpers: [64 rows][4]
+constexpr int CH_YR = 16 + 512;           // finished row block of the inverse: [4][64]
+constexpr int CH_BUF = 16 + 768;          // per step parity
+constexpr int CH_CHAIN = 2;               // chain warps
+constexpr int CH_HELPERS = (NCW - CH_CHAIN) * 32;
+
+template <int ID, int COUNT> __device__ __forceinline__ void nbar_sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
+template <int ID, int COUNT> __device__ __forceinline__ void nbar_arrive() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
+
+__device__ __forceinline__ void ld4(const double* __restrict__ p, double (&v)[4]) {       // 32-byte aligned
+  const double2 a = reinterpret_cast<const double2*>(p)[0], b = reinterpret_cast<const double2*>(p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void st4(double* __restrict__ p, const double (&v)[4]) {
+  reinterpret_cast<double2*>(p)[0] = make_double2(v[0], v[1]);
+  reinterpret_cast<double2*>(p)[1] = make_double2(v[2], v[3]);
+}
+
+#ifdef POTF2_PROF
+__device__ long long g_potf2_prof[16];
+#define PROF_T(k) do { const long long t_ = clock64(); pacc_[k] += t_ - tp_; tp_ = t_; } while (0)
+#else
+#define PROF_T(k) do { } while (0)
+#endif
+
+__device__ __forceinline__ double zero_if_less(double v, int a, int b) {     // a < b ? 0 : v, without a branch
+  double o;
+  asm volatile("{\n .reg .pred p;\n setp.lt.s32 p, %2, %3;\n selp.f64 %0, 0d0000000000000000, %1, p;\n}\n" : "=d"(o) : "d"(v), "r"(a), "r"(b));
+  return o;
+}
+
+// DBG (micro-benchmark only, wrong results): 1 no panel stores, 2 no l / r / pivot publication, 4 no update of the next diagonal
+// block, 8 no update of the next panel row, 16 helpers skip their updates, 32 helpers skip the inverse rows
+template <int DBG = 0>
+__device__ void potf2_inv_chain(double* __restrict__ At, int off, double* __restrict__ Ys, double* __restrict__ scratch,
+                                double* __restrict__ pivs /* 64 */, int tid, double* logsum_out, int32_t* status) {
+  const int warp = tid >> 5, lane = tid & 31;
+  if (warp < CH_CHAIN) {
+    // ================= chain warps =================
+    // a lone warp issues an instruction every ~3.5 cycles whatever it is: what counts below is the number of instructions on
+    // the path.  So the 64 panel rows are split over two warps (one row per lane, each warp factorising the diagonal block
+    // for itself), addresses are running pointers, and the rows of the diagonal block take the same path as every other row.
+    const int row = tid;                              // 0..63
+    double c[4], dg[10];
+    double* atp = At + AT_IDX(off + row, 0);          // own row of the tile, at the first column of the current step
+    double* ptp = scratch + CH_PT + row;              // own row in the transposed panel buffer (parity 0)
+#pragma unroll
+    for (int k = 0; k < 4; k++) c[k] = atp[k * UL];
+    dg[0] = At[AT_IDX(off + 0, 0)]; dg[1] = At[AT_IDX(off + 1, 0)]; dg[2] = At[AT_IDX(off + 2, 0)]; dg[3] = At[AT_IDX(off + 3, 0)];
+    dg[4] = At[AT_IDX(off + 1, 1)]; dg[5] = At[AT_IDX(off + 2, 1)]; dg[6] = At[AT_IDX(off + 3, 1)];
+    dg[7] = At[AT_IDX(off + 2, 2)]; dg[8] = At[AT_IDX(off + 3, 2)]; dg[9] = At[AT_IDX(off + 3, 3)];
+    int rel = row;                                    // row - 4 cb
+    double* buf = scratch;
+    int flip = CH_BUF;                                // buf of the next step = buf + flip
+#ifdef POTF2_PROF
+    long long pacc_[5] = {0, 0, 0, 0, 0};
+    long long tp_ = clock64();
+#endif
+#pragma unroll 1
+    for (int cb = 0; cb < TN / 4; cb++) {
+      // ---- 4 x 4 factor, the same in every lane (a non-positive pivot shows as NaN in pivs: checked at the end) ----
+      double l[6], r[4], pv[4];
+      pv[0] = dg[0]; r[0] = fast_rsqrt(pv[0]);
+      l[0] = dg[1] * r[0]; l[1] = dg[2] * r[0]; l[2] = dg[3] * r[0];
+      pv[1] = dg[4] - l[0] * l[0]; r[1] = fast_rsqrt(pv[1]);
+      l[3] = (dg[5] - l[1] * l[0]) * r[1]; l[4] = (dg[6] - l[2] * l[0]) * r[1];
+      pv[2] = dg[7] - l[1] * l[1] - l[3] * l[3]; r[2] = fast_rsqrt(pv[2]);
+      l[5] = (dg[8] - l[2] * l[1] - l[4] * l[3]) * r[2];
+      pv[3] = dg[9] - l[2] * l[2] - l[4] * l[4] - l[5] * l[5]; r[3] = fast_rsqrt(pv[3]);
+      PROF_T(0);
+      // ---- the next panel as the helpers left it (updates of all earlier steps applied) ----
+      const bool more = cb + 1 < TN / 4;
+      double nx[4], dn[4][4];
+      if (more) {
+        if (cb & 1) nbar_sync<6, NCW * 32>(); else nbar_sync<5, NCW * 32>();
+        PROF_T(1);
+        const double* nb = buf + CH_NB;
+        ld4(nb + row * 4, nx);
+#pragma unroll
+        for (int i = 0; i < 4; i++) ld4(nb + (4 * cb + 4 + i) * 4, dn[i]);
+      }
+      // ---- own panel row: (c0 c1 c2 c3) inv(L44)'.  A row of the diagonal block comes out as the row of L44 (the entries
+      //      right of the diagonal were computed from what lies above the diagonal of A: replaced by zeros) ----
+      blk4_subst_row(l, r, c[0], c[1], c[2], c[3]);
+      c[1] = zero_if_less(c[1], rel, 1);              // selects, not branches: the lanes must not split into five paths
+      c[2] = zero_if_less(c[2], rel, 2);
+      c[3] = zero_if_less(c[3], rel, 3);
+      if (rel >= 0 && !(DBG & 1)) {
+        double* t = ptp + (buf - scratch);
+        atp[0] = c[0]; atp[UL] = c[1]; atp[2 * UL] = c[2]; atp[3 * UL] = c[3];
+        t[0] = c[0]; t[64] = c[1]; t[128] = c[2]; t[192] = c[3];
+      }
+      atp += (cb == 7) ? (2 * UNIT - 28 * UL) : 4 * UL;            // columns 32.. live two units further
+      rel -= 4;
+      PROF_T(2);
+      if (tid == 32 && !(DBG & 2)) {                  // the second warp's first lane: its rows die last
+        double2* lr = reinterpret_cast<double2*>(buf + CH_LR);
+        lr[0] = make_double2(l[0], l[1]); lr[1] = make_double2(l[2], l[3]); lr[2] = make_double2(l[4], l[5]);
+        lr[3] = make_double2(r[0], r[1]); lr[4] = make_double2(r[2], r[3]);
+        st4(pivs + 4 * cb, pv);
+      }
+      nbar_sync<8, CH_CHAIN * 32>();                  // the panel of this step is complete (both chain warps)
+      if (cb & 1) nbar_arrive<4, NCW * 32>(); else nbar_arrive<3, NCW * 32>();
+      PROF_T(3);
+      if (more) {
+        // ---- this step's rank-4 update of the next panel (own row) and of the next diagonal block (every lane) ----
+        double pd[4][4];                              // pd[k][i] = P[4 cb + 4 + i][k]
+#pragma unroll
+        for (int k = 0; k < 4; k++) ld4(buf + CH_PT + k * 64 + 4 * cb + 4, pd[k]);
+        if (!(DBG & 4)) {
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int jj = 0; jj <= i; jj++)
+#pragma unroll
+              for (int k = 0; k < 4; k++) dn[i][jj] -= pd[k][i] * pd[k][jj];
+        }
+        dg[0] = dn[0][0]; dg[1] = dn[1][0]; dg[2] = dn[2][0]; dg[3] = dn[3][0]; dg[4] = dn[1][1]; dg[5] = dn[2][1]; dg[6] = dn[3][1];
+        dg[7] = dn[2][2]; dg[8] = dn[3][2]; dg[9] = dn[3][3];
+        if (!(DBG & 8)) {
+#pragma unroll
+          for (int jj = 0; jj < 4; jj++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) nx[jj] -= c[k] * pd[k][jj];
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) c[jj] = nx[jj];
+      }
+      buf += flip; flip = -flip;
+      PROF_T(4);
+    }
+#ifdef POTF2_PROF
+    if (tid == 32) for (int k = 0; k < 5; k++) g_potf2_prof[k] += pacc_[k];
+#endif
+  } else {
+    // ================= helper warps =================
+    const int b = tid - CH_CHAIN * 32;                // block number, row-major over the lower triangle (>= 136: no block)
+    int br = (int)((sqrtf(8.0f * (float)b + 1.0f) - 1.0f) * 0.5f);
+    while ((br + 1) * (br + 2) / 2 <= b) br++;
+    while (br * (br + 1) / 2 > b) br--;
+    const int bc = b - br * (br + 1) / 2;
+    const bool live = br < TN / 4;
+    // zeros above the block diagonal of L and of the inverse: 120 blocks, spread over the helper threads
+    for (int z = b; z < 120; z += CH_HELPERS) {
+      int zc = (int)((sqrtf(8.0f * (float)z + 1.0f) - 1.0f) * 0.5f);
+      while ((zc + 1) * (zc + 2) / 2 <= z) zc++;
+      while (zc * (zc + 1) / 2 > z) zc--;
+      const int zr = z - zc * (zc + 1) / 2;          // block (zr, zc + 1), zr <= zc: strictly above the diagonal
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) { At[AT_IDX(off + 4 * zr + i, 4 * (zc + 1) + jj)] = 0.0; Ys[(4 * (zc + 1) + jj) * LDB_S + 4 * zr + i] = 0.0; }
+    }
+    double u[4][4];
+    const bool tmode = live && bc >= 1;               // u holds the trailing block first, the block of the inverse later
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int jj = 0; jj < 4; jj++) u[i][jj] = tmode ? At[AT_IDX(off + 4 * br + i, 4 * bc + jj)] : ((br == bc && i == jj) ? 1.0 : 0.0);
+    if (live && bc == 1) {                            // column block 1 goes to the chain warp untouched
+#pragma unroll
+      for (int i = 0; i < 4; i++) st4(scratch + CH_NB + (4 * br + i) * 4, u[i]);
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) u[i][jj] = (br == bc && i == jj) ? 1.0 : 0.0;
+    }
+    nbar_arrive<5, NCW * 32>();
+#pragma unroll 1
+    for (int s = 0; s < TN / 4; s++) {
+      double* buf = scratch + (s & 1) * CH_BUF;
+      if (s & 1) nbar_sync<4, NCW * 32>(); else nbar_sync<3, NCW * 32>();
+      // ---- first what the chain warp waits for: the column it takes over next step ----
+      if (live && bc == s + 2 && !(DBG & 16)) {
+        double pr[4][4], qq[4][4];                    // pr[k][i] = P[4 br + i][k];  qq[k][jj] = P[4 bc + jj][k]
+#pragma unroll
+        for (int k = 0; k < 4; k++) { ld4(buf + CH_PT + k * 64 + 4 * br, pr[k]); ld4(buf + CH_PT + k * 64 + 4 * bc, qq[k]); }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int jj = 0; jj < 4; jj++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) u[i][jj] -= pr[k][i] * qq[k][jj];
+        double* nb = scratch + ((s + 1) & 1) * CH_BUF + CH_NB;
+#pragma unroll
+        for (int i = 0; i < 4; i++) st4(nb + (4 * br + i) * 4, u[i]);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int jj = 0; jj < 4; jj++) u[i][jj] = (br == bc && i == jj) ? 1.0 : 0.0;      // from here on: the block of the inverse
+      }
+      if (s + 2 < TN / 4) { if ((s + 1) & 1) nbar_arrive<6, NCW * 32>(); else nbar_arrive<5, NCW * 32>(); }
+      // ---- row block s of the inverse: inv(L44) times the columns of u; final ----
+      if (live && br == s && !(DBG & 32)) {
+        double l[6], r[4];
+        const double2* lr = reinterpret_cast<const double2*>(buf + CH_LR);
+        const double2 t0 = lr[0], t1 = lr[1], t2 = lr[2], t3 = lr[3], t4 = lr[4];
+        l[0] = t0.x; l[1] = t0.y; l[2] = t1.x; l[3] = t1.y; l[4] = t2.x; l[5] = t2.y; r[0] = t3.x; r[1] = t3.y; r[2] = t4.x; r[3] = t4.y;
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) blk4_subst_row(l, r, u[0][jj], u[1][jj], u[2][jj], u[3][jj]);
+#pragma unroll
+        for (int k = 0; k < 4; k++) st4(buf + CH_YR + k * 64 + 4 * bc, u[k]);
+      }
+      nbar_sync<7, CH_HELPERS>();
+      if (live && br == s && !(DBG & 32)) {           // its final place (nobody waits for these stores)
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+          double2* y2 = reinterpret_cast<double2*>(Ys + (4 * bc + jj) * LDB_S + 4 * br);
+          y2[0] = make_double2(u[0][jj], u[1][jj]); y2[1] = make_double2(u[2][jj], u[3][jj]);
+        }
+      }
+      // ---- every other block: trailing blocks right of the next column, blocks of the inverse left of this one ----
+      if (live && br > s && (bc > s + 2 || bc <= s) && !(DBG & 16)) {
+        const double* qb = buf + (bc > s ? CH_PT : CH_YR) + 4 * bc;
+        double pr[4][4], qq[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { ld4(buf + CH_PT + k * 64 + 4 * br, pr[k]); ld4(qb + k * 64, qq[k]); }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int jj = 0; jj < 4; jj++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) u[i][jj] -= pr[k][i] * qq[k][jj];
+      }
+    }
+  }
+  consumer_bar();
+  if (tid < 64) { const double pv = pivs[tid]; if (!(pv > 0.0) || isinf(pv)) atomicExch(status, 1); }
+  if (tid < 32) {   // log-determinant of the block: fixed-order tree, deterministic
+    double v = log(pivs[tid]) + log(pivs[tid + 32]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (tid == 0) *logsum_out = v;
+  }
+}
+
 // MODE: every problem of a launch has the same mode (0 factorisation, 1 panel solve against a finished factor, 2 plain
 // product).  Modes 1 and 2 have their own instantiation (no registers spent on the other epilogues: +1.2 % on the kriging
 // panels); the factorisation runs the generic body (MODE = -1, mode read from the problem) -- its specialised
@@ -641,7 +895,7 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
       int row_lo = 0;
       if (is_diag) {
         const int off = (j & 1) * TN;
-        if (LOOKAHEAD) potf2_inv_la(At, off, Ys, smem + 2 * STAGE_D, s_comm + 256, tid, pb->logsum + j, status);
+        if (LOOKAHEAD) potf2_inv_chain(At, off, Ys, smem + 2 * STAGE_D, s_comm + 256, tid, pb->logsum + j, status);
         else potf2_inv_blk4<false>(At, off, Ys, smem + 2 * STAGE_D, s_comm + 256, tid, pb->logsum + j, status);   // scratch: stage 2, drained
         double* invd = pb->invd + (int64_t)j * INVD_BLOCK;       // stored with the padded stride: one bulk copy reloads it
         for (int idx = tid; idx < INVD_BLOCK / 2; idx += NCW * 32)

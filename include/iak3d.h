@@ -160,6 +160,19 @@ IAK3D_API int iak3d_lndet_invCb(iak3d_ctx* ctx, int64_t n, const double* C, int3
  * Builds A = setCIAK3D(pars), factorises it and returns lndetA and WiAW = t(W) A^-1 W (q x q).
  * iAW (n x q, A^-1 W; fitIAK3D.R:782-808) is optional (NULL to skip the back-substitution). */
 IAK3D_API int iak3d_nll_terms(iak3d_ds* ds, const iak3d_pars* pars, double* lndetA, double* WiAW, double* iAW);
+
+/* ---- the closed-form tail == the rest of nllIAK3D (fitIAK3D.R:821-880; compositeLikIAK3D.R:191-265) -------------------------
+ * Host arithmetic, O(p^3): betahat = solve(XiAX, XiAz), resiAres, the profiled variance cxdhat = resiAres / (n - p) [REML] or
+ * / n, and nll = 0.5 ((n - p) log 2pi + lndetC + lndetXiCX + resiCres) [REML] or 0.5 (n log 2pi + lndetC + resiCres).
+ * WiAW is q x q column-major (q = p + 1), only its UPPER triangle is read (forceSymmetric, fitIAK3D.R:811).  n_for_cxd /
+ * n_for_lndet <= 0 select the defaults; the composite likelihood passes its own counts (compositeLikIAK3D.R:206-240).
+ * *ok = 0 and *nll = 9e99 (the reference's badnll) where XiAX is not positive definite.  Outputs other than nll / ok may be NULL. */
+IAK3D_API int iak3d_reml_tail(const double* WiAW, double lndetA, int64_t n, int32_t p, int32_t useReml, double n_for_cxd, double n_for_lndet,
+                              double* nll, double* betahat, double* cxdhat, double* lndetXiAX, double* resiAres, int32_t* ok);
+/* nllIAK3D(pars, ..., rtnAll = FALSE) in one call: iak3d_nll_terms on the device + the tail above.  *status = IAK3D_OK /
+ * IAK3D_NOT_SPD / IAK3D_BAD_PARS (then *nll = 9e99, fitIAK3D.R:885).  betahat (p), cxdhat, lndetA, WiAW (q*q) may be NULL. */
+IAK3D_API int iak3d_nll_reml(iak3d_ds* ds, const iak3d_pars* pars, int32_t useReml, double* nll, double* betahat, double* cxdhat,
+                             double* lndetA, double* WiAW, int32_t* status);
 /* The same for `count` independent (dataset, parameter) pairs in one launch: the composite-
  * likelihood block loop (compositeLikIAK3D.R:49-93,105-155; mcmapply over blocks) and the forward-
  * difference gradient (fitIAK3D.R:1865-1886; npar+1 evaluations).  status[i] is per evaluation;

@@ -205,6 +205,9 @@ nllIAK3D <- function(pars, zData, XData, vXU, iU, modelx, nud, sdfdType_cd1, sdf
                              sdfdType_cxd1 = sdfdType_cxd1, cmeOpt = cmeOpt, prodSum = prodSum, parBnds = parBnds, lnTfmdData = lnTfmdData)
   .Call('iak3dR_set_W', setupMats$iak3d, cbind(XData, zData))
   pv <- .iak3d_pv(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt)
+  if(!rtnAll && !forCompLik){                      # what optim() calls: one .Call, device terms + the closed-form tail in the library
+    return(.Call('iak3dR_nll_reml', setupMats$iak3d, pv, as.logical(useReml)))
+  }
   if(forCompLik || (rtnAll && !attachBigMats)){
     tmp <- .Call('iak3dR_nll_terms_iAW', setupMats$iak3d, pv)
     status <- tmp[[1]] ; lndetA <- tmp[[2]] ; WiAW <- tmp[[3]] ; iAW <- tmp[[4]]

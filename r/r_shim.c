@@ -131,6 +131,17 @@ SEXP iak3dR_nll_terms(SEXP dsp, SEXP pmat) {
   return out;
 }
 
+/* nllIAK3D(..., rtnAll = FALSE) in one call: device terms + the closed-form REML / ML tail in the library (fitIAK3D.R:730-880).
+ * Returns the value itself (9E99 where the reference returns badnll). */
+SEXP iak3dR_nll_reml(SEXP dsp, SEXP pv, SEXP useReml) {
+  iak3d_ds* ds = (iak3d_ds*)R_ExternalPtrAddr(dsp);
+  iak3d_pars P; pars_from(pv, &P);
+  double nll = 9e99; int32_t status = 0;
+  int st = iak3d_nll_reml(ds, &P, asLogical(useReml) ? 1 : 0, &nll, NULL, NULL, NULL, NULL, &status);
+  if (st < 0) error("iak3d_nll_reml: %s", iak3d_last_error(g_ctx));
+  return ScalarReal(status != 0 ? 9e99 : nll);
+}
+
 /* one evaluation that also returns iAW = A^-1 W (n x q) for rtnAll / forCompLik callers */
 SEXP iak3dR_nll_terms_iAW(SEXP dsp, SEXP pv) {
   iak3d_ds* ds = (iak3d_ds*)R_ExternalPtrAddr(dsp);
@@ -544,6 +555,7 @@ SEXP iak3dR_predict_ssre(SEXP fp, SEXP xyMap, SEXP dIMap, SEXP XMap, SEXP siteid
 
 static const R_CallMethodDef call_methods[] = {
   {"iak3dR_dataset", (DL_FUNC)&iak3dR_dataset, 3},       {"iak3dR_set_W", (DL_FUNC)&iak3dR_set_W, 2},
+  {"iak3dR_nll_reml", (DL_FUNC)&iak3dR_nll_reml, 3},
   {"iak3dR_nll_terms", (DL_FUNC)&iak3dR_nll_terms, 2},   {"iak3dR_nll_terms_iAW", (DL_FUNC)&iak3dR_nll_terms_iAW, 2},
   {"iak3dR_cov_build", (DL_FUNC)&iak3dR_cov_build, 3},   {"iak3dR_cov_cross", (DL_FUNC)&iak3dR_cov_cross, 4},
   {"iak3dR_lndet_invCb", (DL_FUNC)&iak3dR_lndet_invCb, 2}, {"iak3dR_fit", (DL_FUNC)&iak3dR_fit, 4},

@@ -87,6 +87,28 @@ def test_nll_from_unconstrained_pars_and_gradient(ctx):
     assert np.max(np.abs(g - gw)) <= 2e-2 * max(1.0, np.max(np.abs(gw)))
 
 
+def test_one_call_nll_equals_terms_plus_tail(ctx):
+    """iak3d_nll_reml (device terms + the library's host tail, what nllIAK3D calls when rtnAll = FALSE) against the rtnAll
+    path (iak3d_nll_terms, then iak3d_reml_tail from Python): same bits; betahat / cxdhat of the one-call form included."""
+    import ctypes as C
+    from iak3d_b200._lib import make_pars, dptr
+    ds = synth.make_dataset(900, 13)
+    P, modelx, types, cmeOpt = case_pars("edgeroi", False, 0.5)
+    sm = iak.setupIAK3D(ds["xData"], ds["dIData"], ctx=ctx)
+    for useReml in (True, False):
+        kw = dict(modelx=modelx, nud=0.5, sdfdType_cd1=types[0], sdfdType_cxd0=types[1], sdfdType_cxd1=types[2], cmeOpt=cmeOpt,
+                  setupMats=sm, parBnds=PARBNDS, useReml=useReml, parsBTfmd=P)
+        v = iak.nllIAK3D(None, ds["zData"], ds["XData"], **kw)
+        full = iak.nllIAK3D(None, ds["zData"], ds["XData"], rtnAll=True, **kw)
+        assert v == full["nll"]
+        p = ds["XData"].shape[1]
+        nll, cxd, st = C.c_double(), C.c_double(), C.c_int32()
+        beta = np.empty(p)
+        Ps = make_pars(P, modelx, *types, cmeOpt)
+        ctx.check(ctx.lib.iak3d_nll_reml(sm.h, C.byref(Ps), int(useReml), C.byref(nll), dptr(beta), C.byref(cxd), None, None, C.byref(st)))
+        assert st.value == 0 and nll.value == v and cxd.value == full["cxdhat"] and np.array_equal(beta, np.ravel(full["betahat"]))
+
+
 def test_failures_map_to_badnll(ctx):
     ds = synth.make_dataset(300, 5)
     P, modelx, types, cmeOpt = case_pars("matern0.5", False, 0.5)
