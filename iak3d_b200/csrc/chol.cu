@@ -141,17 +141,19 @@ __device__ __forceinline__ void solve_segment(double (&x)[4][4][2], const double
   }
 }
 
-// 1/sqrt(x) for a positive finite pivot: MUFU seed + two Newton steps (max relative error 1.24 ulp); rsqrt() from the
-// math library carries special-case handling that sits on the column-to-column dependency chain.
+// 1/sqrt(x) for a positive finite pivot: MUFU seed (relative error 9e-7) + ONE third-order step,
+//   y (1 + e/2 + 3 e^2/8),  e = 1 - x y^2   (remainder 5/16 e^3 ~ 2e-18),
+// max relative error 1.23 ulp over 2^20 inputs (scripts/micro/rsqrt_acc.cu; two Newton steps: 1.24 ulp) in four dependent
+// operations instead of six: the result sits on the column-to-column dependency chain of every diagonal block.  rsqrt() from
+// the math library carries special-case handling on top.
 __device__ __forceinline__ double fast_rsqrt(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double hx = 0.5 * x;
-  double e = fma(-hx * y, y, 0.5);      // 0.5 - 0.5 x y^2
-  y = fma(y, e, y);
-  e = fma(-hx * y, y, 0.5);
-  y = fma(y, e, y);
-  return y;                             // seed 9e-7 -> 1.2e-12 -> 1.24 ulp; a third step changes nothing (scripts/micro/rsqrt_acc.cu)
+  const double t = x * y;
+  const double e = fma(-t, y, 1.0);
+  const double w = fma(e, 0.375, 0.5);
+  const double ye = y * e;
+  return fma(ye, w, y);
 }
 
 // ---- diagonal block, 4 columns per step ------------------------------------------------------------------------------
@@ -477,10 +479,11 @@ __device__ void potf2_inv_la(double* __restrict__ At, int off, double* __restric
 // The chain never waits for a helper that is not at least a step ahead: arrive / sync pairs on named barriers (ids 3..6,
 // alternating by step parity), one helper-only barrier (7) between the inverse row and its use.
 constexpr int CH_LR = 0;                  // l10 l20 l30 l21 l31 l32 | r0..r3   (16 reserved)
-constexpr int CH_PT = 16;                 // this step's panel, transposed: [4][64]
-constexpr int CH_NB = 16 + 256;           // next panel column as deposited by the helpers: [64 rows][4]
-constexpr int CH_YR = 16 + 512;           // finished row block of the inverse: [4][64]
-constexpr int CH_BUF = 16 + 768;          // per step parity
+constexpr int CH_PT = 16;                 // this step's panel, transposed: [4][64] (conflict-free for the helpers' block loads)
+constexpr int CH_YR = 16 + 256;           // finished row block of the inverse: [4][64]
+constexpr int CH_BUF = 16 + 512;          // one of THREE such buffers per step (s mod 3): the helpers still read the previous
+                                          // step's while the chain warps write the next step's
+constexpr int CH_NB = 3 * CH_BUF;         // + parity * 256: next panel column as deposited by the helpers: [64 rows][4]
 constexpr int CH_CHAIN = 2;               // chain warps
 constexpr int CH_HELPERS = (NCW - CH_CHAIN) * 32;
 
@@ -498,9 +501,14 @@ __device__ __forceinline__ void st4(double* __restrict__ p, const double (&v)[4]
 
 #ifdef POTF2_PROF
 __device__ long long g_potf2_prof[16];
+// BAR.SYNC is "defer blocking": the warp runs on until its next memory instruction.  A probe after a barrier first reads shared
+// memory and branches on the value, so that the wait is charged to the barrier and not to whatever follows.
 #define PROF_T(k) do { const long long t_ = clock64(); pacc_[k] += t_ - tp_; tp_ = t_; } while (0)
+#define PROF_TB(k) do { unsigned x_; asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(x_) : "r"(s_u32(scratch)) : "memory"); \
+                        if (x_ == 0x7fc12345u) pacc_[k] += 1; PROF_T(k); } while (0)
 #else
 #define PROF_T(k) do { } while (0)
+#define PROF_TB(k) do { } while (0)
 #endif
 
 __device__ __forceinline__ double zero_if_less(double v, int a, int b) {     // a < b ? 0 : v, without a branch
@@ -522,16 +530,14 @@ __device__ void potf2_inv_chain(double* __restrict__ At, int off, double* __rest
     // for itself), addresses are running pointers, and the rows of the diagonal block take the same path as every other row.
     const int row = tid;                              // 0..63
     double c[4], dg[10];
-    double* atp = At + AT_IDX(off + row, 0);          // own row of the tile, at the first column of the current step
     double* ptp = scratch + CH_PT + row;              // own row in the transposed panel buffer (parity 0)
 #pragma unroll
-    for (int k = 0; k < 4; k++) c[k] = atp[k * UL];
+    for (int k = 0; k < 4; k++) c[k] = At[AT_IDX(off + row, k)];
     dg[0] = At[AT_IDX(off + 0, 0)]; dg[1] = At[AT_IDX(off + 1, 0)]; dg[2] = At[AT_IDX(off + 2, 0)]; dg[3] = At[AT_IDX(off + 3, 0)];
     dg[4] = At[AT_IDX(off + 1, 1)]; dg[5] = At[AT_IDX(off + 2, 1)]; dg[6] = At[AT_IDX(off + 3, 1)];
     dg[7] = At[AT_IDX(off + 2, 2)]; dg[8] = At[AT_IDX(off + 3, 2)]; dg[9] = At[AT_IDX(off + 3, 3)];
     int rel = row;                                    // row - 4 cb
-    double* buf = scratch;
-    int flip = CH_BUF;                                // buf of the next step = buf + flip
+    int pofs = 0;                                     // this step's buffer (offset from scratch), cycling over three
 #ifdef POTF2_PROF
     long long pacc_[5] = {0, 0, 0, 0, 0};
     long long tp_ = clock64();
@@ -553,8 +559,8 @@ __device__ void potf2_inv_chain(double* __restrict__ At, int off, double* __rest
       double nx[4], dn[4][4];
       if (more) {
         if (cb & 1) nbar_sync<6, NCW * 32>(); else nbar_sync<5, NCW * 32>();
-        PROF_T(1);
-        const double* nb = buf + CH_NB;
+        PROF_TB(1);
+        const double* nb = scratch + CH_NB + (cb & 1) * 256;
         ld4(nb + row * 4, nx);
 #pragma unroll
         for (int i = 0; i < 4; i++) ld4(nb + (4 * cb + 4 + i) * 4, dn[i]);
@@ -565,28 +571,34 @@ __device__ void potf2_inv_chain(double* __restrict__ At, int off, double* __rest
       c[1] = zero_if_less(c[1], rel, 1);              // selects, not branches: the lanes must not split into five paths
       c[2] = zero_if_less(c[2], rel, 2);
       c[3] = zero_if_less(c[3], rel, 3);
-      if (rel >= 0 && !(DBG & 1)) {
-        double* t = ptp + (buf - scratch);
-        atp[0] = c[0]; atp[UL] = c[1]; atp[2 * UL] = c[2]; atp[3 * UL] = c[3];
-        t[0] = c[0]; t[64] = c[1]; t[128] = c[2]; t[192] = c[3];
-      }
-      atp += (cb == 7) ? (2 * UNIT - 28 * UL) : 4 * UL;            // columns 32.. live two units further
+      if (rel >= 0 && !(DBG & 1)) { double* t = ptp + pofs; t[0] = c[0]; t[64] = c[1]; t[128] = c[2]; t[192] = c[3]; }   // (a helper warp copies it into the tile)
       rel -= 4;
       PROF_T(2);
       if (tid == 32 && !(DBG & 2)) {                  // the second warp's first lane: its rows die last
-        double2* lr = reinterpret_cast<double2*>(buf + CH_LR);
+        double2* lr = reinterpret_cast<double2*>(scratch + pofs + CH_LR);
         lr[0] = make_double2(l[0], l[1]); lr[1] = make_double2(l[2], l[3]); lr[2] = make_double2(l[4], l[5]);
         lr[3] = make_double2(r[0], r[1]); lr[4] = make_double2(r[2], r[3]);
         st4(pivs + 4 * cb, pv);
       }
-      nbar_sync<8, CH_CHAIN * 32>();                  // the panel of this step is complete (both chain warps)
+      // the rows of the next diagonal block belong to the first warp up to step 6, to the second from step 7 on: only the
+      // second warp ever waits for the other one's stores
+      if (cb < 7) { if (warp == 0) nbar_arrive<8, CH_CHAIN * 32>(); else nbar_sync<8, CH_CHAIN * 32>(); }
+      else __syncwarp();
       if (cb & 1) nbar_arrive<4, NCW * 32>(); else nbar_arrive<3, NCW * 32>();
       PROF_T(3);
+      if (warp == 0 && cb >= 7) {                     // the first warp's rows are finished: it only keeps the barrier counts
+#pragma unroll 1
+        for (int c2 = cb + 1; c2 < TN / 4; c2++) {
+          if (c2 + 1 < TN / 4) { if (c2 & 1) nbar_sync<6, NCW * 32>(); else nbar_sync<5, NCW * 32>(); }
+          if (c2 & 1) nbar_arrive<4, NCW * 32>(); else nbar_arrive<3, NCW * 32>();
+        }
+        break;
+      }
       if (more) {
         // ---- this step's rank-4 update of the next panel (own row) and of the next diagonal block (every lane) ----
         double pd[4][4];                              // pd[k][i] = P[4 cb + 4 + i][k]
 #pragma unroll
-        for (int k = 0; k < 4; k++) ld4(buf + CH_PT + k * 64 + 4 * cb + 4, pd[k]);
+        for (int k = 0; k < 4; k++) ld4(scratch + pofs + CH_PT + k * 64 + 4 * cb + 4, pd[k]);
         if (!(DBG & 4)) {
 #pragma unroll
           for (int i = 0; i < 4; i++)
@@ -606,7 +618,7 @@ __device__ void potf2_inv_chain(double* __restrict__ At, int off, double* __rest
 #pragma unroll
         for (int jj = 0; jj < 4; jj++) c[jj] = nx[jj];
       }
-      buf += flip; flip = -flip;
+      pofs = (pofs == 2 * CH_BUF) ? 0 : pofs + CH_BUF;
       PROF_T(4);
     }
 #ifdef POTF2_PROF
@@ -614,14 +626,20 @@ __device__ void potf2_inv_chain(double* __restrict__ At, int off, double* __rest
 #endif
   } else {
     // ================= helper warps =================
-    const int b = tid - CH_CHAIN * 32;                // block number, row-major over the lower triangle (>= 136: no block)
-    int br = (int)((sqrtf(8.0f * (float)b + 1.0f) - 1.0f) * 0.5f);
-    while ((br + 1) * (br + 2) / 2 <= b) br++;
-    while (br * (br + 1) / 2 > b) br--;
-    const int bc = b - br * (br + 1) / 2;
-    const bool live = br < TN / 4;
+    // the chain warps sit on the first two of the SM's four schedulers (warp id mod 4) and share their FP64 pipes with warps 4
+    // and 5: the long-lived blocks (late rows) go to the helper warps of the other two schedulers (2, 3, 6, 7), the first
+    // rows -- finished after three steps -- to warp 4; warp 5 holds no block (it copies the finished panels into the tile)
+    const int hw = warp == 2 ? 0 : (warp == 3 ? 1 : (warp == 6 ? 2 : (warp == 7 ? 3 : (warp == 4 ? 4 : 5))));
+    const int b = 135 - (hw * 32 + lane);             // block number, row-major over the lower triangle; < 0: no block
+    const bool live = b >= 0;
+    int br = live ? (int)((sqrtf(8.0f * (float)b + 1.0f) - 1.0f) * 0.5f) : TN / 4;
+    if (live) {
+      while ((br + 1) * (br + 2) / 2 <= b) br++;
+      while (br * (br + 1) / 2 > b) br--;
+    }
+    const int bc = live ? b - br * (br + 1) / 2 : 0;
     // zeros above the block diagonal of L and of the inverse: 120 blocks, spread over the helper threads
-    for (int z = b; z < 120; z += CH_HELPERS) {
+    for (int z = tid - CH_CHAIN * 32; z < 120; z += CH_HELPERS) {
       int zc = (int)((sqrtf(8.0f * (float)z + 1.0f) - 1.0f) * 0.5f);
       while ((zc + 1) * (zc + 2) / 2 <= z) zc++;
       while (zc * (zc + 1) / 2 > z) zc--;
@@ -637,7 +655,7 @@ __device__ void potf2_inv_chain(double* __restrict__ At, int off, double* __rest
     for (int i = 0; i < 4; i++)
 #pragma unroll
       for (int jj = 0; jj < 4; jj++) u[i][jj] = tmode ? At[AT_IDX(off + 4 * br + i, 4 * bc + jj)] : ((br == bc && i == jj) ? 1.0 : 0.0);
-    if (live && bc == 1) {                            // column block 1 goes to the chain warp untouched
+    if (live && bc == 1) {                            // column block 1 goes to the chain warps untouched
 #pragma unroll
       for (int i = 0; i < 4; i++) st4(scratch + CH_NB + (4 * br + i) * 4, u[i]);
 #pragma unroll
@@ -645,31 +663,61 @@ __device__ void potf2_inv_chain(double* __restrict__ At, int off, double* __rest
 #pragma unroll
         for (int jj = 0; jj < 4; jj++) u[i][jj] = (br == bc && i == jj) ? 1.0 : 0.0;
     }
-    nbar_arrive<5, NCW * 32>();
+    nbar_arrive<5, NCW * 32>();                       // column 1 is there
+    // One update per thread and step, one instruction stream for all of them:  u -= P_br * Q.  A trailing block takes the
+    // update of THIS step (Q = P_bc', from the panel just published); a block of the inverse takes the update of the
+    // PREVIOUS step (Q = row block s - 1 of the inverse, finished at the end of the previous step) -- the lag removes the
+    // helpers' own barrier between "finish the row block" and "use it": the next step's barrier with the chain warps orders
+    // them.  The column the chain takes over next (bc == s + 2) is handed over right after the update.
+    const int po_br = CH_PT + 4 * br, po_bc = CH_PT + 4 * bc, yo_bc = CH_YR + 4 * bc;
+#ifdef POTF2_PROF
+    long long pacc_[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tp_ = clock64();
+#endif
+    const int crow = lane;                            // warp 5: rows crow and crow + 32 of every finished panel go into the tile
 #pragma unroll 1
     for (int s = 0; s < TN / 4; s++) {
-      double* buf = scratch + (s & 1) * CH_BUF;
+      double* buf = scratch + (s % 3) * CH_BUF;
+      double* bufp = scratch + ((s + 2) % 3) * CH_BUF;
       if (s & 1) nbar_sync<4, NCW * 32>(); else nbar_sync<3, NCW * 32>();
-      // ---- first what the chain warp waits for: the column it takes over next step ----
-      if (live && bc == s + 2 && !(DBG & 16)) {
-        double pr[4][4], qq[4][4];                    // pr[k][i] = P[4 br + i][k];  qq[k][jj] = P[4 bc + jj][k]
+      PROF_TB(5);
+      const bool tupd = bc >= s + 2;                  // live implies br >= bc; column s + 1 is with the chain warps
+      const bool yupd = br >= s && bc <= s - 1;
+      if (live && (tupd || yupd) && !(DBG & 16)) {
+        const double* pb_ = (tupd ? buf : bufp) + po_br;
+        const double* qb_ = tupd ? buf + po_bc : bufp + yo_bc;
+        double pr[4][4], qq[4][4];                    // pr[k][i] = P[4 br + i][k];  qq[k][jj] = P[4 bc + jj][k] or Y[4 s - 4 + k][4 bc + jj]
 #pragma unroll
-        for (int k = 0; k < 4; k++) { ld4(buf + CH_PT + k * 64 + 4 * br, pr[k]); ld4(buf + CH_PT + k * 64 + 4 * bc, qq[k]); }
+        for (int k = 0; k < 4; k++) { ld4(pb_ + k * 64, pr[k]); ld4(qb_ + k * 64, qq[k]); }
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll
           for (int jj = 0; jj < 4; jj++)
 #pragma unroll
             for (int k = 0; k < 4; k++) u[i][jj] -= pr[k][i] * qq[k][jj];
-        double* nb = scratch + ((s + 1) & 1) * CH_BUF + CH_NB;
+        if (bc == s + 2) {                            // all earlier updates applied: the chain warps take the column over
+          double* nb = scratch + CH_NB + ((s + 1) & 1) * 256;
 #pragma unroll
-        for (int i = 0; i < 4; i++) st4(nb + (4 * br + i) * 4, u[i]);
+          for (int i = 0; i < 4; i++) st4(nb + (4 * br + i) * 4, u[i]);
 #pragma unroll
-        for (int i = 0; i < 4; i++)
+          for (int i = 0; i < 4; i++)
 #pragma unroll
-          for (int jj = 0; jj < 4; jj++) u[i][jj] = (br == bc && i == jj) ? 1.0 : 0.0;      // from here on: the block of the inverse
+            for (int jj = 0; jj < 4; jj++) u[i][jj] = (br == bc && i == jj) ? 1.0 : 0.0;      // from here on: the block of the inverse
+        }
       }
+      PROF_T(6);
       if (s + 2 < TN / 4) { if ((s + 1) & 1) nbar_arrive<6, NCW * 32>(); else nbar_arrive<5, NCW * 32>(); }
+      PROF_T(7);
+      if (warp == 5 && !(DBG & 1)) {                  // the finished panel (rows of the diagonal block included) into the tile
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          const int row = crow + 32 * q;
+          if (row >= 4 * s) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) At[AT_IDX(off + row, 4 * s + k)] = buf[CH_PT + k * 64 + row];
+          }
+        }
+      }
       // ---- row block s of the inverse: inv(L44) times the columns of u; final ----
       if (live && br == s && !(DBG & 32)) {
         double l[6], r[4];
@@ -679,30 +727,18 @@ __device__ void potf2_inv_chain(double* __restrict__ At, int off, double* __rest
 #pragma unroll
         for (int jj = 0; jj < 4; jj++) blk4_subst_row(l, r, u[0][jj], u[1][jj], u[2][jj], u[3][jj]);
 #pragma unroll
-        for (int k = 0; k < 4; k++) st4(buf + CH_YR + k * 64 + 4 * bc, u[k]);
-      }
-      nbar_sync<7, CH_HELPERS>();
-      if (live && br == s && !(DBG & 32)) {           // its final place (nobody waits for these stores)
+        for (int k = 0; k < 4; k++) st4(buf + yo_bc + k * 64, u[k]);
 #pragma unroll
         for (int jj = 0; jj < 4; jj++) {
-          double2* y2 = reinterpret_cast<double2*>(Ys + (4 * bc + jj) * LDB_S + 4 * br);
-          y2[0] = make_double2(u[0][jj], u[1][jj]); y2[1] = make_double2(u[2][jj], u[3][jj]);
+          const double col[4] = {u[0][jj], u[1][jj], u[2][jj], u[3][jj]};
+          st4(Ys + (4 * bc + jj) * LDB_S + 4 * br, col);
         }
       }
-      // ---- every other block: trailing blocks right of the next column, blocks of the inverse left of this one ----
-      if (live && br > s && (bc > s + 2 || bc <= s) && !(DBG & 16)) {
-        const double* qb = buf + (bc > s ? CH_PT : CH_YR) + 4 * bc;
-        double pr[4][4], qq[4][4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) { ld4(buf + CH_PT + k * 64 + 4 * br, pr[k]); ld4(qb + k * 64, qq[k]); }
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-          for (int jj = 0; jj < 4; jj++)
-#pragma unroll
-            for (int k = 0; k < 4; k++) u[i][jj] -= pr[k][i] * qq[k][jj];
-      }
+      PROF_T(8);
     }
+#ifdef POTF2_PROF
+    if (tid == POTF2_PROF_HELPER) for (int k = 5; k < 9; k++) g_potf2_prof[k] += pacc_[k];
+#endif
   }
   consumer_bar();
   if (tid < 64) { const double pv = pivs[tid]; if (!(pv > 0.0) || isinf(pv)) atomicExch(status, 1); }
@@ -900,16 +936,17 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
         double* invd = pb->invd + (int64_t)j * INVD_BLOCK;       // stored with the padded stride: one bulk copy reloads it
         for (int idx = tid; idx < INVD_BLOCK / 2; idx += NCW * 32)
           reinterpret_cast<double2*>(invd)[idx] = reinterpret_cast<const double2*>(Ys)[idx];
-        // L_jj: the two units (column halves) of row half off/64
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");   // later readers fetch this block with the TMA engine
+        consumer_bar();
+        if (tid == 0) st_release(pb->invdone + j, epoch);
+        // L_jj itself: the two units (column halves) of row half off/64.  Nobody reads it before the tile's own flag (E6, which
+        // fences): it is stored AFTER the inverse has been published, off the column-to-column critical path
         for (int idx = tid; idx < UNIT; idx += NCW * 32) {        // UNIT double2 = 2 units
           const int ch = idx / (UNIT / 2), w2 = idx % (UNIT / 2);
           const double2 v = reinterpret_cast<const double2*>(At + (ch * 2 + (off >> 6)) * UNIT)[w2];
           reinterpret_cast<double2*>((ch ? Pt1 : Pt0) + (off >> 6) * UNIT)[w2] = v;
         }
-        __threadfence();
-        asm volatile("fence.proxy.async;" ::: "memory");   // later readers fetch this block with the TMA engine
-        consumer_bar();
-        if (tid == 0) st_release(pb->invdone + j, epoch);
         row_lo = off + TN;
       } else {
         mbar_wait(&inv_bar, inv_phase, status, abort_flag);

@@ -1,2 +1,2 @@
 mkdir -p gpurun_out/r2u
-timeout 120 scripts/micro/potf2_bench 2>&1 | tee gpurun_out/r2u/potf2_bench.txt
+timeout 20 scripts/micro/potf2_bench_np 2>&1 | cut -c1-200 | tee gpurun_out/r2u/potf2_bench.txt

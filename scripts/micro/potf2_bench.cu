@@ -1,6 +1,11 @@
 // Micro-benchmark of potf2_inv_blk4 (chol.cu) on one CTA: cycles per call, and a breakdown by disabling parts.
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I. scripts/micro/potf2_bench.cu -o gpurun_out/potf2_bench
+#ifndef NO_POTF2_PROF
 #define POTF2_PROF 1
+#endif
+#ifndef POTF2_PROF_HELPER
+#define POTF2_PROF_HELPER 64
+#endif
 #include "../../iak3d_b200/csrc/chol.cu"
 cudaError_t iak_pool_alloc(iak3d_ctx*, void** p, size_t bytes) { return cudaMalloc(p, bytes); }   // chol.cu's host side is not used here
 void iak_pool_free(iak3d_ctx*, void* p) { cudaFree(p); }
@@ -54,7 +59,22 @@ template <int V> void run(const char* name, const std::vector<double>& A, const 
          cudaGetErrorString(e), c, c / 1965.0, c / 64.0, e1, e2, e3, fabs(ld - out[2 * n * n]));
 }
 
+#ifdef POTF2_PROF
+static void prof_reset() { long long z[16] = {0}; cudaMemcpyToSymbol(g_potf2_prof, z, sizeof(z)); }
+static void prof_print() {
+  long long h[16]; cudaMemcpyFromSymbol(h, g_potf2_prof, sizeof(h));
+  printf("   chain warp, cycles per 4-column step: barrier %.0f | early update + factor %.0f | subst + stores %.0f | publish %.0f | late update %.0f\n",
+         h[1] / 300.0, h[0] / 320.0, h[2] / 320.0, h[3] / 320.0, h[4] / 320.0);
+  printf("   helper thread %d: wait for the panel %.0f | update (+ deposit) %.0f | arrive %.0f | copy / inverse row %.0f\n", POTF2_PROF_HELPER,
+         h[5] / 320.0, h[6] / 320.0, h[7] / 320.0, h[8] / 320.0);
+}
+#else
+static void prof_reset() {}
+static void prof_print() {}
+#endif
+
 int main() {
+  setvbuf(stdout, nullptr, _IONBF, 0);
   const int n = 64;
   std::vector<double> A(n * n);
   for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) A[j * n + i] = (i == j ? 3.0 : 0.0) + 1.0 / (1.0 + abs(i - j)) + 0.3 * sin(0.37 * (i + 1) * (j + 1)) * sin(0.11 * (i - j));
@@ -65,18 +85,13 @@ int main() {
   cudaMemcpy(dA, A.data(), A.size() * 8, cudaMemcpyHostToDevice);
   run<0>("potf2_inv_blk4", A, dA, dout, dc);
   run<1>("potf2_inv_la", A, dA, dout, dc);
-  { long long z[16] = {0}; cudaMemcpyToSymbol(g_potf2_prof, z, sizeof(z)); }
-  run<2>("potf2_inv_chain", A, dA, dout, dc);
-  { long long h[16]; cudaMemcpyFromSymbol(h, g_potf2_prof, sizeof(h));
-    printf("chain warp, cycles per 4-column step (20 calls x 16 steps): factor %.0f | wait deposit %.0f | subst + stores %.0f | publish %.0f | next-panel update %.0f\n",
-           h[0] / 320.0, h[1] / 300.0, h[2] / 320.0, h[3] / 320.0, h[4] / 320.0); }
+  prof_reset(); run<2>("potf2_inv_chain", A, dA, dout, dc); prof_print();
+  prof_reset(); run<148>("chain: helpers idle", A, dA, dout, dc); prof_print();
   run<101>("chain: no panel stores", A, dA, dout, dc);
   run<102>("chain: no lr publish", A, dA, dout, dc);
   run<104>("chain: no dn update", A, dA, dout, dc);
   run<108>("chain: no nx update", A, dA, dout, dc);
   run<116>("chain: helpers no updates", A, dA, dout, dc);
   run<132>("chain: helpers no inverse", A, dA, dout, dc);
-  run<148>("chain: helpers idle", A, dA, dout, dc);
-  run<163>("chain: all off", A, dA, dout, dc);
   return 0;
 }
