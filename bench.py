@@ -130,7 +130,7 @@ def fd_candidates(pars, step_no, delta=1e-6):
 def run_s5(args, rank, local_rank, world, comm):
     import ctypes as C
     import iak3d_b200 as iak
-    from iak3d_b200 import api
+    from iak3d_b200 import api, synth
     from iak3d_b200._lib import Pars, make_pars, dptr, iptr
 
     n = args.n
@@ -203,6 +203,31 @@ def run_s5(args, rank, local_rank, world, comm):
         ctx.check(lib.iak3d_nll_terms_batch_fetch(ctx.h, dptr(lnd), dptr(G), iptr(st)))
     single_ms = ctx.timer_stop() / reps
 
+    # ---- the Edgeroi-sized call (BASELINE configs[0]: n ~ 1200): what optim() pays per function evaluation ----
+    dsE = synth.make_dataset(1450, synth.SEEDS["E"])
+    keepE = dsE["prof"] < dsE["prof"].max() - 59                       # 60 hold-out profiles, getEdgeroiData.R:87
+    smE = api.setupIAK3D(dsE["xData"][keepE], dsE["dIData"][keepE], ctx=ctx)
+    PE, mxE, tyE, cmE = synth.default_pars("edgeroi")
+    kwE = dict(modelx=mxE, nud=0.5, sdfdType_cd1=tyE[0], sdfdType_cxd0=tyE[1], sdfdType_cxd1=tyE[2], cmeOpt=cmE, setupMats=smE, parBnds=PARBNDS,
+               useReml=True)
+    zE, XE = dsE["zData"][keepE], dsE["XData"][keepE]
+    for k in range(3):
+        api.nllIAK3D(None, zE, XE, parsBTfmd=PE, **kwE)
+    stageE = np.zeros(4)
+    ctx.sync(); t0 = time.perf_counter()
+    for k in range(50):
+        PEk = dict(PE); PEk["ax"] = PE["ax"] * (1.0 + 1e-3 * k)
+        vE = api.nllIAK3D(None, zE, XE, parsBTfmd=PEk, **kwE)
+        stageE += np.array(ctx.last_stage_ms()[0])
+    edgeroi_ms = 1e3 * (time.perf_counter() - t0) / 50
+    stageE /= 50
+    assert np.isfinite(vE) and vE < 1e90
+    edgeroi = dict(n=int(keepE.sum()), nll_call_wall_ms=edgeroi_ms, device_ms=float(stageE.sum()),
+                   stage_ms=dict(tables=stageE[0], cov_build=stageE[1], factorise=stageE[2], finish=stageE[3]),
+                   what="nllIAK3D(pars, ...) through the host mirror at Edgeroi size: one library call (iak3d_nll_reml: device terms + "
+                        "REML tail in C++); 19 block columns, each a warp-specialised 64 x 64 diagonal factorisation on the critical path")
+    smE.close()
+
     # ---- the same gradient by the analytic pass (iak3d_nll_grad; informational, not part of `value`) ----
     kwg = dict(modelx=modelx, nud=0.5, sdfdType_cd1=types[0], sdfdType_cxd0=types[1], sdfdType_cxd1=types[2], cmeOpt=cmeOpt, prodSum=True,
                setupMats=sm, parBnds=PARBNDS, useReml=True)
@@ -238,7 +263,7 @@ def run_s5(args, rank, local_rank, world, comm):
         metric=METRIC, value=value, unit="evals/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
         config=s5_config(n, p, sm.nxU, sm.ndIU, modelx, types, cmeOpt, nb, world),
-        single_eval_ms=single_ms, single_eval_per_s=1e3 / single_ms, gradient_wall_ms=grad_ms, fp64_peaks_tflops=peaks,
+        single_eval_ms=single_ms, single_eval_per_s=1e3 / single_ms, edgeroi_sized=edgeroi, gradient_wall_ms=grad_ms, fp64_peaks_tflops=peaks,
         stage_ms=dict(tables=stage[0], cov_build=stage[1], factorise=stage[2], finish=stage[3]),
         roofline=dict(kernel="tile_pair_kernel<0> (tile Cholesky + bordered solves, FP64 DMMA; two half-size CTAs per SM, chol_pair.cuh)",
                       bound="tensor", achieved=tf,
