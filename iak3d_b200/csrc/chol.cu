@@ -1285,6 +1285,8 @@ int chol_configure(iak3d_ctx* ctx) {
   if (e && e[0] == '3' && ctx->engine == 2) ctx->engine = 3;   // tests: single-problem launches through the pair engine too
   const char* w = getenv("IAK3D_PAIR_WIDTH");
   if (w && atoi(w) > 0) ctx->pair_min_width = atoi(w);
+  const char* dg = getenv("IAK3D_DIAG");
+  if (dg) ctx->diag_chain = atoi(dg) != 0;
   return 0;
 }
 
@@ -1313,7 +1315,9 @@ int launch_tile_tasks(iak3d_ctx* ctx, const ProblemDesc* d_problems, const int4*
   }
   int grid = ctx->sm_count;
   if (grid > ntasks) grid = ntasks;
-  if (mode == 0 && latency_bound) tile_task_kernel<-1, 1><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(d_problems, d_tasks, ntasks, d_ticket);
+  // factorisations on the full-size CTA always take the warp-specialised diagonal block (LOOKAHEAD = 1; IAK3D_DIAG=0: the
+  // four-column routine of the batched engines, kept for comparison -- same bits)
+  if (mode == 0 && (latency_bound || ctx->diag_chain)) tile_task_kernel<-1, 1><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(d_problems, d_tasks, ntasks, d_ticket);
   else if (mode == 0) tile_task_kernel<-1, 0><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(d_problems, d_tasks, ntasks, d_ticket);
   else if (mode == 1) tile_task_kernel<1, 0><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(d_problems, d_tasks, ntasks, d_ticket);
   else tile_task_kernel<2, 0><<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(d_problems, d_tasks, ntasks, d_ticket);

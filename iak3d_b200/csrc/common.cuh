@@ -45,6 +45,7 @@ struct iak3d_ctx {
   int64_t launches = 0;
   int pair_warps = 4;        // MMA warps per CTA of the pair engine
   int pair_min_width = 148;  // tasks per dependency step from which a throughput launch uses the CTA-pair engine
+  bool diag_chain = true;    // full-size CTAs: warp-specialised diagonal blocks in every factorisation launch (IAK3D_DIAG=0: only single-problem ones)
   int engine = 1;            // tile engine of throughput launches: 1 = one CTA per SM (chol.cu), 2 = CTA pairs (chol_pair.cuh)
   // scratch
   void* flush_buf = nullptr; size_t flush_bytes = 0;
