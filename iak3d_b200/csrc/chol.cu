@@ -929,17 +929,25 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
       if (prof && tid == 0) tp2 = (long long)gtime();
       // ---- E2: diagonal block or fetch of the inverted diagonal block ----
       int row_lo = 0;
+      bool defer_inv = false;
       if (is_diag) {
         const int off = (j & 1) * TN;
         if (LOOKAHEAD) potf2_inv_chain(At, off, Ys, smem + 2 * STAGE_D, s_comm + 256, tid, pb->logsum + j, status);
         else potf2_inv_blk4<false>(At, off, Ys, smem + 2 * STAGE_D, s_comm + 256, tid, pb->logsum + j, status);   // scratch: stage 2, drained
-        double* invd = pb->invd + (int64_t)j * INVD_BLOCK;       // stored with the padded stride: one bulk copy reloads it
-        for (int idx = tid; idx < INVD_BLOCK / 2; idx += NCW * 32)
-          reinterpret_cast<double2*>(invd)[idx] = reinterpret_cast<const double2*>(Ys)[idx];
-        __threadfence();
-        asm volatile("fence.proxy.async;" ::: "memory");   // later readers fetch this block with the TMA engine
-        consumer_bar();
-        if (tid == 0) st_release(pb->invdone + j, epoch);
+        // Even columns: the next diagonal block waits for THIS task's lower half (solved below from the inverse in shared
+        // memory) and the column's other tiles have a whole diagonal block of slack: the inverse goes out after the tile has
+        // been published (end of the task).  Odd columns: the next diagonal block waits for another CTA's tile, which waits
+        // for the inverse: it goes out first.
+        defer_inv = LOOKAHEAD && off == 0;
+        if (!defer_inv) {
+          double* invd = pb->invd + (int64_t)j * INVD_BLOCK;     // stored with the padded stride: one bulk copy reloads it
+          for (int idx = tid; idx < INVD_BLOCK / 2; idx += NCW * 32)
+            reinterpret_cast<double2*>(invd)[idx] = reinterpret_cast<const double2*>(Ys)[idx];
+          __threadfence();
+          asm volatile("fence.proxy.async;" ::: "memory");   // later readers fetch this block with the TMA engine
+          consumer_bar();
+          if (tid == 0) st_release(pb->invdone + j, epoch);
+        }
         // L_jj itself: the two units (column halves) of row half off/64.  Nobody reads it before the tile's own flag (E6, which
         // fences): it is stored AFTER the inverse has been published, off the column-to-column critical path
         for (int idx = tid; idx < UNIT; idx += NCW * 32) {        // UNIT double2 = 2 units
@@ -1069,6 +1077,15 @@ tile_task_kernel(const ProblemDesc* __restrict__ probs, const int4* __restrict__
       asm volatile("fence.proxy.async;" ::: "memory");     // the tile is re-read by other CTAs' TMA bulk copies
       consumer_bar();
       if (tid == 0) st_release(pb->doneP + (int64_t)r * nCB + j, epoch);
+      if (defer_inv) {                                           // (Ys is untouched until the next task's operands arrive)
+        double* invd = pb->invd + (int64_t)j * INVD_BLOCK;
+        for (int idx = tid; idx < INVD_BLOCK / 2; idx += NCW * 32)
+          reinterpret_cast<double2*>(invd)[idx] = reinterpret_cast<const double2*>(Ys)[idx];
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        consumer_bar();
+        if (tid == 0) st_release(pb->invdone + j, epoch);
+      }
       if (prof && tid == 0) {
         prof[0] = tp0; prof[1] = tp1; prof[2] = tp2; prof[3] = tp3; prof[4] = tp4; prof[5] = (long long)gtime();
         prof[6] = (nchunks > kstart) ? s_tdep : tp0;

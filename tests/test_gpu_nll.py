@@ -29,6 +29,19 @@ def test_lndetANDinvCb_vs_lapack(ctx, n, nrhs):
     assert scaled_err(got["invCb"], want_x) <= TOL
 
 
+@pytest.mark.parametrize("scale,cond", [(1e-100, 1e4), (1e100, 1e4), (1.0, 1e10), (3.7e-9, 1e8)])
+def test_lndetANDinvCb_scales_and_conditioning(ctx, scale, cond):
+    """The diagonal-block routine takes 1/sqrt(pivot) from a MUFU seed + one third-order step: pivots far from 1 and
+    ill-conditioned blocks must come out like LAPACK's (relative to the conditioning)."""
+    n = 333
+    A = _spd(n, 17, cond=cond) * scale; A = 0.5 * (A + A.T)
+    b = np.random.default_rng(5).standard_normal((n, 3))
+    got = iak.lndetANDinvCb(A, b, ctx=ctx)
+    want_lnd, want_x = orc.lndetANDinvCb(A, b)
+    assert abs(got["lndetC"] - want_lnd) <= 1e-9 * max(1.0, abs(want_lnd))
+    assert scaled_err(got["invCb"], want_x) <= max(TOL, 1e-15 * cond * 10)
+
+
 def test_lndetANDinvCb_not_spd_returns_na(ctx):
     A = _spd(90, 4); A[40, 40] = -1.0
     got = iak.lndetANDinvCb(A, np.ones((90, 1)), ctx=ctx)
