@@ -34,6 +34,16 @@ class Pars(C.Structure):
     ]
 
 
+class Model(C.Structure):
+    """struct iak3d_model (include/iak3d.h): the switches and bounds readParsIAK3D needs."""
+    _fields_ = [
+        ("modelx", C.c_int32), ("cmeOpt", C.c_int32), ("prodSum", C.c_int32), ("lnTfmdData", C.c_int32),
+        ("sdfdType", C.c_int32 * 3), ("reserved_", C.c_int32), ("nud", C.c_double),
+        ("axBnds", C.c_double * 2), ("nuxBnds", C.c_double * 2), ("adBnds", C.c_double * 2), ("tau2Bnds", C.c_double * 2),
+        ("sxd1Bnds", C.c_double * 2), ("maxd", C.c_double),
+    ]
+
+
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
 _vp = C.c_void_p
@@ -76,6 +86,9 @@ _PROTOS = {
     "iak3d_nll_terms_batch_fetch": (C.c_int, [_vp, _dp, _dp, _ip]),
     "iak3d_nll_terms_batch_wsum": (C.c_int, [_vp, _i32, C.POINTER(_vp), C.POINTER(Pars), _dp, _ip, _i32, _vp, _dp]),
     "iak3d_nll_terms_batch_wsum_multi": (C.c_int, [_i32, C.POINTER(_vp), _ip, C.POINTER(_vp), C.POINTER(Pars), _dp, _ip, _i32, _i32, _dp]),
+    "iak3d_read_pars": (C.c_int, [C.POINTER(Model), _dp, _i32, C.POINTER(Pars)]),
+    "iak3d_nll_vector": (C.c_int, [_vp, C.POINTER(Model), _dp, _i32, _i32, _dp]),
+    "iak3d_gradnll_fd": (C.c_int, [_vp, C.POINTER(Model), _dp, _i32, C.c_double, _i32, _dp, _dp]),
     "iak3d_reml_tail": (C.c_int, [_dp, C.c_double, C.c_int64, _i32, _i32, C.c_double, C.c_double, _dp, _dp, _dp, _dp, _dp, C.POINTER(_i32)]),
     "iak3d_nll_reml": (C.c_int, [_vp, C.POINTER(Pars), _i32, _dp, _dp, _dp, _dp, _dp, C.POINTER(_i32)]),
     "iak3d_peer_create": (C.c_int, [_vp, _i32, _i32, _i32, C.POINTER(_vp), _vp]),
@@ -191,6 +204,22 @@ def make_pars(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cme
         for e in range(cs.size):
             P.cssre[e] = float(cs[e])
     return P
+
+
+def make_model(modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds, lnTfmdData=False):
+    """The arguments of readParsIAK3D other than the vector -> struct iak3d_model."""
+    M = Model()
+    M.modelx = MODELX[modelx]
+    M.cmeOpt, M.prodSum, M.lnTfmdData = int(cmeOpt), 1 if prodSum else 0, 1 if lnTfmdData else 0
+    for i, t in enumerate((sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1)):
+        M.sdfdType[i] = int(t)
+    M.nud = float(nud)
+    nan2 = (float("nan"), float("nan"))
+    for name in ("axBnds", "nuxBnds", "adBnds", "tau2Bnds", "sxd1Bnds"):
+        lo, hi = parBnds.get(name, nan2)
+        getattr(M, name)[0], getattr(M, name)[1] = float(lo), float(hi)
+    M.maxd = float(parBnds.get("maxd", float("nan")))
+    return M
 
 
 def spl_ptrs(mats):

@@ -19,7 +19,7 @@ import math
 import numpy as np
 
 from . import _lib
-from ._lib import BAD_PARS, NOT_SPD, OK, Context, Iak3dError, Pars, default_context, dptr, f64, iptr, load, make_pars, spl_ptrs
+from ._lib import BAD_PARS, NOT_SPD, OK, Context, Iak3dError, Pars, default_context, dptr, f64, iptr, load, make_model, make_pars, spl_ptrs
 
 BADNLL = 9e99   # fitIAK3D.R:685
 
@@ -649,6 +649,15 @@ def nllIAK3D(pars, zData, XData, vXU=None, iU=None, modelx="matern", nud=0.5, sd
     zData = np.asarray(zData, float).reshape(-1)
     XData = np.asarray(XData, float).reshape(zData.size, -1)
     n, p = XData.shape
+    if parsBTfmd is None and not (lnTfmdData or rtnAll or forCompLik):
+        # what an optimiser calls: the vector goes to the library as it is (iak3d_nll_vector: readParsIAK3D, device terms and
+        # the closed-form tail natively -- one call, no interpreter work per evaluation beyond this function)
+        sm.set_W(np.column_stack([XData, zData]))
+        M = make_model(modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds)
+        pv = np.ascontiguousarray(pars, dtype=np.float64).reshape(-1)
+        v = C.c_double()
+        sm.ctx.check(sm.ctx.lib.iak3d_nll_vector(sm.h, C.byref(M), dptr(pv), pv.size, 1 if useReml else 0, C.byref(v)))
+        return v.value
     if parsBTfmd is None:
         parsBTfmd = readParsIAK3D(pars, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds,
                                   lnTfmdData=lnTfmdData)
@@ -746,6 +755,14 @@ def gradnllIAK3D(pars, zData, XData, vXU=None, iU=None, modelx="matern", nud=0.5
     n, p = XData.shape
     sm.set_W(np.column_stack([XData, zData]))
     npar = pars.size
+    if analytic == "auto":            # measured on B200: the pass pays from n ~ 4000 on (1.7x at 5000, 2.8x at 20000)
+        analytic = n >= 4000 and getattr(sm, "nssre", 0) == 0      # site-specific random effects: forward differences
+    if not analytic:
+        # forward differences: npar + 1 evaluations in one batched launch, transform and tails in the library (iak3d_gradnll_fd)
+        M = make_model(modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds)
+        g = np.empty(npar); v0 = C.c_double()
+        sm.ctx.check(sm.ctx.lib.iak3d_gradnll_fd(sm.h, C.byref(M), dptr(pars), npar, float(delta), 1 if useReml else 0, dptr(g), C.byref(v0)))
+        return (g, v0.value) if rtn_nll else g
     cand = [pars.copy()]
     for i in range(npar):
         v = pars.copy(); v[i] += delta
@@ -754,8 +771,6 @@ def gradnllIAK3D(pars, zData, XData, vXU=None, iU=None, modelx="matern", nud=0.5
     for v in cand:
         pb = readParsIAK3D(v, modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds)
         structs.append(make_pars(pb, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt))
-    if analytic == "auto":            # measured on B200: the pass pays from n ~ 4000 on (1.7x at 5000, 2.8x at 20000)
-        analytic = n >= 4000 and getattr(sm, "nssre", 0) == 0      # site-specific random effects: forward differences
     if analytic:
         parr = (Pars * len(cand))(*structs)
         dl = f64(np.full(npar, float(delta)))

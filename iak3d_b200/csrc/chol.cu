@@ -298,173 +298,9 @@ __device__ void potf2_inv_blk4(double* __restrict__ At, int off, double* __restr
   }
 }
 
-// ---- diagonal block with look-ahead (single-problem launches: the per-column critical path is the whole run time) -------
-// As potf2_inv_blk4, but the serial part -- the 4 x 4 factor of the NEXT diagonal block, four dependent rsqrt chains --
-// runs in thread 0 (whose own rows are finished after the first step) while every other thread applies the rank-4 update of
-// the current step: the owner of the next diagonal block takes its update early, straight from the panel its warp
-// neighbour has just written, and hands the block over through shared memory.  40.0k -> 36.7k cycles per block.  Its
-// larger body costs the K-loop registers (spills), so batched launches keep potf2_inv_blk4.
-constexpr int LA_L = 0;                   // l10 l20 l30 l21 l31 l32 | r0..r3 | l00..l33 (16 reserved)
-constexpr int LA_P = 16;                  // panel: [64 rows][4]
-constexpr int LA_Y = 16 + 256;            // inverse block row: [4][64]
-constexpr int LA_D = 16 + 256 + 256;      // lower triangle of the next diagonal block after this step's update (10, 16 reserved)
-constexpr int LA_BUF = 16 + 256 + 256 + 16;
-
-__device__ __forceinline__ void la_factor(const double (&a)[10], int cb, double* __restrict__ buf, double* __restrict__ pivs, bool& bad) {
-  double l[6], r[4], pv[4];
-  pv[0] = a[0]; r[0] = fast_rsqrt(pv[0]);
-  l[0] = a[1] * r[0]; l[1] = a[2] * r[0]; l[2] = a[3] * r[0];
-  pv[1] = a[4] - l[0] * l[0]; r[1] = fast_rsqrt(pv[1]);
-  l[3] = (a[5] - l[1] * l[0]) * r[1]; l[4] = (a[6] - l[2] * l[0]) * r[1];
-  pv[2] = a[7] - l[1] * l[1] - l[3] * l[3]; r[2] = fast_rsqrt(pv[2]);
-  l[5] = (a[8] - l[2] * l[1] - l[4] * l[3]) * r[2];
-  pv[3] = a[9] - l[2] * l[2] - l[4] * l[4] - l[5] * l[5]; r[3] = fast_rsqrt(pv[3]);
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    if (!(pv[k] > 0.0) || isinf(pv[k])) bad = true;
-    pivs[4 * cb + k] = pv[k];
-    buf[LA_L + 6 + k] = r[k];
-    buf[LA_L + 10 + k] = pv[k] * r[k];
-  }
-#pragma unroll
-  for (int k = 0; k < 6; k++) buf[LA_L + k] = l[k];
-}
-
-__device__ __forceinline__ void la_load_rows(const double* __restrict__ src4, double (&out)[4][4]) {   // four rows of four doubles, 32-byte aligned
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const double2* s2 = reinterpret_cast<const double2*>(src4 + i * 4);
-    const double2 lo = s2[0], hi = s2[1];
-    out[i][0] = lo.x; out[i][1] = lo.y; out[i][2] = hi.x; out[i][3] = hi.y;
-  }
-}
-
-__device__ void potf2_inv_la(double* __restrict__ At, int off, double* __restrict__ Ys, double* __restrict__ scratch,
-                             double* __restrict__ pivs /* 64 */, int tid, double* logsum_out, int32_t* status) {
-  const int br = tid >> 4, bc = tid & 15;
-  const bool live = (bc <= br);
-  double d[4][4], y[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int jj = 0; jj < 4; jj++) {
-      d[i][jj] = live ? At[AT_IDX(off + 4 * br + i, 4 * bc + jj)] : 0.0;
-      y[i][jj] = (br == bc && i == jj) ? 1.0 : 0.0;
-    }
-  bool bad = false;
-  if (tid == 0) {
-    const double a[10] = {d[0][0], d[1][0], d[2][0], d[3][0], d[1][1], d[2][1], d[3][1], d[2][2], d[3][2], d[3][3]};
-    la_factor(a, 0, scratch, pivs, bad);
-  }
-#pragma unroll 1
-  for (int cb = 0; cb < TN / 4; cb++) {
-    double* buf = scratch + (cb & 1) * LA_BUF;
-    consumer_bar();                                     // the factor of block cb is in buf
-    if (live && (bc == cb || br == cb)) {
-      double l[6], r[4];
-#pragma unroll
-      for (int k = 0; k < 6; k++) l[k] = buf[LA_L + k];
-#pragma unroll
-      for (int k = 0; k < 4; k++) r[k] = buf[LA_L + 6 + k];
-      if (br == cb && bc == cb) {       // owner of the diagonal block: take L44; inv(L44) by substitution on the identity
-        d[0][0] = buf[LA_L + 10]; d[0][1] = 0.0; d[0][2] = 0.0; d[0][3] = 0.0;
-        d[1][0] = l[0]; d[1][1] = buf[LA_L + 11]; d[1][2] = 0.0; d[1][3] = 0.0;
-        d[2][0] = l[1]; d[2][1] = l[3]; d[2][2] = buf[LA_L + 12]; d[2][3] = 0.0;
-        d[3][0] = l[2]; d[3][1] = l[4]; d[3][2] = l[5]; d[3][3] = buf[LA_L + 13];
-#pragma unroll
-        for (int jj = 0; jj < 4; jj++) {
-          blk4_subst_row(l, r, y[0][jj], y[1][jj], y[2][jj], y[3][jj]);
-#pragma unroll
-          for (int k = 0; k < 4; k++) buf[LA_Y + k * 64 + 4 * cb + jj] = y[k][jj];
-        }
-      } else if (bc == cb) {            // panel block below the diagonal block
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          blk4_subst_row(l, r, d[i][0], d[i][1], d[i][2], d[i][3]);
-#pragma unroll
-          for (int k = 0; k < 4; k++) buf[LA_P + (4 * br + i) * 4 + k] = d[i][k];
-        }
-      } else {                          // block row cb of the inverse, left of the diagonal
-#pragma unroll
-        for (int jj = 0; jj < 4; jj++) {
-          blk4_subst_row(l, r, y[0][jj], y[1][jj], y[2][jj], y[3][jj]);
-#pragma unroll
-          for (int k = 0; k < 4; k++) buf[LA_Y + k * 64 + 4 * bc + jj] = y[k][jj];
-        }
-      }
-    }
-    __syncwarp();
-    const bool next_owner = (br == cb + 1) && (bc == cb + 1);      // its panel block was written by the lane before it
-    if (next_owner) {
-      double pr[4][4];
-      la_load_rows(buf + LA_P + 4 * br * 4, pr);
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int jj = 0; jj <= i; jj++)
-#pragma unroll
-          for (int k = 0; k < 4; k++) d[i][jj] -= pr[i][k] * pr[jj][k];
-      buf[LA_D + 0] = d[0][0]; buf[LA_D + 1] = d[1][0]; buf[LA_D + 2] = d[2][0]; buf[LA_D + 3] = d[3][0];
-      buf[LA_D + 4] = d[1][1]; buf[LA_D + 5] = d[2][1]; buf[LA_D + 6] = d[3][1];
-      buf[LA_D + 7] = d[2][2]; buf[LA_D + 8] = d[3][2]; buf[LA_D + 9] = d[3][3];
-    }
-    consumer_bar();                                     // panel, inverse row and the next diagonal block are in buf
-    if (tid == 0 && cb + 1 < TN / 4) {
-      double a[10];
-#pragma unroll
-      for (int k = 0; k < 10; k++) a[k] = buf[LA_D + k];
-      la_factor(a, cb + 1, scratch + ((cb + 1) & 1) * LA_BUF, pivs, bad);
-    }
-    if (live && br > cb && !next_owner) {
-      double pr[4][4];
-      la_load_rows(buf + LA_P + 4 * br * 4, pr);
-      if (bc > cb) {        // trailing block: d -= P_br P_bc'
-        double pc[4][4];
-        la_load_rows(buf + LA_P + 4 * bc * 4, pc);
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-          for (int jj = 0; jj < 4; jj++)
-#pragma unroll
-            for (int k = 0; k < 4; k++) d[i][jj] -= pr[i][k] * pc[jj][k];
-      } else {              // inverse block (br, bc <= cb): y -= P_br Y(cb, bc)
-        double yb[4][4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const double2* s2 = reinterpret_cast<const double2*>(buf + LA_Y + k * 64 + 4 * bc);
-          const double2 lo = s2[0], hi = s2[1];
-          yb[k][0] = lo.x; yb[k][1] = lo.y; yb[k][2] = hi.x; yb[k][3] = hi.y;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-          for (int jj = 0; jj < 4; jj++)
-#pragma unroll
-            for (int k = 0; k < 4; k++) y[i][jj] -= pr[i][k] * yb[k][jj];
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int jj = 0; jj < 4; jj++) {
-      const int r = 4 * br + i, cc = 4 * bc + jj;
-      At[AT_IDX(off + r, cc)] = (live && r >= cc) ? d[i][jj] : 0.0;
-      Ys[cc * LDB_S + r] = (live && r >= cc) ? y[i][jj] : 0.0;
-    }
-  if (bad) atomicExch(status, 1);
-  consumer_bar();
-  if (tid < 32) {
-    double v = log(pivs[tid]) + log(pivs[tid + 32]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (tid == 0) *logsum_out = v;
-  }
-}
-
 // ---- diagonal block, warp-specialised (single-problem launches) ---------------------------------------------------------
 // The per-column critical path of a single evaluation is this routine (23 of the 35 us between two diagonal blocks at
-// n = 1200 ... 5000 with potf2_inv_la), and there most cycles were not the pivot chain but what surrounded it: two
+// n = 1200 ... 5000 with round 1's look-ahead variant), and there most cycles were not the pivot chain but what surrounded it: two
 // block-wide barriers and three shared-memory round trips per four columns, and -- in every warp -- the panel, inverse-row
 // and trailing-update branches executed one after the other (divergence).  Here the chain is ONE warp running ONE
 // instruction stream:

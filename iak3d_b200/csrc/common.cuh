@@ -243,7 +243,7 @@ struct ProblemDesc {
 int chol_configure(iak3d_ctx* ctx);
 int launch_tile_tasks(iak3d_ctx* ctx, const ProblemDesc* d_problems, const int4* d_tasks, int32_t ntasks, int32_t* d_ticket /* 2 ints */,
                       int mode /* the mode of every problem of the launch */,
-                      int latency_bound = 0 /* one factorisation alone: use the look-ahead diagonal-block kernel */,
+                      int latency_bound = 0 /* one factorisation alone: never the CTA-pair engine (the column-to-column path is what counts) */,
                       int width = 0 /* independent tasks per dependency step (column of a factorisation, row chains of a panel,
                                        all tiles of a product): selects the CTA-pair engine for wide launches */);
 int launch_finish(iak3d_ctx* ctx, const ProblemDesc* d_problems, int32_t count, double* d_results, int32_t stride);

@@ -169,6 +169,29 @@ IAK3D_API int iak3d_nll_terms(iak3d_ds* ds, const iak3d_pars* pars, double* lnde
  * *ok = 0 and *nll = 9e99 (the reference's badnll) where XiAX is not positive definite.  Outputs other than nll / ok may be NULL. */
 IAK3D_API int iak3d_reml_tail(const double* WiAW, double lndetA, int64_t n, int32_t p, int32_t useReml, double n_for_cxd, double n_for_lndet,
                               double* nll, double* betahat, double* cxdhat, double* lndetXiAX, double* resiAres, int32_t* ok);
+/* ---- the optimiser's callbacks, natively ---------------------------------------------------------------------------------
+ * The model switches and parameter bounds that readParsIAK3D needs (fitIAK3D.R:1332-1417; parBnds: setInitsIAK3D.R). */
+typedef struct iak3d_model {
+  int32_t modelx;          /* IAK3D_MODELX_* : 0 nugget, 1 spherical, 2 matern, 3 wendland */
+  int32_t cmeOpt, prodSum, lnTfmdData;
+  int32_t sdfdType[3];     /* cd1, cxd0, cxd1 */
+  int32_t reserved_;
+  double nud;
+  double axBnds[2], nuxBnds[2], adBnds[2], tau2Bnds[2], sxd1Bnds[2];
+  double maxd;
+} iak3d_model;
+/* readParsIAK3D: unconstrained vector -> parsBTfmd, in the reference's consumption order: ax [, nux unless spherical], ad,
+ * [cx0, cx1 if prodSum], [cd1 unless sdfdType_cd1 == -9], cxd1 (logit; cxd0 = 1 - cxd1) or (cxd0, cxd1) if lnTfmdData, the sd-function
+ * parameters of the three components, [cme if cmeOpt == 1], then exp() of whatever is left = cssre.  IAK3D_ERR_ARG when the
+ * vector is too short or an option is unknown. */
+IAK3D_API int iak3d_read_pars(const iak3d_model* model, const double* pars, int32_t npar, iak3d_pars* out);
+/* nllIAK3D(pars, ...) for the optimiser: transform + device terms + tail; 9e99 where the reference returns badnll. */
+IAK3D_API int iak3d_nll_vector(iak3d_ds* ds, const iak3d_model* model, const double* pars, int32_t npar, int32_t useReml, double* nll);
+/* gradnllIAK3D (fitIAK3D.R:1776-1911): npar + 1 evaluations in one batched launch, forward differences with the reference's
+ * failure conventions (:1812-1813).  nll0 (may be NULL) <- the value at pars. */
+IAK3D_API int iak3d_gradnll_fd(iak3d_ds* ds, const iak3d_model* model, const double* pars, int32_t npar, double delta, int32_t useReml,
+                               double* grad, double* nll0);
+
 /* nllIAK3D(pars, ..., rtnAll = FALSE) in one call: iak3d_nll_terms on the device + the tail above.  *status = IAK3D_OK /
  * IAK3D_NOT_SPD / IAK3D_BAD_PARS (then *nll = 9e99, fitIAK3D.R:885).  betahat (p), cxdhat, lndetA, WiAW (q*q) may be NULL. */
 IAK3D_API int iak3d_nll_reml(iak3d_ds* ds, const iak3d_pars* pars, int32_t useReml, double* nll, double* betahat, double* cxdhat,

@@ -16,6 +16,13 @@
 .iak3d_dbl <- function(x){ x <- as.matrix(x) ; storage.mode(x) <- 'double' ; x }
 
 .iak3d_maxspl <- 12   # IAK3D_MAX_SPL
+### the arguments of readParsIAK3D other than the vector, as the numeric vector r_shim.c's model_from() reads
+.iak3d_model <- function(modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds, lnTfmdData = FALSE){
+  b <- function(nm){ v <- parBnds[[nm]] ; if(is.null(v)) c(NaN, NaN) else as.numeric(v)[1:2] }
+  as.numeric(c(.iak3d_modelx[[modelx]], cmeOpt, as.integer(prodSum), as.integer(lnTfmdData), sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, nud,
+               b('axBnds'), b('nuxBnds'), b('adBnds'), b('tau2Bnds'), b('sxd1Bnds'), if(is.null(parBnds$maxd)) NaN else parBnds$maxd))
+}
+
 .iak3d_pv <- function(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, quirk_scale = 1){
   tau <- function(v, t){ if(t == -1){ as.numeric(v)[1:2] }else{ c(0, 0) } }
   spl <- function(v, t){ out <- numeric(.iak3d_maxspl) ; if(t > 0){ out[seq(t)] <- as.numeric(v)[seq(t)] } ; out }
@@ -201,13 +208,15 @@ nllIAK3D <- function(pars, zData, XData, vXU, iU, modelx, nud, sdfdType_cd1, sdf
                           setupMats, parBnds, rtnAll, attachBigMats))
   }
   XData <- .iak3d_dbl(XData) ; zData <- as.numeric(zData) ; n <- length(zData) ; p <- ncol(XData)
+  if(!rtnAll && !forCompLik){                      # what optim() calls: the vector goes to the library as it is (one .Call)
+    .Call('iak3dR_set_W', setupMats$iak3d, cbind(XData, zData))
+    return(.Call('iak3dR_nll_vector', setupMats$iak3d,
+                 .iak3d_model(modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds), as.numeric(pars), as.logical(useReml)))
+  }
   parsBTfmd <- readParsIAK3D(pars = pars, modelx = modelx, nud = nud, sdfdType_cd1 = sdfdType_cd1, sdfdType_cxd0 = sdfdType_cxd0,
                              sdfdType_cxd1 = sdfdType_cxd1, cmeOpt = cmeOpt, prodSum = prodSum, parBnds = parBnds, lnTfmdData = lnTfmdData)
   .Call('iak3dR_set_W', setupMats$iak3d, cbind(XData, zData))
   pv <- .iak3d_pv(parsBTfmd, modelx, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt)
-  if(!rtnAll && !forCompLik){                      # what optim() calls: one .Call, device terms + the closed-form tail in the library
-    return(.Call('iak3dR_nll_reml', setupMats$iak3d, pv, as.logical(useReml)))
-  }
   if(forCompLik || (rtnAll && !attachBigMats)){
     tmp <- .Call('iak3dR_nll_terms_iAW', setupMats$iak3d, pv)
     status <- tmp[[1]] ; lndetA <- tmp[[2]] ; WiAW <- tmp[[3]] ; iAW <- tmp[[4]]
@@ -249,6 +258,10 @@ gradnllIAK3D <- function(pars, zData, XData, vXU, iU, modelx, nud, sdfdType_cd1,
                          setupMats, parBnds, useReml, lnTfmdData, ...){
   XData <- .iak3d_dbl(XData) ; zData <- as.numeric(zData) ; n <- length(zData) ; p <- ncol(XData) ; delta <- 1E-6
   .Call('iak3dR_set_W', setupMats$iak3d, cbind(XData, zData))
+  if(!lnTfmdData){                                 # transform, npar + 1 evaluations in one launch, tails, differences: one .Call
+    return(.Call('iak3dR_gradnll_fd', setupMats$iak3d,
+                 .iak3d_model(modelx, nud, sdfdType_cd1, sdfdType_cxd0, sdfdType_cxd1, cmeOpt, prodSum, parBnds), as.numeric(pars), delta, as.logical(useReml))[[1]])
+  }
   cand <- cbind(pars, pars + delta * diag(length(pars)))
   pm <- apply(cand, 2, function(v){
     .iak3d_pv(readParsIAK3D(pars = v, modelx = modelx, nud = nud, sdfdType_cd1 = sdfdType_cd1, sdfdType_cxd0 = sdfdType_cxd0,

@@ -142,6 +142,51 @@ SEXP iak3dR_nll_reml(SEXP dsp, SEXP pv, SEXP useReml) {
   return ScalarReal(status != 0 ? 9e99 : nll);
 }
 
+/* the switches and bounds readParsIAK3D needs, as the numeric vector .iak3d_model() builds (r/iak3d_cuda.R):
+ * modelx, cmeOpt, prodSum, lnTfmdData, sdfdType x 3, nud, axBnds, nuxBnds, adBnds, tau2Bnds, sxd1Bnds (2 each), maxd */
+#define IAK3D_MV_LEN 19
+static void model_from(SEXP mv, iak3d_model* M) {
+  need_real(mv, "model vector");
+  if (LENGTH(mv) != IAK3D_MV_LEN) error("iak3d: model vector must have %d entries", IAK3D_MV_LEN);
+  const double* v = REAL(mv);
+  memset(M, 0, sizeof(*M));
+  M->modelx = (int32_t)v[0]; M->cmeOpt = (int32_t)v[1]; M->prodSum = (int32_t)v[2]; M->lnTfmdData = (int32_t)v[3];
+  for (int c = 0; c < 3; c++) M->sdfdType[c] = (int32_t)v[4 + c];
+  M->nud = v[7];
+  for (int e = 0; e < 2; e++) {
+    M->axBnds[e] = v[8 + e]; M->nuxBnds[e] = v[10 + e]; M->adBnds[e] = v[12 + e]; M->tau2Bnds[e] = v[14 + e]; M->sxd1Bnds[e] = v[16 + e];
+  }
+  M->maxd = v[18];
+}
+
+/* nllIAK3D(pars, ...) as optim() calls it: the unconstrained vector in, the value out (readParsIAK3D, device terms and the tail
+ * inside the library; fitIAK3D.R:670-949 with rtnAll = FALSE) */
+SEXP iak3dR_nll_vector(SEXP dsp, SEXP mv, SEXP pars, SEXP useReml) {
+  iak3d_ds* ds = (iak3d_ds*)R_ExternalPtrAddr(dsp);
+  iak3d_model M; model_from(mv, &M);
+  need_real(pars, "pars");
+  double nll = 9e99;
+  int st = iak3d_nll_vector(ds, &M, REAL(pars), LENGTH(pars), asLogical(useReml) ? 1 : 0, &nll);
+  if (st < 0) error("iak3d_nll_vector: %s", iak3d_last_error(g_ctx));
+  return ScalarReal(nll);
+}
+
+/* gradnllIAK3D (fitIAK3D.R:1776-1911): forward differences, npar + 1 evaluations in one launch.  Returns list(grad, nll0). */
+SEXP iak3dR_gradnll_fd(SEXP dsp, SEXP mv, SEXP pars, SEXP delta, SEXP useReml) {
+  iak3d_ds* ds = (iak3d_ds*)R_ExternalPtrAddr(dsp);
+  iak3d_model M; model_from(mv, &M);
+  need_real(pars, "pars");
+  const int npar = LENGTH(pars);
+  SEXP g = PROTECT(allocVector(REALSXP, npar));
+  double nll0 = 9e99;
+  int st = iak3d_gradnll_fd(ds, &M, REAL(pars), npar, asReal(delta), asLogical(useReml) ? 1 : 0, REAL(g), &nll0);
+  if (st < 0) error("iak3d_gradnll_fd: %s", iak3d_last_error(g_ctx));
+  SEXP out = PROTECT(allocVector(VECSXP, 2));
+  SET_VECTOR_ELT(out, 0, g); SET_VECTOR_ELT(out, 1, ScalarReal(nll0));
+  UNPROTECT(2);
+  return out;
+}
+
 /* one evaluation that also returns iAW = A^-1 W (n x q) for rtnAll / forCompLik callers */
 SEXP iak3dR_nll_terms_iAW(SEXP dsp, SEXP pv) {
   iak3d_ds* ds = (iak3d_ds*)R_ExternalPtrAddr(dsp);
@@ -556,6 +601,7 @@ SEXP iak3dR_predict_ssre(SEXP fp, SEXP xyMap, SEXP dIMap, SEXP XMap, SEXP siteid
 static const R_CallMethodDef call_methods[] = {
   {"iak3dR_dataset", (DL_FUNC)&iak3dR_dataset, 3},       {"iak3dR_set_W", (DL_FUNC)&iak3dR_set_W, 2},
   {"iak3dR_nll_reml", (DL_FUNC)&iak3dR_nll_reml, 3},
+  {"iak3dR_nll_vector", (DL_FUNC)&iak3dR_nll_vector, 4}, {"iak3dR_gradnll_fd", (DL_FUNC)&iak3dR_gradnll_fd, 5},
   {"iak3dR_nll_terms", (DL_FUNC)&iak3dR_nll_terms, 2},   {"iak3dR_nll_terms_iAW", (DL_FUNC)&iak3dR_nll_terms_iAW, 2},
   {"iak3dR_cov_build", (DL_FUNC)&iak3dR_cov_build, 3},   {"iak3dR_cov_cross", (DL_FUNC)&iak3dR_cov_cross, 4},
   {"iak3dR_lndet_invCb", (DL_FUNC)&iak3dR_lndet_invCb, 2}, {"iak3dR_fit", (DL_FUNC)&iak3dR_fit, 4},

@@ -25,7 +25,6 @@ template <int V> __global__ void __launch_bounds__(NTHREADS, 1) bench_kernel(con
     const long long t0 = clock64();
     double ls;
     if (V == 0) potf2_inv_blk4<false>(At, 0, Ys, smem + 2 * STAGE_D, s_comm + 256, tid, &ls, status);
-    else if (V == 1) potf2_inv_la(At, 0, Ys, smem + 2 * STAGE_D, s_comm + 256, tid, &ls, status);
     else potf2_inv_chain<(V >= 100 ? V - 100 : 0)>(At, 0, Ys, smem + 2 * STAGE_D, s_comm + 256, tid, &ls, status);
     consumer_bar();
     total += clock64() - t0;
@@ -84,7 +83,6 @@ int main() {
   cudaMalloc(&dA, A.size() * 8); cudaMalloc(&dout, (2 * n * n + 1) * 8); cudaMalloc(&dc, 8);
   cudaMemcpy(dA, A.data(), A.size() * 8, cudaMemcpyHostToDevice);
   run<0>("potf2_inv_blk4", A, dA, dout, dc);
-  run<1>("potf2_inv_la", A, dA, dout, dc);
   prof_reset(); run<2>("potf2_inv_chain", A, dA, dout, dc); prof_print();
   prof_reset(); run<148>("chain: helpers idle", A, dA, dout, dc); prof_print();
   run<101>("chain: no panel stores", A, dA, dout, dc);
