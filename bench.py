@@ -222,10 +222,27 @@ def run_s5(args, rank, local_rank, world, comm):
     edgeroi_ms = 1e3 * (time.perf_counter() - t0) / 50
     stageE /= 50
     assert np.isfinite(vE) and vE < 1e90
-    edgeroi = dict(n=int(keepE.sum()), nll_call_wall_ms=edgeroi_ms, device_ms=float(stageE.sum()),
+    parsE = np.array([float(api.logitab(PE["ax"], *PARBNDS["axBnds"])), float(api.logitab(PE["ad"], *PARBNDS["adBnds"])), np.log(PE["cx0"]),
+                      np.log(PE["cx1"]), float(api.logitab(PE["cxd1"], *PARBNDS["sxd1Bnds"])), np.log(PE["cme"])])
+    kwV = {k: v for k, v in kwE.items()}
+    for k in range(3):
+        api.nllIAK3D(parsE, zE, XE, prodSum=True, **kwV); api.gradnllIAK3D(parsE, zE, XE, prodSum=True, **kwV)
+    ctx.sync(); t0 = time.perf_counter()
+    for k in range(50):
+        api.nllIAK3D(parsE * (1.0 + 1e-4 * k), zE, XE, prodSum=True, **kwV)
+    vec_ms = 1e3 * (time.perf_counter() - t0) / 50
+    ctx.sync(); t0 = time.perf_counter()
+    for k in range(20):
+        gE = api.gradnllIAK3D(parsE * (1.0 + 1e-4 * k), zE, XE, prodSum=True, **kwV)
+    gradE_ms = 1e3 * (time.perf_counter() - t0) / 20
+    assert np.all(np.isfinite(gE))
+    edgeroi = dict(n=int(keepE.sum()), nll_call_wall_ms=edgeroi_ms, nll_vector_call_wall_ms=vec_ms, gradient_call_wall_ms=gradE_ms,
+                   gradient_evals=int(parsE.size + 1), device_ms=float(stageE.sum()),
                    stage_ms=dict(tables=stageE[0], cov_build=stageE[1], factorise=stageE[2], finish=stageE[3]),
-                   what="nllIAK3D(pars, ...) through the host mirror at Edgeroi size: one library call (iak3d_nll_reml: device terms + "
-                        "REML tail in C++); 19 block columns, each a warp-specialised 64 x 64 diagonal factorisation on the critical path")
+                   what="the optimiser's callbacks through the host mirror at Edgeroi size: nll_call = nllIAK3D(parsBTfmd given; "
+                        "iak3d_nll_reml), nll_vector_call = nllIAK3D(pars) (iak3d_nll_vector: transform + device terms + REML tail in one "
+                        "library call), gradient_call = gradnllIAK3D (iak3d_gradnll_fd: 7 evaluations in one launch); 19 block columns, each "
+                        "a warp-specialised 64 x 64 diagonal factorisation on the critical path")
     smE.close()
 
     # ---- the same gradient by the analytic pass (iak3d_nll_grad; informational, not part of `value`) ----
