@@ -86,6 +86,7 @@ _PROTOS = {
     "iak3d_nll_terms_batch_fetch": (C.c_int, [_vp, _dp, _dp, _ip]),
     "iak3d_nll_terms_batch_wsum": (C.c_int, [_vp, _i32, C.POINTER(_vp), C.POINTER(Pars), _dp, _ip, _i32, _vp, _dp]),
     "iak3d_nll_terms_batch_wsum_multi": (C.c_int, [_i32, C.POINTER(_vp), _ip, C.POINTER(_vp), C.POINTER(Pars), _dp, _ip, _i32, _i32, _dp]),
+    "iak3d_dataset_same_W": (C.c_int, [_vp, _dp, _i32, C.POINTER(_i32)]),
     "iak3d_read_pars": (C.c_int, [C.POINTER(Model), _dp, _i32, C.POINTER(Pars)]),
     "iak3d_nll_vector": (C.c_int, [_vp, C.POINTER(Model), _dp, _i32, _i32, _dp]),
     "iak3d_gradnll_fd": (C.c_int, [_vp, C.POINTER(Model), _dp, _i32, C.c_double, _i32, _dp, _dp]),

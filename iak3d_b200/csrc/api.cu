@@ -349,7 +349,17 @@ extern "C" int iak3d_dataset_set_W(iak3d_ds* ds, const double* W, int32_t q) {
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     memcpy(ds->h_W, W, (size_t)ds->n * q * sizeof(double));
     CUDA_TRY(ctx, cudaMemcpyAsync(ds->d_W, ds->h_W, (size_t)ds->n * q * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ds->w_set = true;
   }
+  return IAK3D_OK;
+}
+
+// W unchanged since the last iak3d_dataset_set_W?  (optim() passes the same XData / zData to every callback: the R glue asks
+// before it uploads n x q doubles again; bit-wise comparison against the pinned host copy.)
+extern "C" int iak3d_dataset_same_W(iak3d_ds* ds, const double* W, int32_t q, int32_t* same) {
+  if (!ds || !same) return IAK3D_ERR_ARG;
+  *same = (q == ds->q && q > 0 && W != nullptr && ds->h_W != nullptr && ds->w_set &&
+           memcmp(ds->h_W, W, (size_t)ds->n * q * sizeof(double)) == 0) ? 1 : 0;
   return IAK3D_OK;
 }
 

@@ -91,6 +91,7 @@ struct iak3d_ds {
   int32_t nssre = 0;                     // site-specific random effects: columns of d_Xs, site id of every row
   int32_t* d_sid = nullptr; double* d_Xs = nullptr;
   double* h_W = nullptr;                 // n x q column-major copy in PINNED host memory: staging of the H2D copy
+  bool w_set = false;                    // h_W holds what the device holds
   int32_t *d_xid = nullptr, *d_did = nullptr;
   double *d_xU = nullptr, *d_dIU = nullptr;   // column-major nxU x 2 / ndIU x 2
   double* d_W = nullptr;                  // n x q column-major

@@ -90,6 +90,9 @@ IAK3D_API int iak3d_dataset_create(iak3d_ctx* ctx, int64_t n, const double* xy, 
                          const double* W, int32_t q, iak3d_ds** out);
 IAK3D_API int iak3d_dataset_destroy(iak3d_ds* ds);
 IAK3D_API int iak3d_dataset_set_W(iak3d_ds* ds, const double* W, int32_t q);
+/* *same = 1 when W equals, bit for bit, what the last iak3d_dataset_set_W stored (optim() passes the same data to every
+ * callback; the R glue asks before uploading again) */
+IAK3D_API int iak3d_dataset_same_W(iak3d_ds* ds, const double* W, int32_t q, int32_t* same);
 IAK3D_API int iak3d_dataset_info(iak3d_ds* ds, int64_t* n, int64_t* nxU, int64_t* ndIU, int32_t* q);
 /* 0-based ids of each row's unique location / unique depth interval (Kx, Kd as id vectors) */
 IAK3D_API int iak3d_dataset_ids(iak3d_ds* ds, int32_t* xid, int32_t* did);

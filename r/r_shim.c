@@ -78,6 +78,11 @@ SEXP iak3dR_dataset(SEXP xy, SEXP dI, SEXP W) {
 
 SEXP iak3dR_set_W(SEXP dsp, SEXP W) {
   need_real(W, "W");
+  int64_t n = 0;
+  iak3d_dataset_info((iak3d_ds*)R_ExternalPtrAddr(dsp), &n, NULL, NULL, NULL);
+  if ((int64_t)nrows(W) != n) error("iak3d: W must have the dataset's %d rows", (int)n);
+  int32_t same = 0;                                   /* optim() passes the same data to every callback: upload once */
+  if (iak3d_dataset_same_W((iak3d_ds*)R_ExternalPtrAddr(dsp), REAL(W), ncols(W), &same) == IAK3D_OK && same) return R_NilValue;
   int st = iak3d_dataset_set_W((iak3d_ds*)R_ExternalPtrAddr(dsp), REAL(W), ncols(W));
   if (st != IAK3D_OK) error("iak3d_dataset_set_W: %s", iak3d_last_error(g_ctx));
   return R_NilValue;
