@@ -226,7 +226,7 @@ extern "C" int iak3d_ctx_destroy(iak3d_ctx* ctx) {
     delete b;
   }
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
-  cudaFree(ctx->d_fbjobs);
+  cudaFree(ctx->d_fbjobs); cudaFree(ctx->d_tabjobs); if (ctx->h_tabjobs) cudaFreeHost(ctx->h_tabjobs);
   cudaFree(ctx->d_prof);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   for (int i = 0; i < 5; i++) cudaEventDestroy(ctx->evs[i]);
@@ -480,7 +480,9 @@ struct TableCache {
 TableCache* iak_table_cache_new() { return new TableCache(); }
 void iak_table_cache_free(TableCache* c) { delete c; }
 
-int iak_square_tables(iak3d_ctx* ctx, const iak3d_ds* ds, const EvalPlan& pl, Slot* s, CovArgs* a, TableCache* cache = nullptr) {
+int iak_square_tables(iak3d_ctx* ctx, const iak3d_ds* ds, const EvalPlan& pl, Slot* s, CovArgs* a, TableCache* cache = nullptr,
+                      TableQueue* tq = nullptr /* batches: queue the plain tables instead of launching them (flush_table_queue) */) {
+  if (pl.approx) tq = nullptr;         // the spline-sd tables are scaled from a source table right here: launch in order
   const int64_t nd = ds->ndIU, nx = ds->nxU;
   double* const avbase = s->d_phid + (size_t)NTAB_BUF * nd * nd;
   for (int k = 0; k < 3; k++) { a->T[k] = nullptr; a->av[k] = nullptr; }
@@ -492,8 +494,12 @@ int iak_square_tables(iak3d_ctx* ctx, const iak3d_ds* ds, const EvalPlan& pl, Sl
     const double* hit = cache ? cache->find(ds, 1, key, avout) : nullptr;
     if (hit != nullptr) { *out = hit; return 0; }
     double* T = s->d_phid + (size_t)buf * nd * nd;
-    const int st = launch_iacov_table(ctx, P, ds->d_dIU, nd, ds->d_dIU, nd, T, avbase + (size_t)buf * nd);
-    if (st != 0) return st;
+    if (tq != nullptr) {
+      if (nd > 0) tq->ia.push_back(IaTabJob{P, ds->d_dIU, nd, T, avbase + (size_t)buf * nd});
+    } else {
+      const int st = launch_iacov_table(ctx, P, ds->d_dIU, nd, ds->d_dIU, nd, T, avbase + (size_t)buf * nd);
+      if (st != 0) return st;
+    }
     *out = T; *avout = avbase + (size_t)buf * nd;
     if (cache) cache->add(ds, 1, key, T, *avout);
     return 0;
@@ -535,8 +541,12 @@ int iak_square_tables(iak3d_ctx* ctx, const iak3d_ds* ds, const EvalPlan& pl, Sl
     if (hit != nullptr) {
       a->phix = hit;
     } else {
-      const int st = launch_phix_table(ctx, pl.H, ds->d_xU, nx, ds->d_xU, nx, s->d_phix, nullptr);
-      if (st != 0) return st;
+      if (tq != nullptr) {
+        if (nx > 0) tq->hx.push_back(HxTabJob{pl.H, ds->d_xU, nx, s->d_phix});
+      } else {
+        const int st = launch_phix_table(ctx, pl.H, ds->d_xU, nx, ds->d_xU, nx, s->d_phix, nullptr);
+        if (st != 0) return st;
+      }
       a->phix = s->d_phix;
       if (cache) cache->add(ds, 2, key, s->d_phix);
     }
@@ -1053,11 +1063,15 @@ extern "C" int iak3d_nll_terms_batch_enqueue(iak3d_ctx* ctx, int32_t count, iak3
   CUDA_TRY(ctx, cudaEventRecord(ctx->evs[0], ctx->stream));
   std::vector<CovArgs> cargs((size_t)count);
   TableCache cache;
+  TableQueue tq;                                  // the plain tables of all problems: one launch per kind (tables.cu)
+  TableQueue* const tqp = (count > 16 && !ctx->no_table_queue) ? &tq : nullptr;   // small batches: nothing to gain, one sync to lose
   for (int i = 0; i < count; i++) {
     if (!live[i]) continue;
-    st = iak_square_tables(ctx, dss[i], plans[i], b->slots[i], &cargs[i], &cache);
+    st = iak_square_tables(ctx, dss[i], plans[i], b->slots[i], &cargs[i], &cache, tqp);
     if (st != 0) return st;
   }
+  st = flush_table_queue(ctx, tqp);
+  if (st != 0) return st;
   CUDA_TRY(ctx, cudaEventRecord(ctx->evs[1], ctx->stream));
   std::vector<FactorBuildJob> jobs;
   jobs.reserve((size_t)count);

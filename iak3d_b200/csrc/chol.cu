@@ -1138,6 +1138,8 @@ int chol_configure(iak3d_ctx* ctx) {
   if (e && e[0] == '3' && ctx->engine == 2) ctx->engine = 3;   // tests: single-problem launches through the pair engine too
   const char* w = getenv("IAK3D_PAIR_WIDTH");
   if (w && atoi(w) > 0) ctx->pair_min_width = atoi(w);
+  const char* tqe = getenv("IAK3D_TABLE_QUEUE");
+  if (tqe) ctx->no_table_queue = atoi(tqe) == 0;
   const char* dg = getenv("IAK3D_DIAG");
   if (dg) ctx->diag_chain = atoi(dg) != 0;
   return 0;

@@ -45,6 +45,7 @@ struct iak3d_ctx {
   int64_t launches = 0;
   int pair_warps = 4;        // MMA warps per CTA of the pair engine
   int pair_min_width = 148;  // tasks per dependency step from which a throughput launch uses the CTA-pair engine
+  bool no_table_queue = false;  // IAK3D_TABLE_QUEUE=0: one launch per table, as before (comparison)
   bool diag_chain = true;    // full-size CTAs: warp-specialised diagonal blocks in every factorisation launch (IAK3D_DIAG=0: only single-problem ones)
   int engine = 1;            // tile engine of throughput launches: 1 = one CTA per SM (chol.cu), 2 = CTA pairs (chol_pair.cuh)
   // scratch
@@ -55,6 +56,7 @@ struct iak3d_ctx {
   double last_chol_flops = 0, last_cov_bytes = 0;
   bool stage_events_valid = false;
   void* d_fbjobs = nullptr; size_t fbjobs_cap = 0;     // device copy of the covariance-build jobs of one launch
+  void* d_tabjobs = nullptr; void* h_tabjobs = nullptr; size_t tabjobs_cap = 0;   // queued table jobs of one batch (device / pinned)
   long long* d_prof = nullptr; int64_t prof_cap = 0; int32_t prof_ntasks = 0; const int4* d_prof_tasks = nullptr;   // IAK3D_PROF=1 diagnostics
 };
 
@@ -143,6 +145,11 @@ void iak_pool_free(iak3d_ctx* ctx, void* p);
 cudaError_t iak_malloc(iak3d_ctx* ctx, void** p, size_t bytes);
 
 // ---- table kernels (tables.cu) ----------------------------------------------------------------
+// square tables of many problems, queued on the host and run as one launch per kind (tables.cu: flush_table_queue)
+struct IaTabJob { IaPrm P; const double* dI; int64_t n; double* out; double* av; };
+struct HxTabJob { HxPrm H; const double* x; int64_t n; double* out; };
+struct TableQueue { std::vector<IaTabJob> ia; std::vector<HxTabJob> hx; };
+int flush_table_queue(iak3d_ctx* ctx, TableQueue* tq);
 int launch_iacov_table(iak3d_ctx* ctx, const IaPrm& P, const double* d_dI1, int64_t n1, const double* d_dI2,
                        int64_t n2, double* d_out /* n1 x n2 col-major: out[j*n1+i] */, double* d_avvar1);
 int launch_phix_table(iak3d_ctx* ctx, const HxPrm& H, const double* d_x1, int64_t n1, const double* d_x2, int64_t n2,

@@ -136,6 +136,89 @@ int launch_phix_table(iak3d_ctx* ctx, const HxPrm& H, const double* d_x1, int64_
   return 0;
 }
 
+// ---- the square tables of MANY problems in one launch each ------------------------------------------------------------------
+// A composite-likelihood evaluation builds one depth table and one horizontal table per block pair: 286 pairs = 572 launches of
+// 5-10 us kernels, each alone too small for the machine and separated by launch gaps (6.5 ms of a 229 ms evaluation).  The jobs
+// are queued on the host (TableQueue, common.cuh) and run as two launches, blockIdx.y = job.  Same arithmetic per entry as the
+// one-job kernels above (same device functions, same -fmad=false translation unit): same bits.
+__global__ void iacov_table_batch_kernel(const IaTabJob* __restrict__ jobs) {
+  const IaTabJob& jb = jobs[blockIdx.y];
+  const int64_t n1 = jb.n, total = n1 * n1;
+  const double* __restrict__ dI = jb.dI;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = idx % n1, j = idx / n1;
+    jb.out[idx] = iak_avcov(dI[i], dI[n1 + i], dI[j], dI[n1 + j], &jb.P);
+    if (jb.av != nullptr && j == 0) jb.av[i] = iak_avvar(dI[i], dI[n1 + i], &jb.P);
+  }
+}
+
+__global__ void phix_table_batch_kernel(const HxTabJob* __restrict__ jobs) {
+  __shared__ double s_rt[4 * IAK_BK_NRT];
+  const HxTabJob& jb = jobs[blockIdx.y];
+  const HxPrm H = jb.H;
+  const bool bessel = (H.modelx == 2 && H.half == 0);
+  if (bessel) {
+    for (int i = 1 + threadIdx.x; i < IAK_BK_NRT; i += blockDim.x) iak_besselk_table(H.nu, s_rt, i);
+    __syncthreads();
+  }
+  const double* rt = bessel ? s_rt : nullptr;
+  const int64_t n1 = jb.n, total = n1 * n1;
+  const double* __restrict__ x = jb.x;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = idx % n1, j = idx / n1;
+    if (i < j) continue;                          // the lower triangle is mirrored (same arithmetic, same bits)
+    const double dx = x[i] - x[j], dy = x[n1 + i] - x[n1 + j];
+    double D = 0.0;
+    D = D + dx * dx;
+    D = D + dy * dy;
+    D = sqrt(D);
+    const double v = iak_phix(D, &H, rt);
+    jb.out[idx] = v;
+    jb.out[i * n1 + j] = v;
+  }
+}
+
+int flush_table_queue(iak3d_ctx* ctx, TableQueue* tq) {
+  if (!tq) return 0;
+  const size_t na = tq->ia.size(), nh = tq->hx.size();
+  if (na + nh == 0) return 0;
+  const size_t bytes = na * sizeof(IaTabJob) + nh * sizeof(HxTabJob);
+  if (bytes > ctx->tabjobs_cap) {
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_tabjobs); ctx->d_tabjobs = nullptr;
+    if (ctx->h_tabjobs) { cudaFreeHost(ctx->h_tabjobs); ctx->h_tabjobs = nullptr; }
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_tabjobs, bytes * 2));
+    CUDA_TRY(ctx, cudaMallocHost(&ctx->h_tabjobs, bytes * 2));
+    ctx->tabjobs_cap = bytes * 2;
+  } else {
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));           // the pinned staging buffer of the previous flush
+  }
+  char* h = static_cast<char*>(ctx->h_tabjobs);
+  if (na) memcpy(h, tq->ia.data(), na * sizeof(IaTabJob));
+  if (nh) memcpy(h + na * sizeof(IaTabJob), tq->hx.data(), nh * sizeof(HxTabJob));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_tabjobs, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  const char* d = static_cast<const char*>(ctx->d_tabjobs);
+  for (size_t j0 = 0; j0 < na; j0 += 65535) {
+    const size_t jc = std::min<size_t>(65535, na - j0);
+    int64_t mx = 0;
+    for (size_t j = j0; j < j0 + jc; j++) mx = std::max(mx, tq->ia[j].n * tq->ia[j].n);
+    const unsigned bx = (unsigned)std::max<int64_t>(1, std::min<int64_t>((mx + 255) / 256, 64));
+    iacov_table_batch_kernel<<<dim3(bx, (unsigned)jc), 256, 0, ctx->stream>>>(reinterpret_cast<const IaTabJob*>(d) + j0);
+    ctx->launches++;
+  }
+  for (size_t j0 = 0; j0 < nh; j0 += 65535) {
+    const size_t jc = std::min<size_t>(65535, nh - j0);
+    int64_t mx = 0;
+    for (size_t j = j0; j < j0 + jc; j++) mx = std::max(mx, tq->hx[j].n * tq->hx[j].n);
+    const unsigned bx = (unsigned)std::max<int64_t>(1, std::min<int64_t>((mx + 255) / 256, 256));
+    phix_table_batch_kernel<<<dim3(bx, (unsigned)jc), 256, 0, ctx->stream>>>(reinterpret_cast<const HxTabJob*>(d + na * sizeof(IaTabJob)) + j0);
+    ctx->launches++;
+  }
+  CUDA_TRY(ctx, cudaGetLastError());
+  tq->ia.clear(); tq->hx.clear();
+  return 0;
+}
+
 __global__ void phix_vec_kernel(HxPrm H, const double* __restrict__ D, int64_t m, double* __restrict__ out) {
   __shared__ double s_rt[4 * IAK_BK_NRT];
   const bool bessel = (H.modelx == 2 && H.half == 0);

@@ -122,6 +122,36 @@ def test_one_call_nll_equals_terms_plus_tail(ctx):
         assert st.value == 0 and nll.value == v and cxd.value == full["cxdhat"] and np.array_equal(beta, np.ravel(full["betahat"]))
 
 
+@pytest.mark.parametrize("kind,nonstat", [("edgeroi", False), ("matern0.8", False), ("matern0.5", True)])
+def test_native_callbacks_match_the_composed_path(ctx, kind, nonstat):
+    """iak3d_nll_vector / iak3d_gradnll_fd (transform, device terms, tail and differences inside the library) against the same
+    steps composed from Python: the value through readParsIAK3D + iak3d_nll_reml (the two exp() implementations differ by an
+    ulp in the transform: 1e-12), the gradient as differences of single iak3d_nll_vector evaluations (same bits: one transform,
+    batch == single)."""
+    ds = synth.make_dataset(700, 23)
+    P, modelx, types, cmeOpt = case_pars(kind, nonstat, 0.5)
+    sm = iak.setupIAK3D(ds["xData"], ds["dIData"], ctx=ctx)
+    kw = dict(modelx=modelx, nud=0.5, sdfdType_cd1=types[0], sdfdType_cxd0=types[1], sdfdType_cxd1=types[2], cmeOpt=cmeOpt, prodSum=True,
+              setupMats=sm, parBnds=PARBNDS, useReml=True)
+    from iak3d_b200 import api
+    lg = lambda k, b: float(api.logitab(P[k], *PARBNDS[b]))
+    pars = [lg("ax", "axBnds")] + ([lg("nux", "nuxBnds")] if modelx != "spherical" else []) + [lg("ad", "adBnds"), np.log(P["cx0"] - 1e-8),
+            np.log(P["cx1"] - 1e-8)] + ([np.log(P["cd1"] - 1e-8)] if types[0] != -9 else []) + [lg("cxd1", "sxd1Bnds")]
+    for k, t in zip(("sdfdPars_cd1", "sdfdPars_cxd0", "sdfdPars_cxd1"), types):
+        if t == -1:
+            pars += list(api.tauTfm(P[k], PARBNDS))
+    pars = np.array(pars + [np.log(P["cme"])]) + 0.01 * np.random.default_rng(3).standard_normal(len(pars) + 1)
+    npar = pars.size
+    v = iak.nllIAK3D(pars, ds["zData"], ds["XData"], **kw)
+    pb = iak.readParsIAK3D(pars, modelx, 0.5, *types, cmeOpt, True, PARBNDS)
+    v2 = iak.nllIAK3D(None, ds["zData"], ds["XData"], parsBTfmd=pb, **kw)
+    assert v < 1e90 and abs(v - v2) <= 1e-12 * abs(v2)
+    g, v0 = iak.gradnllIAK3D(pars, ds["zData"], ds["XData"], rtn_nll=True, analytic=False, **kw)
+    assert v0 == v
+    singles = np.array([iak.nllIAK3D(pars + 1e-6 * np.eye(npar)[k], ds["zData"], ds["XData"], **kw) for k in range(npar)])
+    assert np.array_equal(g, (singles - v) / 1e-6)
+
+
 def test_failures_map_to_badnll(ctx):
     ds = synth.make_dataset(300, 5)
     P, modelx, types, cmeOpt = case_pars("matern0.5", False, 0.5)
