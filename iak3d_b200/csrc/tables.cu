@@ -75,7 +75,11 @@ __global__ void phix_table_kernel(HxPrm H, const double* __restrict__ x1, int64_
   const int64_t total = n1 * n2;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = idx % n1, j = idx / n1;
-    if (symmetric && i < j) continue;            // x1 == x2: the lower triangle is mirrored (same arithmetic, same bits)
+    // x1 == x2 and an expensive model (Bessel-K): half the entries are computed and mirrored -- a strided store.  The cheap
+    // models compute both halves instead and keep every store coalesced: (x_i - x_j)^2 == (x_j - x_i)^2 exactly, so the two
+    // halves carry the same bits either way.
+    const bool mirror = symmetric && bessel;
+    if (mirror && i < j) continue;
     const double dx = x1[i] - x2[j], dy = x1[n1 + i] - x2[n2 + j];
     double D = 0.0;
     D = D + dx * dx;
@@ -84,7 +88,7 @@ __global__ void phix_table_kernel(HxPrm H, const double* __restrict__ x1, int64_
     if (out != nullptr) {
       const double v = iak_phix(D, &H, rt);
       out[idx] = v;
-      if (symmetric) out[i * n1 + j] = v;
+      if (mirror) out[i * n1 + j] = v;
     }
     if (zero != nullptr) zero[idx] = (D == 0.0) ? 1 : 0;
   }
@@ -166,7 +170,7 @@ __global__ void phix_table_batch_kernel(const HxTabJob* __restrict__ jobs) {
   const double* __restrict__ x = jb.x;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = idx % n1, j = idx / n1;
-    if (i < j) continue;                          // the lower triangle is mirrored (same arithmetic, same bits)
+    if (bessel && i < j) continue;                // expensive model: mirrored half (see phix_table_kernel)
     const double dx = x[i] - x[j], dy = x[n1 + i] - x[n1 + j];
     double D = 0.0;
     D = D + dx * dx;
@@ -174,7 +178,7 @@ __global__ void phix_table_batch_kernel(const HxTabJob* __restrict__ jobs) {
     D = sqrt(D);
     const double v = iak_phix(D, &H, rt);
     jb.out[idx] = v;
-    jb.out[i * n1 + j] = v;
+    if (bessel) jb.out[i * n1 + j] = v;
   }
 }
 
