@@ -100,3 +100,35 @@ def test_unit_plan_balances_and_covers():
             assert len(units) == npairs and all(u["kind"] == "pair" for u in units)
         if optn == 4:
             assert len(units) == 12 and all(u["weight"] == 1.0 for u in units)
+
+
+def _peer_worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    from iak3d_b200 import parallel
+    parallel.init(backend="gloo")
+    comm = parallel.BlockComm()
+    first = comm.attach_peer(None)                      # no device context on this machine: every rank must agree on "no"
+    second = comm.attach_peer(None)                     # and the answer is remembered (the call is collective only once)
+    s = comm.allreduce_sum(np.array([1.0 + rank, 10.0]))
+    q.put((rank, first, second, comm.device_buffer(8) is None, list(s)))
+    comm.barrier()
+    import torch.distributed as dist
+    dist.destroy_process_group()
+
+
+def test_peer_exchange_declines_without_device_contexts():
+    """The peer-memory exchange is negotiated collectively; ranks without a CUDA context (this CPU box, or a rank that owns
+    no unit) make every rank fall back to the process group's all-reduce."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in res:
+        assert r[1] is False and r[2] is False and r[3] is True and r[4] == [3.0, 20.0]
