@@ -13,9 +13,21 @@ __global__ void iacov_table_kernel(IaPrm P, const double* __restrict__ dI1, int6
                                    const double* __restrict__ dI2, int64_t n2, double* __restrict__ out,
                                    double* __restrict__ avvar1) {
   const int64_t total = n1 * n2;
+  // one set against itself: the reference evaluates the pairs (i <= j) only, first interval = the one with the smaller index,
+  // and fills both triangles with that value (iaCovMatern.R:60-70, 99-100).  Same here: half the exp() work, and the table is
+  // symmetric to the bit also where two intervals share their upper limit (the only case in which the argument order matters).
+  const bool sym = (dI1 == dI2 && n1 == n2);
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = idx % n1, j = idx / n1;
-    out[idx] = iak_avcov(dI1[i], dI1[n1 + i], dI2[j], dI2[n2 + j], &P);
+    if (sym) {
+      if (i >= j) {
+        const double v = iak_avcov(dI1[j], dI1[n1 + j], dI1[i], dI1[n1 + i], &P);
+        out[idx] = v;
+        out[j + i * n1] = v;
+      }
+    } else {
+      out[idx] = iak_avcov(dI1[i], dI1[n1 + i], dI2[j], dI2[n2 + j], &P);
+    }
     if (avvar1 != nullptr && j == 0) avvar1[i] = iak_avvar(dI1[i], dI1[n1 + i], &P);
   }
 }
@@ -151,7 +163,11 @@ __global__ void iacov_table_batch_kernel(const IaTabJob* __restrict__ jobs) {
   const double* __restrict__ dI = jb.dI;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = idx % n1, j = idx / n1;
-    jb.out[idx] = iak_avcov(dI[i], dI[n1 + i], dI[j], dI[n1 + j], &jb.P);
+    if (i >= j) {                                  // pairs (j <= i), first interval = the smaller index; mirrored (see iacov_table_kernel)
+      const double v = iak_avcov(dI[j], dI[n1 + j], dI[i], dI[n1 + i], &jb.P);
+      jb.out[idx] = v;
+      jb.out[j + i * n1] = v;
+    }
     if (jb.av != nullptr && j == 0) jb.av[i] = iak_avvar(dI[i], dI[n1 + i], &jb.P);
   }
 }
