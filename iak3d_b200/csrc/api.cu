@@ -465,15 +465,19 @@ int iak_get_slot(iak3d_ds* ds, size_t k, Slot** out) {
 // `cache` (optional) de-duplicates tables inside one batch: the npar+1 evaluations of a forward-difference gradient
 // differ in one parameter each, so all but one share the horizontal table and all but one the depth tables.
 struct TableCache {
-  struct Entry { const iak3d_ds* ds; int kind; double k[6]; const double* ptr; const double* av; };
-  std::vector<Entry> e;
+  // per dataset: a composite-likelihood batch holds hundreds of datasets (times npar + 1 parameter sets), and one flat list
+  // made every look-up a walk over all of them
+  struct Entry { int kind; double k[6]; const double* ptr; const double* av; };
+  std::unordered_map<const iak3d_ds*, std::vector<Entry>> e;
   const double* find(const iak3d_ds* ds, int kind, const double* k, const double** av = nullptr) const {
-    for (const Entry& x : e)
-      if (x.ds == ds && x.kind == kind && memcmp(x.k, k, sizeof(x.k)) == 0) { if (av) *av = x.av; return x.ptr; }
+    const auto it = e.find(ds);
+    if (it == e.end()) return nullptr;
+    for (const Entry& x : it->second)
+      if (x.kind == kind && memcmp(x.k, k, sizeof(x.k)) == 0) { if (av) *av = x.av; return x.ptr; }
     return nullptr;
   }
   void add(const iak3d_ds* ds, int kind, const double* k, const double* ptr, const double* av = nullptr) {
-    Entry x; x.ds = ds; x.kind = kind; memcpy(x.k, k, sizeof(x.k)); x.ptr = ptr; x.av = av; e.push_back(x);
+    Entry x; x.kind = kind; memcpy(x.k, k, sizeof(x.k)); x.ptr = ptr; x.av = av; e[ds].push_back(x);
   }
 };
 
@@ -1075,15 +1079,18 @@ extern "C" int iak3d_nll_terms_batch_enqueue(iak3d_ctx* ctx, int32_t count, iak3
   CUDA_TRY(ctx, cudaEventRecord(ctx->evs[1], ctx->stream));
   std::vector<FactorBuildJob> jobs;
   jobs.reserve((size_t)count);
+  std::unordered_map<const iak3d_ds*, std::vector<int>> seen;
   for (int i = 0; i < count; i++) {
     if (!live[i]) continue;
     Slot* s = b->slots[i];
     if (cov_one_table(cargs[i])) {           // the expansion depends on (dataset, table) only: share it inside the batch
-      for (int k = 0; k < i; k++)
-        if (live[k] && dss[k] == dss[i] && cov_one_table(cargs[k]) && cargs[k].T[0] == cargs[i].T[0]) {
+      std::vector<int>& prev = seen[dss[i]];   // earlier problems of the same dataset (not a walk over the whole batch)
+      for (int k : prev)
+        if (cov_one_table(cargs[k]) && cargs[k].T[0] == cargs[i].T[0]) {
           cargs[i].E_shared = cargs[k].E_shared ? cargs[k].E_shared : cargs[k].Ebuf;
           break;
         }
+      prev.push_back(i);
     }
     if (dss[i]->lncol >= 0 && dss[i]->lncol < q) {
       // lognormal data: column lncol of W is sigma2Vec - diag(C) of THIS evaluation (nrUpdatesIAK3DlnN.R:15, 194)
