@@ -298,22 +298,25 @@ __device__ void potf2_inv_blk4(double* __restrict__ At, int off, double* __restr
   }
 }
 
-// ---- diagonal block, warp-specialised (single-problem launches) ---------------------------------------------------------
+// ---- diagonal block, warp-specialised (every factorisation launch of the full-size CTA) ---------------------------------
 // The per-column critical path of a single evaluation is this routine (23 of the 35 us between two diagonal blocks at
-// n = 1200 ... 5000 with round 1's look-ahead variant), and there most cycles were not the pivot chain but what surrounded it: two
-// block-wide barriers and three shared-memory round trips per four columns, and -- in every warp -- the panel, inverse-row
-// and trailing-update branches executed one after the other (divergence).  Here the chain is ONE warp running ONE
-// instruction stream:
-//   chain warp (warp 0): lane l owns rows l and l + 32 of the current four-column panel.  Per step: every lane factorises
-//     the 4 x 4 diagonal block redundantly (no broadcast), substitutes its own two panel rows, publishes them (final L, and
-//     transposed for the helpers), then applies this step's rank-4 update to the NEXT panel itself -- whose earlier updates
-//     the helpers deposited a step ago -- and to the next diagonal block (again redundantly in every lane).
-//   helper warps (1..7): thread <-> one 4 x 4 block (br, bc <= br) held in registers: the trailing block T(br, bc) until its
-//     column is handed to the chain warp (deposit, two steps ahead of the chain), the block Y(br, bc) of the inverse
-//     afterwards.  Both updates are the same instruction stream,  u -= P_br * Q,  Q = P_bc' or the finished row block of the
-//     inverse, selected by a pointer.
-// The chain never waits for a helper that is not at least a step ahead: arrive / sync pairs on named barriers (ids 3..6,
-// alternating by step parity), one helper-only barrier (7) between the inverse row and its use.
+// n = 1200 ... 5000 with round 1's look-ahead variant), and there most cycles were not the pivot chain but what surrounded it:
+// two block-wide barriers and three shared-memory round trips per four columns, and -- in every warp -- the panel,
+// inverse-row and trailing-update branches executed one after the other (divergence).  Here:
+//   two CHAIN warps (0, 1): thread t owns row t of the current four-column panel.  Per step every lane factorises the 4 x 4
+//     diagonal block for itself (no broadcast), substitutes its own row (rows of the diagonal block take the same path: the
+//     entries right of the diagonal are replaced by zeros with selects, never with branches), publishes it transposed for
+//     the helpers, then applies this step's rank-4 update to the NEXT panel column itself -- whose earlier updates the helpers
+//     deposited a step ago -- and to the next diagonal block (again in every lane).  The first warp's rows are finished after
+//     step 7: it retires and only keeps the barrier counts.
+//   HELPER warps (2, 3, 6, 7 and 4): thread <-> one 4 x 4 block (br, bc <= br) held in registers: the trailing block T(br, bc)
+//     until its column is handed to the chain warps, the block Y(br, bc) of the inverse afterwards.  One update per step and
+//     thread, one instruction stream:  u -= P_br * Q,  Q = P_bc' of this step (trailing block) or the finished row block of
+//     the inverse of the PREVIOUS step (the lag removes a helper-only barrier).  The long-lived blocks sit on the two
+//     schedulers the chain warps do not use.  Warp 5 copies each finished panel into the tile.
+// Hand-overs are bar.arrive / bar.sync pairs on named barriers (ids 3..6 alternating by step parity, 8 between the two chain
+// warps); the per-step buffers cycle over three steps.  Measured alternatives and what each part costs: DESIGN.md section 4,
+// profiles/potf2_variants_r02.txt (scripts/micro/potf2_bench.cu).
 constexpr int CH_LR = 0;                  // l10 l20 l30 l21 l31 l32 | r0..r3   (16 reserved)
 constexpr int CH_PT = 16;                 // this step's panel, transposed: [4][64] (conflict-free for the helpers' block loads)
 constexpr int CH_YR = 16 + 256;           // finished row block of the inverse: [4][64]
