@@ -131,7 +131,7 @@ def run_s5(args, rank, local_rank, world, comm):
     import ctypes as C
     import iak3d_b200 as iak
     from iak3d_b200 import api, synth
-    from iak3d_b200._lib import Pars, make_pars, dptr, iptr
+    from iak3d_b200._lib import Pars, make_model, make_pars, dptr, iptr
 
     n = args.n
     ds, pars, modelx, types, cmeOpt = s5_inputs(n)
@@ -144,23 +144,29 @@ def run_s5(args, rank, local_rank, world, comm):
     dsarr = (C.c_void_p * nb)(*[sm.h] * nb)
     lnd = np.empty(nb); G = np.empty((nb, q * q)); st = np.empty(nb, np.int32)
 
+    model = make_model(modelx, 0.5, *types, cmeOpt, True, PARBNDS)
+
     def structs(step_no):
+        # the unconstrained vectors of one gradient batch -> parsBTfmd structs, by the library's readParsIAK3D (iak3d_read_pars)
         arr = (Pars * nb)()
         for i, v in enumerate(fd_candidates(pars, step_no)):
-            pb = api.readParsIAK3D(v, modelx, 0.5, *types, cmeOpt, True, PARBNDS)
-            arr[i] = make_pars(pb, modelx, *types, cmeOpt)
+            vv = np.ascontiguousarray(v, dtype=np.float64)
+            ctx.check(lib.iak3d_read_pars(C.byref(model), dptr(vv), vv.size, C.byref(arr[i])))
         return arr
 
     def step_resident(step_no):
         ctx.check(lib.iak3d_nll_terms_batch_enqueue(ctx.h, nb, dsarr, structs(step_no)))
         ctx.check(lib.iak3d_nll_terms_batch_fetch(ctx.h, dptr(lnd), dptr(G), iptr(st)))
 
+    kw_e2e = dict(modelx=modelx, nud=0.5, sdfdType_cd1=types[0], sdfdType_cxd0=types[1], sdfdType_cxd1=types[2], cmeOpt=cmeOpt, prodSum=True,
+                  setupMats=sm, parBnds=PARBNDS, useReml=True)
+
     def step_e2e(step_no):
-        """the reference-facing call: host W in, nll values out"""
+        """the reference-facing call: host W in (uploaded every step), the forward-difference gradient and the value out --
+        gradnllIAK3D as optim() calls it (npar + 1 = 9 evaluations in one batched launch; iak3d_gradnll_fd)"""
         sm.upload_W(W)
-        lnd_, G_, st_ = api.nll_terms_batch(ctx, [sm] * nb, list(structs(step_no)))
-        Gt = np.transpose(G_, (0, 2, 1))
-        return list(api.reml_tail_batch(np.triu(Gt) + np.transpose(np.triu(Gt, 1), (0, 2, 1)), lnd_, n, p, True))
+        g, v0 = api.gradnllIAK3D(fd_candidates(pars, step_no)[0], ds["zData"], ds["XData"], analytic=False, rtn_nll=True, **kw_e2e)
+        return [v0] + list(g)
 
     peaks = dict(dfma=ctx.fp64_peak(0), dmma=ctx.fp64_peak(1), dfma_and_dmma_together=ctx.fp64_peak(2))
     # a write-only stream (cudaMemsetAsync, 16 x 256 MiB): the ceiling of a kernel that only writes, as the covariance build does
