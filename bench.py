@@ -131,7 +131,7 @@ def run_s5(args, rank, local_rank, world, comm):
     import ctypes as C
     import iak3d_b200 as iak
     from iak3d_b200 import api, synth
-    from iak3d_b200._lib import Pars, make_model, make_pars, dptr, iptr
+    from iak3d_b200._lib import Pars, make_model, dptr, iptr
 
     n = args.n
     ds, pars, modelx, types, cmeOpt = s5_inputs(n)

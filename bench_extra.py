@@ -14,7 +14,7 @@ import time
 
 import numpy as np
 
-from bench import PARBNDS, ClockSampler, measured_peak
+from bench import PARBNDS, ClockSampler
 
 
 def _cl(args, rank, local_rank, world, comm):

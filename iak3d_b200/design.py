@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import OK, dptr, f64
+from ._lib import dptr, f64
 
 
 def mlr_names(modelX, covNames, covLevels):
